@@ -1,0 +1,173 @@
+/*
+ * dbsgym.h -- C ABI of the B200-native DBS-Gym environment-step engine.
+ *
+ * The reference (NevVerVer/DBS-Gym) is pure Python: it has no FFI of its own.  The
+ * boundary this library replaces is the body of the reference's gymnasium env
+ * (paths relative to the reference checkout):
+ *
+ *   environment/env.py:415-454   SpatialKuramoto.step   -> dbsgym_step / dbsgym_step_host
+ *   environment/env.py:605-612   transient part of reset -> dbsgym_transient
+ *   environment/env.py:252-271   KuramotoJAX.dynamics / forward (diffrax Dopri5 +
+ *                                PIDController(rtol=atol=1e-5), SaveAt(ts))      -> the step kernel
+ *   environment/env.py:396-412   calc_naive_lfp / calc_distance_lfp             -> fused in the step kernel
+ *   environment/env.py:447-452, :638-688, utils.py:21-27, :794-816
+ *                                window slide, rewards R1/R2/R3                 -> the observation kernel
+ *
+ * Conventions
+ *   - plain C types only; every call returns 0 on success or a negative DBSGYM_E* code and
+ *     never throws; dbsgym_last_error() gives the text of the last failure.
+ *   - "host" pointers are ordinary CPU memory (pinned memory makes the copies faster);
+ *     "device" pointers are CUDA device memory owned by the caller (e.g. a torch tensor's
+ *     data_ptr()) and must stay alive until the stream work that uses them has finished.
+ *   - per-oscillator parameter vectors always cross the boundary as float64, whatever the
+ *     compute precision of the handle.
+ *   - a handle is bound to one GPU and is not thread-safe; use one handle per GPU.
+ *   - stream arguments are cudaStream_t values passed as void* (NULL = the handle's own stream).
+ */
+#ifndef DBSGYM_H_
+#define DBSGYM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBSGYM_ABI_VERSION 1
+
+typedef struct DbsGymHandle DbsGymHandle;
+
+enum { DBSGYM_OK = 0, DBSGYM_EINVAL = -1, DBSGYM_ECUDA = -2, DBSGYM_ENOMEM = -3,
+       DBSGYM_ESTATE = -4, DBSGYM_ESOLVER = -5 };
+
+enum { DBSGYM_F32 = 0, DBSGYM_F64 = 1 };                 /* compute precision */
+enum { DBSGYM_COUPLING_GRID = 0,                         /* alpha_ij = f(|dz|,|dx|,|dy|) on a regular grid */
+       DBSGYM_COUPLING_DENSE = 1 };                      /* arbitrary symmetric alpha[N][N]            */
+enum { DBSGYM_REWARD_BBPOW = 0,                          /* env.py:638-650  */
+       DBSGYM_REWARD_TEMP_CONST = 1,                     /* env.py:653-666  */
+       DBSGYM_REWARD_BBPOW_THRESH = 2 };                 /* env.py:669-688  */
+
+typedef struct DbsGymConfig {
+    uint32_t struct_bytes;      /* sizeof(DbsGymConfig), checked                                  */
+    int32_t  device;            /* CUDA ordinal                                                   */
+    int32_t  n_envs;            /* B: environments owned by this handle                           */
+    int32_t  n_osc;             /* N: oscillators per environment (params_dict['num_oscillators']) */
+    int32_t  grid[3];           /* gx, gy, gz of utils.py:478-497 (row i = z*gx*gy + x*gy + y)    */
+    int32_t  window;            /* W: observe_wind_idxs, env.py:296-297 (2340)                    */
+    int32_t  precision;         /* DBSGYM_F32 | DBSGYM_F64                                        */
+    int32_t  coupling;          /* DBSGYM_COUPLING_*                                              */
+    int32_t  max_step_samples;  /* >= nI + nII - 1 of any step (env.py:444)                       */
+    int32_t  max_steps;         /* diffrax max_steps per solve (4096)                             */
+    double   K;                 /* params_dict['K']; the kernel applies K / N (env.py:264)        */
+    double   rtol, atol, dt0;   /* env.py:249, :267                                               */
+    double   safety, factor_min, factor_max;   /* diffrax PIDController defaults .9 / .2 / 10     */
+    double   action_lo, action_hi;             /* dbs_action_bounds, env.py:389-393               */
+} DbsGymConfig;
+
+typedef struct DbsGymRewardSpec {
+    uint32_t struct_bytes;
+    int32_t  kind;              /* DBSGYM_REWARD_*                                                */
+    int32_t  bin_lo, bin_hi;    /* rfft bins k with beta_a < k/(W*dt) < beta_b, inclusive range   */
+    double   power_scale;       /* 1e4 (R1, R3)                                                   */
+    double   action_cost;       /* 1e-2 (R1, R2), 1 (R3)                                          */
+    double   threshold;         /* 20 (R3)                                                        */
+    double   threshold_penalty; /* 5 (R3)                                                         */
+    double   temp_scale;        /* 1e3 (R2)                                                       */
+} DbsGymRewardSpec;
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int  dbsgym_abi_version(void);
+int  dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out);
+void dbsgym_destroy(DbsGymHandle* h);
+/* text of the last error on this handle (h == NULL: last error of a failed create) */
+const char* dbsgym_last_error(const DbsGymHandle* h);
+
+/* ---- model set-up (host pointers, float64) ---------------------------------------------
+ * GRID: table[(dz*gx + dx)*gy + dy] = alpha between two neurons whose grid offsets are
+ *       (dx,dy,dz) -- i.e. cos(distance) or the wavelet kernel of env.py:219-229.
+ * DENSE: alpha[i*N + j], must be symmetric.  Shared by every environment of the handle. */
+int dbsgym_set_coupling_grid(DbsGymHandle* h, const double* table);
+int dbsgym_set_coupling_dense(DbsGymHandle* h, const double* alpha);
+
+/* Per-environment vectors uploaded at reset (env.py:566-598): natural frequencies after
+ * remove_negative_w0, stimulation conductance of the first contact (env.py:422-423), summed
+ * recording conductance (env.py:410-411; NULL = 'naive' recording kernel) and the unwrapped
+ * initial phases.  Arrays are [n][N]; env_ids == NULL means environments 0..n-1; any vector
+ * pointer may be NULL to leave that quantity untouched. */
+int dbsgym_set_env_params(DbsGymHandle* h, const int32_t* env_ids, int32_t n,
+                          const double* w0, const double* stim_cond,
+                          const double* rec_cond, const double* y0);
+/* recording kernel: 0 = naive (observation = mean cos), 1 = conductance weighted */
+int dbsgym_set_recording(DbsGymHandle* h, int32_t weighted);
+
+/* The np.arange time grids of env.py:426-437 for step index 0..n_steps-1, computed on the
+ * host with numpy itself (they depend on float64 rounding).
+ * offs_I[k*max_I + j] = t_eval_step_I[j] - t_eval_step_I[0]; same for II. */
+int dbsgym_set_schedule(DbsGymHandle* h, int32_t n_steps,
+                        const int32_t* n_I, const int32_t* n_II,
+                        const double* offs_I, int32_t max_I,
+                        const double* offs_II, int32_t max_II);
+
+/* reward definition; lin_functional (float64 [W], chronological order) is the vector g with
+ * x_filt[-1] - mean(x_filt) == g . window for the filtfilt band-pass of utils.py:794-816
+ * (needed for DBSGYM_REWARD_TEMP_CONST only, else NULL). */
+int dbsgym_set_reward(DbsGymHandle* h, const DbsGymRewardSpec* spec, const double* lin_functional);
+
+/* step counter and episode length (env.py:299-300, :450-451) of the listed environments */
+int dbsgym_set_episode(DbsGymHandle* h, const int32_t* env_ids, int32_t n,
+                       const int32_t* step_idx, const int32_t* episode_len);
+
+/* ---- the hot path ----------------------------------------------------------------------
+ * dbsgym_transient: env.py:605-612.  Integrates the listed environments from their current
+ * phases over ts_offsets[0..n_ts-1] (one diffrax solve), fills the observation window with
+ * the last W recorded LFP samples of ts[0..n_ts-2], leaves the phases at ts[n_ts-1], and
+ * writes the reset observation obs[b*W .. ] (device float32, may be NULL).  env_ids is a host
+ * pointer (NULL = all). Asynchronous on `stream`. */
+int dbsgym_transient(DbsGymHandle* h, const int32_t* env_ids, int32_t n,
+                     const double* ts_offsets, int32_t n_ts, float* obs_dev, void* stream);
+
+/* dbsgym_step: env.py:415-454 for every environment of the handle.
+ *   actions_dev  [B]     float32 in [-1, 1] (policy output, env.py:419)
+ *   obs_dev      [B][W]  float32 observation window after the step
+ *   reward_dev   [B]     float32 reward  (float64 copy: dbsgym_get_rewards)
+ *   done_dev     [B]     uint8   current_step >= total_episode_counts
+ * Asynchronous on `stream`; any output pointer may be NULL. */
+int dbsgym_step(DbsGymHandle* h, const float* actions_dev, float* obs_dev,
+                float* reward_dev, uint8_t* done_dev, void* stream);
+
+/* Same with HOST buffers: copies actions in, runs the step, copies obs / reward / done out
+ * and synchronises.  This is the call a gym VecEnv makes. */
+int dbsgym_step_host(DbsGymHandle* h, const float* actions, float* obs,
+                     float* reward, uint8_t* done);
+/* reset observation (window as float32) of all environments to a host buffer [B][W] */
+int dbsgym_get_obs_host(DbsGymHandle* h, float* obs);
+
+/* ---- introspection (host buffers, synchronising) -------------------------------------- */
+/* LFP samples of the last step: lfp_true = theta_mean (env.py:444), lfp_rec = theta_records
+ * (env.py:445), each [B][max_step_samples] float64; n_samples [B]. Any may be NULL. */
+int dbsgym_get_lfp(DbsGymHandle* h, double* lfp_true, double* lfp_rec, int32_t* n_samples);
+int dbsgym_get_rewards(DbsGymHandle* h, double* reward, double* u);
+/* unwrapped phases, float64 [n][N] */
+int dbsgym_get_state(DbsGymHandle* h, const int32_t* env_ids, int32_t n, double* y);
+/* observation window in chronological order, float64 [n][W] */
+int dbsgym_get_window(DbsGymHandle* h, const int32_t* env_ids, int32_t n, double* window);
+int dbsgym_set_window(DbsGymHandle* h, const int32_t* env_ids, int32_t n, const double* window);
+int dbsgym_get_episode(DbsGymHandle* h, int32_t* step_idx, uint8_t* done);
+/* totals since create (or the last call with reset != 0): accepted RK steps, rejected RK
+ * steps, RHS evaluations, summed over environments; and the device status word (0 = ok). */
+int dbsgym_counters(DbsGymHandle* h, uint64_t* accepted, uint64_t* rejected,
+                    uint64_t* rhs_evals, int32_t* status, int32_t reset);
+/* elapsed device time (ms) of the kernels of the most recent dbsgym_step*, measured with
+ * CUDA events on the launching stream: [0] step kernel, [1] observation kernel */
+int dbsgym_last_step_ms(DbsGymHandle* h, float* ms2);
+/* enable / disable the per-kernel event timing above (off by default) */
+int dbsgym_set_timing(DbsGymHandle* h, int32_t enabled);
+
+/* FP32-FMA throughput micro-benchmark used for the roofline denominator: runs a dependent-
+ * chain FFMA kernel on `device` for about `ms_target` ms; returns TFLOP/s in *tflops. */
+int dbsgym_measure_fp32_peak(int32_t device, double ms_target, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBSGYM_H_ */
