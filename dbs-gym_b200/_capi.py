@@ -1,0 +1,145 @@
+"""ctypes binding of ``include/dbsgym.h`` (the C-ABI of the CUDA step engine).
+
+The library is built in-tree by :func:`build` (``nvcc -gencode arch=compute_100a,code=sm_100a``)
+into ``csrc/libdbsgym.so``.  There is no CPU fallback: if the library is missing or no
+CUDA device is present every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "libdbsgym.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "dbsgym.h")
+
+F32, F64 = 0, 1
+COUPLING_GRID, COUPLING_DENSE = 0, 1
+REWARD_BBPOW, REWARD_TEMP_CONST, REWARD_BBPOW_THRESH = 0, 1, 2
+
+EXPORTS = [
+    "dbsgym_abi_version", "dbsgym_create", "dbsgym_destroy", "dbsgym_last_error",
+    "dbsgym_set_coupling_grid", "dbsgym_set_coupling_dense", "dbsgym_set_env_params",
+    "dbsgym_set_recording", "dbsgym_set_schedule", "dbsgym_set_reward", "dbsgym_set_episode",
+    "dbsgym_transient", "dbsgym_step", "dbsgym_step_host", "dbsgym_get_obs_host",
+    "dbsgym_get_lfp", "dbsgym_get_rewards", "dbsgym_get_state", "dbsgym_get_window",
+    "dbsgym_set_window", "dbsgym_get_episode", "dbsgym_counters", "dbsgym_last_step_ms",
+    "dbsgym_set_timing", "dbsgym_measure_fp32_peak",
+]
+
+
+class DbsGymConfig(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_uint32), ("device", C.c_int32), ("n_envs", C.c_int32),
+        ("n_osc", C.c_int32), ("grid", C.c_int32 * 3), ("window", C.c_int32),
+        ("precision", C.c_int32), ("coupling", C.c_int32), ("max_step_samples", C.c_int32),
+        ("max_steps", C.c_int32), ("K", C.c_double), ("rtol", C.c_double), ("atol", C.c_double),
+        ("dt0", C.c_double), ("safety", C.c_double), ("factor_min", C.c_double),
+        ("factor_max", C.c_double), ("action_lo", C.c_double), ("action_hi", C.c_double),
+    ]
+
+
+class DbsGymRewardSpec(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_uint32), ("kind", C.c_int32), ("bin_lo", C.c_int32),
+        ("bin_hi", C.c_int32), ("power_scale", C.c_double), ("action_cost", C.c_double),
+        ("threshold", C.c_double), ("threshold_penalty", C.c_double), ("temp_scale", C.c_double),
+    ]
+
+
+class DbsGymError(RuntimeError):
+    pass
+
+
+def sources():
+    return [os.path.join(CSRC, f) for f in ("api.cu", "step_kernel.cuh", "obs_kernel.cuh")] + [HEADER]
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile ``csrc/api.cu`` for sm_100a into ``csrc/libdbsgym.so`` (cross-compiles without a GPU)."""
+    if not force and os.path.exists(LIB_PATH):
+        newest = max(os.path.getmtime(s) for s in sources())
+        if os.path.getmtime(LIB_PATH) >= newest:
+            return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise DbsGymError("nvcc not found: cannot build libdbsgym.so")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH + ".tmp", os.path.join(CSRC, "api.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise DbsGymError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library and declare every prototype of ``include/dbsgym.h``."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DbsGymError(f"{LIB_PATH} is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32p, f32p, f64p, u8p, u64p = (C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_float),
+                                       C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_uint64))
+    P = {
+        "dbsgym_abi_version": (C.c_int, []),
+        "dbsgym_create": (C.c_int, [C.POINTER(DbsGymConfig), C.POINTER(vp)]),
+        "dbsgym_destroy": (None, [vp]),
+        "dbsgym_last_error": (C.c_char_p, [vp]),
+        "dbsgym_set_coupling_grid": (C.c_int, [vp, vp]),
+        "dbsgym_set_coupling_dense": (C.c_int, [vp, vp]),
+        "dbsgym_set_env_params": (C.c_int, [vp, vp, C.c_int32, vp, vp, vp, vp]),
+        "dbsgym_set_recording": (C.c_int, [vp, C.c_int32]),
+        "dbsgym_set_schedule": (C.c_int, [vp, C.c_int32, vp, vp, vp, C.c_int32, vp, C.c_int32]),
+        "dbsgym_set_reward": (C.c_int, [vp, C.POINTER(DbsGymRewardSpec), vp]),
+        "dbsgym_set_episode": (C.c_int, [vp, vp, C.c_int32, vp, vp]),
+        "dbsgym_transient": (C.c_int, [vp, vp, C.c_int32, vp, C.c_int32, vp, vp]),
+        "dbsgym_step": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+        "dbsgym_step_host": (C.c_int, [vp, vp, vp, vp, vp]),
+        "dbsgym_get_obs_host": (C.c_int, [vp, vp]),
+        "dbsgym_get_lfp": (C.c_int, [vp, vp, vp, vp]),
+        "dbsgym_get_rewards": (C.c_int, [vp, vp, vp]),
+        "dbsgym_get_state": (C.c_int, [vp, vp, C.c_int32, vp]),
+        "dbsgym_get_window": (C.c_int, [vp, vp, C.c_int32, vp]),
+        "dbsgym_set_window": (C.c_int, [vp, vp, C.c_int32, vp]),
+        "dbsgym_get_episode": (C.c_int, [vp, vp, vp]),
+        "dbsgym_counters": (C.c_int, [vp, u64p, u64p, u64p, i32p, C.c_int32]),
+        "dbsgym_last_step_ms": (C.c_int, [vp, f32p]),
+        "dbsgym_set_timing": (C.c_int, [vp, C.c_int32]),
+        "dbsgym_measure_fp32_peak": (C.c_int, [C.c_int32, C.c_double, f64p]),
+    }
+    assert sorted(P) == sorted(EXPORTS)
+    for name, (res, args) in P.items():
+        fn = getattr(lib, name)        # AttributeError if the symbol is not exported
+        fn.restype, fn.argtypes = res, args
+    if lib.dbsgym_abi_version() != 1:
+        raise DbsGymError("libdbsgym.so ABI version mismatch; rebuild")
+    _lib = lib
+    return lib
+
+
+def ptr(a):
+    """void* of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def check(lib, handle, rc):
+    if rc != 0:
+        msg = lib.dbsgym_last_error(handle)
+        raise DbsGymError(f"dbsgym error {rc}: {msg.decode() if msg else '?'}")

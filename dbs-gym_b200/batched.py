@@ -1,0 +1,150 @@
+"""A batch of reference-semantics environments on one GPU.
+
+``BatchedKuramoto`` = B x (host bookkeeping of reference environment/env.py, see host_env.py)
++ one :class:`KuramotoEngine` that integrates all B environments per call.  It behaves like a
+sequential ``DummyVecEnv`` of reference envs built from the same ``params_dict`` list: same
+construction / reset order, same global-``np.random`` stream, same schedule, same outputs.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import KuramotoEngine
+from .geometry import coupling_rows, coupling_table
+from .host_env import HostEnvState
+from .schedule import StepSchedule, transient_grid
+
+_SHARED_KEYS = ("num_oscillators", "grid_size", "K", "spatial_kernel", "wavelet_amp", "wavelet_steepness",
+                "electrode_width", "electrode_pause", "verbose_dt", "observe_wind_counts",
+                "transient_state_len", "dbs_action_bounds", "reward_func", "recording_kernel")
+
+
+def _pinned(shape, dtype):
+    """Page-locked host buffer (through torch) when a GPU is present, plain numpy otherwise."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            tdt = {np.float32: torch.float32, np.uint8: torch.uint8, np.float64: torch.float64}[dtype]
+            t = torch.empty(shape, dtype=tdt, pin_memory=True)
+            return t.numpy(), t          # caller keeps `t` alive: the numpy view borrows its memory
+    except Exception:                                                    # noqa: BLE001
+        pass
+    return np.empty(shape, dtype=dtype), None
+
+
+class BatchedKuramoto:
+    def __init__(self, params_dicts, *, precision="f32", device=0, compat_env2=False, force_dense=False,
+                 save_init=False):
+        if isinstance(params_dicts, dict):
+            params_dicts = [params_dicts]
+        self.params_dicts = list(params_dicts)
+        self.num_envs = B = len(self.params_dicts)
+        p0 = self.params_dicts[0]
+        for k in _SHARED_KEYS:
+            for d in self.params_dicts[1:]:
+                if not _same(d[k], p0[k]):
+                    raise ValueError(f"params_dict['{k}'] must be identical for all environments of one batch")
+        self.precision = precision
+        # --- host state, in index order: construct (seeds the global RNG) then first reset draws ---
+        self.hosts, setups = [], []
+        for d in self.params_dicts:
+            h = HostEnvState(d, save_init=save_init, compat_env2=compat_env2)
+            self.hosts.append(h)
+            setups.append(h.begin_episode())
+        h0 = self.hosts[0]
+        self.n_osc = int(p0["num_oscillators"])
+        self.window = h0.observe_wind_idxs
+        self.t_transient = transient_grid(h0.transient_state_len, p0["verbose_dt"])
+        max_len = max(h.total_episode_counts for h in self.hosts)
+        self.schedule = StepSchedule(max_len + 1, self.t_transient[-1], p0["electrode_width"],
+                                     p0["electrode_pause"], p0["verbose_dt"])
+        # --- coupling operator (shared by every env: it depends only on the neuron grid) ---
+        table = None if force_dense else coupling_table(p0["neur_coords"], p0["neur_grid"], p0["grid_size"],
+                                                        p0["spatial_kernel"], p0["wavelet_amp"],
+                                                        p0["wavelet_steepness"])
+        alpha = None
+        if table is None:
+            alpha = coupling_rows(p0["neur_coords"], np.arange(self.n_osc), p0["spatial_kernel"],
+                                  p0["wavelet_amp"], p0["wavelet_steepness"])
+        self.engine = KuramotoEngine(B, self.n_osc, p0["grid_size"], self.window, p0["K"],
+                                     precision=precision, coupling_table=table, alpha=alpha, device=device,
+                                     max_step_samples=max(self.schedule.max_samples, 20),
+                                     action_bounds=p0["dbs_action_bounds"])
+        self.engine.set_recording(p0["recording_kernel"] == "gaussian")
+        self.engine.set_schedule(self.schedule)
+        self.engine.set_reward(p0["reward_func"], p0["verbose_dt"])
+        self.electrodes = [None] * B
+        self.w0_model = [None] * B
+        self._pin = []
+        self.obs_buf, t = _pinned((B, self.window), np.float32); self._pin.append(t)
+        self.rew_buf, t = _pinned((B,), np.float32); self._pin.append(t)
+        self.done_buf, t = _pinned((B,), np.uint8); self._pin.append(t)
+        self.act_buf, t = _pinned((B,), np.float32); self._pin.append(t)
+        self._lfp_cache = None
+        self.current_step = np.zeros(B, dtype=np.int64)
+        self._upload_and_run_transient(np.arange(B), setups)
+
+    # -------------------------------------------------------------------------------------
+    def _upload_and_run_transient(self, ids, setups):
+        ids = np.asarray(ids, dtype=np.int32)
+        self.engine.set_env_params(ids, w0=np.stack([s.w0 for s in setups]),
+                                   stim=np.stack([s.stim for s in setups]),
+                                   rec=np.stack([s.rec for s in setups]),
+                                   y0=np.stack([s.y0 for s in setups]))
+        self.engine.set_episode(ids, step_idx=0,
+                                episode_len=[self.hosts[i].total_episode_counts for i in ids])
+        for i, s in zip(ids, setups):
+            self.electrodes[i] = s.electrode
+            self.w0_model[i] = s.w0
+            self.current_step[i] = 0
+        self.engine.transient(self.t_transient, env_ids=ids)
+        self._lfp_cache = None
+
+    def reset_envs(self, ids):
+        """reset() of the listed environments, in the order given (reference env.py:467-614)."""
+        setups = [self.hosts[i].begin_episode() for i in ids]
+        self._upload_and_run_transient(ids, setups)
+
+    def observations(self):
+        """Current observation windows [B, W] float32 (host)."""
+        return self.engine.obs_host(self.obs_buf)
+
+    def step(self, actions):
+        """Advance every environment by one step.  Returns host views (obs [B,W] f32, reward [B] f32,
+        done [B] bool) that are overwritten by the next call."""
+        self.act_buf[:] = np.asarray(actions, dtype=np.float32).reshape(self.num_envs)
+        self.engine.step_host(self.act_buf, self.obs_buf, self.rew_buf, self.done_buf)
+        self.current_step += 1
+        self._lfp_cache = None
+        return self.obs_buf, self.rew_buf, self.done_buf.view(np.bool_)
+
+    # -------------------------------------------------------------------------------------
+    def _lfp(self):
+        if self._lfp_cache is None:
+            self._lfp_cache = self.engine.lfp()
+        return self._lfp_cache
+
+    def theta_mean(self, i):
+        t, _, n = self._lfp()
+        return t[i, :n[i]].copy()
+
+    def theta_records(self, i):
+        _, r, n = self._lfp()
+        return r[i, :n[i]].copy()
+
+    def u(self, i):
+        return [float(self.engine.rewards()[1][i])]
+
+    def current_time(self, i):
+        k = int(self.current_step[i])
+        return float(self.t_transient[-1]) if k == 0 else float(self.schedule.t_after[k - 1])
+
+    def close(self):
+        self.engine.close()
+
+
+def _same(a, b):
+    try:
+        return bool(np.all(np.asarray(a) == np.asarray(b)))
+    except Exception:                                                    # noqa: BLE001
+        return a == b

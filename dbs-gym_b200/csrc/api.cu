@@ -1,0 +1,803 @@
+// C-ABI of the DBS-Gym step engine (see include/dbsgym.h for the contract).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/dbsgym.h"
+#include "obs_kernel.cuh"
+#include "step_kernel.cuh"
+
+using namespace dbsgym;
+
+namespace {
+
+thread_local char g_create_err[512] = "";
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct DbsGymHandle {
+    DbsGymConfig cfg;
+    int N = 0, Np = 0, B = 0, W = 0, smax = 0;
+    bool f64 = false;
+    size_t rb = 4;                       // bytes per real
+    int nthreads = 0, tab = 0;
+    cudaStream_t stream = nullptr;
+    // model
+    void* table = nullptr; void* alpha = nullptr;
+    bool have_coupling = false;
+    int weighted_rec = 0;
+    // per-env state
+    void *w0 = nullptr, *stim = nullptr, *rec = nullptr, *phase = nullptr, *ring = nullptr;
+    int32_t *wind = nullptr, *head = nullptr, *n_samples = nullptr, *step_idx = nullptr, *episode_len = nullptr;
+    double *lfp_true = nullptr, *lfp_rec = nullptr, *u = nullptr, *reward = nullptr;
+    uint8_t* done = nullptr;
+    // schedule
+    int32_t *sched_nI = nullptr, *sched_nII = nullptr;
+    double *sched_offI = nullptr, *sched_offII = nullptr;
+    int maxI = 0, maxII = 0, n_sched = 0;
+    // transient
+    double* ts_dev = nullptr; int ts_cap = 0;
+    int32_t* ids_dev = nullptr; int ids_cap = 0;
+    // reward
+    DbsGymRewardSpec rspec;
+    bool have_reward = false;
+    double *lin_g = nullptr, *tw_seed = nullptr, *tw_rot = nullptr;
+    int nbins = 0;
+    // bookkeeping
+    unsigned long long* counters = nullptr;
+    int32_t* status = nullptr;
+    // host-API staging
+    float *st_actions = nullptr, *st_obs = nullptr, *st_reward = nullptr;
+    uint8_t* st_done = nullptr;
+    // timing
+    bool timing = false;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    float last_ms[2] = {0.f, 0.f};
+    char err[512] = "";
+};
+
+namespace {
+
+int fail(DbsGymHandle* h, int code, const char* fmt, ...) {
+    char* dst = h ? h->err : g_create_err;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(h, call)                                                                            \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(h, DBSGYM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t count) {
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, count * sizeof(T));
+    return e;
+}
+
+__global__ void scatter_rows_kernel(unsigned char* dst, const unsigned char* src, const int32_t* ids,
+                                    int n, size_t row_bytes) {
+    const int r = blockIdx.x;
+    if (r >= n) return;
+    const int d = ids ? ids[r] : r;
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src + (size_t)r * row_bytes);
+    uint32_t* o = reinterpret_cast<uint32_t*>(dst + (size_t)d * row_bytes);
+    for (size_t i = threadIdx.x; i < row_bytes / 4; i += blockDim.x) o[i] = s[i];
+}
+
+__global__ void gather_rows_kernel(unsigned char* dst, const unsigned char* src, const int32_t* ids,
+                                   int n, size_t row_bytes) {
+    const int r = blockIdx.x;
+    if (r >= n) return;
+    const int d = ids ? ids[r] : r;
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src + (size_t)d * row_bytes);
+    uint32_t* o = reinterpret_cast<uint32_t*>(dst + (size_t)r * row_bytes);
+    for (size_t i = threadIdx.x; i < row_bytes / 4; i += blockDim.x) o[i] = s[i];
+}
+
+// dependent FFMA chains; 2*kChains*iters flops per thread
+constexpr int kChains = 8;
+__global__ void fma_peak_kernel(float* out, int iters, float a, float b) {
+    float v[kChains];
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) v[c] = (float)(threadIdx.x + c);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int c = 0; c < kChains; ++c) v[c] = fmaf(v[c], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) s += v[c];
+    if (s == 123.456f) out[0] = s;
+}
+
+int upload_ids(DbsGymHandle* h, const int32_t* env_ids, int n, const int32_t** dev) {
+    *dev = nullptr;
+    if (!env_ids) return DBSGYM_OK;
+    for (int i = 0; i < n; ++i)
+        if (env_ids[i] < 0 || env_ids[i] >= h->B) return fail(h, DBSGYM_EINVAL, "env id %d out of range", env_ids[i]);
+    if (n > h->ids_cap) {
+        if (h->ids_dev) cudaFree(h->ids_dev);
+        h->ids_dev = nullptr;
+        CU(h, cudaMalloc(&h->ids_dev, sizeof(int32_t) * (size_t)n));
+        h->ids_cap = n;
+    }
+    CU(h, cudaMemcpyAsync(h->ids_dev, env_ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));     // env_ids is caller memory
+    *dev = h->ids_dev;
+    return DBSGYM_OK;
+}
+
+// scatter n rows of `row_bytes` from a host staging vector into a [B][row] device array
+int scatter_to_device(DbsGymHandle* h, void* dst, const void* host_rows, const int32_t* ids_dev, int n,
+                      size_t row_bytes) {
+    void* tmp = nullptr;
+    CU(h, cudaMalloc(&tmp, row_bytes * (size_t)n));
+    cudaError_t e = cudaMemcpyAsync(tmp, host_rows, row_bytes * (size_t)n, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        scatter_rows_kernel<<<n, 128, 0, h->stream>>>(static_cast<unsigned char*>(dst),
+                                                      static_cast<const unsigned char*>(tmp), ids_dev, n, row_bytes);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(h, DBSGYM_ECUDA, "scatter failed: %s", cudaGetErrorString(e));
+    return DBSGYM_OK;
+}
+
+int gather_from_device(DbsGymHandle* h, void* host_rows, const void* src, const int32_t* ids_dev, int n,
+                       size_t row_bytes) {
+    void* tmp = nullptr;
+    CU(h, cudaMalloc(&tmp, row_bytes * (size_t)n));
+    gather_rows_kernel<<<n, 128, 0, h->stream>>>(static_cast<unsigned char*>(tmp),
+                                                 static_cast<const unsigned char*>(src), ids_dev, n, row_bytes);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_rows, tmp, row_bytes * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return fail(h, DBSGYM_ECUDA, "gather failed: %s", cudaGetErrorString(e));
+    return DBSGYM_OK;
+}
+
+template <typename real>
+void to_real_rows(const double* src, int n, int N, int Np, std::vector<unsigned char>& out) {
+    out.assign((size_t)n * Np * sizeof(real), 0);
+    real* o = reinterpret_cast<real*>(out.data());
+    for (int r = 0; r < n; ++r)
+        for (int i = 0; i < N; ++i) o[(size_t)r * Np + i] = (real)src[(size_t)r * N + i];
+}
+
+void fill_params(DbsGymHandle* h, StepParams& p) {
+    const DbsGymConfig& c = h->cfg;
+    p.N = h->N; p.Np = h->Np; p.B = h->B;
+    p.GX = c.grid[0]; p.GZ = c.grid[2];
+    p.weighted_rec = h->weighted_rec;
+    p.max_steps = c.max_steps;
+    p.k_over_n = c.K / (double)h->N;
+    p.rtol = c.rtol; p.atol = c.atol; p.dt0 = c.dt0;
+    p.safety = c.safety; p.fmin = c.factor_min; p.fmax = c.factor_max;
+    p.tol_end = 1e-10;
+    p.act_lo = c.action_lo; p.act_hi = c.action_hi;
+    p.table = h->table; p.alpha = h->alpha;
+    p.phase = h->phase; p.wind = h->wind;
+    p.w0 = h->w0; p.stim = h->stim; p.rec = h->rec;
+    p.step_idx = h->step_idx;
+    p.sched_nI = h->sched_nI; p.sched_nII = h->sched_nII;
+    p.sched_offI = h->sched_offI; p.sched_offII = h->sched_offII;
+    p.maxI = h->maxI; p.maxII = h->maxII; p.n_sched = h->n_sched;
+    p.lfp_true = h->lfp_true; p.lfp_rec = h->lfp_rec; p.n_samples = h->n_samples;
+    p.smax = h->smax; p.u_out = h->u;
+    p.ring = h->ring; p.W = h->W; p.head = h->head;
+    p.counters = h->counters; p.status = h->status;
+    p.ts = nullptr; p.n_ts = 0; p.actions = nullptr; p.env_ids = nullptr; p.n_launch = 0; p.mode = MODE_STEP;
+}
+
+template <typename real, bool DENSE, int MAXT>
+cudaError_t launch_step_t(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
+    const size_t smem = step_smem_bytes(h->Np, DENSE ? 0 : h->tab, h->nthreads, sizeof(real));
+    auto kern = step_kernel<real, DENSE, MAXT>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<p.n_launch, h->nthreads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <typename real, bool DENSE>
+cudaError_t launch_step_m(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
+    const int t = h->nthreads;
+    if (t <= 64) return launch_step_t<real, DENSE, 64>(h, p, s);
+    if (t <= 128) return launch_step_t<real, DENSE, 128>(h, p, s);
+    if (t <= 256) return launch_step_t<real, DENSE, 256>(h, p, s);
+    if (t <= 512) return launch_step_t<real, DENSE, 512>(h, p, s);
+    return launch_step_t<real, DENSE, 1024>(h, p, s);
+}
+
+cudaError_t launch_step(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
+    const bool dense = h->cfg.coupling == DBSGYM_COUPLING_DENSE;
+    if (h->f64) return dense ? launch_step_m<double, true>(h, p, s) : launch_step_m<double, false>(h, p, s);
+    return dense ? launch_step_m<float, true>(h, p, s) : launch_step_m<float, false>(h, p, s);
+}
+
+cudaError_t launch_obs(DbsGymHandle* h, float* obs, float* reward_f, uint8_t* done_out, int append,
+                       const int32_t* ids_dev, int n, cudaStream_t s) {
+    ObsParams o;
+    o.B = h->B; o.W = h->W; o.smax = h->smax;
+    o.ring = h->ring; o.head = h->head;
+    o.lfp_rec = h->lfp_rec; o.n_samples = h->n_samples;
+    o.obs = obs; o.reward_f = reward_f; o.reward = h->reward; o.done_out = done_out; o.done_dev = h->done;
+    o.step_idx = h->step_idx; o.episode_len = h->episode_len; o.u = h->u;
+    o.kind = h->rspec.kind; o.nbins = h->nbins;
+    o.power_scale = h->rspec.power_scale; o.action_cost = h->rspec.action_cost;
+    o.threshold = h->rspec.threshold; o.threshold_penalty = h->rspec.threshold_penalty;
+    o.temp_scale = h->rspec.temp_scale;
+    o.lin_g = h->lin_g; o.tw_seed = h->tw_seed; o.tw_rot = h->tw_rot;
+    o.append = append; o.env_ids = ids_dev; o.n_launch = n;
+    const size_t smem = (size_t)h->W * sizeof(double);
+    if (h->f64) obs_kernel<double><<<n, kObsThreads, smem, s>>>(o);
+    else obs_kernel<float><<<n, kObsThreads, smem, s>>>(o);
+    return cudaGetLastError();
+}
+
+int check_ready(DbsGymHandle* h, bool need_step) {
+    if (!h) return DBSGYM_EINVAL;
+    if (!h->have_coupling) return fail(h, DBSGYM_ESTATE, "coupling not set (dbsgym_set_coupling_*)");
+    if (need_step) {
+        if (h->n_sched <= 0) return fail(h, DBSGYM_ESTATE, "schedule not set (dbsgym_set_schedule)");
+        if (!h->have_reward) return fail(h, DBSGYM_ESTATE, "reward not set (dbsgym_set_reward)");
+    }
+    return DBSGYM_OK;
+}
+
+int step_impl(DbsGymHandle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+              cudaStream_t s) {
+    StepParams p;
+    fill_params(h, p);
+    p.mode = MODE_STEP; p.actions = actions_dev; p.n_launch = h->B;
+    if (h->timing) CU(h, cudaEventRecord(h->ev[0], s));
+    CU(h, launch_step(h, p, s));
+    if (h->timing) CU(h, cudaEventRecord(h->ev[1], s));
+    CU(h, launch_obs(h, obs_dev, reward_dev, done_dev, 1, nullptr, h->B, s));
+    if (h->timing) CU(h, cudaEventRecord(h->ev[2], s));
+    return DBSGYM_OK;
+}
+
+}  // namespace
+
+// ============================================================================================
+extern "C" {
+
+int dbsgym_abi_version(void) { return DBSGYM_ABI_VERSION; }
+
+const char* dbsgym_last_error(const DbsGymHandle* h) { return h ? h->err : g_create_err; }
+
+int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
+    if (!cfg || !out) return fail(nullptr, DBSGYM_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->struct_bytes != sizeof(DbsGymConfig))
+        return fail(nullptr, DBSGYM_EINVAL, "DbsGymConfig size mismatch: got %u, library expects %zu",
+                    cfg->struct_bytes, sizeof(DbsGymConfig));
+    if (cfg->n_envs <= 0 || cfg->n_osc <= 0 || cfg->window <= 0 || cfg->max_step_samples <= 0)
+        return fail(nullptr, DBSGYM_EINVAL, "n_envs, n_osc, window and max_step_samples must be positive");
+    if (cfg->precision != DBSGYM_F32 && cfg->precision != DBSGYM_F64)
+        return fail(nullptr, DBSGYM_EINVAL, "unknown precision %d", cfg->precision);
+    if (cfg->coupling != DBSGYM_COUPLING_GRID && cfg->coupling != DBSGYM_COUPLING_DENSE)
+        return fail(nullptr, DBSGYM_EINVAL, "unknown coupling mode %d", cfg->coupling);
+    if (!(cfg->rtol > 0) || !(cfg->atol > 0) || !(cfg->dt0 > 0) || cfg->max_steps <= 0)
+        return fail(nullptr, DBSGYM_EINVAL, "rtol, atol, dt0 and max_steps must be positive");
+    const int Np = (cfg->n_osc + kRows - 1) / kRows * kRows;
+    if (Np / kRows > 1024) return fail(nullptr, DBSGYM_EINVAL, "n_osc %d too large for the resident-state kernel (max 8192)", cfg->n_osc);
+    if (cfg->coupling == DBSGYM_COUPLING_GRID) {
+        if (cfg->grid[1] != kRows)
+            return fail(nullptr, DBSGYM_EINVAL, "GRID coupling needs grid[1] (gy) == %d, got %d", kRows, cfg->grid[1]);
+        if (cfg->grid[0] <= 0 || cfg->grid[2] <= 0 || cfg->n_osc % kRows != 0 ||
+            cfg->n_osc > cfg->grid[0] * cfg->grid[1] * cfg->grid[2] || cfg->n_osc % (cfg->grid[0] * kRows) != 0)
+            return fail(nullptr, DBSGYM_EINVAL, "GRID coupling needs n_osc to be whole z-planes of a gx*8*gz grid");
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, DBSGYM_ECUDA, "no CUDA device available (%s); this library has no CPU path",
+                    cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, DBSGYM_EINVAL, "device %d out of range", cfg->device);
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, DBSGYM_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+
+    DbsGymHandle* h = new (std::nothrow) DbsGymHandle();
+    if (!h) return fail(nullptr, DBSGYM_ENOMEM, "out of host memory");
+    h->cfg = *cfg;
+    h->N = cfg->n_osc; h->Np = Np; h->B = cfg->n_envs; h->W = cfg->window; h->smax = cfg->max_step_samples;
+    h->f64 = cfg->precision == DBSGYM_F64;
+    h->rb = h->f64 ? 8 : 4;
+    h->nthreads = Np / kRows;
+    if (cfg->coupling == DBSGYM_COUPLING_GRID) {
+        // only the z-planes actually populated take part
+        h->cfg.grid[2] = cfg->n_osc / (cfg->grid[0] * kRows);
+        h->tab = h->cfg.grid[2] * cfg->grid[0] * kRows;
+    }
+    memset(&h->rspec, 0, sizeof(h->rspec));
+    const size_t BN = (size_t)h->B * Np;
+    bool ok = true;
+    ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
+    auto A = [&](void** p, size_t bytes) {
+        if (!ok) return;
+        ok = cudaMalloc(p, bytes) == cudaSuccess && cudaMemset(*p, 0, bytes) == cudaSuccess;
+    };
+    A(&h->w0, BN * h->rb); A(&h->stim, BN * h->rb); A(&h->rec, BN * h->rb); A(&h->phase, BN * h->rb);
+    A((void**)&h->wind, BN * 4);
+    A(&h->ring, (size_t)h->B * h->W * h->rb);
+    A((void**)&h->head, (size_t)h->B * 4); A((void**)&h->n_samples, (size_t)h->B * 4);
+    A((void**)&h->step_idx, (size_t)h->B * 4); A((void**)&h->episode_len, (size_t)h->B * 4);
+    A((void**)&h->lfp_true, (size_t)h->B * h->smax * 8); A((void**)&h->lfp_rec, (size_t)h->B * h->smax * 8);
+    A((void**)&h->u, (size_t)h->B * 8); A((void**)&h->reward, (size_t)h->B * 8);
+    A((void**)&h->done, (size_t)h->B);
+    A((void**)&h->counters, 3 * sizeof(unsigned long long)); A((void**)&h->status, 4);
+    A((void**)&h->st_actions, (size_t)h->B * 4); A((void**)&h->st_obs, (size_t)h->B * h->W * 4);
+    A((void**)&h->st_reward, (size_t)h->B * 4); A((void**)&h->st_done, (size_t)h->B);
+    for (int i = 0; i < 3 && ok; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
+    if (ok) {
+        // episode_len defaults to "never done"
+        std::vector<int32_t> big((size_t)h->B, 0x7fffffff);
+        ok = cudaMemcpy(h->episode_len, big.data(), big.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    if (!ok) {
+        fail(nullptr, DBSGYM_ENOMEM, "device allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        dbsgym_destroy(h);
+        return DBSGYM_ENOMEM;
+    }
+    *out = h;
+    return DBSGYM_OK;
+}
+
+void dbsgym_destroy(DbsGymHandle* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* bufs[] = {h->table, h->alpha, h->w0, h->stim, h->rec, h->phase, h->ring, h->wind, h->head, h->n_samples,
+                    h->step_idx, h->episode_len, h->lfp_true, h->lfp_rec, h->u, h->reward, h->done, h->sched_nI,
+                    h->sched_nII, h->sched_offI, h->sched_offII, h->ts_dev, h->ids_dev, h->lin_g, h->tw_seed,
+                    h->tw_rot, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    for (int i = 0; i < 3; ++i)
+        if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int dbsgym_set_coupling_grid(DbsGymHandle* h, const double* table) {
+    if (!h || !table) return fail(h, DBSGYM_EINVAL, "null argument");
+    if (h->cfg.coupling != DBSGYM_COUPLING_GRID) return fail(h, DBSGYM_ESTATE, "handle was created with DENSE coupling");
+    CU(h, cudaSetDevice(h->cfg.device));
+    const int GX = h->cfg.grid[0], GZ = h->cfg.grid[2], NC = GZ * GX;
+    const int n = h->f64 ? 2 : 4;                      // elements per 16 bytes
+    std::vector<unsigned char> buf((size_t)h->tab * h->rb);
+    for (int c = 0; c < NC; ++c)
+        for (int dy = 0; dy < kRows; ++dy) {
+            const double v = table[(size_t)c * kRows + dy];
+            const size_t at = ((size_t)(dy / n) * NC + c) * n + dy % n;
+            if (h->f64) reinterpret_cast<double*>(buf.data())[at] = v;
+            else reinterpret_cast<float*>(buf.data())[at] = (float)v;
+        }
+    if (!h->table) CU(h, cudaMalloc(&h->table, buf.size()));
+    CU(h, cudaMemcpy(h->table, buf.data(), buf.size(), cudaMemcpyHostToDevice));
+    h->have_coupling = true;
+    return DBSGYM_OK;
+}
+
+int dbsgym_set_coupling_dense(DbsGymHandle* h, const double* alpha) {
+    if (!h || !alpha) return fail(h, DBSGYM_EINVAL, "null argument");
+    if (h->cfg.coupling != DBSGYM_COUPLING_DENSE) return fail(h, DBSGYM_ESTATE, "handle was created with GRID coupling");
+    CU(h, cudaSetDevice(h->cfg.device));
+    const int N = h->N, Np = h->Np;
+    std::vector<unsigned char> buf((size_t)Np * Np * h->rb, 0);
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {                  // stored transposed: [j][i]
+            const double v = alpha[(size_t)i * N + j];
+            if (h->f64) reinterpret_cast<double*>(buf.data())[(size_t)j * Np + i] = v;
+            else reinterpret_cast<float*>(buf.data())[(size_t)j * Np + i] = (float)v;
+        }
+    if (!h->alpha) CU(h, cudaMalloc(&h->alpha, buf.size()));
+    CU(h, cudaMemcpy(h->alpha, buf.data(), buf.size(), cudaMemcpyHostToDevice));
+    h->have_coupling = true;
+    return DBSGYM_OK;
+}
+
+int dbsgym_set_recording(DbsGymHandle* h, int32_t weighted) {
+    if (!h) return DBSGYM_EINVAL;
+    h->weighted_rec = weighted ? 1 : 0;
+    return DBSGYM_OK;
+}
+
+int dbsgym_set_env_params(DbsGymHandle* h, const int32_t* env_ids, int32_t n, const double* w0,
+                          const double* stim_cond, const double* rec_cond, const double* y0) {
+    if (!h) return DBSGYM_EINVAL;
+    if (n <= 0 || n > h->B) return fail(h, DBSGYM_EINVAL, "n=%d out of range", n);
+    CU(h, cudaSetDevice(h->cfg.device));
+    const int32_t* ids = nullptr;
+    int rc = upload_ids(h, env_ids, n, &ids);
+    if (rc) return rc;
+    std::vector<unsigned char> buf;
+    const size_t row = (size_t)h->Np * h->rb;
+    struct { const double* src; void* dst; } vecs[3] = {{w0, h->w0}, {stim_cond, h->stim}, {rec_cond, h->rec}};
+    for (auto& v : vecs) {
+        if (!v.src) continue;
+        if (h->f64) to_real_rows<double>(v.src, n, h->N, h->Np, buf);
+        else to_real_rows<float>(v.src, n, h->N, h->Np, buf);
+        rc = scatter_to_device(h, v.dst, buf.data(), ids, n, row);
+        if (rc) return rc;
+    }
+    if (y0) {
+        if (h->f64) {
+            to_real_rows<double>(y0, n, h->N, h->Np, buf);
+            rc = scatter_to_device(h, h->phase, buf.data(), ids, n, row);
+            if (rc) return rc;
+        } else {
+            // fp32 state: wrapped phase + integer winding count, y = phase + 2*pi*wind
+            std::vector<float> ph((size_t)n * h->Np, 0.f);
+            std::vector<int32_t> wd((size_t)n * h->Np, 0);
+            for (int r = 0; r < n; ++r)
+                for (int i = 0; i < h->N; ++i) {
+                    const double y = y0[(size_t)r * h->N + i];
+                    const double k = std::floor(y / kTwoPi);
+                    ph[(size_t)r * h->Np + i] = (float)(y - k * kTwoPi);
+                    wd[(size_t)r * h->Np + i] = (int32_t)k;
+                }
+            rc = scatter_to_device(h, h->phase, ph.data(), ids, n, row);
+            if (rc) return rc;
+            rc = scatter_to_device(h, h->wind, wd.data(), ids, n, (size_t)h->Np * 4);
+            if (rc) return rc;
+        }
+    }
+    return DBSGYM_OK;
+}
+
+int dbsgym_set_schedule(DbsGymHandle* h, int32_t n_steps, const int32_t* n_I, const int32_t* n_II,
+                        const double* offs_I, int32_t max_I, const double* offs_II, int32_t max_II) {
+    if (!h || !n_I || !n_II || !offs_I || !offs_II) return fail(h, DBSGYM_EINVAL, "null argument");
+    if (n_steps <= 0 || max_I <= 0 || max_II <= 0) return fail(h, DBSGYM_EINVAL, "bad schedule sizes");
+    for (int k = 0; k < n_steps; ++k) {
+        if (n_I[k] < 2 || n_I[k] > max_I || n_II[k] < 2 || n_II[k] > max_II)
+            return fail(h, DBSGYM_EINVAL, "schedule step %d: segment lengths (%d,%d) out of range", k, n_I[k], n_II[k]);
+        if (n_I[k] + n_II[k] - 1 > h->smax)
+            return fail(h, DBSGYM_EINVAL, "schedule step %d needs %d samples > max_step_samples %d", k,
+                        n_I[k] + n_II[k] - 1, h->smax);
+        if (offs_I[(size_t)k * max_I] != 0.0 || offs_II[(size_t)k * max_II] != 0.0)
+            return fail(h, DBSGYM_EINVAL, "schedule offsets must start at 0");
+    }
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (void* b : {(void*)h->sched_nI, (void*)h->sched_nII, (void*)h->sched_offI, (void*)h->sched_offII})
+        if (b) cudaFree(b);
+    h->sched_nI = h->sched_nII = nullptr; h->sched_offI = h->sched_offII = nullptr; h->n_sched = 0;
+    CU(h, cudaMalloc(&h->sched_nI, (size_t)n_steps * 4));
+    CU(h, cudaMalloc(&h->sched_nII, (size_t)n_steps * 4));
+    CU(h, cudaMalloc(&h->sched_offI, (size_t)n_steps * max_I * 8));
+    CU(h, cudaMalloc(&h->sched_offII, (size_t)n_steps * max_II * 8));
+    CU(h, cudaMemcpy(h->sched_nI, n_I, (size_t)n_steps * 4, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->sched_nII, n_II, (size_t)n_steps * 4, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->sched_offI, offs_I, (size_t)n_steps * max_I * 8, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->sched_offII, offs_II, (size_t)n_steps * max_II * 8, cudaMemcpyHostToDevice));
+    h->maxI = max_I; h->maxII = max_II; h->n_sched = n_steps;
+    return DBSGYM_OK;
+}
+
+int dbsgym_set_reward(DbsGymHandle* h, const DbsGymRewardSpec* spec, const double* lin_functional) {
+    if (!h || !spec) return fail(h, DBSGYM_EINVAL, "null argument");
+    if (spec->struct_bytes != sizeof(DbsGymRewardSpec)) return fail(h, DBSGYM_EINVAL, "DbsGymRewardSpec size mismatch");
+    if (spec->kind < 0 || spec->kind > 2) return fail(h, DBSGYM_EINVAL, "unknown reward kind %d", spec->kind);
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    const int W = h->W;
+    if (spec->kind == DBSGYM_REWARD_TEMP_CONST) {
+        if (!lin_functional) return fail(h, DBSGYM_EINVAL, "TEMP_CONST reward needs the linear functional");
+        if (!h->lin_g) CU(h, cudaMalloc(&h->lin_g, (size_t)W * 8));
+        CU(h, cudaMemcpy(h->lin_g, lin_functional, (size_t)W * 8, cudaMemcpyHostToDevice));
+        h->nbins = 0;
+    } else {
+        const int nb = spec->bin_hi - spec->bin_lo + 1;
+        if (spec->bin_lo < 0 || nb <= 0 || nb > kMaxBins || spec->bin_hi > W / 2)
+            return fail(h, DBSGYM_EINVAL, "bad rfft bin range [%d,%d] (at most %d bins)", spec->bin_lo, spec->bin_hi, kMaxBins);
+        std::vector<double> seed((size_t)nb * kObsThreads * 2), rot((size_t)nb * 2);
+        const double two_pi = kTwoPi;
+        for (int b = 0; b < nb; ++b) {
+            const long long k = spec->bin_lo + b;
+            for (int m = 0; m < kObsThreads; ++m) {
+                const long long q = (k * m) % W;       // exact integer phase reduction
+                seed[((size_t)b * kObsThreads + m) * 2] = std::cos(two_pi * (double)q / W);
+                seed[((size_t)b * kObsThreads + m) * 2 + 1] = std::sin(two_pi * (double)q / W);
+            }
+            const long long q = (k * kObsThreads) % W;
+            rot[(size_t)b * 2] = std::cos(two_pi * (double)q / W);
+            rot[(size_t)b * 2 + 1] = std::sin(two_pi * (double)q / W);
+        }
+        if (h->tw_seed) cudaFree(h->tw_seed);
+        if (h->tw_rot) cudaFree(h->tw_rot);
+        h->tw_seed = h->tw_rot = nullptr;
+        CU(h, cudaMalloc(&h->tw_seed, seed.size() * 8));
+        CU(h, cudaMalloc(&h->tw_rot, rot.size() * 8));
+        CU(h, cudaMemcpy(h->tw_seed, seed.data(), seed.size() * 8, cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->tw_rot, rot.data(), rot.size() * 8, cudaMemcpyHostToDevice));
+        h->nbins = nb;
+    }
+    h->rspec = *spec;
+    h->have_reward = true;
+    return DBSGYM_OK;
+}
+
+int dbsgym_set_episode(DbsGymHandle* h, const int32_t* env_ids, int32_t n, const int32_t* step_idx,
+                       const int32_t* episode_len) {
+    if (!h) return DBSGYM_EINVAL;
+    if (n <= 0 || n > h->B) return fail(h, DBSGYM_EINVAL, "n=%d out of range", n);
+    CU(h, cudaSetDevice(h->cfg.device));
+    const int32_t* ids = nullptr;
+    int rc = upload_ids(h, env_ids, n, &ids);
+    if (rc) return rc;
+    if (step_idx) { rc = scatter_to_device(h, h->step_idx, step_idx, ids, n, 4); if (rc) return rc; }
+    if (episode_len) { rc = scatter_to_device(h, h->episode_len, episode_len, ids, n, 4); if (rc) return rc; }
+    if (step_idx) {
+        std::vector<uint8_t> z((size_t)n, 0);
+        // done flags of re-armed environments are cleared (1-byte rows cannot use the 4-byte scatter)
+        std::vector<uint8_t> all((size_t)h->B);
+        CU(h, cudaMemcpy(all.data(), h->done, (size_t)h->B, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < n; ++i) all[env_ids ? env_ids[i] : i] = 0;
+        CU(h, cudaMemcpy(h->done, all.data(), (size_t)h->B, cudaMemcpyHostToDevice));
+    }
+    return DBSGYM_OK;
+}
+
+int dbsgym_transient(DbsGymHandle* h, const int32_t* env_ids, int32_t n, const double* ts_offsets, int32_t n_ts,
+                     float* obs_dev, void* stream) {
+    int rc = check_ready(h, false);
+    if (rc) return rc;
+    if (!ts_offsets || n_ts < 2) return fail(h, DBSGYM_EINVAL, "need at least two sample times");
+    if (n <= 0 || n > h->B) return fail(h, DBSGYM_EINVAL, "n=%d out of range", n);
+    if (ts_offsets[0] != 0.0) return fail(h, DBSGYM_EINVAL, "ts_offsets must start at 0");
+    if (n_ts - 1 < h->W) return fail(h, DBSGYM_EINVAL, "transient gives %d samples < window %d (env.py:303-304)", n_ts - 1, h->W);
+    CU(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    const int32_t* ids = nullptr;
+    rc = upload_ids(h, env_ids, n, &ids);
+    if (rc) return rc;
+    if (n_ts > h->ts_cap) {
+        CU(h, cudaStreamSynchronize(s));
+        if (h->ts_dev) cudaFree(h->ts_dev);
+        h->ts_dev = nullptr;
+        CU(h, cudaMalloc(&h->ts_dev, (size_t)n_ts * 8));
+        h->ts_cap = n_ts;
+    }
+    CU(h, cudaMemcpyAsync(h->ts_dev, ts_offsets, (size_t)n_ts * 8, cudaMemcpyHostToDevice, s));
+    CU(h, cudaStreamSynchronize(s));               // ts_offsets is caller memory
+    StepParams p;
+    fill_params(h, p);
+    p.mode = MODE_TRANSIENT; p.env_ids = ids; p.n_launch = n; p.ts = h->ts_dev; p.n_ts = n_ts;
+    CU(h, launch_step(h, p, s));
+    CU(h, launch_obs(h, obs_dev, nullptr, nullptr, 0, ids, n, s));
+    if (ids) CU(h, cudaStreamSynchronize(s));      // ids_dev is reused by the next call
+    return DBSGYM_OK;
+}
+
+int dbsgym_step(DbsGymHandle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                void* stream) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    if (!actions_dev) return fail(h, DBSGYM_EINVAL, "actions_dev is null");
+    CU(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    return step_impl(h, actions_dev, obs_dev, reward_dev, done_dev, s);
+}
+
+int dbsgym_step_host(DbsGymHandle* h, const float* actions, float* obs, float* reward, uint8_t* done) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    if (!actions) return fail(h, DBSGYM_EINVAL, "actions is null");
+    CU(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t s = h->stream;
+    CU(h, cudaMemcpyAsync(h->st_actions, actions, (size_t)h->B * 4, cudaMemcpyHostToDevice, s));
+    rc = step_impl(h, h->st_actions, obs ? h->st_obs : nullptr, h->st_reward, h->st_done, s);
+    if (rc) return rc;
+    if (obs) CU(h, cudaMemcpyAsync(obs, h->st_obs, (size_t)h->B * h->W * 4, cudaMemcpyDeviceToHost, s));
+    if (reward) CU(h, cudaMemcpyAsync(reward, h->st_reward, (size_t)h->B * 4, cudaMemcpyDeviceToHost, s));
+    if (done) CU(h, cudaMemcpyAsync(done, h->st_done, (size_t)h->B, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    return DBSGYM_OK;
+}
+
+int dbsgym_get_obs_host(DbsGymHandle* h, float* obs) {
+    int rc = check_ready(h, false);
+    if (rc) return rc;
+    if (!obs) return fail(h, DBSGYM_EINVAL, "obs is null");
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, launch_obs(h, h->st_obs, nullptr, nullptr, 0, nullptr, h->B, h->stream));
+    CU(h, cudaMemcpyAsync(obs, h->st_obs, (size_t)h->B * h->W * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    return DBSGYM_OK;
+}
+
+int dbsgym_get_lfp(DbsGymHandle* h, double* lfp_true, double* lfp_rec, int32_t* n_samples) {
+    if (!h) return DBSGYM_EINVAL;
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaDeviceSynchronize());
+    const size_t nb = (size_t)h->B * h->smax * 8;
+    if (lfp_true) CU(h, cudaMemcpy(lfp_true, h->lfp_true, nb, cudaMemcpyDeviceToHost));
+    if (lfp_rec) CU(h, cudaMemcpy(lfp_rec, h->lfp_rec, nb, cudaMemcpyDeviceToHost));
+    if (n_samples) CU(h, cudaMemcpy(n_samples, h->n_samples, (size_t)h->B * 4, cudaMemcpyDeviceToHost));
+    return DBSGYM_OK;
+}
+
+int dbsgym_get_rewards(DbsGymHandle* h, double* reward, double* u) {
+    if (!h) return DBSGYM_EINVAL;
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaDeviceSynchronize());
+    if (reward) CU(h, cudaMemcpy(reward, h->reward, (size_t)h->B * 8, cudaMemcpyDeviceToHost));
+    if (u) CU(h, cudaMemcpy(u, h->u, (size_t)h->B * 8, cudaMemcpyDeviceToHost));
+    return DBSGYM_OK;
+}
+
+int dbsgym_get_state(DbsGymHandle* h, const int32_t* env_ids, int32_t n, double* y) {
+    if (!h || !y) return fail(h, DBSGYM_EINVAL, "null argument");
+    if (n <= 0 || n > h->B) return fail(h, DBSGYM_EINVAL, "n=%d out of range", n);
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaDeviceSynchronize());
+    const int32_t* ids = nullptr;
+    int rc = upload_ids(h, env_ids, n, &ids);
+    if (rc) return rc;
+    std::vector<unsigned char> ph((size_t)n * h->Np * h->rb);
+    rc = gather_from_device(h, ph.data(), h->phase, ids, n, (size_t)h->Np * h->rb);
+    if (rc) return rc;
+    if (h->f64) {
+        const double* p = reinterpret_cast<const double*>(ph.data());
+        for (int r = 0; r < n; ++r)
+            for (int i = 0; i < h->N; ++i) y[(size_t)r * h->N + i] = p[(size_t)r * h->Np + i];
+    } else {
+        std::vector<int32_t> wd((size_t)n * h->Np);
+        rc = gather_from_device(h, wd.data(), h->wind, ids, n, (size_t)h->Np * 4);
+        if (rc) return rc;
+        const float* p = reinterpret_cast<const float*>(ph.data());
+        for (int r = 0; r < n; ++r)
+            for (int i = 0; i < h->N; ++i)
+                y[(size_t)r * h->N + i] = (double)p[(size_t)r * h->Np + i] + kTwoPi * (double)wd[(size_t)r * h->Np + i];
+    }
+    return DBSGYM_OK;
+}
+
+int dbsgym_get_window(DbsGymHandle* h, const int32_t* env_ids, int32_t n, double* window) {
+    if (!h || !window) return fail(h, DBSGYM_EINVAL, "null argument");
+    if (n <= 0 || n > h->B) return fail(h, DBSGYM_EINVAL, "n=%d out of range", n);
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaDeviceSynchronize());
+    const int32_t* ids = nullptr;
+    int rc = upload_ids(h, env_ids, n, &ids);
+    if (rc) return rc;
+    const int W = h->W;
+    std::vector<unsigned char> rg((size_t)n * W * h->rb);
+    std::vector<int32_t> hd((size_t)n);
+    rc = gather_from_device(h, rg.data(), h->ring, ids, n, (size_t)W * h->rb);
+    if (rc) return rc;
+    rc = gather_from_device(h, hd.data(), h->head, ids, n, 4);
+    if (rc) return rc;
+    for (int r = 0; r < n; ++r)
+        for (int m = 0; m < W; ++m) {
+            int c = m - hd[r];
+            if (c < 0) c += W;
+            window[(size_t)r * W + c] = h->f64 ? reinterpret_cast<const double*>(rg.data())[(size_t)r * W + m]
+                                               : (double)reinterpret_cast<const float*>(rg.data())[(size_t)r * W + m];
+        }
+    return DBSGYM_OK;
+}
+
+int dbsgym_set_window(DbsGymHandle* h, const int32_t* env_ids, int32_t n, const double* window) {
+    if (!h || !window) return fail(h, DBSGYM_EINVAL, "null argument");
+    if (n <= 0 || n > h->B) return fail(h, DBSGYM_EINVAL, "n=%d out of range", n);
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaDeviceSynchronize());
+    const int32_t* ids = nullptr;
+    int rc = upload_ids(h, env_ids, n, &ids);
+    if (rc) return rc;
+    std::vector<unsigned char> buf;
+    if (h->f64) to_real_rows<double>(window, n, h->W, h->W, buf);
+    else to_real_rows<float>(window, n, h->W, h->W, buf);
+    rc = scatter_to_device(h, h->ring, buf.data(), ids, n, (size_t)h->W * h->rb);
+    if (rc) return rc;
+    std::vector<int32_t> z((size_t)n, 0);
+    return scatter_to_device(h, h->head, z.data(), ids, n, 4);
+}
+
+int dbsgym_get_episode(DbsGymHandle* h, int32_t* step_idx, uint8_t* done) {
+    if (!h) return DBSGYM_EINVAL;
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaDeviceSynchronize());
+    if (step_idx) CU(h, cudaMemcpy(step_idx, h->step_idx, (size_t)h->B * 4, cudaMemcpyDeviceToHost));
+    if (done) CU(h, cudaMemcpy(done, h->done, (size_t)h->B, cudaMemcpyDeviceToHost));
+    return DBSGYM_OK;
+}
+
+int dbsgym_counters(DbsGymHandle* h, uint64_t* accepted, uint64_t* rejected, uint64_t* rhs_evals, int32_t* status,
+                    int32_t reset) {
+    if (!h) return DBSGYM_EINVAL;
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaDeviceSynchronize());
+    unsigned long long c[3];
+    int32_t st = 0;
+    CU(h, cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
+    CU(h, cudaMemcpy(&st, h->status, 4, cudaMemcpyDeviceToHost));
+    if (accepted) *accepted = c[0];
+    if (rejected) *rejected = c[1];
+    if (rhs_evals) *rhs_evals = c[2];
+    if (status) *status = st;
+    if (reset) {
+        CU(h, cudaMemset(h->counters, 0, sizeof(c)));
+        CU(h, cudaMemset(h->status, 0, 4));
+    }
+    return DBSGYM_OK;
+}
+
+int dbsgym_set_timing(DbsGymHandle* h, int32_t enabled) {
+    if (!h) return DBSGYM_EINVAL;
+    h->timing = enabled != 0;
+    return DBSGYM_OK;
+}
+
+int dbsgym_last_step_ms(DbsGymHandle* h, float* ms2) {
+    if (!h || !ms2) return fail(h, DBSGYM_EINVAL, "null argument");
+    if (!h->timing) return fail(h, DBSGYM_ESTATE, "timing is off (dbsgym_set_timing)");
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaEventSynchronize(h->ev[2]));
+    CU(h, cudaEventElapsedTime(&ms2[0], h->ev[0], h->ev[1]));
+    CU(h, cudaEventElapsedTime(&ms2[1], h->ev[1], h->ev[2]));
+    return DBSGYM_OK;
+}
+
+int dbsgym_measure_fp32_peak(int32_t device, double ms_target, double* tflops) {
+    if (!tflops) return DBSGYM_EINVAL;
+    DbsGymHandle* h = nullptr;
+    CU(h, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(h, cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 4, threads = 512;
+    float* out = nullptr;
+    CU(h, cudaMalloc(&out, 4));
+    cudaEvent_t a, b;
+    CU(h, cudaEventCreate(&a));
+    CU(h, cudaEventCreate(&b));
+    int iters = 1 << 14;
+    double best = 0.0;
+    for (int rep = 0; rep < 8; ++rep) {
+        cudaEventRecord(a);
+        fma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001f, 1e-9f);
+        cudaEventRecord(b);
+        cudaError_t e = cudaEventSynchronize(b);
+        if (e != cudaSuccess) { cudaFree(out); return fail(h, DBSGYM_ECUDA, "peak kernel: %s", cudaGetErrorString(e)); }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        const double fl = 2.0 * kChains * (double)iters * blocks * threads;
+        const double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep >= 2 && tf > best) best = tf;
+        if (ms < ms_target && iters < (1 << 24)) iters *= 2;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    *tflops = best;
+    return DBSGYM_OK;
+}
+
+}  // extern "C"

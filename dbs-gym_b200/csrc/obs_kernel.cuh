@@ -1,0 +1,138 @@
+// Observation / reward kernel (sm_100a), HBM-bound.
+//
+// Per environment: append the step's recorded LFP samples to the observation ring
+// (reference environment/env.py:447-448), emit the window in chronological order as the
+// float32 observation (env.py:454), and evaluate the reward of env.py:638-688:
+//   R1/R3  beta-band power  sum_k 2 |X_k / W|^2 over the rfft bins inside (12.5, 21) Hz
+//          (utils.py:21-27).  |X_k| is invariant under a circular shift when the DFT length
+//          equals the ring length, so the bins are accumulated in ring STORAGE order; the
+//          twiddles come from a [bins][threads] seed table and a per-bin rotation.
+//   R2     -1e3 (x_f[-1] - mean x_f)^2 with x_f = filtfilt(butter(2,[12,30] Hz)) (env.py:653-666,
+//          utils.py:794-816).  filtfilt (odd padding + lfilter_zi start) is linear in the
+//          window, so the bracket is a dot product g . window with g precomputed on the host.
+// One CTA per environment; the window passes through shared memory once.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dbsgym {
+
+constexpr int kObsThreads = 128;
+constexpr int kMaxBins = 32;
+
+struct ObsParams {
+    int B, W, smax;
+    void* ring; int32_t* head;
+    const double* lfp_rec; const int32_t* n_samples;
+    float* obs; float* reward_f; double* reward; uint8_t* done_out; uint8_t* done_dev;
+    int32_t* step_idx; const int32_t* episode_len; const double* u;
+    int kind, nbins;
+    double power_scale, action_cost, threshold, threshold_penalty, temp_scale;
+    const double* lin_g;      // [W] chronological
+    const double* tw_seed;    // [nbins][kObsThreads][2]  cos, sin of 2*pi*k*m/W for m < kObsThreads
+    const double* tw_rot;     // [nbins][2]               rotation by kObsThreads samples
+    int append;               // 1: full step; 0: only emit the observation of the current window
+    const int32_t* env_ids; int n_launch;
+};
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(kObsThreads) obs_kernel(const ObsParams p) {
+    extern __shared__ double xs[];                    // [W] window, ring storage order
+    __shared__ double part[kMaxBins + 1][kObsThreads / 32][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slot = blockIdx.x;
+    if (slot >= p.n_launch) return;
+    const int env = p.env_ids ? p.env_ids[slot] : slot;
+    const int W = p.W;
+    real* ring = reinterpret_cast<real*>(p.ring) + (size_t)env * W;
+    const int head = p.head[env];
+    const int S = p.append ? p.n_samples[env] : 0;
+
+    for (int m = tid; m < W; m += kObsThreads) xs[m] = (double)ring[m];
+    __syncthreads();
+    for (int i = tid; i < S; i += kObsThreads) {
+        int pos = head + i;
+        if (pos >= W) pos -= W;
+        const real v = real(p.lfp_rec[(size_t)env * p.smax + i]);
+        ring[pos] = v;
+        xs[pos] = (double)v;
+    }
+    int new_head = head + S;
+    if (new_head >= W) new_head -= W;
+    __syncthreads();
+
+    if (p.obs) {
+        float* o = p.obs + (size_t)env * W;
+        for (int m = tid; m < W; m += kObsThreads) {
+            int n = m - new_head;
+            if (n < 0) n += W;
+            o[n] = (float)xs[m];
+        }
+    }
+    if (!p.append) return;
+
+    if (p.kind == 1) {                                // R2: g . window (chronological order)
+        double acc = 0.0;
+        for (int m = tid; m < W; m += kObsThreads) {
+            int n = m - new_head;
+            if (n < 0) n += W;
+            acc = fma(p.lin_g[n], xs[m], acc);
+        }
+        acc = warp_sum_d(acc);
+        if (lane == 0) part[kMaxBins][warp][0] = acc;
+    } else {
+        for (int kb = 0; kb < p.nbins; ++kb) {
+            double cr = p.tw_seed[(kb * kObsThreads + tid) * 2];
+            double ci = p.tw_seed[(kb * kObsThreads + tid) * 2 + 1];
+            const double rr = p.tw_rot[kb * 2], ri = p.tw_rot[kb * 2 + 1];
+            double re = 0.0, im = 0.0;
+            for (int m = tid; m < W; m += kObsThreads) {
+                const double x = xs[m];
+                re = fma(x, cr, re);
+                im = fma(x, ci, im);
+                const double ncr = cr * rr - ci * ri;
+                ci = cr * ri + ci * rr;
+                cr = ncr;
+            }
+            re = warp_sum_d(re);
+            im = warp_sum_d(im);
+            if (lane == 0) { part[kb][warp][0] = re; part[kb][warp][1] = im; }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double au = fabs(p.u[env]);
+        double r;
+        if (p.kind == 1) {
+            double d = 0.0;
+            for (int w = 0; w < kObsThreads / 32; ++w) d += part[kMaxBins][w][0];
+            r = -p.temp_scale * d * d - p.action_cost * au;
+        } else {
+            double pw = 0.0;
+            for (int kb = 0; kb < p.nbins; ++kb) {
+                double re = 0.0, im = 0.0;
+                for (int w = 0; w < kObsThreads / 32; ++w) { re += part[kb][w][0]; im += part[kb][w][1]; }
+                re /= (double)W; im /= (double)W;
+                pw += (re * re + im * im) * 2.0;
+            }
+            if (p.kind == 0) r = -p.power_scale * pw - p.action_cost * au;
+            else r = -((p.power_scale * pw > p.threshold) ? p.threshold_penalty : 0.0) - p.action_cost * au;
+        }
+        p.reward[env] = r;
+        if (p.reward_f) p.reward_f[env] = (float)r;
+        const int k = p.step_idx[env] + 1;
+        p.step_idx[env] = k;
+        const uint8_t dn = k >= p.episode_len[env] ? 1 : 0;
+        p.done_dev[env] = dn;
+        if (p.done_out) p.done_out[env] = dn;
+        p.head[env] = new_head;
+    }
+}
+
+}  // namespace dbsgym

@@ -1,0 +1,501 @@
+// Fused Kuramoto environment-step kernel (sm_100a).
+//
+// One CTA integrates ONE environment through every Runge-Kutta sub-step of one
+// SpatialKuramoto.step() call (reference environment/env.py:415-454) -- or through the
+// reset transient (env.py:605-612) -- with the oscillator state resident on chip:
+//
+//   registers : phases y0 (+ winding counts in fp32 mode), natural frequencies w0,
+//               stimulation conductance, recording conductance      (8 oscillators / thread)
+//   shared    : the seven Dopri5 stage derivatives K[7][N], the [sin,cos] operand of the
+//               coupling contraction (double buffered) and the coupling table
+//
+// The ODE right-hand side (env.py:252-256) is evaluated through
+//     sum_j a_ij sin(th_j - th_i) = cos(th_i) (A sin th)_i - sin(th_i) (A cos th)_i,
+// i.e. one [N x N] x [N x 2] contraction per evaluation.  In GRID mode the coupling
+// a_ij = f(|dz|,|dx|,|dy|) of a regular neuron grid (utils.py:478-497, env.py:219-229) is a
+// 3-level block-Toeplitz operator: a thread owns the 8 oscillators of one grid line (fixed
+// z,x) and needs only the 8 table entries t[|yi-yj|] of block (|dz|,|dx|) for 128 FMAs, so
+// the whole operator lives in 2 KB of shared memory and no matrix is streamed from L2.
+// DENSE mode streams an arbitrary symmetric alpha from global memory (generic fallback).
+//
+// The integrator follows diffrax 0.7.0's Dopri5 + PIDController(I-only) + SaveAt(ts) as
+// the reference calls it (env.py:247-249, :260-271); see oracle/diffrax_restated.py for the
+// statement of those semantics this kernel is tested against.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dbsgym {
+
+constexpr int kRows = 8;           // oscillators per thread
+constexpr int kSampleBatch = 16;   // dense-output samples reduced per block barrier
+
+enum { MODE_STEP = 0, MODE_TRANSIENT = 1 };
+enum { STATUS_MAX_STEPS = 1, STATUS_NAN = 2, STATUS_SCHEDULE = 4 };
+
+struct StepParams {
+    int N, Np, B;
+    int GX, GZ;                    // GRID coupling: lines of 8 along y, GZ*GX lines
+    int weighted_rec;
+    int max_steps;
+    double k_over_n;
+    double rtol, atol, dt0, safety, fmin, fmax, tol_end;
+    double act_lo, act_hi;
+    const void* table;             // GRID: split-layout table (real)
+    const void* alpha;             // DENSE: alpha^T [Np][Np] (real)
+    void* phase; int32_t* wind;    // [B][Np]
+    const void* w0; const void* stim; const void* rec;
+    int mode;
+    const int32_t* env_ids; int n_launch;
+    // MODE_STEP
+    const float* actions; const int32_t* step_idx;
+    const int32_t* sched_nI; const int32_t* sched_nII;
+    const double* sched_offI; const double* sched_offII;
+    int maxI, maxII, n_sched;
+    double* lfp_true; double* lfp_rec; int32_t* n_samples; int smax; double* u_out;
+    // MODE_TRANSIENT
+    const double* ts; int n_ts; void* ring; int W; int32_t* head;
+    // bookkeeping
+    unsigned long long* counters;  // accepted, rejected, rhs evals
+    int32_t* status;
+};
+
+// ---- Dormand-Prince 5(4) coefficients (same values as oracle/diffrax_restated.py) ----------
+__constant__ double c_A[7][8] = {
+    {0, 0, 0, 0, 0, 0, 0, 0},
+    {1.0 / 5, 0, 0, 0, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0, 0, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0, 0, 0},
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84, 0, 0}};
+__constant__ double c_Berr[8] = {
+    35.0 / 384 - 1951.0 / 21600, 0, 500.0 / 1113 - 22642.0 / 50085, 125.0 / 192 - 451.0 / 720,
+    -2187.0 / 6784 + 12231.0 / 42400, 11.0 / 84 - 649.0 / 6300, -1.0 / 60, 0};
+__constant__ double c_Cmid[8] = {
+    0.5 * (6025192743.0 / 30085553152.0), 0, 0.5 * (51252292925.0 / 65400821598.0),
+    0.5 * (-2691868925.0 / 45128329728.0), 0.5 * (187940372067.0 / 1594534317056.0),
+    0.5 * (-1776094331.0 / 19743644256.0), 0.5 * (11237099.0 / 235043384.0), 0};
+
+constexpr double kTwoPi = 6.283185307179586476925286766559;
+
+// ---- small typed helpers ---------------------------------------------------------------
+template <typename real> struct Vec;
+template <> struct Vec<float>  { using T = float4;  static constexpr int n = 4; };
+template <> struct Vec<double> { using T = double2; static constexpr int n = 2; };
+
+__device__ __forceinline__ void unpack(const float4& v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ void unpack(const double2& v, double* o) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ float4 pack4(const float* o) { return make_float4(o[0], o[1], o[2], o[3]); }
+__device__ __forceinline__ double2 pack4(const double* o) { return make_double2(o[0], o[1]); }
+
+// load / store CNT contiguous reals (16-byte aligned) with 128-bit accesses
+template <int CNT, typename real>
+__device__ __forceinline__ void loadv(const real* __restrict__ p, real* o) {
+    using V = typename Vec<real>::T;
+    constexpr int n = Vec<real>::n;
+#pragma unroll
+    for (int q = 0; q < CNT / n; ++q) unpack(reinterpret_cast<const V*>(p)[q], o + q * n);
+}
+template <int CNT, typename real>
+__device__ __forceinline__ void storev(real* __restrict__ p, const real* o) {
+    using V = typename Vec<real>::T;
+    constexpr int n = Vec<real>::n;
+#pragma unroll
+    for (int q = 0; q < CNT / n; ++q) reinterpret_cast<V*>(p)[q] = pack4(o + q * n);
+}
+
+__device__ __forceinline__ float  fma_r(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_r(double a, double b, double c) { return fma(a, b, c); }
+
+// sin / cos of a phase.  fp64 follows the reference literally (theta = fmod(y, 2*pi),
+// env.py:253); fp32 phases are kept wrapped, so the library range reduction is exact enough.
+__device__ __forceinline__ void sincos_r(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ void sincos_r(double x, double* s, double* c) { sincos(fmod(x, kTwoPi), s, c); }
+__device__ __forceinline__ float  cos_r(float x) { return cosf(x); }
+__device__ __forceinline__ double cos_r(double x) { return cos(x); }
+
+// ---- coupling contraction, GRID mode --------------------------------------------------
+// Shared table layout: value for block c = dz*GX+dx and offset dy sits at
+//   T[((dy / n) * NC + c) * n + dy % n],   n = elements per 16 bytes,
+// so that a quarter warp (8 lanes, 8 different dx) reads 8 different 16-byte granules.
+template <typename real>
+__device__ __forceinline__ void couple_grid(const real* __restrict__ sc, const real* __restrict__ T,
+                                            int GZ, int GX, int zi, int xi,
+                                            real (&as)[kRows], real (&ac)[kRows]) {
+    using V = typename Vec<real>::T;
+    constexpr int n = Vec<real>::n;
+    const int NC = GZ * GX;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) { as[r] = real(0); ac[r] = real(0); }
+    for (int zj = 0; zj < GZ; ++zj) {
+        const int dz = zi > zj ? zi - zj : zj - zi;
+        const real* tz = T + dz * GX * n;
+        const real* bz = sc + zj * GX * (2 * kRows);
+#pragma unroll 2
+        for (int xj = 0; xj < GX; ++xj) {
+            const int dx = xi > xj ? xi - xj : xj - xi;
+            real t[kRows];
+#pragma unroll
+            for (int q = 0; q < kRows / n; ++q)
+                unpack(*reinterpret_cast<const V*>(tz + (q * NC + dx) * n), t + q * n);
+            real b[2 * kRows];
+            loadv<2 * kRows>(bz + xj * (2 * kRows), b);
+#pragma unroll
+            for (int yj = 0; yj < kRows; ++yj) {
+                const real s = b[2 * yj], c = b[2 * yj + 1];
+#pragma unroll
+                for (int yi = 0; yi < kRows; ++yi) {
+                    const real a = t[yi > yj ? yi - yj : yj - yi];
+                    as[yi] = fma_r(a, s, as[yi]);
+                    ac[yi] = fma_r(a, c, ac[yi]);
+                }
+            }
+        }
+    }
+}
+
+// ---- coupling contraction, DENSE mode (alpha^T streamed from global / L2) -----------------
+template <typename real>
+__device__ __forceinline__ void couple_dense(const real* __restrict__ sc, const real* __restrict__ alphaT,
+                                             int Np, int i0, real (&as)[kRows], real (&ac)[kRows]) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) { as[r] = real(0); ac[r] = real(0); }
+    const real* col = alphaT + i0;
+#pragma unroll 4
+    for (int j = 0; j < Np; ++j) {
+        real a[kRows];
+        loadv<kRows>(col + (size_t)j * Np, a);
+        const real s = sc[2 * j], c = sc[2 * j + 1];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            as[r] = fma_r(a[r], s, as[r]);
+            ac[r] = fma_r(a[r], c, ac[r]);
+        }
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// =========================================================================================
+// resident CTAs per SM the register allocation is tuned for (fp32: 128 regs/thread)
+template <typename real, int MAXT> struct MinBlocks {
+    static constexpr int v = (sizeof(real) == 4 && MAXT <= 128) ? (512 / MAXT) : 1;
+};
+
+template <typename real, bool DENSE, int MAXT>
+__global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(const StepParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
+    const int Np = p.Np;
+    const int tab = DENSE ? 0 : p.GZ * p.GX * kRows;
+
+    real* K = reinterpret_cast<real*>(smem_raw);          // [7][Np] stage derivatives f(y_s)
+    real* SC = K + 7 * Np;                                // [2][2*Np] interleaved (sin, cos)
+    real* T = SC + 4 * Np;                                // [tab]
+    double* part = reinterpret_cast<double*>(T + tab);    // [nwarps][kSampleBatch][2]
+    double* red = part + nwarps * kSampleBatch * 2;       // [nwarps]
+
+    const int slot = blockIdx.x;
+    if (slot >= p.n_launch) return;
+    const int env = p.env_ids ? p.env_ids[slot] : slot;
+    const size_t base = (size_t)env * Np;
+    const int i0 = tid * kRows;
+    const int zi = DENSE ? 0 : tid / p.GX, xi = DENSE ? 0 : tid % p.GX;
+
+    real y0[kRows], w0[kRows], stim[kRows], rc[kRows];
+    int wd[kRows];
+    loadv<kRows>(reinterpret_cast<const real*>(p.phase) + base + i0, y0);
+    loadv<kRows>(reinterpret_cast<const real*>(p.w0) + base + i0, w0);
+    loadv<kRows>(reinterpret_cast<const real*>(p.stim) + base + i0, stim);
+    if (p.weighted_rec) loadv<kRows>(reinterpret_cast<const real*>(p.rec) + base + i0, rc);
+    else {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) rc[r] = real(0);
+    }
+    if (sizeof(real) == 4) {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) wd[r] = p.wind[base + i0 + r];
+    } else {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) wd[r] = 0;
+    }
+    if (!DENSE) {
+        const real* tg = reinterpret_cast<const real*>(p.table);
+        for (int i = tid; i < tab; i += nt) T[i] = tg[i];
+    }
+    __syncthreads();
+
+    const real kn = real(p.k_over_n);
+    const real rtol = real(p.rtol), atol = real(p.atol);
+    const real two_pi_r = real(kTwoPi);
+    unsigned int n_acc = 0, n_rej = 0, n_rhs = 0;
+    int status = 0;
+    int pbuf = 0;
+
+    // ---- segment programme -------------------------------------------------------------
+    int nseg;
+    const double* seg_ts[2];
+    int seg_nts[2], seg_nrec[2], seg_from[2], seg_out[2];
+    real seg_amp[2];
+    if (p.mode == MODE_STEP) {
+        int k = p.step_idx[env];
+        if (k < 0 || k >= p.n_sched) { status |= STATUS_SCHEDULE; k = k < 0 ? 0 : p.n_sched - 1; }
+        const int nI = p.sched_nI[k], nII = p.sched_nII[k];
+        // env.py:389-393 rescale_action, env.py:419
+        const double a = (double)p.actions[env];
+        const double u = p.act_lo + ((p.act_hi - p.act_lo) * (a - (-1.0))) / (1.0 - (-1.0));
+        if (tid == 0) { p.u_out[env] = u; p.n_samples[env] = nI + nII - 1; }
+        nseg = 2;
+        seg_ts[0] = p.sched_offI + (size_t)k * p.maxI;   seg_nts[0] = nI;  seg_nrec[0] = nI;
+        seg_ts[1] = p.sched_offII + (size_t)k * p.maxII; seg_nts[1] = nII; seg_nrec[1] = nII - 1;
+        seg_from[0] = seg_from[1] = 0;
+        seg_out[0] = 0; seg_out[1] = nI;
+        seg_amp[0] = real(u); seg_amp[1] = real(0);
+    } else {
+        nseg = 1;
+        seg_ts[0] = p.ts; seg_nts[0] = p.n_ts; seg_nrec[0] = p.n_ts - 1;
+        seg_from[0] = seg_nrec[0] > p.W ? seg_nrec[0] - p.W : 0;
+        seg_out[0] = 0; seg_amp[0] = real(0);
+        seg_ts[1] = nullptr; seg_nts[1] = seg_nrec[1] = seg_from[1] = seg_out[1] = 0; seg_amp[1] = real(0);
+    }
+
+    for (int sg = 0; sg < nseg; ++sg) {
+        const double* __restrict__ ts = seg_ts[sg];
+        const int n_ts = seg_nts[sg], n_rec = seg_nrec[sg], rec_from = seg_from[sg], out_base = seg_out[sg];
+        const real amp = seg_amp[sg];
+        const double T_end = ts[n_ts - 1];
+        double t = 0.0;
+        double tnext = fmin(p.dt0, T_end);
+        int save_idx = 0;
+        int attempts = 0;
+        bool have_f0 = false;                 // each forward() starts without FSAL data (env.py:260)
+
+        while (t < T_end) {
+            if (++attempts > p.max_steps) { status |= STATUS_MAX_STEPS; break; }
+            const double dt_d = tnext - t;
+            const real dt = real(dt_d);
+            real d1[kRows];
+
+            // ---- stages: s = 0 is f(y0) (only when no FSAL value is carried) -----------
+#pragma unroll 1
+            for (int s = have_f0 ? 1 : 0; s < 7; ++s) {
+                real inc[kRows];
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) inc[r] = real(0);
+#pragma unroll 1
+                for (int j = 0; j < s; ++j) {
+                    const real a = real(c_A[s][j]);
+                    if (a != real(0)) {
+                        real kj[kRows];
+                        loadv<kRows>(K + j * Np + i0, kj);
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) inc[r] = fma_r(a, kj[r], inc[r]);
+                    }
+                }
+                real sv[kRows], cv[kRows];
+                {
+                    real scw[2 * kRows];
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) {
+                        inc[r] *= dt;
+                        sincos_r(y0[r] + inc[r], &sv[r], &cv[r]);
+                        scw[2 * r] = sv[r]; scw[2 * r + 1] = cv[r];
+                    }
+                    storev<2 * kRows>(SC + pbuf * 2 * Np + 2 * i0, scw);
+                }
+                if (s == 6) {
+#pragma unroll
+                    for (int r = 0; r < kRows; ++r) d1[r] = inc[r];
+                }
+                __syncthreads();
+                real as[kRows], ac[kRows];
+                if (DENSE) couple_dense<real>(SC + pbuf * 2 * Np, reinterpret_cast<const real*>(p.alpha), Np, i0, as, ac);
+                else couple_grid<real>(SC + pbuf * 2 * Np, T, p.GZ, p.GX, zi, xi, as, ac);
+                real ks[kRows];
+#pragma unroll
+                for (int r = 0; r < kRows; ++r)
+                    ks[r] = w0[r] + kn * (cv[r] * as[r] - sv[r] * ac[r]) + amp * stim[r];
+                storev<kRows>(K + s * Np + i0, ks);
+                pbuf ^= 1;
+                ++n_rhs;
+            }
+            have_f0 = true;
+
+            // ---- embedded error estimate and step-size controller ----------------------
+            double sq = 0.0;
+            {
+                real e[kRows];
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) e[r] = real(0);
+#pragma unroll 1
+                for (int j = 0; j < 7; ++j) {
+                    const real b = real(c_Berr[j]);
+                    if (b != real(0)) {
+                        real kj[kRows];
+                        loadv<kRows>(K + j * Np + i0, kj);
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) e[r] = fma_r(b, kj[r], e[r]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) {
+                    if (i0 + r < p.N) {
+                        const real yu0 = y0[r] + two_pi_r * real(wd[r]);
+                        const real yu1 = yu0 + d1[r];
+                        const real scale = atol + fmax(fabs(yu0), fabs(yu1)) * rtol;
+                        const double q = (double)((e[r] * dt) / scale);
+                        sq += q * q;
+                    }
+                }
+            }
+            sq = warp_sum(sq);
+            if (lane == 0) red[warp] = sq;
+            __syncthreads();
+            double tot = 0.0;
+            for (int w = 0; w < nwarps; ++w) tot += red[w];
+            const double err = sqrt(tot / (double)p.N);
+            if (!(err == err)) { status |= STATUS_NAN; break; }
+            const bool keep = err < 1.0;
+            double factor;
+            if (err == 0.0) factor = p.fmax;
+            else factor = fmin(fmax(p.safety * pow(1.0 / err, 0.2), keep ? 1.0 : p.fmin), p.fmax);
+            const double dt_next = dt_d * factor;
+
+            double t_new0;
+            if (keep) {
+                ++n_acc;
+                // ---- dense output (4th-order Dopri5 interpolant, increment form) -------
+                if (save_idx < n_ts && ts[save_idx] <= tnext) {
+                    real f0[kRows], pa[kRows], pb[kRows], pc[kRows];
+                    {
+                        real k0[kRows], k6[kRows], dm[kRows];
+                        loadv<kRows>(K + i0, k0);
+                        loadv<kRows>(K + 6 * Np + i0, k6);
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) dm[r] = real(0);
+#pragma unroll 1
+                        for (int j = 0; j < 7; ++j) {
+                            const real c = real(c_Cmid[j]);
+                            if (c != real(0)) {
+                                real kj[kRows];
+                                loadv<kRows>(K + j * Np + i0, kj);
+#pragma unroll
+                                for (int r = 0; r < kRows; ++r) dm[r] = fma_r(c, kj[r], dm[r]);
+                            }
+                        }
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) {
+                            const real f0r = k0[r] * dt, f1r = k6[r] * dt, dmr = dm[r] * dt, d = d1[r];
+                            f0[r] = f0r;
+                            pa[r] = real(2) * (f1r - f0r) - real(8) * d + real(16) * dmr;
+                            pb[r] = real(5) * f0r - real(3) * f1r + real(14) * d - real(32) * dmr;
+                            pc[r] = f1r - real(4) * f0r - real(5) * d + real(16) * dmr;
+                        }
+                    }
+                    while (save_idx < n_ts && ts[save_idx] <= tnext) {
+                        int nb = 0;
+                        while (nb < kSampleBatch && save_idx + nb < n_ts && ts[save_idx + nb] <= tnext) {
+                            const int idx = save_idx + nb;
+                            if (idx >= rec_from && idx < n_rec) {
+                                const double tsv = ts[idx];
+                                const bool at_end = (tsv == tnext);
+                                const real tau = (tnext == t) ? real(0) : real((tsv - t) / (tnext - t));
+                                real st = real(0), sr = real(0);
+#pragma unroll
+                                for (int r = 0; r < kRows; ++r) {
+                                    real inc = (((pa[r] * tau + pb[r]) * tau + pc[r]) * tau + f0[r]) * tau;
+                                    if (at_end) inc = d1[r];
+                                    const real c = cos_r(y0[r] + inc);
+                                    if (i0 + r < p.N) { st += c; sr = fma_r(c, rc[r], sr); }
+                                }
+                                const double wt = warp_sum((double)st), wr = warp_sum((double)sr);
+                                if (lane == 0) {
+                                    part[(warp * kSampleBatch + nb) * 2] = wt;
+                                    part[(warp * kSampleBatch + nb) * 2 + 1] = wr;
+                                }
+                            }
+                            ++nb;
+                        }
+                        __syncthreads();
+                        for (int q = tid; q < nb; q += nt) {
+                            const int idx = save_idx + q;
+                            if (idx >= rec_from && idx < n_rec) {
+                                double a_t = 0.0, a_r = 0.0;
+                                for (int w = 0; w < nwarps; ++w) {
+                                    a_t += part[(w * kSampleBatch + q) * 2];
+                                    a_r += part[(w * kSampleBatch + q) * 2 + 1];
+                                }
+                                a_t /= (double)p.N; a_r /= (double)p.N;
+                                if (!p.weighted_rec) a_r = a_t;
+                                if (p.mode == MODE_STEP) {
+                                    p.lfp_true[(size_t)env * p.smax + out_base + idx] = a_t;
+                                    p.lfp_rec[(size_t)env * p.smax + out_base + idx] = a_r;
+                                } else {
+                                    reinterpret_cast<real*>(p.ring)[(size_t)env * p.W + (idx - rec_from)] = real(a_r);
+                                }
+                            }
+                        }
+                        __syncthreads();
+                        save_idx += nb;
+                    }
+                }
+                // ---- accept: y0 <- y1, FSAL k1 <- k7 ------------------------------------
+                {
+                    real k6[kRows];
+                    loadv<kRows>(K + 6 * Np + i0, k6);
+                    storev<kRows>(K + i0, k6);
+                }
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) {
+                    real y1 = y0[r] + d1[r];
+                    if (sizeof(real) == 4) {
+                        // keep the fp32 phase wrapped: y = phase + 2*pi*wind (two-constant reduction)
+                        const float n = floorf((float)y1 * 0.15915494309189535f);
+                        if (n != 0.0f) {
+                            float yw = fmaf(-n, 6.2831854820251465f, (float)y1);
+                            yw = fmaf(-n, -1.7484555314695172e-07f, yw);
+                            y1 = real(yw);
+                            wd[r] += (int)n;
+                        }
+                    }
+                    y0[r] = y1;
+                }
+                t_new0 = tnext;
+            } else {
+                ++n_rej;
+                t_new0 = t;
+            }
+            const double new_t1 = t_new0 + dt_next;
+            t = fmin(t_new0, T_end);
+            tnext = (new_t1 > T_end - p.tol_end) ? (keep ? T_end : t + 0.5 * (T_end - t)) : new_t1;
+        }
+        if (status & (STATUS_MAX_STEPS | STATUS_NAN)) break;
+    }
+
+    // ---- write back ------------------------------------------------------------------------
+    storev<kRows>(reinterpret_cast<real*>(p.phase) + base + i0, y0);
+    if (sizeof(real) == 4) {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) p.wind[base + i0 + r] = wd[r];
+    }
+    if (tid == 0) {
+        if (p.mode == MODE_TRANSIENT) p.head[env] = 0;
+        atomicAdd(p.counters + 0, (unsigned long long)n_acc);
+        atomicAdd(p.counters + 1, (unsigned long long)n_rej);
+        atomicAdd(p.counters + 2, (unsigned long long)n_rhs);
+        if (status) atomicOr(p.status, status);
+    }
+}
+
+inline size_t step_smem_bytes(int Np, int tab, int nthreads, size_t real_bytes) {
+    const int nwarps = (nthreads + 31) / 32;
+    return (size_t)(11 * Np + tab) * real_bytes + (size_t)(nwarps * kSampleBatch * 2 + nwarps) * sizeof(double);
+}
+
+}  // namespace dbsgym

@@ -1,0 +1,234 @@
+"""Python face of the C-ABI step engine: one :class:`KuramotoEngine` == one ``DbsGymHandle`` == one GPU.
+
+All compute happens in ``csrc/libdbsgym.so`` (hand-written sm_100a kernels).  This module only
+marshals numpy / torch buffers into the plain-pointer calls of ``include/dbsgym.h``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from .schedule import StepSchedule
+
+_REWARD_KIND = {"bbpow_action": _capi.REWARD_BBPOW, "temp_const_action": _capi.REWARD_TEMP_CONST,
+                "bbpow_threth_action": _capi.REWARD_BBPOW_THRESH}
+
+
+def _ids(env_ids):
+    if env_ids is None:
+        return None
+    return np.ascontiguousarray(env_ids, dtype=np.int32)
+
+
+def _f64(a, shape=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and a.shape != shape:
+        raise ValueError(f"expected shape {shape}, got {a.shape}")
+    return a
+
+
+class KuramotoEngine:
+    def __init__(self, n_envs, n_osc, grid_size, window, K, *, precision="f32", coupling_table=None,
+                 alpha=None, device=0, max_step_samples=20, rtol=1e-5, atol=1e-5, dt0=0.05,
+                 action_bounds=(-5.0, 5.0), max_steps=4096):
+        if precision not in ("f32", "f64"):
+            raise ValueError("precision must be 'f32' or 'f64'")
+        if (coupling_table is None) == (alpha is None):
+            raise ValueError("give exactly one of coupling_table (GRID) or alpha (DENSE)")
+        self.lib = _capi.load()
+        self.n_envs, self.n_osc, self.window = int(n_envs), int(n_osc), int(window)
+        self.precision = precision
+        self.max_step_samples = int(max_step_samples)
+        self.coupling = "grid" if coupling_table is not None else "dense"
+        cfg = _capi.DbsGymConfig()
+        cfg.struct_bytes = C.sizeof(_capi.DbsGymConfig)
+        cfg.device, cfg.n_envs, cfg.n_osc = int(device), self.n_envs, self.n_osc
+        cfg.grid[0], cfg.grid[1], cfg.grid[2] = (int(g) for g in grid_size)
+        cfg.window = self.window
+        cfg.precision = _capi.F64 if precision == "f64" else _capi.F32
+        cfg.coupling = _capi.COUPLING_GRID if coupling_table is not None else _capi.COUPLING_DENSE
+        cfg.max_step_samples, cfg.max_steps = self.max_step_samples, int(max_steps)
+        cfg.K, cfg.rtol, cfg.atol, cfg.dt0 = float(K), float(rtol), float(atol), float(dt0)
+        cfg.safety, cfg.factor_min, cfg.factor_max = 0.9, 0.2, 10.0     # diffrax PIDController defaults
+        cfg.action_lo, cfg.action_hi = float(action_bounds[0]), float(action_bounds[1])
+        self._h = C.c_void_p()
+        rc = self.lib.dbsgym_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            msg = self.lib.dbsgym_last_error(None)
+            self._h = None
+            raise _capi.DbsGymError(f"dbsgym_create failed ({rc}): {msg.decode() if msg else '?'}")
+        self.device = int(device)
+        if coupling_table is not None:
+            t = _f64(coupling_table)
+            self._ck(self.lib.dbsgym_set_coupling_grid(self._h, _capi.ptr(t)))
+        else:
+            a = _f64(alpha, (self.n_osc, self.n_osc))
+            if not np.array_equal(a, a.T):
+                raise ValueError("dense coupling must be symmetric")
+            self._ck(self.lib.dbsgym_set_coupling_dense(self._h, _capi.ptr(a)))
+        self.schedule = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc):
+        _capi.check(self.lib, self._h, rc)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.dbsgym_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ set-up
+    def set_env_params(self, env_ids=None, w0=None, stim=None, rec=None, y0=None):
+        ids = _ids(env_ids)
+        n = self.n_envs if ids is None else len(ids)
+        shape = (n, self.n_osc)
+        w0, stim, rec, y0 = (_f64(v, shape) for v in (w0, stim, rec, y0))
+        self._ck(self.lib.dbsgym_set_env_params(self._h, _capi.ptr(ids), n, _capi.ptr(w0), _capi.ptr(stim),
+                                                _capi.ptr(rec), _capi.ptr(y0)))
+
+    def set_recording(self, weighted: bool):
+        self._ck(self.lib.dbsgym_set_recording(self._h, 1 if weighted else 0))
+
+    def set_schedule(self, sched: StepSchedule):
+        if sched.max_samples > self.max_step_samples:
+            raise ValueError("schedule needs more samples per step than max_step_samples")
+        nI = np.ascontiguousarray(sched.n_I, dtype=np.int32)
+        nII = np.ascontiguousarray(sched.n_II, dtype=np.int32)
+        oI, oII = _f64(sched.offs_I), _f64(sched.offs_II)
+        self._ck(self.lib.dbsgym_set_schedule(self._h, sched.n_steps, _capi.ptr(nI), _capi.ptr(nII),
+                                              _capi.ptr(oI), sched.max_I, _capi.ptr(oII), sched.max_II))
+        self.schedule = sched
+
+    def set_reward(self, reward_func, verbose_dt, lin_functional=None):
+        """reward_func: one of params_dict['reward_func'] (env.py:323-330)."""
+        from .utils import beta_bins, temp_const_functional, units2sec
+        spec = _capi.DbsGymRewardSpec()
+        spec.struct_bytes = C.sizeof(_capi.DbsGymRewardSpec)
+        spec.kind = _REWARD_KIND[reward_func]
+        dt_sec = units2sec(verbose_dt)
+        spec.bin_lo, spec.bin_hi = beta_bins(self.window, dt_sec, 12.5, 21)      # env.py:644
+        spec.power_scale, spec.temp_scale = 1e4, 1e3
+        spec.threshold, spec.threshold_penalty = 20.0, 5.0
+        spec.action_cost = 1.0 if reward_func == "bbpow_threth_action" else 1e-2
+        g = None
+        if reward_func == "temp_const_action":
+            g = _f64(lin_functional if lin_functional is not None
+                     else temp_const_functional(self.window, 1 / dt_sec, order=2), (self.window,))
+        self._ck(self.lib.dbsgym_set_reward(self._h, C.byref(spec), _capi.ptr(g)))
+
+    def set_episode(self, env_ids=None, step_idx=None, episode_len=None):
+        ids = _ids(env_ids)
+        n = self.n_envs if ids is None else len(ids)
+
+        def arr(v):
+            if v is None:
+                return None
+            return np.ascontiguousarray(np.broadcast_to(np.asarray(v, dtype=np.int32), (n,)))
+        s, e = arr(step_idx), arr(episode_len)
+        self._ck(self.lib.dbsgym_set_episode(self._h, _capi.ptr(ids), n, _capi.ptr(s), _capi.ptr(e)))
+
+    # ------------------------------------------------------------------ hot path
+    def transient(self, ts, env_ids=None, obs_dev_ptr=None, stream=None):
+        ids = _ids(env_ids)
+        n = self.n_envs if ids is None else len(ids)
+        offs = _f64(np.asarray(ts, dtype=np.float64) - float(ts[0]))
+        self._ck(self.lib.dbsgym_transient(self._h, _capi.ptr(ids), n, _capi.ptr(offs), len(offs),
+                                           obs_dev_ptr, stream))
+
+    def step_host(self, actions, obs=None, reward=None, done=None):
+        """One batched env step through host buffers (pinned numpy / torch memory is fastest)."""
+        a = np.ascontiguousarray(actions, dtype=np.float32).reshape(-1)
+        if a.shape[0] != self.n_envs:
+            raise ValueError(f"expected {self.n_envs} actions")
+        if obs is None:
+            obs = np.empty((self.n_envs, self.window), dtype=np.float32)
+        if reward is None:
+            reward = np.empty(self.n_envs, dtype=np.float32)
+        if done is None:
+            done = np.empty(self.n_envs, dtype=np.uint8)
+        self._ck(self.lib.dbsgym_step_host(self._h, _capi.ptr(a), _capi.ptr(obs), _capi.ptr(reward),
+                                           _capi.ptr(done)))
+        return obs, reward, done
+
+    def step_device(self, actions_ptr, obs_ptr=None, reward_ptr=None, done_ptr=None, stream=None):
+        """Asynchronous step on raw device pointers (e.g. ``tensor.data_ptr()``)."""
+        self._ck(self.lib.dbsgym_step(self._h, actions_ptr, obs_ptr, reward_ptr, done_ptr, stream))
+
+    def obs_host(self, out=None):
+        if out is None:
+            out = np.empty((self.n_envs, self.window), dtype=np.float32)
+        self._ck(self.lib.dbsgym_get_obs_host(self._h, _capi.ptr(out)))
+        return out
+
+    # ------------------------------------------------------------------ introspection
+    def lfp(self):
+        t = np.empty((self.n_envs, self.max_step_samples))
+        r = np.empty((self.n_envs, self.max_step_samples))
+        n = np.empty(self.n_envs, dtype=np.int32)
+        self._ck(self.lib.dbsgym_get_lfp(self._h, _capi.ptr(t), _capi.ptr(r), _capi.ptr(n)))
+        return t, r, n
+
+    def rewards(self):
+        r, u = np.empty(self.n_envs), np.empty(self.n_envs)
+        self._ck(self.lib.dbsgym_get_rewards(self._h, _capi.ptr(r), _capi.ptr(u)))
+        return r, u
+
+    def state(self, env_ids=None):
+        ids = _ids(env_ids)
+        n = self.n_envs if ids is None else len(ids)
+        y = np.empty((n, self.n_osc))
+        self._ck(self.lib.dbsgym_get_state(self._h, _capi.ptr(ids), n, _capi.ptr(y)))
+        return y
+
+    def window_values(self, env_ids=None):
+        ids = _ids(env_ids)
+        n = self.n_envs if ids is None else len(ids)
+        w = np.empty((n, self.window))
+        self._ck(self.lib.dbsgym_get_window(self._h, _capi.ptr(ids), n, _capi.ptr(w)))
+        return w
+
+    def set_window(self, window, env_ids=None):
+        ids = _ids(env_ids)
+        n = self.n_envs if ids is None else len(ids)
+        w = _f64(window, (n, self.window))
+        self._ck(self.lib.dbsgym_set_window(self._h, _capi.ptr(ids), n, _capi.ptr(w)))
+
+    def episode(self):
+        s = np.empty(self.n_envs, dtype=np.int32)
+        d = np.empty(self.n_envs, dtype=np.uint8)
+        self._ck(self.lib.dbsgym_get_episode(self._h, _capi.ptr(s), _capi.ptr(d)))
+        return s, d
+
+    def counters(self, reset=False):
+        a, r, f = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        st = C.c_int32()
+        self._ck(self.lib.dbsgym_counters(self._h, C.byref(a), C.byref(r), C.byref(f), C.byref(st),
+                                          1 if reset else 0))
+        return {"accepted": a.value, "rejected": r.value, "rhs_evals": f.value, "status": st.value}
+
+    def set_timing(self, enabled=True):
+        self._ck(self.lib.dbsgym_set_timing(self._h, 1 if enabled else 0))
+
+    def last_step_ms(self):
+        ms = (C.c_float * 2)()
+        self._ck(self.lib.dbsgym_last_step_ms(self._h, ms))
+        return float(ms[0]), float(ms[1])
+
+
+def measure_fp32_peak(device=0, ms_target=20.0):
+    lib = _capi.load()
+    out = C.c_double()
+    rc = lib.dbsgym_measure_fp32_peak(int(device), float(ms_target), C.byref(out))
+    if rc != 0:
+        raise _capi.DbsGymError(f"fp32 peak measurement failed ({rc})")
+    return out.value

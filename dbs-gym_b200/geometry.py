@@ -1,0 +1,147 @@
+"""Host-side geometry of the oscillator grid and the DBS electrode (numpy, vectorised).
+
+Mirrors what the reference computes with Python loops (paths relative to the reference):
+  utils.py:478-497  generate_neuron_grid_3D      -> :func:`neuron_grid`
+  utils.py:457-466  create_distance_matrix       -> :func:`distances_from` (only the rows used)
+  env.py:219-229    alpha = cos(D) | wavelet(D)  -> :func:`coupling_rows`, :func:`coupling_table`
+  env.py:61-171     SimpleDBS                    -> :class:`ElectrodeModel`
+  utils.py:30-57    create_directed_stim_masks   -> :func:`sector_masks`
+  utils.py:885-891  create_oscillation_locus     -> :func:`locus_mask`
+Index conventions are the reference's, quirks included.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+LINE = 8   # oscillators per grid line handled by one GPU thread (csrc/step_kernel.cuh kRows)
+
+
+def neuron_grid(gx, gy, gz, n_neurons, coord_modif=0.1):
+    """Integer grid points, row ``i = z*gx*gy + x*gy + y`` holding ``[x, y, z]``; first n rows."""
+    if n_neurons > gx * gy * gz:
+        raise ValueError("Number of neurons should be less than grid size.")
+    z, x, y = np.unravel_index(np.arange(n_neurons), (gz, gx, gy))
+    grid = np.column_stack([x, y, z]).astype(np.int64)
+    return grid * coord_modif, grid
+
+
+def distances_from(points, rows):
+    """Euclidean distance from ``points[rows]`` to every point: [len(rows), N]."""
+    pts = np.asarray(points, dtype=np.float64)
+    diff = pts[np.atleast_1d(rows)][:, None, :] - pts[None, :, :]
+    return np.sqrt(np.einsum("rnk,rnk->rn", diff, diff))
+
+
+def kernel_values(dist, spatial_kernel, wavelet_amp=1.0, wavelet_steepness=1.0):
+    if spatial_kernel == "cos":
+        return np.cos(dist)
+    if spatial_kernel == "wavelet":
+        s = wavelet_steepness
+        return wavelet_amp * (-s) * (12 * s ** 4 * dist ** 2 - 8 * s ** 2) * np.exp(-s * dist ** 2) / (2 * np.pi)
+    raise ValueError(f"Wrong distance matrix type: {spatial_kernel}")
+
+
+def coupling_rows(neur_coords, rows, spatial_kernel, wavelet_amp=1.0, wavelet_steepness=1.0):
+    return kernel_values(distances_from(neur_coords, rows), spatial_kernel, wavelet_amp, wavelet_steepness)
+
+
+def grid_structure(neur_grid, grid_size):
+    """Return (gx, gy, gz_used) when ``neur_grid`` is the un-shuffled regular grid in whole
+    z-planes with gy == LINE (the layout the GRID kernel needs), else None."""
+    g = np.asarray(neur_grid)
+    gx, gy, gz = (int(v) for v in grid_size)
+    n = g.shape[0]
+    if gy != LINE or n % (gx * gy) != 0 or n > gx * gy * gz:
+        return None
+    _, ref = neuron_grid(gx, gy, gz, n, 1.0)
+    if g.shape != ref.shape or not np.array_equal(g, ref):
+        return None
+    return gx, gy, n // (gx * gy)
+
+
+def coupling_table(neur_coords, neur_grid, grid_size, spatial_kernel, wavelet_amp=1.0,
+                   wavelet_steepness=1.0, check_rows=6, tol=1e-12):
+    """Block-Toeplitz table ``T[(dz*gx+dx)*gy + dy]`` of the coupling operator, or None when the
+    coordinates are not an affine image of the regular grid (then the DENSE path is used).
+    Verified against directly computed rows of alpha."""
+    st = grid_structure(neur_grid, grid_size)
+    if st is None:
+        return None
+    gx, gy, gzu = st
+    n = gx * gy * gzu
+    row0 = coupling_rows(neur_coords, [0], spatial_kernel, wavelet_amp, wavelet_steepness)[0]
+    table = row0.reshape(gzu, gx, gy).copy()            # offsets from neuron 0 == (dz, dx, dy)
+    rng = np.random.default_rng(12345)
+    rows = np.unique(np.concatenate([[0, n - 1], rng.integers(0, n, check_rows)]))
+    direct = coupling_rows(neur_coords, rows, spatial_kernel, wavelet_amp, wavelet_steepness)
+    g = np.asarray(neur_grid)
+    for r, a in zip(rows, direct):
+        d = np.abs(g - g[r])
+        if np.max(np.abs(table[d[:, 2], d[:, 0], d[:, 1]] - a)) > tol:
+            return None
+    return np.ascontiguousarray(table.reshape(-1))
+
+
+def contact_index(coord, grid_size):
+    # env.py:94,97 -- note grid_size[2]**2 and the axis order (x<->z permuted w.r.t. the grid rows)
+    return int(coord[0] * grid_size[2] ** 2 + coord[1] * grid_size[1] + coord[2])
+
+
+def sector_masks(neur_grid, center, forced_idx):
+    g = np.asarray(neur_grid, dtype=np.float64)
+    az = np.arctan2(g[:, 1] - center[1], g[:, 0] - center[0])
+    third = np.pi / 3
+    masks = [(az >= -third) & (az < third), (az >= third) & (az <= np.pi), (az >= -np.pi) & (az < -third)]
+    for m in masks:
+        m[forced_idx] = True
+    return masks
+
+
+def locus_mask(neur_grid, grid_size, locus_coord, locus_size):
+    d = distances_from(np.asarray(neur_grid) * locus_size, [contact_index(locus_coord, grid_size)])[0]
+    return np.where(1 - d < 0.0, 0.0, 1.0)
+
+
+class ElectrodeModel:
+    """Contact -> neuron index, stimulation and recording conductances (env.py:61-171)."""
+
+    def __init__(self, grid_size, neur_grid, conduct_modifier, elec_coords, rec_coords, amplitudes,
+                 directed_stimulation=False, prc_type="I", naive=False, verbose=False):
+        if len(amplitudes) != len(elec_coords):
+            raise AssertionError("Number of amplitudes is not equal to number of electrode coordinates!")
+        if prc_type not in ("I", "II", "Gaussian", "dummy"):
+            raise ValueError("Wrong type of PRC function!")
+        self.neur_grid = neur_grid
+        self.elec_idxs = [contact_index(c, grid_size) for c in elec_coords]
+        self.rec_idxs = [contact_index(c, grid_size) for c in rec_coords]
+        scaled = np.asarray(neur_grid) * conduct_modifier
+        n = scaled.shape[0]
+
+        def conductance_rows(idxs):
+            if naive:
+                return [np.ones(n) for _ in idxs]
+            d = distances_from(scaled, idxs) if len(idxs) else np.zeros((0, n))
+            return [np.where(1 - row < 0.0, 0, 1 - row) for row in d]
+
+        self.conductances = conductance_rows(self.elec_idxs)
+        if verbose and not directed_stimulation:
+            for c in self.conductances:
+                print(f"DBS affects {np.count_nonzero(c > 0.0)} neurons, min={round(c.min(), 3)} & max={round(c.max(), 3)}")
+        self.directional_masks_list = []
+        if directed_stimulation:
+            stale = self.elec_idxs[-1]            # env.py:128-131 passes the loop variable left over
+            self.directional_masks_list = [sector_masks(neur_grid, np.asarray(c), stale) for c in elec_coords]
+            self.directional_mask = [m[0] for m in self.directional_masks_list]
+            self.conductances = [c * m for c, m in zip(self.conductances, self.directional_mask)]
+        self.rec_conductances = conductance_rows(self.rec_idxs)
+
+    def stim_vector(self):
+        """What step() applies: only the first contact is driven by the 1-d action (env.py:419-423)."""
+        return np.asarray(self.conductances[0], dtype=np.float64)
+
+    def rec_vector(self):
+        """Sum over recording contacts (env.py:409-411 sums the per-contact means)."""
+        out = np.zeros(len(self.neur_grid))
+        for c in self.rec_conductances:
+            out = out + c
+        return out

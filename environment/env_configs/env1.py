@@ -1,0 +1,4 @@
+from dbsgym_b200.configs.env1 import *  # noqa: F401,F403
+from dbsgym_b200.configs.env1 import (checking, coord_modif, eval0, eval1, eval2, eval3, eval4,  # noqa: F401
+                                    eval_envs_list, grid_size, locus_center, locus_size, n_neurons,
+                                    params_dict_train)

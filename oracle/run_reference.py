@@ -31,9 +31,11 @@ def load_reference():
     for k in saved:
         del sys.modules[k]
     path0 = list(sys.path)
-    sys.path[:0] = [_SHIMS, REFERENCE_ROOT]
-    if _REPO not in sys.path:
-        sys.path.append(_REPO)
+    import oracle.diffrax_restated  # noqa: F401  (resolved through sys.modules once the path changes)
+    # the reference's `environment` has no __init__.py (namespace package): any regular package of
+    # that name -- ours -- would win regardless of path order, so hide those path entries.
+    sys.path[:] = [_SHIMS, REFERENCE_ROOT] + [
+        q for q in path0 if not os.path.isfile(os.path.join(q or ".", "environment", "__init__.py"))]
     try:
         env = importlib.import_module("environment.env")
         utils = importlib.import_module("environment.utils")

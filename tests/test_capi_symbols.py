@@ -1,0 +1,63 @@
+"""The C-ABI library loads here (no GPU) and exports every symbol include/dbsgym.h declares."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+from dbsgym_b200 import _capi
+
+
+@pytest.fixture(scope="module")
+def lib():
+    _capi.build()
+    return _capi.load()
+
+
+def test_header_and_exports_agree(lib):
+    hdr = open(os.path.join(ROOT, "include", "dbsgym.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|void|const char\*)\s+\*?(dbsgym_\w+)\s*\(", hdr, flags=re.M))
+    assert declared == set(_capi.EXPORTS), declared ^ set(_capi.EXPORTS)
+    raw = C.CDLL(_capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(raw, name), name
+    assert lib.dbsgym_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    # sizes are checked inside the library as well (struct_bytes); these guard the ctypes mirror
+    assert C.sizeof(_capi.DbsGymConfig) == 4 * 12 + 8 * 9
+    assert C.sizeof(_capi.DbsGymRewardSpec) == 4 * 4 + 8 * 5
+
+
+def test_create_rejects_bad_config_without_touching_a_gpu(lib):
+    cfg = _capi.DbsGymConfig()
+    h = C.c_void_p()
+    cfg.struct_bytes = 3
+    assert lib.dbsgym_create(C.byref(cfg), C.byref(h)) == -1
+    assert b"size mismatch" in lib.dbsgym_last_error(None)
+    cfg.struct_bytes = C.sizeof(_capi.DbsGymConfig)
+    assert lib.dbsgym_create(C.byref(cfg), C.byref(h)) == -1        # zero sizes
+    assert not h.value
+
+
+def test_no_cpu_fallback(lib):
+    """Without a CUDA device the engine must fail loudly, never compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from dbsgym_b200.engine import KuramotoEngine
+    import numpy as np
+    with pytest.raises(_capi.DbsGymError, match="no CPU path|no CUDA|CUDA"):
+        KuramotoEngine(1, 512, [8, 8, 8], 2340, 0.52, coupling_table=np.ones(512))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "dbs-gym_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+                assert "/root/reference" not in src, f

@@ -1,0 +1,166 @@
+"""Product HOST code (dbs-gym_b200/*.py) against the reference-generated fixtures.  CPU only.
+Integer / index results must be bit-exact; float vectors agree to rounding."""
+import re
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, make_params
+from dbsgym_b200 import geometry, utils
+from dbsgym_b200.host_env import HostEnvState, generate_perturbations
+from dbsgym_b200.schedule import StepSchedule, transient_grid
+
+
+def test_grid_order_and_contact_indices_bit_exact():
+    g = load_golden("geometry.npz")
+    coords, grid = geometry.neuron_grid(8, 8, 8, 512, 0.1)
+    assert np.array_equal(grid, g["neur_grid"])
+    assert geometry.contact_index([4, 3, 4], [8, 8, 8]) == 284 and grid[284].tolist() == [3, 4, 4]
+    for n, gs in ((256, (8, 8, 8)), (100, (5, 5, 5))):
+        assert np.array_equal(utils.generate_neuron_grid_3D(*gs, n, 0.1)[1], g[f"grid_{n}_{gs[0]}"])
+    with pytest.raises(ValueError):
+        utils.generate_neuron_grid_3D(2, 2, 2, 9)
+
+
+def test_electrode_model_matches_reference():
+    g = load_golden("geometry.npz")
+    _, grid = geometry.neuron_grid(8, 8, 8, 512, 0.1)
+    for i in range(5):
+        el = geometry.ElectrodeModel([8, 8, 8], grid, float(g[f"case{i}_cm"]), g[f"case{i}_elec"].tolist(),
+                                     g[f"case{i}_rec"].tolist(), [0.], bool(g[f"case{i}_directed"]), "dummy")
+        assert el.elec_idxs == g[f"case{i}_elec_idx"].tolist()
+        assert el.rec_idxs == g[f"case{i}_rec_idx"].tolist()
+        # which neurons are stimulated / recorded is an index set: bit-exact
+        assert np.array_equal(el.conductances[0] > 0, g[f"case{i}_cond"] > 0)
+        assert np.array_equal(el.rec_conductances[0] > 0, g[f"case{i}_rec_cond"] > 0)
+        np.testing.assert_allclose(el.conductances[0], g[f"case{i}_cond"], rtol=0, atol=5e-16)
+        np.testing.assert_allclose(el.rec_conductances[0], g[f"case{i}_rec_cond"], rtol=0, atol=5e-16)
+        if g[f"case{i}_directed"]:
+            assert np.array_equal(np.array(el.directional_masks_list[0]), g[f"case{i}_masks"])
+    # notebook known answer (explore_kuramoto_dynamics.ipynb cell 3): 512 neurons, min 0.307, max 1.0
+    el = geometry.ElectrodeModel([8, 8, 8], grid, 0.1, [[4, 3, 4]], [[1, 1, 1]], [0.])
+    c = el.conductances[0]
+    assert (np.count_nonzero(c > 0), round(c.min(), 3), round(c.max(), 3)) == (512, 0.307, 1.0)
+    with pytest.raises(AssertionError):
+        geometry.ElectrodeModel([8, 8, 8], grid, 0.1, [[4, 3, 4]], [[1, 1, 1]], [0., 1.])
+    with pytest.raises(ValueError):
+        geometry.ElectrodeModel([8, 8, 8], grid, 0.1, [[4, 3, 4]], [[1, 1, 1]], [0.], prc_type="bogus")
+
+
+def test_locus_mask_and_w0_generation_bit_exact():
+    g = load_golden("geometry.npz")
+    _, grid = geometry.neuron_grid(8, 8, 8, 512, 0.1)
+    assert np.array_equal(geometry.locus_mask(grid, [8, 8, 8], [4, 4, 4], 0.55), g["locus_mask_444_055"])
+    s = load_golden("step_env0.npz")
+    d = make_params("env0", 10)
+    for k in ("w0", "w0_without_locus", "locus_without_w0", "locus_mask"):
+        assert np.array_equal(d[k], s[k]), k
+
+
+def test_coupling_table_expands_to_dense_alpha():
+    g = load_golden("geometry.npz")
+    coords, grid = geometry.neuron_grid(8, 8, 8, 512, 0.1)
+    for kern, amp, st in (("cos", 1.0, 0.6), ("wavelet", 1.3, 0.6)):
+        t = geometry.coupling_table(coords, grid, [8, 8, 8], kern, amp, st)
+        assert t is not None and t.shape == (512,)
+        alpha = geometry.coupling_rows(coords, np.arange(512), kern, amp, st)
+        d = np.abs(grid[:, None, :] - grid[None, :, :])
+        expanded = t.reshape(8, 8, 8)[d[..., 2], d[..., 0], d[..., 1]]
+        assert np.max(np.abs(expanded - alpha)) < 1e-13
+    np.testing.assert_allclose(geometry.coupling_rows(coords, [0, 284], "cos"),
+                               np.stack([g["alpha_row0"], g["alpha_row284"]]), rtol=0, atol=3e-16)
+    # half grid (first 256 rows) is still whole z-planes; shuffled or non-8 lines are not
+    c2, g2 = geometry.neuron_grid(8, 8, 8, 256, 0.1)
+    assert geometry.coupling_table(c2, g2, [8, 8, 8], "cos") is not None
+    perm = np.random.default_rng(0).permutation(512)
+    assert geometry.coupling_table(coords[perm], grid[perm], [8, 8, 8], "cos") is None
+    c3, g3 = geometry.neuron_grid(5, 5, 5, 100, 0.1)
+    assert geometry.coupling_table(c3, g3, [5, 5, 5], "cos") is None
+    with pytest.raises(ValueError):
+        geometry.kernel_values(np.zeros(3), "gauss")
+
+
+def test_schedule_bit_exact():
+    g = load_golden("schedule.npz")
+    tt = transient_grid(200., 0.05)
+    assert len(tt) == 4000 and tt[-1] == 199.95000000000002
+    for tag, n in (("train", 5555), ("eval", 1111)):
+        s = StepSchedule(n, tt[-1], 0.15, 0.75, 0.05)
+        assert np.array_equal(s.n_I, g[f"nI_{tag}"]) and np.array_equal(s.n_II, g[f"nII_{tag}"])
+        assert s.t_after[-1] == g[f"t_final_{tag}"]
+        assert np.array_equal(s.t_after[::100], g[f"t_cur_every100_{tag}"])
+        assert s.max_samples == 19 and (s.max_I, s.max_II) == (4, 16)
+    st = load_golden("step_env0.npz")
+    s = StepSchedule(70, tt[-1], 0.15, 0.75, 0.05)
+    assert np.array_equal(s.n_I, st["nI"]) and np.array_equal(s.n_II, st["nII"])
+    for k in range(70):
+        assert np.array_equal(s.offs_I[k, :s.n_I[k]], st["offs_I"][k, :s.n_I[k]])
+        assert np.array_equal(s.offs_II[k, :s.n_II[k]], st["offs_II"][k, :s.n_II[k]])
+    assert np.array_equal(s.t_after, st["t_cur"])
+
+
+def test_host_rewards_and_linear_functional():
+    g = load_golden("rewards.npz")
+    lo, hi = utils.beta_bins(2340, 0.0005, 12.5, 21)
+    assert (lo, hi) == (15, 24)
+    gvec = utils.temp_const_functional(2340, 2000.0, order=2)
+    for w, u, r, bb in zip(g["windows"], g["u"], g["rewards"], g["bbpow"]):
+        assert utils.calc_beta_band_power(w, 0.0005, 12.5, 21) == pytest.approx(bb, rel=1e-12)
+        # R2 as a dot product with the precomputed functional == filtfilt pipeline of the reference
+        r2 = -1e3 * float(gvec @ w) ** 2 - 1e-2 * abs(u)
+        assert r2 == pytest.approx(r[1], rel=1e-7, abs=1e-9)
+        # circular-shift invariance used by the observation kernel
+        assert utils.calc_beta_band_power(np.roll(w, 777), 0.0005, 12.5, 21) == pytest.approx(bb, rel=1e-11)
+
+
+def test_host_env_state_replays_env2_events_and_rng_order():
+    g = load_golden("env2_events.npz")
+    d = make_params("env2", 21, plasticity_drift_freq=10 ** 6, transient_state_len=117.5,
+                    total_episode_len=9., spatial_var_freq=4)
+    h = HostEnvState(d)
+    assert h.total_episode_counts == 10 and h.observe_wind_idxs == 2340
+    for r in range(len(g["elec"])):
+        s = h.begin_episode()
+        assert h.reset_count == r
+        assert np.array_equal(np.array(h.elec_coords)[0], g["elec"][r]), r
+        assert np.array_equal(np.array(h.rec_coords)[0], g["rec"][r]), r
+        assert h.encapsulation_coeff == g["encaps"][r]
+        assert np.array_equal(s.w0, g["w0"][r])
+        assert np.array_equal(s.y0, g["init_state"][r])
+        assert h.elec_drift_episode == g["elec_drift_episode"][r]
+        assert h.elec_encaps_episode == g["encaps_episode"][r]
+
+
+def test_host_env_state_errors_like_reference():
+    with pytest.raises(AssertionError):
+        HostEnvState(make_params("env2", 3))                        # env.py:368
+    h = HostEnvState(make_params("env2", 3), compat_env2=True)      # explicit compatibility switch
+    h.begin_episode()
+    for bad in (dict(reward_func="nope"), dict(recording_kernel="nope"), dict(transient_state_len=100.)):
+        with pytest.raises(ValueError):
+            HostEnvState(make_params("env0", 3, **bad))
+
+
+def test_generate_perturbations_matches_definition():
+    v = np.random.default_rng(1).uniform(0.1, 2, 64)
+    np.random.seed(4)
+    w = generate_perturbations(v, M=5, step_scale=0.02)
+    np.random.seed(4)
+    exp = [v.copy()]
+    for _ in range(5):
+        exp.append(exp[-1] + 0.02 * np.std(v, ddof=1) * np.random.randn(64))
+    assert np.array_equal(w, np.array(exp)) and w.shape == (6, 64)
+
+
+def test_configs_expose_reference_names():
+    import environment.env_configs.env0 as e0
+    import environment.env_configs.env1 as e1
+    import environment.env_configs.env2 as e2
+    import data.configs.env2 as d2
+    for m in (e0, e1, e2, d2):
+        assert len(m.eval_envs_list) == 5 and m.n_neurons == 512 and m.grid_size == [8, 8, 8]
+        assert m.params_dict_train["observe_wind_counts"] == 130
+    assert len(e1.stim_rec_locus_coordinates) == 15 and len(e2.stim_rec_locus_coordinates) == 40
+    assert e0.params_dict_train["recording_kernel"] == "naive" and e1.params_dict_train["recording_kernel"] == "gaussian"
+    assert e2.params_dict_train["temporal_drift"] and e2.eval0["electrode_drift_freq"] == 2
+    assert e0.eval0["total_episode_len"] == 1000 and e0.eval2["rand_seed"] == 20
