@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""Throughput benchmark of the DBS-Gym environment step (BASELINE.json metric: env-steps/s and
+oscillator-updates/s at 1/2/4/8 B200 beside the reference's CPU step()).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU step() (oracle port)
+
+Workload (``config.workload``): BASELINE.json configs[2] -- env1 (distance-weighted recording,
+spatial electrode variation), N = 512 oscillators, 4096 environments PER GPU (weak scaling), one
+uniform(-1,1) action per environment per step, synthetic inputs (w0 drawn by the reference's own
+sampler, N(pi,0.6) initial phases, 200-unit transient).  One "step" = one batched VecEnv step =
+4096 env-steps per GPU.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import copy
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_OSC = 512
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+# ------------------------------------------------------------------------------------------
+def build_params(n_envs, seed0=10, distinct_w0=32, cfg_name="env1", reward="bbpow_action"):
+    """params_dict list the way aDBS_RL/train_aDBS_RL.py:95-112 builds one, with per-env seeds.
+    The w0 sampler (polyfit + quad) costs ~5 ms, so `distinct_w0` frequency sets are cycled."""
+    import importlib
+    from dbsgym_b200 import utils
+    cfg = importlib.import_module(f"dbsgym_b200.configs.{cfg_name}")
+    base = cfg.params_dict_train
+    sets = []
+    for s in range(distinct_w0):
+        np.random.seed(seed0 + s)
+        sets.append(utils.generate_w0_with_locus(
+            cfg.n_neurons, cfg.grid_size, cfg.coord_modif, locus_center=base["locus_center"],
+            locus_size=base["locus_size"], wmuL=base["wmuL"], wsdL=base["wsdL"], show=False))
+    dicts = []
+    for e in range(n_envs):
+        w0, nc, ng, w0t, wl, lm = sets[e % distinct_w0]
+        d = copy.deepcopy(base)
+        d.update(w0=w0.copy(), w0_without_locus=w0t.copy(), locus_without_w0=wl, locus_mask=lm,
+                 neur_coords=sets[0][1], neur_grid=sets[0][2], reward_func=reward, verbose=0,
+                 rand_seed=seed0 + e)
+        dicts.append(d)
+    return dicts
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:  # noqa: BLE001
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_port_steps_per_sec(n_steps, rhs_form, dtype, seed=10):
+    """The oracle port of the reference step(), one process, one env (env1)."""
+    from oracle import kuramoto_oracle as ko
+    d = build_params(1, seed0=seed, distinct_w0=1)[0]
+    env = ko.OracleEnv(d, rhs_form="matvec", dtype=dtype)         # transient with the fast RHS (not timed)
+    env.kuramoto.rhs_form = rhs_form
+    acts = np.random.default_rng(0).uniform(-1, 1, n_steps).astype(np.float32)
+    env.step(np.array([acts[0]], dtype=np.float32))
+    t0 = time.perf_counter()
+    for a in acts:
+        env.step(np.array([a], dtype=np.float32))
+    return n_steps / (time.perf_counter() - t0)
+
+
+def _ref_worker(args):
+    seed, n_steps, barrier_t = args
+    from oracle import kuramoto_oracle as ko
+    d = build_params(1, seed0=seed, distinct_w0=1)[0]
+    env = ko.OracleEnv(d, rhs_form="matvec", dtype=np.float32)
+    env.kuramoto.rhs_form = "as_written"
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(len(n_steps)):
+        t0 = time.perf_counter()
+        for _ in range(n_steps[k]):
+            env.step(rng.uniform(-1, 1, 1).astype(np.float32))
+        out.append(time.perf_counter() - t0)
+    return out
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU formulation of step() (N x N sine RHS as written at
+    environment/env.py:252-256, float32 like the JAX default) through the oracle port, one
+    environment per process on every host core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_step = 2                                              # env-steps per process per bench step
+    plan = [per_step] * (args.warmup + args.steps)
+    with mp.get_context("spawn").Pool(cores) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_ref_worker, [(100 + i, plan, 0.0) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    per_proc = np.array(res)                                  # [cores, warmup+steps] seconds
+    timed = per_proc[:, args.warmup:].sum(axis=1).max()       # slowest process over the timed steps
+    total_env_steps = cores * per_step * args.steps
+    value = total_env_steps / timed
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * timed / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "env1 N=512, one env per host process, reference RHS as written (N x N sin), float32",
+                   "env_steps_per_bench_step": cores * per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{cores} processes x {per_step} env-steps x {args.steps} steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "oscillator_updates_per_sec": value * N_OSC * 5,
+        "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from dbsgym_b200.engine import measure_fp32_peak
+    from dbsgym_b200.sharding import gather_episode_stats
+    from dbsgym_b200.vec_env import BatchedKuramotoVecEnv
+
+    B = args.envs
+    t_setup = time.perf_counter()
+    dicts = build_params(B, seed0=10 + rank * B)
+    for d in dicts:
+        d["precision"] = args.precision
+    venv = BatchedKuramotoVecEnv(dicts, device=local_rank)
+    venv.reset()
+    eng = venv.core.engine
+    setup_s = time.perf_counter() - t_setup
+    K, Wm = args.steps, args.warmup
+    rng = np.random.default_rng(1234 + rank)
+    actions = rng.uniform(-1, 1, (Wm + K, B)).astype(np.float32)
+
+    # ---------- (1) device-resident timing: inputs already in HBM, CUDA events per step ----------
+    act_dev = torch.from_numpy(actions).to(dev)
+    obs_dev = torch.empty((B, venv.core.window), dtype=torch.float32, device=dev)
+    rew_dev = torch.empty(B, dtype=torch.float32, device=dev)
+    done_dev = torch.empty(B, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # 256 MB > 126 MB L2
+    stream = torch.cuda.current_stream()
+    eng.set_timing(True)
+    eng.set_episode(None, step_idx=0, episode_len=2 ** 30)          # no resets inside the timed region
+    eng.counters(reset=True)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    clocks = ClockSampler(local_rank)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    kern_ms = []
+    for i in range(Wm):
+        flush.zero_()
+        eng.step_device(act_dev[i].data_ptr(), obs_dev.data_ptr(), rew_dev.data_ptr(), done_dev.data_ptr(),
+                        stream.cuda_stream)
+    sync_all()
+    c0 = eng.counters(reset=True)
+    clocks.start()
+    t_wall = time.perf_counter()
+    for i in range(K):
+        flush.zero_()                                               # L2 flush between timed iterations
+        ev[i][0].record(stream)
+        eng.step_device(act_dev[Wm + i].data_ptr(), obs_dev.data_ptr(), rew_dev.data_ptr(),
+                        done_dev.data_ptr(), stream.cuda_stream)
+        ev[i][1].record(stream)
+        if i % 8 == 7 or i == K - 1:
+            torch.cuda.synchronize()
+            kern_ms.append(eng.last_step_ms())
+    sync_all()
+    wall_dev = time.perf_counter() - t_wall
+    clk = clocks.stop()
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    dev_time_s = float(step_ms.sum()) * 1e-3
+    counters = eng.counters()
+
+    # ---------- (2) end to end through the public VecEnv API with host buffers ----------
+    eng.set_timing(False)
+    for i in range(Wm):
+        venv.step_async(actions[i].reshape(B, 1)); venv.step_wait()
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(K):
+        venv.step_async(actions[Wm + i].reshape(B, 1))
+        obs, rew, done, infos = venv.step_wait()
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    # the raw C-ABI host call (no Python list building)
+    t0 = time.perf_counter()
+    for i in range(K):
+        venv.core.step(actions[Wm + i])
+    sync_all()
+    capi_s = time.perf_counter() - t0
+
+    # ---------- max over ranks ----------
+    times = torch.tensor([dev_time_s, e2e_s, capi_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+        # NCCL is used only off the step path: gather per-env episode statistics
+        stats = gather_episode_stats(np.stack([rew.astype(np.float64), done.astype(np.float64)], axis=1),
+                                     B * world, rank, world, device=dev)
+        assert stats.shape == (B * world, 2)
+    dev_time_s, e2e_s, capi_s = (float(v) for v in times.cpu())
+
+    if rank == 0:
+        total_env_steps = B * world * K
+        value = total_env_steps / dev_time_s
+        rhs_per_env_step = counters["rhs_evals"] / (B * K)
+        substeps_per_env_step = (counters["accepted"] + counters["rejected"]) / (B * K)
+        # algorithmic work of the step kernel: R * 4 N^2 (coupling contraction) + ~700 N
+        flop_per_env_step = rhs_per_env_step * 4 * N_OSC * N_OSC + 700 * N_OSC
+        k_step = float(np.mean([m[0] for m in kern_ms])) * 1e-3
+        k_obs = float(np.mean([m[1] for m in kern_ms])) * 1e-3
+        peaks, peak_src = measured_peaks()
+        fp32_peak = measure_fp32_peak(local_rank)
+        achieved_tf = flop_per_env_step * B / k_step / 1e12
+        obs_bytes = B * (2 * 2340 * 4 + 19 * 8 + 32)                 # ring read + obs write + samples
+        cpu_n = 12
+        cpu_as_written = cpu_port_steps_per_sec(cpu_n, "as_written", np.float32)
+        cpu_matvec = cpu_port_steps_per_sec(200, "matvec", np.float64)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+            "ms_per_step": 1e3 * dev_time_s / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if args.precision == "f32" else "f64", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: env1, N=512 oscillators, 4096 envs per GPU, uniform(-1,1) actions",
+                       "envs_per_gpu": B, "global_envs": B * world, "precision": args.precision,
+                       "coupling": eng.coupling, "l2": "256 MB buffer written between timed iterations (flush)",
+                       "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks"},
+            "oscillator_updates_per_sec": value * N_OSC * substeps_per_env_step,
+            "oscillator_rhs_evals_per_sec": value * N_OSC * rhs_per_env_step,
+            "rk_substeps_per_env_step": substeps_per_env_step, "rhs_evals_per_env_step": rhs_per_env_step,
+            "solver_status": counters["status"],
+            "e2e": {"value": B * world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 4,
+                    "d2h_bytes_per_step": B * (2340 * 4 + 4 + 1), "api": "BatchedKuramotoVecEnv.step_async/step_wait (numpy in/out, pinned)",
+                    "c_abi_step_host": B * world * K / capi_s},
+            "gpu_launches": 2 * K,
+            "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": None,
+                         "kernel": "step_kernel<float,GRID>", "kernel_ms": k_step * 1e3,
+                         "flop_per_env_step": flop_per_env_step,
+                         "peak_source": "FFMA micro-benchmark run in this process (dbsgym_measure_fp32_peak); nominal 74.4"},
+            "roofline_obs": {"bound": "hbm", "achieved": obs_bytes / k_obs / 1e9, "peak": peaks.get("hbm_gbs"),
+                             "unit": "GB/s", "frac": obs_bytes / k_obs / 1e9 / peaks.get("hbm_gbs", 1.0),
+                             "kernel": "obs_kernel", "kernel_ms": k_obs * 1e3, "peak_source": peak_src},
+            "cpu_baseline": {"value": cpu_as_written, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": f"{cpu_n} env1 steps, one env, oracle port with the reference's N x N sine RHS in float32",
+                             "matvec_f64_value": cpu_matvec, "published_reference": "17-20 it/s (notebook tqdm, unknown CPU)"},
+            "clocks": clk, "setup_s": setup_s, "wall_s_device_loop": wall_dev,
+        }
+        print(json.dumps(line), flush=True)
+    venv.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -76,7 +76,13 @@ class BatchedKuramoto:
         self.electrodes = [None] * B
         self.w0_model = [None] * B
         self._pin = []
-        self.obs_buf, t = _pinned((B, self.window), np.float32); self._pin.append(t)
+        # two observation buffers used alternately: the array returned by step() stays valid until
+        # the step after the next one, so callers need not copy 9.4 KB x B per step
+        self._obs_bufs = []
+        for _ in range(2):
+            a, t = _pinned((B, self.window), np.float32); self._pin.append(t); self._obs_bufs.append(a)
+        self._obs_flip = 0
+        self.obs_buf = self._obs_bufs[0]
         self.rew_buf, t = _pinned((B,), np.float32); self._pin.append(t)
         self.done_buf, t = _pinned((B,), np.uint8); self._pin.append(t)
         self.act_buf, t = _pinned((B,), np.float32); self._pin.append(t)
@@ -110,9 +116,11 @@ class BatchedKuramoto:
         return self.engine.obs_host(self.obs_buf)
 
     def step(self, actions):
-        """Advance every environment by one step.  Returns host views (obs [B,W] f32, reward [B] f32,
-        done [B] bool) that are overwritten by the next call."""
+        """Advance every environment by one step.  Returns host views: obs [B,W] f32 (valid until the
+        step after the next), reward [B] f32 and done [B] bool (overwritten by the next call)."""
         self.act_buf[:] = np.asarray(actions, dtype=np.float32).reshape(self.num_envs)
+        self._obs_flip ^= 1
+        self.obs_buf = self._obs_bufs[self._obs_flip]
         self.engine.step_host(self.act_buf, self.obs_buf, self.rew_buf, self.done_buf)
         self.current_step += 1
         self._lfp_cache = None

@@ -75,7 +75,7 @@ class BatchedKuramotoVecEnv(VecEnvBase):
 
     def step_wait(self):
         obs, rew, done = self.core.step(self._actions)
-        obs = obs.reshape(self.num_envs, 1, -1).copy()
+        obs = obs.reshape(self.num_envs, 1, -1)       # view of a double-buffered pinned array (no 38 MB copy)
         rew = rew.copy()
         done = done.copy()
         self._ep_ret += rew
@@ -89,8 +89,11 @@ class BatchedKuramotoVecEnv(VecEnvBase):
                     infos[i]["episode"] = {"r": round(float(self._ep_ret[i]), 6), "l": int(self._ep_len[i]),
                                            "t": round(time.time() - self._t0, 6)}
             self.core.reset_envs(finished)            # index order == sequential DummyVecEnv order
-            fresh = self.core.observations()
-            obs[finished, 0, :] = fresh[finished]
+            term = {i: infos[i]["terminal_observation"] for i in finished}
+            fresh = self.core.observations()          # writes the whole current obs buffer
+            obs = fresh.reshape(self.num_envs, 1, -1)
+            for i in finished:
+                infos[i]["terminal_observation"] = term[i]
             self._ep_ret[finished] = 0
             self._ep_len[finished] = 0
         return obs, rew, done, infos

@@ -1,0 +1,178 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (ctypes -> libdbsgym.so),
+against the reference-generated golden fixtures and the CPU oracle.
+
+Tolerances (BASELINE.json north_star): per-step phases within 1e-9 rad in fp64 mode and 1e-5 rad in
+fp32 mode, teacher-forced (every step restarted from the reference state); integer results
+(sample counts, schedule, done flags, RK step / RHS counters) bit-exact.
+"""
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, make_params
+
+pytestmark = pytest.mark.gpu
+
+PHASE_TOL = {"f64": 1e-9, "f32": 1e-5}
+LFP_TOL = {"f64": 1e-11, "f32": 2e-6}
+
+
+def _engine_from_params(d, B, precision, force_dense=False):
+    from dbsgym_b200.batched import BatchedKuramoto
+    return BatchedKuramoto([copy.deepcopy(d) for _ in range(B)], precision=precision, force_dense=force_dense)
+
+
+def _teacher_forced(core, g, precision, n_steps, reward_tol_rel):
+    eng = core.engine
+    B = core.num_envs
+    K = min(n_steps, len(g["actions"]))
+    y_prev = g["y_after_transient"]
+    win_prev = g["window0"]
+    for k in range(K):
+        eng.set_env_params(None, y0=np.tile(y_prev, (B, 1)))
+        eng.set_window(np.tile(win_prev, (B, 1)))
+        eng.set_episode(None, step_idx=k)
+        obs, rew, done = core.step(np.full(B, g["actions"][k], dtype=np.float32))
+        y = eng.state()
+        t, r, n = eng.lfp()
+        s = g["nI"][k] + g["nII"][k] - 1
+        assert np.all(n == s)                                        # schedule / sample count: bit-exact
+        err = np.max(np.abs(y - g["y_end"][k][None, :]))
+        assert err < PHASE_TOL[precision], (k, err)
+        assert np.max(np.abs(t[:, :s] - g["lfp_true"][k, :s])) < LFP_TOL[precision]
+        assert np.max(np.abs(r[:, :s] - g["lfp_rec"][k, :s])) < LFP_TOL[precision]
+        rr, uu = eng.rewards()
+        assert np.all(uu == g["u"][k])                               # action rescale: exact in float64
+        np.testing.assert_allclose(rr, g["reward"][k], rtol=reward_tol_rel, atol=1e-7)
+        assert not done.any()
+        y_prev = g["y_end"][k]
+        # window after this step (reference): previous window shifted by s + new recorded samples
+        win_prev = np.concatenate([win_prev, g["lfp_rec"][k, :s]])[-2340:]
+        np.testing.assert_allclose(obs[0], win_prev.astype(np.float32), rtol=0,
+                                   atol=1e-7 if precision == "f64" else 3e-6)
+    c = eng.counters()
+    assert c["status"] == 0
+    return c
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_env0_teacher_forced_per_step_parity(precision):
+    g = load_golden("step_env0.npz")
+    d = make_params("env0", 10)
+    core = _engine_from_params(d, 2, precision)
+    core.engine.counters(reset=True)
+    c = _teacher_forced(core, g, precision, 70, 1e-9 if precision == "f64" else 2e-4)
+    # exactly 5 accepted sub-steps and 32 RHS evaluations per step, no rejections
+    assert (c["accepted"], c["rejected"], c["rhs_evals"]) == (2 * 70 * 5, 0, 2 * 70 * 32)
+    core.close()
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_env1_weighted_recording_parity(precision):
+    g = load_golden("step_env1.npz")
+    d = make_params("env1", 11)
+    core = _engine_from_params(d, 1, precision)
+    _teacher_forced(core, g, precision, 12, 1e-9 if precision == "f64" else 2e-4)
+    core.close()
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_env1_directed_stimulation_and_temp_const_reward(precision):
+    g = load_golden("step_env1_directed.npz")
+    d = make_params("env1", 12, reward="temp_const_action", directed_stimulation=True,
+                    elec_coords=[[5, 2, 3]], rec_coords=[[3, 5, 1]])
+    core = _engine_from_params(d, 1, precision)
+    _teacher_forced(core, g, precision, 6, 1e-7 if precision == "f64" else 5e-3)
+    core.close()
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_reset_transient_matches_reference(precision):
+    """Device transient (env.py:605-612): adaptive steps WITH rejections, 4000 dense-output samples."""
+    g = load_golden("step_env0.npz")
+    d = make_params("env0", 10)
+    core = _engine_from_params(d, 1, precision)          # constructor == reference __init__ -> reset()
+    assert np.array_equal(core.hosts[0].init_state, g["init_state"])
+    c = core.engine.counters()
+    keys = list(g["stats_keys"])
+    ref = dict(zip(keys, g["reset_stats"]))
+    assert c["status"] == 0
+    if precision == "f64":
+        assert (c["accepted"], c["rejected"], c["rhs_evals"]) == (
+            ref["num_accepted_steps"], ref["num_rejected_steps"], ref["num_rhs_evals"])
+    y = core.engine.state()[0]
+    w = core.engine.window_values()[0]
+    tol_y, tol_w = (1e-7, 1e-9) if precision == "f64" else (5e-3, 5e-4)
+    assert np.max(np.abs(y - g["y_after_transient"])) < tol_y
+    assert np.max(np.abs(w - g["window0"])) < tol_w
+    obs = core.observations()
+    np.testing.assert_allclose(obs[0], g["window0"].astype(np.float32), rtol=0, atol=tol_w + 1e-7)
+    core.close()
+
+
+def test_free_running_episode_matches_oracle_f64():
+    """No teacher forcing: 40 consecutive steps from the transient on, against the CPU oracle."""
+    from oracle import kuramoto_oracle as ko
+    d = make_params("env1", 7)
+    orc = ko.OracleEnv(copy.deepcopy(d))
+    core = _engine_from_params(d, 1, "f64")
+    acts = np.random.default_rng(3).uniform(-1, 1, 40).astype(np.float32)
+    for k, a in enumerate(acts):
+        o_ref, r_ref, d_ref, _, _ = orc.step(np.array([a], dtype=np.float32))
+        obs, rew, done = core.step(np.array([a]))
+        assert np.max(np.abs(core.engine.state()[0] - orc.sol_state[-1])) < 1e-7, k
+        assert abs(core.engine.rewards()[0][0] - r_ref) < 1e-6 * max(1.0, abs(r_ref))
+        np.testing.assert_allclose(obs[0], o_ref[0], rtol=0, atol=1e-6)
+    core.close()
+
+
+def test_dense_fallback_agrees_with_grid_kernel():
+    g = load_golden("step_env0.npz")
+    d = make_params("env0", 10)
+    outs = []
+    for dense in (False, True):
+        core = _engine_from_params(d, 1, "f64", force_dense=dense)
+        assert core.engine.coupling == ("dense" if dense else "grid")
+        core.engine.set_env_params(None, y0=g["y_after_transient"][None, :])
+        core.step(np.array([g["actions"][0]]))
+        outs.append(core.engine.state()[0])
+        core.close()
+    assert np.max(np.abs(outs[0] - g["y_end"][0])) < 1e-9
+    assert np.max(np.abs(outs[1] - g["y_end"][0])) < 1e-9
+
+
+def test_shuffled_grid_uses_dense_path_and_matches_oracle():
+    """Coordinates that are not the regular grid (utils.py:490 shuffle=True) -> DENSE coupling."""
+    from oracle import kuramoto_oracle as ko
+    d = make_params("env0", 4, transient_state_len=118.0)
+    perm = np.random.default_rng(1).permutation(512)
+    d["neur_coords"] = d["neur_coords"][perm]
+    d["neur_grid"] = d["neur_grid"][perm]
+    orc = ko.OracleEnv(copy.deepcopy(d))
+    core = _engine_from_params(d, 1, "f64")
+    assert core.engine.coupling == "dense"
+    assert np.max(np.abs(core.engine.state()[0] - orc.sol_state[-1])) < 1e-7
+    o_ref, r_ref, *_ = orc.step(np.array([0.4], dtype=np.float32))
+    obs, rew, done = core.step(np.array([0.4]))
+    assert np.max(np.abs(core.engine.state()[0] - orc.sol_state[-1])) < 1e-7
+    core.close()
+
+
+def test_half_grid_256_oscillators():
+    """N = 256 (first four z-planes, BASELINE config 5's smallest point) on the GRID kernel."""
+    from oracle import kuramoto_oracle as ko
+    import dbsgym_b200.utils as U
+    np.random.seed(2)
+    w0, nc, ng, w0t, wl, lm = U.generate_w0_with_locus(256, [8, 8, 8], 0.1, [2, 4, 4], 0.55, 17, 1, show=False)
+    d = make_params("env0", 2, transient_state_len=118.0, num_oscillators=256, elec_coords=[[2, 3, 4]])
+    d.update(w0=w0, w0_without_locus=w0t, locus_without_w0=wl, locus_mask=lm, neur_coords=nc, neur_grid=ng)
+    orc = ko.OracleEnv(copy.deepcopy(d))
+    core = _engine_from_params(d, 1, "f64")
+    assert core.engine.coupling == "grid"
+    assert np.max(np.abs(core.engine.state()[0] - orc.sol_state[-1])) < 1e-7
+    orc.step(np.array([-0.6], dtype=np.float32))
+    core.step(np.array([-0.6]))
+    assert np.max(np.abs(core.engine.state()[0] - orc.sol_state[-1])) < 1e-7
+    np.testing.assert_allclose(core.theta_mean(0), orc.theta_mean, rtol=0, atol=1e-10)
+    core.close()

@@ -1,0 +1,164 @@
+"""Boundary tests on the GPU: the gymnasium env, the batched VecEnv and size-independent properties
+at BASELINE.json's full batch size (4096 environments)."""
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, make_params
+
+pytestmark = pytest.mark.gpu
+
+
+def test_spatial_kuramoto_gym_api_matches_reference_golden():
+    from environment.env import SpatialKuramoto
+    g = load_golden("step_env0.npz")
+    env = SpatialKuramoto(make_params("env0", 10, precision="f64"))
+    assert env.observation_space.shape == (1, 2340) and env.action_space.shape == (1,)
+    assert env.total_episode_counts == 5555 and env.observe_wind_idxs == 2340
+    assert env.current_time == g["t_after_transient"]
+    np.testing.assert_allclose(env.theta_state[0], g["window0"], rtol=0, atol=1e-9)
+    for k in range(5):
+        obs, r, done, trunc, info = env.step(np.array([g["actions"][k]], dtype=np.float32))
+        assert obs.shape == (1, 2340) and obs.dtype == np.float32
+        assert isinstance(r, float) and done is False and trunc is False and info == {}
+        s = g["nI"][k] + g["nII"][k] - 1
+        assert env.theta_mean.shape == (s,) and env.current_time == g["t_cur"][k]
+        assert env.u == [g["u"][k]]
+        np.testing.assert_allclose(env.theta_mean, g["lfp_true"][k, :s], rtol=0, atol=1e-8)
+        np.testing.assert_allclose(env.sol_state[-1], g["y_end"][k], rtol=0, atol=1e-7)
+        assert r == pytest.approx(g["reward"][k], rel=1e-6)
+    assert env.kuramoto.dbs.conductances[0].shape == (512,) and env.kuramoto.neur_grid.shape == (512, 3)
+    obs, info = env.reset()
+    assert obs.shape == (1, 2340) and info == {} and env.current_step == 0 and env.reset_count == 1
+    env.close()
+
+
+def test_constructor_errors_match_reference():
+    from environment.env import SpatialKuramoto
+    with pytest.raises(ValueError, match="Wrong reward function"):
+        SpatialKuramoto(make_params("env0", 1, reward="x"))
+    with pytest.raises(ValueError, match="Wrong recording kernel"):
+        SpatialKuramoto(make_params("env0", 1, recording_kernel="x"))
+    with pytest.raises(ValueError, match="Transient state"):
+        SpatialKuramoto(make_params("env0", 1, transient_state_len=50.))
+    with pytest.raises(AssertionError):
+        SpatialKuramoto(make_params("env0", 1, electrode_amps=[0., 0.]))
+
+
+def test_vecenv_semantics_autoreset_monitor_and_rng_order():
+    """Short episodes: done flags, terminal_observation, Monitor-style episode info, and the
+    sequential-DummyVecEnv RNG order of the initial phases across environments and resets."""
+    from dbsgym_b200.vec_env import BatchedKuramotoVecEnv
+    from dbsgym_b200.host_env import HostEnvState
+    B = 3
+    dicts = [make_params("env1", 20 + e, transient_state_len=118.0, total_episode_len=3.6, rand_seed=50 + e,
+                         precision="f64") for e in range(B)]
+    # expected draws: replay the host logic of a sequential DummyVecEnv([...]) with the same dicts
+    ref_hosts, ref_y0 = [], []
+    for d in copy.deepcopy(dicts):
+        h = HostEnvState(d); ref_hosts.append(h); ref_y0.append(h.begin_episode().y0)
+    venv = BatchedKuramotoVecEnv(dicts)
+    assert venv.num_envs == B and venv.observation_space.shape == (1, 2340)
+    for i in range(B):
+        assert np.array_equal(venv.core.hosts[i].init_state, ref_y0[i])
+    # both share the global np.random stream: replay the expected draws, rewind, then let the VecEnv draw
+    st = np.random.get_state()
+    ref_y0 = [h.begin_episode().y0 for h in ref_hosts]
+    np.random.set_state(st)
+    obs = venv.reset()                                   # SB3 calls reset() after construction
+    for i in range(B):
+        assert np.array_equal(venv.core.hosts[i].init_state, ref_y0[i])
+    assert obs.shape == (B, 1, 2340) and obs.dtype == np.float32
+    total = venv.get_attr("total_episode_counts")[0]
+    assert total == 4
+    rets = np.zeros(B)
+    for k in range(total):
+        if k == total - 1:                               # the auto-reset inside this step_wait draws, in index order
+            st = np.random.get_state()
+            ref_y0 = [h.begin_episode().y0 for h in ref_hosts]
+            np.random.set_state(st)
+        venv.step_async(np.full((B, 1), 0.5, dtype=np.float32))
+        obs2, rew, done, infos = venv.step_wait()
+        rets += rew
+        assert rew.shape == (B,) and done.dtype == np.bool_ and len(infos) == B
+        tm = venv.get_attr("theta_mean")
+        if k < total - 1:
+            assert not done.any() and "terminal_observation" not in infos[0]
+            assert len(tm[0]) in (17, 18, 19) and venv.get_attr("u")[1] == [2.5]
+    assert done.all()
+    for i in range(B):
+        assert infos[i]["TimeLimit.truncated"] is False
+        assert infos[i]["terminal_observation"].shape == (1, 2340)
+        assert infos[i]["episode"]["l"] == total
+        assert infos[i]["episode"]["r"] == pytest.approx(rets[i], rel=1e-5)
+        assert np.array_equal(venv.core.hosts[i].init_state, ref_y0[i])
+        assert not np.array_equal(infos[i]["terminal_observation"], obs2[i])      # obs is the fresh episode's
+    assert venv.get_attr("current_step", [0, 2])[1] == 0
+    assert venv.get_attr("params_dict")[1] is dicts[1]
+    assert venv.env_is_wrapped(type("Monitor", (), {})) == [True] * B
+    venv.close()
+
+
+def test_new_returns_vecenv_when_num_envs_gt_1():
+    from environment.env import SpatialKuramoto
+    from dbsgym_b200.vec_env import BatchedKuramotoVecEnv
+    d = make_params("env0", 3, transient_state_len=118.0, num_envs=4)
+    v = SpatialKuramoto(d)
+    assert isinstance(v, BatchedKuramotoVecEnv) and v.num_envs == 4
+    v.close()
+
+
+@pytest.mark.parametrize("precision", ["f32"])
+def test_full_size_batch_properties(precision):
+    """B = 4096 (BASELINE config 2/3 size): size-independent properties.
+    * environments with identical inputs give bit-identical outputs wherever they sit in the batch
+    * every environment agrees with the same environment run alone (B = 1)
+    * the observation window slides by exactly the step's sample count
+    * counters: 5 accepted sub-steps and 32 RHS evaluations per env-step."""
+    from dbsgym_b200.batched import BatchedKuramoto
+    B = 4096
+    g = load_golden("step_env0.npz")
+    d = make_params("env0", 10)
+    core = BatchedKuramoto([d] * 1, precision=precision)
+    # build the 4096 batch directly on the engine (host reset of 4096 envs is not what is tested here)
+    from dbsgym_b200.engine import KuramotoEngine
+    from dbsgym_b200.geometry import coupling_table
+    table = coupling_table(d["neur_coords"], d["neur_grid"], d["grid_size"], "cos")
+    eng = KuramotoEngine(B, 512, [8, 8, 8], 2340, d["K"], precision=precision, coupling_table=table)
+    eng.set_schedule(core.schedule)
+    eng.set_reward("bbpow_action", 0.05)
+    rng = np.random.default_rng(0)
+    kinds = 8                                             # 8 distinct environments, tiled
+    w0 = np.abs(rng.normal(1.0, 0.4, (kinds, 512))) + 0.05
+    y0 = rng.normal(np.pi, 0.6, (kinds, 512)) + 40.0
+    stim = np.tile(g["stim_cond"][0], (kinds, 1))
+    win = rng.uniform(-0.3, 0.3, (kinds, 2340))
+    acts = rng.uniform(-1, 1, kinds).astype(np.float32)
+    rep = B // kinds
+    tile = lambda a: np.tile(a, (rep,) + (1,) * (a.ndim - 1))     # noqa: E731
+    eng.set_env_params(None, w0=tile(w0), stim=tile(stim), rec=tile(stim), y0=tile(y0))
+    eng.set_window(tile(win))
+    eng.set_episode(None, step_idx=0, episode_len=3)
+    eng.counters(reset=True)
+    obs, rew, done = eng.step_host(tile(acts))
+    y = eng.state()
+    for k in range(kinds):
+        assert np.all(y[k::kinds] == y[k]) and np.all(obs[k::kinds] == obs[k]) and np.all(rew[k::kinds] == rew[k])
+    c = eng.counters()
+    assert (c["accepted"], c["rejected"], c["rhs_evals"], c["status"]) == (B * 5, 0, B * 32, 0)
+    s = int(core.schedule.n_I[0] + core.schedule.n_II[0] - 1)
+    assert np.all(eng.lfp()[2] == s)
+    assert np.allclose(obs[:kinds, :2340 - s], win[:, s:].astype(np.float32), atol=1e-7)
+    # same environments alone
+    solo = KuramotoEngine(kinds, 512, [8, 8, 8], 2340, d["K"], precision=precision, coupling_table=table)
+    solo.set_schedule(core.schedule); solo.set_reward("bbpow_action", 0.05)
+    solo.set_env_params(None, w0=w0, stim=stim, rec=stim, y0=y0); solo.set_window(win)
+    solo.set_episode(None, step_idx=0, episode_len=3)
+    o1, r1, d1 = solo.step_host(acts)
+    assert np.array_equal(solo.state(), y[:kinds]) and np.array_equal(o1, obs[:kinds]) and np.array_equal(r1, rew[:kinds])
+    # done after episode_len steps
+    assert not done.any()
+    eng.step_host(tile(acts)); _, _, done = eng.step_host(tile(acts))
+    assert done.all() and np.all(eng.episode()[0] == 3)
+    eng.close(); solo.close(); core.close()
