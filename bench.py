@@ -221,6 +221,7 @@ def run_gpu_arm(args):
             torch.cuda.synchronize()
 
     clocks = ClockSampler(local_rank)
+    clocks.start()                                                  # nvidia-smi needs ~1 s to start sampling
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     kern_ms = []
     for i in range(Wm):
@@ -229,7 +230,7 @@ def run_gpu_arm(args):
                         stream.cuda_stream)
     sync_all()
     c0 = eng.counters(reset=True)
-    clocks.start()
+    n_clk0 = len(clocks.rows)
     t_wall = time.perf_counter()
     for i in range(K):
         flush.zero_()                                               # L2 flush between timed iterations
@@ -242,7 +243,7 @@ def run_gpu_arm(args):
             kern_ms.append(eng.last_step_ms())
     sync_all()
     wall_dev = time.perf_counter() - t_wall
-    clk = clocks.stop()
+    n_clk1 = len(clocks.rows)
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     dev_time_s = float(step_ms.sum()) * 1e-3
     counters = eng.counters()
@@ -264,6 +265,8 @@ def run_gpu_arm(args):
         venv.core.step(actions[Wm + i])
     sync_all()
     capi_s = time.perf_counter() - t0
+    clk = clocks.stop()
+    clk["samples_in_device_loop"] = n_clk1 - n_clk0
 
     # ---------- max over ranks ----------
     times = torch.tensor([dev_time_s, e2e_s, capi_s], dtype=torch.float64, device=dev)
@@ -285,7 +288,9 @@ def run_gpu_arm(args):
         k_step = float(np.mean([m[0] for m in kern_ms])) * 1e-3
         k_obs = float(np.mean([m[1] for m in kern_ms])) * 1e-3
         peaks, peak_src = measured_peaks()
-        fp32_peak = measure_fp32_peak(local_rank)
+        peak_ffma = measure_fp32_peak(local_rank, packed=False)
+        peak_ffma2 = measure_fp32_peak(local_rank, packed=True)
+        fp32_peak = max(peak_ffma, peak_ffma2)
         achieved_tf = flop_per_env_step * B / k_step / 1e12
         obs_bytes = B * (2 * 2340 * 4 + 19 * 8 + 32)                 # ring read + obs write + samples
         cpu_n = 12
@@ -311,7 +316,8 @@ def run_gpu_arm(args):
                          "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": None,
                          "kernel": "step_kernel<float,GRID>", "kernel_ms": k_step * 1e3,
                          "flop_per_env_step": flop_per_env_step,
-                         "peak_source": "FFMA micro-benchmark run in this process (dbsgym_measure_fp32_peak); nominal 74.4"},
+                         "peak_source": "best of the FFMA and FFMA2 micro-benchmarks run in this process (dbsgym_measure_fp32_peak_mode); nominal 74.4",
+                         "peak_ffma": peak_ffma, "peak_ffma2": peak_ffma2},
             "roofline_obs": {"bound": "hbm", "achieved": obs_bytes / k_obs / 1e9, "peak": peaks.get("hbm_gbs"),
                              "unit": "GB/s", "frac": obs_bytes / k_obs / 1e9 / peaks.get("hbm_gbs", 1.0),
                              "kernel": "obs_kernel", "kernel_ms": k_obs * 1e3, "peak_source": peak_src},
@@ -329,7 +335,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")

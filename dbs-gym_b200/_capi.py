@@ -27,7 +27,7 @@ EXPORTS = [
     "dbsgym_transient", "dbsgym_step", "dbsgym_step_host", "dbsgym_get_obs_host",
     "dbsgym_get_lfp", "dbsgym_get_rewards", "dbsgym_get_state", "dbsgym_get_window",
     "dbsgym_set_window", "dbsgym_get_episode", "dbsgym_counters", "dbsgym_last_step_ms",
-    "dbsgym_set_timing", "dbsgym_measure_fp32_peak",
+    "dbsgym_set_timing", "dbsgym_measure_fp32_peak", "dbsgym_measure_fp32_peak_mode",
 ]
 
 
@@ -120,6 +120,7 @@ def load():
         "dbsgym_last_step_ms": (C.c_int, [vp, f32p]),
         "dbsgym_set_timing": (C.c_int, [vp, C.c_int32]),
         "dbsgym_measure_fp32_peak": (C.c_int, [C.c_int32, C.c_double, f64p]),
+        "dbsgym_measure_fp32_peak_mode": (C.c_int, [C.c_int32, C.c_double, C.c_int32, f64p]),
     }
     assert sorted(P) == sorted(EXPORTS)
     for name, (res, args) in P.items():

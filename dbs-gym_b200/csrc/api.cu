@@ -128,6 +128,21 @@ __global__ void fma_peak_kernel(float* out, int iters, float a, float b) {
     if (s == 123.456f) out[0] = s;
 }
 
+__global__ void fma2_peak_kernel(float* out, int iters, float a, float b) {
+    float2 v[kChains];
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) v[c] = make_float2((float)(threadIdx.x + c), (float)c);
+    const float2 bb = make_float2(b, b * 0.5f);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int c = 0; c < kChains; ++c) v[c] = __ffma2_rn(make_float2(a, a), v[c], bb);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) s += v[c].x + v[c].y;
+    if (s == 123.456f) out[0] = s;
+}
+
 int upload_ids(DbsGymHandle* h, const int32_t* env_ids, int n, const int32_t** dev) {
     *dev = nullptr;
     if (!env_ids) return DBSGYM_OK;
@@ -265,6 +280,10 @@ int check_ready(DbsGymHandle* h, bool need_step) {
         if (!h->have_reward) return fail(h, DBSGYM_ESTATE, "reward not set (dbsgym_set_reward)");
     }
     return DBSGYM_OK;
+}
+
+cudaStream_t pick_stream(DbsGymHandle* h, void* stream) {
+    return stream == DBSGYM_OWN_STREAM ? h->stream : static_cast<cudaStream_t>(stream);
 }
 
 int step_impl(DbsGymHandle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
@@ -573,7 +592,7 @@ int dbsgym_transient(DbsGymHandle* h, const int32_t* env_ids, int32_t n, const d
     if (ts_offsets[0] != 0.0) return fail(h, DBSGYM_EINVAL, "ts_offsets must start at 0");
     if (n_ts - 1 < h->W) return fail(h, DBSGYM_EINVAL, "transient gives %d samples < window %d (env.py:303-304)", n_ts - 1, h->W);
     CU(h, cudaSetDevice(h->cfg.device));
-    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    cudaStream_t s = pick_stream(h, stream);
     const int32_t* ids = nullptr;
     rc = upload_ids(h, env_ids, n, &ids);
     if (rc) return rc;
@@ -601,7 +620,7 @@ int dbsgym_step(DbsGymHandle* h, const float* actions_dev, float* obs_dev, float
     if (rc) return rc;
     if (!actions_dev) return fail(h, DBSGYM_EINVAL, "actions_dev is null");
     CU(h, cudaSetDevice(h->cfg.device));
-    cudaStream_t s = stream ? static_cast<cudaStream_t>(stream) : h->stream;
+    cudaStream_t s = pick_stream(h, stream);
     return step_impl(h, actions_dev, obs_dev, reward_dev, done_dev, s);
 }
 
@@ -767,6 +786,18 @@ int dbsgym_last_step_ms(DbsGymHandle* h, float* ms2) {
 }
 
 int dbsgym_measure_fp32_peak(int32_t device, double ms_target, double* tflops) {
+    // best of the scalar FFMA chain and the packed FFMA2 chain
+    if (!tflops) return DBSGYM_EINVAL;
+    double a = 0.0, b = 0.0;
+    int rc = dbsgym_measure_fp32_peak_mode(device, ms_target, 0, &a);
+    if (rc) return rc;
+    rc = dbsgym_measure_fp32_peak_mode(device, ms_target, 1, &b);
+    if (rc) return rc;
+    *tflops = a > b ? a : b;
+    return DBSGYM_OK;
+}
+
+int dbsgym_measure_fp32_peak_mode(int32_t device, double ms_target, int32_t packed, double* tflops) {
     if (!tflops) return DBSGYM_EINVAL;
     DbsGymHandle* h = nullptr;
     CU(h, cudaSetDevice(device));
@@ -782,13 +813,14 @@ int dbsgym_measure_fp32_peak(int32_t device, double ms_target, double* tflops) {
     double best = 0.0;
     for (int rep = 0; rep < 8; ++rep) {
         cudaEventRecord(a);
-        fma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001f, 1e-9f);
+        if (packed) fma2_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001f, 1e-9f);
+        else fma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001f, 1e-9f);
         cudaEventRecord(b);
         cudaError_t e = cudaEventSynchronize(b);
         if (e != cudaSuccess) { cudaFree(out); return fail(h, DBSGYM_ECUDA, "peak kernel: %s", cudaGetErrorString(e)); }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, a, b);
-        const double fl = 2.0 * kChains * (double)iters * blocks * threads;
+        const double fl = (packed ? 4.0 : 2.0) * kChains * (double)iters * blocks * threads;
         const double tf = fl / (ms * 1e-3) / 1e12;
         if (rep >= 2 && tf > best) best = tf;
         if (ms < ms_target && iters < (1 << 24)) iters *= 2;

@@ -16,6 +16,14 @@ _REWARD_KIND = {"bbpow_action": _capi.REWARD_BBPOW, "temp_const_action": _capi.R
                 "bbpow_threth_action": _capi.REWARD_BBPOW_THRESH}
 
 
+_OWN_STREAM = C.c_void_p(-1)          # DBSGYM_OWN_STREAM
+
+
+def _stream(stream):
+    """None -> the handle's private stream; otherwise a raw cudaStream_t (0 = legacy default stream)."""
+    return _OWN_STREAM if stream is None else C.c_void_p(int(stream))
+
+
 def _ids(env_ids):
     if env_ids is None:
         return None
@@ -143,7 +151,7 @@ class KuramotoEngine:
         n = self.n_envs if ids is None else len(ids)
         offs = _f64(np.asarray(ts, dtype=np.float64) - float(ts[0]))
         self._ck(self.lib.dbsgym_transient(self._h, _capi.ptr(ids), n, _capi.ptr(offs), len(offs),
-                                           obs_dev_ptr, stream))
+                                           obs_dev_ptr, _stream(stream)))
 
     def step_host(self, actions, obs=None, reward=None, done=None):
         """One batched env step through host buffers (pinned numpy / torch memory is fastest)."""
@@ -162,7 +170,7 @@ class KuramotoEngine:
 
     def step_device(self, actions_ptr, obs_ptr=None, reward_ptr=None, done_ptr=None, stream=None):
         """Asynchronous step on raw device pointers (e.g. ``tensor.data_ptr()``)."""
-        self._ck(self.lib.dbsgym_step(self._h, actions_ptr, obs_ptr, reward_ptr, done_ptr, stream))
+        self._ck(self.lib.dbsgym_step(self._h, actions_ptr, obs_ptr, reward_ptr, done_ptr, _stream(stream)))
 
     def obs_host(self, out=None):
         if out is None:
@@ -225,10 +233,14 @@ class KuramotoEngine:
         return float(ms[0]), float(ms[1])
 
 
-def measure_fp32_peak(device=0, ms_target=20.0):
+def measure_fp32_peak(device=0, ms_target=20.0, packed=None):
+    """FP32 FMA peak in TFLOP/s: packed=None best of both, False scalar FFMA, True FFMA2."""
     lib = _capi.load()
     out = C.c_double()
-    rc = lib.dbsgym_measure_fp32_peak(int(device), float(ms_target), C.byref(out))
+    if packed is None:
+        rc = lib.dbsgym_measure_fp32_peak(int(device), float(ms_target), C.byref(out))
+    else:
+        rc = lib.dbsgym_measure_fp32_peak_mode(int(device), float(ms_target), 1 if packed else 0, C.byref(out))
     if rc != 0:
         raise _capi.DbsGymError(f"fp32 peak measurement failed ({rc})")
     return out.value

@@ -22,7 +22,10 @@
  *   - per-oscillator parameter vectors always cross the boundary as float64, whatever the
  *     compute precision of the handle.
  *   - a handle is bound to one GPU and is not thread-safe; use one handle per GPU.
- *   - stream arguments are cudaStream_t values passed as void* (NULL = the handle's own stream).
+ *   - stream arguments are cudaStream_t values passed as void*: NULL is CUDA's legacy default
+ *     stream as usual, DBSGYM_OWN_STREAM selects the handle's private non-blocking stream (the one
+ *     the *_host calls use).  Calls issued on different streams are not ordered with respect to
+ *     each other: synchronise when switching between them.
  */
 #ifndef DBSGYM_H_
 #define DBSGYM_H_
@@ -34,6 +37,7 @@ extern "C" {
 #endif
 
 #define DBSGYM_ABI_VERSION 1
+#define DBSGYM_OWN_STREAM ((void*)(intptr_t)-1)
 
 typedef struct DbsGymHandle DbsGymHandle;
 
@@ -166,6 +170,8 @@ int dbsgym_set_timing(DbsGymHandle* h, int32_t enabled);
 /* FP32-FMA throughput micro-benchmark used for the roofline denominator: runs a dependent-
  * chain FFMA kernel on `device` for about `ms_target` ms; returns TFLOP/s in *tflops. */
 int dbsgym_measure_fp32_peak(int32_t device, double ms_target, double* tflops);
+/* the two variants separately: packed == 0 scalar FFMA chains, packed == 1 FFMA2 (f32x2) chains */
+int dbsgym_measure_fp32_peak_mode(int32_t device, double ms_target, int32_t packed, double* tflops);
 
 #ifdef __cplusplus
 }
