@@ -38,6 +38,27 @@ def generate_perturbations(initial_vector, M=10, step_scale=0.1, random_seed=Non
     return np.array(walk)
 
 
+_ELECTRODE_CACHE = {}
+
+
+def cached_electrode(p, conduct_modifier, elec_coords, rec_coords, verbose):
+    """Electrode geometry depends only on (grid, contacts, conduct_modifier, flags): thousands of
+    batched environments share a handful of distinct electrodes, so build each one once."""
+    grid = p["neur_grid"]
+    key = (id(grid), tuple(p["grid_size"]), float(conduct_modifier), repr(elec_coords), repr(rec_coords),
+           repr(p["electrode_amps"]), bool(p["directed_stimulation"]), p["electrode_prc_type"], bool(p["naive_dbs"]))
+    hit = _ELECTRODE_CACHE.get(key)
+    if hit is not None and hit[0] is grid and not verbose:
+        return hit[1]
+    el = ElectrodeModel(p["grid_size"], grid, conduct_modifier, elec_coords, rec_coords, p["electrode_amps"],
+                        directed_stimulation=p["directed_stimulation"], prc_type=p["electrode_prc_type"],
+                        naive=p["naive_dbs"], verbose=bool(verbose))
+    if len(_ELECTRODE_CACHE) > 4096:
+        _ELECTRODE_CACHE.clear()
+    _ELECTRODE_CACHE[key] = (grid, el)          # holding `grid` keeps id(grid) unique while cached
+    return el
+
+
 @dataclass
 class EpisodeSetup:
     """What one reset hands to the device."""
@@ -182,11 +203,8 @@ class HostEnvState:
         # KuramotoJAX.__init__ (env.py:211-243)
         self.w0 = remove_negative_w0(self.w0)
         assert np.min(self.w0) >= 0, "Natural frequencies w0 must be positive!"
-        electrode = ElectrodeModel(p["grid_size"], p["neur_grid"], self.encapsulation_coeff,
-                                   self.elec_coords, self.rec_coords, p["electrode_amps"],
-                                   directed_stimulation=p["directed_stimulation"],
-                                   prc_type=p["electrode_prc_type"], naive=p["naive_dbs"],
-                                   verbose=bool(self.verbose))
+        electrode = cached_electrode(p, self.encapsulation_coeff, self.elec_coords, self.rec_coords,
+                                     self.verbose)
         if not self.save_init or self.init_state is None:
             self.init_state = np.random.normal(loc=p["init_state_mean"], scale=p["init_state_sd"],
                                                size=(p["num_oscillators"]))
