@@ -259,10 +259,14 @@ def run_gpu_arm(args):
         obs, rew, done, infos = venv.step_wait()
     sync_all()
     e2e_s = time.perf_counter() - t0
-    # the raw C-ABI host call (no Python list building)
+    # the C-ABI host call that returns the FULL [B, W] observation every step (no host-side window mirror)
+    core = venv.core
+    for i in range(Wm):
+        eng.step_host(actions[i], core._obs_bufs[0], core.rew_buf, core.done_buf)
+    sync_all()
     t0 = time.perf_counter()
     for i in range(K):
-        venv.core.step(actions[Wm + i])
+        eng.step_host(actions[Wm + i], core._obs_bufs[0], core.rew_buf, core.done_buf)
     sync_all()
     capi_s = time.perf_counter() - t0
     clk = clocks.stop()
@@ -309,8 +313,11 @@ def run_gpu_arm(args):
             "rk_substeps_per_env_step": substeps_per_env_step, "rhs_evals_per_env_step": rhs_per_env_step,
             "solver_status": counters["status"],
             "e2e": {"value": B * world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 4,
-                    "d2h_bytes_per_step": B * (2340 * 4 + 4 + 1), "api": "BatchedKuramotoVecEnv.step_async/step_wait (numpy in/out, pinned)",
-                    "c_abi_step_host": B * world * K / capi_s},
+                    "d2h_bytes_per_step": B * (eng.max_step_samples * 4 + 4 + 4 + 1),
+                    "api": "BatchedKuramotoVecEnv.step_async/step_wait, numpy in/out; delta transfer: only the step's new "
+                           "window samples cross PCIe (dbsgym_step_host_samples), the host slides its mirror of the window",
+                    "full_obs_d2h": {"value": B * world * K / capi_s, "d2h_bytes_per_step": B * (2340 * 4 + 4 + 1),
+                                     "api": "dbsgym_step_host (whole [B,2340] f32 observation copied to pinned host memory every step)"}},
             "gpu_launches": 2 * K,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": None,

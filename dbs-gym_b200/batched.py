@@ -34,7 +34,7 @@ def _pinned(shape, dtype):
 
 class BatchedKuramoto:
     def __init__(self, params_dicts, *, precision="f32", device=0, compat_env2=False, force_dense=False,
-                 save_init=False):
+                 save_init=False, transfer="delta"):
         if isinstance(params_dicts, dict):
             params_dicts = [params_dicts]
         self.params_dicts = list(params_dicts)
@@ -86,6 +86,18 @@ class BatchedKuramoto:
         self.rew_buf, t = _pinned((B,), np.float32); self._pin.append(t)
         self.done_buf, t = _pinned((B,), np.uint8); self._pin.append(t)
         self.act_buf, t = _pinned((B,), np.float32); self._pin.append(t)
+        # delta transfer: the host mirrors the observation window and receives only the step's new
+        # samples (B x 19 floats instead of B x 2340) -- see dbsgym_step_host_samples
+        if transfer not in ("delta", "full"):
+            raise ValueError("transfer must be 'delta' or 'full'")
+        self.transfer = transfer
+        smax = self.engine.max_step_samples
+        self.samples_buf, t = _pinned((B, smax), np.float32); self._pin.append(t)
+        self.nsamp_buf, t = _pinned((B,), np.int32); self._pin.append(t)
+        self._slack = self.window
+        self._mirror = np.empty((B, self.window + self._slack), dtype=np.float32) if transfer == "delta" else None
+        self._mirror_off = 0
+        self._mirror_ok = False
         self._lfp_cache = None
         self.current_step = np.zeros(B, dtype=np.int64)
         self._upload_and_run_transient(np.arange(B), setups)
@@ -105,6 +117,7 @@ class BatchedKuramoto:
             self.current_step[i] = 0
         self.engine.transient(self.t_transient, env_ids=ids)
         self._lfp_cache = None
+        self._mirror_ok = False
 
     def reset_envs(self, ids):
         """reset() of the listed environments, in the order given (reference env.py:467-614)."""
@@ -112,19 +125,63 @@ class BatchedKuramoto:
         self._upload_and_run_transient(ids, setups)
 
     def observations(self):
-        """Current observation windows [B, W] float32 (host)."""
-        return self.engine.obs_host(self.obs_buf)
+        """Current observation windows [B, W] float32 (host), read back from the device."""
+        obs = self.engine.obs_host(self.obs_buf)
+        if self._mirror is not None:
+            self._mirror[:, :self.window] = obs
+            self._mirror_off = 0
+            self._mirror_ok = True
+            return self._mirror[:, :self.window]
+        return obs
 
     def step(self, actions):
-        """Advance every environment by one step.  Returns host views: obs [B,W] f32 (valid until the
-        step after the next), reward [B] f32 and done [B] bool (overwritten by the next call)."""
+        """Advance every environment by one step.  Returns host views: obs [B,W] f32, reward [B] f32
+        and done [B] bool, all overwritten by later calls (copy what you keep)."""
         self.act_buf[:] = np.asarray(actions, dtype=np.float32).reshape(self.num_envs)
+        self._lfp_cache = None
+        if self._mirror is not None:
+            if not self._mirror_ok:
+                self.observations()
+            self.engine.step_host_samples(self.act_buf, self.samples_buf, self.nsamp_buf, self.rew_buf,
+                                          self.done_buf)
+            self.current_step += 1
+            n = int(self.nsamp_buf[0])
+            if np.all(self.nsamp_buf == n):
+                W, off = self.window, self._mirror_off
+                if off + W + n > self._mirror.shape[1]:            # out of slack: compact (rare, amortised)
+                    self._mirror[:, :W] = self._mirror[:, off:off + W].copy()
+                    off = 0
+                self._mirror[:, off + W:off + W + n] = self.samples_buf[:, :n]
+                self._mirror_off = off + n
+                obs = self._mirror[:, off + n:off + n + W]
+            else:                                                  # environments out of lockstep: full read-back
+                obs = self.observations()
+            return obs, self.rew_buf, self.done_buf.view(np.bool_)
         self._obs_flip ^= 1
         self.obs_buf = self._obs_bufs[self._obs_flip]
         self.engine.step_host(self.act_buf, self.obs_buf, self.rew_buf, self.done_buf)
         self.current_step += 1
-        self._lfp_cache = None
         return self.obs_buf, self.rew_buf, self.done_buf.view(np.bool_)
+
+    def step_tensor(self, actions, obs=None, reward=None, done=None):
+        """On-device step for GPU-resident policies: torch CUDA tensors in, torch CUDA tensors out, no
+        host copies at all; asynchronous on torch's current stream.  actions: float32 [B]."""
+        import torch
+        dev = torch.device("cuda", self.engine.device)
+        B, W = self.num_envs, self.window
+        actions = actions.to(device=dev, dtype=torch.float32).contiguous().view(B)
+        if obs is None:
+            obs = torch.empty((B, W), dtype=torch.float32, device=dev)
+        if reward is None:
+            reward = torch.empty(B, dtype=torch.float32, device=dev)
+        if done is None:
+            done = torch.empty(B, dtype=torch.uint8, device=dev)
+        self.engine.step_device(actions.data_ptr(), obs.data_ptr(), reward.data_ptr(), done.data_ptr(),
+                                torch.cuda.current_stream(dev).cuda_stream)
+        self.current_step += 1
+        self._lfp_cache = None
+        self._mirror_ok = False
+        return obs, reward, done
 
     # -------------------------------------------------------------------------------------
     def _lfp(self):

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -57,9 +58,10 @@ struct DbsGymHandle {
     unsigned long long* counters = nullptr;
     int32_t* status = nullptr;
     // host-API staging
-    float *st_actions = nullptr, *st_obs = nullptr, *st_reward = nullptr;
+    float *st_actions = nullptr, *st_obs = nullptr, *st_reward = nullptr, *st_samples = nullptr;
     uint8_t* st_done = nullptr;
     // timing
+    int ctas_per_sm = 0;                 // 0 = whatever fits
     bool timing = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     float last_ms[2] = {0.f, 0.f};
@@ -226,7 +228,13 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
 
 template <typename real, bool DENSE, int MAXT>
 cudaError_t launch_step_t(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
-    const size_t smem = step_smem_bytes(h->Np, DENSE ? 0 : h->tab, h->nthreads, sizeof(real));
+    size_t smem = step_smem_bytes(h->Np, DENSE ? 0 : h->tab, h->nthreads, sizeof(real));
+    if (h->ctas_per_sm > 0) {
+        // occupancy knob: pad the dynamic shared memory so that exactly ctas_per_sm CTAs fit on an SM
+        // (227 KB usable, 1 KB reserved per CTA) -- used to balance the waves of a launch
+        const size_t want = (size_t)(227 * 1024) / (size_t)h->ctas_per_sm - 1024;
+        if (want > smem) smem = want & ~(size_t)15;
+    }
     auto kern = step_kernel<real, DENSE, MAXT>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -253,8 +261,9 @@ cudaError_t launch_step(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
 }
 
 cudaError_t launch_obs(DbsGymHandle* h, float* obs, float* reward_f, uint8_t* done_out, int append,
-                       const int32_t* ids_dev, int n, cudaStream_t s) {
+                       const int32_t* ids_dev, int n, cudaStream_t s, float* samples_f = nullptr) {
     ObsParams o;
+    o.samples_f = samples_f;
     o.B = h->B; o.W = h->W; o.smax = h->smax;
     o.ring = h->ring; o.head = h->head;
     o.lfp_rec = h->lfp_rec; o.n_samples = h->n_samples;
@@ -287,14 +296,14 @@ cudaStream_t pick_stream(DbsGymHandle* h, void* stream) {
 }
 
 int step_impl(DbsGymHandle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
-              cudaStream_t s) {
+              cudaStream_t s, float* samples_dev = nullptr) {
     StepParams p;
     fill_params(h, p);
     p.mode = MODE_STEP; p.actions = actions_dev; p.n_launch = h->B;
     if (h->timing) CU(h, cudaEventRecord(h->ev[0], s));
     CU(h, launch_step(h, p, s));
     if (h->timing) CU(h, cudaEventRecord(h->ev[1], s));
-    CU(h, launch_obs(h, obs_dev, reward_dev, done_dev, 1, nullptr, h->B, s));
+    CU(h, launch_obs(h, obs_dev, reward_dev, done_dev, 1, nullptr, h->B, s, samples_dev));
     if (h->timing) CU(h, cudaEventRecord(h->ev[2], s));
     return DBSGYM_OK;
 }
@@ -353,6 +362,7 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
         h->tab = h->cfg.grid[2] * cfg->grid[0] * kRows;
     }
     memset(&h->rspec, 0, sizeof(h->rspec));
+    if (const char* e = getenv("DBSGYM_CTAS_PER_SM")) h->ctas_per_sm = atoi(e);
     const size_t BN = (size_t)h->B * Np;
     bool ok = true;
     ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -371,6 +381,7 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
     A((void**)&h->counters, 3 * sizeof(unsigned long long)); A((void**)&h->status, 4);
     A((void**)&h->st_actions, (size_t)h->B * 4); A((void**)&h->st_obs, (size_t)h->B * h->W * 4);
     A((void**)&h->st_reward, (size_t)h->B * 4); A((void**)&h->st_done, (size_t)h->B);
+    A((void**)&h->st_samples, (size_t)h->B * h->smax * 4);
     for (int i = 0; i < 3 && ok; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
     if (ok) {
         // episode_len defaults to "never done"
@@ -393,7 +404,7 @@ void dbsgym_destroy(DbsGymHandle* h) {
     void* bufs[] = {h->table, h->alpha, h->w0, h->stim, h->rec, h->phase, h->ring, h->wind, h->head, h->n_samples,
                     h->step_idx, h->episode_len, h->lfp_true, h->lfp_rec, h->u, h->reward, h->done, h->sched_nI,
                     h->sched_nII, h->sched_offI, h->sched_offII, h->ts_dev, h->ids_dev, h->lin_g, h->tw_seed,
-                    h->tw_rot, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done};
+                    h->tw_rot, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples};
     for (void* b : bufs)
         if (b) cudaFree(b);
     for (int i = 0; i < 3; ++i)
@@ -634,6 +645,24 @@ int dbsgym_step_host(DbsGymHandle* h, const float* actions, float* obs, float* r
     rc = step_impl(h, h->st_actions, obs ? h->st_obs : nullptr, h->st_reward, h->st_done, s);
     if (rc) return rc;
     if (obs) CU(h, cudaMemcpyAsync(obs, h->st_obs, (size_t)h->B * h->W * 4, cudaMemcpyDeviceToHost, s));
+    if (reward) CU(h, cudaMemcpyAsync(reward, h->st_reward, (size_t)h->B * 4, cudaMemcpyDeviceToHost, s));
+    if (done) CU(h, cudaMemcpyAsync(done, h->st_done, (size_t)h->B, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    return DBSGYM_OK;
+}
+
+int dbsgym_step_host_samples(DbsGymHandle* h, const float* actions, float* samples, int32_t* n_samples,
+                             float* reward, uint8_t* done) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    if (!actions || !samples || !n_samples) return fail(h, DBSGYM_EINVAL, "null argument");
+    CU(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t s = h->stream;
+    CU(h, cudaMemcpyAsync(h->st_actions, actions, (size_t)h->B * 4, cudaMemcpyHostToDevice, s));
+    rc = step_impl(h, h->st_actions, nullptr, h->st_reward, h->st_done, s, h->st_samples);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(samples, h->st_samples, (size_t)h->B * h->smax * 4, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(n_samples, h->n_samples, (size_t)h->B * 4, cudaMemcpyDeviceToHost, s));
     if (reward) CU(h, cudaMemcpyAsync(reward, h->st_reward, (size_t)h->B * 4, cudaMemcpyDeviceToHost, s));
     if (done) CU(h, cudaMemcpyAsync(done, h->st_done, (size_t)h->B, cudaMemcpyDeviceToHost, s));
     CU(h, cudaStreamSynchronize(s));

@@ -24,7 +24,7 @@ struct ObsParams {
     int B, W, smax;
     void* ring; int32_t* head;
     const double* lfp_rec; const int32_t* n_samples;
-    float* obs; float* reward_f; double* reward; uint8_t* done_out; uint8_t* done_dev;
+    float* obs; float* samples_f; float* reward_f; double* reward; uint8_t* done_out; uint8_t* done_dev;
     int32_t* step_idx; const int32_t* episode_len; const double* u;
     int kind, nbins;
     double power_scale, action_cost, threshold, threshold_penalty, temp_scale;
@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kObsThreads) obs_kernel(const ObsParams p) {
         const real v = real(p.lfp_rec[(size_t)env * p.smax + i]);
         ring[pos] = v;
         xs[pos] = (double)v;
+        if (p.samples_f) p.samples_f[(size_t)env * p.smax + i] = (float)v;
     }
     int new_head = head + S;
     if (new_head >= W) new_head -= W;

@@ -168,6 +168,11 @@ class KuramotoEngine:
                                            _capi.ptr(done)))
         return obs, reward, done
 
+    def step_host_samples(self, actions, samples, n_samples, reward, done):
+        """Delta-transfer step: only the new window samples come back ([B, max_step_samples] f32)."""
+        self._ck(self.lib.dbsgym_step_host_samples(self._h, _capi.ptr(actions), _capi.ptr(samples),
+                                                   _capi.ptr(n_samples), _capi.ptr(reward), _capi.ptr(done)))
+
     def step_device(self, actions_ptr, obs_ptr=None, reward_ptr=None, done_ptr=None, stream=None):
         """Asynchronous step on raw device pointers (e.g. ``tensor.data_ptr()``)."""
         self._ck(self.lib.dbsgym_step(self._h, actions_ptr, obs_ptr, reward_ptr, done_ptr, _stream(stream)))

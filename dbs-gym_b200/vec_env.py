@@ -41,14 +41,14 @@ class _LazyAttrList:
 
 class BatchedKuramotoVecEnv(VecEnvBase):
     def __init__(self, params_dicts, num_envs=None, precision=None, device=0, compat_env2=False,
-                 monitor=True):
+                 monitor=True, transfer="delta"):
         if isinstance(params_dicts, dict):
             n = int(num_envs or params_dicts.get("num_envs", 1))
             # like DummyVecEnv([make_env(d)] * n): every env gets its own copy of the dict
             params_dicts = [copy.deepcopy(params_dicts) for _ in range(n)]
         p0 = params_dicts[0]
         self.core = BatchedKuramoto(params_dicts, precision=precision or _default_precision(p0),
-                                    device=device, compat_env2=compat_env2)
+                                    device=device, compat_env2=compat_env2, transfer=transfer)
         B, W = self.core.num_envs, self.core.window
         obs_space = Box(low=-1.5, high=1.5, shape=(1, W), dtype=np.float32)
         act_space = Box(low=-1., high=1., shape=(1,), dtype=np.float32)
@@ -75,7 +75,7 @@ class BatchedKuramotoVecEnv(VecEnvBase):
 
     def step_wait(self):
         obs, rew, done = self.core.step(self._actions)
-        obs = obs.reshape(self.num_envs, 1, -1)       # view of a double-buffered pinned array (no 38 MB copy)
+        obs = obs.reshape(self.num_envs, 1, -1)       # a view (host window mirror / pinned buffer): no 38 MB copy
         rew = rew.copy()
         done = done.copy()
         self._ep_ret += rew

@@ -143,6 +143,12 @@ int dbsgym_step(DbsGymHandle* h, const float* actions_dev, float* obs_dev,
  * and synchronises.  This is the call a gym VecEnv makes. */
 int dbsgym_step_host(DbsGymHandle* h, const float* actions, float* obs,
                      float* reward, uint8_t* done);
+/* Delta-transfer variant for hosts that mirror the observation window themselves: instead of the
+ * [B][W] window only the step's NEW samples cross PCIe -- samples[b*max_step_samples + i], float32,
+ * i < n_samples[b], exactly the values appended to the window (env.py:447) -- so the host can
+ * slide its own copy (obs_{t+1} = concat(obs_t[n:], samples)).  reward / done as above. */
+int dbsgym_step_host_samples(DbsGymHandle* h, const float* actions, float* samples,
+                             int32_t* n_samples, float* reward, uint8_t* done);
 /* reset observation (window as float32) of all environments to a host buffer [B][W] */
 int dbsgym_get_obs_host(DbsGymHandle* h, float* obs);
 

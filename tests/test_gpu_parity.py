@@ -18,9 +18,12 @@ PHASE_TOL = {"f64": 1e-9, "f32": 1e-5}
 LFP_TOL = {"f64": 1e-11, "f32": 2e-6}
 
 
-def _engine_from_params(d, B, precision, force_dense=False):
+def _engine_from_params(d, B, precision, force_dense=False, transfer="full"):
+    # transfer="full": these tests overwrite device state between steps (teacher forcing), which the
+    # host-side window mirror of the delta-transfer mode cannot see
     from dbsgym_b200.batched import BatchedKuramoto
-    return BatchedKuramoto([copy.deepcopy(d) for _ in range(B)], precision=precision, force_dense=force_dense)
+    return BatchedKuramoto([copy.deepcopy(d) for _ in range(B)], precision=precision, force_dense=force_dense,
+                           transfer=transfer)
 
 
 def _teacher_forced(core, g, precision, n_steps, reward_tol_rel):

@@ -162,3 +162,47 @@ def test_full_size_batch_properties(precision):
     eng.step_host(tile(acts)); _, _, done = eng.step_host(tile(acts))
     assert done.all() and np.all(eng.episode()[0] == 3)
     eng.close(); solo.close(); core.close()
+
+
+def test_delta_transfer_equals_full_observation_readback():
+    """The host-mirrored window (only the new samples cross PCIe) must give bit-identical observations,
+    rewards and done flags to the full [B, W] read-back, across a mirror compaction (> 130 steps) and an
+    episode boundary with auto-reset."""
+    from dbsgym_b200.vec_env import BatchedKuramotoVecEnv
+    B, steps = 3, 150
+    mk = lambda: [make_params("env1", 30 + e, transient_state_len=118.0, total_episode_len=126.0,   # noqa: E731
+                              rand_seed=70 + e) for e in range(B)]
+    outs = {}
+    for mode in ("full", "delta"):
+        venv = BatchedKuramotoVecEnv(mk(), transfer=mode)
+        obs = venv.reset()
+        rng = np.random.default_rng(9)
+        rec = [obs.copy()]
+        dones = 0
+        for k in range(steps):
+            o, r, d, infos = venv.step(rng.uniform(-1, 1, (B, 1)).astype(np.float32))
+            rec.append(o.copy()); rec.append(r.copy()); rec.append(d.copy())
+            if d.any():
+                dones += 1
+                rec.append(np.stack([infos[i]["terminal_observation"] for i in range(B)]))
+        assert dones == 1 and venv.get_attr("total_episode_counts")[0] == 140
+        outs[mode] = rec
+        venv.close()
+    assert len(outs["full"]) == len(outs["delta"])
+    for a, b in zip(outs["full"], outs["delta"]):
+        assert np.array_equal(a, b)
+
+
+def test_step_tensor_matches_host_step():
+    import torch
+    from dbsgym_b200.batched import BatchedKuramoto
+    d = [make_params("env0", 40 + e, transient_state_len=118.0) for e in range(2)]
+    a = BatchedKuramoto(copy.deepcopy(d)); b = BatchedKuramoto(copy.deepcopy(d))
+    acts = np.array([0.3, -0.9], dtype=np.float32)
+    for _ in range(3):
+        o1, r1, d1 = a.step(acts)
+        o2, r2, d2 = b.step_tensor(torch.from_numpy(acts).cuda())
+        torch.cuda.synchronize()
+        assert np.array_equal(o1, o2.cpu().numpy()) and np.array_equal(r1, r2.cpu().numpy())
+        assert np.array_equal(d1, d2.cpu().numpy().astype(bool))
+    a.close(); b.close()
