@@ -80,11 +80,14 @@ class BatchedKuramotoVecEnv(VecEnvBase):
         done = done.copy()
         self._ep_ret += rew
         self._ep_len += 1
-        infos = [{"TimeLimit.truncated": False} for _ in range(self.num_envs)]
+        # one shared info dict for the environments that did not finish (building thousands of dicts per
+        # step costs more than the GPU step); finished environments get their own
+        shared = {"TimeLimit.truncated": False}
+        infos = [shared] * self.num_envs
         finished = np.flatnonzero(done)
         if finished.size:
             for i in finished:
-                infos[i]["terminal_observation"] = obs[i].copy()
+                infos[i] = {"TimeLimit.truncated": False, "terminal_observation": obs[i].copy()}
                 if self.monitor:
                     infos[i]["episode"] = {"r": round(float(self._ep_ret[i]), 6), "l": int(self._ep_len[i]),
                                            "t": round(time.time() - self._t0, 6)}
