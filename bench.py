@@ -174,6 +174,9 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------
 def run_gpu_arm(args):
+    # keep stdout clean for the ONE JSON line: libraries (NCCL's version banner, ...) write to fd 1
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
@@ -333,7 +336,8 @@ def run_gpu_arm(args):
                              "matvec_f64_value": cpu_matvec, "published_reference": "17-20 it/s (notebook tqdm, unknown CPU)"},
             "clocks": clk, "setup_s": setup_s, "wall_s_device_loop": wall_dev,
         }
-        print(json.dumps(line), flush=True)
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     venv.close()
     if world > 1:
         dist.destroy_process_group()
