@@ -2,10 +2,12 @@
 the per-step parity of test_gpu_parity.py the comparison is statistical.
 
 Stated tolerances
-* free-running fp64 GPU vs fp64 oracle, same inputs: LFP (order-parameter) trajectory within 1e-6
-  absolute for at least the first 150 steps (after that rounding differences are amplified);
-* beta-band (12.5-21 Hz) power of the true LFP over an evaluation episode, GPU fp32 vs oracle fp64:
-  within 35 % relative per environment (the paper's own seed-to-seed sd is 27 %);
+* free-running fp64 GPU vs fp64 oracle, same inputs: LFP (order-parameter) trajectory within 1e-9
+  absolute over 300 consecutive steps (measured 5e-12: at these parameters rounding differences are
+  NOT amplified noticeably over an episode);
+* beta-band (12.5-21 Hz) power of the true LFP over a full 1111-step evaluation episode, GPU fp32 vs
+  oracle fp64: within 1 % relative per environment (measured 5e-6 .. 3e-5; the paper's own
+  seed-to-seed sd is 27 %);
 * the paper's table (data/kur-table-metrics.xlsx, env0): DBS-OFF 11.83e-3 (sd 3.2e-3), HF-DBS
   2.34e-3 (sd 0.2e-3) -- batch means must fall inside mean +- 3 sd.
 """
@@ -63,7 +65,7 @@ def test_free_running_divergence_horizon_f64():
     per_step = np.maximum.reduceat(err, np.arange(0, len(err) - 17, 18))
     horizon = int(np.argmax(per_step > 1e-6)) if (per_step > 1e-6).any() else len(per_step)
     print("fp64 free-run: LFP error after 50/150/300 steps", err[:900].max(), err[:2700].max(), err.max(), "horizon", horizon)
-    assert err[: 150 * 17].max() < 1e-6
+    assert err.max() < 1e-9
     assert st["status"] == 0 and st["rejected"] <= st["accepted"] // 4
 
 
@@ -90,6 +92,6 @@ def test_eval_episode_beta_power_statistics(controller, action, paper_mean, pape
             tr.append(orc.theta_mean.copy())
         b_ref = eval_bbpow(np.concatenate(tr))
         print(controller, "env", i, "oracle", b_ref, "gpu", bb[i])
-        assert abs(bb[i] - b_ref) / b_ref < 0.35
+        assert abs(bb[i] - b_ref) / b_ref < 1e-2
     if controller == "hf_dbs":
         assert np.isclose(np.abs(acts).sum() * 5, 5555.0)         # paper table: HF-DBS energy 5555
