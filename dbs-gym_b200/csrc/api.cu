@@ -62,6 +62,7 @@ struct DbsGymHandle {
     uint8_t* st_done = nullptr;
     // timing
     int ctas_per_sm = 0;                 // 0 = whatever fits
+    bool grid_sym = false;               // GRID coupling: use the reflection-symmetry reduced contraction
     bool timing = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     float last_ms[2] = {0.f, 0.f};
@@ -226,16 +227,16 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
     p.ts = nullptr; p.n_ts = 0; p.actions = nullptr; p.env_ids = nullptr; p.n_launch = 0; p.mode = MODE_STEP;
 }
 
-template <typename real, bool DENSE, int MAXT>
+template <typename real, int CPL, int MAXT>
 cudaError_t launch_step_t(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
-    size_t smem = step_smem_bytes(h->Np, DENSE ? 0 : h->tab, h->nthreads, sizeof(real));
+    size_t smem = step_smem_bytes(h->Np, CPL == CPL_DENSE ? 0 : h->tab, h->nthreads, sizeof(real));
     if (h->ctas_per_sm > 0) {
         // occupancy knob: pad the dynamic shared memory so that exactly ctas_per_sm CTAs fit on an SM
         // (227 KB usable, 1 KB reserved per CTA) -- used to balance the waves of a launch
         const size_t want = (size_t)(227 * 1024) / (size_t)h->ctas_per_sm - 1024;
         if (want > smem) smem = want & ~(size_t)15;
     }
-    auto kern = step_kernel<real, DENSE, MAXT>;
+    auto kern = step_kernel<real, CPL, MAXT>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -244,20 +245,24 @@ cudaError_t launch_step_t(DbsGymHandle* h, const StepParams& p, cudaStream_t s) 
     return cudaGetLastError();
 }
 
-template <typename real, bool DENSE>
+template <typename real, int CPL>
 cudaError_t launch_step_m(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
     const int t = h->nthreads;
-    if (t <= 64) return launch_step_t<real, DENSE, 64>(h, p, s);
-    if (t <= 128) return launch_step_t<real, DENSE, 128>(h, p, s);
-    if (t <= 256) return launch_step_t<real, DENSE, 256>(h, p, s);
-    if (t <= 512) return launch_step_t<real, DENSE, 512>(h, p, s);
-    return launch_step_t<real, DENSE, 1024>(h, p, s);
+    if (t <= 64) return launch_step_t<real, CPL, 64>(h, p, s);
+    if (t <= 128) return launch_step_t<real, CPL, 128>(h, p, s);
+    if (t <= 256) return launch_step_t<real, CPL, 256>(h, p, s);
+    if (t <= 512) return launch_step_t<real, CPL, 512>(h, p, s);
+    return launch_step_t<real, CPL, 1024>(h, p, s);
+}
+
+template <typename real>
+cudaError_t launch_step_c(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
+    if (h->cfg.coupling == DBSGYM_COUPLING_DENSE) return launch_step_m<real, CPL_DENSE>(h, p, s);
+    return h->grid_sym ? launch_step_m<real, CPL_GRID_SYM>(h, p, s) : launch_step_m<real, CPL_GRID>(h, p, s);
 }
 
 cudaError_t launch_step(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
-    const bool dense = h->cfg.coupling == DBSGYM_COUPLING_DENSE;
-    if (h->f64) return dense ? launch_step_m<double, true>(h, p, s) : launch_step_m<double, false>(h, p, s);
-    return dense ? launch_step_m<float, true>(h, p, s) : launch_step_m<float, false>(h, p, s);
+    return h->f64 ? launch_step_c<double>(h, p, s) : launch_step_c<float>(h, p, s);
 }
 
 cudaError_t launch_obs(DbsGymHandle* h, float* obs, float* reward_f, uint8_t* done_out, int append,
@@ -331,7 +336,9 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
         return fail(nullptr, DBSGYM_EINVAL, "unknown coupling mode %d", cfg->coupling);
     if (!(cfg->rtol > 0) || !(cfg->atol > 0) || !(cfg->dt0 > 0) || cfg->max_steps <= 0)
         return fail(nullptr, DBSGYM_EINVAL, "rtol, atol, dt0 and max_steps must be positive");
-    const int Np = (cfg->n_osc + kRows - 1) / kRows * kRows;
+    // DENSE: pad to whole warps (padded oscillators are inert); GRID: whole z-planes of 8-lines
+    const int gran = cfg->coupling == DBSGYM_COUPLING_DENSE ? 32 * kRows : kRows;
+    const int Np = (cfg->n_osc + gran - 1) / gran * gran;
     if (Np / kRows > 1024) return fail(nullptr, DBSGYM_EINVAL, "n_osc %d too large for the resident-state kernel (max 8192)", cfg->n_osc);
     if (cfg->coupling == DBSGYM_COUPLING_GRID) {
         if (cfg->grid[1] != kRows)
@@ -339,6 +346,8 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
         if (cfg->grid[0] <= 0 || cfg->grid[2] <= 0 || cfg->n_osc % kRows != 0 ||
             cfg->n_osc > cfg->grid[0] * cfg->grid[1] * cfg->grid[2] || cfg->n_osc % (cfg->grid[0] * kRows) != 0)
             return fail(nullptr, DBSGYM_EINVAL, "GRID coupling needs n_osc to be whole z-planes of a gx*8*gz grid");
+        if ((cfg->n_osc / kRows) % 32 != 0)
+            return fail(nullptr, DBSGYM_EINVAL, "GRID coupling needs a multiple of 32 grid lines (n_osc %% 256 == 0); use DENSE");
     }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -360,6 +369,9 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
         // only the z-planes actually populated take part
         h->cfg.grid[2] = cfg->n_osc / (cfg->grid[0] * kRows);
         h->tab = h->cfg.grid[2] * cfg->grid[0] * kRows;
+        // mirror symmetry in z and x needs even extents; DBSGYM_NO_SYM=1 keeps the plain Toeplitz kernel (A/B runs)
+        const char* nosym = getenv("DBSGYM_NO_SYM");
+        h->grid_sym = h->cfg.grid[2] % 2 == 0 && cfg->grid[0] % 2 == 0 && !(nosym && nosym[0] == '1');
     }
     memset(&h->rspec, 0, sizeof(h->rspec));
     if (const char* e = getenv("DBSGYM_CTAS_PER_SM")) h->ctas_per_sm = atoi(e);

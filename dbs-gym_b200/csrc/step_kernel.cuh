@@ -194,6 +194,113 @@ __device__ __forceinline__ void couple_grid<float>(const float* __restrict__ sc,
     for (int r = 0; r < kRows; ++r) { as[r] = acc[r].x; ac[r] = acc[r].y; }
 }
 
+// ---- coupling contraction, GRID_SYM mode: reflection-symmetry reduced -------------------------
+// alpha_ij = f(|dz|,|dx|,|dy|) commutes with the reflections z -> GZ-1-z and x -> GX-1-x of the grid.
+// In the basis of the four (pz,px) parity sectors  s^p[j'] = sum_g chi_p(g) s[g j']  (j' in the
+// fundamental quarter GZ/2 x GX/2, g in {1,Rz,Rx,RzRx}) the operator is block diagonal:
+//     y^p[i'] = sum_j' U^p[i'][j'] s^p[j'],   U^p[i'][j'] = sum_k chi_p(k) alpha(i', k j'),
+// so one RHS needs 4 x (N/4)^2 instead of N^2 multiply-adds -- the same numbers, reassociated.
+// The four lanes of a quad own the four mirror-image grid lines; the sector transform is a 2-stage
+// warp-shuffle butterfly (no extra shared memory, no extra barrier).  U^p is not stored: its 8 entries
+// per (zj,xj) block are combined on the fly from four rows of the 2 KB Toeplitz table.
+template <typename real>
+__device__ __forceinline__ void quad_butterfly(real (&v)[kRows], real sx, real sz, unsigned mask) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) { const real o = __shfl_xor_sync(mask, v[r], 1); v[r] = fma_r(sx, v[r], o); }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) { const real o = __shfl_xor_sync(mask, v[r], 2); v[r] = fma_r(sz, v[r], o); }
+}
+
+template <typename real>
+__device__ __forceinline__ void couple_grid_sym(const real* __restrict__ bp, const real* __restrict__ T,
+                                                int GZ, int GX, int zq, int xq, real pz, real px,
+                                                real (&as)[kRows], real (&ac)[kRows]) {
+    using V = typename Vec<real>::T;
+    constexpr int n = Vec<real>::n;
+    const int NC = GZ * GX, HZ = GZ >> 1, HX = GX >> 1;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) { as[r] = real(0); ac[r] = real(0); }
+    for (int zj = 0; zj < HZ; ++zj) {
+        const int dz0 = zq > zj ? zq - zj : zj - zq, dz1 = GZ - 1 - zq - zj;
+        const real* t0 = T + dz0 * GX * n;
+        const real* t1 = T + dz1 * GX * n;
+#pragma unroll 1
+        for (int xj = 0; xj < HX; ++xj) {
+            const int dx0 = xq > xj ? xq - xj : xj - xq, dx1 = GX - 1 - xq - xj;
+            real u[kRows];
+#pragma unroll
+            for (int q = 0; q < kRows / n; ++q) {
+                real a00[n], a01[n], a10[n], a11[n];
+                unpack(*reinterpret_cast<const V*>(t0 + (q * NC + dx0) * n), a00);
+                unpack(*reinterpret_cast<const V*>(t0 + (q * NC + dx1) * n), a01);
+                unpack(*reinterpret_cast<const V*>(t1 + (q * NC + dx0) * n), a10);
+                unpack(*reinterpret_cast<const V*>(t1 + (q * NC + dx1) * n), a11);
+#pragma unroll
+                for (int e = 0; e < n; ++e)
+                    u[q * n + e] = fma_r(pz, fma_r(px, a11[e], a10[e]), fma_r(px, a01[e], a00[e]));
+            }
+            real b[2 * kRows];
+            loadv<2 * kRows>(bp + (zj * HX + xj) * (2 * kRows), b);
+#pragma unroll
+            for (int yj = 0; yj < kRows; ++yj) {
+                const real s = b[2 * yj], c = b[2 * yj + 1];
+#pragma unroll
+                for (int yi = 0; yi < kRows; ++yi) {
+                    const real a = u[yi > yj ? yi - yj : yj - yi];
+                    as[yi] = fma_r(a, s, as[yi]);
+                    ac[yi] = fma_r(a, c, ac[yi]);
+                }
+            }
+        }
+    }
+}
+
+template <>
+__device__ __forceinline__ void couple_grid_sym<float>(const float* __restrict__ bp, const float* __restrict__ T,
+                                                       int GZ, int GX, int zq, int xq, float pz, float px,
+                                                       float (&as)[kRows], float (&ac)[kRows]) {
+    const int NC = GZ * GX, HZ = GZ >> 1, HX = GX >> 1;
+    float2 acc[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) acc[r] = make_float2(0.f, 0.f);
+    const float2 px2 = make_float2(px, px), pz2 = make_float2(pz, pz);
+    for (int zj = 0; zj < HZ; ++zj) {
+        const int dz0 = zq > zj ? zq - zj : zj - zq, dz1 = GZ - 1 - zq - zj;
+        const float* t0 = T + dz0 * GX * 4;
+        const float* t1 = T + dz1 * GX * 4;
+#pragma unroll 1
+        for (int xj = 0; xj < HX; ++xj) {
+            const int dx0 = xq > xj ? xq - xj : xj - xq, dx1 = GX - 1 - xq - xj;
+            float u[kRows];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const float4 a00 = *reinterpret_cast<const float4*>(t0 + (q * NC + dx0) * 4);
+                const float4 a01 = *reinterpret_cast<const float4*>(t0 + (q * NC + dx1) * 4);
+                const float4 a10 = *reinterpret_cast<const float4*>(t1 + (q * NC + dx0) * 4);
+                const float4 a11 = *reinterpret_cast<const float4*>(t1 + (q * NC + dx1) * 4);
+                float2 lo = __ffma2_rn(pz2, __ffma2_rn(px2, make_float2(a11.x, a11.y), make_float2(a10.x, a10.y)),
+                                       __ffma2_rn(px2, make_float2(a01.x, a01.y), make_float2(a00.x, a00.y)));
+                float2 hi = __ffma2_rn(pz2, __ffma2_rn(px2, make_float2(a11.z, a11.w), make_float2(a10.z, a10.w)),
+                                       __ffma2_rn(px2, make_float2(a01.z, a01.w), make_float2(a00.z, a00.w)));
+                u[q * 4 + 0] = lo.x; u[q * 4 + 1] = lo.y; u[q * 4 + 2] = hi.x; u[q * 4 + 3] = hi.y;
+            }
+            float b[2 * kRows];
+            loadv<2 * kRows>(bp + (zj * HX + xj) * (2 * kRows), b);
+#pragma unroll
+            for (int yj = 0; yj < kRows; ++yj) {
+                const float2 scj = make_float2(b[2 * yj], b[2 * yj + 1]);
+#pragma unroll
+                for (int yi = 0; yi < kRows; ++yi) {
+                    const float a = u[yi > yj ? yi - yj : yj - yi];
+                    acc[yi] = __ffma2_rn(make_float2(a, a), scj, acc[yi]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) { as[r] = acc[r].x; ac[r] = acc[r].y; }
+}
+
 // ---- coupling contraction, DENSE mode (alpha^T streamed from global / L2) -----------------
 template <typename real>
 __device__ __forceinline__ void couple_dense(const real* __restrict__ sc, const real* __restrict__ alphaT,
@@ -226,17 +333,23 @@ template <typename real, int MAXT> struct MinBlocks {
     static constexpr int v = (sizeof(real) == 4 && MAXT <= 128) ? (512 / MAXT) : 1;
 };
 
-template <typename real, bool DENSE, int MAXT>
+enum { CPL_GRID = 0, CPL_DENSE = 1, CPL_GRID_SYM = 2 };
+constexpr int kScPad = 16;     // reals of padding per operand buffer (GRID_SYM staggers its 4 sectors by 16 B)
+
+template <typename real, int CPL, int MAXT>
 __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(const StepParams p) {
+    constexpr bool DENSE = CPL == CPL_DENSE;
+    constexpr bool SYM = CPL == CPL_GRID_SYM;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
     const int Np = p.Np;
     const int tab = DENSE ? 0 : p.GZ * p.GX * kRows;
+    const int scsz = 2 * Np + kScPad;
 
-    real* K = reinterpret_cast<real*>(smem_raw);          // [7][Np] stage derivatives f(y_s)
-    real* SC = K + 7 * Np;                                // [2][2*Np] interleaved (sin, cos)
-    real* T = SC + 4 * Np;                                // [tab]
+    real* K = reinterpret_cast<real*>(smem_raw);          // [7][Np] stage derivatives f(y_s), thread-private slots
+    real* SC = K + 7 * Np;                                // [2][scsz] interleaved (sin, cos) contraction operand
+    real* T = SC + 2 * scsz;                              // [tab]
     double* part = reinterpret_cast<double*>(T + tab);    // [nwarps][kSampleBatch][2]
     double* red = part + nwarps * kSampleBatch * 2;       // [nwarps]
 
@@ -244,8 +357,27 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
     if (slot >= p.n_launch) return;
     const int env = p.env_ids ? p.env_ids[slot] : slot;
     const size_t base = (size_t)env * Np;
-    const int i0 = tid * kRows;
-    const int zi = DENSE ? 0 : tid / p.GX, xi = DENSE ? 0 : tid % p.GX;
+    const int k0 = tid * kRows;                           // private slot in K (and in the plain operand)
+    // grid line owned by this thread.  GRID: line = tid.  GRID_SYM: a quad of lanes owns the four mirror
+    // images (z,x), (z,X-x), (Z-z,x), (Z-z,X-x) of fundamental line q = tid / 4.
+    int zi = 0, xi = 0, zq = 0, xq = 0;
+    real sgn_x = real(1), sgn_z = real(1);
+    if (SYM) {
+        const int HX = p.GX >> 1, q = tid >> 2;
+        zq = q / HX; xq = q % HX;
+        zi = (tid & 2) ? p.GZ - 1 - zq : zq;
+        xi = (tid & 1) ? p.GX - 1 - xq : xq;
+        sgn_x = (tid & 1) ? real(-1) : real(1);
+        sgn_z = (tid & 2) ? real(-1) : real(1);
+    } else if (!DENSE) {
+        zi = tid / p.GX; xi = tid % p.GX;
+    }
+    const int i0 = DENSE ? k0 : (zi * p.GX + xi) * kRows; // first oscillator index in the global arrays
+    const unsigned wmask = __activemask();
+    // operand slot written by this thread: plain = own line; GRID_SYM = sector (tid & 3), line q
+    const int sec_stride = (p.GZ >> 1) * (p.GX >> 1) * 2 * kRows + (int)(16 / sizeof(real));
+    const int sc_sector = SYM ? (tid & 3) * sec_stride : 0;
+    const int sc_slot = SYM ? sc_sector + (tid >> 2) * 2 * kRows : 2 * k0;
 
     real y0[kRows], w0[kRows], stim[kRows], rc[kRows];
     int wd[kRows];
@@ -270,7 +402,7 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
     }
     __syncthreads();
 
-    const real kn = real(p.k_over_n);
+    const real kn = real(SYM ? 0.25 * p.k_over_n : p.k_over_n);
     const real rtol = real(p.rtol), atol = real(p.atol);
     const real two_pi_r = real(kTwoPi);
     unsigned int n_acc = 0, n_rej = 0, n_rhs = 0;
@@ -332,21 +464,32 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                     const real a = real(c_A[s][j]);
                     if (a != real(0)) {
                         real kj[kRows];
-                        loadv<kRows>(K + j * Np + i0, kj);
+                        loadv<kRows>(K + j * Np + k0, kj);
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) inc[r] = fma_r(a, kj[r], inc[r]);
                     }
                 }
                 real sv[kRows], cv[kRows];
                 {
-                    real scw[2 * kRows];
 #pragma unroll
                     for (int r = 0; r < kRows; ++r) {
                         inc[r] *= dt;
                         sincos_r(y0[r] + inc[r], &sv[r], &cv[r]);
-                        scw[2 * r] = sv[r]; scw[2 * r + 1] = cv[r];
                     }
-                    storev<2 * kRows>(SC + pbuf * 2 * Np + 2 * i0, scw);
+                    real scw[2 * kRows];
+                    if (SYM) {                                   // to the parity-sector basis (quad butterfly)
+                        real ts_[kRows], tc_[kRows];
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) { ts_[r] = sv[r]; tc_[r] = cv[r]; }
+                        quad_butterfly<real>(ts_, sgn_x, sgn_z, wmask);
+                        quad_butterfly<real>(tc_, sgn_x, sgn_z, wmask);
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) { scw[2 * r] = ts_[r]; scw[2 * r + 1] = tc_[r]; }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) { scw[2 * r] = sv[r]; scw[2 * r + 1] = cv[r]; }
+                    }
+                    storev<2 * kRows>(SC + pbuf * scsz + sc_slot, scw);
                 }
                 if (s == 6) {
 #pragma unroll
@@ -354,13 +497,17 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                 }
                 __syncthreads();
                 real as[kRows], ac[kRows];
-                if (DENSE) couple_dense<real>(SC + pbuf * 2 * Np, reinterpret_cast<const real*>(p.alpha), Np, i0, as, ac);
-                else couple_grid<real>(SC + pbuf * 2 * Np, T, p.GZ, p.GX, zi, xi, as, ac);
+                if (DENSE) couple_dense<real>(SC + pbuf * scsz, reinterpret_cast<const real*>(p.alpha), Np, i0, as, ac);
+                else if (SYM) {
+                    couple_grid_sym<real>(SC + pbuf * scsz + sc_sector, T, p.GZ, p.GX, zq, xq, sgn_z, sgn_x, as, ac);
+                    quad_butterfly<real>(as, sgn_x, sgn_z, wmask);   // back to the grid lines (x 1/4 folded into kn)
+                    quad_butterfly<real>(ac, sgn_x, sgn_z, wmask);
+                } else couple_grid<real>(SC + pbuf * scsz, T, p.GZ, p.GX, zi, xi, as, ac);
                 real ks[kRows];
 #pragma unroll
                 for (int r = 0; r < kRows; ++r)
                     ks[r] = w0[r] + kn * (cv[r] * as[r] - sv[r] * ac[r]) + amp * stim[r];
-                storev<kRows>(K + s * Np + i0, ks);
+                storev<kRows>(K + s * Np + k0, ks);
                 pbuf ^= 1;
                 ++n_rhs;
             }
@@ -377,7 +524,7 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                     const real b = real(c_Berr[j]);
                     if (b != real(0)) {
                         real kj[kRows];
-                        loadv<kRows>(K + j * Np + i0, kj);
+                        loadv<kRows>(K + j * Np + k0, kj);
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) e[r] = fma_r(b, kj[r], e[r]);
                     }
@@ -413,9 +560,9 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                 if (save_idx < n_ts && ts[save_idx] <= tnext) {
                     real f0[kRows], pa[kRows], pb[kRows], pc[kRows];
                     {
-                        real k0[kRows], k6[kRows], dm[kRows];
-                        loadv<kRows>(K + i0, k0);
-                        loadv<kRows>(K + 6 * Np + i0, k6);
+                        real kk0[kRows], k6[kRows], dm[kRows];
+                        loadv<kRows>(K + k0, kk0);
+                        loadv<kRows>(K + 6 * Np + k0, k6);
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) dm[r] = real(0);
 #pragma unroll 1
@@ -423,14 +570,14 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                             const real c = real(c_Cmid[j]);
                             if (c != real(0)) {
                                 real kj[kRows];
-                                loadv<kRows>(K + j * Np + i0, kj);
+                                loadv<kRows>(K + j * Np + k0, kj);
 #pragma unroll
                                 for (int r = 0; r < kRows; ++r) dm[r] = fma_r(c, kj[r], dm[r]);
                             }
                         }
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) {
-                            const real f0r = k0[r] * dt, f1r = k6[r] * dt, dmr = dm[r] * dt, d = d1[r];
+                            const real f0r = kk0[r] * dt, f1r = k6[r] * dt, dmr = dm[r] * dt, d = d1[r];
                             f0[r] = f0r;
                             pa[r] = real(2) * (f1r - f0r) - real(8) * d + real(16) * dmr;
                             pb[r] = real(5) * f0r - real(3) * f1r + real(14) * d - real(32) * dmr;
@@ -487,8 +634,8 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                 // ---- accept: y0 <- y1, FSAL k1 <- k7 ------------------------------------
                 {
                     real k6[kRows];
-                    loadv<kRows>(K + 6 * Np + i0, k6);
-                    storev<kRows>(K + i0, k6);
+                    loadv<kRows>(K + 6 * Np + k0, k6);
+                    storev<kRows>(K + k0, k6);
                 }
 #pragma unroll
                 for (int r = 0; r < kRows; ++r) {
@@ -534,7 +681,8 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
 
 inline size_t step_smem_bytes(int Np, int tab, int nthreads, size_t real_bytes) {
     const int nwarps = (nthreads + 31) / 32;
-    return (size_t)(11 * Np + tab) * real_bytes + (size_t)(nwarps * kSampleBatch * 2 + nwarps) * sizeof(double);
+    return (size_t)(11 * Np + 2 * kScPad + tab) * real_bytes +
+           (size_t)(nwarps * kSampleBatch * 2 + nwarps) * sizeof(double);
 }
 
 }  // namespace dbsgym
