@@ -51,8 +51,8 @@ def grid_structure(neur_grid, grid_size):
     g = np.asarray(neur_grid)
     gx, gy, gz = (int(v) for v in grid_size)
     n = g.shape[0]
-    if gy != LINE or n % (gx * gy) != 0 or n > gx * gy * gz:
-        return None
+    if gy != LINE or n % (gx * gy) != 0 or n > gx * gy * gz or (n // LINE) % 32 != 0:
+        return None            # the GRID kernels want whole warps of 8-oscillator lines (n % 256 == 0)
     _, ref = neuron_grid(gx, gy, gz, n, 1.0)
     if g.shape != ref.shape or not np.array_equal(g, ref):
         return None
