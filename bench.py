@@ -290,8 +290,14 @@ def run_gpu_arm(args):
         value = total_env_steps / dev_time_s
         rhs_per_env_step = counters["rhs_evals"] / (B * K)
         substeps_per_env_step = (counters["accepted"] + counters["rejected"]) / (B * K)
-        # algorithmic work of the step kernel: R * 4 N^2 (coupling contraction) + ~700 N
-        flop_per_env_step = rhs_per_env_step * 4 * N_OSC * N_OSC + 700 * N_OSC
+        # Algorithmic work of the step kernel.  Dense formulation: R * 4 N^2 + ~700 N.
+        # The GRID_SYM kernel evaluates the same contraction in the (pz,px) parity-sector basis: N^2 flop
+        # for the four (N/4)^2 sector blocks x {sin,cos}, + 0.1875 N^2 to combine the table rows into the
+        # sector coefficients, + 0.03 N^2 for the quad butterflies = 1.22 N^2 per RHS.  The roofline
+        # fraction is quoted against the kernel's OWN op count (SURVEY.md 8d rule for reduced formulations).
+        dense_flop_per_env_step = rhs_per_env_step * 4 * N_OSC * N_OSC + 700 * N_OSC
+        sym = eng.coupling == "grid" and os.environ.get("DBSGYM_NO_SYM", "") != "1"
+        flop_per_env_step = (rhs_per_env_step * 1.22 * N_OSC * N_OSC + 700 * N_OSC) if sym else dense_flop_per_env_step
         k_step = float(np.mean([m[0] for m in kern_ms])) * 1e-3
         k_obs = float(np.mean([m[1] for m in kern_ms])) * 1e-3
         peaks, peak_src = measured_peaks()
@@ -324,8 +330,10 @@ def run_gpu_arm(args):
             "gpu_launches": 2 * K,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": None,
-                         "kernel": "step_kernel<float,GRID>", "kernel_ms": k_step * 1e3,
-                         "flop_per_env_step": flop_per_env_step,
+                         "kernel": "step_kernel<float,GRID_SYM>" if sym else "step_kernel<float,GRID>",
+                         "kernel_ms": k_step * 1e3, "flop_per_env_step": flop_per_env_step,
+                         "dense_formulation_flop_per_env_step": dense_flop_per_env_step,
+                         "dense_equivalent_tflops": dense_flop_per_env_step * B / k_step / 1e12,
                          "peak_source": "best of the FFMA and FFMA2 micro-benchmarks run in this process (dbsgym_measure_fp32_peak_mode); nominal 74.4",
                          "peak_ffma": peak_ffma, "peak_ffma2": peak_ffma2},
             "roofline_obs": {"bound": "hbm", "achieved": obs_bytes / k_obs / 1e9, "peak": peaks.get("hbm_gbs"),

@@ -13,7 +13,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libdbsgym.so")
+# DBSGYM_LIB selects an alternative build of the same sources (tuning variants, scripts/build_variants.sh)
+LIB_PATH = os.environ.get("DBSGYM_LIB") or os.path.join(CSRC, "libdbsgym.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "dbsgym.h")
 
 F32, F64 = 0, 1
@@ -60,6 +61,8 @@ def sources():
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile ``csrc/api.cu`` for sm_100a into ``csrc/libdbsgym.so`` (cross-compiles without a GPU)."""
+    if os.environ.get("DBSGYM_LIB"):
+        return LIB_PATH
     if not force and os.path.exists(LIB_PATH):
         newest = max(os.path.getmtime(s) for s in sources())
         if os.path.getmtime(LIB_PATH) >= newest:

@@ -227,7 +227,7 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
     p.ts = nullptr; p.n_ts = 0; p.actions = nullptr; p.env_ids = nullptr; p.n_launch = 0; p.mode = MODE_STEP;
 }
 
-template <typename real, int CPL, int MAXT>
+template <typename real, int CPL, int MAXT, int GEO = 0>
 cudaError_t launch_step_t(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
     size_t smem = step_smem_bytes(h->Np, CPL == CPL_DENSE ? 0 : h->tab, h->nthreads, sizeof(real));
     if (h->ctas_per_sm > 0) {
@@ -236,7 +236,7 @@ cudaError_t launch_step_t(DbsGymHandle* h, const StepParams& p, cudaStream_t s) 
         const size_t want = (size_t)(227 * 1024) / (size_t)h->ctas_per_sm - 1024;
         if (want > smem) smem = want & ~(size_t)15;
     }
-    auto kern = step_kernel<real, CPL, MAXT>;
+    auto kern = step_kernel<real, CPL, MAXT, GEO>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -248,6 +248,7 @@ cudaError_t launch_step_t(DbsGymHandle* h, const StepParams& p, cudaStream_t s) 
 template <typename real, int CPL>
 cudaError_t launch_step_m(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
     const int t = h->nthreads;
+    if (CPL == CPL_GRID_SYM && t == 64 && p.GZ == 8 && p.GX == 8) return launch_step_t<real, CPL, 64, 1>(h, p, s);
     if (t <= 64) return launch_step_t<real, CPL, 64>(h, p, s);
     if (t <= 128) return launch_step_t<real, CPL, 128>(h, p, s);
     if (t <= 256) return launch_step_t<real, CPL, 256>(h, p, s);

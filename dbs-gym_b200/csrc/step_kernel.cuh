@@ -28,6 +28,9 @@
 namespace dbsgym {
 
 constexpr int kRows = 8;           // oscillators per thread
+constexpr int kSlots = 6;          // K slots: stage derivative k_{j+1} lives in slot j, except k7 -> slot 1
+                                   // (a[6][1] = b_err[1] = c_mid[1] = 0: k2 is dead once stage 7 starts)
+__device__ __forceinline__ int kslot(int j) { return j == 6 ? 1 : j; }
 constexpr int kSampleBatch = 16;   // dense-output samples reduced per block barrier
 
 enum { MODE_STEP = 0, MODE_TRANSIENT = 1 };
@@ -110,9 +113,25 @@ __device__ __forceinline__ double fma_r(double a, double b, double c) { return f
 
 // sin / cos of a phase.  fp64 follows the reference literally (theta = fmod(y, 2*pi),
 // env.py:253); fp32 phases are kept wrapped, so the library range reduction is exact enough.
+#ifndef DBSGYM_PRECISE_SINCOS
+// range reduction to [-pi, pi] (two-constant Cody-Waite) + MUFU.SIN / MUFU.COS: abs error ~5e-7
+__device__ __forceinline__ void sincos_r(float x, float* s, float* c) {
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, x);
+    r = fmaf(-k, -1.7484555314695172e-07f, r);
+    *s = __sinf(r); *c = __cosf(r);
+}
+__device__ __forceinline__ float cos_r(float x) {
+    const float k = rintf(x * 0.15915494309189535f);
+    float r = fmaf(-k, 6.2831854820251465f, x);
+    r = fmaf(-k, -1.7484555314695172e-07f, r);
+    return __cosf(r);
+}
+#else
 __device__ __forceinline__ void sincos_r(float x, float* s, float* c) { sincosf(x, s, c); }
-__device__ __forceinline__ void sincos_r(double x, double* s, double* c) { sincos(fmod(x, kTwoPi), s, c); }
 __device__ __forceinline__ float  cos_r(float x) { return cosf(x); }
+#endif
+__device__ __forceinline__ void sincos_r(double x, double* s, double* c) { sincos(fmod(x, kTwoPi), s, c); }
 __device__ __forceinline__ double cos_r(double x) { return cos(x); }
 
 // ---- coupling contraction, GRID mode --------------------------------------------------
@@ -255,45 +274,69 @@ __device__ __forceinline__ void couple_grid_sym(const real* __restrict__ bp, con
     }
 }
 
+// fp32: FFMA2 everywhere, and the loop is software pipelined -- the four table rows and the operand line
+// of block b+1 are loaded while the 64 FFMA2 of block b execute (ncu on the un-pipelined version: 22 % of
+// the stall samples were short-scoreboard waits on the LDS issued right before their first use).
+struct SymRows { float4 a00l, a00h, a01l, a01h, a10l, a10h, a11l, a11h; };
+
+__device__ __forceinline__ void sym_load_rows(SymRows& r, const float* __restrict__ T, int GZ, int GX, int NC,
+                                              int zq, int xq, int zj, int xj) {
+    const int dz0 = zq > zj ? zq - zj : zj - zq, dz1 = GZ - 1 - zq - zj;
+    const int dx0 = xq > xj ? xq - xj : xj - xq, dx1 = GX - 1 - xq - xj;
+    const float* t00 = T + (dz0 * GX + dx0) * 4;
+    const float* t01 = T + (dz0 * GX + dx1) * 4;
+    const float* t10 = T + (dz1 * GX + dx0) * 4;
+    const float* t11 = T + (dz1 * GX + dx1) * 4;
+    r.a00l = *reinterpret_cast<const float4*>(t00); r.a00h = *reinterpret_cast<const float4*>(t00 + NC * 4);
+    r.a01l = *reinterpret_cast<const float4*>(t01); r.a01h = *reinterpret_cast<const float4*>(t01 + NC * 4);
+    r.a10l = *reinterpret_cast<const float4*>(t10); r.a10h = *reinterpret_cast<const float4*>(t10 + NC * 4);
+    r.a11l = *reinterpret_cast<const float4*>(t11); r.a11h = *reinterpret_cast<const float4*>(t11 + NC * 4);
+}
+
+__device__ __forceinline__ void sym_combine(const SymRows& r, float2 px2, float2 pz2, float (&u)[kRows]) {
+    auto mix = [&](float a00x, float a00y, float a01x, float a01y, float a10x, float a10y, float a11x, float a11y) {
+        return __ffma2_rn(pz2, __ffma2_rn(px2, make_float2(a11x, a11y), make_float2(a10x, a10y)),
+                          __ffma2_rn(px2, make_float2(a01x, a01y), make_float2(a00x, a00y)));
+    };
+    const float2 u01 = mix(r.a00l.x, r.a00l.y, r.a01l.x, r.a01l.y, r.a10l.x, r.a10l.y, r.a11l.x, r.a11l.y);
+    const float2 u23 = mix(r.a00l.z, r.a00l.w, r.a01l.z, r.a01l.w, r.a10l.z, r.a10l.w, r.a11l.z, r.a11l.w);
+    const float2 u45 = mix(r.a00h.x, r.a00h.y, r.a01h.x, r.a01h.y, r.a10h.x, r.a10h.y, r.a11h.x, r.a11h.y);
+    const float2 u67 = mix(r.a00h.z, r.a00h.w, r.a01h.z, r.a01h.w, r.a10h.z, r.a10h.w, r.a11h.z, r.a11h.w);
+    u[0] = u01.x; u[1] = u01.y; u[2] = u23.x; u[3] = u23.y; u[4] = u45.x; u[5] = u45.y; u[6] = u67.x; u[7] = u67.y;
+}
+
 template <>
 __device__ __forceinline__ void couple_grid_sym<float>(const float* __restrict__ bp, const float* __restrict__ T,
                                                        int GZ, int GX, int zq, int xq, float pz, float px,
                                                        float (&as)[kRows], float (&ac)[kRows]) {
-    const int NC = GZ * GX, HZ = GZ >> 1, HX = GX >> 1;
+    const int NC = GZ * GX, HZ = GZ >> 1, HX = GX >> 1, nblk = HZ * HX;
     float2 acc[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) acc[r] = make_float2(0.f, 0.f);
     const float2 px2 = make_float2(px, px), pz2 = make_float2(pz, pz);
-    for (int zj = 0; zj < HZ; ++zj) {
-        const int dz0 = zq > zj ? zq - zj : zj - zq, dz1 = GZ - 1 - zq - zj;
-        const float* t0 = T + dz0 * GX * 4;
-        const float* t1 = T + dz1 * GX * 4;
-#pragma unroll 1
-        for (int xj = 0; xj < HX; ++xj) {
-            const int dx0 = xq > xj ? xq - xj : xj - xq, dx1 = GX - 1 - xq - xj;
-            float u[kRows];
+    SymRows rows;
+    float bn[2 * kRows];
+    sym_load_rows(rows, T, GZ, GX, NC, zq, xq, 0, 0);
+    loadv<2 * kRows>(bp, bn);
+    int zj = 0, xj = 0;
+#pragma unroll 2
+    for (int blk = 0; blk < nblk; ++blk) {
+        float u[kRows], b[2 * kRows];
+        sym_combine(rows, px2, pz2, u);
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const float4 a00 = *reinterpret_cast<const float4*>(t0 + (q * NC + dx0) * 4);
-                const float4 a01 = *reinterpret_cast<const float4*>(t0 + (q * NC + dx1) * 4);
-                const float4 a10 = *reinterpret_cast<const float4*>(t1 + (q * NC + dx0) * 4);
-                const float4 a11 = *reinterpret_cast<const float4*>(t1 + (q * NC + dx1) * 4);
-                float2 lo = __ffma2_rn(pz2, __ffma2_rn(px2, make_float2(a11.x, a11.y), make_float2(a10.x, a10.y)),
-                                       __ffma2_rn(px2, make_float2(a01.x, a01.y), make_float2(a00.x, a00.y)));
-                float2 hi = __ffma2_rn(pz2, __ffma2_rn(px2, make_float2(a11.z, a11.w), make_float2(a10.z, a10.w)),
-                                       __ffma2_rn(px2, make_float2(a01.z, a01.w), make_float2(a00.z, a00.w)));
-                u[q * 4 + 0] = lo.x; u[q * 4 + 1] = lo.y; u[q * 4 + 2] = hi.x; u[q * 4 + 3] = hi.y;
-            }
-            float b[2 * kRows];
-            loadv<2 * kRows>(bp + (zj * HX + xj) * (2 * kRows), b);
+        for (int i = 0; i < 2 * kRows; ++i) b[i] = bn[i];
+        if (++xj == HX) { xj = 0; ++zj; }
+        if (blk + 1 < nblk) {                       // prefetch block b+1 behind the FMAs of block b
+            sym_load_rows(rows, T, GZ, GX, NC, zq, xq, zj, xj);
+            loadv<2 * kRows>(bp + (blk + 1) * (2 * kRows), bn);
+        }
 #pragma unroll
-            for (int yj = 0; yj < kRows; ++yj) {
-                const float2 scj = make_float2(b[2 * yj], b[2 * yj + 1]);
+        for (int yj = 0; yj < kRows; ++yj) {
+            const float2 scj = make_float2(b[2 * yj], b[2 * yj + 1]);
 #pragma unroll
-                for (int yi = 0; yi < kRows; ++yi) {
-                    const float a = u[yi > yj ? yi - yj : yj - yi];
-                    acc[yi] = __ffma2_rn(make_float2(a, a), scj, acc[yi]);
-                }
+            for (int yi = 0; yi < kRows; ++yi) {
+                const float a = u[yi > yj ? yi - yj : yj - yi];
+                acc[yi] = __ffma2_rn(make_float2(a, a), scj, acc[yi]);
             }
         }
     }
@@ -330,27 +373,35 @@ __device__ __forceinline__ double warp_sum(double v) {
 // =========================================================================================
 // resident CTAs per SM the register allocation is tuned for (fp32: 128 regs/thread)
 template <typename real, int MAXT> struct MinBlocks {
-    static constexpr int v = (sizeof(real) == 4 && MAXT <= 128) ? (512 / MAXT) : 1;
+#ifndef DBSGYM_MINB64
+#define DBSGYM_MINB64 8
+#endif
+    static constexpr int v = (sizeof(real) == 4 && MAXT <= 128) ? (DBSGYM_MINB64 * 64 / MAXT) : 1;
 };
 
 enum { CPL_GRID = 0, CPL_DENSE = 1, CPL_GRID_SYM = 2 };
 constexpr int kScPad = 16;     // reals of padding per operand buffer (GRID_SYM staggers its 4 sectors by 16 B)
 
-template <typename real, int CPL, int MAXT>
+// GEO = 1: the grid extents are the compile-time constants 8 x 8 x 8 (every shipped config), which
+// turns the table / operand address arithmetic of the contraction into immediates.
+template <typename real, int CPL, int MAXT, int GEO = 0>
 __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(const StepParams p) {
     constexpr bool DENSE = CPL == CPL_DENSE;
     constexpr bool SYM = CPL == CPL_GRID_SYM;
+    const int GZ = GEO == 1 ? 8 : p.GZ, GX = GEO == 1 ? 8 : p.GX;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
     const int Np = p.Np;
-    const int tab = DENSE ? 0 : p.GZ * p.GX * kRows;
+    const int tab = DENSE ? 0 : GZ * GX * kRows;
     const int scsz = 2 * Np + kScPad;
 
     real* K = reinterpret_cast<real*>(smem_raw);          // [7][Np] stage derivatives f(y_s), thread-private slots
-    real* SC = K + 7 * Np;                                // [2][scsz] interleaved (sin, cos) contraction operand
+    real* SC = K + kSlots * Np;                                // [2][scsz] interleaved (sin, cos) contraction operand
     real* T = SC + 2 * scsz;                              // [tab]
-    double* part = reinterpret_cast<double*>(T + tab);    // [nwarps][kSampleBatch][2]
+    real* RC = T + tab;                                   // [Np] recording conductance (thread-private slots)
+    int* WD = reinterpret_cast<int*>(RC + Np);            // [Np] fp32 mode: winding counts, y = phase + 2*pi*wind
+    double* part = reinterpret_cast<double*>(WD + Np);    // [nwarps][kSampleBatch][2]
     double* red = part + nwarps * kSampleBatch * 2;       // [nwarps]
 
     const int slot = blockIdx.x;
@@ -363,38 +414,36 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
     int zi = 0, xi = 0, zq = 0, xq = 0;
     real sgn_x = real(1), sgn_z = real(1);
     if (SYM) {
-        const int HX = p.GX >> 1, q = tid >> 2;
+        const int HX = GX >> 1, q = tid >> 2;
         zq = q / HX; xq = q % HX;
-        zi = (tid & 2) ? p.GZ - 1 - zq : zq;
-        xi = (tid & 1) ? p.GX - 1 - xq : xq;
+        zi = (tid & 2) ? GZ - 1 - zq : zq;
+        xi = (tid & 1) ? GX - 1 - xq : xq;
         sgn_x = (tid & 1) ? real(-1) : real(1);
         sgn_z = (tid & 2) ? real(-1) : real(1);
     } else if (!DENSE) {
-        zi = tid / p.GX; xi = tid % p.GX;
+        zi = tid / GX; xi = tid % GX;
     }
-    const int i0 = DENSE ? k0 : (zi * p.GX + xi) * kRows; // first oscillator index in the global arrays
+    const int i0 = DENSE ? k0 : (zi * GX + xi) * kRows; // first oscillator index in the global arrays
     const unsigned wmask = __activemask();
     // operand slot written by this thread: plain = own line; GRID_SYM = sector (tid & 3), line q
-    const int sec_stride = (p.GZ >> 1) * (p.GX >> 1) * 2 * kRows + (int)(16 / sizeof(real));
+    const int sec_stride = (GZ >> 1) * (GX >> 1) * 2 * kRows + (int)(16 / sizeof(real));
     const int sc_sector = SYM ? (tid & 3) * sec_stride : 0;
     const int sc_slot = SYM ? sc_sector + (tid >> 2) * 2 * kRows : 2 * k0;
 
-    real y0[kRows], w0[kRows], stim[kRows], rc[kRows];
-    int wd[kRows];
+    // Register diet: only y0 and (per segment) c0 = w0 + amp * stim stay in registers across the
+    // contraction; the recording conductance and the winding counts live in thread-private shared slots.
+    real y0[kRows];
     loadv<kRows>(reinterpret_cast<const real*>(p.phase) + base + i0, y0);
-    loadv<kRows>(reinterpret_cast<const real*>(p.w0) + base + i0, w0);
-    loadv<kRows>(reinterpret_cast<const real*>(p.stim) + base + i0, stim);
-    if (p.weighted_rec) loadv<kRows>(reinterpret_cast<const real*>(p.rec) + base + i0, rc);
-    else {
+    {
+        real rc[kRows];
+        if (p.weighted_rec) loadv<kRows>(reinterpret_cast<const real*>(p.rec) + base + i0, rc);
+        else {
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) rc[r] = real(0);
-    }
-    if (sizeof(real) == 4) {
+            for (int r = 0; r < kRows; ++r) rc[r] = real(0);
+        }
+        storev<kRows>(RC + k0, rc);
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) wd[r] = p.wind[base + i0 + r];
-    } else {
-#pragma unroll
-        for (int r = 0; r < kRows; ++r) wd[r] = 0;
+        for (int r = 0; r < kRows; ++r) WD[k0 + r] = sizeof(real) == 4 ? p.wind[base + i0 + r] : 0;
     }
     if (!DENSE) {
         const real* tg = reinterpret_cast<const real*>(p.table);
@@ -440,6 +489,14 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
         const double* __restrict__ ts = seg_ts[sg];
         const int n_ts = seg_nts[sg], n_rec = seg_nrec[sg], rec_from = seg_from[sg], out_base = seg_out[sg];
         const real amp = seg_amp[sg];
+        real c0[kRows];                       // w0 + pulse, constant over the segment (env.py:254-255, :421-424)
+        {
+            real w0[kRows], stim[kRows];
+            loadv<kRows>(reinterpret_cast<const real*>(p.w0) + base + i0, w0);
+            loadv<kRows>(reinterpret_cast<const real*>(p.stim) + base + i0, stim);
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) c0[r] = w0[r] + amp * stim[r];
+        }
         const double T_end = ts[n_ts - 1];
         double t = 0.0;
         double tnext = fmin(p.dt0, T_end);
@@ -499,15 +556,15 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                 real as[kRows], ac[kRows];
                 if (DENSE) couple_dense<real>(SC + pbuf * scsz, reinterpret_cast<const real*>(p.alpha), Np, i0, as, ac);
                 else if (SYM) {
-                    couple_grid_sym<real>(SC + pbuf * scsz + sc_sector, T, p.GZ, p.GX, zq, xq, sgn_z, sgn_x, as, ac);
+                    couple_grid_sym<real>(SC + pbuf * scsz + sc_sector, T, GZ, GX, zq, xq, sgn_z, sgn_x, as, ac);
                     quad_butterfly<real>(as, sgn_x, sgn_z, wmask);   // back to the grid lines (x 1/4 folded into kn)
                     quad_butterfly<real>(ac, sgn_x, sgn_z, wmask);
-                } else couple_grid<real>(SC + pbuf * scsz, T, p.GZ, p.GX, zi, xi, as, ac);
+                } else couple_grid<real>(SC + pbuf * scsz, T, GZ, GX, zi, xi, as, ac);
                 real ks[kRows];
 #pragma unroll
                 for (int r = 0; r < kRows; ++r)
-                    ks[r] = w0[r] + kn * (cv[r] * as[r] - sv[r] * ac[r]) + amp * stim[r];
-                storev<kRows>(K + s * Np + k0, ks);
+                    ks[r] = c0[r] + kn * (cv[r] * as[r] - sv[r] * ac[r]);
+                storev<kRows>(K + kslot(s) * Np + k0, ks);
                 pbuf ^= 1;
                 ++n_rhs;
             }
@@ -524,7 +581,7 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                     const real b = real(c_Berr[j]);
                     if (b != real(0)) {
                         real kj[kRows];
-                        loadv<kRows>(K + j * Np + k0, kj);
+                        loadv<kRows>(K + kslot(j) * Np + k0, kj);
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) e[r] = fma_r(b, kj[r], e[r]);
                     }
@@ -532,7 +589,7 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
 #pragma unroll
                 for (int r = 0; r < kRows; ++r) {
                     if (i0 + r < p.N) {
-                        const real yu0 = y0[r] + two_pi_r * real(wd[r]);
+                        const real yu0 = y0[r] + two_pi_r * real(WD[k0 + r]);
                         const real yu1 = yu0 + d1[r];
                         const real scale = atol + fmax(fabs(yu0), fabs(yu1)) * rtol;
                         const double q = (double)((e[r] * dt) / scale);
@@ -562,7 +619,7 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                     {
                         real kk0[kRows], k6[kRows], dm[kRows];
                         loadv<kRows>(K + k0, kk0);
-                        loadv<kRows>(K + 6 * Np + k0, k6);
+                        loadv<kRows>(K + kslot(6) * Np + k0, k6);
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) dm[r] = real(0);
 #pragma unroll 1
@@ -570,7 +627,7 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                             const real c = real(c_Cmid[j]);
                             if (c != real(0)) {
                                 real kj[kRows];
-                                loadv<kRows>(K + j * Np + k0, kj);
+                                loadv<kRows>(K + kslot(j) * Np + k0, kj);
 #pragma unroll
                                 for (int r = 0; r < kRows; ++r) dm[r] = fma_r(c, kj[r], dm[r]);
                             }
@@ -593,6 +650,8 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                                 const bool at_end = (tsv == tnext);
                                 const real tau = (tnext == t) ? real(0) : real((tsv - t) / (tnext - t));
                                 real st = real(0), sr = real(0);
+                                real rc[kRows];
+                                loadv<kRows>(RC + k0, rc);
 #pragma unroll
                                 for (int r = 0; r < kRows; ++r) {
                                     real inc = (((pa[r] * tau + pb[r]) * tau + pc[r]) * tau + f0[r]) * tau;
@@ -634,7 +693,7 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                 // ---- accept: y0 <- y1, FSAL k1 <- k7 ------------------------------------
                 {
                     real k6[kRows];
-                    loadv<kRows>(K + 6 * Np + k0, k6);
+                    loadv<kRows>(K + kslot(6) * Np + k0, k6);
                     storev<kRows>(K + k0, k6);
                 }
 #pragma unroll
@@ -647,7 +706,7 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                             float yw = fmaf(-n, 6.2831854820251465f, (float)y1);
                             yw = fmaf(-n, -1.7484555314695172e-07f, yw);
                             y1 = real(yw);
-                            wd[r] += (int)n;
+                            WD[k0 + r] += (int)n;
                         }
                     }
                     y0[r] = y1;
@@ -668,7 +727,7 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
     storev<kRows>(reinterpret_cast<real*>(p.phase) + base + i0, y0);
     if (sizeof(real) == 4) {
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) p.wind[base + i0 + r] = wd[r];
+        for (int r = 0; r < kRows; ++r) p.wind[base + i0 + r] = WD[k0 + r];
     }
     if (tid == 0) {
         if (p.mode == MODE_TRANSIENT) p.head[env] = 0;
@@ -681,7 +740,7 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
 
 inline size_t step_smem_bytes(int Np, int tab, int nthreads, size_t real_bytes) {
     const int nwarps = (nthreads + 31) / 32;
-    return (size_t)(11 * Np + 2 * kScPad + tab) * real_bytes +
+    return (size_t)((kSlots + 5) * Np + 2 * kScPad + tab) * real_bytes + (size_t)Np * sizeof(int) +
            (size_t)(nwarps * kSampleBatch * 2 + nwarps) * sizeof(double);
 }
 
