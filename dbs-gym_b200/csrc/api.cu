@@ -52,7 +52,9 @@ struct DbsGymHandle {
     // reward
     DbsGymRewardSpec rspec;
     bool have_reward = false;
-    double *lin_g = nullptr, *tw_seed = nullptr, *tw_rot = nullptr;
+    double *lin_g = nullptr, *tw_seed = nullptr;
+    void* tw_inner = nullptr;
+    int obs_iters = 0;
     int nbins = 0;
     // bookkeeping
     unsigned long long* counters = nullptr;
@@ -279,9 +281,9 @@ cudaError_t launch_obs(DbsGymHandle* h, float* obs, float* reward_f, uint8_t* do
     o.power_scale = h->rspec.power_scale; o.action_cost = h->rspec.action_cost;
     o.threshold = h->rspec.threshold; o.threshold_penalty = h->rspec.threshold_penalty;
     o.temp_scale = h->rspec.temp_scale;
-    o.lin_g = h->lin_g; o.tw_seed = h->tw_seed; o.tw_rot = h->tw_rot;
+    o.lin_g = h->lin_g; o.tw_seed = h->tw_seed; o.tw_inner = h->tw_inner; o.iters = h->obs_iters;
     o.append = append; o.env_ids = ids_dev; o.n_launch = n;
-    const size_t smem = (size_t)h->W * sizeof(double);
+    const size_t smem = obs_smem_bytes(h->W, h->nbins, h->obs_iters, h->rb);
     if (h->f64) obs_kernel<double><<<n, kObsThreads, smem, s>>>(o);
     else obs_kernel<float><<<n, kObsThreads, smem, s>>>(o);
     return cudaGetLastError();
@@ -417,7 +419,7 @@ void dbsgym_destroy(DbsGymHandle* h) {
     void* bufs[] = {h->table, h->alpha, h->w0, h->stim, h->rec, h->phase, h->ring, h->wind, h->head, h->n_samples,
                     h->step_idx, h->episode_len, h->lfp_true, h->lfp_rec, h->u, h->reward, h->done, h->sched_nI,
                     h->sched_nII, h->sched_offI, h->sched_offII, h->ts_dev, h->ids_dev, h->lin_g, h->tw_seed,
-                    h->tw_rot, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples};
+                    h->tw_inner, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples};
     for (void* b : bufs)
         if (b) cudaFree(b);
     for (int i = 0; i < 3; ++i)
@@ -559,7 +561,9 @@ int dbsgym_set_reward(DbsGymHandle* h, const DbsGymRewardSpec* spec, const doubl
         const int nb = spec->bin_hi - spec->bin_lo + 1;
         if (spec->bin_lo < 0 || nb <= 0 || nb > kMaxBins || spec->bin_hi > W / 2)
             return fail(h, DBSGYM_EINVAL, "bad rfft bin range [%d,%d] (at most %d bins)", spec->bin_lo, spec->bin_hi, kMaxBins);
-        std::vector<double> seed((size_t)nb * kObsThreads * 2), rot((size_t)nb * 2);
+        const int iters = (W + kObsThreads - 1) / kObsThreads;
+        std::vector<double> seed((size_t)nb * kObsThreads * 2);
+        std::vector<unsigned char> inner((size_t)nb * iters * 2 * h->rb);
         const double two_pi = kTwoPi;
         for (int b = 0; b < nb; ++b) {
             const long long k = spec->bin_lo + b;
@@ -568,17 +572,22 @@ int dbsgym_set_reward(DbsGymHandle* h, const DbsGymRewardSpec* spec, const doubl
                 seed[((size_t)b * kObsThreads + m) * 2] = std::cos(two_pi * (double)q / W);
                 seed[((size_t)b * kObsThreads + m) * 2 + 1] = std::sin(two_pi * (double)q / W);
             }
-            const long long q = (k * kObsThreads) % W;
-            rot[(size_t)b * 2] = std::cos(two_pi * (double)q / W);
-            rot[(size_t)b * 2 + 1] = std::sin(two_pi * (double)q / W);
+            for (int i = 0; i < iters; ++i) {
+                const long long q = (k * (long long)kObsThreads * i) % W;
+                const double c = std::cos(two_pi * (double)q / W), sn = std::sin(two_pi * (double)q / W);
+                const size_t at = ((size_t)b * iters + i) * 2;
+                if (h->f64) { reinterpret_cast<double*>(inner.data())[at] = c; reinterpret_cast<double*>(inner.data())[at + 1] = sn; }
+                else { reinterpret_cast<float*>(inner.data())[at] = (float)c; reinterpret_cast<float*>(inner.data())[at + 1] = (float)sn; }
+            }
         }
         if (h->tw_seed) cudaFree(h->tw_seed);
-        if (h->tw_rot) cudaFree(h->tw_rot);
-        h->tw_seed = h->tw_rot = nullptr;
+        if (h->tw_inner) cudaFree(h->tw_inner);
+        h->tw_seed = nullptr; h->tw_inner = nullptr;
         CU(h, cudaMalloc(&h->tw_seed, seed.size() * 8));
-        CU(h, cudaMalloc(&h->tw_rot, rot.size() * 8));
+        CU(h, cudaMalloc(&h->tw_inner, inner.size()));
         CU(h, cudaMemcpy(h->tw_seed, seed.data(), seed.size() * 8, cudaMemcpyHostToDevice));
-        CU(h, cudaMemcpy(h->tw_rot, rot.data(), rot.size() * 8, cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->tw_inner, inner.data(), inner.size(), cudaMemcpyHostToDevice));
+        h->obs_iters = iters;
         h->nbins = nb;
     }
     h->rspec = *spec;
