@@ -94,9 +94,10 @@ class BatchedKuramoto:
         smax = self.engine.max_step_samples
         self.samples_buf, t = _pinned((B, smax), np.float32); self._pin.append(t)
         self.nsamp_buf, t = _pinned((B,), np.int32); self._pin.append(t)
-        self._slack = self.window
-        self._mirror = np.empty((B, self.window + self._slack), dtype=np.float32) if transfer == "delta" else None
-        self._mirror_off = 0
+        # [B, 2W]: every sample is stored twice (column c and c + W) so the chronological window is always
+        # the contiguous slice [:, pos:pos+W] and nothing ever has to be moved
+        self._mirror = np.empty((B, 2 * self.window), dtype=np.float32) if transfer == "delta" else None
+        self._mirror_pos = 0
         self._mirror_ok = False
         self._lfp_cache = None
         self.current_step = np.zeros(B, dtype=np.int64)
@@ -129,7 +130,8 @@ class BatchedKuramoto:
         obs = self.engine.obs_host(self.obs_buf)
         if self._mirror is not None:
             self._mirror[:, :self.window] = obs
-            self._mirror_off = 0
+            self._mirror[:, self.window:] = obs
+            self._mirror_pos = 0
             self._mirror_ok = True
             return self._mirror[:, :self.window]
         return obs
@@ -142,18 +144,12 @@ class BatchedKuramoto:
         if self._mirror is not None:
             if not self._mirror_ok:
                 self.observations()
-            self.engine.step_host_samples(self.act_buf, self.samples_buf, self.nsamp_buf, self.rew_buf,
-                                          self.done_buf)
+            pos, n = self.engine.step_host_mirror(self.act_buf, self._mirror, self._mirror_pos, self.rew_buf,
+                                                  self.done_buf)
             self.current_step += 1
-            n = int(self.nsamp_buf[0])
-            if np.all(self.nsamp_buf == n):
-                W, off = self.window, self._mirror_off
-                if off + W + n > self._mirror.shape[1]:            # out of slack: compact (rare, amortised)
-                    self._mirror[:, :W] = self._mirror[:, off:off + W].copy()
-                    off = 0
-                self._mirror[:, off + W:off + W + n] = self.samples_buf[:, :n]
-                self._mirror_off = off + n
-                obs = self._mirror[:, off + n:off + n + W]
+            if n >= 0:
+                self._mirror_pos = pos
+                obs = self._mirror[:, pos:pos + self.window]
             else:                                                  # environments out of lockstep: full read-back
                 obs = self.observations()
             return obs, self.rew_buf, self.done_buf.view(np.bool_)

@@ -61,6 +61,8 @@ struct DbsGymHandle {
     int32_t* status = nullptr;
     // host-API staging
     float *st_actions = nullptr, *st_obs = nullptr, *st_reward = nullptr, *st_samples = nullptr;
+    float* pin_samples = nullptr;        // pinned host landing buffers of dbsgym_step_host_mirror
+    int32_t* pin_nsamp = nullptr;
     uint8_t* st_done = nullptr;
     // timing
     int ctas_per_sm = 0;                 // 0 = whatever fits
@@ -397,6 +399,8 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
     A((void**)&h->st_actions, (size_t)h->B * 4); A((void**)&h->st_obs, (size_t)h->B * h->W * 4);
     A((void**)&h->st_reward, (size_t)h->B * 4); A((void**)&h->st_done, (size_t)h->B);
     A((void**)&h->st_samples, (size_t)h->B * h->smax * 4);
+    ok = ok && cudaMallocHost(&h->pin_samples, (size_t)h->B * h->smax * 4) == cudaSuccess;
+    ok = ok && cudaMallocHost(&h->pin_nsamp, (size_t)h->B * 4) == cudaSuccess;
     for (int i = 0; i < 3 && ok; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
     if (ok) {
         // episode_len defaults to "never done"
@@ -422,6 +426,8 @@ void dbsgym_destroy(DbsGymHandle* h) {
                     h->tw_inner, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples};
     for (void* b : bufs)
         if (b) cudaFree(b);
+    if (h->pin_samples) cudaFreeHost(h->pin_samples);
+    if (h->pin_nsamp) cudaFreeHost(h->pin_nsamp);
     for (int i = 0; i < 3; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -688,6 +694,45 @@ int dbsgym_step_host_samples(DbsGymHandle* h, const float* actions, float* sampl
     if (reward) CU(h, cudaMemcpyAsync(reward, h->st_reward, (size_t)h->B * 4, cudaMemcpyDeviceToHost, s));
     if (done) CU(h, cudaMemcpyAsync(done, h->st_done, (size_t)h->B, cudaMemcpyDeviceToHost, s));
     CU(h, cudaStreamSynchronize(s));
+    return DBSGYM_OK;
+}
+
+int dbsgym_step_host_mirror(DbsGymHandle* h, const float* actions, float* mirror, int32_t* pos, int32_t* n_new,
+                            float* reward, uint8_t* done) {
+    int rc = check_ready(h, true);
+    if (rc) return rc;
+    if (!actions || !mirror || !pos || !n_new) return fail(h, DBSGYM_EINVAL, "null argument");
+    const int W = h->W, B = h->B, smax = h->smax;
+    if (*pos < 0 || *pos >= W) return fail(h, DBSGYM_EINVAL, "mirror position %d out of range", *pos);
+    CU(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t s = h->stream;
+    CU(h, cudaMemcpyAsync(h->st_actions, actions, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+    rc = step_impl(h, h->st_actions, nullptr, h->st_reward, h->st_done, s, h->st_samples);
+    if (rc) return rc;
+    CU(h, cudaMemcpyAsync(h->pin_samples, h->st_samples, (size_t)B * smax * 4, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(h->pin_nsamp, h->n_samples, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    if (reward) CU(h, cudaMemcpyAsync(reward, h->st_reward, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    if (done) CU(h, cudaMemcpyAsync(done, h->st_done, (size_t)B, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaStreamSynchronize(s));
+    const int n = h->pin_nsamp[0];
+    for (int b = 1; b < B; ++b)
+        if (h->pin_nsamp[b] != n) { *n_new = -1; return DBSGYM_OK; }
+    const int p0 = *pos;
+    const size_t pitch = (size_t)2 * W;
+    for (int b = 0; b < B; ++b) {
+        float* row = mirror + (size_t)b * pitch;
+        const float* src = h->pin_samples + (size_t)b * smax;
+        for (int i = 0; i < n; ++i) {
+            int c = p0 + i;
+            if (c >= W) c -= W;
+            row[c] = src[i];
+            row[c + W] = src[i];
+        }
+    }
+    int np = p0 + n;
+    if (np >= W) np -= W;
+    *pos = np;
+    *n_new = n;
     return DBSGYM_OK;
 }
 

@@ -173,6 +173,14 @@ class KuramotoEngine:
         self._ck(self.lib.dbsgym_step_host_samples(self._h, _capi.ptr(actions), _capi.ptr(samples),
                                                    _capi.ptr(n_samples), _capi.ptr(reward), _capi.ptr(done)))
 
+    def step_host_mirror(self, actions, mirror, pos, reward, done):
+        """Delta-transfer step that also slides the caller's [B, 2W] host mirror (see dbsgym.h).
+        Returns (new_pos, n_new); n_new == -1 means the environments are out of lockstep."""
+        cpos, cn = C.c_int32(int(pos)), C.c_int32(0)
+        self._ck(self.lib.dbsgym_step_host_mirror(self._h, _capi.ptr(actions), _capi.ptr(mirror), C.byref(cpos),
+                                                  C.byref(cn), _capi.ptr(reward), _capi.ptr(done)))
+        return cpos.value, cn.value
+
     def step_device(self, actions_ptr, obs_ptr=None, reward_ptr=None, done_ptr=None, stream=None):
         """Asynchronous step on raw device pointers (e.g. ``tensor.data_ptr()``)."""
         self._ck(self.lib.dbsgym_step(self._h, actions_ptr, obs_ptr, reward_ptr, done_ptr, _stream(stream)))
