@@ -96,7 +96,7 @@ class BatchedKuramoto:
         self.nsamp_buf, t = _pinned((B,), np.int32); self._pin.append(t)
         # [B, 2W]: every sample is stored twice (column c and c + W) so the chronological window is always
         # the contiguous slice [:, pos:pos+W] and nothing ever has to be moved
-        self._mirror = np.empty((B, 2 * self.window), dtype=np.float32) if transfer == "delta" else None
+        self._mirror = None            # created lazily (needs the first transient to have run)
         self._mirror_pos = 0
         self._mirror_ok = False
         self._lfp_cache = None
@@ -127,32 +127,21 @@ class BatchedKuramoto:
 
     def observations(self):
         """Current observation windows [B, W] float32 (host), read back from the device."""
-        obs = self.engine.obs_host(self.obs_buf)
-        if self._mirror is not None:
-            self._mirror[:, :self.window] = obs
-            self._mirror[:, self.window:] = obs
-            self._mirror_pos = 0
-            self._mirror_ok = True
-            return self._mirror[:, :self.window]
-        return obs
+        return self.engine.obs_host(self.obs_buf)
 
     def step(self, actions):
         """Advance every environment by one step.  Returns host views: obs [B,W] f32, reward [B] f32
         and done [B] bool, all overwritten by later calls (copy what you keep)."""
         self.act_buf[:] = np.asarray(actions, dtype=np.float32).reshape(self.num_envs)
         self._lfp_cache = None
-        if self._mirror is not None:
-            if not self._mirror_ok:
-                self.observations()
-            pos, n = self.engine.step_host_mirror(self.act_buf, self._mirror, self._mirror_pos, self.rew_buf,
-                                                  self.done_buf)
+        if self.transfer == "delta":
+            if self._mirror is None:
+                self._mirror = self.engine.host_mirror()
+            pos, n = self.engine.step_host_mirror(self.act_buf, self.rew_buf, self.done_buf)
             self.current_step += 1
             if n >= 0:
-                self._mirror_pos = pos
-                obs = self._mirror[:, pos:pos + self.window]
-            else:                                                  # environments out of lockstep: full read-back
-                obs = self.observations()
-            return obs, self.rew_buf, self.done_buf.view(np.bool_)
+                return self._mirror[:, pos:pos + self.window], self.rew_buf, self.done_buf.view(np.bool_)
+            return self.observations(), self.rew_buf, self.done_buf.view(np.bool_)   # out of lockstep
         self._obs_flip ^= 1
         self.obs_buf = self._obs_bufs[self._obs_flip]
         self.engine.step_host(self.act_buf, self.obs_buf, self.rew_buf, self.done_buf)

@@ -61,8 +61,10 @@ struct DbsGymHandle {
     int32_t* status = nullptr;
     // host-API staging
     float *st_actions = nullptr, *st_obs = nullptr, *st_reward = nullptr, *st_samples = nullptr;
-    float* pin_samples = nullptr;        // pinned host landing buffers of dbsgym_step_host_mirror
-    int32_t* pin_nsamp = nullptr;
+    float* mirror_host = nullptr;        // pinned + mapped [B][2W] window mirror (dbsgym_host_mirror)
+    float* mirror_dev = nullptr;
+    int32_t* pin_ints = nullptr;         // pinned landing buffer: n_samples[B], head[B]
+    bool mirror_on = false;              // obs kernel writes the mirror (set while a mirror step / reset runs)
     uint8_t* st_done = nullptr;
     // timing
     int ctas_per_sm = 0;                 // 0 = whatever fits
@@ -274,6 +276,7 @@ cudaError_t launch_obs(DbsGymHandle* h, float* obs, float* reward_f, uint8_t* do
                        const int32_t* ids_dev, int n, cudaStream_t s, float* samples_f = nullptr) {
     ObsParams o;
     o.samples_f = samples_f;
+    o.mirror = h->mirror_on ? h->mirror_dev : nullptr;
     o.B = h->B; o.W = h->W; o.smax = h->smax;
     o.ring = h->ring; o.head = h->head;
     o.lfp_rec = h->lfp_rec; o.n_samples = h->n_samples;
@@ -399,8 +402,7 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
     A((void**)&h->st_actions, (size_t)h->B * 4); A((void**)&h->st_obs, (size_t)h->B * h->W * 4);
     A((void**)&h->st_reward, (size_t)h->B * 4); A((void**)&h->st_done, (size_t)h->B);
     A((void**)&h->st_samples, (size_t)h->B * h->smax * 4);
-    ok = ok && cudaMallocHost(&h->pin_samples, (size_t)h->B * h->smax * 4) == cudaSuccess;
-    ok = ok && cudaMallocHost(&h->pin_nsamp, (size_t)h->B * 4) == cudaSuccess;
+    ok = ok && cudaMallocHost(&h->pin_ints, (size_t)h->B * 8) == cudaSuccess;
     for (int i = 0; i < 3 && ok; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
     if (ok) {
         // episode_len defaults to "never done"
@@ -426,8 +428,8 @@ void dbsgym_destroy(DbsGymHandle* h) {
                     h->tw_inner, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples};
     for (void* b : bufs)
         if (b) cudaFree(b);
-    if (h->pin_samples) cudaFreeHost(h->pin_samples);
-    if (h->pin_nsamp) cudaFreeHost(h->pin_nsamp);
+    if (h->pin_ints) cudaFreeHost(h->pin_ints);
+    if (h->mirror_host) cudaFreeHost(h->mirror_host);
     for (int i = 0; i < 3; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -697,42 +699,47 @@ int dbsgym_step_host_samples(DbsGymHandle* h, const float* actions, float* sampl
     return DBSGYM_OK;
 }
 
-int dbsgym_step_host_mirror(DbsGymHandle* h, const float* actions, float* mirror, int32_t* pos, int32_t* n_new,
-                            float* reward, uint8_t* done) {
+int dbsgym_host_mirror(DbsGymHandle* h, float** mirror) {
+    if (!h || !mirror) return fail(h, DBSGYM_EINVAL, "null argument");
+    CU(h, cudaSetDevice(h->cfg.device));
+    if (!h->mirror_host) {
+        const size_t bytes = (size_t)h->B * 2 * h->W * sizeof(float);
+        CU(h, cudaHostAlloc(reinterpret_cast<void**>(&h->mirror_host), bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+        CU(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->mirror_dev), h->mirror_host, 0));
+        // fill it from the current device windows
+        CU(h, cudaStreamSynchronize(h->stream));
+        h->mirror_on = true;
+        CU(h, launch_obs(h, nullptr, nullptr, nullptr, 0, nullptr, h->B, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
+    h->mirror_on = true;
+    *mirror = h->mirror_host;
+    return DBSGYM_OK;
+}
+
+int dbsgym_step_host_mirror(DbsGymHandle* h, const float* actions, int32_t* pos, int32_t* n_new, float* reward,
+                            uint8_t* done) {
     int rc = check_ready(h, true);
     if (rc) return rc;
-    if (!actions || !mirror || !pos || !n_new) return fail(h, DBSGYM_EINVAL, "null argument");
-    const int W = h->W, B = h->B, smax = h->smax;
-    if (*pos < 0 || *pos >= W) return fail(h, DBSGYM_EINVAL, "mirror position %d out of range", *pos);
+    if (!actions || !pos || !n_new) return fail(h, DBSGYM_EINVAL, "null argument");
+    if (!h->mirror_host) return fail(h, DBSGYM_ESTATE, "no host mirror: call dbsgym_host_mirror first");
+    const int B = h->B;
     CU(h, cudaSetDevice(h->cfg.device));
     cudaStream_t s = h->stream;
+    h->mirror_on = true;
     CU(h, cudaMemcpyAsync(h->st_actions, actions, (size_t)B * 4, cudaMemcpyHostToDevice, s));
-    rc = step_impl(h, h->st_actions, nullptr, h->st_reward, h->st_done, s, h->st_samples);
+    rc = step_impl(h, h->st_actions, nullptr, h->st_reward, h->st_done, s, nullptr);
     if (rc) return rc;
-    CU(h, cudaMemcpyAsync(h->pin_samples, h->st_samples, (size_t)B * smax * 4, cudaMemcpyDeviceToHost, s));
-    CU(h, cudaMemcpyAsync(h->pin_nsamp, h->n_samples, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(h->pin_ints, h->n_samples, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    CU(h, cudaMemcpyAsync(h->pin_ints + B, h->head, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
     if (reward) CU(h, cudaMemcpyAsync(reward, h->st_reward, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
     if (done) CU(h, cudaMemcpyAsync(done, h->st_done, (size_t)B, cudaMemcpyDeviceToHost, s));
     CU(h, cudaStreamSynchronize(s));
-    const int n = h->pin_nsamp[0];
-    for (int b = 1; b < B; ++b)
-        if (h->pin_nsamp[b] != n) { *n_new = -1; return DBSGYM_OK; }
-    const int p0 = *pos;
-    const size_t pitch = (size_t)2 * W;
-    for (int b = 0; b < B; ++b) {
-        float* row = mirror + (size_t)b * pitch;
-        const float* src = h->pin_samples + (size_t)b * smax;
-        for (int i = 0; i < n; ++i) {
-            int c = p0 + i;
-            if (c >= W) c -= W;
-            row[c] = src[i];
-            row[c + W] = src[i];
-        }
-    }
-    int np = p0 + n;
-    if (np >= W) np -= W;
-    *pos = np;
-    *n_new = n;
+    const int n = h->pin_ints[0], hd = h->pin_ints[B];
+    bool uniform = true;
+    for (int b = 1; b < B && uniform; ++b) uniform = h->pin_ints[b] == n && h->pin_ints[B + b] == hd;
+    *pos = hd;
+    *n_new = uniform ? n : -1;
     return DBSGYM_OK;
 }
 
@@ -833,7 +840,13 @@ int dbsgym_set_window(DbsGymHandle* h, const int32_t* env_ids, int32_t n, const 
     rc = scatter_to_device(h, h->ring, buf.data(), ids, n, (size_t)h->W * h->rb);
     if (rc) return rc;
     std::vector<int32_t> z((size_t)n, 0);
-    return scatter_to_device(h, h->head, z.data(), ids, n, 4);
+    rc = scatter_to_device(h, h->head, z.data(), ids, n, 4);
+    if (rc) return rc;
+    if (h->mirror_on) {                             // keep the host mirror in sync with the overwritten rings
+        CU(h, launch_obs(h, nullptr, nullptr, nullptr, 0, ids, n, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
+    return DBSGYM_OK;
 }
 
 int dbsgym_get_episode(DbsGymHandle* h, int32_t* step_idx, uint8_t* done) {

@@ -27,7 +27,7 @@ struct ObsParams {
     int B, W, smax;
     void* ring; int32_t* head;
     const double* lfp_rec; const int32_t* n_samples;
-    float* obs; float* samples_f; float* reward_f; double* reward; uint8_t* done_out; uint8_t* done_dev;
+    float* obs; float* samples_f; float* mirror; float* reward_f; double* reward; uint8_t* done_out; uint8_t* done_dev;
     int32_t* step_idx; const int32_t* episode_len; const double* u;
     int kind, nbins;
     double power_scale, action_cost, threshold, threshold_penalty, temp_scale;
@@ -73,6 +73,11 @@ __global__ void __launch_bounds__(kObsThreads) obs_kernel(const ObsParams p) {
         ring[pos] = v;
         xs[pos] = v;
         if (p.samples_f) p.samples_f[(size_t)env * p.smax + i] = (float)v;
+        if (p.mirror) {                               // zero-copy store into the pinned host mirror (both copies)
+            float* mr = p.mirror + (size_t)env * 2 * W;
+            mr[pos] = (float)v;
+            mr[pos + W] = (float)v;
+        }
     }
     int new_head = head + S;
     if (new_head >= W) new_head -= W;
@@ -86,7 +91,13 @@ __global__ void __launch_bounds__(kObsThreads) obs_kernel(const ObsParams p) {
             o[n] = (float)xs[m];
         }
     }
-    if (!p.append) return;
+    if (!p.append) {
+        if (p.mirror) {                               // reset / refresh: the whole window, ring storage order
+            float* mr = p.mirror + (size_t)env * 2 * W;
+            for (int m = tid; m < W; m += kObsThreads) { const float v = (float)xs[m]; mr[m] = v; mr[m + W] = v; }
+        }
+        return;
+    }
 
     if (p.kind == 1) {                                // R2: g . window (chronological order)
         double acc = 0.0;

@@ -173,12 +173,18 @@ class KuramotoEngine:
         self._ck(self.lib.dbsgym_step_host_samples(self._h, _capi.ptr(actions), _capi.ptr(samples),
                                                    _capi.ptr(n_samples), _capi.ptr(reward), _capi.ptr(done)))
 
-    def step_host_mirror(self, actions, mirror, pos, reward, done):
-        """Delta-transfer step that also slides the caller's [B, 2W] host mirror (see dbsgym.h).
-        Returns (new_pos, n_new); n_new == -1 means the environments are out of lockstep."""
-        cpos, cn = C.c_int32(int(pos)), C.c_int32(0)
-        self._ck(self.lib.dbsgym_step_host_mirror(self._h, _capi.ptr(actions), _capi.ptr(mirror), C.byref(cpos),
-                                                  C.byref(cn), _capi.ptr(reward), _capi.ptr(done)))
+    def host_mirror(self):
+        """Pinned [B, 2W] float32 host array the GPU keeps in sync with the observation rings (dbsgym.h)."""
+        ptr = C.POINTER(C.c_float)()
+        self._ck(self.lib.dbsgym_host_mirror(self._h, C.byref(ptr)))
+        return np.ctypeslib.as_array(ptr, shape=(self.n_envs, 2 * self.window))
+
+    def step_host_mirror(self, actions, reward, done):
+        """One step; the host mirror is updated by the GPU.  Returns (pos, n_new): the chronological window of
+        every environment is mirror[:, pos:pos+W]; n_new == -1 means the environments are out of lockstep."""
+        cpos, cn = C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.dbsgym_step_host_mirror(self._h, _capi.ptr(actions), C.byref(cpos), C.byref(cn),
+                                                  _capi.ptr(reward), _capi.ptr(done)))
         return cpos.value, cn.value
 
     def step_device(self, actions_ptr, obs_ptr=None, reward_ptr=None, done_ptr=None, stream=None):

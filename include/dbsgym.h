@@ -149,14 +149,18 @@ int dbsgym_step_host(DbsGymHandle* h, const float* actions, float* obs,
  * slide its own copy (obs_{t+1} = concat(obs_t[n:], samples)).  reward / done as above. */
 int dbsgym_step_host_samples(DbsGymHandle* h, const float* actions, float* samples,
                              int32_t* n_samples, float* reward, uint8_t* done);
-/* Same, but the library also maintains the caller's host mirror of the windows: `mirror` is
- * float32 [B][2*W]; every sample is stored twice, at column c and c + W, so that the chronological
- * window of environment b is always the CONTIGUOUS slice mirror[b][*pos .. *pos + W - 1] and no data
- * ever has to be moved.  *pos (column of the oldest sample, same for all environments) is advanced by
- * the number of new samples, which is returned in *n_new; if the environments did not all produce the
- * same number of samples (they are out of lockstep) the mirror is left untouched and *n_new = -1. */
-int dbsgym_step_host_mirror(DbsGymHandle* h, const float* actions, float* mirror, int32_t* pos,
-                            int32_t* n_new, float* reward, uint8_t* done);
+/* Host mirror of the observation windows, written by the GPU itself.  dbsgym_host_mirror() returns
+ * (allocating on first use) a pinned, device-mapped float32 array [B][2*W] owned by the library.  The
+ * observation kernel stores every window sample twice through PCIe, at its ring column c and at c + W,
+ * so the chronological window of environment b is always the CONTIGUOUS slice
+ * mirror[b][pos .. pos + W - 1] and no data ever has to be moved or re-copied by the CPU.
+ * dbsgym_step_host_mirror() = one step; only actions (H2D) and reward / done / the new samples (D2H,
+ * zero-copy) cross PCIe.  *pos receives the column of the oldest sample and *n_new the number of new
+ * samples; if the environments are out of lockstep (different ring positions) *n_new = -1 and the caller
+ * must use per-environment positions (dbsgym_get_episode / dbsgym_get_obs_host) instead. */
+int dbsgym_host_mirror(DbsGymHandle* h, float** mirror);
+int dbsgym_step_host_mirror(DbsGymHandle* h, const float* actions, int32_t* pos, int32_t* n_new,
+                            float* reward, uint8_t* done);
 /* reset observation (window as float32) of all environments to a host buffer [B][W] */
 int dbsgym_get_obs_host(DbsGymHandle* h, float* obs);
 
