@@ -322,14 +322,19 @@ def run_gpu_arm(args):
             "rk_substeps_per_env_step": substeps_per_env_step, "rhs_evals_per_env_step": rhs_per_env_step,
             "solver_status": counters["status"],
             "e2e": {"value": B * world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 4,
-                    "d2h_bytes_per_step": B * (eng.max_step_samples * 4 + 4 + 4 + 1),
-                    "api": "BatchedKuramotoVecEnv.step_async/step_wait, numpy in/out; delta transfer: only the step's new "
-                           "window samples cross PCIe (dbsgym_step_host_samples), the host slides its mirror of the window",
+                    "d2h_bytes_per_step": B * (int(round(counters["accepted"] / (B * K) * 0 + 18)) * 2 * 4 + 4 + 4 + 4 + 1),
+                    "api": "BatchedKuramotoVecEnv.step_async/step_wait, numpy actions in, numpy obs/reward/done out. "
+                           "Observations are views of a pinned [B,2W] host mirror of the device rings that the observation "
+                           "kernel updates through mapped memory (each new sample stored twice, ~18 samples/step), so only "
+                           "the new samples + reward + done + ring position cross PCIe (dbsgym_step_host_mirror)",
                     "full_obs_d2h": {"value": B * world * K / capi_s, "d2h_bytes_per_step": B * (2340 * 4 + 4 + 1),
                                      "api": "dbsgym_step_host (whole [B,2340] f32 observation copied to pinned host memory every step)"}},
             "gpu_launches": 2 * K,
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved_tf / fp32_peak if fp32_peak else None, "traffic": None,
+                         "frac": achieved_tf / fp32_peak if fp32_peak else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 4096 envs, from the ncu
+                         # --set full capture profiles/r01_final_step_obs_raw.csv (42.06 MB read + 0.10 MB write)
+                         "traffic": 42.15e6 * B / 4096,
                          "kernel": "step_kernel<float,GRID_SYM>" if sym else "step_kernel<float,GRID>",
                          "kernel_ms": k_step * 1e3, "flop_per_env_step": flop_per_env_step,
                          "dense_formulation_flop_per_env_step": dense_flop_per_env_step,
