@@ -80,3 +80,33 @@ class PIDController:
         self.action = self.compute(e if n > 1 else float(e[0]))
         a = np.broadcast_to(np.asarray(self.action, dtype=np.float32), (n,)).astype(np.float32)
         return [a], None
+
+
+class BatchedPID:
+    """PID controller for a whole batch, driven by the reward the GPU already computed.
+
+    The reference's controller (simple_dbs.py:81-95) takes ``e = -reward_func(window, [a_prev])`` with the
+    *normalised* previous action in the penalty term, while the environment's own reward uses the rescaled
+    amplitude ``u = rescale(a_prev)``.  For the two beta-power rewards the band-power term is identical, so
+    ``e = -reward_env - cost * (|u| - |a_prev|)`` and no FFT is needed on the host.  One PID state per env.
+    """
+
+    def __init__(self, Kp, Ki, Kd, dt, n_envs, u_max=1., u_min=-1., action_cost=1e-2, action_bounds=(-5., 5.)):
+        self.Kp, self.Ki, self.Kd, self.dt = Kp, Ki, Kd, dt
+        self.u_max, self.u_min = u_max, u_min
+        self.cost, self.lo, self.hi = action_cost, action_bounds[0], action_bounds[1]
+        self.action = np.zeros(n_envs)
+        self.integral = np.zeros(n_envs)
+        self.prev_error = np.ones(n_envs)
+
+    def error_from_reward(self, reward):
+        u = self.lo + (self.hi - self.lo) * (self.action + 1.0) / 2.0
+        return -np.asarray(reward, dtype=np.float64) - self.cost * (np.abs(u) - np.abs(self.action))
+
+    def act(self, error):
+        self.integral = self.integral + error * self.dt
+        derivative = (error - self.prev_error) / self.dt if self.dt != 0 else 0.0
+        out = self.Kp * error + self.Ki * self.integral + self.Kd * derivative
+        self.prev_error = error
+        self.action = np.clip(out, self.u_min, self.u_max)
+        return self.action.astype(np.float32)
