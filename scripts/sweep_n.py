@@ -1,0 +1,56 @@
+#!/usr/bin/env python
+"""Oscillator-count sweep (BASELINE configs[4]) on the resident-state GRID kernel: 8 x 8 x gz grids
+(lines of 8 along y, gz z-planes), N = 64*gz, holding B*N = 2 097 152.  cos coupling, K/N scaling as in
+env.py:264.  Engine-level (device-resident) timing, one GPU.  N >= 8192 does not fit the one-CTA-per-env
+design (state > 227 KB of shared memory) and is future work."""
+import json, os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from dbsgym_b200.engine import KuramotoEngine
+from dbsgym_b200.geometry import coupling_table, neuron_grid, ElectrodeModel
+from dbsgym_b200.schedule import StepSchedule, transient_grid
+
+out = []
+for gz in (4, 8, 16, 32, 64):
+    N = 64 * gz
+    B = 2097152 // N
+    coords, grid = neuron_grid(8, 8, gz, N, 0.1)
+    table = coupling_table(coords, grid, [8, 8, gz], "cos")
+    assert table is not None
+    eng = KuramotoEngine(B, N, [8, 8, gz], 2340, 0.52, precision="f32", coupling_table=table)
+    tt = transient_grid(200.0, 0.05)
+    sched = StepSchedule(400, tt[-1], 0.15, 0.75, 0.05)
+    eng.set_schedule(sched); eng.set_reward("bbpow_action", 0.05)
+    rng = np.random.default_rng(gz)
+    el = ElectrodeModel([8, 8, gz], grid, 0.1, [[min(gz - 1, 4), 3, 4]], [[1, 1, 1]], [0.])   # index formula needs a cube; any in-range contact
+    stim = np.tile(np.where(np.arange(N) % 7 == 0, 0.5, 0.1), (B, 1)) if el.elec_idxs[0] >= N else np.tile(el.stim_vector(), (B, 1))
+    w0 = np.abs(rng.normal(0.6, 0.4, (B, N))) + 0.02
+    y0 = rng.normal(np.pi, 0.6, (B, N))
+    eng.set_env_params(None, w0=w0, stim=stim, rec=stim, y0=y0)
+    eng.set_episode(None, step_idx=0, episode_len=2 ** 30)
+    t0 = time.perf_counter(); eng.transient(tt); torch.cuda.synchronize(); t_tr = time.perf_counter() - t0
+    dev = torch.device("cuda", 0)
+    act = torch.from_numpy(rng.uniform(-1, 1, (40, B)).astype(np.float32)).to(dev)
+    obs = torch.empty((B, 2340), dtype=torch.float32, device=dev)
+    rew = torch.empty(B, dtype=torch.float32, device=dev); done = torch.empty(B, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    eng.set_timing(True); eng.counters(reset=True)
+    for i in range(5):
+        eng.step_device(act[i].data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), st)
+    torch.cuda.synchronize(); eng.counters(reset=True)
+    ms = []
+    for i in range(5, 35):
+        eng.step_device(act[i].data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), st)
+        torch.cuda.synchronize(); ms.append(eng.last_step_ms())
+    c = eng.counters()
+    k_step, k_obs = np.mean([m[0] for m in ms]), np.mean([m[1] for m in ms])
+    rhs = c["rhs_evals"] / (30 * B)
+    out.append({"N": N, "grid": [8, 8, gz], "envs": B, "step_kernel_ms": float(k_step), "obs_kernel_ms": float(k_obs),
+                "env_steps_per_s": B / ((k_step + k_obs) * 1e-3), "oscillator_updates_per_s": B * N * (c["accepted"] + c["rejected"]) / (30 * B) / ((k_step + k_obs) * 1e-3),
+                "rhs_per_env_step": rhs, "executed_tflops": rhs * 1.22 * N * N * B / (k_step * 1e-3) / 1e12,
+                "dense_equivalent_tflops": rhs * 4 * N * N * B / (k_step * 1e-3) / 1e12,
+                "transient_s": t_tr, "status": c["status"]})
+    print(json.dumps(out[-1]), flush=True)
+    eng.close()
