@@ -24,8 +24,11 @@ for gz in (4, 8, 16, 32, 64):
     sched = StepSchedule(400, tt[-1], 0.15, 0.75, 0.05)
     eng.set_schedule(sched); eng.set_reward("bbpow_action", 0.05)
     rng = np.random.default_rng(gz)
-    el = ElectrodeModel([8, 8, gz], grid, 0.1, [[min(gz - 1, 4), 3, 4]], [[1, 1, 1]], [0.])   # index formula needs a cube; any in-range contact
-    stim = np.tile(np.where(np.arange(N) % 7 == 0, 0.5, 0.1), (B, 1)) if el.elec_idxs[0] >= N else np.tile(el.stim_vector(), (B, 1))
+    # env.py:94's contact-index formula assumes a cubic grid; for the elongated sweep grids the contact is
+    # simply the neuron nearest to the grid centre, with the reference's conductance law max(0, 1 - 0.1 d)
+    from dbsgym_b200.geometry import distances_from
+    centre = int(np.argmin(np.abs(grid - np.array([4, 3, gz // 2])).sum(axis=1)))
+    stim = np.tile(np.maximum(0.0, 1.0 - distances_from(grid * 0.1, [centre])[0]), (B, 1))
     w0 = np.abs(rng.normal(0.6, 0.4, (B, N))) + 0.02
     y0 = rng.normal(np.pi, 0.6, (B, N))
     eng.set_env_params(None, w0=w0, stim=stim, rec=stim, y0=y0)
