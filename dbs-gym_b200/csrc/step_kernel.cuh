@@ -344,6 +344,54 @@ __device__ __forceinline__ void couple_grid_sym<float>(const float* __restrict__
     for (int r = 0; r < kRows; ++r) { as[r] = acc[r].x; ac[r] = acc[r].y; }
 }
 
+// Compile-time extents (GEO = 1: 8 x 8 x 8 grid, HZ = HX = 4): the 16 (zj,xj) blocks are fully unrolled, so every
+// |zq-zj| / |xq-xj| offset is computed once, the mirrored rows are reached through immediates, and the
+// scheduler can hoist the loads of block b+1 above the FFMA2 of block b (ncu on the rolled loop: 76 FFMA2 but
+// ~108 other instructions per block, mostly address arithmetic and operand copies).
+template <int HZ, int HX>
+__device__ __forceinline__ void couple_grid_sym_fixed(const float* __restrict__ bp, const float* __restrict__ T,
+                                                      int zq, int xq, float pz, float px,
+                                                      float (&as)[kRows], float (&ac)[kRows]) {
+    constexpr int GZ = 2 * HZ, GX = 2 * HX, NC = GZ * GX;
+    float2 acc[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) acc[r] = make_float2(0.f, 0.f);
+    const float2 px2 = make_float2(px, px), pz2 = make_float2(pz, pz);
+    const float* tz1 = T + ((GZ - 1 - zq) * GX + (GX - 1 - xq)) * 4;      // row (dz1, dx1) of block (0,0); moves by immediates
+#pragma unroll
+    for (int zj = 0; zj < HZ; ++zj) {
+        const int dz0 = zq > zj ? zq - zj : zj - zq;
+        const float* tz0 = T + dz0 * GX * 4;
+#pragma unroll
+        for (int xj = 0; xj < HX; ++xj) {
+            const int dx0 = xq > xj ? xq - xj : xj - xq;
+            SymRows r;
+            const float* t00 = tz0 + dx0 * 4;
+            const float* t01 = tz0 + (GX - 1 - xq) * 4 - xj * 4;
+            const float* t10 = tz1 - zj * GX * 4 + (dx0 - (GX - 1 - xq)) * 4;
+            const float* t11 = tz1 - (zj * GX + xj) * 4;
+            r.a00l = *reinterpret_cast<const float4*>(t00); r.a00h = *reinterpret_cast<const float4*>(t00 + NC * 4);
+            r.a01l = *reinterpret_cast<const float4*>(t01); r.a01h = *reinterpret_cast<const float4*>(t01 + NC * 4);
+            r.a10l = *reinterpret_cast<const float4*>(t10); r.a10h = *reinterpret_cast<const float4*>(t10 + NC * 4);
+            r.a11l = *reinterpret_cast<const float4*>(t11); r.a11h = *reinterpret_cast<const float4*>(t11 + NC * 4);
+            float u[kRows], b[2 * kRows];
+            sym_combine(r, px2, pz2, u);
+            loadv<2 * kRows>(bp + (zj * HX + xj) * (2 * kRows), b);
+#pragma unroll
+            for (int yj = 0; yj < kRows; ++yj) {
+                const float2 scj = make_float2(b[2 * yj], b[2 * yj + 1]);
+#pragma unroll
+                for (int yi = 0; yi < kRows; ++yi) {
+                    const float a = u[yi > yj ? yi - yj : yj - yi];
+                    acc[yi] = __ffma2_rn(make_float2(a, a), scj, acc[yi]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) { as[r] = acc[r].x; ac[r] = acc[r].y; }
+}
+
 // ---- coupling contraction, DENSE mode (alpha^T streamed from global / L2) -----------------
 template <typename real>
 __device__ __forceinline__ void couple_dense(const real* __restrict__ sc, const real* __restrict__ alphaT,
@@ -485,6 +533,7 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
         seg_ts[1] = nullptr; seg_nts[1] = seg_nrec[1] = seg_from[1] = seg_out[1] = 0; seg_amp[1] = real(0);
     }
 
+#pragma unroll 1
     for (int sg = 0; sg < nseg; ++sg) {
         const double* __restrict__ ts = seg_ts[sg];
         const int n_ts = seg_nts[sg], n_rec = seg_nrec[sg], rec_from = seg_from[sg], out_base = seg_out[sg];
@@ -548,15 +597,16 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                     }
                     storev<2 * kRows>(SC + pbuf * scsz + sc_slot, scw);
                 }
-                if (s == 6) {
-#pragma unroll
-                    for (int r = 0; r < kRows; ++r) d1[r] = inc[r];
-                }
                 __syncthreads();
                 real as[kRows], ac[kRows];
                 if (DENSE) couple_dense<real>(SC + pbuf * scsz, reinterpret_cast<const real*>(p.alpha), Np, i0, as, ac);
                 else if (SYM) {
-                    couple_grid_sym<real>(SC + pbuf * scsz + sc_sector, T, GZ, GX, zq, xq, sgn_z, sgn_x, as, ac);
+                    if (GEO == 1 && sizeof(real) == 4)
+                        couple_grid_sym_fixed<4, 4>(reinterpret_cast<const float*>(SC + pbuf * scsz + sc_sector),
+                                                    reinterpret_cast<const float*>(T), zq, xq, (float)sgn_z, (float)sgn_x,
+                                                    reinterpret_cast<float(&)[kRows]>(as), reinterpret_cast<float(&)[kRows]>(ac));
+                    else
+                        couple_grid_sym<real>(SC + pbuf * scsz + sc_sector, T, GZ, GX, zq, xq, sgn_z, sgn_x, as, ac);
                     quad_butterfly<real>(as, sgn_x, sgn_z, wmask);   // back to the grid lines (x 1/4 folded into kn)
                     quad_butterfly<real>(ac, sgn_x, sgn_z, wmask);
                 } else couple_grid<real>(SC + pbuf * scsz, T, GZ, GX, zi, xi, as, ac);
@@ -569,6 +619,24 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                 ++n_rhs;
             }
             have_f0 = true;
+            // d1 = y1 - y0 = dt * sum_j b_j k_j, recomputed here (bit-identical to the last stage's increment) so that
+            // the stage loop body stays uniform and the compiler keeps ONE copy of the unrolled contraction
+            {
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) d1[r] = real(0);
+#pragma unroll 1
+                for (int j = 0; j < 6; ++j) {
+                    const real a = real(c_A[6][j]);
+                    if (a != real(0)) {
+                        real kj[kRows];
+                        loadv<kRows>(K + j * Np + k0, kj);
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) d1[r] = fma_r(a, kj[r], d1[r]);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < kRows; ++r) d1[r] *= dt;
+            }
 
             // ---- embedded error estimate and step-size controller ----------------------
             double sq = 0.0;

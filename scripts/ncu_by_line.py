@@ -24,7 +24,7 @@ for l in dis[start + 1:]:
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
         seq.append((m.group(2).strip(), cur))
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:step_kernel"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hi = [i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r][0]
 h = rows[hi]; idx = {n: i for i, n in enumerate(h)}
@@ -38,6 +38,8 @@ for r in rows[hi + 1:]:
                     {s: int(r[idx[s]] or 0) for s in stalls}))
     except ValueError:
         pass
+if len(ncu) > len(seq) and len(ncu) % len(seq) == 0:
+    ncu = ncu[:len(seq)]          # several captured launches of the same kernel: use the first
 assert len(ncu) == len(seq), (len(ncu), len(seq))
 ex, sm, ops, ops_s, st = defaultdict(int), defaultdict(int), Counter(), Counter(), Counter()
 for (sass, loc), (s2, e, ns, sd) in zip(seq, ncu):
