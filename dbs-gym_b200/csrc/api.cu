@@ -569,7 +569,7 @@ int dbsgym_set_reward(DbsGymHandle* h, const DbsGymRewardSpec* spec, const doubl
         const int nb = spec->bin_hi - spec->bin_lo + 1;
         if (spec->bin_lo < 0 || nb <= 0 || nb > kMaxBins || spec->bin_hi > W / 2)
             return fail(h, DBSGYM_EINVAL, "bad rfft bin range [%d,%d] (at most %d bins)", spec->bin_lo, spec->bin_hi, kMaxBins);
-        const int iters = (W + kObsThreads - 1) / kObsThreads;
+        const int iters = ((W + kObsThreads - 1) / kObsThreads + 1) & ~1;   // even: table rows stay 16-byte aligned
         std::vector<double> seed((size_t)nb * kObsThreads * 2);
         std::vector<unsigned char> inner((size_t)nb * iters * 2 * h->rb);
         const double two_pi = kTwoPi;

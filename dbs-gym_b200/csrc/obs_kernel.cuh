@@ -39,6 +39,17 @@ struct ObsParams {
     const int32_t* env_ids; int n_launch;
 };
 
+template <int CNT>
+__device__ __forceinline__ void loadv(const float* __restrict__ p, float* o) {
+#pragma unroll
+    for (int q = 0; q < CNT / 4; ++q) { const float4 v = reinterpret_cast<const float4*>(p)[q]; o[4*q] = v.x; o[4*q+1] = v.y; o[4*q+2] = v.z; o[4*q+3] = v.w; }
+}
+template <int CNT>
+__device__ __forceinline__ void loadv(const double* __restrict__ p, double* o) {
+#pragma unroll
+    for (int q = 0; q < CNT / 2; ++q) { const double2 v = reinterpret_cast<const double2*>(p)[q]; o[2*q] = v.x; o[2*q+1] = v.y; }
+}
+
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -124,9 +135,16 @@ __global__ void __launch_bounds__(kObsThreads) obs_kernel(const ObsParams p) {
             const real* tw = twi + (size_t)kb * p.iters * 2;
             real re = real(0), im = real(0);
             if (in_regs) {
+                // the table row is read with 128-bit loads (broadcast): two iterations per LDS for float
+                constexpr int kPer = 16 / (2 * sizeof(real));       // (cos,sin) pairs per 16 bytes
 #pragma unroll
-                for (int i = 0; i < kMaxIters; ++i) {
-                    if (i < p.iters) { re += xr[i] * tw[2 * i]; im += xr[i] * tw[2 * i + 1]; }
+                for (int i = 0; i < kMaxIters; i += kPer) {
+                    if (i < p.iters) {
+                        real t[2 * kPer];
+                        loadv<2 * kPer>(tw + 2 * i, t);
+#pragma unroll
+                        for (int e = 0; e < kPer; ++e) { re += xr[i + e] * t[2 * e]; im += xr[i + e] * t[2 * e + 1]; }
+                    }
                 }
             } else {
                 for (int i = 0; i < p.iters; ++i) {
