@@ -417,6 +417,11 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 
 // =========================================================================================
 // resident CTAs per SM the register allocation is tuned for (fp32: 128 regs/thread)
@@ -494,8 +499,10 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
         for (int r = 0; r < kRows; ++r) WD[k0 + r] = sizeof(real) == 4 ? p.wind[base + i0 + r] : 0;
     }
     if (!DENSE) {
-        const real* tg = reinterpret_cast<const real*>(p.table);
-        for (int i = tid; i < tab; i += nt) T[i] = tg[i];
+        using V = typename Vec<real>::T;
+        constexpr int vn = Vec<real>::n;
+        const V* tg = reinterpret_cast<const V*>(p.table);
+        for (int i = tid; i < tab / vn; i += nt) reinterpret_cast<V*>(T)[i] = tg[i];
     }
     __syncthreads();
 
@@ -639,8 +646,9 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
             }
 
             // ---- embedded error estimate and step-size controller ----------------------
-            double sq = 0.0;
+            double sq;
             {
+                real sqr = real(0);               // 8 terms in the compute precision, then float64 across the CTA
                 real e[kRows];
 #pragma unroll
                 for (int r = 0; r < kRows; ++r) e[r] = real(0);
@@ -660,10 +668,11 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                         const real yu0 = y0[r] + two_pi_r * real(WD[k0 + r]);
                         const real yu1 = yu0 + d1[r];
                         const real scale = atol + fmax(fabs(yu0), fabs(yu1)) * rtol;
-                        const double q = (double)((e[r] * dt) / scale);
-                        sq += q * q;
+                        const real q = (e[r] * dt) / scale;
+                        sqr = fma_r(q, q, sqr);
                     }
                 }
+                sq = (double)sqr;
             }
             sq = warp_sum(sq);
             if (lane == 0) red[warp] = sq;
@@ -727,10 +736,11 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                                     const real c = cos_r(y0[r] + inc);
                                     if (i0 + r < p.N) { st += c; sr = fma_r(c, rc[r], sr); }
                                 }
-                                const double wt = warp_sum((double)st), wr = warp_sum((double)sr);
+                                // 256 terms of magnitude <= 1 per warp: the compute precision is ample here
+                                const real wt = warp_sum(st), wr = warp_sum(sr);
                                 if (lane == 0) {
-                                    part[(warp * kSampleBatch + nb) * 2] = wt;
-                                    part[(warp * kSampleBatch + nb) * 2 + 1] = wr;
+                                    part[(warp * kSampleBatch + nb) * 2] = (double)wt;
+                                    part[(warp * kSampleBatch + nb) * 2 + 1] = (double)wr;
                                 }
                             }
                             ++nb;

@@ -62,3 +62,22 @@ for loc, v in sorted(sm.items(), key=lambda kv: -kv[1])[:top]:
     f, l = loc if loc else ("?", 0)
     text = src[l - 1].strip()[:90] if f == "step_kernel.cuh" and l > 0 else ""
     print(f"   {f}:{l:4d} instr {100 * ex[loc] / tot:5.2f}% samples {100 * v / ts:5.2f}% | {text}")
+
+# ---- optional: samples grouped by code region of step_kernel.cuh (line ranges given as name:lo-hi,...)
+if len(sys.argv) > 4:
+    regions = []
+    for item in sys.argv[4].split(","):
+        name, rng = item.split(":"); lo, hi = rng.split("-"); regions.append((name, int(lo), int(hi)))
+    agg_s, agg_i = Counter(), Counter()
+    for loc, v in sm.items():
+        f, l = loc if loc else ("?", 0)
+        key = "other-file:" + f
+        if f == "step_kernel.cuh":
+            key = "unassigned"
+            for name, lo, hi in regions:
+                if lo <= l <= hi:
+                    key = name; break
+        agg_s[key] += v; agg_i[key] += ex[loc]
+    print("-- regions")
+    for k, v in agg_s.most_common():
+        print(f"   {k:28s} samples {100 * v / ts:5.1f}%  instr {100 * agg_i[k] / tot:5.1f}%")
