@@ -179,3 +179,62 @@ def test_half_grid_256_oscillators():
     assert np.max(np.abs(core.engine.state()[0] - orc.sol_state[-1])) < 1e-7
     np.testing.assert_allclose(core.theta_mean(0), orc.theta_mean, rtol=0, atol=1e-10)
     core.close()
+
+
+def test_plain_toeplitz_contraction_matches_symmetric_one(monkeypatch):
+    """CPL_GRID (DBSGYM_NO_SYM=1) and the default CPL_GRID_SYM kernel evaluate the same sum."""
+    g = load_golden("step_env0.npz")
+    d = make_params("env0", 10)
+    outs = {}
+    for nosym in ("0", "1"):
+        monkeypatch.setenv("DBSGYM_NO_SYM", nosym)
+        for prec in ("f64", "f32"):
+            core = _engine_from_params(d, 1, prec)
+            core.engine.set_env_params(None, y0=g["y_after_transient"][None, :])
+            core.step(np.array([g["actions"][0]]))
+            outs[(nosym, prec)] = core.engine.state()[0]
+            core.close()
+    for prec, tol in (("f64", 1e-9), ("f32", 1e-5)):
+        assert np.max(np.abs(outs[("0", prec)] - g["y_end"][0])) < tol
+        assert np.max(np.abs(outs[("1", prec)] - g["y_end"][0])) < tol
+    assert np.max(np.abs(outs[("0", "f64")] - outs[("1", "f64")])) < 1e-11
+
+
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_threshold_reward_and_wavelet_kernel(precision):
+    """R3 (env.py:669-688) and spatial_kernel='wavelet' (env.py:224-227) against the oracle."""
+    from oracle import kuramoto_oracle as ko
+    d = make_params("env1", 17, reward="bbpow_threth_action", spatial_kernel="wavelet", wavelet_amp=0.8,
+                    wavelet_steepness=0.6, transient_state_len=118.0)
+    orc = ko.OracleEnv(copy.deepcopy(d))
+    core = _engine_from_params(d, 1, precision)
+    assert core.engine.coupling == "grid"
+    tol = 1e-7 if precision == "f64" else 5e-3
+    assert np.max(np.abs(core.engine.state()[0] - orc.sol_state[-1])) < tol
+    for a in (0.9, -0.3, 0.0):
+        o_ref, r_ref, *_ = orc.step(np.array([a], dtype=np.float32))
+        obs, rew, done = core.step(np.array([a]))
+        assert np.max(np.abs(core.engine.state()[0] - orc.sol_state[-1])) < tol
+        assert core.engine.rewards()[0][0] == pytest.approx(r_ref, abs=1e-9 if precision == "f64" else 1e-5)
+    core.close()
+
+
+def test_small_non_grid_system_dense_padding():
+    """N = 100 oscillators on a 5x5x5 grid (not a multiple of 8: padded, DENSE coupling), naive DBS."""
+    from oracle import kuramoto_oracle as ko
+    import dbsgym_b200.utils as U
+    np.random.seed(8)
+    w0, nc, ng, w0t, wl, lm = U.generate_w0_with_locus(100, [5, 5, 5], 0.1, [2, 2, 2], 0.55, 17, 1, show=False)
+    d = make_params("env0", 8, transient_state_len=118.0, num_oscillators=100, grid_size=[5, 5, 5],
+                    elec_coords=[[2, 1, 2]], rec_coords=[[1, 1, 1]], naive_dbs=True, recording_kernel="gaussian")
+    d.update(w0=w0, w0_without_locus=w0t, locus_without_w0=wl, locus_mask=lm, neur_coords=nc, neur_grid=ng)
+    orc = ko.OracleEnv(copy.deepcopy(d))
+    core = _engine_from_params(d, 2, "f64")
+    assert core.engine.coupling == "dense"
+    assert np.max(np.abs(core.engine.state()[0] - orc.sol_state[-1])) < 1e-7
+    o_ref, r_ref, *_ = orc.step(np.array([0.5], dtype=np.float32))
+    obs, rew, done = core.step(np.array([0.5, 0.5]))
+    assert np.max(np.abs(core.engine.state() - orc.sol_state[-1][None, :])) < 1e-7
+    np.testing.assert_allclose(core.theta_records(1), orc.theta_records, rtol=0, atol=1e-10)
+    assert core.engine.rewards()[0][1] == pytest.approx(r_ref, rel=1e-8)
+    core.close()
