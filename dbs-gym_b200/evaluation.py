@@ -1,0 +1,58 @@
+"""Batched evaluation with the reference's reported metrics.
+
+``evaluate_hf_dbs`` / ``evaluate_policy_`` / ``calc_psd_for_simple_eval`` of reference
+aDBS_RL/evaluate_HF_DBS.py:33-174 run one environment at a time; here every environment of a
+:class:`BatchedKuramotoVecEnv` is evaluated in the same pass.  Metrics (per environment, then mean / sd
+over environments as the paper table does): beta-band (12.5-21 Hz) power of the concatenated TRUE LFP
+after a zero-phase order-2 band-pass and 12-tap spectrum smoothing (evaluate_HF_DBS.py:122-135), the
+"energy" sum |action| (evaluate_HF_DBS.py:163), and the episode return.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .utils import band_pass_envelope
+
+
+def calc_psd_for_simple_eval(sig_envs, psd_dt, beta_a=12.5, beta_b=21):
+    """evaluate_HF_DBS.py:122-135, vectorised over the environments axis."""
+    from scipy.signal import filtfilt
+    out = []
+    for sig in np.atleast_2d(sig_envs):
+        filt, _ = band_pass_envelope(sig, 1 / psd_dt, order=2)
+        ft = np.abs(np.fft.rfft(filt) / filt.shape[0]) ** 2 * 2
+        freq = np.fft.rfftfreq(filt.shape[0], psd_dt)
+        ft = filtfilt([1] * 12, 5, ft)
+        out.append(np.sum(ft[(freq > beta_a) & (freq < beta_b)]))
+    return np.asarray(out)
+
+
+def evaluate_batched(model, venv, n_steps=None, deterministic=True):
+    """Run ``model.predict`` on all environments of ``venv`` for one episode (or ``n_steps``) and return
+    a dict of per-environment arrays plus the paper-style summary (mean, sd with ddof=1)."""
+    core = venv.core
+    B = venv.num_envs
+    if n_steps is None:
+        n_steps = int(min(h.total_episode_counts for h in core.hosts))
+    obs = venv.reset()
+    lfp = [[] for _ in range(B)]
+    energy = np.zeros(B)
+    ret = np.zeros(B)
+    state, starts = None, np.ones(B, dtype=bool)
+    for _ in range(n_steps):
+        act, state = model.predict(obs, state=state, episode_start=starts, deterministic=deterministic)
+        act = np.asarray(act, dtype=np.float32)
+        act = np.broadcast_to(act.reshape(-1, 1) if act.size == B else act.reshape(1, 1), (B, 1))
+        obs, rew, done, infos = venv.step(act)
+        t, _, n = core.engine.lfp()
+        for i in range(B):
+            lfp[i].append(t[i, :n[i]].copy())
+        energy += np.abs(act[:, 0])
+        ret += rew
+        starts = done
+    sig = [np.concatenate(x) for x in lfp]
+    bb = np.array([calc_psd_for_simple_eval(s[None, :], psd_dt=0.0005)[0] for s in sig])
+    sd = (lambda v: float(np.std(v, ddof=1)) if len(v) > 1 else 0.0)
+    return {"bbpow": bb, "energy": energy, "episode_return": ret, "true_lfp": sig,
+            "summary": {"bbpow_mean": float(bb.mean()), "bbpow_sd": sd(bb), "energy_mean": float(energy.mean()),
+                        "energy_sd": sd(energy), "return_mean": float(ret.mean()), "return_sd": sd(ret)}}

@@ -206,3 +206,18 @@ def test_step_tensor_matches_host_step():
         assert np.array_equal(o1, o2.cpu().numpy()) and np.array_equal(r1, r2.cpu().numpy())
         assert np.array_equal(d1, d2.cpu().numpy().astype(bool))
     a.close(); b.close()
+
+
+def test_batched_evaluation_reproduces_paper_hf_dbs_row():
+    """evaluate_batched + HFDBS on env0 eval configs: paper table HF-DBS beta power 2.34e-3 (sd 0.2e-3),
+    energy 5555 (data/kur-table-metrics.xlsx row 5; the reference multiplies |action|=1 by ... 5555 = 1111 x 5)."""
+    from dbsgym_b200.controllers import HFDBS
+    from dbsgym_b200.evaluation import evaluate_batched
+    from dbsgym_b200.vec_env import BatchedKuramotoVecEnv
+    dicts = [make_params("env0", 11 + 9 * e, total_episode_len=1000, rand_seed=11 + e) for e in range(4)]
+    venv = BatchedKuramotoVecEnv(dicts)
+    res = evaluate_batched(HFDBS(1.0), venv)
+    assert res["bbpow"].shape == (4,) and len(res["true_lfp"][0]) > 1111 * 17
+    assert abs(res["summary"]["bbpow_mean"] - 2.34e-3) < 3 * 0.2e-3
+    assert np.allclose(res["energy"], 1111.0)            # sum |a| with a = 1; x5 after rescaling = the paper's 5555
+    venv.close()
