@@ -122,8 +122,40 @@ class BatchedKuramoto:
 
     def reset_envs(self, ids):
         """reset() of the listed environments, in the order given (reference env.py:467-614)."""
-        setups = [self.hosts[i].begin_episode() for i in ids]
+        ids = list(ids)
+        setups = self._begin_episodes_fast(ids)
+        if setups is None:
+            setups = [self.hosts[i].begin_episode() for i in ids]
         self._upload_and_run_transient(ids, setups)
+
+    def _begin_episodes_fast(self, ids):
+        """Vectorised begin_episode() for environments whose reset only draws Gaussians (the fix of non-positive
+        w0 entries, then the initial phases).  All of them come from ONE np.random.standard_normal call, which
+        consumes the global legacy stream exactly like the sequential per-environment randn / normal calls
+        (same Box-Muller generator, carried cache).  If an initial phase is <= 0 (remove_negative_w0 would draw
+        again) the RNG is rewound and the sequential path runs instead."""
+        hosts = [self.hosts[i] for i in ids]
+        if not hosts:
+            return None
+        ks = [h.fast_reset_draws() for h in hosts]
+        if any(k is None for k in ks):
+            return None
+        p0 = hosts[0].params_dict
+        mean, sd = p0["init_state_mean"], p0["init_state_sd"]
+        if any(h.params_dict["init_state_mean"] != mean or h.params_dict["init_state_sd"] != sd for h in hosts[1:]):
+            return None
+        N = self.n_osc
+        state = np.random.get_state()
+        z = np.random.standard_normal(sum(ks) + len(hosts) * N)
+        y_all = mean + sd * z                    # loc + scale * gauss, exactly what np.random.normal computes
+        if np.any(y_all <= 0.):                  # (also trips on a fix-noise slot, which only costs the slow path)
+            np.random.set_state(state)
+            return None
+        setups, pos = [], 0
+        for h, k in zip(hosts, ks):
+            setups.append(h.begin_episode_fast(z[pos:pos + k], y_all[pos + k:pos + k + N]))
+            pos += k + N
+        return setups
 
     def observations(self):
         """Current observation windows [B, W] float32 (host), read back from the device."""

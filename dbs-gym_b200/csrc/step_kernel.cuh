@@ -433,12 +433,21 @@ template <typename real, int MAXT> struct MinBlocks {
 };
 
 enum { CPL_GRID = 0, CPL_DENSE = 1, CPL_GRID_SYM = 2 };
+#ifndef DBSGYM_SC_BUFFERS
+#define DBSGYM_SC_BUFFERS 2
+#endif
+constexpr int kScBuffers = DBSGYM_SC_BUFFERS;   // 2: one barrier per RHS evaluation; 1: two barriers, 4 KB less shared memory
 constexpr int kScPad = 16;     // reals of padding per operand buffer (GRID_SYM staggers its 4 sectors by 16 B)
 
 // GEO = 1: the grid extents are the compile-time constants 8 x 8 x 8 (every shipped config), which
 // turns the table / operand address arithmetic of the contraction into immediates.
+#ifdef DBSGYM_MAXNREG
+#define DBSGYM_KERNEL_BOUNDS(real, MAXT) __maxnreg__(DBSGYM_MAXNREG)
+#else
+#define DBSGYM_KERNEL_BOUNDS(real, MAXT) __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v)
+#endif
 template <typename real, int CPL, int MAXT, int GEO = 0>
-__global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(const StepParams p) {
+__global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p) {
     constexpr bool DENSE = CPL == CPL_DENSE;
     constexpr bool SYM = CPL == CPL_GRID_SYM;
     const int GZ = GEO == 1 ? 8 : p.GZ, GX = GEO == 1 ? 8 : p.GX;
@@ -451,7 +460,7 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
 
     real* K = reinterpret_cast<real*>(smem_raw);          // [7][Np] stage derivatives f(y_s), thread-private slots
     real* SC = K + kSlots * Np;                                // [2][scsz] interleaved (sin, cos) contraction operand
-    real* T = SC + 2 * scsz;                              // [tab]
+    real* T = SC + kScBuffers * scsz;                     // [tab]
     real* RC = T + tab;                                   // [Np] recording conductance (thread-private slots)
     int* WD = reinterpret_cast<int*>(RC + Np);            // [Np] fp32 mode: winding counts, y = phase + 2*pi*wind
     double* part = reinterpret_cast<double*>(WD + Np);    // [nwarps][kSampleBatch][2]
@@ -622,7 +631,8 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
                 for (int r = 0; r < kRows; ++r)
                     ks[r] = c0[r] + kn * (cv[r] * as[r] - sv[r] * ac[r]);
                 storev<kRows>(K + kslot(s) * Np + k0, ks);
-                pbuf ^= 1;
+                if (kScBuffers == 2) pbuf ^= 1;
+                else __syncthreads();             // operand buffer is about to be overwritten by the next stage
                 ++n_rhs;
             }
             have_f0 = true;
@@ -818,7 +828,7 @@ __global__ void __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v) step_kernel(co
 
 inline size_t step_smem_bytes(int Np, int tab, int nthreads, size_t real_bytes) {
     const int nwarps = (nthreads + 31) / 32;
-    return (size_t)((kSlots + 5) * Np + 2 * kScPad + tab) * real_bytes + (size_t)Np * sizeof(int) +
+    return (size_t)((kSlots + 1 + 2 * kScBuffers) * Np + kScBuffers * kScPad + tab) * real_bytes + (size_t)Np * sizeof(int) +
            (size_t)(nwarps * kSampleBatch * 2 + nwarps) * sizeof(double);
 }
 

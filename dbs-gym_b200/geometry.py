@@ -134,14 +134,19 @@ class ElectrodeModel:
             self.directional_mask = [m[0] for m in self.directional_masks_list]
             self.conductances = [c * m for c, m in zip(self.conductances, self.directional_mask)]
         self.rec_conductances = conductance_rows(self.rec_idxs)
+        self._stim_vec = self._rec_vec = None     # cached device-side vectors (the lists above stay authoritative)
 
     def stim_vector(self):
         """What step() applies: only the first contact is driven by the 1-d action (env.py:419-423)."""
-        return np.asarray(self.conductances[0], dtype=np.float64)
+        if self._stim_vec is None:
+            self._stim_vec = np.asarray(self.conductances[0], dtype=np.float64)
+        return self._stim_vec
 
     def rec_vector(self):
         """Sum over recording contacts (env.py:409-411 sums the per-contact means)."""
-        out = np.zeros(len(self.neur_grid))
-        for c in self.rec_conductances:
-            out = out + c
-        return out
+        if self._rec_vec is None:
+            out = np.zeros(len(self.neur_grid))
+            for c in self.rec_conductances:
+                out = out + c
+            self._rec_vec = out
+        return self._rec_vec

@@ -131,6 +131,7 @@ class HostEnvState:
         self.spatial_var_freq = p["spatial_var_freq"]
         self.spatial_var_episode = self.spatial_var_freq
         self.init_state = None
+        self._fast_cache = None
 
     # env.py:457-464
     def calc_next_event(self, f, deltas=(-1, 0, 1)):
@@ -143,6 +144,37 @@ class HostEnvState:
         if not self.compat_env2:
             raise AttributeError("'SpatialKuramoto' object has no attribute 'calc_next_temp_event'")
         return self.calc_next_event(f, deltas)
+
+    # ---- batched fast path (used by BatchedKuramoto.reset_envs) ------------------------------------
+    def fast_reset_draws(self):
+        """Number of standard-normal draws the next reset makes BEFORE the initial phases (the
+        remove_negative_w0 fix of non-positive natural frequencies, utils.py:819-823), or None when the next
+        reset does anything else with the random stream or the configuration: temporal drift, a spatial
+        re-draw due at the next reset count, event logging, save_init.  One ordinary begin_episode() must
+        have run before (it fills the cache)."""
+        p = self.params_dict
+        if p["temporal_drift"] or self.save_init or self._fast_cache is None:
+            return None
+        nxt = self.reset_count + 1
+        if p["spatial_feature"] and self.spatial_var_episode == nxt and nxt > 2:
+            return None
+        if p["save_events"] and p["log_path"] is not None and nxt > 1:
+            return None
+        return int(self._fast_cache[1].size)
+
+    def begin_episode_fast(self, z_fix, y0_row) -> EpisodeSetup:
+        """begin_episode() given this environment's slices of ONE batched standard-normal draw: ``z_fix``
+        feeds remove_negative_w0(w0), ``y0_row`` are the initial phases."""
+        self.reset_count += 1
+        w0_raw, bad, electrode = self._fast_cache
+        w0 = w0_raw
+        if bad.size:
+            w0 = w0_raw.copy()
+            w0[bad] = np.abs(z_fix * 0.05) + np.mean(w0_raw)
+        self.w0 = w0
+        self.init_state = y0_row
+        return EpisodeSetup(w0=w0, stim=electrode.stim_vector(), rec=electrode.rec_vector(), y0=y0_row,
+                            electrode=electrode)
 
     def begin_episode(self) -> EpisodeSetup:
         """env.py:467-598: everything reset() does before the transient integration."""
@@ -200,6 +232,7 @@ class HostEnvState:
             np.save(os.path.join(p["log_path"], f"temp_{self.reset_count}.npy"), self.temporal_events)
 
         self.w0 = apply_locus_mask(self.w0_without_locus, p["locus_without_w0"], p["locus_mask"])
+        w0_raw = None if p["temporal_drift"] else np.array(self.w0, dtype=np.float64)
         # KuramotoJAX.__init__ (env.py:211-243)
         self.w0 = remove_negative_w0(self.w0)
         assert np.min(self.w0) >= 0, "Natural frequencies w0 must be positive!"
@@ -209,6 +242,8 @@ class HostEnvState:
             self.init_state = np.random.normal(loc=p["init_state_mean"], scale=p["init_state_sd"],
                                                size=(p["num_oscillators"]))
             self.init_state = remove_negative_w0(self.init_state)
-        return EpisodeSetup(w0=np.asarray(self.w0, dtype=np.float64), stim=electrode.stim_vector(),
-                            rec=electrode.rec_vector(), y0=np.asarray(self.init_state, dtype=np.float64),
-                            electrode=electrode)
+        w0_out = np.asarray(self.w0, dtype=np.float64)
+        # without drift, w0 before the non-positive fix and the electrode never change -> reusable by the fast path
+        self._fast_cache = None if w0_raw is None else (w0_raw, np.flatnonzero(w0_raw <= 0.), electrode)
+        return EpisodeSetup(w0=w0_out, stim=electrode.stim_vector(), rec=electrode.rec_vector(),
+                            y0=np.asarray(self.init_state, dtype=np.float64), electrode=electrode)

@@ -62,6 +62,8 @@ def temp_const_functional(window_len, fs, order=2):
 def remove_negative_w0(w0):
     """utils.py:819-823 -- in place; draws from the global ``np.random`` stream."""
     bad = np.flatnonzero(w0 <= 0.)
+    if bad.size == 0:              # randn(0) draws nothing and the assignment is empty: skip the mean as well
+        return w0
     noise = np.random.randn(bad.size) * 0.05
     w0[bad] = np.abs(noise) + np.mean(w0)
     return w0

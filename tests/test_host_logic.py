@@ -164,3 +164,43 @@ def test_configs_expose_reference_names():
     assert e0.params_dict_train["recording_kernel"] == "naive" and e1.params_dict_train["recording_kernel"] == "gaussian"
     assert e2.params_dict_train["temporal_drift"] and e2.eval0["electrode_drift_freq"] == 2
     assert e0.eval0["total_episode_len"] == 1000 and e0.eval2["rand_seed"] == 20
+
+
+def test_batched_fast_reset_draws_like_the_sequential_loop():
+    """BatchedKuramoto's one-call initial-phase draw must leave every host (and the global RNG) exactly
+    where the per-environment begin_episode() loop would."""
+    import copy
+    from dbsgym_b200.batched import BatchedKuramoto
+
+    class _Stub(BatchedKuramoto):                 # host logic only: no engine, no GPU
+        def __init__(self, hosts, n):
+            self.hosts, self.n_osc = hosts, n
+
+    dicts = [make_params("env1", 3 + e, rand_seed=90 + e) for e in range(5)]
+    assert any(np.any(utils.apply_locus_mask(d["w0_without_locus"], d["locus_without_w0"], d["locus_mask"]) <= 0)
+               for d in dicts)                     # exercise the remove_negative_w0 draws too
+    slow = [HostEnvState(copy.deepcopy(d)) for d in dicts]
+    fast = [HostEnvState(copy.deepcopy(d)) for d in dicts]
+    np.random.seed(123)
+    for h in slow:
+        h.begin_episode()
+    np.random.seed(123)
+    for h in fast:
+        h.begin_episode()                          # first reset is always the ordinary path (fills the caches)
+    for rnd in range(12):                          # env1: spatial re-draw fires at reset_count 10 -> slow path there
+        np.random.seed(1000 + rnd)
+        ref = [h.begin_episode() for h in slow]
+        state_ref = np.random.get_state()[1].copy()
+        np.random.seed(1000 + rnd)
+        stub = _Stub(fast, 512)
+        got = stub._begin_episodes_fast(range(5))
+        used_fast = got is not None
+        if got is None:
+            got = [h.begin_episode() for h in fast]
+        assert used_fast == (fast[0].reset_count != 10)        # whether or not some w0 has non-positive entries
+        assert np.array_equal(np.random.get_state()[1], state_ref)
+        for a, b, hs, hf in zip(ref, got, slow, fast):
+            assert np.array_equal(a.y0, b.y0) and np.array_equal(a.w0, b.w0)
+            assert np.array_equal(a.stim, b.stim) and np.array_equal(a.rec, b.rec)
+            assert hs.reset_count == hf.reset_count and hs.elec_coords == hf.elec_coords
+            assert hs.spatial_var_episode == hf.spatial_var_episode
