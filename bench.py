@@ -146,7 +146,8 @@ def run_reference_arm(args):
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
-    per_step = 2                                              # env-steps per process per bench step
+    # env-steps per process per bench step, sized so that the whole run stays within a few minutes
+    per_step = 2 if args.steps <= 300 else 1
     plan = [per_step] * (args.warmup + args.steps)
     with mp.get_context("spawn").Pool(cores) as pool:
         t0 = time.perf_counter()
@@ -359,7 +360,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
