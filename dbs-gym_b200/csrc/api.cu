@@ -254,7 +254,16 @@ cudaError_t launch_step_t(DbsGymHandle* h, const StepParams& p, cudaStream_t s) 
 template <typename real, int CPL>
 cudaError_t launch_step_m(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
     const int t = h->nthreads;
-    if (CPL == CPL_GRID_SYM && t == 64 && p.GZ == 8 && p.GX == 8) return launch_step_t<real, CPL, 64, 1>(h, p, s);
+    if constexpr (CPL == CPL_GRID_SYM && sizeof(real) == 4) {
+        static const bool no_geo1 = getenv("DBSGYM_NO_GEO1") != nullptr;        // A/B switch for tuning runs
+        if (t == 64 && p.GZ == 8 && p.GX == 8 && !no_geo1) return launch_step_t<real, CPL, 64, 1>(h, p, s);
+    }
+    if constexpr (CPL == CPL_GRID_SYM && sizeof(real) == 4) if (p.GX == 8) {   // sweep grids 8 x 8 x gz
+        if (t <= 64) return launch_step_t<real, CPL, 64, 2>(h, p, s);
+        if (t <= 128) return launch_step_t<real, CPL, 128, 2>(h, p, s);
+        if (t <= 256) return launch_step_t<real, CPL, 256, 2>(h, p, s);
+        if (t <= 512) return launch_step_t<real, CPL, 512, 2>(h, p, s);
+    }
     if (t <= 64) return launch_step_t<real, CPL, 64>(h, p, s);
     if (t <= 128) return launch_step_t<real, CPL, 128>(h, p, s);
     if (t <= 256) return launch_step_t<real, CPL, 256>(h, p, s);

@@ -348,18 +348,20 @@ __device__ __forceinline__ void couple_grid_sym<float>(const float* __restrict__
 // |zq-zj| / |xq-xj| offset is computed once, the mirrored rows are reached through immediates, and the
 // scheduler can hoist the loads of block b+1 above the FFMA2 of block b (ncu on the rolled loop: 76 FFMA2 but
 // ~108 other instructions per block, mostly address arithmetic and operand copies).
-template <int HZ, int HX>
+template <int HZ, int HX>     // HZ == 0: number of z half-planes given at run time (hz_rt); the x loop is always unrolled
 __device__ __forceinline__ void couple_grid_sym_fixed(const float* __restrict__ bp, const float* __restrict__ T,
-                                                      int zq, int xq, float pz, float px,
+                                                      int zq, int xq, float pz, float px, int hz_rt,
                                                       float (&as)[kRows], float (&ac)[kRows]) {
-    constexpr int GZ = 2 * HZ, GX = 2 * HX, NC = GZ * GX;
+    const int hz = HZ > 0 ? HZ : hz_rt;
+    const int GZ = 2 * hz;
+    constexpr int GX = 2 * HX;
+    const int NC = GZ * GX;
     float2 acc[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) acc[r] = make_float2(0.f, 0.f);
     const float2 px2 = make_float2(px, px), pz2 = make_float2(pz, pz);
     const float* tz1 = T + ((GZ - 1 - zq) * GX + (GX - 1 - xq)) * 4;      // row (dz1, dx1) of block (0,0); moves by immediates
-#pragma unroll
-    for (int zj = 0; zj < HZ; ++zj) {
+    auto zplane = [&](int zj) {
         const int dz0 = zq > zj ? zq - zj : zj - zq;
         const float* tz0 = T + dz0 * GX * 4;
 #pragma unroll
@@ -387,6 +389,13 @@ __device__ __forceinline__ void couple_grid_sym_fixed(const float* __restrict__ 
                 }
             }
         }
+    };
+    if (HZ > 0) {
+#pragma unroll
+        for (int zj = 0; zj < HZ; ++zj) zplane(zj);
+    } else {
+#pragma unroll 1
+        for (int zj = 0; zj < hz; ++zj) zplane(zj);
     }
 #pragma unroll
     for (int r = 0; r < kRows; ++r) { as[r] = acc[r].x; ac[r] = acc[r].y; }
@@ -440,7 +449,8 @@ constexpr int kScBuffers = DBSGYM_SC_BUFFERS;   // 2: one barrier per RHS evalua
 constexpr int kScPad = 16;     // reals of padding per operand buffer (GRID_SYM staggers its 4 sectors by 16 B)
 
 // GEO = 1: the grid extents are the compile-time constants 8 x 8 x 8 (every shipped config), which
-// turns the table / operand address arithmetic of the contraction into immediates.
+// turns the table / operand address arithmetic of the contraction into immediates.  GEO = 2: gx = 8 at compile
+// time, gz at run time (the 8 x 8 x gz grids of the oscillator-count sweep): x loop unrolled, z loop rolled.
 #ifdef DBSGYM_MAXNREG
 #define DBSGYM_KERNEL_BOUNDS(real, MAXT) __maxnreg__(DBSGYM_MAXNREG)
 #else
@@ -450,7 +460,7 @@ template <typename real, int CPL, int MAXT, int GEO = 0>
 __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p) {
     constexpr bool DENSE = CPL == CPL_DENSE;
     constexpr bool SYM = CPL == CPL_GRID_SYM;
-    const int GZ = GEO == 1 ? 8 : p.GZ, GX = GEO == 1 ? 8 : p.GX;
+    const int GZ = GEO == 1 ? 8 : p.GZ, GX = GEO >= 1 ? 8 : p.GX;      // GEO == 2: gx = 8 fixed, gz at run time
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
@@ -619,7 +629,11 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                 else if (SYM) {
                     if (GEO == 1 && sizeof(real) == 4)
                         couple_grid_sym_fixed<4, 4>(reinterpret_cast<const float*>(SC + pbuf * scsz + sc_sector),
-                                                    reinterpret_cast<const float*>(T), zq, xq, (float)sgn_z, (float)sgn_x,
+                                                    reinterpret_cast<const float*>(T), zq, xq, (float)sgn_z, (float)sgn_x, 4,
+                                                    reinterpret_cast<float(&)[kRows]>(as), reinterpret_cast<float(&)[kRows]>(ac));
+                    else if (GEO == 2 && sizeof(real) == 4)
+                        couple_grid_sym_fixed<0, 4>(reinterpret_cast<const float*>(SC + pbuf * scsz + sc_sector),
+                                                    reinterpret_cast<const float*>(T), zq, xq, (float)sgn_z, (float)sgn_x, GZ >> 1,
                                                     reinterpret_cast<float(&)[kRows]>(as), reinterpret_cast<float(&)[kRows]>(ac));
                     else
                         couple_grid_sym<real>(SC + pbuf * scsz + sc_sector, T, GZ, GX, zq, xq, sgn_z, sgn_x, as, ac);
