@@ -221,3 +221,12 @@ def test_batched_evaluation_reproduces_paper_hf_dbs_row():
     assert abs(res["summary"]["bbpow_mean"] - 2.34e-3) < 3 * 0.2e-3
     assert np.allclose(res["energy"], 1111.0)            # sum |a| with a = 1; x5 after rescaling = the paper's 5555
     venv.close()
+
+
+def test_torch_policy_rollout_example_runs():
+    import subprocess, sys, os
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "rollout_torch_policy.py"), "--envs", "64",
+                          "--steps", "4", "--cfg", "env0"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "env-steps/s" in out.stdout
