@@ -36,6 +36,10 @@ def main():
     rew_buf = torch.empty((args.steps, B), dtype=torch.float32, device=dev)
     done = torch.empty(B, dtype=torch.uint8, device=dev)
     obs_buf[0].copy_(torch.from_numpy(core.observations()).to(dev))
+    with torch.no_grad():                                      # warm-up: cuBLAS handles, lazy module loading
+        for _ in range(10):
+            a = policy(obs_buf[0]).squeeze(-1)
+            core.step_tensor(a, obs=obs_buf[0], reward=rew_buf[0], done=done)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     with torch.no_grad():
