@@ -297,6 +297,13 @@ cudaError_t launch_obs(DbsGymHandle* h, float* obs, float* reward_f, uint8_t* do
     o.temp_scale = h->rspec.temp_scale;
     o.lin_g = h->lin_g; o.tw_seed = h->tw_seed; o.tw_inner = h->tw_inner; o.iters = h->obs_iters;
     o.append = append; o.env_ids = ids_dev; o.n_launch = n;
+    static const bool no_fast = getenv("DBSGYM_NO_FAST_OBS") != nullptr;     // A/B switch
+    if (append && o.kind != 1 && h->obs_iters == kFastIters && h->nbins <= kFastMaxBins && h->smax <= kObsThreads && !no_fast) {
+        const size_t smem = obs_fast_smem_bytes(h->nbins, h->rb);
+        if (h->f64) obs_kernel_fast<double><<<n, kObsThreads, smem, s>>>(o);
+        else obs_kernel_fast<float><<<n, kObsThreads, smem, s>>>(o);
+        return cudaGetLastError();
+    }
     const size_t smem = obs_smem_bytes(h->W, h->nbins, h->obs_iters, h->rb);
     if (h->f64) obs_kernel<double><<<n, kObsThreads, smem, s>>>(o);
     else obs_kernel<float><<<n, kObsThreads, smem, s>>>(o);
