@@ -67,6 +67,8 @@ struct DbsGymHandle {
     bool mirror_on = false;              // obs kernel writes the mirror (set while a mirror step / reset runs)
     uint8_t* st_done = nullptr;
     // timing
+    int cluster = 1;                     // CTAs per environment (thread-block cluster; > 1 when N > 4096)
+    void* cl_operand = nullptr; double* cl_scratch = nullptr;
     int ctas_per_sm = 0;                 // 0 = whatever fits
     bool grid_sym = false;               // GRID coupling: use the reflection-symmetry reduced contraction
     bool timing = false;
@@ -231,6 +233,7 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
     p.ring = h->ring; p.W = h->W; p.head = h->head;
     p.counters = h->counters; p.status = h->status;
     p.ts = nullptr; p.n_ts = 0; p.actions = nullptr; p.env_ids = nullptr; p.n_launch = 0; p.mode = MODE_STEP;
+    p.cluster = h->cluster; p.cl_operand = h->cl_operand; p.cl_scratch = h->cl_scratch;
 }
 
 template <typename real, int CPL, int MAXT, int GEO = 0>
@@ -271,6 +274,35 @@ cudaError_t launch_step_m(DbsGymHandle* h, const StepParams& p, cudaStream_t s) 
     return launch_step_t<real, CPL, 1024>(h, p, s);
 }
 
+// cluster mode: one environment = a cluster of h->cluster CTAs (cudaLaunchKernelEx + cluster dimension attribute)
+template <int MAXT>
+cudaError_t launch_step_cluster_t(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
+    auto kern = step_kernel<float, CPL_GRID_SYM, MAXT, 2, 1>;
+    const size_t smem = step_smem_bytes_cluster(h->nthreads, sizeof(float));
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess && h->cluster > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(p.n_launch * h->cluster));
+    cfg.blockDim = dim3((unsigned)h->nthreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)h->cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+cudaError_t launch_step_cluster(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
+    const int t = h->nthreads;
+    if (t <= 64) return launch_step_cluster_t<64>(h, p, s);
+    if (t <= 128) return launch_step_cluster_t<128>(h, p, s);
+    if (t <= 256) return launch_step_cluster_t<256>(h, p, s);
+    return launch_step_cluster_t<512>(h, p, s);
+}
+
 template <typename real>
 cudaError_t launch_step_c(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
     if (h->cfg.coupling == DBSGYM_COUPLING_DENSE) return launch_step_m<real, CPL_DENSE>(h, p, s);
@@ -278,6 +310,7 @@ cudaError_t launch_step_c(DbsGymHandle* h, const StepParams& p, cudaStream_t s) 
 }
 
 cudaError_t launch_step(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
+    if (h->cluster > 1) return launch_step_cluster(h, p, s);
     return h->f64 ? launch_step_c<double>(h, p, s) : launch_step_c<float>(h, p, s);
 }
 
@@ -363,7 +396,8 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
     // DENSE: pad to whole warps (padded oscillators are inert); GRID: whole z-planes of 8-lines
     const int gran = cfg->coupling == DBSGYM_COUPLING_DENSE ? 32 * kRows : kRows;
     const int Np = (cfg->n_osc + gran - 1) / gran * gran;
-    if (Np / kRows > 1024) return fail(nullptr, DBSGYM_EINVAL, "n_osc %d too large for the resident-state kernel (max 8192)", cfg->n_osc);
+    if (cfg->coupling == DBSGYM_COUPLING_DENSE && Np / kRows > 1024)
+        return fail(nullptr, DBSGYM_EINVAL, "n_osc %d too large for DENSE coupling (max 8192)", cfg->n_osc);
     if (cfg->coupling == DBSGYM_COUPLING_GRID) {
         if (cfg->grid[1] != kRows)
             return fail(nullptr, DBSGYM_EINVAL, "GRID coupling needs grid[1] (gy) == %d, got %d", kRows, cfg->grid[1]);
@@ -390,6 +424,22 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
     h->rb = h->f64 ? 8 : 4;
     h->nthreads = Np / kRows;
     if (cfg->coupling == DBSGYM_COUPLING_GRID) {
+        // more than 512 grid lines (N > 4096): one environment spans a thread-block cluster of 2..16 CTAs
+        int want = 1;
+        if (const char* e = getenv("DBSGYM_FORCE_CLUSTER")) want = atoi(e);      // test hook: cluster mode at small N
+        while (h->nthreads / want > 512) want *= 2;
+        if (want > 1) {
+            const int lines = Np / kRows;
+            if (want > 16 || lines % (want * 32) != 0 || cfg->grid[0] != 8 || h->f64 ||
+                (cfg->n_osc / (cfg->grid[0] * kRows)) % 2 != 0) {
+                fail(nullptr, DBSGYM_EINVAL, "n_osc %d needs cluster mode (%d CTAs per environment), which supports fp32, "
+                     "8 x 8 x gz grids with even gz and at most 65536 oscillators", cfg->n_osc, want);
+                delete h;
+                return DBSGYM_EINVAL;
+            }
+            h->cluster = want;
+            h->nthreads = lines / want;
+        }
         // only the z-planes actually populated take part
         h->cfg.grid[2] = cfg->n_osc / (cfg->grid[0] * kRows);
         h->tab = h->cfg.grid[2] * cfg->grid[0] * kRows;
@@ -418,6 +468,10 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
     A((void**)&h->st_actions, (size_t)h->B * 4); A((void**)&h->st_obs, (size_t)h->B * h->W * 4);
     A((void**)&h->st_reward, (size_t)h->B * 4); A((void**)&h->st_done, (size_t)h->B);
     A((void**)&h->st_samples, (size_t)h->B * h->smax * 4);
+    if (h->cluster > 1) {
+        A(&h->cl_operand, (size_t)h->B * 2 * (2 * (size_t)Np + kScPad) * sizeof(float));
+        A((void**)&h->cl_scratch, (size_t)h->B * 2 * h->cluster * kClSlots * sizeof(double));
+    }
     ok = ok && cudaMallocHost(&h->pin_ints, (size_t)h->B * 8) == cudaSuccess;
     for (int i = 0; i < 3 && ok; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
     if (ok) {
@@ -441,7 +495,8 @@ void dbsgym_destroy(DbsGymHandle* h) {
     void* bufs[] = {h->table, h->alpha, h->w0, h->stim, h->rec, h->phase, h->ring, h->wind, h->head, h->n_samples,
                     h->step_idx, h->episode_len, h->lfp_true, h->lfp_rec, h->u, h->reward, h->done, h->sched_nI,
                     h->sched_nII, h->sched_offI, h->sched_offII, h->ts_dev, h->ids_dev, h->lin_g, h->tw_seed,
-                    h->tw_inner, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples};
+                    h->tw_inner, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples,
+                    h->cl_operand, h->cl_scratch};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->pin_ints) cudaFreeHost(h->pin_ints);

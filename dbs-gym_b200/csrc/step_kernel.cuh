@@ -61,7 +61,20 @@ struct StepParams {
     // bookkeeping
     unsigned long long* counters;  // accepted, rejected, rhs evals
     int32_t* status;
+    // cluster mode (one environment = a thread-block cluster of `cluster` CTAs, N > 4096)
+    int cluster;                   // CTAs per environment (1 = plain)
+    void* cl_operand;              // [B][2][2*Np + kScPad] contraction operand in global memory (L2)
+    double* cl_scratch;            // [B][2][cluster][kClSlots] cross-CTA reduction scratch
 };
+
+constexpr int kClSlots = 2 * 16;   // doubles per CTA and parity in cl_scratch (= 2 * kSampleBatch)
+
+__device__ __forceinline__ void cluster_barrier() {
+    // release / acquire at cluster scope: global writes made before the barrier by any CTA of the cluster are
+    // visible to every thread of the cluster after it (reads below use ld.global.cg: L1 is not coherent)
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
 
 // ---- Dormand-Prince 5(4) coefficients (same values as oracle/diffrax_restated.py) ----------
 __constant__ double c_A[7][8] = {
@@ -348,7 +361,12 @@ __device__ __forceinline__ void couple_grid_sym<float>(const float* __restrict__
 // |zq-zj| / |xq-xj| offset is computed once, the mirrored rows are reached through immediates, and the
 // scheduler can hoist the loads of block b+1 above the FFMA2 of block b (ncu on the rolled loop: 76 FFMA2 but
 // ~108 other instructions per block, mostly address arithmetic and operand copies).
-template <int HZ, int HX>     // HZ == 0: number of z half-planes given at run time (hz_rt); the x loop is always unrolled
+__device__ __forceinline__ float4 ld_table(const float* p, bool gl) {
+    return gl ? __ldg(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p);
+}
+
+template <int HZ, int HX, bool GL = false>   // HZ == 0: z half-planes given at run time (hz_rt); the x loop is always unrolled.
+                                             // GL: table and operand live in global memory (cluster mode)
 __device__ __forceinline__ void couple_grid_sym_fixed(const float* __restrict__ bp, const float* __restrict__ T,
                                                       int zq, int xq, float pz, float px, int hz_rt,
                                                       float (&as)[kRows], float (&ac)[kRows]) {
@@ -372,13 +390,19 @@ __device__ __forceinline__ void couple_grid_sym_fixed(const float* __restrict__ 
             const float* t01 = tz0 + (GX - 1 - xq) * 4 - xj * 4;
             const float* t10 = tz1 - zj * GX * 4 + (dx0 - (GX - 1 - xq)) * 4;
             const float* t11 = tz1 - (zj * GX + xj) * 4;
-            r.a00l = *reinterpret_cast<const float4*>(t00); r.a00h = *reinterpret_cast<const float4*>(t00 + NC * 4);
-            r.a01l = *reinterpret_cast<const float4*>(t01); r.a01h = *reinterpret_cast<const float4*>(t01 + NC * 4);
-            r.a10l = *reinterpret_cast<const float4*>(t10); r.a10h = *reinterpret_cast<const float4*>(t10 + NC * 4);
-            r.a11l = *reinterpret_cast<const float4*>(t11); r.a11h = *reinterpret_cast<const float4*>(t11 + NC * 4);
+            r.a00l = ld_table(t00, GL); r.a00h = ld_table(t00 + NC * 4, GL);
+            r.a01l = ld_table(t01, GL); r.a01h = ld_table(t01 + NC * 4, GL);
+            r.a10l = ld_table(t10, GL); r.a10h = ld_table(t10 + NC * 4, GL);
+            r.a11l = ld_table(t11, GL); r.a11h = ld_table(t11 + NC * 4, GL);
             float u[kRows], b[2 * kRows];
             sym_combine(r, px2, pz2, u);
-            loadv<2 * kRows>(bp + (zj * HX + xj) * (2 * kRows), b);
+            if (GL) {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    const float4 v = __ldcg(reinterpret_cast<const float4*>(bp + (zj * HX + xj) * (2 * kRows)) + q4);
+                    b[4 * q4] = v.x; b[4 * q4 + 1] = v.y; b[4 * q4 + 2] = v.z; b[4 * q4 + 3] = v.w;
+                }
+            } else loadv<2 * kRows>(bp + (zj * HX + xj) * (2 * kRows), b);
 #pragma unroll
             for (int yj = 0; yj < kRows; ++yj) {
                 const float2 scj = make_float2(b[2 * yj], b[2 * yj + 1]);
@@ -456,37 +480,52 @@ constexpr int kScPad = 16;     // reals of padding per operand buffer (GRID_SYM 
 #else
 #define DBSGYM_KERNEL_BOUNDS(real, MAXT) __launch_bounds__(MAXT, MinBlocks<real, MAXT>::v)
 #endif
-template <typename real, int CPL, int MAXT, int GEO = 0>
+// CL = 1: one environment is integrated by a thread-block CLUSTER of p.cluster CTAs (N > 4096: the stage
+// derivatives no longer fit one SM).  Each CTA keeps its share of the RK state in its own shared memory; the
+// contraction operand is exchanged through a double-buffered global (L2-resident) buffer, the coupling table is
+// read through the read-only path, and the barrier per RHS evaluation as well as the error-norm / LFP reductions
+// become cluster-scope (barrier.cluster release/acquire + a few doubles of global scratch).
+template <typename real, int CPL, int MAXT, int GEO = 0, int CL = 0>
 __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p) {
     constexpr bool DENSE = CPL == CPL_DENSE;
     constexpr bool SYM = CPL == CPL_GRID_SYM;
+    static_assert(CL == 0 || (CPL == CPL_GRID_SYM && GEO == 2 && sizeof(real) == 4), "cluster mode: fp32 GRID_SYM, gx = 8");
     const int GZ = GEO == 1 ? 8 : p.GZ, GX = GEO >= 1 ? 8 : p.GX;      // GEO == 2: gx = 8 fixed, gz at run time
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, nt = blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
     const int Np = p.Np;
-    const int tab = DENSE ? 0 : GZ * GX * kRows;
+    const int NC_ = CL ? p.cluster : 1;                   // CTAs per environment
+    const int crank = CL ? (int)(blockIdx.x % NC_) : 0;   // rank of this CTA in its cluster (1-D grid, cluster dims (C,1,1))
+    const int Nl = CL ? nt * kRows : Np;                  // oscillators whose state lives in THIS CTA's shared memory
+    const int tab = (DENSE || CL) ? 0 : GZ * GX * kRows;
     const int scsz = 2 * Np + kScPad;
 
-    real* K = reinterpret_cast<real*>(smem_raw);          // [7][Np] stage derivatives f(y_s), thread-private slots
-    real* SC = K + kSlots * Np;                                // [2][scsz] interleaved (sin, cos) contraction operand
-    real* T = SC + kScBuffers * scsz;                     // [tab]
-    real* RC = T + tab;                                   // [Np] recording conductance (thread-private slots)
-    int* WD = reinterpret_cast<int*>(RC + Np);            // [Np] fp32 mode: winding counts, y = phase + 2*pi*wind
-    double* part = reinterpret_cast<double*>(WD + Np);    // [nwarps][kSampleBatch][2]
-    double* red = part + nwarps * kSampleBatch * 2;       // [nwarps]
-
-    const int slot = blockIdx.x;
-    if (slot >= p.n_launch) return;
+    const int slot = CL ? (int)(blockIdx.x / NC_) : (int)blockIdx.x;
+    if (slot >= p.n_launch) return;                       // (whole clusters leave together)
     const int env = p.env_ids ? p.env_ids[slot] : slot;
     const size_t base = (size_t)env * Np;
-    const int k0 = tid * kRows;                           // private slot in K (and in the plain operand)
+
+    real* K = reinterpret_cast<real*>(smem_raw);          // [kSlots][Nl] stage derivatives f(y_s), thread-private slots
+    real* SCs = K + kSlots * Nl;                          // [kScBuffers][scsz] (sin, cos) contraction operand (not in cluster mode)
+    real* Ts = SCs + (CL ? 0 : kScBuffers * scsz);        // [tab]
+    real* RC = Ts + tab;                                  // [Nl] recording conductance (thread-private slots)
+    int* WD = reinterpret_cast<int*>(RC + Nl);            // [Nl] fp32 mode: winding counts, y = phase + 2*pi*wind
+    double* part = reinterpret_cast<double*>(WD + Nl);    // [nwarps][kSampleBatch][2]
+    double* red = part + nwarps * kSampleBatch * 2;       // [nwarps]
+    real* SC = CL ? reinterpret_cast<real*>(p.cl_operand) + (size_t)env * 2 * scsz : SCs;
+    const real* T = CL ? reinterpret_cast<const real*>(p.table) : Ts;
+    double* cls = CL ? p.cl_scratch + (size_t)env * 2 * NC_ * kClSlots : nullptr;
+    int cl_par = 0;
+
+    const int tid_g = crank * nt + tid;                   // thread index within the environment
+    const int k0 = tid * kRows;                           // private slot in K / RC / WD (and in the plain operand)
     // grid line owned by this thread.  GRID: line = tid.  GRID_SYM: a quad of lanes owns the four mirror
     // images (z,x), (z,X-x), (Z-z,x), (Z-z,X-x) of fundamental line q = tid / 4.
     int zi = 0, xi = 0, zq = 0, xq = 0;
     real sgn_x = real(1), sgn_z = real(1);
     if (SYM) {
-        const int HX = GX >> 1, q = tid >> 2;
+        const int HX = GX >> 1, q = tid_g >> 2;
         zq = q / HX; xq = q % HX;
         zi = (tid & 2) ? GZ - 1 - zq : zq;
         xi = (tid & 1) ? GX - 1 - xq : xq;
@@ -500,7 +539,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     // operand slot written by this thread: plain = own line; GRID_SYM = sector (tid & 3), line q
     const int sec_stride = (GZ >> 1) * (GX >> 1) * 2 * kRows + (int)(16 / sizeof(real));
     const int sc_sector = SYM ? (tid & 3) * sec_stride : 0;
-    const int sc_slot = SYM ? sc_sector + (tid >> 2) * 2 * kRows : 2 * k0;
+    const int sc_slot = SYM ? sc_sector + (tid_g >> 2) * 2 * kRows : 2 * k0;
 
     // Register diet: only y0 and (per segment) c0 = w0 + amp * stim stay in registers across the
     // contraction; the recording conductance and the winding counts live in thread-private shared slots.
@@ -517,11 +556,11 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
 #pragma unroll
         for (int r = 0; r < kRows; ++r) WD[k0 + r] = sizeof(real) == 4 ? p.wind[base + i0 + r] : 0;
     }
-    if (!DENSE) {
+    if (!DENSE && !CL) {
         using V = typename Vec<real>::T;
         constexpr int vn = Vec<real>::n;
         const V* tg = reinterpret_cast<const V*>(p.table);
-        for (int i = tid; i < tab / vn; i += nt) reinterpret_cast<V*>(T)[i] = tg[i];
+        for (int i = tid; i < tab / vn; i += nt) reinterpret_cast<V*>(Ts)[i] = tg[i];
     }
     __syncthreads();
 
@@ -544,7 +583,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
         // env.py:389-393 rescale_action, env.py:419
         const double a = (double)p.actions[env];
         const double u = p.act_lo + ((p.act_hi - p.act_lo) * (a - (-1.0))) / (1.0 - (-1.0));
-        if (tid == 0) { p.u_out[env] = u; p.n_samples[env] = nI + nII - 1; }
+        if (tid == 0 && crank == 0) { p.u_out[env] = u; p.n_samples[env] = nI + nII - 1; }
         nseg = 2;
         seg_ts[0] = p.sched_offI + (size_t)k * p.maxI;   seg_nts[0] = nI;  seg_nrec[0] = nI;
         seg_ts[1] = p.sched_offII + (size_t)k * p.maxII; seg_nts[1] = nII; seg_nrec[1] = nII - 1;
@@ -596,7 +635,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                     const real a = real(c_A[s][j]);
                     if (a != real(0)) {
                         real kj[kRows];
-                        loadv<kRows>(K + j * Np + k0, kj);
+                        loadv<kRows>(K + j * Nl + k0, kj);
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) inc[r] = fma_r(a, kj[r], inc[r]);
                     }
@@ -623,7 +662,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                     }
                     storev<2 * kRows>(SC + pbuf * scsz + sc_slot, scw);
                 }
-                __syncthreads();
+                if (CL) cluster_barrier(); else __syncthreads();
                 real as[kRows], ac[kRows];
                 if (DENSE) couple_dense<real>(SC + pbuf * scsz, reinterpret_cast<const real*>(p.alpha), Np, i0, as, ac);
                 else if (SYM) {
@@ -632,7 +671,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                                                     reinterpret_cast<const float*>(T), zq, xq, (float)sgn_z, (float)sgn_x, 4,
                                                     reinterpret_cast<float(&)[kRows]>(as), reinterpret_cast<float(&)[kRows]>(ac));
                     else if (GEO == 2 && sizeof(real) == 4)
-                        couple_grid_sym_fixed<0, 4>(reinterpret_cast<const float*>(SC + pbuf * scsz + sc_sector),
+                        couple_grid_sym_fixed<0, 4, CL != 0>(reinterpret_cast<const float*>(SC + pbuf * scsz + sc_sector),
                                                     reinterpret_cast<const float*>(T), zq, xq, (float)sgn_z, (float)sgn_x, GZ >> 1,
                                                     reinterpret_cast<float(&)[kRows]>(as), reinterpret_cast<float(&)[kRows]>(ac));
                     else
@@ -644,8 +683,8 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
 #pragma unroll
                 for (int r = 0; r < kRows; ++r)
                     ks[r] = c0[r] + kn * (cv[r] * as[r] - sv[r] * ac[r]);
-                storev<kRows>(K + kslot(s) * Np + k0, ks);
-                if (kScBuffers == 2) pbuf ^= 1;
+                storev<kRows>(K + kslot(s) * Nl + k0, ks);
+                if (kScBuffers == 2 || CL) pbuf ^= 1;  // (the global operand of cluster mode is always double buffered)
                 else __syncthreads();             // operand buffer is about to be overwritten by the next stage
                 ++n_rhs;
             }
@@ -660,7 +699,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                     const real a = real(c_A[6][j]);
                     if (a != real(0)) {
                         real kj[kRows];
-                        loadv<kRows>(K + j * Np + k0, kj);
+                        loadv<kRows>(K + j * Nl + k0, kj);
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) d1[r] = fma_r(a, kj[r], d1[r]);
                     }
@@ -681,7 +720,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                     const real b = real(c_Berr[j]);
                     if (b != real(0)) {
                         real kj[kRows];
-                        loadv<kRows>(K + kslot(j) * Np + k0, kj);
+                        loadv<kRows>(K + kslot(j) * Nl + k0, kj);
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) e[r] = fma_r(b, kj[r], e[r]);
                     }
@@ -703,6 +742,13 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
             __syncthreads();
             double tot = 0.0;
             for (int w = 0; w < nwarps; ++w) tot += red[w];
+            if (CL) {                              // sum the per-CTA partials of the cluster (same order in every CTA)
+                if (tid == 0) cls[(cl_par * NC_ + crank) * kClSlots] = tot;
+                cluster_barrier();
+                tot = 0.0;
+                for (int r = 0; r < NC_; ++r) tot += __ldcg(cls + (cl_par * NC_ + r) * kClSlots);
+                cl_par ^= 1;
+            }
             const double err = sqrt(tot / (double)p.N);
             if (!(err == err)) { status |= STATUS_NAN; break; }
             const bool keep = err < 1.0;
@@ -720,7 +766,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                     {
                         real kk0[kRows], k6[kRows], dm[kRows];
                         loadv<kRows>(K + k0, kk0);
-                        loadv<kRows>(K + kslot(6) * Np + k0, k6);
+                        loadv<kRows>(K + kslot(6) * Nl + k0, k6);
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) dm[r] = real(0);
 #pragma unroll 1
@@ -728,7 +774,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                             const real c = real(c_Cmid[j]);
                             if (c != real(0)) {
                                 real kj[kRows];
-                                loadv<kRows>(K + kslot(j) * Np + k0, kj);
+                                loadv<kRows>(K + kslot(j) * Nl + k0, kj);
 #pragma unroll
                                 for (int r = 0; r < kRows; ++r) dm[r] = fma_r(c, kj[r], dm[r]);
                             }
@@ -770,10 +816,28 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                             ++nb;
                         }
                         __syncthreads();
-                        for (int q = tid; q < nb; q += nt) {
+                        if (CL) {                  // CTA partials -> global scratch -> summed by the rank-0 CTA below
+                            for (int q = tid; q < nb; q += nt) {
+                                double a_t = 0.0, a_r = 0.0;
+                                for (int w = 0; w < nwarps; ++w) {
+                                    a_t += part[(w * kSampleBatch + q) * 2];
+                                    a_r += part[(w * kSampleBatch + q) * 2 + 1];
+                                }
+                                cls[(cl_par * NC_ + crank) * kClSlots + 2 * q] = a_t;
+                                cls[(cl_par * NC_ + crank) * kClSlots + 2 * q + 1] = a_r;
+                            }
+                            cluster_barrier();
+                        }
+                        for (int q = tid; q < nb && crank == 0; q += nt) {
                             const int idx = save_idx + q;
                             if (idx >= rec_from && idx < n_rec) {
                                 double a_t = 0.0, a_r = 0.0;
+                                if (CL) {
+                                    for (int r = 0; r < NC_; ++r) {
+                                        a_t += __ldcg(cls + (cl_par * NC_ + r) * kClSlots + 2 * q);
+                                        a_r += __ldcg(cls + (cl_par * NC_ + r) * kClSlots + 2 * q + 1);
+                                    }
+                                } else
                                 for (int w = 0; w < nwarps; ++w) {
                                     a_t += part[(w * kSampleBatch + q) * 2];
                                     a_r += part[(w * kSampleBatch + q) * 2 + 1];
@@ -788,6 +852,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                                 }
                             }
                         }
+                        if (CL) cl_par ^= 1;
                         __syncthreads();
                         save_idx += nb;
                     }
@@ -795,7 +860,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                 // ---- accept: y0 <- y1, FSAL k1 <- k7 ------------------------------------
                 {
                     real k6[kRows];
-                    loadv<kRows>(K + kslot(6) * Np + k0, k6);
+                    loadv<kRows>(K + kslot(6) * Nl + k0, k6);
                     storev<kRows>(K + k0, k6);
                 }
 #pragma unroll
@@ -831,13 +896,19 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
 #pragma unroll
         for (int r = 0; r < kRows; ++r) p.wind[base + i0 + r] = WD[k0 + r];
     }
-    if (tid == 0) {
+    if (tid == 0 && crank == 0) {
         if (p.mode == MODE_TRANSIENT) p.head[env] = 0;
         atomicAdd(p.counters + 0, (unsigned long long)n_acc);
         atomicAdd(p.counters + 1, (unsigned long long)n_rej);
         atomicAdd(p.counters + 2, (unsigned long long)n_rhs);
         if (status) atomicOr(p.status, status);
     }
+}
+
+inline size_t step_smem_bytes_cluster(int nthreads, size_t real_bytes) {
+    const int nwarps = (nthreads + 31) / 32, Nl = nthreads * kRows;
+    return (size_t)((kSlots + 1) * Nl) * real_bytes + (size_t)Nl * sizeof(int) +
+           (size_t)(nwarps * kSampleBatch * 2 + nwarps) * sizeof(double);
 }
 
 inline size_t step_smem_bytes(int Np, int tab, int nthreads, size_t real_bytes) {
