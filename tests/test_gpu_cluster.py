@@ -1,0 +1,104 @@
+"""Cluster mode of the step kernel (one environment = a thread-block cluster, N > 4096)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(N, gz, B, monkeypatch=None, force_cluster=None, precision="f32"):
+    from dbsgym_b200.engine import KuramotoEngine
+    from dbsgym_b200.geometry import coupling_table, distances_from, neuron_grid
+    from dbsgym_b200.schedule import StepSchedule, transient_grid
+    if monkeypatch is not None:
+        if force_cluster:
+            monkeypatch.setenv("DBSGYM_FORCE_CLUSTER", str(force_cluster))
+        else:
+            monkeypatch.delenv("DBSGYM_FORCE_CLUSTER", raising=False)
+    coords, grid = neuron_grid(8, 8, gz, N, 0.1)
+    table = coupling_table(coords, grid, [8, 8, gz], "cos")
+    eng = KuramotoEngine(B, N, [8, 8, gz], 2340, 0.52, precision=precision, coupling_table=table)
+    tt = transient_grid(200.0, 0.05)
+    sched = StepSchedule(80, tt[-1], 0.15, 0.75, 0.05)
+    eng.set_schedule(sched)
+    eng.set_reward("bbpow_action", 0.05)
+    eng.set_recording(True)
+    rng = np.random.default_rng(N + B)
+    centre = int(np.argmin(np.abs(grid - np.array([4, 3, gz // 2])).sum(axis=1)))
+    stim = np.tile(np.maximum(0.0, 1.0 - distances_from(grid * 0.1, [centre])[0]), (B, 1))
+    rec = np.tile(np.maximum(0.0, 1.0 - distances_from(grid * 0.1, [centre // 2])[0]), (B, 1))
+    w0 = np.abs(rng.normal(0.6, 0.4, (B, N))) + 0.02
+    y0 = rng.normal(np.pi, 0.6, (B, N)) + 25.0
+    eng.set_env_params(None, w0=w0, stim=stim, rec=rec, y0=y0)
+    eng.set_window(rng.uniform(-0.2, 0.2, (B, 2340)))
+    eng.set_episode(None, step_idx=0, episode_len=1000)
+    return eng, dict(table=table, grid=grid, w0=w0, stim=stim, rec=rec, y0=y0, sched=sched, tt=tt)
+
+
+@pytest.mark.parametrize("N,gz,C", [(1024, 16, 2), (1024, 16, 4), (4096, 64, 8), (2048, 32, 2)])
+def test_cluster_mode_equals_single_cta_mode(monkeypatch, N, gz, C):
+    """Same inputs through the single-CTA kernel and through the C-CTA cluster kernel (forced at a size both can run):
+    steps, a transient with rejections, LFP, rewards and counters must agree (only reduction orders differ)."""
+    acts = np.random.default_rng(1).uniform(-1, 1, (3, 3)).astype(np.float32)
+    res = {}
+    for mode in (None, C):
+        eng, d = _engine(N, gz, 3, monkeypatch, mode)
+        eng.counters(reset=True)
+        out = []
+        for a in acts:
+            obs, rew, done = eng.step_host(a)
+            out.append((eng.state().copy(), obs.copy(), rew.copy(), eng.lfp()[0].copy(), eng.lfp()[1].copy()))
+        eng.transient(np.arange(0.0, 130.0, 0.05))
+        out.append((eng.state().copy(), eng.obs_host().copy()))
+        res[mode] = (out, eng.counters())
+        eng.close()
+    (a, ca), (b, cb) = res[None], res[C]
+    assert ca == cb and ca["status"] == 0 and ca["rejected"] > 0
+    for x, y in zip(a, b):
+        for u, v in zip(x, y):
+            np.testing.assert_allclose(u, v, rtol=0, atol=2e-5 if u.ndim == 2 and u.shape[1] >= 1024 else 5e-6)
+
+
+def test_n8192_cluster_step_matches_oracle():
+    """N = 8192 (8 x 8 x 128 grid, 2 CTAs per environment): one step() against the fp64 oracle integrator with a
+    chunked evaluation of the same coupling operator."""
+    from oracle.diffrax_restated import Dopri5, ODETerm, PIDController, SaveAt, diffeqsolve
+    N, gz = 8192, 128
+    eng, d = _engine(N, gz, 2)
+    a = np.array([0.7, -0.4], dtype=np.float32)
+    obs, rew, done = eng.step_host(a)
+    y_gpu = eng.state()
+    lfp_t, lfp_r, ns = eng.lfp()
+    c = eng.counters()
+    assert c["status"] == 0 and c["rhs_evals"] == 2 * 32
+    table, grid = d["table"].reshape(gz, 8, 8), d["grid"]
+
+    def coupled(v):                                    # alpha @ v, alpha_ij = table[|dz|,|dx|,|dy|], in row chunks
+        out = np.empty((N, v.shape[1]))
+        for lo in range(0, N, 512):
+            dd = np.abs(grid[lo:lo + 512, None, :] - grid[None, :, :])
+            out[lo:lo + 512] = table[dd[..., 2], dd[..., 0], dd[..., 1]] @ v
+        return out
+
+    sched = d["sched"]
+    for e in range(1):                                 # one environment on the CPU (32 chunked RHS evaluations)
+        u = -5 + (10 * (float(a[e]) + 1)) / 2
+        y = d["y0"][e].copy()
+        segs = [(sched.offs_I[0, :sched.n_I[0]], u), (sched.offs_II[0, :sched.n_II[0]], 0.0)]
+        rows = []
+        for ts, amp in segs:
+            pulse = amp * d["stim"][e]
+
+            def rhs(t, yy, args, pulse=pulse):
+                th = np.fmod(yy, 2 * np.pi)
+                sc = coupled(np.stack([np.sin(th), np.cos(th)], axis=1))
+                return d["w0"][e] + (0.52 / N) * (np.cos(th) * sc[:, 0] - np.sin(th) * sc[:, 1]) + pulse
+            sol = diffeqsolve(ODETerm(rhs), Dopri5(), t0=ts[0], t1=ts[-1], dt0=0.05, y0=y, saveat=SaveAt(ts=ts),
+                              stepsize_controller=PIDController(rtol=1e-5, atol=1e-5))
+            y = sol.ys[-1]
+            rows.append(sol.ys)
+        allrows = np.concatenate(rows)[:-1]
+        assert np.max(np.abs(y_gpu[e] - y)) < 1e-5
+        n = ns[e]
+        np.testing.assert_allclose(lfp_t[e, :n], np.mean(np.cos(allrows), axis=1), rtol=0, atol=2e-6)
+        np.testing.assert_allclose(lfp_r[e, :n], np.mean(np.cos(allrows) * d["rec"][e], axis=1), rtol=0, atol=2e-6)
+    eng.close()
