@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Oscillator-count sweep (BASELINE configs[4]) on the resident-state GRID kernel: 8 x 8 x gz grids
 (lines of 8 along y, gz z-planes), N = 64*gz, holding B*N = 2 097 152.  cos coupling, K/N scaling as in
-env.py:264.  Engine-level (device-resident) timing, one GPU.  N >= 8192 does not fit the one-CTA-per-env
-design (state > 227 KB of shared memory) and is future work."""
+env.py:264.  Engine-level (device-resident) timing, one GPU.  N <= 4096: one CTA per environment; N >= 8192:
+one thread-block cluster of N / 4096 CTAs per environment (cluster mode of the step kernel)."""
 import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,7 +13,7 @@ from dbsgym_b200.geometry import coupling_table, neuron_grid, ElectrodeModel
 from dbsgym_b200.schedule import StepSchedule, transient_grid
 
 out = []
-for gz in (4, 8, 16, 32, 64):
+for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024):
     N = 64 * gz
     B = 2097152 // N
     coords, grid = neuron_grid(8, 8, gz, N, 0.1)
@@ -40,20 +40,21 @@ for gz in (4, 8, 16, 32, 64):
     rew = torch.empty(B, dtype=torch.float32, device=dev); done = torch.empty(B, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     eng.set_timing(True); eng.counters(reset=True)
-    for i in range(5):
+    for i in range(5 if N <= 8192 else 2):
         eng.step_device(act[i].data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), st)
     torch.cuda.synchronize(); eng.counters(reset=True)
     ms = []
-    for i in range(5, 35):
+    n_timed = 30 if N <= 8192 else 6
+    for i in range(5, 5 + n_timed):
         eng.step_device(act[i].data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), st)
         torch.cuda.synchronize(); ms.append(eng.last_step_ms())
     c = eng.counters()
     k_step, k_obs = np.mean([m[0] for m in ms]), np.mean([m[1] for m in ms])
-    rhs = c["rhs_evals"] / (30 * B)
+    rhs = c["rhs_evals"] / (n_timed * B)
     out.append({"N": N, "grid": [8, 8, gz], "envs": B, "step_kernel_ms": float(k_step), "obs_kernel_ms": float(k_obs),
-                "env_steps_per_s": B / ((k_step + k_obs) * 1e-3), "oscillator_updates_per_s": B * N * (c["accepted"] + c["rejected"]) / (30 * B) / ((k_step + k_obs) * 1e-3),
+                "env_steps_per_s": B / ((k_step + k_obs) * 1e-3), "oscillator_updates_per_s": B * N * (c["accepted"] + c["rejected"]) / (n_timed * B) / ((k_step + k_obs) * 1e-3),
                 "rhs_per_env_step": rhs, "executed_tflops": rhs * 1.22 * N * N * B / (k_step * 1e-3) / 1e12,
                 "dense_equivalent_tflops": rhs * 4 * N * N * B / (k_step * 1e-3) / 1e12,
-                "transient_s": t_tr, "status": c["status"]})
+                "transient_s": t_tr, "status": c["status"], "ctas_per_env": max(1, N // 4096)})
     print(json.dumps(out[-1]), flush=True)
     eng.close()
