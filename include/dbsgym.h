@@ -55,7 +55,9 @@ typedef struct DbsGymConfig {
     uint32_t struct_bytes;      /* sizeof(DbsGymConfig), checked                                  */
     int32_t  device;            /* CUDA ordinal                                                   */
     int32_t  n_envs;            /* B: environments owned by this handle                           */
-    int32_t  n_osc;             /* N: oscillators per environment (params_dict['num_oscillators']) */
+    int32_t  n_osc;             /* N: oscillators per environment (params_dict['num_oscillators']).
+                                   GRID coupling: N <= 4096 one CTA per environment; 4096 < N <= 65536 (fp32, 8 x 8 x gz
+                                   grids) one thread-block cluster of N/4096 CTAs per environment.  DENSE: N <= 8192. */
     int32_t  grid[3];           /* gx, gy, gz of utils.py:478-497 (row i = z*gx*gy + x*gy + y)    */
     int32_t  window;            /* W: observe_wind_idxs, env.py:296-297 (2340)                    */
     int32_t  precision;         /* DBSGYM_F32 | DBSGYM_F64                                        */
