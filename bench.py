@@ -292,13 +292,19 @@ def run_gpu_arm(args):
         rhs_per_env_step = counters["rhs_evals"] / (B * K)
         substeps_per_env_step = (counters["accepted"] + counters["rejected"]) / (B * K)
         # Algorithmic work of the step kernel.  Dense formulation: R * 4 N^2 + ~700 N.
-        # The GRID_SYM kernel evaluates the same contraction in the (pz,px) parity-sector basis: N^2 flop
-        # for the four (N/4)^2 sector blocks x {sin,cos}, + 0.1875 N^2 to combine the table rows into the
-        # sector coefficients, + 0.03 N^2 for the quad butterflies = 1.22 N^2 per RHS.  The roofline
-        # fraction is quoted against the kernel's OWN op count (SURVEY.md 8d rule for reduced formulations).
+        # The GRID_SYM kernel evaluates the same contraction in the parity-sector basis; its OWN executed
+        # flop count (what the roofline fraction is quoted against, SURVEY.md 8d rule for reduced
+        # formulations) per thread and (zj,xj) block -- there are N^2/256 of those per RHS -- is
+        #   z/x sectors only : 12 FFMA2 (table rows -> sector coefficients) + 64 FFMA2        = 304 flop
+        #   + y parity       : 12 FFMA2 + 20 FADD (even/odd coefficients) + 32 FFMA2          = 196 flop
+        # (instruction counts checked in the SASS: 704 FFMA2 = 16 x 44 in the unrolled contraction), plus the
+        # quad butterflies (128 flop) and, with y parity, the even/odd folds (32 flop) per thread = N/8 threads.
+        from dbsgym_b200 import _capi
+        ypar = bool(_capi.load().dbsgym_build_flags() & 1)
         dense_flop_per_env_step = rhs_per_env_step * 4 * N_OSC * N_OSC + 700 * N_OSC
         sym = eng.coupling == "grid" and os.environ.get("DBSGYM_NO_SYM", "") != "1"
-        flop_per_env_step = (rhs_per_env_step * 1.22 * N_OSC * N_OSC + 700 * N_OSC) if sym else dense_flop_per_env_step
+        sym_flop_per_rhs = ((196 if ypar else 304) / 256.0) * N_OSC * N_OSC + ((160 if ypar else 128) / 8.0) * N_OSC
+        flop_per_env_step = (rhs_per_env_step * sym_flop_per_rhs + 700 * N_OSC) if sym else dense_flop_per_env_step
         k_step = float(np.mean([m[0] for m in kern_ms])) * 1e-3
         k_obs = float(np.mean([m[1] for m in kern_ms])) * 1e-3
         peaks, peak_src = measured_peaks()
@@ -306,7 +312,8 @@ def run_gpu_arm(args):
         peak_ffma2 = measure_fp32_peak(local_rank, packed=True)
         fp32_peak = max(peak_ffma, peak_ffma2)
         achieved_tf = flop_per_env_step * B / k_step / 1e12
-        obs_bytes = B * (2 * 2340 * 4 + 19 * 8 + 32)                 # ring read + obs write + samples
+        fused_obs = os.environ.get("DBSGYM_NO_FUSED_OBS") is None     # ring append + reward live in the step kernel's tail
+        obs_bytes = B * (2 * 2340 * 4) if fused_obs else B * (2 * 2340 * 4 + 19 * 8 + 32)   # ring read + obs write (+ samples)
         cpu_n = 12
         cpu_as_written = cpu_port_steps_per_sec(cpu_n, "as_written", np.float32)
         cpu_matvec = cpu_port_steps_per_sec(200, "matvec", np.float64)
@@ -330,13 +337,13 @@ def run_gpu_arm(args):
                            "the new samples + reward + done + ring position cross PCIe (dbsgym_step_host_mirror)",
                     "full_obs_d2h": {"value": B * world * K / capi_s, "d2h_bytes_per_step": B * (2340 * 4 + 4 + 1),
                                      "api": "dbsgym_step_host (whole [B,2340] f32 observation copied to pinned host memory every step)"}},
-            "gpu_launches": 2 * K,
+            "gpu_launches": 2 * K,      # device-timed region: step_kernel + observation kernel per step (the e2e region: 1 per step when fused)
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp32_peak if fp32_peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 4096 envs, from the ncu
                          # --set full capture profiles/r01_final_step_obs_raw.csv (42.06 MB read + 0.10 MB write)
                          "traffic": 42.15e6 * B / 4096,
-                         "kernel": "step_kernel<float,GRID_SYM>" if sym else "step_kernel<float,GRID>",
+                         "kernel": ("step_kernel<float,GRID_SYM,y-parity>" if ypar else "step_kernel<float,GRID_SYM>") if sym else "step_kernel<float,GRID>",
                          "kernel_ms": k_step * 1e3, "flop_per_env_step": flop_per_env_step,
                          "dense_formulation_flop_per_env_step": dense_flop_per_env_step,
                          "dense_equivalent_tflops": dense_flop_per_env_step * B / k_step / 1e12,
@@ -344,7 +351,8 @@ def run_gpu_arm(args):
                          "peak_ffma": peak_ffma, "peak_ffma2": peak_ffma2},
             "roofline_obs": {"bound": "hbm", "achieved": obs_bytes / k_obs / 1e9, "peak": peaks.get("hbm_gbs"),
                              "unit": "GB/s", "frac": obs_bytes / k_obs / 1e9 / peaks.get("hbm_gbs", 1.0),
-                             "kernel": "obs_kernel", "kernel_ms": k_obs * 1e3, "peak_source": peak_src},
+                             "kernel": "obs_copy_kernel (ring -> chronological [B,W] f32; append/reward fused into the step kernel)" if fused_obs else "obs_kernel",
+                             "kernel_ms": k_obs * 1e3, "peak_source": peak_src},
             "cpu_baseline": {"value": cpu_as_written, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"{cpu_n} env1 steps, one env, oracle port with the reference's N x N sine RHS in float32",
                              "matvec_f64_value": cpu_matvec, "published_reference": "17-20 it/s (notebook tqdm, unknown CPU)"},

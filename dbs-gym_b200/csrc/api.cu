@@ -54,6 +54,8 @@ struct DbsGymHandle {
     bool have_reward = false;
     double *lin_g = nullptr, *tw_seed = nullptr;
     void* tw_inner = nullptr;
+    double *spec = nullptr, *tw_full = nullptr;   // fused observation tail: running rfft bins [B][kTailBins][2], twiddles [W][nbins][2]
+    bool fuse_tail = false;
     int obs_iters = 0;
     int nbins = 0;
     // bookkeeping
@@ -234,6 +236,13 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
     p.counters = h->counters; p.status = h->status;
     p.ts = nullptr; p.n_ts = 0; p.actions = nullptr; p.env_ids = nullptr; p.n_launch = 0; p.mode = MODE_STEP;
     p.cluster = h->cluster; p.cl_operand = h->cl_operand; p.cl_scratch = h->cl_scratch;
+    p.tail_on = 0; p.tail_kind = h->rspec.kind; p.tail_nbins = h->nbins;
+    p.spec = h->spec; p.tw_full = h->tw_full;
+    p.samples_f = nullptr; p.mirror = nullptr; p.reward_f = nullptr; p.reward = h->reward;
+    p.done_out = nullptr; p.done_dev = h->done;
+    p.step_idx_rw = h->step_idx; p.episode_len = h->episode_len;
+    p.power_scale = h->rspec.power_scale; p.action_cost = h->rspec.action_cost;
+    p.threshold = h->rspec.threshold; p.threshold_penalty = h->rspec.threshold_penalty;
 }
 
 template <typename real, int CPL, int MAXT, int GEO = 0>
@@ -343,6 +352,20 @@ cudaError_t launch_obs(DbsGymHandle* h, float* obs, float* reward_f, uint8_t* do
     return cudaGetLastError();
 }
 
+// running rfft bins of the given environments from their whole rings (fused-tail state)
+cudaError_t launch_spec_init(DbsGymHandle* h, const int32_t* ids_dev, int n, cudaStream_t s) {
+    if (!h->fuse_tail) return cudaSuccess;
+    if (h->f64) spec_init_kernel<double><<<n, kObsThreads, 0, s>>>(h->ring, h->tw_full, h->spec, h->W, h->nbins, kTailBins, ids_dev, n);
+    else spec_init_kernel<float><<<n, kObsThreads, 0, s>>>(h->ring, h->tw_full, h->spec, h->W, h->nbins, kTailBins, ids_dev, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_obs_copy(DbsGymHandle* h, float* obs, cudaStream_t s) {
+    if (h->f64) obs_copy_kernel<double><<<h->B, kCopyThreads, 0, s>>>(h->ring, h->head, obs, h->W, h->B);
+    else obs_copy_kernel<float><<<h->B, kCopyThreads, 0, s>>>(h->ring, h->head, obs, h->W, h->B);
+    return cudaGetLastError();
+}
+
 int check_ready(DbsGymHandle* h, bool need_step) {
     if (!h) return DBSGYM_EINVAL;
     if (!h->have_coupling) return fail(h, DBSGYM_ESTATE, "coupling not set (dbsgym_set_coupling_*)");
@@ -362,10 +385,18 @@ int step_impl(DbsGymHandle* h, const float* actions_dev, float* obs_dev, float* 
     StepParams p;
     fill_params(h, p);
     p.mode = MODE_STEP; p.actions = actions_dev; p.n_launch = h->B;
+    if (h->fuse_tail) {
+        // ring append, host mirror, beta-power reward and episode bookkeeping happen in the step kernel's tail;
+        // a separate (pure copy) kernel runs only when the caller wants the chronological window on the device
+        p.tail_on = 1;
+        p.samples_f = samples_dev; p.mirror = h->mirror_on ? h->mirror_dev : nullptr;
+        p.reward_f = reward_dev; p.done_out = done_dev;
+    }
     if (h->timing) CU(h, cudaEventRecord(h->ev[0], s));
     CU(h, launch_step(h, p, s));
     if (h->timing) CU(h, cudaEventRecord(h->ev[1], s));
-    CU(h, launch_obs(h, obs_dev, reward_dev, done_dev, 1, nullptr, h->B, s, samples_dev));
+    if (!h->fuse_tail) CU(h, launch_obs(h, obs_dev, reward_dev, done_dev, 1, nullptr, h->B, s, samples_dev));
+    else if (obs_dev) CU(h, launch_obs_copy(h, obs_dev, s));
     if (h->timing) CU(h, cudaEventRecord(h->ev[2], s));
     return DBSGYM_OK;
 }
@@ -376,6 +407,14 @@ int step_impl(DbsGymHandle* h, const float* actions_dev, float* obs_dev, float* 
 extern "C" {
 
 int dbsgym_abi_version(void) { return DBSGYM_ABI_VERSION; }
+
+int dbsgym_build_flags(void) {
+    int f = kYParity ? 1 : 0;
+#ifdef DBSGYM_PRECISE_SINCOS
+    f |= 2;
+#endif
+    return f;
+}
 
 const char* dbsgym_last_error(const DbsGymHandle* h) { return h ? h->err : g_create_err; }
 
@@ -465,6 +504,7 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
     A((void**)&h->u, (size_t)h->B * 8); A((void**)&h->reward, (size_t)h->B * 8);
     A((void**)&h->done, (size_t)h->B);
     A((void**)&h->counters, 3 * sizeof(unsigned long long)); A((void**)&h->status, 4);
+    A((void**)&h->spec, (size_t)h->B * kTailBins * 2 * sizeof(double));
     A((void**)&h->st_actions, (size_t)h->B * 4); A((void**)&h->st_obs, (size_t)h->B * h->W * 4);
     A((void**)&h->st_reward, (size_t)h->B * 4); A((void**)&h->st_done, (size_t)h->B);
     A((void**)&h->st_samples, (size_t)h->B * h->smax * 4);
@@ -495,7 +535,7 @@ void dbsgym_destroy(DbsGymHandle* h) {
     void* bufs[] = {h->table, h->alpha, h->w0, h->stim, h->rec, h->phase, h->ring, h->wind, h->head, h->n_samples,
                     h->step_idx, h->episode_len, h->lfp_true, h->lfp_rec, h->u, h->reward, h->done, h->sched_nI,
                     h->sched_nII, h->sched_offI, h->sched_offII, h->ts_dev, h->ids_dev, h->lin_g, h->tw_seed,
-                    h->tw_inner, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples,
+                    h->tw_inner, h->spec, h->tw_full, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples,
                     h->cl_operand, h->cl_scratch};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -668,9 +708,27 @@ int dbsgym_set_reward(DbsGymHandle* h, const DbsGymRewardSpec* spec, const doubl
         CU(h, cudaMemcpy(h->tw_inner, inner.data(), inner.size(), cudaMemcpyHostToDevice));
         h->obs_iters = iters;
         h->nbins = nb;
+        // fused observation tail: twiddles of every ring position, [W][nb][2] float64 (exact integer phase reduction)
+        std::vector<double> full((size_t)W * nb * 2);
+        for (int m = 0; m < W; ++m)
+            for (int b = 0; b < nb; ++b) {
+                const long long q = ((long long)(spec->bin_lo + b) * m) % W;
+                full[((size_t)m * nb + b) * 2] = std::cos(two_pi * (double)q / W);
+                full[((size_t)m * nb + b) * 2 + 1] = std::sin(two_pi * (double)q / W);
+            }
+        if (h->tw_full) cudaFree(h->tw_full);
+        h->tw_full = nullptr;
+        CU(h, cudaMalloc(&h->tw_full, full.size() * 8));
+        CU(h, cudaMemcpy(h->tw_full, full.data(), full.size() * 8, cudaMemcpyHostToDevice));
     }
     h->rspec = *spec;
     h->have_reward = true;
+    const bool no_fuse = getenv("DBSGYM_NO_FUSED_OBS") != nullptr;     // A/B switch (read per call): separate observation kernel
+    h->fuse_tail = spec->kind != DBSGYM_REWARD_TEMP_CONST && h->nbins <= kTailBins && h->smax <= W && !no_fuse;
+    if (h->fuse_tail) {                              // the bins of whatever the rings hold now
+        CU(h, launch_spec_init(h, nullptr, h->B, h->stream));
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
     return DBSGYM_OK;
 }
 
@@ -721,6 +779,7 @@ int dbsgym_transient(DbsGymHandle* h, const int32_t* env_ids, int32_t n, const d
     fill_params(h, p);
     p.mode = MODE_TRANSIENT; p.env_ids = ids; p.n_launch = n; p.ts = h->ts_dev; p.n_ts = n_ts;
     CU(h, launch_step(h, p, s));
+    CU(h, launch_spec_init(h, ids, n, s));
     CU(h, launch_obs(h, obs_dev, nullptr, nullptr, 0, ids, n, s));
     if (ids) CU(h, cudaStreamSynchronize(s));      // ids_dev is reused by the next call
     return DBSGYM_OK;
@@ -913,6 +972,8 @@ int dbsgym_set_window(DbsGymHandle* h, const int32_t* env_ids, int32_t n, const 
     std::vector<int32_t> z((size_t)n, 0);
     rc = scatter_to_device(h, h->head, z.data(), ids, n, 4);
     if (rc) return rc;
+    CU(h, launch_spec_init(h, ids, n, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
     if (h->mirror_on) {                             // keep the host mirror in sync with the overwritten rings
         CU(h, launch_obs(h, nullptr, nullptr, nullptr, 0, ids, n, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));

@@ -307,6 +307,71 @@ __global__ void __launch_bounds__(kObsThreads) obs_kernel_fast(const ObsParams p
     }
 }
 
+// ---- companions of the fused observation tail (step_kernel.cuh: obs_tail) -------------------------------
+// spec_init_kernel: the running rfft bins of an environment, recomputed from its whole ring in float64
+// (after a reset transient, dbsgym_set_window or dbsgym_set_reward).  X_k = sum_m ring[m] e^{j 2 pi k m / W}
+// in ring storage order; one CTA per environment.
+template <typename real>
+__global__ void __launch_bounds__(kObsThreads) spec_init_kernel(const void* ring_, const double* tw_full, double* spec,
+                                                                int W, int nbins, int spec_pitch,
+                                                                const int32_t* env_ids, int n_launch) {
+    __shared__ double part[kObsThreads / 32][2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int slot = blockIdx.x;
+    if (slot >= n_launch) return;
+    const int env = env_ids ? env_ids[slot] : slot;
+    const real* ring = reinterpret_cast<const real*>(ring_) + (size_t)env * W;
+    const double2* tw = reinterpret_cast<const double2*>(tw_full);
+    for (int kb = 0; kb < nbins; ++kb) {
+        double re = 0.0, im = 0.0;
+        for (int m = tid; m < W; m += kObsThreads) {
+            const double x = (double)ring[m];
+            const double2 w = tw[(size_t)m * nbins + kb];
+            re = fma(x, w.x, re);
+            im = fma(x, w.y, im);
+        }
+        re = warp_sum_d(re); im = warp_sum_d(im);
+        if (lane == 0) { part[warp][0] = re; part[warp][1] = im; }
+        __syncthreads();
+        if (tid == 0) {
+            double a = 0.0, b = 0.0;
+            for (int w = 0; w < kObsThreads / 32; ++w) { a += part[w][0]; b += part[w][1]; }
+            spec[((size_t)env * spec_pitch + kb) * 2] = a;
+            spec[((size_t)env * spec_pitch + kb) * 2 + 1] = b;
+        }
+        __syncthreads();
+    }
+}
+
+// obs_copy_kernel: the chronological float32 observation (env.py:454) of every environment from its ring,
+// obs[b][n] = ring[b][(head_b + n) mod W].  Pure HBM streaming: each thread has kCopyPer independent loads
+// in flight; reads are coalesced and writes are coalesced up to the rotation.
+constexpr int kCopyThreads = 256;
+constexpr int kCopyPer = 10;       // 256 * 10 >= W = 2340 in one pass
+template <typename real>
+__global__ void __launch_bounds__(kCopyThreads) obs_copy_kernel(const void* ring_, const int32_t* head, float* obs, int W, int B) {
+    const int env = blockIdx.x;
+    if (env >= B) return;
+    const real* ring = reinterpret_cast<const real*>(ring_) + (size_t)env * W;
+    float* o = obs + (size_t)env * W;
+    const int hd = head[env];
+    for (int base = 0; base < W; base += kCopyThreads * kCopyPer) {
+        real x[kCopyPer];
+#pragma unroll
+        for (int i = 0; i < kCopyPer; ++i) {
+            const int n = base + i * kCopyThreads + threadIdx.x;      // chronological index
+            int m = n + hd;
+            if (m >= W) m -= W;
+            x[i] = n < W ? ring[m] : real(0);
+        }
+#pragma unroll
+        for (int i = 0; i < kCopyPer; ++i) {
+            const int n = base + i * kCopyThreads + threadIdx.x;
+            if (n < W) o[n] = (float)x[i];
+        }
+    }
+}
+
 inline size_t obs_fast_smem_bytes(int nbins, size_t real_bytes) {
     return (size_t)(nbins * kFastIters * 2 + 2 * nbins * kRedPitch) * real_bytes;
 }

@@ -33,6 +33,16 @@ constexpr int kSlots = 6;          // K slots: stage derivative k_{j+1} lives in
 __device__ __forceinline__ int kslot(int j) { return j == 6 ? 1 : j; }
 constexpr int kSampleBatch = 16;   // dense-output samples reduced per block barrier
 
+// y-parity: besides z and x the coupling is also even in dy, and a grid line (8 oscillators along y) lives in ONE
+// thread, so the y reflection needs no shuffles: with e[j] = v[j] + v[7-j], o[j] = v[j] - v[7-j] (j < 4) the 8x8
+// Toeplitz block t[|i-j|] splits into two 4x4 blocks  E_i = sum_j (t[|i-j|] + t[7-i-j]) e[j],
+// O_i = sum_j (t[|i-j|] - t[7-i-j]) o[j]:  32 FFMA2 + 32 FADD instead of 64 FFMA2 per (zj,xj) block (96 instead
+// of 128 FMA-pipe cycles).  Applied in the fp32 fixed-extent contraction (GEO = 1, 2 and cluster mode).
+#ifndef DBSGYM_Y_PARITY
+#define DBSGYM_Y_PARITY 1
+#endif
+constexpr bool kYParity = DBSGYM_Y_PARITY != 0;
+
 enum { MODE_STEP = 0, MODE_TRANSIENT = 1 };
 enum { STATUS_MAX_STEPS = 1, STATUS_NAN = 2, STATUS_SCHEDULE = 4 };
 
@@ -61,12 +71,20 @@ struct StepParams {
     // bookkeeping
     unsigned long long* counters;  // accepted, rejected, rhs evals
     int32_t* status;
+    // fused observation tail (MODE_STEP, beta-power rewards): see obs_tail() below
+    int tail_on, tail_kind, tail_nbins;
+    double* spec;                  // [B][2 * kTailBins] running DFT bins of the ring (storage order), float64
+    const double* tw_full;         // [W][nbins][2] cos, sin of 2*pi*k*m/W
+    float* samples_f; float* mirror; float* reward_f; double* reward; uint8_t* done_out; uint8_t* done_dev;
+    int32_t* step_idx_rw; const int32_t* episode_len;
+    double power_scale, action_cost, threshold, threshold_penalty;
     // cluster mode (one environment = a thread-block cluster of `cluster` CTAs, N > 4096)
     int cluster;                   // CTAs per environment (1 = plain)
     void* cl_operand;              // [B][2][2*Np + kScPad] contraction operand in global memory (L2)
     double* cl_scratch;            // [B][2][cluster][kClSlots] cross-CTA reduction scratch
 };
 
+constexpr int kTailBins = 32;      // at most one rfft bin per lane of the tail warp
 constexpr int kClSlots = 2 * 16;   // doubles per CTA and parity in cl_scratch (= 2 * kSampleBatch)
 
 __device__ __forceinline__ void cluster_barrier() {
@@ -403,13 +421,29 @@ __device__ __forceinline__ void couple_grid_sym_fixed(const float* __restrict__ 
                     b[4 * q4] = v.x; b[4 * q4 + 1] = v.y; b[4 * q4 + 2] = v.z; b[4 * q4 + 3] = v.w;
                 }
             } else loadv<2 * kRows>(bp + (zj * HX + xj) * (2 * kRows), b);
+            if (kYParity) {
+                // operand line layout: pairs (sin, cos) of e[0..3] then o[0..3]; accumulators: E_0..3 then O_0..3
 #pragma unroll
-            for (int yj = 0; yj < kRows; ++yj) {
-                const float2 scj = make_float2(b[2 * yj], b[2 * yj + 1]);
+                for (int j = 0; j < 4; ++j) {
+                    const float2 be = make_float2(b[2 * j], b[2 * j + 1]);
+                    const float2 bo = make_float2(b[8 + 2 * j], b[8 + 2 * j + 1]);
 #pragma unroll
-                for (int yi = 0; yi < kRows; ++yi) {
-                    const float a = u[yi > yj ? yi - yj : yj - yi];
-                    acc[yi] = __ffma2_rn(make_float2(a, a), scj, acc[yi]);
+                    for (int i = 0; i < 4; ++i) {
+                        const float t = u[i > j ? i - j : j - i], h = u[7 - i - j];
+                        const float ce = t + h, co = t - h;
+                        acc[i] = __ffma2_rn(make_float2(ce, ce), be, acc[i]);
+                        acc[4 + i] = __ffma2_rn(make_float2(co, co), bo, acc[4 + i]);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int yj = 0; yj < kRows; ++yj) {
+                    const float2 scj = make_float2(b[2 * yj], b[2 * yj + 1]);
+#pragma unroll
+                    for (int yi = 0; yi < kRows; ++yi) {
+                        const float a = u[yi > yj ? yi - yj : yj - yi];
+                        acc[yi] = __ffma2_rn(make_float2(a, a), scj, acc[yi]);
+                    }
                 }
             }
         }
@@ -454,6 +488,80 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// ---- fused observation tail ------------------------------------------------------------------
+// What the separate observation kernel did after every step (env.py:447-454, :638-650, :669-688), done by
+// the first warp of the environment's own CTA while the other CTAs of the SM keep the FMA pipe busy:
+// append the step's S recorded samples to the ring (and to the host mirror / sample buffer), and update
+// the beta-band reward INCREMENTALLY.  The rfft bins are kept in ring STORAGE order (|X_k| is invariant
+// under the circular shift when the DFT length equals the ring length), so overwriting ring[pos] changes
+//     X_k  by  (x_new - x_old) * e^{j 2 pi k pos / W}:
+// S * nbins float64 FMAs per step instead of a W * nbins pass over the window, and no read of the window
+// at all.  The bins are (re)initialised from the whole ring by spec_init_kernel after a reset transient.
+template <typename real>
+__device__ __forceinline__ void obs_tail(const StepParams& p, int env, int lane, int S) {
+    __shared__ double t_delta[32];
+    __shared__ int t_pos[32];
+    const int W = p.W, nb = p.tail_nbins;
+    real* ring = reinterpret_cast<real*>(p.ring) + (size_t)env * W;
+    const int head = p.head[env];
+    const double2* tw = reinterpret_cast<const double2*>(p.tw_full);
+    double re = 0.0, im = 0.0;
+    for (int i0 = 0; i0 < S; i0 += 32) {
+        const int i = i0 + lane;
+        if (i < S) {
+            int pos = head + i;
+            if (pos >= W) pos -= W;
+            const real v = real(p.lfp_rec[(size_t)env * p.smax + i]);
+            const real old = ring[pos];
+            ring[pos] = v;
+            if (p.samples_f) p.samples_f[(size_t)env * p.smax + i] = (float)v;
+            if (p.mirror) {                           // zero-copy store into the pinned host mirror (both copies)
+                float* mr = p.mirror + (size_t)env * 2 * W;
+                mr[pos] = (float)v;
+                mr[pos + W] = (float)v;
+            }
+            t_delta[lane] = (double)v - (double)old;
+            t_pos[lane] = pos;
+        }
+        __syncwarp();
+        if (lane < nb) {
+            const int cnt = S - i0 < 32 ? S - i0 : 32;
+            for (int j = 0; j < cnt; ++j) {
+                const double2 w = tw[(size_t)t_pos[j] * nb + lane];
+                re = fma(t_delta[j], w.x, re);
+                im = fma(t_delta[j], w.y, im);
+            }
+        }
+        __syncwarp();
+    }
+    double pw = 0.0;
+    if (lane < nb) {
+        double2* sp = reinterpret_cast<double2*>(p.spec) + (size_t)env * kTailBins + lane;
+        double2 X = *sp;
+        X.x += re; X.y += im;
+        *sp = X;
+        const double a = X.x / (double)W, b = X.y / (double)W;
+        pw = (a * a + b * b) * 2.0;                   // utils.py:21-27: one-sided power of bin k
+    }
+    pw = warp_sum(pw);
+    if (lane == 0) {
+        const double au = fabs(p.u_out[env]);
+        double r;
+        if (p.tail_kind == 0) r = -p.power_scale * pw - p.action_cost * au;                                   // env.py:638-650
+        else r = -((p.power_scale * pw > p.threshold) ? p.threshold_penalty : 0.0) - p.action_cost * au;      // env.py:669-688
+        p.reward[env] = r;
+        if (p.reward_f) p.reward_f[env] = (float)r;
+        const int k = p.step_idx_rw[env] + 1;
+        p.step_idx_rw[env] = k;
+        const uint8_t dn = k >= p.episode_len[env] ? 1 : 0;
+        p.done_dev[env] = dn;
+        if (p.done_out) p.done_out[env] = dn;
+        int nh = head + S;
+        if (nh >= W) nh -= W;
+        p.head[env] = nh;
+    }
 }
 
 // =========================================================================================
@@ -564,7 +672,8 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     }
     __syncthreads();
 
-    const real kn = real(SYM ? 0.25 * p.k_over_n : p.k_over_n);
+    constexpr bool YPAR = kYParity && SYM && GEO >= 1 && sizeof(real) == 4;     // the paths that call couple_grid_sym_fixed
+    const real kn = real(SYM ? (YPAR ? 0.125 : 0.25) * p.k_over_n : p.k_over_n);
     const real rtol = real(p.rtol), atol = real(p.atol);
     const real two_pi_r = real(kTwoPi);
     unsigned int n_acc = 0, n_rej = 0, n_rhs = 0;
@@ -654,8 +763,16 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                         for (int r = 0; r < kRows; ++r) { ts_[r] = sv[r]; tc_[r] = cv[r]; }
                         quad_butterfly<real>(ts_, sgn_x, sgn_z, wmask);
                         quad_butterfly<real>(tc_, sgn_x, sgn_z, wmask);
+                        if (YPAR) {                              // y reflection: even / odd combinations of the line
 #pragma unroll
-                        for (int r = 0; r < kRows; ++r) { scw[2 * r] = ts_[r]; scw[2 * r + 1] = tc_[r]; }
+                            for (int r = 0; r < 4; ++r) {
+                                scw[2 * r] = ts_[r] + ts_[7 - r];         scw[2 * r + 1] = tc_[r] + tc_[7 - r];
+                                scw[8 + 2 * r] = ts_[r] - ts_[7 - r];     scw[8 + 2 * r + 1] = tc_[r] - tc_[7 - r];
+                            }
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < kRows; ++r) { scw[2 * r] = ts_[r]; scw[2 * r + 1] = tc_[r]; }
+                        }
                     } else {
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) { scw[2 * r] = sv[r]; scw[2 * r + 1] = cv[r]; }
@@ -676,6 +793,19 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                                                     reinterpret_cast<float(&)[kRows]>(as), reinterpret_cast<float(&)[kRows]>(ac));
                     else
                         couple_grid_sym<real>(SC + pbuf * scsz + sc_sector, T, GZ, GX, zq, xq, sgn_z, sgn_x, as, ac);
+                    if (YPAR) {                                  // (E, O) -> rows i and 7-i (x 1/2 folded into kn)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            const real es = as[r], os = as[4 + r], ec = ac[r], oc = ac[4 + r];
+                            as[r] = es + os; ac[r] = ec + oc;
+                            as[4 + r] = es - os; ac[4 + r] = ec - oc;       // temporarily row 7-r at index 4+r
+                        }
+#pragma unroll
+                        for (int r = 0; r < 2; ++r) {                    // index 4+r holds row 7-r: reverse the upper half
+                            real t_ = as[4 + r]; as[4 + r] = as[7 - r]; as[7 - r] = t_;
+                            t_ = ac[4 + r]; ac[4 + r] = ac[7 - r]; ac[7 - r] = t_;
+                        }
+                    }
                     quad_butterfly<real>(as, sgn_x, sgn_z, wmask);   // back to the grid lines (x 1/4 folded into kn)
                     quad_butterfly<real>(ac, sgn_x, sgn_z, wmask);
                 } else couple_grid<real>(SC + pbuf * scsz, T, GZ, GX, zi, xi, as, ac);
@@ -896,6 +1026,8 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
 #pragma unroll
         for (int r = 0; r < kRows; ++r) p.wind[base + i0 + r] = WD[k0 + r];
     }
+    if (p.tail_on && p.mode == MODE_STEP && crank == 0 && warp == 0)       // (the samples were written before the
+        obs_tail<real>(p, env, lane, seg_nrec[0] + seg_nrec[1]);            //  last __syncthreads of the solve loop)
     if (tid == 0 && crank == 0) {
         if (p.mode == MODE_TRANSIENT) p.head[env] = 0;
         atomicAdd(p.counters + 0, (unsigned long long)n_acc);

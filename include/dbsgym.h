@@ -83,6 +83,9 @@ typedef struct DbsGymRewardSpec {
 
 /* ---- lifetime ------------------------------------------------------------------------- */
 int  dbsgym_abi_version(void);
+/* compile-time switches of this build, for honest op counts in benchmarks: bit 0 = y-parity sector
+ * contraction (DBSGYM_Y_PARITY), bit 1 = libm sincos instead of MUFU (DBSGYM_PRECISE_SINCOS) */
+int  dbsgym_build_flags(void);
 int  dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out);
 void dbsgym_destroy(DbsGymHandle* h);
 /* text of the last error on this handle (h == NULL: last error of a failed create) */

@@ -51,9 +51,11 @@ for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024):
     c = eng.counters()
     k_step, k_obs = np.mean([m[0] for m in ms]), np.mean([m[1] for m in ms])
     rhs = c["rhs_evals"] / (n_timed * B)
+    ypar = bool(eng.lib.dbsgym_build_flags() & 1)          # own op count of the sector contraction, see bench.py
+    SYM_FLOP, SYM_LIN = ((196 if ypar else 304) / 256.0), ((160 if ypar else 128) / 8.0)
     out.append({"N": N, "grid": [8, 8, gz], "envs": B, "step_kernel_ms": float(k_step), "obs_kernel_ms": float(k_obs),
                 "env_steps_per_s": B / ((k_step + k_obs) * 1e-3), "oscillator_updates_per_s": B * N * (c["accepted"] + c["rejected"]) / (n_timed * B) / ((k_step + k_obs) * 1e-3),
-                "rhs_per_env_step": rhs, "executed_tflops": rhs * 1.22 * N * N * B / (k_step * 1e-3) / 1e12,
+                "rhs_per_env_step": rhs, "executed_tflops": rhs * (SYM_FLOP * N * N + SYM_LIN * N) * B / (k_step * 1e-3) / 1e12,
                 "dense_equivalent_tflops": rhs * 4 * N * N * B / (k_step * 1e-3) / 1e12,
                 "transient_s": t_tr, "status": c["status"], "ctas_per_env": max(1, N // 4096)})
     print(json.dumps(out[-1]), flush=True)
