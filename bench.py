@@ -295,16 +295,23 @@ def run_gpu_arm(args):
         # The GRID_SYM kernel evaluates the same contraction in the parity-sector basis; its OWN executed
         # flop count (what the roofline fraction is quoted against, SURVEY.md 8d rule for reduced
         # formulations) per thread and (zj,xj) block -- there are N^2/256 of those per RHS -- is
-        #   z/x sectors only : 12 FFMA2 (table rows -> sector coefficients) + 64 FFMA2        = 304 flop
-        #   + y parity       : 12 FFMA2 + 20 FADD (even/odd coefficients) + 32 FFMA2          = 196 flop
-        # (instruction counts checked in the SASS: 704 FFMA2 = 16 x 44 in the unrolled contraction), plus the
-        # quad butterflies (128 flop) and, with y parity, the even/odd folds (32 flop) per thread = N/8 threads.
+        #   z/x sectors only            : 12 FFMA2 (table rows -> sector coefficients) + 64 FFMA2      = 304 flop
+        #   + y parity                  : 12 FFMA2 + 20 FADD (even/odd coefficients) + 32 FFMA2        = 196 flop
+        #   + y parity, multi-worker    : 20 FADD + 32 FFMA2 (coefficients precomputed once per CTA)   = 148 flop
+        # (instruction counts checked in the SASS: 704 = 16 x 44 resp. 512 = 16 x 32 FFMA2 in the unrolled contraction),
+        # plus the quad butterflies (128 flop) and, with y parity, the even/odd folds (32 flop) per thread = N/8 threads.
         from dbsgym_b200 import _capi
         ypar = bool(_capi.load().dbsgym_build_flags() & 1)
+        variant = eng.step_variant(B)
         dense_flop_per_env_step = rhs_per_env_step * 4 * N_OSC * N_OSC + 700 * N_OSC
-        sym = eng.coupling == "grid" and os.environ.get("DBSGYM_NO_SYM", "") != "1"
-        sym_flop_per_rhs = ((196 if ypar else 304) / 256.0) * N_OSC * N_OSC + ((160 if ypar else 128) / 8.0) * N_OSC
+        sym = variant in (2, 3, 4, 6)
+        blk_flop = 148 if variant == 4 else (196 if (ypar and variant in (3, 6)) else 304)
+        sym_flop_per_rhs = (blk_flop / 256.0) * N_OSC * N_OSC + ((160 if ypar else 128) / 8.0) * N_OSC
         flop_per_env_step = (rhs_per_env_step * sym_flop_per_rhs + 700 * N_OSC) if sym else dense_flop_per_env_step
+        kernel_name = {0: "step_kernel<float,GRID>", 1: "step_kernel<DENSE>", 2: "step_kernel<GRID_SYM>",
+                       3: "step_kernel<float,GRID_SYM,8x8x8" + (",y-parity>" if ypar else ">"),
+                       4: "step_kernel<float,GRID_SYM,8x8x8,y-parity,multi-worker (8 envs per CTA, precomputed sector coefficients)>",
+                       5: "step_kernel<cluster>", 6: "step_kernel<float,GRID_SYM,gx=8>"}.get(variant, "step_kernel")
         k_step = float(np.mean([m[0] for m in kern_ms])) * 1e-3
         k_obs = float(np.mean([m[1] for m in kern_ms])) * 1e-3
         peaks, peak_src = measured_peaks()
@@ -343,7 +350,7 @@ def run_gpu_arm(args):
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 4096 envs, from the ncu
                          # --set full capture profiles/r01_final_step_obs_raw.csv (42.06 MB read + 0.10 MB write)
                          "traffic": 42.15e6 * B / 4096,
-                         "kernel": ("step_kernel<float,GRID_SYM,y-parity>" if ypar else "step_kernel<float,GRID_SYM>") if sym else "step_kernel<float,GRID>",
+                         "kernel": kernel_name,
                          "kernel_ms": k_step * 1e3, "flop_per_env_step": flop_per_env_step,
                          "dense_formulation_flop_per_env_step": dense_flop_per_env_step,
                          "dense_equivalent_tflops": dense_flop_per_env_step * B / k_step / 1e12,

@@ -22,7 +22,7 @@ COUPLING_GRID, COUPLING_DENSE = 0, 1
 REWARD_BBPOW, REWARD_TEMP_CONST, REWARD_BBPOW_THRESH = 0, 1, 2
 
 EXPORTS = [
-    "dbsgym_abi_version", "dbsgym_build_flags", "dbsgym_create", "dbsgym_destroy", "dbsgym_last_error",
+    "dbsgym_abi_version", "dbsgym_build_flags", "dbsgym_step_variant", "dbsgym_create", "dbsgym_destroy", "dbsgym_last_error",
     "dbsgym_set_coupling_grid", "dbsgym_set_coupling_dense", "dbsgym_set_env_params",
     "dbsgym_set_recording", "dbsgym_set_schedule", "dbsgym_set_reward", "dbsgym_set_episode",
     "dbsgym_transient", "dbsgym_step", "dbsgym_step_host", "dbsgym_step_host_samples", "dbsgym_host_mirror", "dbsgym_step_host_mirror", "dbsgym_get_obs_host",
@@ -100,6 +100,7 @@ def load():
     P = {
         "dbsgym_abi_version": (C.c_int, []),
         "dbsgym_build_flags": (C.c_int, []),
+        "dbsgym_step_variant": (C.c_int, [vp, C.c_int32]),
         "dbsgym_create": (C.c_int, [C.POINTER(DbsGymConfig), C.POINTER(vp)]),
         "dbsgym_destroy": (None, [vp]),
         "dbsgym_last_error": (C.c_char_p, [vp]),

@@ -72,6 +72,8 @@ struct DbsGymHandle {
     int cluster = 1;                     // CTAs per environment (thread-block cluster; > 1 when N > 4096)
     void* cl_operand = nullptr; double* cl_scratch = nullptr;
     int ctas_per_sm = 0;                 // 0 = whatever fits
+    int num_sms = 0;
+    int mw_mode = -1;                    // multi-worker step kernel: -1 auto (full-occupancy batches), 0 never, 1 always
     bool grid_sym = false;               // GRID coupling: use the reflection-symmetry reduced contraction
     bool timing = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -263,12 +265,29 @@ cudaError_t launch_step_t(DbsGymHandle* h, const StepParams& p, cudaStream_t s) 
     return cudaGetLastError();
 }
 
+// multi-worker kernel: kMwEnvs environments per CTA (one per 64-thread worker), one persistent CTA per SM
+cudaError_t launch_step_mw(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
+    auto kern = step_kernel<float, CPL_GRID_SYM, kMwEnvs * kMwThreads, 1, 0, kMwEnvs>;
+    const size_t smem = step_smem_bytes_mw(h->Np);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int ctas = (p.n_launch + kMwEnvs - 1) / kMwEnvs;
+    if (ctas > h->num_sms) ctas = h->num_sms;
+    kern<<<ctas, kMwEnvs * kMwThreads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
 template <typename real, int CPL>
 cudaError_t launch_step_m(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
     const int t = h->nthreads;
     if constexpr (CPL == CPL_GRID_SYM && sizeof(real) == 4) {
         static const bool no_geo1 = getenv("DBSGYM_NO_GEO1") != nullptr;        // A/B switch for tuning runs
-        if (t == 64 && p.GZ == 8 && p.GX == 8 && !no_geo1) return launch_step_t<real, CPL, 64, 1>(h, p, s);
+        if (t == 64 && p.GZ == 8 && p.GX == 8 && !no_geo1) {
+            // enough environments to fill every SM with kMwEnvs of them: share the sector-coefficient table
+            const bool mw = kYParity && (h->mw_mode == 1 || (h->mw_mode < 0 && p.n_launch >= kMwEnvs * h->num_sms));
+            if (mw) return launch_step_mw(h, p, s);
+            return launch_step_t<real, CPL, 64, 1>(h, p, s);
+        }
     }
     if constexpr (CPL == CPL_GRID_SYM && sizeof(real) == 4) if (p.GX == 8) {   // sweep grids 8 x 8 x gz
         if (t <= 64) return launch_step_t<real, CPL, 64, 2>(h, p, s);
@@ -408,6 +427,20 @@ extern "C" {
 
 int dbsgym_abi_version(void) { return DBSGYM_ABI_VERSION; }
 
+int dbsgym_step_variant(const DbsGymHandle* h, int32_t n_envs) {
+    if (!h) return DBSGYM_EINVAL;
+    if (h->cluster > 1) return 5;
+    if (h->cfg.coupling == DBSGYM_COUPLING_DENSE) return 1;
+    if (!h->grid_sym) return 0;
+    if (h->f64) return 2;
+    const bool geo1 = h->nthreads == 64 && h->cfg.grid[2] == 8 && h->cfg.grid[0] == 8 && !getenv("DBSGYM_NO_GEO1");
+    if (geo1) {
+        const bool mw = kYParity && (h->mw_mode == 1 || (h->mw_mode < 0 && n_envs >= kMwEnvs * h->num_sms));
+        return mw ? 4 : 3;
+    }
+    return h->cfg.grid[0] == 8 ? 6 : 2;
+}
+
 int dbsgym_build_flags(void) {
     int f = kYParity ? 1 : 0;
 #ifdef DBSGYM_PRECISE_SINCOS
@@ -488,6 +521,8 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
     }
     memset(&h->rspec, 0, sizeof(h->rspec));
     if (const char* e = getenv("DBSGYM_CTAS_PER_SM")) h->ctas_per_sm = atoi(e);
+    if (const char* e = getenv("DBSGYM_MW")) h->mw_mode = atoi(e);             // A/B and test hook
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
     const size_t BN = (size_t)h->B * Np;
     bool ok = true;
     ok = ok && cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess;

@@ -253,12 +253,12 @@ __device__ __forceinline__ void couple_grid<float>(const float* __restrict__ sc,
 // The four lanes of a quad own the four mirror-image grid lines; the sector transform is a 2-stage
 // warp-shuffle butterfly (no extra shared memory, no extra barrier).  U^p is not stored: its 8 entries
 // per (zj,xj) block are combined on the fly from four rows of the 2 KB Toeplitz table.
-template <typename real>
+template <typename real, int MX = 1, int MZ = 2>   // lane bits that select the x- and the z-mirror image
 __device__ __forceinline__ void quad_butterfly(real (&v)[kRows], real sx, real sz, unsigned mask) {
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) { const real o = __shfl_xor_sync(mask, v[r], 1); v[r] = fma_r(sx, v[r], o); }
+    for (int r = 0; r < kRows; ++r) { const real o = __shfl_xor_sync(mask, v[r], MX); v[r] = fma_r(sx, v[r], o); }
 #pragma unroll
-    for (int r = 0; r < kRows; ++r) { const real o = __shfl_xor_sync(mask, v[r], 2); v[r] = fma_r(sz, v[r], o); }
+    for (int r = 0; r < kRows; ++r) { const real o = __shfl_xor_sync(mask, v[r], MZ); v[r] = fma_r(sz, v[r], o); }
 }
 
 template <typename real>
@@ -459,6 +459,79 @@ __device__ __forceinline__ void couple_grid_sym_fixed(const float* __restrict__ 
     for (int r = 0; r < kRows; ++r) { as[r] = acc[r].x; ac[r] = acc[r].y; }
 }
 
+// ---- multi-worker mode (MW): precomputed sector coefficients ------------------------------------------
+// ncu on the kernel above (profiles/r01b_*): the contraction is bound by the shared-memory pipe, not by the FMA
+// pipe -- per (zj,xj) block a warp issues 8 LDS.128 for the four table rows (2 cycles each: the lanes of a quad
+// share the address) and 4 LDS.128 for the operand line (4 cycles each: lanes with equal sector share the
+// address, but the LSU only merges ADJACENT lanes -- scripts/microbench/lds_patterns.cu), 32 cycles against 27
+// cycles of FFMA2 / FADD.  The sector coefficients u^p[(zq,xq)][(zj,xj)][dy] do not depend on the environment:
+// 4 x 16 x 16 x 8 floats = 32 KB.  One CTA therefore hosts kMwEnvs environments (one 64-thread WORKER each,
+// named barriers, persistent loop over environments), builds the 32 KB table once and shares it: per block a
+// thread now loads its 8 coefficients directly (2 LDS.128, distinct per lane: 4 cycles each) and -- with the
+// lanes of a warp ordered sector-major (lane = 8 * sector + quad) -- the operand line with merged 2-cycle loads:
+// 16 cycles of shared memory and 21 cycles of FFMA2 / FADD per block (no coefficient combination either).
+constexpr int kMwEnvs = 8;                          // environments (workers) per CTA
+constexpr int kMwThreads = 64;                      // threads per worker = grid lines of the 8 x 8 x 8 grid
+constexpr int kMwUFloat4 = 16 * 2 * kMwThreads;     // [block][half][worker thread] float4 entries of the coefficient table
+
+__device__ __forceinline__ void couple_sym_upre(const float* __restrict__ bp, const float4* __restrict__ U4, int tid_w,
+                                                float (&as)[kRows], float (&ac)[kRows]) {
+    float2 acc[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int blk = 0; blk < 16; ++blk) {
+        float u[kRows], b[2 * kRows];
+        unpack(U4[(2 * blk) * kMwThreads + tid_w], u);
+        unpack(U4[(2 * blk + 1) * kMwThreads + tid_w], u + 4);
+        loadv<2 * kRows>(bp + blk * (2 * kRows), b);
+        // operand line layout: pairs (sin, cos) of e[0..3] then o[0..3]; accumulators: E_0..3 then O_0..3
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 be = make_float2(b[2 * j], b[2 * j + 1]);
+            const float2 bo = make_float2(b[8 + 2 * j], b[8 + 2 * j + 1]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float t = u[i > j ? i - j : j - i], h = u[7 - i - j];
+                const float ce = t + h, co = t - h;
+                acc[i] = __ffma2_rn(make_float2(ce, ce), be, acc[i]);
+                acc[4 + i] = __ffma2_rn(make_float2(co, co), bo, acc[4 + i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) { as[r] = acc[r].x; ac[r] = acc[r].y; }
+}
+
+// coefficient table of the 8 x 8 x 8 grid, built once per CTA from the 2 KB Toeplitz table in global memory.
+// Entry (blk = zj*4+xj, half, t): u^p[dy = 4*half .. 4*half+3] of worker thread t, combined in the same order
+// (and therefore to the same bits) as sym_combine() does on the fly.
+__device__ __forceinline__ void mw_decode(int t, int& zq, int& xq, int& sec) {
+    const int lane = t & 31, q = (t >> 5) * 8 + (lane & 7);
+    sec = lane >> 3; zq = q >> 2; xq = q & 3;
+}
+__device__ __forceinline__ void mw_build_table(float4* U4, const float* __restrict__ Tg, int tid, int nthreads) {
+    constexpr int GX = 8, GZ = 8, NC = GX * GZ;
+    for (int e = tid; e < kMwUFloat4; e += nthreads) {
+        const int t = e & (kMwThreads - 1), half = (e >> 6) & 1, blk = e >> 7;
+        int zq, xq, sec;
+        mw_decode(t, zq, xq, sec);
+        const int zj = blk >> 2, xj = blk & 3;
+        const int dz0 = zq > zj ? zq - zj : zj - zq, dz1 = GZ - 1 - zq - zj;
+        const int dx0 = xq > xj ? xq - xj : xj - xq, dx1 = GX - 1 - xq - xj;
+        const float px = (sec & 1) ? -1.f : 1.f, pz = (sec & 2) ? -1.f : 1.f;
+        const float4* T4 = reinterpret_cast<const float4*>(Tg) + half * NC;
+        const float4 a00 = __ldg(T4 + dz0 * GX + dx0), a01 = __ldg(T4 + dz0 * GX + dx1);
+        const float4 a10 = __ldg(T4 + dz1 * GX + dx0), a11 = __ldg(T4 + dz1 * GX + dx1);
+        float4 u;
+        u.x = fmaf(pz, fmaf(px, a11.x, a10.x), fmaf(px, a01.x, a00.x));
+        u.y = fmaf(pz, fmaf(px, a11.y, a10.y), fmaf(px, a01.y, a00.y));
+        u.z = fmaf(pz, fmaf(px, a11.z, a10.z), fmaf(px, a01.z, a00.z));
+        u.w = fmaf(pz, fmaf(px, a11.w, a10.w), fmaf(px, a01.w, a00.w));
+        U4[e] = u;
+    }
+}
+
 // ---- coupling contraction, DENSE mode (alpha^T streamed from global / L2) -----------------
 template <typename real>
 __device__ __forceinline__ void couple_dense(const real* __restrict__ sc, const real* __restrict__ alphaT,
@@ -500,9 +573,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // S * nbins float64 FMAs per step instead of a W * nbins pass over the window, and no read of the window
 // at all.  The bins are (re)initialised from the whole ring by spec_init_kernel after a reset transient.
 template <typename real>
-__device__ __forceinline__ void obs_tail(const StepParams& p, int env, int lane, int S) {
-    __shared__ double t_delta[32];
-    __shared__ int t_pos[32];
+__device__ __forceinline__ void obs_tail(const StepParams& p, int env, int lane, int S, double* t_delta, int* t_pos) {
     const int W = p.W, nb = p.tail_nbins;
     real* ring = reinterpret_cast<real*>(p.ring) + (size_t)env * W;
     const int head = p.head[env];
@@ -580,6 +651,14 @@ enum { CPL_GRID = 0, CPL_DENSE = 1, CPL_GRID_SYM = 2 };
 constexpr int kScBuffers = DBSGYM_SC_BUFFERS;   // 2: one barrier per RHS evaluation; 1: two barriers, 4 KB less shared memory
 constexpr int kScPad = 16;     // reals of padding per operand buffer (GRID_SYM staggers its 4 sectors by 16 B)
 
+// shared memory of one worker in multi-worker mode (fp32): K slots, double-buffered operand, winding counts,
+// reduction scratch, observation-tail scratch
+__host__ __device__ inline size_t step_smem_bytes_worker(int Np) {
+    const int nwarps = kMwThreads / 32;
+    return (size_t)(kSlots * Np + kScBuffers * (2 * Np + kScPad)) * sizeof(float) + (size_t)Np * sizeof(int) +
+           (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 32 * sizeof(int);
+}
+
 // GEO = 1: the grid extents are the compile-time constants 8 x 8 x 8 (every shipped config), which
 // turns the table / operand address arithmetic of the contraction into immediates.  GEO = 2: gx = 8 at compile
 // time, gz at run time (the 8 x 8 x gz grids of the oscillator-count sweep): x loop unrolled, z loop rolled.
@@ -593,61 +672,93 @@ constexpr int kScPad = 16;     // reals of padding per operand buffer (GRID_SYM 
 // contraction operand is exchanged through a double-buffered global (L2-resident) buffer, the coupling table is
 // read through the read-only path, and the barrier per RHS evaluation as well as the error-norm / LFP reductions
 // become cluster-scope (barrier.cluster release/acquire + a few doubles of global scratch).
-template <typename real, int CPL, int MAXT, int GEO = 0, int CL = 0>
+template <typename real, int CPL, int MAXT, int GEO = 0, int CL = 0, int EPC = 1>
 __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p) {
     constexpr bool DENSE = CPL == CPL_DENSE;
     constexpr bool SYM = CPL == CPL_GRID_SYM;
+    constexpr bool MW = EPC > 1;       // multi-worker mode: EPC environments per CTA, one 64-thread worker each
     static_assert(CL == 0 || (CPL == CPL_GRID_SYM && GEO == 2 && sizeof(real) == 4), "cluster mode: fp32 GRID_SYM, gx = 8");
+    static_assert(!MW || (CPL == CPL_GRID_SYM && GEO == 1 && sizeof(real) == 4 && CL == 0 && kYParity && MAXT == EPC * kMwThreads),
+                  "multi-worker mode: fp32 GRID_SYM on the 8 x 8 x 8 grid with y parity");
     const int GZ = GEO == 1 ? 8 : p.GZ, GX = GEO >= 1 ? 8 : p.GX;      // GEO == 2: gx = 8 fixed, gz at run time
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, nt = blockDim.x;
+    const int wid = MW ? (int)(threadIdx.x / kMwThreads) : 0;         // worker of this thread
+    const int tid = MW ? (int)(threadIdx.x % kMwThreads) : (int)threadIdx.x, nt = MW ? kMwThreads : (int)blockDim.x;
     const int lane = tid & 31, warp = tid >> 5, nwarps = (nt + 31) >> 5;
     const int Np = p.Np;
     const int NC_ = CL ? p.cluster : 1;                   // CTAs per environment
     const int crank = CL ? (int)(blockIdx.x % NC_) : 0;   // rank of this CTA in its cluster (1-D grid, cluster dims (C,1,1))
-    const int Nl = CL ? nt * kRows : Np;                  // oscillators whose state lives in THIS CTA's shared memory
-    const int tab = (DENSE || CL) ? 0 : GZ * GX * kRows;
+    const int Nl = CL ? nt * kRows : Np;                  // oscillators whose state lives in THIS CTA's (worker's) shared memory
+    const int tab = (DENSE || CL || MW) ? 0 : GZ * GX * kRows;
     const int scsz = 2 * Np + kScPad;
 
-    const int slot = CL ? (int)(blockIdx.x / NC_) : (int)blockIdx.x;
-    if (slot >= p.n_launch) return;                       // (whole clusters leave together)
-    const int env = p.env_ids ? p.env_ids[slot] : slot;
-    const size_t base = (size_t)env * Np;
-
-    real* K = reinterpret_cast<real*>(smem_raw);          // [kSlots][Nl] stage derivatives f(y_s), thread-private slots
+    // shared memory of this CTA (MW: the coefficient table, then one such block per worker)
+    unsigned char* wsm = smem_raw + (MW ? kMwUFloat4 * sizeof(float4) + (size_t)wid * step_smem_bytes_worker(Np) : 0);
+    real* K = reinterpret_cast<real*>(wsm);               // [kSlots][Nl] stage derivatives f(y_s), thread-private slots
     real* SCs = K + kSlots * Nl;                          // [kScBuffers][scsz] (sin, cos) contraction operand (not in cluster mode)
     real* Ts = SCs + (CL ? 0 : kScBuffers * scsz);        // [tab]
-    real* RC = Ts + tab;                                  // [Nl] recording conductance (thread-private slots)
-    int* WD = reinterpret_cast<int*>(RC + Nl);            // [Nl] fp32 mode: winding counts, y = phase + 2*pi*wind
+    real* RC = Ts + tab;                                  // [Nl] recording conductance (thread-private slots; MW: read from global)
+    int* WD = reinterpret_cast<int*>(RC + (MW ? 0 : Nl)); // [Nl] fp32 mode: winding counts, y = phase + 2*pi*wind
     double* part = reinterpret_cast<double*>(WD + Nl);    // [nwarps][kSampleBatch][2]
     double* red = part + nwarps * kSampleBatch * 2;       // [nwarps]
-    real* SC = CL ? reinterpret_cast<real*>(p.cl_operand) + (size_t)env * 2 * scsz : SCs;
+    double* t_delta = red + nwarps;                       // [32] observation tail scratch
+    int* t_pos = reinterpret_cast<int*>(t_delta + 32);    // [32]
     const real* T = CL ? reinterpret_cast<const real*>(p.table) : Ts;
-    double* cls = CL ? p.cl_scratch + (size_t)env * 2 * NC_ * kClSlots : nullptr;
-    int cl_par = 0;
+    const float4* U4 = reinterpret_cast<const float4*>(smem_raw);       // MW: [16][2][64] sector coefficients
+
+    // barrier over the threads that integrate one environment
+    auto env_sync = [&]() {
+        if (MW) asm volatile("bar.sync %0, %1;" ::"r"(wid + 1), "n"(kMwThreads) : "memory");
+        else __syncthreads();
+    };
 
     const int tid_g = crank * nt + tid;                   // thread index within the environment
     const int k0 = tid * kRows;                           // private slot in K / RC / WD (and in the plain operand)
-    // grid line owned by this thread.  GRID: line = tid.  GRID_SYM: a quad of lanes owns the four mirror
-    // images (z,x), (z,X-x), (Z-z,x), (Z-z,X-x) of fundamental line q = tid / 4.
-    int zi = 0, xi = 0, zq = 0, xq = 0;
+    // grid line owned by this thread.  GRID: line = tid.  GRID_SYM: the four mirror images (z,x), (z,X-x), (Z-z,x),
+    // (Z-z,X-x) of fundamental line q are owned by the four lanes of a quad (q = tid / 4, image = tid & 3), in
+    // multi-worker mode by lanes 8 apart (lane = 8 * image + q % 8: lanes with equal image are adjacent).
+    int zi = 0, xi = 0, zq = 0, xq = 0, img = 0, qline = 0;
     real sgn_x = real(1), sgn_z = real(1);
     if (SYM) {
-        const int HX = GX >> 1, q = tid_g >> 2;
-        zq = q / HX; xq = q % HX;
-        zi = (tid & 2) ? GZ - 1 - zq : zq;
-        xi = (tid & 1) ? GX - 1 - xq : xq;
-        sgn_x = (tid & 1) ? real(-1) : real(1);
-        sgn_z = (tid & 2) ? real(-1) : real(1);
+        const int HX = GX >> 1;
+        if (MW) mw_decode(tid, zq, xq, img);
+        else { const int q = tid_g >> 2; zq = q / HX; xq = q % HX; img = tid & 3; }
+        qline = zq * HX + xq;
+        zi = (img & 2) ? GZ - 1 - zq : zq;
+        xi = (img & 1) ? GX - 1 - xq : xq;
+        sgn_x = (img & 1) ? real(-1) : real(1);
+        sgn_z = (img & 2) ? real(-1) : real(1);
     } else if (!DENSE) {
         zi = tid / GX; xi = tid % GX;
     }
     const int i0 = DENSE ? k0 : (zi * GX + xi) * kRows; // first oscillator index in the global arrays
     const unsigned wmask = __activemask();
-    // operand slot written by this thread: plain = own line; GRID_SYM = sector (tid & 3), line q
+    // operand slot written by this thread: plain = own line; GRID_SYM = sector img, line q
     const int sec_stride = (GZ >> 1) * (GX >> 1) * 2 * kRows + (int)(16 / sizeof(real));
-    const int sc_sector = SYM ? (tid & 3) * sec_stride : 0;
-    const int sc_slot = SYM ? sc_sector + (tid_g >> 2) * 2 * kRows : 2 * k0;
+    const int sc_sector = SYM ? img * sec_stride : 0;
+    const int sc_slot = SYM ? sc_sector + qline * 2 * kRows : 2 * k0;
+    constexpr int BMX = MW ? 8 : 1, BMZ = MW ? 16 : 2;     // lane bits of the x / z mirror image (quad_butterfly)
+
+    if (MW) {                                             // the coefficient table, once per CTA
+        mw_build_table(reinterpret_cast<float4*>(smem_raw), reinterpret_cast<const float*>(p.table), (int)threadIdx.x, (int)blockDim.x);
+        __syncthreads();
+    } else if (!DENSE && !CL) {
+        using V = typename Vec<real>::T;
+        constexpr int vn = Vec<real>::n;
+        const V* tg = reinterpret_cast<const V*>(p.table);
+        for (int i = tid; i < tab / vn; i += nt) reinterpret_cast<V*>(Ts)[i] = tg[i];
+    }
+
+    // ---- environments of this CTA (worker): exactly one, or in multi-worker mode a persistent loop --------
+    int slot = MW ? wid * (int)gridDim.x + (int)blockIdx.x : (CL ? (int)(blockIdx.x / NC_) : (int)blockIdx.x);
+    const int slot_stride = MW ? (int)gridDim.x * EPC : 0;
+#pragma unroll 1
+    for (; slot < p.n_launch; slot += slot_stride) {      // (in cluster mode whole clusters leave together)
+    const int env = p.env_ids ? p.env_ids[slot] : slot;
+    const size_t base = (size_t)env * Np;
+    real* SC = CL ? reinterpret_cast<real*>(p.cl_operand) + (size_t)env * 2 * scsz : SCs;
+    double* cls = CL ? p.cl_scratch + (size_t)env * 2 * NC_ * kClSlots : nullptr;
+    int cl_par = 0;
 
     // Register diet: only y0 and (per segment) c0 = w0 + amp * stim stay in registers across the
     // contraction; the recording conductance and the winding counts live in thread-private shared slots.
@@ -660,17 +771,11 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
 #pragma unroll
             for (int r = 0; r < kRows; ++r) rc[r] = real(0);
         }
-        storev<kRows>(RC + k0, rc);
+        if (!MW) storev<kRows>(RC + k0, rc);
 #pragma unroll
         for (int r = 0; r < kRows; ++r) WD[k0 + r] = sizeof(real) == 4 ? p.wind[base + i0 + r] : 0;
     }
-    if (!DENSE && !CL) {
-        using V = typename Vec<real>::T;
-        constexpr int vn = Vec<real>::n;
-        const V* tg = reinterpret_cast<const V*>(p.table);
-        for (int i = tid; i < tab / vn; i += nt) reinterpret_cast<V*>(Ts)[i] = tg[i];
-    }
-    __syncthreads();
+    env_sync();
 
     constexpr bool YPAR = kYParity && SYM && GEO >= 1 && sizeof(real) == 4;     // the paths that call couple_grid_sym_fixed
     const real kn = real(SYM ? (YPAR ? 0.125 : 0.25) * p.k_over_n : p.k_over_n);
@@ -761,8 +866,8 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                         real ts_[kRows], tc_[kRows];
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) { ts_[r] = sv[r]; tc_[r] = cv[r]; }
-                        quad_butterfly<real>(ts_, sgn_x, sgn_z, wmask);
-                        quad_butterfly<real>(tc_, sgn_x, sgn_z, wmask);
+                        quad_butterfly<real, BMX, BMZ>(ts_, sgn_x, sgn_z, wmask);
+                        quad_butterfly<real, BMX, BMZ>(tc_, sgn_x, sgn_z, wmask);
                         if (YPAR) {                              // y reflection: even / odd combinations of the line
 #pragma unroll
                             for (int r = 0; r < 4; ++r) {
@@ -779,11 +884,14 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                     }
                     storev<2 * kRows>(SC + pbuf * scsz + sc_slot, scw);
                 }
-                if (CL) cluster_barrier(); else __syncthreads();
+                if (CL) cluster_barrier(); else env_sync();
                 real as[kRows], ac[kRows];
                 if (DENSE) couple_dense<real>(SC + pbuf * scsz, reinterpret_cast<const real*>(p.alpha), Np, i0, as, ac);
                 else if (SYM) {
-                    if (GEO == 1 && sizeof(real) == 4)
+                    if (MW)
+                        couple_sym_upre(reinterpret_cast<const float*>(SC + pbuf * scsz + sc_sector), U4, tid,
+                                        reinterpret_cast<float(&)[kRows]>(as), reinterpret_cast<float(&)[kRows]>(ac));
+                    else if (GEO == 1 && sizeof(real) == 4)
                         couple_grid_sym_fixed<4, 4>(reinterpret_cast<const float*>(SC + pbuf * scsz + sc_sector),
                                                     reinterpret_cast<const float*>(T), zq, xq, (float)sgn_z, (float)sgn_x, 4,
                                                     reinterpret_cast<float(&)[kRows]>(as), reinterpret_cast<float(&)[kRows]>(ac));
@@ -806,8 +914,8 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                             t_ = ac[4 + r]; ac[4 + r] = ac[7 - r]; ac[7 - r] = t_;
                         }
                     }
-                    quad_butterfly<real>(as, sgn_x, sgn_z, wmask);   // back to the grid lines (x 1/4 folded into kn)
-                    quad_butterfly<real>(ac, sgn_x, sgn_z, wmask);
+                    quad_butterfly<real, BMX, BMZ>(as, sgn_x, sgn_z, wmask);   // back to the grid lines (x 1/4 folded into kn)
+                    quad_butterfly<real, BMX, BMZ>(ac, sgn_x, sgn_z, wmask);
                 } else couple_grid<real>(SC + pbuf * scsz, T, GZ, GX, zi, xi, as, ac);
                 real ks[kRows];
 #pragma unroll
@@ -815,7 +923,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                     ks[r] = c0[r] + kn * (cv[r] * as[r] - sv[r] * ac[r]);
                 storev<kRows>(K + kslot(s) * Nl + k0, ks);
                 if (kScBuffers == 2 || CL) pbuf ^= 1;  // (the global operand of cluster mode is always double buffered)
-                else __syncthreads();             // operand buffer is about to be overwritten by the next stage
+                else env_sync();                  // operand buffer is about to be overwritten by the next stage
                 ++n_rhs;
             }
             have_f0 = true;
@@ -869,7 +977,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
             }
             sq = warp_sum(sq);
             if (lane == 0) red[warp] = sq;
-            __syncthreads();
+            env_sync();
             double tot = 0.0;
             for (int w = 0; w < nwarps; ++w) tot += red[w];
             if (CL) {                              // sum the per-CTA partials of the cluster (same order in every CTA)
@@ -928,7 +1036,12 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                                 const real tau = (tnext == t) ? real(0) : real((tsv - t) / (tnext - t));
                                 real st = real(0), sr = real(0);
                                 real rc[kRows];
-                                loadv<kRows>(RC + k0, rc);
+                                if (!MW) loadv<kRows>(RC + k0, rc);
+                                else if (p.weighted_rec) loadv<kRows>(reinterpret_cast<const real*>(p.rec) + base + i0, rc);
+                                else {
+#pragma unroll
+                                    for (int r = 0; r < kRows; ++r) rc[r] = real(0);
+                                }
 #pragma unroll
                                 for (int r = 0; r < kRows; ++r) {
                                     real inc = (((pa[r] * tau + pb[r]) * tau + pc[r]) * tau + f0[r]) * tau;
@@ -945,7 +1058,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                             }
                             ++nb;
                         }
-                        __syncthreads();
+                        env_sync();
                         if (CL) {                  // CTA partials -> global scratch -> summed by the rank-0 CTA below
                             for (int q = tid; q < nb; q += nt) {
                                 double a_t = 0.0, a_r = 0.0;
@@ -983,7 +1096,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                             }
                         }
                         if (CL) cl_par ^= 1;
-                        __syncthreads();
+                        env_sync();
                         save_idx += nb;
                     }
                 }
@@ -1027,7 +1140,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
         for (int r = 0; r < kRows; ++r) p.wind[base + i0 + r] = WD[k0 + r];
     }
     if (p.tail_on && p.mode == MODE_STEP && crank == 0 && warp == 0)       // (the samples were written before the
-        obs_tail<real>(p, env, lane, seg_nrec[0] + seg_nrec[1]);            //  last __syncthreads of the solve loop)
+        obs_tail<real>(p, env, lane, seg_nrec[0] + seg_nrec[1], t_delta, t_pos);   //  last barrier of the solve loop)
     if (tid == 0 && crank == 0) {
         if (p.mode == MODE_TRANSIENT) p.head[env] = 0;
         atomicAdd(p.counters + 0, (unsigned long long)n_acc);
@@ -1035,18 +1148,23 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
         atomicAdd(p.counters + 2, (unsigned long long)n_rhs);
         if (status) atomicOr(p.status, status);
     }
+    if (!MW) break;
+    env_sync();                                           // the worker's shared memory is reused by its next environment
+    }
 }
+
+inline size_t step_smem_bytes_mw(int Np) { return kMwUFloat4 * sizeof(float4) + kMwEnvs * step_smem_bytes_worker(Np); }
 
 inline size_t step_smem_bytes_cluster(int nthreads, size_t real_bytes) {
     const int nwarps = (nthreads + 31) / 32, Nl = nthreads * kRows;
     return (size_t)((kSlots + 1) * Nl) * real_bytes + (size_t)Nl * sizeof(int) +
-           (size_t)(nwarps * kSampleBatch * 2 + nwarps) * sizeof(double);
+           (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 32 * sizeof(int);
 }
 
 inline size_t step_smem_bytes(int Np, int tab, int nthreads, size_t real_bytes) {
     const int nwarps = (nthreads + 31) / 32;
     return (size_t)((kSlots + 1 + 2 * kScBuffers) * Np + kScBuffers * kScPad + tab) * real_bytes + (size_t)Np * sizeof(int) +
-           (size_t)(nwarps * kSampleBatch * 2 + nwarps) * sizeof(double);
+           (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 32 * sizeof(int);
 }
 
 }  // namespace dbsgym

@@ -243,6 +243,10 @@ class KuramotoEngine:
                                           1 if reset else 0))
         return {"accepted": a.value, "rejected": r.value, "rhs_evals": f.value, "status": st.value}
 
+    def step_variant(self, n_envs=None):
+        """Which step-kernel variant a launch over n_envs environments uses (dbsgym.h: dbsgym_step_variant)."""
+        return int(self.lib.dbsgym_step_variant(self._h, self.n_envs if n_envs is None else int(n_envs)))
+
     def set_timing(self, enabled=True):
         self._ck(self.lib.dbsgym_set_timing(self._h, 1 if enabled else 0))
 

@@ -102,3 +102,37 @@ def test_n8192_cluster_step_matches_oracle():
         np.testing.assert_allclose(lfp_t[e, :n], np.mean(np.cos(allrows), axis=1), rtol=0, atol=2e-6)
         np.testing.assert_allclose(lfp_r[e, :n], np.mean(np.cos(allrows) * d["rec"][e], axis=1), rtol=0, atol=2e-6)
     eng.close()
+
+
+@pytest.mark.parametrize("B", [5, 21])
+def test_multi_worker_kernel_equals_the_single_environment_kernel(monkeypatch, B):
+    """DBSGYM_MW=1 forces the multi-worker step kernel (8 environments per CTA sharing the precomputed sector
+    coefficients, persistent loop, named barriers) at a batch size where the default would use one CTA per
+    environment.  The contraction is the same sum in the same order; only the lane order of the warp reductions
+    (LFP samples, error norm) differs, so results agree to an ulp of float32 and the counters exactly -- for full
+    launches (partially filled CTAs, several environments per worker) and for a partial reset transient."""
+    acts = np.random.default_rng(2).uniform(-1, 1, (4, B)).astype(np.float32)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DBSGYM_MW", mode)
+        eng, d = _engine(512, 8, B)
+        eng.counters(reset=True)
+        out = []
+        for a in acts[:3]:
+            obs, rew, done = eng.step_host(a)
+            out.append((eng.state().copy(), obs.copy(), rew.copy(), eng.lfp()[0].copy(), eng.lfp()[1].copy(), eng.lfp()[2].copy()))
+        ids = [1, B - 2, 3]
+        eng.transient(np.arange(0.0, 130.0, 0.05), env_ids=ids)
+        out.append((eng.state().copy(), eng.obs_host().copy()))
+        obs, rew, done = eng.step_host(acts[3])
+        out.append((eng.state().copy(), obs.copy(), rew.copy()))
+        res[mode] = (out, eng.counters())
+        eng.close()
+    (a, ca), (b, cb) = res["0"], res["1"]
+    assert ca == cb and ca["status"] == 0 and ca["rejected"] > 0
+    for x, y in zip(a, b):
+        for u, v in zip(x, y):
+            if u.dtype.kind == "i":
+                assert np.array_equal(u, v)
+            else:
+                np.testing.assert_allclose(u, v, rtol=2e-6, atol=2e-6 if u.ndim == 2 and u.shape[1] == 512 else 3e-7)

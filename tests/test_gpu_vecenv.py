@@ -156,7 +156,15 @@ def test_full_size_batch_properties(precision):
     solo.set_env_params(None, w0=w0, stim=stim, rec=stim, y0=y0); solo.set_window(win)
     solo.set_episode(None, step_idx=0, episode_len=3)
     o1, r1, d1 = solo.step_host(acts)
-    assert np.array_equal(solo.state(), y[:kinds]) and np.array_equal(o1, obs[:kinds]) and np.array_equal(r1, rew[:kinds])
+    if precision == "f64":
+        assert np.array_equal(solo.state(), y[:kinds]) and np.array_equal(o1, obs[:kinds]) and np.array_equal(r1, rew[:kinds])
+    else:
+        # fp32: the 4096-batch runs the multi-worker kernel, the 8-batch one CTA per environment; the lane order of
+        # the warp reductions (LFP samples, error norm) differs between the two, everything else is the same sum
+        assert eng.step_variant() == 4 and solo.step_variant() == 3
+        np.testing.assert_allclose(solo.state(), y[:kinds], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(o1, obs[:kinds], rtol=0, atol=3e-7)
+        np.testing.assert_allclose(r1, rew[:kinds], rtol=2e-6)
     # done after episode_len steps
     assert not done.any()
     eng.step_host(tile(acts)); _, _, done = eng.step_host(tile(acts))
