@@ -759,7 +759,7 @@ int dbsgym_set_reward(DbsGymHandle* h, const DbsGymRewardSpec* spec, const doubl
     h->rspec = *spec;
     h->have_reward = true;
     const bool no_fuse = getenv("DBSGYM_NO_FUSED_OBS") != nullptr;     // A/B switch (read per call): separate observation kernel
-    h->fuse_tail = spec->kind != DBSGYM_REWARD_TEMP_CONST && h->nbins <= kTailBins && h->smax <= W && !no_fuse;
+    h->fuse_tail = spec->kind != DBSGYM_REWARD_TEMP_CONST && h->nbins <= kTailBins && h->smax <= 32 && h->smax <= W && !no_fuse;
     if (h->fuse_tail) {                              // the bins of whatever the rings hold now
         CU(h, launch_spec_init(h, nullptr, h->B, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));

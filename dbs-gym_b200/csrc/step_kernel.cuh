@@ -94,22 +94,8 @@ __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 
-// ---- Dormand-Prince 5(4) coefficients (same values as oracle/diffrax_restated.py) ----------
-__constant__ double c_A[7][8] = {
-    {0, 0, 0, 0, 0, 0, 0, 0},
-    {1.0 / 5, 0, 0, 0, 0, 0, 0, 0},
-    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0, 0, 0},
-    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0, 0, 0},
-    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0, 0, 0},
-    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0, 0, 0},
-    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84, 0, 0}};
-__constant__ double c_Berr[8] = {
-    35.0 / 384 - 1951.0 / 21600, 0, 500.0 / 1113 - 22642.0 / 50085, 125.0 / 192 - 451.0 / 720,
-    -2187.0 / 6784 + 12231.0 / 42400, 11.0 / 84 - 649.0 / 6300, -1.0 / 60, 0};
-__constant__ double c_Cmid[8] = {
-    0.5 * (6025192743.0 / 30085553152.0), 0, 0.5 * (51252292925.0 / 65400821598.0),
-    0.5 * (-2691868925.0 / 45128329728.0), 0.5 * (187940372067.0 / 1594534317056.0),
-    0.5 * (-1776094331.0 / 19743644256.0), 0.5 * (11237099.0 / 235043384.0), 0};
+// Dormand-Prince 5(4) coefficients (same values as oracle/diffrax_restated.py): compile-time lists in
+// stage_increment() (tableau rows a[s][.]) and at the error-estimate / dense-output sites (b_err, c_mid) below.
 
 constexpr double kTwoPi = 6.283185307179586476925286766559;
 
@@ -141,6 +127,49 @@ __device__ __forceinline__ void storev(real* __restrict__ p, const real* o) {
 
 __device__ __forceinline__ float  fma_r(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_r(double a, double b, double c) { return fma(a, b, c); }
+
+// sum_j coef[j] * K[slot[j]] over the thread's 8 oscillators with compile-time coefficient lists: all rows are loaded
+// first (independent LDS), then accumulated in ascending j -- the same FMA sequence as a rolled loop over the
+// tableau row, without its per-j constant-bank load, zero test, branch and exposed LDS latency.
+template <typename real, int NJ>
+__device__ __forceinline__ void lincomb(const real* __restrict__ Kb, int Nl, const int (&slot)[NJ], const double (&coef)[NJ],
+                                        real (&out)[kRows]) {
+    real kj[NJ][kRows];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) loadv<kRows>(Kb + slot[j] * Nl, kj[j]);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) out[r] = real(0);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const real a = real(coef[j]);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) out[r] = fma_r(a, kj[j][r], out[r]);
+    }
+}
+
+// stage increment sum_j a[s][j] k_{j+1} (k_{j+1} lives in slot j; row 6 skips the zero a[6][1])
+template <typename real>
+__device__ __forceinline__ void stage_increment(int s, const real* __restrict__ Kb, int Nl, real (&inc)[kRows]) {
+    switch (s) {
+        case 1: { constexpr int sl[] = {0}; constexpr double cf[] = {1.0 / 5}; lincomb<real, 1>(Kb, Nl, sl, cf, inc); break; }
+        case 2: { constexpr int sl[] = {0, 1}; constexpr double cf[] = {3.0 / 40, 9.0 / 40}; lincomb<real, 2>(Kb, Nl, sl, cf, inc); break; }
+        case 3: { constexpr int sl[] = {0, 1, 2}; constexpr double cf[] = {44.0 / 45, -56.0 / 15, 32.0 / 9};
+                  lincomb<real, 3>(Kb, Nl, sl, cf, inc); break; }
+        case 4: { constexpr int sl[] = {0, 1, 2, 3};
+                  constexpr double cf[] = {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729};
+                  lincomb<real, 4>(Kb, Nl, sl, cf, inc); break; }
+        case 5: { constexpr int sl[] = {0, 1, 2, 3, 4};
+                  constexpr double cf[] = {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656};
+                  lincomb<real, 5>(Kb, Nl, sl, cf, inc); break; }
+        case 6: { constexpr int sl[] = {0, 2, 3, 4, 5};
+                  constexpr double cf[] = {35.0 / 384, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
+                  lincomb<real, 5>(Kb, Nl, sl, cf, inc); break; }
+        default: {
+#pragma unroll
+            for (int r = 0; r < kRows; ++r) inc[r] = real(0);
+        }
+    }
+}
 
 // sin / cos of a phase.  fp64 follows the reference literally (theta = fmod(y, 2*pi),
 // env.py:253); fp32 phases are kept wrapped, so the library range reduction is exact enough.
@@ -259,6 +288,30 @@ __device__ __forceinline__ void quad_butterfly(real (&v)[kRows], real sx, real s
     for (int r = 0; r < kRows; ++r) { const real o = __shfl_xor_sync(mask, v[r], MX); v[r] = fma_r(sx, v[r], o); }
 #pragma unroll
     for (int r = 0; r < kRows; ++r) { const real o = __shfl_xor_sync(mask, v[r], MZ); v[r] = fma_r(sz, v[r], o); }
+}
+
+// the same butterfly on two arrays at once (sin and cos, or the two contraction results): for float the pair shares
+// one FFMA2 per stage and row -- the same two fmas, half the FMA-pipe issue slots
+template <typename real, int MX, int MZ>
+__device__ __forceinline__ void quad_butterfly2(real (&a)[kRows], real (&b)[kRows], real sx, real sz, unsigned mask) {
+    quad_butterfly<real, MX, MZ>(a, sx, sz, mask);
+    quad_butterfly<real, MX, MZ>(b, sx, sz, mask);
+}
+template <int MX, int MZ>
+__device__ __forceinline__ void quad_butterfly2f(float (&a)[kRows], float (&b)[kRows], float sx, float sz, unsigned mask) {
+    const float2 sx2 = make_float2(sx, sx), sz2 = make_float2(sz, sz);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        const float2 o = make_float2(__shfl_xor_sync(mask, a[r], MX), __shfl_xor_sync(mask, b[r], MX));
+        const float2 v = __ffma2_rn(sx2, make_float2(a[r], b[r]), o);
+        a[r] = v.x; b[r] = v.y;
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+        const float2 o = make_float2(__shfl_xor_sync(mask, a[r], MZ), __shfl_xor_sync(mask, b[r], MZ));
+        const float2 v = __ffma2_rn(sz2, make_float2(a[r], b[r]), o);
+        a[r] = v.x; b[r] = v.y;
+    }
 }
 
 template <typename real>
@@ -573,39 +626,47 @@ __device__ __forceinline__ float warp_sum(float v) {
 // S * nbins float64 FMAs per step instead of a W * nbins pass over the window, and no read of the window
 // at all.  The bins are (re)initialised from the whole ring by spec_init_kernel after a reset transient.
 template <typename real>
+__device__ __forceinline__ void obs_tail_prefetch(const StepParams& p, int env, int lane, int S, double* t_delta, int* t_pos) {
+    // ring positions of the step's samples and the values they overwrite, fetched at the START of the step so that
+    // the tail itself has no dependent global-load chain (S <= 32, checked by the host)
+    const int W = p.W;
+    const int head = p.head[env];
+    if (lane < S) {
+        int pos = head + lane;
+        if (pos >= W) pos -= W;
+        t_pos[lane] = pos;
+        t_delta[lane] = (double)(reinterpret_cast<const real*>(p.ring) + (size_t)env * W)[pos];
+    }
+    if (lane == 0) t_pos[32] = head;
+}
+
+template <typename real>
 __device__ __forceinline__ void obs_tail(const StepParams& p, int env, int lane, int S, double* t_delta, int* t_pos) {
     const int W = p.W, nb = p.tail_nbins;
     real* ring = reinterpret_cast<real*>(p.ring) + (size_t)env * W;
-    const int head = p.head[env];
+    const int head = t_pos[32];
     const double2* tw = reinterpret_cast<const double2*>(p.tw_full);
     double re = 0.0, im = 0.0;
-    for (int i0 = 0; i0 < S; i0 += 32) {
-        const int i = i0 + lane;
-        if (i < S) {
-            int pos = head + i;
-            if (pos >= W) pos -= W;
-            const real v = real(p.lfp_rec[(size_t)env * p.smax + i]);
-            const real old = ring[pos];
-            ring[pos] = v;
-            if (p.samples_f) p.samples_f[(size_t)env * p.smax + i] = (float)v;
-            if (p.mirror) {                           // zero-copy store into the pinned host mirror (both copies)
-                float* mr = p.mirror + (size_t)env * 2 * W;
-                mr[pos] = (float)v;
-                mr[pos + W] = (float)v;
-            }
-            t_delta[lane] = (double)v - (double)old;
-            t_pos[lane] = pos;
+    if (lane < S) {
+        const int pos = t_pos[lane];
+        const real v = real(p.lfp_rec[(size_t)env * p.smax + lane]);
+        ring[pos] = v;
+        if (p.samples_f) p.samples_f[(size_t)env * p.smax + lane] = (float)v;
+        if (p.mirror) {                               // zero-copy store into the pinned host mirror (both copies)
+            float* mr = p.mirror + (size_t)env * 2 * W;
+            mr[pos] = (float)v;
+            mr[pos + W] = (float)v;
         }
-        __syncwarp();
-        if (lane < nb) {
-            const int cnt = S - i0 < 32 ? S - i0 : 32;
-            for (int j = 0; j < cnt; ++j) {
-                const double2 w = tw[(size_t)t_pos[j] * nb + lane];
-                re = fma(t_delta[j], w.x, re);
-                im = fma(t_delta[j], w.y, im);
-            }
+        t_delta[lane] = (double)v - t_delta[lane];
+    }
+    __syncwarp();
+    if (lane < nb) {
+#pragma unroll 4
+        for (int j = 0; j < S; ++j) {
+            const double2 w = tw[(size_t)t_pos[j] * nb + lane];
+            re = fma(t_delta[j], w.x, re);
+            im = fma(t_delta[j], w.y, im);
         }
-        __syncwarp();
     }
     double pw = 0.0;
     if (lane < nb) {
@@ -656,7 +717,7 @@ constexpr int kScPad = 16;     // reals of padding per operand buffer (GRID_SYM 
 __host__ __device__ inline size_t step_smem_bytes_worker(int Np) {
     const int nwarps = kMwThreads / 32;
     return (size_t)(kSlots * Np + kScBuffers * (2 * Np + kScPad)) * sizeof(float) + (size_t)Np * sizeof(int) +
-           (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 32 * sizeof(int);
+           (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 36 * sizeof(int);
 }
 
 // GEO = 1: the grid extents are the compile-time constants 8 x 8 x 8 (every shipped config), which
@@ -812,6 +873,9 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
         seg_ts[1] = nullptr; seg_nts[1] = seg_nrec[1] = seg_from[1] = seg_out[1] = 0; seg_amp[1] = real(0);
     }
 
+    const bool tail = p.tail_on && p.mode == MODE_STEP && crank == 0 && warp == 0;
+    if (tail) obs_tail_prefetch<real>(p, env, lane, seg_nrec[0] + seg_nrec[1], t_delta, t_pos);
+
 #pragma unroll 1
     for (int sg = 0; sg < nseg; ++sg) {
         const double* __restrict__ ts = seg_ts[sg];
@@ -842,18 +906,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
 #pragma unroll 1
             for (int s = have_f0 ? 1 : 0; s < 7; ++s) {
                 real inc[kRows];
-#pragma unroll
-                for (int r = 0; r < kRows; ++r) inc[r] = real(0);
-#pragma unroll 1
-                for (int j = 0; j < s; ++j) {
-                    const real a = real(c_A[s][j]);
-                    if (a != real(0)) {
-                        real kj[kRows];
-                        loadv<kRows>(K + j * Nl + k0, kj);
-#pragma unroll
-                        for (int r = 0; r < kRows; ++r) inc[r] = fma_r(a, kj[r], inc[r]);
-                    }
-                }
+                stage_increment<real>(s, K + k0, Nl, inc);
                 real sv[kRows], cv[kRows];
                 {
 #pragma unroll
@@ -866,8 +919,10 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                         real ts_[kRows], tc_[kRows];
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) { ts_[r] = sv[r]; tc_[r] = cv[r]; }
-                        quad_butterfly<real, BMX, BMZ>(ts_, sgn_x, sgn_z, wmask);
-                        quad_butterfly<real, BMX, BMZ>(tc_, sgn_x, sgn_z, wmask);
+                        if constexpr (sizeof(real) == 4)
+                            quad_butterfly2f<BMX, BMZ>(reinterpret_cast<float(&)[kRows]>(ts_), reinterpret_cast<float(&)[kRows]>(tc_),
+                                                       (float)sgn_x, (float)sgn_z, wmask);
+                        else quad_butterfly2<real, BMX, BMZ>(ts_, tc_, sgn_x, sgn_z, wmask);
                         if (YPAR) {                              // y reflection: even / odd combinations of the line
 #pragma unroll
                             for (int r = 0; r < 4; ++r) {
@@ -914,8 +969,11 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                             t_ = ac[4 + r]; ac[4 + r] = ac[7 - r]; ac[7 - r] = t_;
                         }
                     }
-                    quad_butterfly<real, BMX, BMZ>(as, sgn_x, sgn_z, wmask);   // back to the grid lines (x 1/4 folded into kn)
-                    quad_butterfly<real, BMX, BMZ>(ac, sgn_x, sgn_z, wmask);
+                    // back to the grid lines (x 1/4 folded into kn)
+                    if constexpr (sizeof(real) == 4)
+                        quad_butterfly2f<BMX, BMZ>(reinterpret_cast<float(&)[kRows]>(as), reinterpret_cast<float(&)[kRows]>(ac),
+                                                   (float)sgn_x, (float)sgn_z, wmask);
+                    else quad_butterfly2<real, BMX, BMZ>(as, ac, sgn_x, sgn_z, wmask);
                 } else couple_grid<real>(SC + pbuf * scsz, T, GZ, GX, zi, xi, as, ac);
                 real ks[kRows];
 #pragma unroll
@@ -930,18 +988,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
             // d1 = y1 - y0 = dt * sum_j b_j k_j, recomputed here (bit-identical to the last stage's increment) so that
             // the stage loop body stays uniform and the compiler keeps ONE copy of the unrolled contraction
             {
-#pragma unroll
-                for (int r = 0; r < kRows; ++r) d1[r] = real(0);
-#pragma unroll 1
-                for (int j = 0; j < 6; ++j) {
-                    const real a = real(c_A[6][j]);
-                    if (a != real(0)) {
-                        real kj[kRows];
-                        loadv<kRows>(K + j * Nl + k0, kj);
-#pragma unroll
-                        for (int r = 0; r < kRows; ++r) d1[r] = fma_r(a, kj[r], d1[r]);
-                    }
-                }
+                stage_increment<real>(6, K + k0, Nl, d1);
 #pragma unroll
                 for (int r = 0; r < kRows; ++r) d1[r] *= dt;
             }
@@ -951,17 +998,11 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
             {
                 real sqr = real(0);               // 8 terms in the compute precision, then float64 across the CTA
                 real e[kRows];
-#pragma unroll
-                for (int r = 0; r < kRows; ++r) e[r] = real(0);
-#pragma unroll 1
-                for (int j = 0; j < 7; ++j) {
-                    const real b = real(c_Berr[j]);
-                    if (b != real(0)) {
-                        real kj[kRows];
-                        loadv<kRows>(K + kslot(j) * Nl + k0, kj);
-#pragma unroll
-                        for (int r = 0; r < kRows; ++r) e[r] = fma_r(b, kj[r], e[r]);
-                    }
+                {                                     // b_err[1] = 0; k7 lives in slot 1
+                    constexpr int sl[] = {0, 2, 3, 4, 5, 1};
+                    constexpr double cf[] = {35.0 / 384 - 1951.0 / 21600, 500.0 / 1113 - 22642.0 / 50085, 125.0 / 192 - 451.0 / 720,
+                                             -2187.0 / 6784 + 12231.0 / 42400, 11.0 / 84 - 649.0 / 6300, -1.0 / 60};
+                    lincomb<real, 6>(K + k0, Nl, sl, cf, e);
                 }
 #pragma unroll
                 for (int r = 0; r < kRows; ++r) {
@@ -1005,17 +1046,12 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                         real kk0[kRows], k6[kRows], dm[kRows];
                         loadv<kRows>(K + k0, kk0);
                         loadv<kRows>(K + kslot(6) * Nl + k0, k6);
-#pragma unroll
-                        for (int r = 0; r < kRows; ++r) dm[r] = real(0);
-#pragma unroll 1
-                        for (int j = 0; j < 7; ++j) {
-                            const real c = real(c_Cmid[j]);
-                            if (c != real(0)) {
-                                real kj[kRows];
-                                loadv<kRows>(K + kslot(j) * Nl + k0, kj);
-#pragma unroll
-                                for (int r = 0; r < kRows; ++r) dm[r] = fma_r(c, kj[r], dm[r]);
-                            }
+                        {                             // c_mid[1] = 0; k7 lives in slot 1
+                            constexpr int sl[] = {0, 2, 3, 4, 5, 1};
+                            constexpr double cf[] = {0.5 * (6025192743.0 / 30085553152.0), 0.5 * (51252292925.0 / 65400821598.0),
+                                                     0.5 * (-2691868925.0 / 45128329728.0), 0.5 * (187940372067.0 / 1594534317056.0),
+                                                     0.5 * (-1776094331.0 / 19743644256.0), 0.5 * (11237099.0 / 235043384.0)};
+                            lincomb<real, 6>(K + k0, Nl, sl, cf, dm);
                         }
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) {
@@ -1139,7 +1175,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
 #pragma unroll
         for (int r = 0; r < kRows; ++r) p.wind[base + i0 + r] = WD[k0 + r];
     }
-    if (p.tail_on && p.mode == MODE_STEP && crank == 0 && warp == 0)       // (the samples were written before the
+    if (tail)                                                              // (the samples were written before the
         obs_tail<real>(p, env, lane, seg_nrec[0] + seg_nrec[1], t_delta, t_pos);   //  last barrier of the solve loop)
     if (tid == 0 && crank == 0) {
         if (p.mode == MODE_TRANSIENT) p.head[env] = 0;
@@ -1158,13 +1194,13 @@ inline size_t step_smem_bytes_mw(int Np) { return kMwUFloat4 * sizeof(float4) + 
 inline size_t step_smem_bytes_cluster(int nthreads, size_t real_bytes) {
     const int nwarps = (nthreads + 31) / 32, Nl = nthreads * kRows;
     return (size_t)((kSlots + 1) * Nl) * real_bytes + (size_t)Nl * sizeof(int) +
-           (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 32 * sizeof(int);
+           (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 36 * sizeof(int);
 }
 
 inline size_t step_smem_bytes(int Np, int tab, int nthreads, size_t real_bytes) {
     const int nwarps = (nthreads + 31) / 32;
     return (size_t)((kSlots + 1 + 2 * kScBuffers) * Np + kScBuffers * kScPad + tab) * real_bytes + (size_t)Np * sizeof(int) +
-           (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 32 * sizeof(int);
+           (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 36 * sizeof(int);
 }
 
 }  // namespace dbsgym
