@@ -125,6 +125,25 @@ __device__ __forceinline__ void storev(real* __restrict__ p, const real* o) {
     for (int q = 0; q < CNT / n; ++q) reinterpret_cast<V*>(p)[q] = pack4(o + q * n);
 }
 
+// Thread-private rows of 8 reals in shared memory (stage derivatives K, winding counts).  Stored INTERLEAVED: the
+// q-th 16-byte piece of thread t sits at vector index q * nt + t, so that a warp's 128-bit access covers 512
+// contiguous bytes (4 wavefronts).  The natural layout (8 contiguous reals per thread, lane stride 32 B) costs 8
+// wavefronts per LDS.128 / STS.128 and 8 per scalar LDS: ncu showed 32 M bank-conflict wavefronts per launch.
+template <typename real>
+__device__ __forceinline__ void load_row(const real* __restrict__ row, int tid, int nt, real* o) {
+    using V = typename Vec<real>::T;
+    constexpr int n = Vec<real>::n;
+#pragma unroll
+    for (int q = 0; q < kRows / n; ++q) unpack(reinterpret_cast<const V*>(row)[q * nt + tid], o + q * n);
+}
+template <typename real>
+__device__ __forceinline__ void store_row(real* __restrict__ row, int tid, int nt, const real* o) {
+    using V = typename Vec<real>::T;
+    constexpr int n = Vec<real>::n;
+#pragma unroll
+    for (int q = 0; q < kRows / n; ++q) reinterpret_cast<V*>(row)[q * nt + tid] = pack4(o + q * n);
+}
+
 __device__ __forceinline__ float  fma_r(float a, float b, float c) { return fmaf(a, b, c); }
 __device__ __forceinline__ double fma_r(double a, double b, double c) { return fma(a, b, c); }
 
@@ -132,11 +151,11 @@ __device__ __forceinline__ double fma_r(double a, double b, double c) { return f
 // first (independent LDS), then accumulated in ascending j -- the same FMA sequence as a rolled loop over the
 // tableau row, without its per-j constant-bank load, zero test, branch and exposed LDS latency.
 template <typename real, int NJ>
-__device__ __forceinline__ void lincomb(const real* __restrict__ Kb, int Nl, const int (&slot)[NJ], const double (&coef)[NJ],
-                                        real (&out)[kRows]) {
+__device__ __forceinline__ void lincomb(const real* __restrict__ Kb, int Nl, int tid, int nt, const int (&slot)[NJ],
+                                        const double (&coef)[NJ], real (&out)[kRows]) {
     real kj[NJ][kRows];
 #pragma unroll
-    for (int j = 0; j < NJ; ++j) loadv<kRows>(Kb + slot[j] * Nl, kj[j]);
+    for (int j = 0; j < NJ; ++j) load_row<real>(Kb + slot[j] * Nl, tid, nt, kj[j]);
 #pragma unroll
     for (int r = 0; r < kRows; ++r) out[r] = real(0);
 #pragma unroll
@@ -149,21 +168,21 @@ __device__ __forceinline__ void lincomb(const real* __restrict__ Kb, int Nl, con
 
 // stage increment sum_j a[s][j] k_{j+1} (k_{j+1} lives in slot j; row 6 skips the zero a[6][1])
 template <typename real>
-__device__ __forceinline__ void stage_increment(int s, const real* __restrict__ Kb, int Nl, real (&inc)[kRows]) {
+__device__ __forceinline__ void stage_increment(int s, const real* __restrict__ Kb, int Nl, int tid, int nt, real (&inc)[kRows]) {
     switch (s) {
-        case 1: { constexpr int sl[] = {0}; constexpr double cf[] = {1.0 / 5}; lincomb<real, 1>(Kb, Nl, sl, cf, inc); break; }
-        case 2: { constexpr int sl[] = {0, 1}; constexpr double cf[] = {3.0 / 40, 9.0 / 40}; lincomb<real, 2>(Kb, Nl, sl, cf, inc); break; }
+        case 1: { constexpr int sl[] = {0}; constexpr double cf[] = {1.0 / 5}; lincomb<real, 1>(Kb, Nl, tid, nt, sl, cf, inc); break; }
+        case 2: { constexpr int sl[] = {0, 1}; constexpr double cf[] = {3.0 / 40, 9.0 / 40}; lincomb<real, 2>(Kb, Nl, tid, nt, sl, cf, inc); break; }
         case 3: { constexpr int sl[] = {0, 1, 2}; constexpr double cf[] = {44.0 / 45, -56.0 / 15, 32.0 / 9};
-                  lincomb<real, 3>(Kb, Nl, sl, cf, inc); break; }
+                  lincomb<real, 3>(Kb, Nl, tid, nt, sl, cf, inc); break; }
         case 4: { constexpr int sl[] = {0, 1, 2, 3};
                   constexpr double cf[] = {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729};
-                  lincomb<real, 4>(Kb, Nl, sl, cf, inc); break; }
+                  lincomb<real, 4>(Kb, Nl, tid, nt, sl, cf, inc); break; }
         case 5: { constexpr int sl[] = {0, 1, 2, 3, 4};
                   constexpr double cf[] = {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656};
-                  lincomb<real, 5>(Kb, Nl, sl, cf, inc); break; }
+                  lincomb<real, 5>(Kb, Nl, tid, nt, sl, cf, inc); break; }
         case 6: { constexpr int sl[] = {0, 2, 3, 4, 5};
                   constexpr double cf[] = {35.0 / 384, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84};
-                  lincomb<real, 5>(Kb, Nl, sl, cf, inc); break; }
+                  lincomb<real, 5>(Kb, Nl, tid, nt, sl, cf, inc); break; }
         default: {
 #pragma unroll
             for (int r = 0; r < kRows; ++r) inc[r] = real(0);
@@ -834,7 +853,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
         }
         if (!MW) storev<kRows>(RC + k0, rc);
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) WD[k0 + r] = sizeof(real) == 4 ? p.wind[base + i0 + r] : 0;
+        for (int r = 0; r < kRows; ++r) WD[r * nt + tid] = sizeof(real) == 4 ? p.wind[base + i0 + r] : 0;   // [r][thread]: conflict-free
     }
     env_sync();
 
@@ -906,7 +925,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
 #pragma unroll 1
             for (int s = have_f0 ? 1 : 0; s < 7; ++s) {
                 real inc[kRows];
-                stage_increment<real>(s, K + k0, Nl, inc);
+                stage_increment<real>(s, K, Nl, tid, nt, inc);
                 real sv[kRows], cv[kRows];
                 {
 #pragma unroll
@@ -979,7 +998,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
 #pragma unroll
                 for (int r = 0; r < kRows; ++r)
                     ks[r] = c0[r] + kn * (cv[r] * as[r] - sv[r] * ac[r]);
-                storev<kRows>(K + kslot(s) * Nl + k0, ks);
+                store_row<real>(K + kslot(s) * Nl, tid, nt, ks);
                 if (kScBuffers == 2 || CL) pbuf ^= 1;  // (the global operand of cluster mode is always double buffered)
                 else env_sync();                  // operand buffer is about to be overwritten by the next stage
                 ++n_rhs;
@@ -988,7 +1007,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
             // d1 = y1 - y0 = dt * sum_j b_j k_j, recomputed here (bit-identical to the last stage's increment) so that
             // the stage loop body stays uniform and the compiler keeps ONE copy of the unrolled contraction
             {
-                stage_increment<real>(6, K + k0, Nl, d1);
+                stage_increment<real>(6, K, Nl, tid, nt, d1);
 #pragma unroll
                 for (int r = 0; r < kRows; ++r) d1[r] *= dt;
             }
@@ -1002,12 +1021,12 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                     constexpr int sl[] = {0, 2, 3, 4, 5, 1};
                     constexpr double cf[] = {35.0 / 384 - 1951.0 / 21600, 500.0 / 1113 - 22642.0 / 50085, 125.0 / 192 - 451.0 / 720,
                                              -2187.0 / 6784 + 12231.0 / 42400, 11.0 / 84 - 649.0 / 6300, -1.0 / 60};
-                    lincomb<real, 6>(K + k0, Nl, sl, cf, e);
+                    lincomb<real, 6>(K, Nl, tid, nt, sl, cf, e);
                 }
 #pragma unroll
                 for (int r = 0; r < kRows; ++r) {
                     if (i0 + r < p.N) {
-                        const real yu0 = y0[r] + two_pi_r * real(WD[k0 + r]);
+                        const real yu0 = y0[r] + two_pi_r * real(WD[r * nt + tid]);
                         const real yu1 = yu0 + d1[r];
                         const real scale = atol + fmax(fabs(yu0), fabs(yu1)) * rtol;
                         const real q = (e[r] * dt) / scale;
@@ -1044,14 +1063,14 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                     real f0[kRows], pa[kRows], pb[kRows], pc[kRows];
                     {
                         real kk0[kRows], k6[kRows], dm[kRows];
-                        loadv<kRows>(K + k0, kk0);
-                        loadv<kRows>(K + kslot(6) * Nl + k0, k6);
+                        load_row<real>(K, tid, nt, kk0);
+                        load_row<real>(K + kslot(6) * Nl, tid, nt, k6);
                         {                             // c_mid[1] = 0; k7 lives in slot 1
                             constexpr int sl[] = {0, 2, 3, 4, 5, 1};
                             constexpr double cf[] = {0.5 * (6025192743.0 / 30085553152.0), 0.5 * (51252292925.0 / 65400821598.0),
                                                      0.5 * (-2691868925.0 / 45128329728.0), 0.5 * (187940372067.0 / 1594534317056.0),
                                                      0.5 * (-1776094331.0 / 19743644256.0), 0.5 * (11237099.0 / 235043384.0)};
-                            lincomb<real, 6>(K + k0, Nl, sl, cf, dm);
+                            lincomb<real, 6>(K, Nl, tid, nt, sl, cf, dm);
                         }
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) {
@@ -1139,8 +1158,8 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                 // ---- accept: y0 <- y1, FSAL k1 <- k7 ------------------------------------
                 {
                     real k6[kRows];
-                    loadv<kRows>(K + kslot(6) * Nl + k0, k6);
-                    storev<kRows>(K + k0, k6);
+                    load_row<real>(K + kslot(6) * Nl, tid, nt, k6);
+                    store_row<real>(K, tid, nt, k6);
                 }
 #pragma unroll
                 for (int r = 0; r < kRows; ++r) {
@@ -1152,7 +1171,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                             float yw = fmaf(-n, 6.2831854820251465f, (float)y1);
                             yw = fmaf(-n, -1.7484555314695172e-07f, yw);
                             y1 = real(yw);
-                            WD[k0 + r] += (int)n;
+                            WD[r * nt + tid] += (int)n;
                         }
                     }
                     y0[r] = y1;
@@ -1173,7 +1192,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     storev<kRows>(reinterpret_cast<real*>(p.phase) + base + i0, y0);
     if (sizeof(real) == 4) {
 #pragma unroll
-        for (int r = 0; r < kRows; ++r) p.wind[base + i0 + r] = WD[k0 + r];
+        for (int r = 0; r < kRows; ++r) p.wind[base + i0 + r] = WD[r * nt + tid];
     }
     if (tail)                                                              // (the samples were written before the
         obs_tail<real>(p, env, lane, seg_nrec[0] + seg_nrec[1], t_delta, t_pos);   //  last barrier of the solve loop)
