@@ -542,7 +542,11 @@ __device__ __forceinline__ void couple_grid_sym_fixed(const float* __restrict__ 
 // thread now loads its 8 coefficients directly (2 LDS.128, distinct per lane: 4 cycles each) and -- with the
 // lanes of a warp ordered sector-major (lane = 8 * sector + quad) -- the operand line with merged 2-cycle loads:
 // 16 cycles of shared memory and 21 cycles of FFMA2 / FADD per block (no coefficient combination either).
-constexpr int kMwEnvs = 8;                          // environments (workers) per CTA
+#ifndef DBSGYM_MW_ENVS
+#define DBSGYM_MW_ENVS 8
+#endif
+constexpr int kMwEnvs = DBSGYM_MW_ENVS;             // environments (workers) per CTA; more than 8 only fit with a
+                                                    // single-buffered operand (two barriers per RHS) and <= 96 registers
 constexpr int kMwThreads = 64;                      // threads per worker = grid lines of the 8 x 8 x 8 grid
 constexpr int kMwUFloat4 = 16 * 2 * kMwThreads;     // [block][half][worker thread] float4 entries of the coefficient table
 
@@ -729,13 +733,14 @@ enum { CPL_GRID = 0, CPL_DENSE = 1, CPL_GRID_SYM = 2 };
 #define DBSGYM_SC_BUFFERS 2
 #endif
 constexpr int kScBuffers = DBSGYM_SC_BUFFERS;   // 2: one barrier per RHS evaluation; 1: two barriers, 4 KB less shared memory
+constexpr int kMwScBuffers = kMwEnvs > 8 ? 1 : kScBuffers;
 constexpr int kScPad = 16;     // reals of padding per operand buffer (GRID_SYM staggers its 4 sectors by 16 B)
 
 // shared memory of one worker in multi-worker mode (fp32): K slots, double-buffered operand, winding counts,
 // reduction scratch, observation-tail scratch
 __host__ __device__ inline size_t step_smem_bytes_worker(int Np) {
     const int nwarps = kMwThreads / 32;
-    return (size_t)(kSlots * Np + kScBuffers * (2 * Np + kScPad)) * sizeof(float) + (size_t)Np * sizeof(int) +
+    return (size_t)(kSlots * Np + kMwScBuffers * (2 * Np + kScPad)) * sizeof(float) + (size_t)Np * sizeof(int) +
            (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 36 * sizeof(int);
 }
 
@@ -776,7 +781,8 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     unsigned char* wsm = smem_raw + (MW ? kMwUFloat4 * sizeof(float4) + (size_t)wid * step_smem_bytes_worker(Np) : 0);
     real* K = reinterpret_cast<real*>(wsm);               // [kSlots][Nl] stage derivatives f(y_s), thread-private slots
     real* SCs = K + kSlots * Nl;                          // [kScBuffers][scsz] (sin, cos) contraction operand (not in cluster mode)
-    real* Ts = SCs + (CL ? 0 : kScBuffers * scsz);        // [tab]
+    constexpr int SCB = MW ? kMwScBuffers : kScBuffers;   // operand buffers
+    real* Ts = SCs + (CL ? 0 : SCB * scsz);               // [tab]
     real* RC = Ts + tab;                                  // [Nl] recording conductance (thread-private slots; MW: read from global)
     int* WD = reinterpret_cast<int*>(RC + (MW ? 0 : Nl)); // [Nl] fp32 mode: winding counts, y = phase + 2*pi*wind
     double* part = reinterpret_cast<double*>(WD + Nl);    // [nwarps][kSampleBatch][2]
@@ -999,7 +1005,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                 for (int r = 0; r < kRows; ++r)
                     ks[r] = c0[r] + kn * (cv[r] * as[r] - sv[r] * ac[r]);
                 store_row<real>(K + kslot(s) * Nl, tid, nt, ks);
-                if (kScBuffers == 2 || CL) pbuf ^= 1;  // (the global operand of cluster mode is always double buffered)
+                if (SCB == 2 || CL) pbuf ^= 1;    // (the global operand of cluster mode is always double buffered)
                 else env_sync();                  // operand buffer is about to be overwritten by the next stage
                 ++n_rhs;
             }
