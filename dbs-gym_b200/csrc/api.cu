@@ -66,6 +66,9 @@ struct DbsGymHandle {
     float* mirror_host = nullptr;        // pinned + mapped [B][2W] window mirror (dbsgym_host_mirror)
     float* mirror_dev = nullptr;
     int32_t* pin_ints = nullptr;         // pinned landing buffer: n_samples[B], head[B]
+    // zero-copy control block of the host-mirror step (pinned + mapped): actions[B] f32 | reward[B] f32 |
+    // n_samples[B] i32 | head[B] i32 | done[B] u8 -- read / written by the step kernel itself through PCIe
+    unsigned char* ctl_host = nullptr; unsigned char* ctl_dev = nullptr;
     bool mirror_on = false;              // obs kernel writes the mirror (set while a mirror step / reset runs)
     uint8_t* st_done = nullptr;
     // timing
@@ -243,6 +246,7 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
     p.samples_f = nullptr; p.mirror = nullptr; p.reward_f = nullptr; p.reward = h->reward;
     p.done_out = nullptr; p.done_dev = h->done;
     p.step_idx_rw = h->step_idx; p.episode_len = h->episode_len;
+    p.nsamp_out = nullptr; p.head_out = nullptr;
     p.power_scale = h->rspec.power_scale; p.action_cost = h->rspec.action_cost;
     p.threshold = h->rspec.threshold; p.threshold_penalty = h->rspec.threshold_penalty;
 }
@@ -400,9 +404,10 @@ cudaStream_t pick_stream(DbsGymHandle* h, void* stream) {
 }
 
 int step_impl(DbsGymHandle* h, const float* actions_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
-              cudaStream_t s, float* samples_dev = nullptr) {
+              cudaStream_t s, float* samples_dev = nullptr, int32_t* nsamp_out = nullptr, int32_t* head_out = nullptr) {
     StepParams p;
     fill_params(h, p);
+    p.nsamp_out = nsamp_out; p.head_out = head_out;
     p.mode = MODE_STEP; p.actions = actions_dev; p.n_launch = h->B;
     if (h->fuse_tail) {
         // ring append, host mirror, beta-power reward and episode bookkeeping happen in the step kernel's tail;
@@ -576,6 +581,7 @@ void dbsgym_destroy(DbsGymHandle* h) {
         if (b) cudaFree(b);
     if (h->pin_ints) cudaFreeHost(h->pin_ints);
     if (h->mirror_host) cudaFreeHost(h->mirror_host);
+    if (h->ctl_host) cudaFreeHost(h->ctl_host);
     for (int i = 0; i < 3; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -892,18 +898,40 @@ int dbsgym_step_host_mirror(DbsGymHandle* h, const float* actions, int32_t* pos,
     CU(h, cudaSetDevice(h->cfg.device));
     cudaStream_t s = h->stream;
     h->mirror_on = true;
-    CU(h, cudaMemcpyAsync(h->st_actions, actions, (size_t)B * 4, cudaMemcpyHostToDevice, s));
-    rc = step_impl(h, h->st_actions, nullptr, h->st_reward, h->st_done, s, nullptr);
-    if (rc) return rc;
-    CU(h, cudaMemcpyAsync(h->pin_ints, h->n_samples, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    CU(h, cudaMemcpyAsync(h->pin_ints + B, h->head, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    if (reward) CU(h, cudaMemcpyAsync(reward, h->st_reward, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    if (done) CU(h, cudaMemcpyAsync(done, h->st_done, (size_t)B, cudaMemcpyDeviceToHost, s));
-    CU(h, cudaStreamSynchronize(s));
-    const int n = h->pin_ints[0], hd = h->pin_ints[B];
+    const int32_t *ns = nullptr, *hd = nullptr;
+    if (h->fuse_tail) {
+        // zero-copy control block: the kernel reads the actions from, and its tail writes reward / done / n_samples /
+        // ring head to, pinned mapped host memory -- no memcpy nodes on the stream, one launch and one sync per step
+        if (!h->ctl_host) {
+            CU(h, cudaHostAlloc(reinterpret_cast<void**>(&h->ctl_host), (size_t)B * 17 + 64, cudaHostAllocMapped | cudaHostAllocPortable));
+            CU(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->ctl_dev), h->ctl_host, 0));
+        }
+        auto at = [&](unsigned char* base, int k) { return base + (size_t)k * B * 4; };
+        memcpy(at(h->ctl_host, 0), actions, (size_t)B * 4);
+        rc = step_impl(h, reinterpret_cast<const float*>(at(h->ctl_dev, 0)), nullptr, reinterpret_cast<float*>(at(h->ctl_dev, 1)),
+                       at(h->ctl_dev, 4), s, nullptr, reinterpret_cast<int32_t*>(at(h->ctl_dev, 2)),
+                       reinterpret_cast<int32_t*>(at(h->ctl_dev, 3)));
+        if (rc) return rc;
+        CU(h, cudaStreamSynchronize(s));
+        if (reward) memcpy(reward, at(h->ctl_host, 1), (size_t)B * 4);
+        if (done) memcpy(done, at(h->ctl_host, 4), (size_t)B);
+        ns = reinterpret_cast<const int32_t*>(at(h->ctl_host, 2));
+        hd = reinterpret_cast<const int32_t*>(at(h->ctl_host, 3));
+    } else {
+        CU(h, cudaMemcpyAsync(h->st_actions, actions, (size_t)B * 4, cudaMemcpyHostToDevice, s));
+        rc = step_impl(h, h->st_actions, nullptr, h->st_reward, h->st_done, s, nullptr);
+        if (rc) return rc;
+        CU(h, cudaMemcpyAsync(h->pin_ints, h->n_samples, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaMemcpyAsync(h->pin_ints + B, h->head, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+        if (reward) CU(h, cudaMemcpyAsync(reward, h->st_reward, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+        if (done) CU(h, cudaMemcpyAsync(done, h->st_done, (size_t)B, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaStreamSynchronize(s));
+        ns = h->pin_ints; hd = h->pin_ints + B;
+    }
+    const int n = ns[0], hd0 = hd[0];
     bool uniform = true;
-    for (int b = 1; b < B && uniform; ++b) uniform = h->pin_ints[b] == n && h->pin_ints[B + b] == hd;
-    *pos = hd;
+    for (int b = 1; b < B && uniform; ++b) uniform = ns[b] == n && hd[b] == hd0;
+    *pos = hd0;
     *n_new = uniform ? n : -1;
     return DBSGYM_OK;
 }

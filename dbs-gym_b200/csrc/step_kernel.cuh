@@ -77,6 +77,7 @@ struct StepParams {
     const double* tw_full;         // [W][nbins][2] cos, sin of 2*pi*k*m/W
     float* samples_f; float* mirror; float* reward_f; double* reward; uint8_t* done_out; uint8_t* done_dev;
     int32_t* step_idx_rw; const int32_t* episode_len;
+    int32_t* nsamp_out; int32_t* head_out;      // optional copies of n_samples / the new ring head (mapped host memory)
     double power_scale, action_cost, threshold, threshold_penalty;
     // cluster mode (one environment = a thread-block cluster of `cluster` CTAs, N > 4096)
     int cluster;                   // CTAs per environment (1 = plain)
@@ -716,6 +717,8 @@ __device__ __forceinline__ void obs_tail(const StepParams& p, int env, int lane,
         int nh = head + S;
         if (nh >= W) nh -= W;
         p.head[env] = nh;
+        if (p.nsamp_out) p.nsamp_out[env] = S;
+        if (p.head_out) p.head_out[env] = nh;
     }
 }
 

@@ -20,6 +20,14 @@ print("ms per VecEnv.step:", (time.perf_counter() - t0) * 10)
 core = venv.core
 t0 = time.perf_counter()
 for i in range(100):
+    core.engine.step_host_mirror(core.act_buf, core.rew_buf, core.done_buf)
+print("ms per raw dbsgym_step_host_mirror:", (time.perf_counter() - t0) * 10)
+core.engine.set_timing(True)
+core.engine.step_host_mirror(core.act_buf, core.rew_buf, core.done_buf)
+print("kernel ms (step, obs):", core.engine.last_step_ms())
+core.engine.set_timing(False)
+t0 = time.perf_counter()
+for i in range(100):
     core.engine.step_host_samples(core.act_buf, core.samples_buf, core.nsamp_buf, core.rew_buf, core.done_buf)
 print("ms per raw dbsgym_step_host_samples:", (time.perf_counter() - t0) * 10)
 pr = cProfile.Profile(); pr.enable()
