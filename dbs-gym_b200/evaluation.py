@@ -15,10 +15,21 @@ from .utils import band_pass_envelope
 
 
 def calc_psd_for_simple_eval(sig_envs, psd_dt, beta_a=12.5, beta_b=21):
-    """evaluate_HF_DBS.py:122-135, vectorised over the environments axis."""
-    from scipy.signal import filtfilt
+    """evaluate_HF_DBS.py:122-135 for every row of ``sig_envs``.  Rows of equal length (a 2-D array: the batched
+    case, environments in lockstep) go through ONE filtfilt / rfft / filtfilt along the last axis -- scipy's
+    filters act on each row exactly as on a 1-D signal; ragged inputs fall back to the row loop."""
+    from scipy.signal import butter, filtfilt
+    if isinstance(sig_envs, np.ndarray) and sig_envs.ndim == 2:
+        nyq = 0.5 / psd_dt
+        b, a = butter(2, [12 / nyq, 30 / nyq], btype="band")       # band_pass_envelope(..., order=2), utils.py:794-816
+        filt = filtfilt(b, a, sig_envs, axis=-1)
+        ft = np.abs(np.fft.rfft(filt, axis=-1) / filt.shape[-1]) ** 2 * 2
+        freq = np.fft.rfftfreq(filt.shape[-1], psd_dt)
+        ft = filtfilt([1] * 12, 5, ft, axis=-1)
+        return np.sum(ft[:, (freq > beta_a) & (freq < beta_b)], axis=1)
     out = []
-    for sig in np.atleast_2d(sig_envs):
+    for sig in sig_envs:
+        sig = np.asarray(sig)
         filt, _ = band_pass_envelope(sig, 1 / psd_dt, order=2)
         ft = np.abs(np.fft.rfft(filt) / filt.shape[0]) ** 2 * 2
         freq = np.fft.rfftfreq(filt.shape[0], psd_dt)
@@ -35,7 +46,10 @@ def evaluate_batched(model, venv, n_steps=None, deterministic=True):
     if n_steps is None:
         n_steps = int(min(h.total_episode_counts for h in core.hosts))
     obs = venv.reset()
-    lfp = [[] for _ in range(B)]
+    smax = core.engine.max_step_samples
+    trace = np.empty((B, n_steps * smax))           # TRUE LFP of every environment, concatenated over the steps
+    fill = np.zeros(B, dtype=np.int64)
+    rows = np.arange(B)[:, None]
     energy = np.zeros(B)
     ret = np.zeros(B)
     state, starts = None, np.ones(B, dtype=bool)
@@ -45,13 +59,26 @@ def evaluate_batched(model, venv, n_steps=None, deterministic=True):
         act = np.broadcast_to(act.reshape(-1, 1) if act.size == B else act.reshape(1, 1), (B, 1))
         obs, rew, done, infos = venv.step(act)
         t, _, n = core.engine.lfp()
-        for i in range(B):
-            lfp[i].append(t[i, :n[i]].copy())
+        if np.all(n == n[0]):                        # lockstep: one block copy
+            k = int(n[0])
+            if np.all(fill == fill[0]):
+                trace[:, fill[0]:fill[0] + k] = t[:, :k]
+            else:
+                trace[rows, fill[:, None] + np.arange(k)[None, :]] = t[:, :k]
+            fill += k
+        else:
+            for i in range(B):
+                trace[i, fill[i]:fill[i] + n[i]] = t[i, :n[i]]
+            fill += n
         energy += np.abs(act[:, 0])
         ret += rew
         starts = done
-    sig = [np.concatenate(x) for x in lfp]
-    bb = np.array([calc_psd_for_simple_eval(s[None, :], psd_dt=0.0005)[0] for s in sig])
+    if np.all(fill == fill[0]):
+        sig = trace[:, :fill[0]]
+        bb = calc_psd_for_simple_eval(sig, psd_dt=0.0005)
+    else:
+        sig = [trace[i, :fill[i]] for i in range(B)]
+        bb = calc_psd_for_simple_eval(sig, psd_dt=0.0005)
     sd = (lambda v: float(np.std(v, ddof=1)) if len(v) > 1 else 0.0)
     return {"bbpow": bb, "energy": energy, "episode_return": ret, "true_lfp": sig,
             "summary": {"bbpow_mean": float(bb.mean()), "bbpow_sd": sd(bb), "energy_mean": float(energy.mean()),

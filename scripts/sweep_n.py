@@ -1,13 +1,22 @@
 #!/usr/bin/env python
 """Oscillator-count sweep (BASELINE configs[4]) on the resident-state GRID kernel: 8 x 8 x gz grids
 (lines of 8 along y, gz z-planes), N = 64*gz, holding B*N = 2 097 152.  cos coupling, K/N scaling as in
-env.py:264.  Engine-level (device-resident) timing, one GPU.  N <= 4096: one CTA per environment; N >= 8192:
-one thread-block cluster of N / 4096 CTAs per environment (cluster mode of the step kernel)."""
+env.py:264.  Engine-level (device-resident) timing.  N <= 4096: one CTA (N = 512: one worker) per environment;
+N >= 8192: one thread-block cluster of N / 4096 CTAs per environment (cluster mode of the step kernel).
+One GPU, or under torchrun one process per GPU (weak scaling: every rank runs the same B environments per N, the
+per-N kernel time is the MAX over ranks, the reported rates are the whole job's):
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29519 scripts/sweep_n.py"""
 import json, os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
+import torch.distributed as dist
+RANK, WORLD, LOCAL = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+torch.cuda.set_device(LOCAL)
+if WORLD > 1:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
 from dbsgym_b200.engine import KuramotoEngine
 from dbsgym_b200.geometry import coupling_table, neuron_grid, ElectrodeModel
 from dbsgym_b200.schedule import StepSchedule, transient_grid
@@ -19,11 +28,11 @@ for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024):
     coords, grid = neuron_grid(8, 8, gz, N, 0.1)
     table = coupling_table(coords, grid, [8, 8, gz], "cos")
     assert table is not None
-    eng = KuramotoEngine(B, N, [8, 8, gz], 2340, 0.52, precision="f32", coupling_table=table)
+    eng = KuramotoEngine(B, N, [8, 8, gz], 2340, 0.52, precision="f32", coupling_table=table, device=LOCAL)
     tt = transient_grid(200.0, 0.05)
     sched = StepSchedule(400, tt[-1], 0.15, 0.75, 0.05)
     eng.set_schedule(sched); eng.set_reward("bbpow_action", 0.05)
-    rng = np.random.default_rng(gz)
+    rng = np.random.default_rng(gz + 1000 * RANK)
     # env.py:94's contact-index formula assumes a cubic grid; for the elongated sweep grids the contact is
     # simply the neuron nearest to the grid centre, with the reference's conductance law max(0, 1 - 0.1 d)
     from dbsgym_b200.geometry import distances_from
@@ -34,7 +43,7 @@ for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024):
     eng.set_env_params(None, w0=w0, stim=stim, rec=stim, y0=y0)
     eng.set_episode(None, step_idx=0, episode_len=2 ** 30)
     t0 = time.perf_counter(); eng.transient(tt); torch.cuda.synchronize(); t_tr = time.perf_counter() - t0
-    dev = torch.device("cuda", 0)
+    dev = torch.device("cuda", LOCAL)
     act = torch.from_numpy(rng.uniform(-1, 1, (40, B)).astype(np.float32)).to(dev)
     obs = torch.empty((B, 2340), dtype=torch.float32, device=dev)
     rew = torch.empty(B, dtype=torch.float32, device=dev); done = torch.empty(B, dtype=torch.uint8, device=dev)
@@ -50,13 +59,20 @@ for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024):
         torch.cuda.synchronize(); ms.append(eng.last_step_ms())
     c = eng.counters()
     k_step, k_obs = np.mean([m[0] for m in ms]), np.mean([m[1] for m in ms])
+    if WORLD > 1:                                    # slowest rank
+        tmax = torch.tensor([k_step, k_obs], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        k_step, k_obs = (float(v) for v in tmax.cpu())
     rhs = c["rhs_evals"] / (n_timed * B)
     ypar = bool(eng.lib.dbsgym_build_flags() & 1)          # own op count of the sector contraction, see bench.py
-    SYM_FLOP, SYM_LIN = ((196 if ypar else 304) / 256.0), ((160 if ypar else 128) / 8.0)
-    out.append({"N": N, "grid": [8, 8, gz], "envs": B, "step_kernel_ms": float(k_step), "obs_kernel_ms": float(k_obs),
-                "env_steps_per_s": B / ((k_step + k_obs) * 1e-3), "oscillator_updates_per_s": B * N * (c["accepted"] + c["rejected"]) / (n_timed * B) / ((k_step + k_obs) * 1e-3),
-                "rhs_per_env_step": rhs, "executed_tflops": rhs * (SYM_FLOP * N * N + SYM_LIN * N) * B / (k_step * 1e-3) / 1e12,
-                "dense_equivalent_tflops": rhs * 4 * N * N * B / (k_step * 1e-3) / 1e12,
+    SYM_FLOP, SYM_LIN = ((148 if eng.step_variant(B) == 4 else 196 if ypar else 304) / 256.0), ((160 if ypar else 128) / 8.0)
+    out.append({"N": N, "grid": [8, 8, gz], "n_gpus": WORLD, "envs_per_gpu": B, "envs": B * WORLD, "step_kernel_ms": float(k_step), "obs_kernel_ms": float(k_obs),
+                "env_steps_per_s": WORLD * B / ((k_step + k_obs) * 1e-3), "oscillator_updates_per_s": WORLD * B * N * (c["accepted"] + c["rejected"]) / (n_timed * B) / ((k_step + k_obs) * 1e-3),
+                "rhs_per_env_step": rhs, "executed_tflops": WORLD * rhs * (SYM_FLOP * N * N + SYM_LIN * N) * B / (k_step * 1e-3) / 1e12,
+                "dense_equivalent_tflops": WORLD * rhs * 4 * N * N * B / (k_step * 1e-3) / 1e12,
                 "transient_s": t_tr, "status": c["status"], "ctas_per_env": max(1, N // 4096)})
-    print(json.dumps(out[-1]), flush=True)
+    if RANK == 0:
+        print(json.dumps(out[-1]), flush=True)
     eng.close()
+if WORLD > 1:
+    dist.destroy_process_group()

@@ -204,3 +204,23 @@ def test_batched_fast_reset_draws_like_the_sequential_loop():
             assert np.array_equal(a.stim, b.stim) and np.array_equal(a.rec, b.rec)
             assert hs.reset_count == hf.reset_count and hs.elec_coords == hf.elec_coords
             assert hs.spatial_var_episode == hf.spatial_var_episode
+
+
+def test_batched_eval_metric_equals_row_by_row_reference_formula():
+    """calc_psd_for_simple_eval (aDBS_RL/evaluate_HF_DBS.py:122-135): the batched 2-D path (one filtfilt / rfft /
+    filtfilt along the last axis) gives the same beta-band power as the reference's per-signal loop."""
+    from scipy.signal import butter, filtfilt
+    from dbsgym_b200.evaluation import calc_psd_for_simple_eval
+    rng = np.random.default_rng(5)
+    t = np.arange(19998) * 0.0005
+    x = 0.05 * rng.normal(size=(6, t.size)).cumsum(axis=1) / 30 + 0.1 * np.sin(2 * np.pi * 17.0 * t)[None, :] * rng.uniform(0.5, 1.5, (6, 1))
+    ref = []
+    for sig in x:                                    # the reference's loop, written out
+        b, a = butter(2, [12 / 1000.0, 30 / 1000.0], btype="band")
+        f = filtfilt(b, a, sig)
+        ft = np.abs(np.fft.rfft(f) / f.shape[0]) ** 2 * 2
+        freq = np.fft.rfftfreq(f.shape[0], 0.0005)
+        ft = filtfilt([1] * 12, 5, ft)
+        ref.append(np.sum(ft[np.where((freq > 12.5) & (freq < 21))]))
+    np.testing.assert_allclose(calc_psd_for_simple_eval(x, 0.0005), ref, rtol=1e-12)
+    np.testing.assert_allclose(calc_psd_for_simple_eval([r for r in x], 0.0005), ref, rtol=1e-12)
