@@ -1097,7 +1097,10 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                             if (idx >= rec_from && idx < n_rec) {
                                 const double tsv = ts[idx];
                                 const bool at_end = (tsv == tnext);
-                                const real tau = (tnext == t) ? real(0) : real((tsv - t) / (tnext - t));
+                                // fp32: the quotient of the (exact, float64) differences in single precision -- a float64
+                                // division per sample and thread costs ~40 instructions for one ulp of tau
+                                const real tau = (tnext == t) ? real(0)
+                                               : (sizeof(real) == 4 ? real((float)(tsv - t) / (float)(tnext - t)) : real((tsv - t) / (tnext - t)));
                                 real st = real(0), sr = real(0);
                                 real rc[kRows];
                                 if (!MW) loadv<kRows>(RC + k0, rc);

@@ -82,6 +82,17 @@ class SpatialKuramoto(GymEnv):
     def current_step(self):
         return int(self._core.current_step[0])
 
+    def __getattr__(self, name):
+        # reference attributes that are pure host bookkeeping (reset_count, elec_drift_episode, elec_encaps_episode,
+        # plasticity_episode, spatial_var_episode, w0_without_locus, ...; env.py:339-386, :483-557) live on the
+        # HostEnvState; only reached when normal lookup fails
+        if name.startswith("__") or name in ("_host", "_core"):
+            raise AttributeError(name)
+        host = self.__dict__.get("_host")
+        if host is not None and hasattr(host, name):
+            return getattr(host, name)
+        raise AttributeError(f"'SpatialKuramoto' object has no attribute '{name}'")
+
     @property
     def current_time(self):
         return self._core.current_time(0)

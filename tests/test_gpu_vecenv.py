@@ -238,3 +238,28 @@ def test_torch_policy_rollout_example_runs():
                           "--steps", "4", "--cfg", "env0"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "env-steps/s" in out.stdout
+
+
+def test_env2_drift_resets_match_reference_golden():
+    """env2 (temporal drift: electrode movement, encapsulation, plasticity-walk regeneration, spatial re-draw) through
+    the GPU-backed SpatialKuramoto: 14 resets against the fixture the REFERENCE's own env.py produced
+    (tests/golden/make_golden.py:record_env2_events; env.py:483-557 + the transient of env.py:605-612)."""
+    from environment.env import SpatialKuramoto
+    g = load_golden("env2_events.npz")
+    d = make_params("env2", 21, plasticity_drift_freq=10 ** 6, transient_state_len=117.5,
+                    total_episode_len=9., spatial_var_freq=4, precision="f64")
+    assert np.array_equal(d["w0"], g["in_w0"])
+    env = SpatialKuramoto(d)
+    for r in range(len(g["elec"])):
+        if r > 0:
+            obs, info = env.reset()
+            assert obs.shape == (1, 2340) and info == {}
+        assert np.array_equal(np.array(env.elec_coords)[0], g["elec"][r]), r
+        assert np.array_equal(np.array(env.rec_coords)[0], g["rec"][r]), r
+        assert env.encapsulation_coeff == g["encaps"][r]
+        assert np.array_equal(env.kuramoto.w0, g["w0"][r])
+        assert np.array_equal(env.init_state, g["init_state"][r])
+        np.testing.assert_allclose(env.theta_state[0][:8], g["window_head"][r], rtol=0, atol=1e-9)
+        assert env.elec_drift_episode == g["elec_drift_episode"][r]
+        assert env.elec_encaps_episode == g["encaps_episode"][r]
+    env.close()
