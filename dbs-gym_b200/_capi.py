@@ -29,6 +29,7 @@ EXPORTS = [
     "dbsgym_get_lfp", "dbsgym_get_rewards", "dbsgym_get_state", "dbsgym_get_window",
     "dbsgym_set_window", "dbsgym_get_episode", "dbsgym_counters", "dbsgym_last_step_ms",
     "dbsgym_set_timing", "dbsgym_measure_fp32_peak", "dbsgym_measure_fp32_peak_mode",
+    "dbsgym_trace_begin", "dbsgym_trace_end", "dbsgym_trace_get", "dbsgym_eval_bbpow",
 ]
 
 
@@ -51,12 +52,19 @@ class DbsGymRewardSpec(C.Structure):
     ]
 
 
+class DbsGymEvalSpec(C.Structure):
+    _fields_ = [
+        ("struct_bytes", C.c_uint32), ("padlen", C.c_int32), ("b", C.c_double * 5), ("a", C.c_double * 5),
+        ("zi", C.c_double * 4), ("k_lo", C.c_int32), ("n_k", C.c_int32),
+    ]
+
+
 class DbsGymError(RuntimeError):
     pass
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in ("api.cu", "step_kernel.cuh", "obs_kernel.cuh")] + [HEADER]
+    return [os.path.join(CSRC, f) for f in ("api.cu", "step_kernel.cuh", "obs_kernel.cuh", "eval_kernel.cuh")] + [HEADER]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -127,6 +135,10 @@ def load():
         "dbsgym_counters": (C.c_int, [vp, u64p, u64p, u64p, i32p, C.c_int32]),
         "dbsgym_last_step_ms": (C.c_int, [vp, f32p]),
         "dbsgym_set_timing": (C.c_int, [vp, C.c_int32]),
+        "dbsgym_trace_begin": (C.c_int, [vp, C.c_int32]),
+        "dbsgym_trace_end": (C.c_int, [vp]),
+        "dbsgym_trace_get": (C.c_int, [vp, vp, vp]),
+        "dbsgym_eval_bbpow": (C.c_int, [vp, C.POINTER(DbsGymEvalSpec), vp, vp]),
         "dbsgym_measure_fp32_peak": (C.c_int, [C.c_int32, C.c_double, f64p]),
         "dbsgym_measure_fp32_peak_mode": (C.c_int, [C.c_int32, C.c_double, C.c_int32, f64p]),
     }

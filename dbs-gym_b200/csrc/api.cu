@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../include/dbsgym.h"
+#include "eval_kernel.cuh"
 #include "obs_kernel.cuh"
 #include "step_kernel.cuh"
 
@@ -69,6 +70,8 @@ struct DbsGymHandle {
     // zero-copy control block of the host-mirror step (pinned + mapped): actions[B] f32 | reward[B] f32 |
     // n_samples[B] i32 | head[B] i32 | done[B] u8 -- read / written by the step kernel itself through PCIe
     unsigned char* ctl_host = nullptr; unsigned char* ctl_dev = nullptr;
+    // evaluation trace (dbsgym_trace_begin): TRUE LFP of every step, [B][trace_cap] float64
+    double* trace = nullptr; int32_t* trace_len = nullptr; int trace_cap = 0; bool trace_on = false;
     bool mirror_on = false;              // obs kernel writes the mirror (set while a mirror step / reset runs)
     uint8_t* st_done = nullptr;
     // timing
@@ -247,6 +250,7 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
     p.done_out = nullptr; p.done_dev = h->done;
     p.step_idx_rw = h->step_idx; p.episode_len = h->episode_len;
     p.nsamp_out = nullptr; p.head_out = nullptr;
+    p.trace = nullptr; p.trace_len = nullptr; p.trace_cap = 0;
     p.power_scale = h->rspec.power_scale; p.action_cost = h->rspec.action_cost;
     p.threshold = h->rspec.threshold; p.threshold_penalty = h->rspec.threshold_penalty;
 }
@@ -415,6 +419,7 @@ int step_impl(DbsGymHandle* h, const float* actions_dev, float* obs_dev, float* 
         p.tail_on = 1;
         p.samples_f = samples_dev; p.mirror = h->mirror_on ? h->mirror_dev : nullptr;
         p.reward_f = reward_dev; p.done_out = done_dev;
+        if (h->trace_on) { p.trace = h->trace; p.trace_len = h->trace_len; p.trace_cap = h->trace_cap; }
     }
     if (h->timing) CU(h, cudaEventRecord(h->ev[0], s));
     CU(h, launch_step(h, p, s));
@@ -582,6 +587,8 @@ void dbsgym_destroy(DbsGymHandle* h) {
     if (h->pin_ints) cudaFreeHost(h->pin_ints);
     if (h->mirror_host) cudaFreeHost(h->mirror_host);
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
+    if (h->trace) cudaFree(h->trace);
+    if (h->trace_len) cudaFree(h->trace_len);
     for (int i = 0; i < 3; ++i)
         if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1086,6 +1093,78 @@ int dbsgym_last_step_ms(DbsGymHandle* h, float* ms2) {
     CU(h, cudaEventSynchronize(h->ev[2]));
     CU(h, cudaEventElapsedTime(&ms2[0], h->ev[0], h->ev[1]));
     CU(h, cudaEventElapsedTime(&ms2[1], h->ev[1], h->ev[2]));
+    return DBSGYM_OK;
+}
+
+int dbsgym_trace_begin(DbsGymHandle* h, int32_t capacity) {
+    if (!h) return DBSGYM_EINVAL;
+    if (capacity <= 0) return fail(h, DBSGYM_EINVAL, "trace capacity must be positive");
+    if (!h->fuse_tail) return fail(h, DBSGYM_ESTATE, "the evaluation trace needs a beta-power reward (fused observation tail)");
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (capacity > h->trace_cap) {
+        if (h->trace) cudaFree(h->trace);
+        h->trace = nullptr; h->trace_cap = 0;
+        CU(h, cudaMalloc(&h->trace, (size_t)h->B * capacity * sizeof(double)));
+        h->trace_cap = capacity;
+    }
+    if (!h->trace_len) CU(h, cudaMalloc(&h->trace_len, (size_t)h->B * 4));
+    CU(h, cudaMemset(h->trace_len, 0, (size_t)h->B * 4));
+    h->trace_on = true;
+    return DBSGYM_OK;
+}
+
+int dbsgym_trace_end(DbsGymHandle* h) {
+    if (!h) return DBSGYM_EINVAL;
+    h->trace_on = false;
+    return DBSGYM_OK;
+}
+
+int dbsgym_trace_get(DbsGymHandle* h, double* trace, int32_t* len) {
+    if (!h) return DBSGYM_EINVAL;
+    if (!h->trace) return fail(h, DBSGYM_ESTATE, "no trace recorded (dbsgym_trace_begin)");
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaDeviceSynchronize());
+    if (trace) CU(h, cudaMemcpy(trace, h->trace, (size_t)h->B * h->trace_cap * sizeof(double), cudaMemcpyDeviceToHost));
+    if (len) CU(h, cudaMemcpy(len, h->trace_len, (size_t)h->B * 4, cudaMemcpyDeviceToHost));
+    return DBSGYM_OK;
+}
+
+int dbsgym_eval_bbpow(DbsGymHandle* h, const DbsGymEvalSpec* spec, const double* weights, double* bbpow) {
+    if (!h || !spec || !weights || !bbpow) return fail(h, DBSGYM_EINVAL, "null argument");
+    if (spec->struct_bytes != sizeof(DbsGymEvalSpec)) return fail(h, DBSGYM_EINVAL, "DbsGymEvalSpec size mismatch");
+    if (!h->trace) return fail(h, DBSGYM_ESTATE, "no trace recorded (dbsgym_trace_begin)");
+    if (spec->n_k <= 0 || spec->k_lo < 0 || spec->padlen < 0) return fail(h, DBSGYM_EINVAL, "bad bin range / padlen");
+    if (spec->a[0] != 1.0) return fail(h, DBSGYM_EINVAL, "filter must be normalised (a[0] == 1)");
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaDeviceSynchronize());
+    std::vector<int32_t> len((size_t)h->B);
+    CU(h, cudaMemcpy(len.data(), h->trace_len, (size_t)h->B * 4, cudaMemcpyDeviceToHost));
+    const int n = len[0];
+    for (int b = 1; b < h->B; ++b)
+        if (len[b] != n) return fail(h, DBSGYM_ESTATE, "traces have different lengths (%d vs %d): evaluate in lockstep", len[b], n);
+    if (n < spec->padlen + 2) return fail(h, DBSGYM_ESTATE, "trace of %d samples is shorter than the filter padding", n);
+    if (spec->k_lo + spec->n_k - 1 > n / 2) return fail(h, DBSGYM_EINVAL, "bin range exceeds the rfft length");
+    EvalParams p;
+    p.trace = h->trace; p.cap = h->trace_cap; p.n = n; p.B = h->B; p.pad = spec->padlen;
+    for (int i = 0; i < 5; ++i) { p.b[i] = spec->b[i]; p.a[i] = spec->a[i]; }
+    for (int i = 0; i < 4; ++i) p.zi[i] = spec->zi[i];
+    p.k_lo = spec->k_lo; p.n_k = spec->n_k;
+    double *scratch = nullptr, *w = nullptr, *out = nullptr;
+    cudaError_t e = cudaMalloc(&scratch, (size_t)h->B * (n + 2 * spec->padlen) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&w, (size_t)spec->n_k * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&out, (size_t)h->B * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(w, weights, (size_t)spec->n_k * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        p.scratch = scratch; p.weights = w; p.out = out;
+        eval_filtfilt_kernel<<<(h->B + 31) / 32, 32, 0, h->stream>>>(p);
+        eval_band_power_kernel<<<h->B, kEvalThreads, 0, h->stream>>>(p);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(bbpow, out, (size_t)h->B * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(scratch); cudaFree(w); cudaFree(out);
+    if (e != cudaSuccess) return fail(h, DBSGYM_ECUDA, "evaluation kernels failed: %s", cudaGetErrorString(e));
     return DBSGYM_OK;
 }
 

@@ -78,6 +78,7 @@ struct StepParams {
     float* samples_f; float* mirror; float* reward_f; double* reward; uint8_t* done_out; uint8_t* done_dev;
     int32_t* step_idx_rw; const int32_t* episode_len;
     int32_t* nsamp_out; int32_t* head_out;      // optional copies of n_samples / the new ring head (mapped host memory)
+    double* trace; int32_t* trace_len; int trace_cap;   // optional recording of the TRUE LFP of every step (evaluation)
     double power_scale, action_cost, threshold, threshold_penalty;
     // cluster mode (one environment = a thread-block cluster of `cluster` CTAs, N > 4096)
     int cluster;                   // CTAs per environment (1 = plain)
@@ -682,6 +683,10 @@ __device__ __forceinline__ void obs_tail(const StepParams& p, int env, int lane,
             mr[pos + W] = (float)v;
         }
         t_delta[lane] = (double)v - t_delta[lane];
+        if (p.trace) {                                // evaluation trace: theta_mean of the step (env.py:441)
+            const int at = p.trace_len[env] + lane;
+            if (at < p.trace_cap) p.trace[(size_t)env * p.trace_cap + at] = p.lfp_true[(size_t)env * p.smax + lane];
+        }
     }
     __syncwarp();
     if (lane < nb) {
@@ -717,6 +722,7 @@ __device__ __forceinline__ void obs_tail(const StepParams& p, int env, int lane,
         int nh = head + S;
         if (nh >= W) nh -= W;
         p.head[env] = nh;
+        if (p.trace) p.trace_len[env] = min(p.trace_len[env] + S, p.trace_cap);
         if (p.nsamp_out) p.nsamp_out[env] = S;
         if (p.head_out) p.head_out[env] = nh;
     }

@@ -243,6 +243,37 @@ class KuramotoEngine:
                                           1 if reset else 0))
         return {"accepted": a.value, "rejected": r.value, "rhs_evals": f.value, "status": st.value}
 
+    # ------------------------------------------------------------------ evaluation metric on the device
+    def trace_begin(self, capacity):
+        """Record the TRUE LFP (theta_mean) of every following step on the device, up to `capacity` samples per env."""
+        self._trace_cap = int(capacity)
+        self._ck(self.lib.dbsgym_trace_begin(self._h, self._trace_cap))
+
+    def trace_end(self):
+        self._ck(self.lib.dbsgym_trace_end(self._h))
+
+    def trace(self):
+        """(trace [B, capacity] float64, lengths [B] int32) copied to the host."""
+        t = np.empty((self.n_envs, self._trace_cap))
+        n = np.empty(self.n_envs, dtype=np.int32)
+        self._ck(self.lib.dbsgym_trace_get(self._h, _capi.ptr(t), _capi.ptr(n)))
+        return t, n
+
+    def eval_bbpow(self, b, a, zi, padlen, k_lo, weights):
+        """Beta-band power of every environment's recorded trace (dbsgym.h: dbsgym_eval_bbpow)."""
+        spec = _capi.DbsGymEvalSpec()
+        spec.struct_bytes = C.sizeof(_capi.DbsGymEvalSpec)
+        spec.padlen = int(padlen)
+        for i in range(5):
+            spec.b[i], spec.a[i] = float(b[i]), float(a[i])
+        for i in range(4):
+            spec.zi[i] = float(zi[i])
+        w = _f64(weights)
+        spec.k_lo, spec.n_k = int(k_lo), int(w.size)
+        out = np.empty(self.n_envs)
+        self._ck(self.lib.dbsgym_eval_bbpow(self._h, C.byref(spec), _capi.ptr(w), _capi.ptr(out)))
+        return out
+
     def step_variant(self, n_envs=None):
         """Which step-kernel variant a launch over n_envs environments uses (dbsgym.h: dbsgym_step_variant)."""
         return int(self.lib.dbsgym_step_variant(self._h, self.n_envs if n_envs is None else int(n_envs)))

@@ -195,6 +195,27 @@ int dbsgym_last_step_ms(DbsGymHandle* h, float* ms2);
 /* enable / disable the per-kernel event timing above (off by default) */
 int dbsgym_set_timing(DbsGymHandle* h, int32_t enabled);
 
+/* ---- evaluation metric on the device (aDBS_RL/evaluate_HF_DBS.py:122-135) -----------------------
+ * dbsgym_trace_begin: from now on every step appends its TRUE-LFP samples (theta_mean, env.py:441) to a per-
+ * environment device trace of `capacity` float64 samples (lengths reset to 0); needs the beta-power reward
+ * path (the fused observation tail).  dbsgym_trace_end stops recording (the trace stays readable).
+ * dbsgym_trace_get copies trace [n_envs][capacity] and the lengths to the host (either may be NULL). */
+int dbsgym_trace_begin(DbsGymHandle* h, int32_t capacity);
+int dbsgym_trace_end(DbsGymHandle* h);
+int dbsgym_trace_get(DbsGymHandle* h, double* trace, int32_t* len);
+
+typedef struct DbsGymEvalSpec {
+    uint32_t struct_bytes;
+    int32_t  padlen;            /* filtfilt odd extension: 3 * max(len(a), len(b)) = 15                       */
+    double   b[5], a[5];        /* butter(2, [12, 30] Hz, 'band') at fs = 1 / psd_dt (utils.py:794-816)       */
+    double   zi[4];             /* scipy.signal.lfilter_zi(b, a)                                              */
+    int32_t  k_lo, n_k;         /* rfft bins k_lo .. k_lo + n_k - 1 carry non-zero weight                     */
+} DbsGymEvalSpec;
+/* bbpow[e] = sum_k weights[k] * 2 |rfft(filtfilt(b, a, trace_e))[k_lo + k] / n|^2 for every environment; all
+ * traces must have the same length n >= padlen + 2.  `weights` (float64 [n_k], host) folds the 12-tap spectrum
+ * smoothing and the band sum of calc_psd_for_simple_eval (evaluate_HF_DBS.py:130-134). */
+int dbsgym_eval_bbpow(DbsGymHandle* h, const DbsGymEvalSpec* spec, const double* weights, double* bbpow);
+
 /* FP32-FMA throughput micro-benchmark used for the roofline denominator: runs a dependent-
  * chain FFMA kernel on `device` for about `ms_target` ms; returns TFLOP/s in *tflops. */
 int dbsgym_measure_fp32_peak(int32_t device, double ms_target, double* tflops);

@@ -29,6 +29,7 @@ def test_struct_layouts_match_header():
     # sizes are checked inside the library as well (struct_bytes); these guard the ctypes mirror
     assert C.sizeof(_capi.DbsGymConfig) == 4 * 12 + 8 * 9
     assert C.sizeof(_capi.DbsGymRewardSpec) == 4 * 4 + 8 * 5
+    assert C.sizeof(_capi.DbsGymEvalSpec) == 4 * 2 + 8 * 14 + 4 * 2
 
 
 def test_create_rejects_bad_config_without_touching_a_gpu(lib):

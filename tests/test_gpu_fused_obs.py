@@ -110,3 +110,29 @@ def test_host_mirror_and_sample_transfer_with_fused_tail():
     full = eng.obs_host()
     np.testing.assert_array_equal(full, mirror[:, pos:pos + W])
     eng.close()
+
+
+@pytest.mark.parametrize("precision", ["f32", "f64"])
+def test_device_evaluation_metric_matches_scipy_on_the_recorded_trace(precision):
+    """The evaluation trace recorded by the step kernel's tail is the concatenation of the per-step TRUE-LFP
+    samples, and the device kernels (odd-extension filtfilt + weighted band power) reproduce
+    calc_psd_for_simple_eval (aDBS_RL/evaluate_HF_DBS.py:122-135, scipy on the host) to 1e-9."""
+    from dbsgym_b200.evaluation import calc_psd_for_simple_eval, device_bbpow
+    B, n_steps = 7, 120
+    eng, sched, rng = _engine(B, precision)
+    eng.trace_begin(n_steps * eng.max_step_samples)
+    host = [[] for _ in range(B)]
+    for k in range(n_steps):
+        eng.step_host(rng.uniform(-1, 1, B).astype(np.float32))
+        t, _, n = eng.lfp()
+        for b in range(B):
+            host[b].append(t[b, :n[b]].copy())
+    eng.trace_end()
+    eng.step_host(rng.uniform(-1, 1, B).astype(np.float32))          # not recorded any more
+    tr, ln = eng.trace()
+    sig = np.stack([np.concatenate(h) for h in host])
+    assert np.all(ln == sig.shape[1])
+    assert np.array_equal(tr[:, :ln[0]], sig)
+    ref = calc_psd_for_simple_eval(sig, 0.0005)
+    np.testing.assert_allclose(device_bbpow(eng), ref, rtol=1e-9)
+    eng.close()

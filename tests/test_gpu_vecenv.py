@@ -228,6 +228,12 @@ def test_batched_evaluation_reproduces_paper_hf_dbs_row():
     assert res["bbpow"].shape == (4,) and len(res["true_lfp"][0]) > 1111 * 17
     assert abs(res["summary"]["bbpow_mean"] - 2.34e-3) < 3 * 0.2e-3
     assert np.allclose(res["energy"], 1111.0)            # sum |a| with a = 1; x5 after rescaling = the paper's 5555
+    # the same episode with the trace recorded and the metric evaluated on the device (same seeds -> same episode)
+    venv.close()
+    venv = BatchedKuramotoVecEnv([make_params("env0", 11 + 9 * e, total_episode_len=1000, rand_seed=11 + e) for e in range(4)])
+    dev = evaluate_batched(HFDBS(1.0), venv, on_device=True)
+    np.testing.assert_allclose(dev["bbpow"], res["bbpow"], rtol=1e-7)
+    assert np.array_equal(np.asarray(dev["true_lfp"]), np.asarray(res["true_lfp"]))
     venv.close()
 
 
