@@ -44,28 +44,26 @@ __global__ void __launch_bounds__(32) eval_filtfilt_kernel(const EvalParams p) {
         const double x0 = ext(0);
         z0 = p.zi[0] * x0; z1 = p.zi[1] * x0; z2 = p.zi[2] * x0; z3 = p.zi[3] * x0;
     }
-    for (int i = 0; i < m; ++i) {          // forward lfilter (direct form II transposed)
-        const double xi = ext(i);
+    auto step = [&](double xi) -> double {  // one sample of lfilter, direct form II transposed (scipy's recurrence)
         const double yi = b0 * xi + z0;
         z0 = b1 * xi + z1 - a1 * yi;
         z1 = b2 * xi + z2 - a2 * yi;
         z2 = b3 * xi + z3 - a3 * yi;
         z3 = b4 * xi - a4 * yi;
-        y[i] = yi;
-    }
+        return yi;
+    };
+    // forward pass; the interior is unrolled so that the (independent) loads of 8 samples are in flight together --
+    // the recurrence itself is sequential, one thread per environment
+    for (int i = 0; i < pad; ++i) y[i] = step(ext(i));
+#pragma unroll 8
+    for (int j = 0; j < n; ++j) y[pad + j] = step(x[j]);
+    for (int i = pad + n; i < m; ++i) y[i] = step(ext(i));
     {
         const double x0 = y[m - 1];
         z0 = p.zi[0] * x0; z1 = p.zi[1] * x0; z2 = p.zi[2] * x0; z3 = p.zi[3] * x0;
     }
-    for (int i = m - 1; i >= 0; --i) {     // backward pass, in place
-        const double xi = y[i];
-        const double yi = b0 * xi + z0;
-        z0 = b1 * xi + z1 - a1 * yi;
-        z1 = b2 * xi + z2 - a2 * yi;
-        z2 = b3 * xi + z3 - a3 * yi;
-        z3 = b4 * xi - a4 * yi;
-        y[i] = yi;
-    }
+#pragma unroll 8
+    for (int i = m - 1; i >= 0; --i) y[i] = step(y[i]);   // backward pass, in place
 }
 
 // one CTA per environment, one bin per thread: X_k = sum_t sig_f[t] e^{-j 2 pi k t / n} with a rotation recurrence

@@ -259,6 +259,11 @@ class KuramotoEngine:
         self._ck(self.lib.dbsgym_trace_get(self._h, _capi.ptr(t), _capi.ptr(n)))
         return t, n
 
+    def trace_lengths(self):
+        n = np.empty(self.n_envs, dtype=np.int32)
+        self._ck(self.lib.dbsgym_trace_get(self._h, None, _capi.ptr(n)))
+        return n
+
     def eval_bbpow(self, b, a, zi, padlen, k_lo, weights):
         """Beta-band power of every environment's recorded trace (dbsgym.h: dbsgym_eval_bbpow)."""
         spec = _capi.DbsGymEvalSpec()

@@ -9,6 +9,8 @@ after a zero-phase order-2 band-pass and 12-tap spectrum smoothing (evaluate_HF_
 """
 from __future__ import annotations
 
+import functools
+
 import numpy as np
 
 from .utils import band_pass_envelope
@@ -38,6 +40,7 @@ def calc_psd_for_simple_eval(sig_envs, psd_dt, beta_a=12.5, beta_b=21):
     return np.asarray(out)
 
 
+@functools.lru_cache(maxsize=8)
 def bbpow_spec(n, psd_dt, beta_a=12.5, beta_b=21):
     """Everything the device metric (csrc/eval_kernel.cuh) needs for traces of n samples: the band-pass of
     band_pass_envelope(order=2) with scipy's filtfilt start-up values, and the weights w with
@@ -63,7 +66,7 @@ def bbpow_spec(n, psd_dt, beta_a=12.5, beta_b=21):
 
 def device_bbpow(engine, psd_dt=0.0005):
     """calc_psd_for_simple_eval of every environment's recorded device trace, computed on the GPU."""
-    _, n = engine.trace()
+    n = engine.trace_lengths()
     if not np.all(n == n[0]):
         raise ValueError("device evaluation needs traces of equal length (environments in lockstep)")
     sp = bbpow_spec(int(n[0]), psd_dt)
