@@ -29,7 +29,7 @@ EXPORTS = [
     "dbsgym_get_lfp", "dbsgym_get_rewards", "dbsgym_get_state", "dbsgym_get_window",
     "dbsgym_set_window", "dbsgym_get_episode", "dbsgym_counters", "dbsgym_last_step_ms",
     "dbsgym_set_timing", "dbsgym_measure_fp32_peak", "dbsgym_measure_fp32_peak_mode",
-    "dbsgym_trace_begin", "dbsgym_trace_end", "dbsgym_trace_get", "dbsgym_eval_bbpow",
+    "dbsgym_rhs_reused", "dbsgym_trace_begin", "dbsgym_trace_end", "dbsgym_trace_get", "dbsgym_eval_bbpow",
 ]
 
 
@@ -135,6 +135,7 @@ def load():
         "dbsgym_counters": (C.c_int, [vp, u64p, u64p, u64p, i32p, C.c_int32]),
         "dbsgym_last_step_ms": (C.c_int, [vp, f32p]),
         "dbsgym_set_timing": (C.c_int, [vp, C.c_int32]),
+        "dbsgym_rhs_reused": (C.c_int, [vp, u64p]),
         "dbsgym_trace_begin": (C.c_int, [vp, C.c_int32]),
         "dbsgym_trace_end": (C.c_int, [vp]),
         "dbsgym_trace_get": (C.c_int, [vp, vp, vp]),

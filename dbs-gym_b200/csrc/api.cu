@@ -72,6 +72,8 @@ struct DbsGymHandle {
     unsigned char* ctl_host = nullptr; unsigned char* ctl_dev = nullptr;
     // evaluation trace (dbsgym_trace_begin): TRUE LFP of every step, [B][trace_cap] float64
     double* trace = nullptr; int32_t* trace_len = nullptr; int trace_cap = 0; bool trace_on = false;
+    // FSAL carried across segments / launches (fp32): last stage derivative per environment + valid flags
+    void* k_fsal = nullptr; int32_t* fsal_valid = nullptr; bool fsal_on = false;
     bool mirror_on = false;              // obs kernel writes the mirror (set while a mirror step / reset runs)
     uint8_t* st_done = nullptr;
     // timing
@@ -251,6 +253,7 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
     p.step_idx_rw = h->step_idx; p.episode_len = h->episode_len;
     p.nsamp_out = nullptr; p.head_out = nullptr;
     p.trace = nullptr; p.trace_len = nullptr; p.trace_cap = 0;
+    p.fsal_on = h->fsal_on ? 1 : 0; p.k_fsal = h->k_fsal; p.fsal_valid = h->fsal_valid;
     p.power_scale = h->rspec.power_scale; p.action_cost = h->rspec.action_cost;
     p.threshold = h->rspec.threshold; p.threshold_penalty = h->rspec.threshold_penalty;
 }
@@ -548,7 +551,9 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
     A((void**)&h->lfp_true, (size_t)h->B * h->smax * 8); A((void**)&h->lfp_rec, (size_t)h->B * h->smax * 8);
     A((void**)&h->u, (size_t)h->B * 8); A((void**)&h->reward, (size_t)h->B * 8);
     A((void**)&h->done, (size_t)h->B);
-    A((void**)&h->counters, 3 * sizeof(unsigned long long)); A((void**)&h->status, 4);
+    A((void**)&h->counters, 4 * sizeof(unsigned long long)); A((void**)&h->status, 4);
+    h->fsal_on = !h->f64 && getenv("DBSGYM_NO_FSAL_REUSE") == nullptr;       // A/B switch
+    if (h->fsal_on) { A(&h->k_fsal, BN * h->rb); A((void**)&h->fsal_valid, (size_t)h->B * 4); }
     A((void**)&h->spec, (size_t)h->B * kTailBins * 2 * sizeof(double));
     A((void**)&h->st_actions, (size_t)h->B * 4); A((void**)&h->st_obs, (size_t)h->B * h->W * 4);
     A((void**)&h->st_reward, (size_t)h->B * 4); A((void**)&h->st_done, (size_t)h->B);
@@ -580,7 +585,7 @@ void dbsgym_destroy(DbsGymHandle* h) {
     void* bufs[] = {h->table, h->alpha, h->w0, h->stim, h->rec, h->phase, h->ring, h->wind, h->head, h->n_samples,
                     h->step_idx, h->episode_len, h->lfp_true, h->lfp_rec, h->u, h->reward, h->done, h->sched_nI,
                     h->sched_nII, h->sched_offI, h->sched_offII, h->ts_dev, h->ids_dev, h->lin_g, h->tw_seed,
-                    h->tw_inner, h->spec, h->tw_full, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples,
+                    h->tw_inner, h->spec, h->tw_full, h->k_fsal, h->fsal_valid, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples,
                     h->cl_operand, h->cl_scratch};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -612,6 +617,7 @@ int dbsgym_set_coupling_grid(DbsGymHandle* h, const double* table) {
     if (!h->table) CU(h, cudaMalloc(&h->table, buf.size()));
     CU(h, cudaMemcpy(h->table, buf.data(), buf.size(), cudaMemcpyHostToDevice));
     h->have_coupling = true;
+    if (h->fsal_valid) CU(h, cudaMemset(h->fsal_valid, 0, (size_t)h->B * 4));
     return DBSGYM_OK;
 }
 
@@ -630,6 +636,7 @@ int dbsgym_set_coupling_dense(DbsGymHandle* h, const double* alpha) {
     if (!h->alpha) CU(h, cudaMalloc(&h->alpha, buf.size()));
     CU(h, cudaMemcpy(h->alpha, buf.data(), buf.size(), cudaMemcpyHostToDevice));
     h->have_coupling = true;
+    if (h->fsal_valid) CU(h, cudaMemset(h->fsal_valid, 0, (size_t)h->B * 4));
     return DBSGYM_OK;
 }
 
@@ -647,6 +654,11 @@ int dbsgym_set_env_params(DbsGymHandle* h, const int32_t* env_ids, int32_t n, co
     const int32_t* ids = nullptr;
     int rc = upload_ids(h, env_ids, n, &ids);
     if (rc) return rc;
+    if (h->fsal_valid) {                            // the carried stage derivative belongs to the old vectors
+        std::vector<int32_t> z((size_t)n, 0);
+        rc = scatter_to_device(h, h->fsal_valid, z.data(), ids, n, 4);
+        if (rc) return rc;
+    }
     std::vector<unsigned char> buf;
     const size_t row = (size_t)h->Np * h->rb;
     struct { const double* src; void* dst; } vecs[3] = {{w0, h->w0}, {stim_cond, h->stim}, {rec_cond, h->rec}};
@@ -1065,7 +1077,7 @@ int dbsgym_counters(DbsGymHandle* h, uint64_t* accepted, uint64_t* rejected, uin
     if (!h) return DBSGYM_EINVAL;
     CU(h, cudaSetDevice(h->cfg.device));
     CU(h, cudaDeviceSynchronize());
-    unsigned long long c[3];
+    unsigned long long c[4];
     int32_t st = 0;
     CU(h, cudaMemcpy(c, h->counters, sizeof(c), cudaMemcpyDeviceToHost));
     CU(h, cudaMemcpy(&st, h->status, 4, cudaMemcpyDeviceToHost));
@@ -1077,6 +1089,16 @@ int dbsgym_counters(DbsGymHandle* h, uint64_t* accepted, uint64_t* rejected, uin
         CU(h, cudaMemset(h->counters, 0, sizeof(c)));
         CU(h, cudaMemset(h->status, 0, 4));
     }
+    return DBSGYM_OK;
+}
+
+int dbsgym_rhs_reused(DbsGymHandle* h, uint64_t* reused) {
+    if (!h || !reused) return fail(h, DBSGYM_EINVAL, "null argument");
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaDeviceSynchronize());
+    unsigned long long v = 0;
+    CU(h, cudaMemcpy(&v, h->counters + 3, sizeof(v), cudaMemcpyDeviceToHost));
+    *reused = v;
     return DBSGYM_OK;
 }
 

@@ -243,6 +243,13 @@ class KuramotoEngine:
                                           1 if reset else 0))
         return {"accepted": a.value, "rejected": r.value, "rhs_evals": f.value, "status": st.value}
 
+    def rhs_reused(self):
+        """How many of the counted RHS evaluations were carried over instead of executed (dbsgym.h: dbsgym_rhs_reused);
+        read it BEFORE counters(reset=True)."""
+        v = C.c_uint64()
+        self._ck(self.lib.dbsgym_rhs_reused(self._h, C.byref(v)))
+        return v.value
+
     # ------------------------------------------------------------------ evaluation metric on the device
     def trace_begin(self, capacity):
         """Record the TRUE LFP (theta_mean) of every following step on the device, up to `capacity` samples per env."""

@@ -189,6 +189,11 @@ int dbsgym_get_episode(DbsGymHandle* h, int32_t* step_idx, uint8_t* done);
  * steps, RHS evaluations, summed over environments; and the device status word (0 = ok). */
 int dbsgym_counters(DbsGymHandle* h, uint64_t* accepted, uint64_t* rejected,
                     uint64_t* rhs_evals, int32_t* status, int32_t reset);
+/* of the rhs_evals counted above (the evaluations the reference performs), how many the fp32 kernel did NOT execute
+ * because the first stage of a segment was taken from the last stage of the previous accepted sub-step (same state,
+ * only the pulse term differs: k1 = k7 + (amp_new - amp_old) * stim); reset together with dbsgym_counters */
+int dbsgym_rhs_reused(DbsGymHandle* h, uint64_t* reused);
+
 /* elapsed device time (ms) of the kernels of the most recent dbsgym_step*, measured with
  * CUDA events on the launching stream: [0] step kernel, [1] observation kernel */
 int dbsgym_last_step_ms(DbsGymHandle* h, float* ms2);

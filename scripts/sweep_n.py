@@ -63,7 +63,7 @@ for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024):
         tmax = torch.tensor([k_step, k_obs], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         k_step, k_obs = (float(v) for v in tmax.cpu())
-    rhs = c["rhs_evals"] / (n_timed * B)
+    rhs = (c["rhs_evals"] - eng.rhs_reused()) / (n_timed * B)       # executed evaluations (the reference's count is 32)
     ypar = bool(eng.lib.dbsgym_build_flags() & 1)          # own op count of the sector contraction, see bench.py
     SYM_FLOP, SYM_LIN = ((148 if eng.step_variant(B) == 4 else 196 if ypar else 304) / 256.0), ((160 if ypar else 128) / 8.0)
     out.append({"N": N, "grid": [8, 8, gz], "n_gpus": WORLD, "envs_per_gpu": B, "envs": B * WORLD, "step_kernel_ms": float(k_step), "obs_kernel_ms": float(k_obs),

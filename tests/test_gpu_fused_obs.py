@@ -136,3 +136,41 @@ def test_device_evaluation_metric_matches_scipy_on_the_recorded_trace(precision)
     ref = calc_psd_for_simple_eval(sig, 0.0005)
     np.testing.assert_allclose(device_bbpow(eng), ref, rtol=1e-9)
     eng.close()
+
+
+def test_fsal_reuse_across_segments_and_launches(monkeypatch):
+    """fp32 mode takes the first stage of every segment from the last stage of the previous accepted sub-step (same
+    state, only the pulse term changes) instead of evaluating the RHS again -- also across kernel launches and after
+    a reset transient.  The counters keep the reference's (logical) count of 32 evaluations per step; 2 per step
+    are reused (1 in the very first step after the vectors were uploaded); phases, windows and rewards agree with the
+    kernel that evaluates every stage (DBSGYM_NO_FSAL_REUSE=1) to float32 rounding."""
+    B, n = 6, 8
+    outs = {}
+    for mode in ("reuse", "evaluate"):
+        if mode == "evaluate":
+            monkeypatch.setenv("DBSGYM_NO_FSAL_REUSE", "1")
+        else:
+            monkeypatch.delenv("DBSGYM_NO_FSAL_REUSE", raising=False)
+        eng, sched, rng = _engine(B, "f32")
+        eng.counters(reset=True)
+        for k in range(n):
+            eng.step_host(rng.uniform(-1, 1, B).astype(np.float32))
+        c1, r1 = eng.counters(), eng.rhs_reused()
+        eng.transient(np.arange(0.0, 118.0, 0.05), env_ids=[2, 3])
+        eng.set_episode([2, 3], step_idx=0, episode_len=2 ** 30)
+        eng.counters(reset=True)
+        obs, rew, done = eng.step_host(rng.uniform(-1, 1, B).astype(np.float32))
+        c2, r2 = eng.counters(), eng.rhs_reused()
+        outs[mode] = (c1, r1, c2, r2, eng.state(), eng.window_values(), rew.copy())
+        eng.close()
+    (c1, r1, c2, r2, y, w, rew), (d1, s1, d2, s2, y0, w0, rew0) = outs["reuse"], outs["evaluate"]
+    assert c1 == d1 and c2 == d2 and c1["rhs_evals"] == B * n * 32 and c1["status"] == 0
+    assert (s1, s2) == (0, 0)
+    assert r1 == B * (2 * n - 1)            # the first segment after set_env_params has nothing to reuse
+    assert r2 == B * 2                      # the transient of environments 2 and 3 left its last stage behind as well
+    # nine free-running steps: the one-ulp differences of the carried stage grow like any fp32 rounding difference
+    # (tests/test_gpu_episode_stats.py measures that horizon); per-step accuracy against the fp64 oracle is what the
+    # teacher-forced parity tests in tests/test_gpu_parity.py check, with the reuse active
+    np.testing.assert_allclose(y, y0, rtol=0, atol=1e-3)
+    np.testing.assert_allclose(w, w0, rtol=0, atol=2e-5)
+    np.testing.assert_allclose(rew, rew0, rtol=1e-3, atol=1e-5)
