@@ -25,7 +25,7 @@ EXPORTS = [
     "dbsgym_abi_version", "dbsgym_build_flags", "dbsgym_step_variant", "dbsgym_create", "dbsgym_destroy", "dbsgym_last_error",
     "dbsgym_set_coupling_grid", "dbsgym_set_coupling_dense", "dbsgym_set_env_params",
     "dbsgym_set_recording", "dbsgym_set_schedule", "dbsgym_set_reward", "dbsgym_set_episode",
-    "dbsgym_transient", "dbsgym_step", "dbsgym_step_host", "dbsgym_step_host_samples", "dbsgym_host_mirror", "dbsgym_step_host_mirror", "dbsgym_get_obs_host",
+    "dbsgym_transient", "dbsgym_step", "dbsgym_step_host", "dbsgym_step_host_samples", "dbsgym_host_mirror", "dbsgym_step_host_mirror", "dbsgym_step_host_mirror_begin", "dbsgym_step_host_mirror_end", "dbsgym_get_obs_host",
     "dbsgym_get_lfp", "dbsgym_get_rewards", "dbsgym_get_state", "dbsgym_get_window",
     "dbsgym_set_window", "dbsgym_get_episode", "dbsgym_counters", "dbsgym_last_step_ms",
     "dbsgym_set_timing", "dbsgym_measure_fp32_peak", "dbsgym_measure_fp32_peak_mode",
@@ -125,6 +125,8 @@ def load():
         "dbsgym_step_host_samples": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "dbsgym_host_mirror": (C.c_int, [vp, C.POINTER(f32p)]),
         "dbsgym_step_host_mirror": (C.c_int, [vp, vp, i32p, i32p, vp, vp]),
+        "dbsgym_step_host_mirror_begin": (C.c_int, [vp, vp]),
+        "dbsgym_step_host_mirror_end": (C.c_int, [vp, i32p, i32p, vp, vp]),
         "dbsgym_get_obs_host": (C.c_int, [vp, vp]),
         "dbsgym_get_lfp": (C.c_int, [vp, vp, vp, vp]),
         "dbsgym_get_rewards": (C.c_int, [vp, vp, vp]),

@@ -172,6 +172,33 @@ class BatchedKuramoto:
         """Current observation windows [B, W] float32 (host), read back from the device."""
         return self.engine.obs_host(self.obs_buf)
 
+    def step_begin(self, actions):
+        """Launch one step of every environment and return at once (the GPU works); finish with step_end().
+        Only the delta-transfer (host mirror) path is asynchronous; the full-observation path runs in step_end."""
+        self.act_buf[:] = np.asarray(actions, dtype=np.float32).reshape(self.num_envs)
+        self._lfp_cache = None
+        self._pending = True
+        if self.transfer == "delta":
+            if self._mirror is None:
+                self._mirror = self.engine.host_mirror()
+            self.engine.step_host_mirror_begin(self.act_buf)
+
+    def step_end(self):
+        if not getattr(self, "_pending", False):
+            raise RuntimeError("step_end() without step_begin()")
+        self._pending = False
+        if self.transfer == "delta":
+            pos, n = self.engine.step_host_mirror_end(self.rew_buf, self.done_buf)
+            self.current_step += 1
+            if n >= 0:
+                return self._mirror[:, pos:pos + self.window], self.rew_buf, self.done_buf.view(np.bool_)
+            return self.observations(), self.rew_buf, self.done_buf.view(np.bool_)   # out of lockstep
+        self._obs_flip ^= 1
+        self.obs_buf = self._obs_bufs[self._obs_flip]
+        self.engine.step_host(self.act_buf, self.obs_buf, self.rew_buf, self.done_buf)
+        self.current_step += 1
+        return self.obs_buf, self.rew_buf, self.done_buf.view(np.bool_)
+
     def step(self, actions):
         """Advance every environment by one step.  Returns host views: obs [B,W] f32, reward [B] f32
         and done [B] bool, all overwritten by later calls (copy what you keep)."""

@@ -75,6 +75,7 @@ struct DbsGymHandle {
     // FSAL carried across segments / launches (fp32): last stage derivative per environment + valid flags
     void* k_fsal = nullptr; int32_t* fsal_valid = nullptr; bool fsal_on = false;
     bool mirror_on = false;              // obs kernel writes the mirror (set while a mirror step / reset runs)
+    bool mirror_pending = false;         // between dbsgym_step_host_mirror_begin and _end
     uint8_t* st_done = nullptr;
     // timing
     int cluster = 1;                     // CTAs per environment (thread-block cluster; > 1 when N > 4096)
@@ -907,17 +908,18 @@ int dbsgym_host_mirror(DbsGymHandle* h, float** mirror) {
     return DBSGYM_OK;
 }
 
-int dbsgym_step_host_mirror(DbsGymHandle* h, const float* actions, int32_t* pos, int32_t* n_new, float* reward,
-                            uint8_t* done) {
+// The host-mirror step in two halves: _begin copies the actions and launches (returns at once, the GPU works),
+// _end waits and hands back reward / done / ring position.  dbsgym_step_host_mirror = _begin + _end.
+int dbsgym_step_host_mirror_begin(DbsGymHandle* h, const float* actions) {
     int rc = check_ready(h, true);
     if (rc) return rc;
-    if (!actions || !pos || !n_new) return fail(h, DBSGYM_EINVAL, "null argument");
+    if (!actions) return fail(h, DBSGYM_EINVAL, "null argument");
     if (!h->mirror_host) return fail(h, DBSGYM_ESTATE, "no host mirror: call dbsgym_host_mirror first");
+    if (h->mirror_pending) return fail(h, DBSGYM_ESTATE, "a host-mirror step is already in flight (call dbsgym_step_host_mirror_end)");
     const int B = h->B;
     CU(h, cudaSetDevice(h->cfg.device));
     cudaStream_t s = h->stream;
     h->mirror_on = true;
-    const int32_t *ns = nullptr, *hd = nullptr;
     if (h->fuse_tail) {
         // zero-copy control block: the kernel reads the actions from, and its tail writes reward / done / n_samples /
         // ring head to, pinned mapped host memory -- no memcpy nodes on the stream, one launch and one sync per step
@@ -931,17 +933,33 @@ int dbsgym_step_host_mirror(DbsGymHandle* h, const float* actions, int32_t* pos,
                        at(h->ctl_dev, 4), s, nullptr, reinterpret_cast<int32_t*>(at(h->ctl_dev, 2)),
                        reinterpret_cast<int32_t*>(at(h->ctl_dev, 3)));
         if (rc) return rc;
-        CU(h, cudaStreamSynchronize(s));
-        if (reward) memcpy(reward, at(h->ctl_host, 1), (size_t)B * 4);
-        if (done) memcpy(done, at(h->ctl_host, 4), (size_t)B);
-        ns = reinterpret_cast<const int32_t*>(at(h->ctl_host, 2));
-        hd = reinterpret_cast<const int32_t*>(at(h->ctl_host, 3));
     } else {
         CU(h, cudaMemcpyAsync(h->st_actions, actions, (size_t)B * 4, cudaMemcpyHostToDevice, s));
         rc = step_impl(h, h->st_actions, nullptr, h->st_reward, h->st_done, s, nullptr);
         if (rc) return rc;
         CU(h, cudaMemcpyAsync(h->pin_ints, h->n_samples, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
         CU(h, cudaMemcpyAsync(h->pin_ints + B, h->head, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    }
+    h->mirror_pending = true;
+    return DBSGYM_OK;
+}
+
+int dbsgym_step_host_mirror_end(DbsGymHandle* h, int32_t* pos, int32_t* n_new, float* reward, uint8_t* done) {
+    if (!h || !pos || !n_new) return fail(h, DBSGYM_EINVAL, "null argument");
+    if (!h->mirror_pending) return fail(h, DBSGYM_ESTATE, "no host-mirror step in flight (call dbsgym_step_host_mirror_begin)");
+    const int B = h->B;
+    CU(h, cudaSetDevice(h->cfg.device));
+    cudaStream_t s = h->stream;
+    h->mirror_pending = false;
+    const int32_t *ns = nullptr, *hd = nullptr;
+    if (h->fuse_tail) {
+        auto at = [&](unsigned char* base, int k) { return base + (size_t)k * B * 4; };
+        CU(h, cudaStreamSynchronize(s));
+        if (reward) memcpy(reward, at(h->ctl_host, 1), (size_t)B * 4);
+        if (done) memcpy(done, at(h->ctl_host, 4), (size_t)B);
+        ns = reinterpret_cast<const int32_t*>(at(h->ctl_host, 2));
+        hd = reinterpret_cast<const int32_t*>(at(h->ctl_host, 3));
+    } else {
         if (reward) CU(h, cudaMemcpyAsync(reward, h->st_reward, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
         if (done) CU(h, cudaMemcpyAsync(done, h->st_done, (size_t)B, cudaMemcpyDeviceToHost, s));
         CU(h, cudaStreamSynchronize(s));
@@ -953,6 +971,14 @@ int dbsgym_step_host_mirror(DbsGymHandle* h, const float* actions, int32_t* pos,
     *pos = hd0;
     *n_new = uniform ? n : -1;
     return DBSGYM_OK;
+}
+
+int dbsgym_step_host_mirror(DbsGymHandle* h, const float* actions, int32_t* pos, int32_t* n_new, float* reward,
+                            uint8_t* done) {
+    if (!pos || !n_new) return fail(h, DBSGYM_EINVAL, "null argument");
+    int rc = dbsgym_step_host_mirror_begin(h, actions);
+    if (rc) return rc;
+    return dbsgym_step_host_mirror_end(h, pos, n_new, reward, done);
 }
 
 int dbsgym_get_obs_host(DbsGymHandle* h, float* obs) {

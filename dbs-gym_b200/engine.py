@@ -187,6 +187,16 @@ class KuramotoEngine:
                                                   _capi.ptr(reward), _capi.ptr(done)))
         return cpos.value, cn.value
 
+    def step_host_mirror_begin(self, actions):
+        """Launch one host-mirror step and return immediately (finish it with step_host_mirror_end)."""
+        self._ck(self.lib.dbsgym_step_host_mirror_begin(self._h, _capi.ptr(actions)))
+
+    def step_host_mirror_end(self, reward, done):
+        cpos, cn = C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.dbsgym_step_host_mirror_end(self._h, C.byref(cpos), C.byref(cn), _capi.ptr(reward),
+                                                      _capi.ptr(done)))
+        return cpos.value, cn.value
+
     def step_device(self, actions_ptr, obs_ptr=None, reward_ptr=None, done_ptr=None, stream=None):
         """Asynchronous step on raw device pointers (e.g. ``tensor.data_ptr()``)."""
         self._ck(self.lib.dbsgym_step(self._h, actions_ptr, obs_ptr, reward_ptr, done_ptr, _stream(stream)))

@@ -71,19 +71,21 @@ class BatchedKuramotoVecEnv(VecEnvBase):
         return self.core.observations().reshape(self.num_envs, 1, -1).copy()
 
     def step_async(self, actions):
-        self._actions = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, -1)[:, 0]
+        """Really asynchronous: the step kernel is launched here; the bookkeeping that does not depend on its
+        results runs while the GPU works, step_wait() only waits and reads the results."""
+        self.core.step_begin(np.asarray(actions, dtype=np.float32).reshape(self.num_envs, -1)[:, 0])
+        self._ep_len += 1
+        # one shared info dict for the environments that did not finish (building thousands of dicts per
+        # step costs more than the GPU step); finished environments get their own
+        self._infos = [{"TimeLimit.truncated": False}] * self.num_envs
 
     def step_wait(self):
-        obs, rew, done = self.core.step(self._actions)
+        obs, rew, done = self.core.step_end()
         obs = obs.reshape(self.num_envs, 1, -1)       # a view (host window mirror / pinned buffer): no 38 MB copy
         rew = rew.copy()
         done = done.copy()
         self._ep_ret += rew
-        self._ep_len += 1
-        # one shared info dict for the environments that did not finish (building thousands of dicts per
-        # step costs more than the GPU step); finished environments get their own
-        shared = {"TimeLimit.truncated": False}
-        infos = [shared] * self.num_envs
+        infos = self._infos
         finished = np.flatnonzero(done)
         if finished.size:
             for i in finished:

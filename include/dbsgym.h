@@ -172,6 +172,10 @@ int dbsgym_host_mirror(DbsGymHandle* h, float** mirror);
 int dbsgym_step_host_mirror(DbsGymHandle* h, const float* actions, int32_t* pos, int32_t* n_new,
                             float* reward, uint8_t* done);
 /* reset observation (window as float32) of all environments to a host buffer [B][W] */
+/* the same step in two halves: _begin copies the actions and launches the step kernel (returns immediately), _end
+ * waits for it and returns what dbsgym_step_host_mirror returns -- host work can overlap the GPU in between */
+int dbsgym_step_host_mirror_begin(DbsGymHandle* h, const float* actions);
+int dbsgym_step_host_mirror_end(DbsGymHandle* h, int32_t* pos, int32_t* n_new, float* reward, uint8_t* done);
 int dbsgym_get_obs_host(DbsGymHandle* h, float* obs);
 
 /* ---- introspection (host buffers, synchronising) -------------------------------------- */
