@@ -351,8 +351,8 @@ def run_gpu_arm(args):
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp32_peak if fp32_peak else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 4096 envs, from the ncu
-                         # --set full capture profiles/r01_final2_step_obs_raw.csv (44.05 MB read + 0.04 MB write)
-                         "traffic": 44.08e6 * B / 4096,
+                         # --set full capture profiles/r01_final3_step_obs_raw.csv (52.45 MB read + 0.73 MB write)
+                         "traffic": 53.19e6 * B / 4096,
                          "kernel": kernel_name,
                          "kernel_ms": k_step * 1e3, "flop_per_env_step": flop_per_env_step,
                          "dense_formulation_flop_per_env_step": dense_flop_per_env_step,

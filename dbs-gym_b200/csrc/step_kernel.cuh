@@ -1,26 +1,26 @@
 // Fused Kuramoto environment-step kernel (sm_100a).
 //
-// One CTA integrates ONE environment through every Runge-Kutta sub-step of one
-// SpatialKuramoto.step() call (reference environment/env.py:415-454) -- or through the
-// reset transient (env.py:605-612) -- with the oscillator state resident on chip:
+// One WORKER (64 threads at N = 512; a whole CTA, or one of the 8 workers of a multi-worker CTA, or a thread-block
+// cluster for N > 4096) integrates ONE environment through every Runge-Kutta sub-step of one SpatialKuramoto.step()
+// call (reference environment/env.py:415-454) -- or through the reset transient (env.py:605-612) -- with the
+// oscillator state resident on chip, and finishes with the observation tail (window append, beta-power reward,
+// episode bookkeeping: env.py:447-454, :638-650, :669-688):
 //
-//   registers : phases y0 (+ winding counts in fp32 mode), natural frequencies w0,
-//               stimulation conductance, recording conductance      (8 oscillators / thread)
-//   shared    : the seven Dopri5 stage derivatives K[7][N], the [sin,cos] operand of the
-//               coupling contraction (double buffered) and the coupling table
+//   registers : phases y0 (fp32: wrapped, winding counts in shared memory), w0 + pulse        (8 oscillators / thread)
+//   shared    : six slots for the seven Dopri5 stage derivatives (k7 re-uses the slot of the dead k2), the [sin,cos]
+//               operand of the coupling contraction (double buffered), the coupling table / sector coefficients
 //
 // The ODE right-hand side (env.py:252-256) is evaluated through
 //     sum_j a_ij sin(th_j - th_i) = cos(th_i) (A sin th)_i - sin(th_i) (A cos th)_i,
 // i.e. one [N x N] x [N x 2] contraction per evaluation.  In GRID mode the coupling
 // a_ij = f(|dz|,|dx|,|dy|) of a regular neuron grid (utils.py:478-497, env.py:219-229) is a
-// 3-level block-Toeplitz operator: a thread owns the 8 oscillators of one grid line (fixed
-// z,x) and needs only the 8 table entries t[|yi-yj|] of block (|dz|,|dx|) for 128 FMAs, so
-// the whole operator lives in 2 KB of shared memory and no matrix is streamed from L2.
-// DENSE mode streams an arbitrary symmetric alpha from global memory (generic fallback).
+// 3-level block-Toeplitz operator held as a 2 KB table; it commutes with the three reflections of the grid, so the
+// contraction runs block-diagonally in the basis of the 8 parity sectors (GRID_SYM: 1/8 of the multiply-adds, the
+// same sum reassociated).  DENSE mode streams an arbitrary symmetric alpha from global memory (generic fallback).
 //
 // The integrator follows diffrax 0.7.0's Dopri5 + PIDController(I-only) + SaveAt(ts) as
 // the reference calls it (env.py:247-249, :260-271); see oracle/diffrax_restated.py for the
-// statement of those semantics this kernel is tested against.
+// statement of those semantics this kernel is tested against.  DESIGN.md section 3 has the measurements.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

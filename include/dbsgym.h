@@ -11,7 +11,9 @@
  *                                PIDController(rtol=atol=1e-5), SaveAt(ts))      -> the step kernel
  *   environment/env.py:396-412   calc_naive_lfp / calc_distance_lfp             -> fused in the step kernel
  *   environment/env.py:447-452, :638-688, utils.py:21-27, :794-816
- *                                window slide, rewards R1/R2/R3                 -> the observation kernel
+ *                                window slide, rewards R1/R2/R3                 -> the step kernel's fused tail
+ *                                                                                  (R1/R3), the observation kernel (R2)
+ *   aDBS_RL/evaluate_HF_DBS.py:122-135  calc_psd_for_simple_eval                -> dbsgym_trace_* / dbsgym_eval_bbpow
  *
  * Conventions
  *   - plain C types only; every call returns 0 on success or a negative DBSGYM_E* code and
