@@ -59,6 +59,9 @@ class BatchedKuramoto:
         self.schedule = StepSchedule(max_len + 1, self.t_transient[-1], p0["electrode_width"],
                                      p0["electrode_pause"], p0["verbose_dt"])
         # --- coupling operator (shared by every env: it depends only on the neuron grid) ---
+        # lines of 16 (gy = 16) are handled by the fp32 structured kernel only: fp64 parity mode takes the DENSE path
+        if int(p0["grid_size"][1]) != 8 and precision == "f64":
+            force_dense = True
         table = None if force_dense else coupling_table(p0["neur_coords"], p0["neur_grid"], p0["grid_size"],
                                                         p0["spatial_kernel"], p0["wavelet_amp"],
                                                         p0["wavelet_steepness"])

@@ -226,7 +226,7 @@ void to_real_rows(const double* src, int n, int N, int Np, std::vector<unsigned 
 void fill_params(DbsGymHandle* h, StepParams& p) {
     const DbsGymConfig& c = h->cfg;
     p.N = h->N; p.Np = h->Np; p.B = h->B;
-    p.GX = c.grid[0]; p.GZ = c.grid[2];
+    p.GX = c.grid[0]; p.GZ = c.grid[2]; p.GY = c.grid[1];
     p.weighted_rec = h->weighted_rec;
     p.max_steps = c.max_steps;
     p.k_over_n = c.K / (double)h->N;
@@ -292,6 +292,12 @@ cudaError_t launch_step_mw(DbsGymHandle* h, const StepParams& p, cudaStream_t s)
 template <typename real, int CPL>
 cudaError_t launch_step_m(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
     const int t = h->nthreads;
+    if constexpr (CPL == CPL_GRID_SYM && sizeof(real) == 4) if (p.GY == 2 * kRows) {   // lines of 16 (cubic 16^3 grids)
+        if (t <= 64) return launch_step_t<real, CPL, 64, 3>(h, p, s);
+        if (t <= 128) return launch_step_t<real, CPL, 128, 3>(h, p, s);
+        if (t <= 256) return launch_step_t<real, CPL, 256, 3>(h, p, s);
+        return launch_step_t<real, CPL, 512, 3>(h, p, s);
+    }
     if constexpr (CPL == CPL_GRID_SYM && sizeof(real) == 4) {
         static const bool no_geo1 = getenv("DBSGYM_NO_GEO1") != nullptr;        // A/B switch for tuning runs
         if (t == 64 && p.GZ == 8 && p.GX == 8 && !no_geo1) {
@@ -447,6 +453,7 @@ int dbsgym_step_variant(const DbsGymHandle* h, int32_t n_envs) {
     if (h->cfg.coupling == DBSGYM_COUPLING_DENSE) return 1;
     if (!h->grid_sym) return 0;
     if (h->f64) return 2;
+    if (h->cfg.grid[1] == 2 * kRows) return 7;
     const bool geo1 = h->nthreads == 64 && h->cfg.grid[2] == 8 && h->cfg.grid[0] == 8 && !getenv("DBSGYM_NO_GEO1");
     if (geo1) {
         const bool mw = kYParity && (h->mw_mode == 1 || (h->mw_mode < 0 && n_envs >= kMwEnvs * h->num_sms));
@@ -485,11 +492,20 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
     if (cfg->coupling == DBSGYM_COUPLING_DENSE && Np / kRows > 1024)
         return fail(nullptr, DBSGYM_EINVAL, "n_osc %d too large for DENSE coupling (max 8192)", cfg->n_osc);
     if (cfg->coupling == DBSGYM_COUPLING_GRID) {
-        if (cfg->grid[1] != kRows)
-            return fail(nullptr, DBSGYM_EINVAL, "GRID coupling needs grid[1] (gy) == %d, got %d", kRows, cfg->grid[1]);
+        const int gy = cfg->grid[1];
+        if (gy != kRows && gy != 2 * kRows)
+            return fail(nullptr, DBSGYM_EINVAL, "GRID coupling needs grid[1] (gy) == %d or %d, got %d", kRows, 2 * kRows, gy);
         if (cfg->grid[0] <= 0 || cfg->grid[2] <= 0 || cfg->n_osc % kRows != 0 ||
-            cfg->n_osc > cfg->grid[0] * cfg->grid[1] * cfg->grid[2] || cfg->n_osc % (cfg->grid[0] * kRows) != 0)
-            return fail(nullptr, DBSGYM_EINVAL, "GRID coupling needs n_osc to be whole z-planes of a gx*8*gz grid");
+            cfg->n_osc > cfg->grid[0] * gy * cfg->grid[2] || cfg->n_osc % (cfg->grid[0] * gy) != 0)
+            return fail(nullptr, DBSGYM_EINVAL, "GRID coupling needs n_osc to be whole z-planes of a gx*gy*gz grid");
+        if (gy == 2 * kRows) {
+            // lines of 16: fp32, mirror-symmetric contraction (even gx and populated gz), one CTA per environment
+            const int gzu = cfg->n_osc / (cfg->grid[0] * gy);
+            if (cfg->precision != DBSGYM_F32 || cfg->grid[0] % 2 != 0 || gzu % 2 != 0 || cfg->n_osc > 4096 ||
+                ((cfg->grid[0] / 2) * (gzu / 2)) % 8 != 0)
+                return fail(nullptr, DBSGYM_EINVAL, "GRID coupling with gy = 16 supports fp32, even gx and gz, a multiple of 8 "
+                            "fundamental lines and at most 4096 oscillators; use DENSE");
+        }
         if ((cfg->n_osc / kRows) % 32 != 0)
             return fail(nullptr, DBSGYM_EINVAL, "GRID coupling needs a multiple of 32 grid lines (n_osc %% 256 == 0); use DENSE");
     }
@@ -516,7 +532,7 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
         while (h->nthreads / want > 512) want *= 2;
         if (want > 1) {
             const int lines = Np / kRows;
-            if (want > 16 || lines % (want * 32) != 0 || cfg->grid[0] != 8 || h->f64 ||
+            if (want > 16 || lines % (want * 32) != 0 || cfg->grid[0] != 8 || cfg->grid[1] != kRows || h->f64 ||
                 (cfg->n_osc / (cfg->grid[0] * kRows)) % 2 != 0) {
                 fail(nullptr, DBSGYM_EINVAL, "n_osc %d needs cluster mode (%d CTAs per environment), which supports fp32, "
                      "8 x 8 x gz grids with even gz and at most 65536 oscillators", cfg->n_osc, want);
@@ -527,11 +543,22 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
             h->nthreads = lines / want;
         }
         // only the z-planes actually populated take part
-        h->cfg.grid[2] = cfg->n_osc / (cfg->grid[0] * kRows);
-        h->tab = h->cfg.grid[2] * cfg->grid[0] * kRows;
+        h->cfg.grid[2] = cfg->n_osc / (cfg->grid[0] * cfg->grid[1]);
+        h->tab = h->cfg.grid[2] * cfg->grid[0] * cfg->grid[1];
         // mirror symmetry in z and x needs even extents; DBSGYM_NO_SYM=1 keeps the plain Toeplitz kernel (A/B runs)
         const char* nosym = getenv("DBSGYM_NO_SYM");
         h->grid_sym = h->cfg.grid[2] % 2 == 0 && cfg->grid[0] % 2 == 0 && !(nosym && nosym[0] == '1');
+    }
+    if (h->cluster == 1) {                               // does one environment's state fit the shared memory of an SM?
+        int max_smem = 0;
+        cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+        const size_t need = step_smem_bytes(Np, cfg->coupling == DBSGYM_COUPLING_DENSE ? 0 : h->tab, h->nthreads, h->rb);
+        if (need > (size_t)max_smem) {
+            fail(nullptr, DBSGYM_EINVAL, "n_osc %d in %s needs %zu bytes of shared memory per environment, the device allows %d",
+                 cfg->n_osc, h->f64 ? "fp64" : "fp32", need, max_smem);
+            delete h;
+            return DBSGYM_EINVAL;
+        }
     }
     memset(&h->rspec, 0, sizeof(h->rspec));
     if (const char* e = getenv("DBSGYM_CTAS_PER_SM")) h->ctas_per_sm = atoi(e);
@@ -605,12 +632,12 @@ int dbsgym_set_coupling_grid(DbsGymHandle* h, const double* table) {
     if (!h || !table) return fail(h, DBSGYM_EINVAL, "null argument");
     if (h->cfg.coupling != DBSGYM_COUPLING_GRID) return fail(h, DBSGYM_ESTATE, "handle was created with DENSE coupling");
     CU(h, cudaSetDevice(h->cfg.device));
-    const int GX = h->cfg.grid[0], GZ = h->cfg.grid[2], NC = GZ * GX;
+    const int GX = h->cfg.grid[0], GZ = h->cfg.grid[2], GY = h->cfg.grid[1], NC = GZ * GX;
     const int n = h->f64 ? 2 : 4;                      // elements per 16 bytes
     std::vector<unsigned char> buf((size_t)h->tab * h->rb);
     for (int c = 0; c < NC; ++c)
-        for (int dy = 0; dy < kRows; ++dy) {
-            const double v = table[(size_t)c * kRows + dy];
+        for (int dy = 0; dy < GY; ++dy) {
+            const double v = table[(size_t)c * GY + dy];
             const size_t at = ((size_t)(dy / n) * NC + c) * n + dy % n;
             if (h->f64) reinterpret_cast<double*>(buf.data())[at] = v;
             else reinterpret_cast<float*>(buf.data())[at] = (float)v;

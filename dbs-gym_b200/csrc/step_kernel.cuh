@@ -48,7 +48,8 @@ enum { STATUS_MAX_STEPS = 1, STATUS_NAN = 2, STATUS_SCHEDULE = 4 };
 
 struct StepParams {
     int N, Np, B;
-    int GX, GZ;                    // GRID coupling: lines of 8 along y, GZ*GX lines
+    int GX, GZ;                    // GRID coupling: lines along y, GZ*GX lines
+    int GY;                        // oscillators per line: 8, or 16 (GEO = 3: two threads per line)
     int weighted_rec;
     int max_steps;
     double k_over_n;
@@ -538,6 +539,66 @@ __device__ __forceinline__ void couple_grid_sym_fixed(const float* __restrict__ 
     for (int r = 0; r < kRows; ++r) { as[r] = acc[r].x; ac[r] = acc[r].y; }
 }
 
+// ---- GRID_SYM with lines of 8*C oscillators (GEO = 3, cubic 16^3 grids): C threads per line ------------------
+// Thread (quad q, mirror image, chunk a) owns oscillators y = 8a .. 8a+7 of its line.  Per source block (zj,xj) the
+// whole sector row u[0 .. 8C-1] is combined once from the four table rows; the block between target chunk a and
+// source chunk a' is Toeplitz with coefficients u[|8(a-a') + i - j|].  The chunk index is uniform per warp
+// (tid = (a * quads + q) * 4 + image), so the switch over a does not diverge and every index is a compile-time constant.
+template <int C, int A>
+__device__ __forceinline__ void chunk_row_fma(const float (&u)[8 * C], const float* __restrict__ bline, float2 (&acc)[kRows]) {
+#pragma unroll
+    for (int ap = 0; ap < C; ++ap) {
+        float b[2 * kRows];
+        loadv<2 * kRows>(bline + ap * (2 * kRows), b);
+#pragma unroll
+        for (int yj = 0; yj < kRows; ++yj) {
+            const float2 scj = make_float2(b[2 * yj], b[2 * yj + 1]);
+#pragma unroll
+            for (int yi = 0; yi < kRows; ++yi) {
+                constexpr int dummy = 0; (void)dummy;
+                const int d = 8 * (A - ap) + yi - yj;
+                const float cf = u[d < 0 ? -d : d];
+                acc[yi] = __ffma2_rn(make_float2(cf, cf), scj, acc[yi]);
+            }
+        }
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void couple_grid_sym_chunks(const float* __restrict__ bp, const float* __restrict__ T,
+                                                       int GZ, int GX, int zq, int xq, int a, float pz, float px,
+                                                       float (&as)[kRows], float (&ac)[kRows]) {
+    const int NC = GZ * GX, HZ = GZ >> 1, HX = GX >> 1;
+    float2 acc[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) acc[r] = make_float2(0.f, 0.f);
+    const float4* T4 = reinterpret_cast<const float4*>(T);          // piece q of row c at T4[q * NC + c]
+    for (int zj = 0; zj < HZ; ++zj) {
+        const int dz0 = zq > zj ? zq - zj : zj - zq, dz1 = GZ - 1 - zq - zj;
+#pragma unroll 1
+        for (int xj = 0; xj < HX; ++xj) {
+            const int dx0 = xq > xj ? xq - xj : xj - xq, dx1 = GX - 1 - xq - xj;
+            const int c00 = dz0 * GX + dx0, c01 = dz0 * GX + dx1, c10 = dz1 * GX + dx0, c11 = dz1 * GX + dx1;
+            float u[8 * C];
+#pragma unroll
+            for (int q = 0; q < 2 * C; ++q) {
+                const float4 a00 = T4[q * NC + c00], a01 = T4[q * NC + c01], a10 = T4[q * NC + c10], a11 = T4[q * NC + c11];
+                u[4 * q + 0] = fmaf(pz, fmaf(px, a11.x, a10.x), fmaf(px, a01.x, a00.x));
+                u[4 * q + 1] = fmaf(pz, fmaf(px, a11.y, a10.y), fmaf(px, a01.y, a00.y));
+                u[4 * q + 2] = fmaf(pz, fmaf(px, a11.z, a10.z), fmaf(px, a01.z, a00.z));
+                u[4 * q + 3] = fmaf(pz, fmaf(px, a11.w, a10.w), fmaf(px, a01.w, a00.w));
+            }
+            const float* bline = bp + (zj * HX + xj) * C * (2 * kRows);
+            if (C == 1) chunk_row_fma<C, 0>(u, bline, acc);
+            else if (C == 2) {
+                if (a == 0) chunk_row_fma<C, 0>(u, bline, acc); else chunk_row_fma<C, (C > 1 ? 1 : 0)>(u, bline, acc);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) { as[r] = acc[r].x; ac[r] = acc[r].y; }
+}
+
 // ---- multi-worker mode (MW): precomputed sector coefficients ------------------------------------------
 // ncu on the kernel above (profiles/r01b_*): the contraction is bound by the shared-memory pipe, not by the FMA
 // pipe -- per (zj,xj) block a warp issues 8 LDS.128 for the four table rows (2 cycles each: the lanes of a quad
@@ -779,7 +840,10 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     static_assert(CL == 0 || (CPL == CPL_GRID_SYM && GEO == 2 && sizeof(real) == 4), "cluster mode: fp32 GRID_SYM, gx = 8");
     static_assert(!MW || (CPL == CPL_GRID_SYM && GEO == 1 && sizeof(real) == 4 && CL == 0 && kYParity && MAXT == EPC * kMwThreads),
                   "multi-worker mode: fp32 GRID_SYM on the 8 x 8 x 8 grid with y parity");
-    const int GZ = GEO == 1 ? 8 : p.GZ, GX = GEO >= 1 ? 8 : p.GX;      // GEO == 2: gx = 8 fixed, gz at run time
+    const int GZ = GEO == 1 ? 8 : p.GZ, GX = (GEO == 1 || GEO == 2) ? 8 : p.GX;      // GEO == 2: gx = 8 fixed, gz at run time
+    constexpr int CH = GEO == 3 ? 2 : 1;                                 // GEO == 3: lines of 16, two threads (chunks) per line
+    static_assert(GEO != 3 || (CPL == CPL_GRID_SYM && sizeof(real) == 4 && CL == 0 && EPC == 1), "GEO 3: fp32 GRID_SYM, one CTA");
+    const int GY = CH * kRows;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wid = MW ? (int)(threadIdx.x / kMwThreads) : 0;         // worker of this thread
     const int tid = MW ? (int)(threadIdx.x % kMwThreads) : (int)threadIdx.x, nt = MW ? kMwThreads : (int)blockDim.x;
@@ -788,7 +852,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     const int NC_ = CL ? p.cluster : 1;                   // CTAs per environment
     const int crank = CL ? (int)(blockIdx.x % NC_) : 0;   // rank of this CTA in its cluster (1-D grid, cluster dims (C,1,1))
     const int Nl = CL ? nt * kRows : Np;                  // oscillators whose state lives in THIS CTA's (worker's) shared memory
-    const int tab = (DENSE || CL || MW) ? 0 : GZ * GX * kRows;
+    const int tab = (DENSE || CL || MW) ? 0 : GZ * GX * GY;
     const int scsz = 2 * Np + kScPad;
 
     // shared memory of this CTA (MW: the coefficient table, then one such block per worker)
@@ -817,12 +881,17 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     // grid line owned by this thread.  GRID: line = tid.  GRID_SYM: the four mirror images (z,x), (z,X-x), (Z-z,x),
     // (Z-z,X-x) of fundamental line q are owned by the four lanes of a quad (q = tid / 4, image = tid & 3), in
     // multi-worker mode by lanes 8 apart (lane = 8 * image + q % 8: lanes with equal image are adjacent).
-    int zi = 0, xi = 0, zq = 0, xq = 0, img = 0, qline = 0;
+    int zi = 0, xi = 0, zq = 0, xq = 0, img = 0, qline = 0, chunk = 0;
     real sgn_x = real(1), sgn_z = real(1);
     if (SYM) {
         const int HX = GX >> 1;
         if (MW) mw_decode(tid, zq, xq, img);
-        else { const int q = tid_g >> 2; zq = q / HX; xq = q % HX; img = tid & 3; }
+        else if (CH > 1) {                                // tid = (chunk * quads + q) * 4 + image: the chunk is warp-uniform
+            const int nq4 = (GZ >> 1) * HX * 4;
+            chunk = tid / nq4;
+            const int r4 = tid % nq4, q = r4 >> 2;
+            zq = q / HX; xq = q % HX; img = r4 & 3;
+        } else { const int q = tid_g >> 2; zq = q / HX; xq = q % HX; img = tid & 3; }
         qline = zq * HX + xq;
         zi = (img & 2) ? GZ - 1 - zq : zq;
         xi = (img & 1) ? GX - 1 - xq : xq;
@@ -831,12 +900,12 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     } else if (!DENSE) {
         zi = tid / GX; xi = tid % GX;
     }
-    const int i0 = DENSE ? k0 : (zi * GX + xi) * kRows; // first oscillator index in the global arrays
+    const int i0 = DENSE ? k0 : (zi * GX + xi) * GY + chunk * kRows; // first oscillator index in the global arrays
     const unsigned wmask = __activemask();
     // operand slot written by this thread: plain = own line; GRID_SYM = sector img, line q
-    const int sec_stride = (GZ >> 1) * (GX >> 1) * 2 * kRows + (int)(16 / sizeof(real));
+    const int sec_stride = (GZ >> 1) * (GX >> 1) * CH * 2 * kRows + (int)(16 / sizeof(real));
     const int sc_sector = SYM ? img * sec_stride : 0;
-    const int sc_slot = SYM ? sc_sector + qline * 2 * kRows : 2 * k0;
+    const int sc_slot = SYM ? sc_sector + (qline * CH + chunk) * 2 * kRows : 2 * k0;
     constexpr int BMX = MW ? 8 : 1, BMZ = MW ? 16 : 2;     // lane bits of the x / z mirror image (quad_butterfly)
 
     if (MW) {                                             // the coefficient table, once per CTA
@@ -877,7 +946,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     }
     env_sync();
 
-    constexpr bool YPAR = kYParity && SYM && GEO >= 1 && sizeof(real) == 4;     // the paths that call couple_grid_sym_fixed
+    constexpr bool YPAR = kYParity && SYM && (GEO == 1 || GEO == 2) && sizeof(real) == 4;     // the paths that call couple_grid_sym_fixed
     const real kn = real(SYM ? (YPAR ? 0.125 : 0.25) * p.k_over_n : p.k_over_n);
     const real rtol = real(p.rtol), atol = real(p.atol);
     const real two_pi_r = real(kTwoPi);
@@ -1003,7 +1072,11 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                 real as[kRows], ac[kRows];
                 if (DENSE) couple_dense<real>(SC + pbuf * scsz, reinterpret_cast<const real*>(p.alpha), Np, i0, as, ac);
                 else if (SYM) {
-                    if (MW)
+                    if (GEO == 3)
+                        couple_grid_sym_chunks<CH>(reinterpret_cast<const float*>(SC + pbuf * scsz + sc_sector),
+                                                   reinterpret_cast<const float*>(T), GZ, GX, zq, xq, chunk, (float)sgn_z, (float)sgn_x,
+                                                   reinterpret_cast<float(&)[kRows]>(as), reinterpret_cast<float(&)[kRows]>(ac));
+                    else if (MW)
                         couple_sym_upre(reinterpret_cast<const float*>(SC + pbuf * scsz + sc_sector), U4, tid,
                                         reinterpret_cast<float(&)[kRows]>(as), reinterpret_cast<float(&)[kRows]>(ac));
                     else if (GEO == 1 && sizeof(real) == 4)

@@ -22,13 +22,18 @@ from dbsgym_b200.geometry import coupling_table, neuron_grid, ElectrodeModel
 from dbsgym_b200.schedule import StepSchedule, transient_grid
 
 out = []
-for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024):
-    N = 64 * gz
+# 8 x 8 x gz grids (lines of 8), then the cubic grids of SURVEY.md 8d config 5 that fit one CTA: the first 4 / 8 / 16
+# z-planes of the 16 x 16 x 16 grid (lines of 16, two threads per line)
+GRIDS = [(8, 8, gz) for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024)] + [(16, 16, gz) for gz in (4, 8, 16)]
+if os.environ.get("SWEEP_ONLY_CUBIC"):
+    GRIDS = [g for g in GRIDS if g[1] == 16]
+for gx, gy, gz in GRIDS:
+    N = gx * gy * gz
     B = 2097152 // N
-    coords, grid = neuron_grid(8, 8, gz, N, 0.1)
-    table = coupling_table(coords, grid, [8, 8, gz], "cos")
+    coords, grid = neuron_grid(gx, gy, gz, N, 0.1)
+    table = coupling_table(coords, grid, [gx, gy, gz], "cos")
     assert table is not None
-    eng = KuramotoEngine(B, N, [8, 8, gz], 2340, 0.52, precision="f32", coupling_table=table, device=LOCAL)
+    eng = KuramotoEngine(B, N, [gx, gy, gz], 2340, 0.52, precision="f32", coupling_table=table, device=LOCAL)
     tt = transient_grid(200.0, 0.05)
     sched = StepSchedule(400, tt[-1], 0.15, 0.75, 0.05)
     eng.set_schedule(sched); eng.set_reward("bbpow_action", 0.05)
@@ -36,7 +41,7 @@ for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024):
     # env.py:94's contact-index formula assumes a cubic grid; for the elongated sweep grids the contact is
     # simply the neuron nearest to the grid centre, with the reference's conductance law max(0, 1 - 0.1 d)
     from dbsgym_b200.geometry import distances_from
-    centre = int(np.argmin(np.abs(grid - np.array([4, 3, gz // 2])).sum(axis=1)))
+    centre = int(np.argmin(np.abs(grid - np.array([gx // 2, gy // 2 - 1, gz // 2])).sum(axis=1)))
     stim = np.tile(np.maximum(0.0, 1.0 - distances_from(grid * 0.1, [centre])[0]), (B, 1))
     w0 = np.abs(rng.normal(0.6, 0.4, (B, N))) + 0.02
     y0 = rng.normal(np.pi, 0.6, (B, N))
@@ -65,12 +70,15 @@ for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024):
         k_step, k_obs = (float(v) for v in tmax.cpu())
     rhs = (c["rhs_evals"] - eng.rhs_reused()) / (n_timed * B)       # executed evaluations (the reference's count is 32)
     ypar = bool(eng.lib.dbsgym_build_flags() & 1)          # own op count of the sector contraction, see bench.py
-    SYM_FLOP, SYM_LIN = ((148 if eng.step_variant(B) == 4 else 196 if ypar else 304) / 256.0), ((160 if ypar else 128) / 8.0)
-    out.append({"N": N, "grid": [8, 8, gz], "n_gpus": WORLD, "envs_per_gpu": B, "envs": B * WORLD, "step_kernel_ms": float(k_step), "obs_kernel_ms": float(k_obs),
+    variant = eng.step_variant(B)
+    SYM_FLOP, SYM_LIN = ((148 if variant == 4 else 196 if ypar else 304) / 256.0), ((160 if ypar else 128) / 8.0)
+    if variant == 7:          # lines of 16: per (zj,xj) block and thread 24 FFMA2 (sector row of 16) + 2 x 64 FFMA2, N^2/512 of those
+        SYM_FLOP, SYM_LIN = (4 * 152) / 512.0, 128 / 8.0
+    out.append({"N": N, "grid": [gx, gy, gz], "n_gpus": WORLD, "envs_per_gpu": B, "envs": B * WORLD, "step_kernel_ms": float(k_step), "obs_kernel_ms": float(k_obs),
                 "env_steps_per_s": WORLD * B / ((k_step + k_obs) * 1e-3), "oscillator_updates_per_s": WORLD * B * N * (c["accepted"] + c["rejected"]) / (n_timed * B) / ((k_step + k_obs) * 1e-3),
                 "rhs_per_env_step": rhs, "executed_tflops": WORLD * rhs * (SYM_FLOP * N * N + SYM_LIN * N) * B / (k_step * 1e-3) / 1e12,
                 "dense_equivalent_tflops": WORLD * rhs * 4 * N * N * B / (k_step * 1e-3) / 1e12,
-                "transient_s": t_tr, "status": c["status"], "ctas_per_env": max(1, N // 4096)})
+                "transient_s": t_tr, "status": c["status"], "ctas_per_env": 1 if gy == 16 else max(1, N // 4096), "variant": variant})
     if RANK == 0:
         print(json.dumps(out[-1]), flush=True)
     eng.close()

@@ -136,3 +136,60 @@ def test_multi_worker_kernel_equals_the_single_environment_kernel(monkeypatch, B
                 assert np.array_equal(u, v)
             else:
                 np.testing.assert_allclose(u, v, rtol=2e-6, atol=2e-6 if u.ndim == 2 and u.shape[1] == 512 else 3e-7)
+
+
+@pytest.mark.parametrize("N", [1024, 4096])
+def test_lines_of_16_cubic_grid_matches_dense_path(N):
+    """First N rows of the 16 x 16 x 16 grid (the cubic grids of SURVEY.md 8d config 5): the structured GRID_SYM kernel
+    with two threads per 16-oscillator line against the generic DENSE kernel on the same alpha = cos(distance), in fp32
+    and against fp64 DENSE; steps and a transient with rejections."""
+    from dbsgym_b200.engine import KuramotoEngine
+    from dbsgym_b200.geometry import coupling_rows, coupling_table, distances_from, neuron_grid
+    from dbsgym_b200.schedule import StepSchedule, transient_grid
+    B = 3
+    coords, grid = neuron_grid(16, 16, 16, N, 0.1)
+    table = coupling_table(coords, grid, [16, 16, 16], "cos")
+    assert table is not None and table.size == N
+    alpha = coupling_rows(coords, np.arange(N), "cos")
+    rng = np.random.default_rng(N)
+    centre = int(np.argmin(np.abs(grid - np.array([8, 7, grid[:, 2].max() // 2])).sum(axis=1)))
+    stim = np.tile(np.maximum(0.0, 1.0 - distances_from(grid * 0.1, [centre])[0]), (B, 1))
+    w0 = np.abs(rng.normal(0.6, 0.4, (B, N))) + 0.02
+    y0 = rng.normal(np.pi, 0.6, (B, N)) + 12.0
+    win = rng.uniform(-0.2, 0.2, (B, 2340))
+    acts = rng.uniform(-1, 1, (2, B)).astype(np.float32)
+    tt = transient_grid(200.0, 0.05)
+    res = {}
+    engines = [("grid", dict(coupling_table=table), "f32"), ("dense", dict(alpha=alpha), "f32")]
+    if N <= 2048:                                     # (the fp64 DENSE kernel keeps 11 N doubles in shared memory)
+        engines.append(("dense64", dict(alpha=alpha), "f64"))
+    for name, kw, prec in engines:
+        eng = KuramotoEngine(B, N, [16, 16, 16], 2340, 0.52, precision=prec, **kw)
+        eng.set_schedule(StepSchedule(80, tt[-1], 0.15, 0.75, 0.05)); eng.set_reward("bbpow_action", 0.05)
+        eng.set_recording(True)
+        eng.set_env_params(None, w0=w0, stim=stim, rec=stim, y0=y0)
+        eng.set_window(win); eng.set_episode(None, step_idx=0, episode_len=1000)
+        if name == "grid":
+            assert eng.step_variant() == 7
+        eng.counters(reset=True)
+        out = []
+        for a in acts:
+            obs, rew, done = eng.step_host(a)
+            out.append((eng.state().copy(), eng.lfp()[1].copy(), rew.copy()))
+        if N == 1024:
+            eng.transient(np.arange(0.0, 125.0, 0.05))
+            out.append((eng.state().copy(), eng.obs_host().copy()))
+        res[name] = (out, eng.counters())
+        eng.close()
+    (g, cg), (d, cd) = res["grid"], res["dense"]
+    d64, c64 = res.get("dense64", res["dense"])
+    assert cg == cd == c64 and cg["status"] == 0
+    for k, (x, y, z) in enumerate(zip(g, d, d64)):
+        for u, v, w in zip(x, y, z):
+            if k < len(acts):                         # single steps: fp32 rounding only
+                tol = 5e-5 if u.ndim == 2 and u.shape[1] == N else 5e-6
+            else:                                     # 125 time units of free-running transient: fp32 rounding differences
+                tol = 2e-2 if u.shape[1] == N else 2e-3   # have grown (tests/test_gpu_episode_stats.py measures the horizon)
+            np.testing.assert_allclose(u, w, rtol=2e-5, atol=tol)          # structured fp32 vs fp64 dense
+            if k < len(acts):                         # (over the long transient the sequential fp32 sums of the DENSE
+                np.testing.assert_allclose(u, v, rtol=2e-5, atol=tol)      #  kernel drift further from fp64 than the structured kernel does)
