@@ -298,6 +298,11 @@ cudaError_t launch_step_m(DbsGymHandle* h, const StepParams& p, cudaStream_t s) 
         if (t <= 256) return launch_step_t<real, CPL, 256, 3>(h, p, s);
         return launch_step_t<real, CPL, 512, 3>(h, p, s);
     }
+    if constexpr (CPL == CPL_GRID_SYM && sizeof(real) == 4) if (p.GY == 4 * kRows) {   // lines of 32 (cubic 32^3 grids)
+        if (t <= 128) return launch_step_t<real, CPL, 128, 4>(h, p, s);
+        if (t <= 256) return launch_step_t<real, CPL, 256, 4>(h, p, s);
+        return launch_step_t<real, CPL, 512, 4>(h, p, s);
+    }
     if constexpr (CPL == CPL_GRID_SYM && sizeof(real) == 4) {
         static const bool no_geo1 = getenv("DBSGYM_NO_GEO1") != nullptr;        // A/B switch for tuning runs
         if (t == 64 && p.GZ == 8 && p.GX == 8 && !no_geo1) {
@@ -321,9 +326,9 @@ cudaError_t launch_step_m(DbsGymHandle* h, const StepParams& p, cudaStream_t s) 
 }
 
 // cluster mode: one environment = a cluster of h->cluster CTAs (cudaLaunchKernelEx + cluster dimension attribute)
-template <int MAXT>
+template <int MAXT, int GEO = 2>
 cudaError_t launch_step_cluster_t(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
-    auto kern = step_kernel<float, CPL_GRID_SYM, MAXT, 2, 1>;
+    auto kern = step_kernel<float, CPL_GRID_SYM, MAXT, GEO, 1>;
     const size_t smem = step_smem_bytes_cluster(h->nthreads, sizeof(float));
     cudaError_t e = cudaSuccess;
     if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -343,6 +348,8 @@ cudaError_t launch_step_cluster_t(DbsGymHandle* h, const StepParams& p, cudaStre
 
 cudaError_t launch_step_cluster(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
     const int t = h->nthreads;
+    if (p.GY == 2 * kRows) return t <= 256 ? launch_step_cluster_t<256, 3>(h, p, s) : launch_step_cluster_t<512, 3>(h, p, s);
+    if (p.GY == 4 * kRows) return t <= 256 ? launch_step_cluster_t<256, 4>(h, p, s) : launch_step_cluster_t<512, 4>(h, p, s);
     if (t <= 64) return launch_step_cluster_t<64>(h, p, s);
     if (t <= 128) return launch_step_cluster_t<128>(h, p, s);
     if (t <= 256) return launch_step_cluster_t<256>(h, p, s);
@@ -454,6 +461,7 @@ int dbsgym_step_variant(const DbsGymHandle* h, int32_t n_envs) {
     if (!h->grid_sym) return 0;
     if (h->f64) return 2;
     if (h->cfg.grid[1] == 2 * kRows) return 7;
+    if (h->cfg.grid[1] == 4 * kRows) return 8;
     const bool geo1 = h->nthreads == 64 && h->cfg.grid[2] == 8 && h->cfg.grid[0] == 8 && !getenv("DBSGYM_NO_GEO1");
     if (geo1) {
         const bool mw = kYParity && (h->mw_mode == 1 || (h->mw_mode < 0 && n_envs >= kMwEnvs * h->num_sms));
@@ -493,18 +501,18 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
         return fail(nullptr, DBSGYM_EINVAL, "n_osc %d too large for DENSE coupling (max 8192)", cfg->n_osc);
     if (cfg->coupling == DBSGYM_COUPLING_GRID) {
         const int gy = cfg->grid[1];
-        if (gy != kRows && gy != 2 * kRows)
-            return fail(nullptr, DBSGYM_EINVAL, "GRID coupling needs grid[1] (gy) == %d or %d, got %d", kRows, 2 * kRows, gy);
+        if (gy != kRows && gy != 2 * kRows && gy != 4 * kRows)
+            return fail(nullptr, DBSGYM_EINVAL, "GRID coupling needs grid[1] (gy) == %d, %d or %d, got %d", kRows, 2 * kRows, 4 * kRows, gy);
         if (cfg->grid[0] <= 0 || cfg->grid[2] <= 0 || cfg->n_osc % kRows != 0 ||
             cfg->n_osc > cfg->grid[0] * gy * cfg->grid[2] || cfg->n_osc % (cfg->grid[0] * gy) != 0)
             return fail(nullptr, DBSGYM_EINVAL, "GRID coupling needs n_osc to be whole z-planes of a gx*gy*gz grid");
-        if (gy == 2 * kRows) {
-            // lines of 16: fp32, mirror-symmetric contraction (even gx and populated gz), one CTA per environment
+        if (gy != kRows) {
+            // lines of 16 / 32: fp32, mirror-symmetric contraction (even gx and populated gz); the chunk index of a thread
+            // must be uniform per warp: a multiple of 8 fundamental (quarter-grid) lines
             const int gzu = cfg->n_osc / (cfg->grid[0] * gy);
-            if (cfg->precision != DBSGYM_F32 || cfg->grid[0] % 2 != 0 || gzu % 2 != 0 || cfg->n_osc > 4096 ||
-                ((cfg->grid[0] / 2) * (gzu / 2)) % 8 != 0)
-                return fail(nullptr, DBSGYM_EINVAL, "GRID coupling with gy = 16 supports fp32, even gx and gz, a multiple of 8 "
-                            "fundamental lines and at most 4096 oscillators; use DENSE");
+            if (cfg->precision != DBSGYM_F32 || cfg->grid[0] % 2 != 0 || gzu % 2 != 0 || ((cfg->grid[0] / 2) * (gzu / 2)) % 8 != 0)
+                return fail(nullptr, DBSGYM_EINVAL, "GRID coupling with gy = %d supports fp32, even gx and gz and a multiple of 8 "
+                            "fundamental lines; use DENSE", gy);
         }
         if ((cfg->n_osc / kRows) % 32 != 0)
             return fail(nullptr, DBSGYM_EINVAL, "GRID coupling needs a multiple of 32 grid lines (n_osc %% 256 == 0); use DENSE");
@@ -532,10 +540,10 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
         while (h->nthreads / want > 512) want *= 2;
         if (want > 1) {
             const int lines = Np / kRows;
-            if (want > 16 || lines % (want * 32) != 0 || cfg->grid[0] != 8 || cfg->grid[1] != kRows || h->f64 ||
-                (cfg->n_osc / (cfg->grid[0] * kRows)) % 2 != 0) {
+            if (want > 16 || lines % (want * 32) != 0 || (cfg->grid[1] == kRows && cfg->grid[0] != 8) || h->f64 ||
+                (cfg->n_osc / (cfg->grid[0] * cfg->grid[1])) % 2 != 0) {
                 fail(nullptr, DBSGYM_EINVAL, "n_osc %d needs cluster mode (%d CTAs per environment), which supports fp32, "
-                     "8 x 8 x gz grids with even gz and at most 65536 oscillators", cfg->n_osc, want);
+                     "8 x 8 x gz grids or lines of 16 / 32, even gz and at most 65536 oscillators", cfg->n_osc, want);
                 delete h;
                 return DBSGYM_EINVAL;
             }

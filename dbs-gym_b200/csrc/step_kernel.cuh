@@ -544,18 +544,23 @@ __device__ __forceinline__ void couple_grid_sym_fixed(const float* __restrict__ 
 // whole sector row u[0 .. 8C-1] is combined once from the four table rows; the block between target chunk a and
 // source chunk a' is Toeplitz with coefficients u[|8(a-a') + i - j|].  The chunk index is uniform per warp
 // (tid = (a * quads + q) * 4 + image), so the switch over a does not diverge and every index is a compile-time constant.
-template <int C, int A>
+template <int C, int A, bool GL>
 __device__ __forceinline__ void chunk_row_fma(const float (&u)[8 * C], const float* __restrict__ bline, float2 (&acc)[kRows]) {
 #pragma unroll
     for (int ap = 0; ap < C; ++ap) {
         float b[2 * kRows];
-        loadv<2 * kRows>(bline + ap * (2 * kRows), b);
+        if (GL) {                                     // cluster mode: the operand lives in global memory (L2)
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const float4 v = __ldcg(reinterpret_cast<const float4*>(bline + ap * (2 * kRows)) + q4);
+                b[4 * q4] = v.x; b[4 * q4 + 1] = v.y; b[4 * q4 + 2] = v.z; b[4 * q4 + 3] = v.w;
+            }
+        } else loadv<2 * kRows>(bline + ap * (2 * kRows), b);
 #pragma unroll
         for (int yj = 0; yj < kRows; ++yj) {
             const float2 scj = make_float2(b[2 * yj], b[2 * yj + 1]);
 #pragma unroll
             for (int yi = 0; yi < kRows; ++yi) {
-                constexpr int dummy = 0; (void)dummy;
                 const int d = 8 * (A - ap) + yi - yj;
                 const float cf = u[d < 0 ? -d : d];
                 acc[yi] = __ffma2_rn(make_float2(cf, cf), scj, acc[yi]);
@@ -564,7 +569,7 @@ __device__ __forceinline__ void chunk_row_fma(const float (&u)[8 * C], const flo
     }
 }
 
-template <int C>
+template <int C, bool GL>
 __device__ __forceinline__ void couple_grid_sym_chunks(const float* __restrict__ bp, const float* __restrict__ T,
                                                        int GZ, int GX, int zq, int xq, int a, float pz, float px,
                                                        float (&as)[kRows], float (&ac)[kRows]) {
@@ -572,7 +577,8 @@ __device__ __forceinline__ void couple_grid_sym_chunks(const float* __restrict__
     float2 acc[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) acc[r] = make_float2(0.f, 0.f);
-    const float4* T4 = reinterpret_cast<const float4*>(T);          // piece q of row c at T4[q * NC + c]
+    const float* Tp = T;                                            // piece q of row c at float4 index q * NC + c
+#pragma unroll 1
     for (int zj = 0; zj < HZ; ++zj) {
         const int dz0 = zq > zj ? zq - zj : zj - zq, dz1 = GZ - 1 - zq - zj;
 #pragma unroll 1
@@ -582,16 +588,25 @@ __device__ __forceinline__ void couple_grid_sym_chunks(const float* __restrict__
             float u[8 * C];
 #pragma unroll
             for (int q = 0; q < 2 * C; ++q) {
-                const float4 a00 = T4[q * NC + c00], a01 = T4[q * NC + c01], a10 = T4[q * NC + c10], a11 = T4[q * NC + c11];
+                const float4 a00 = ld_table(Tp + (q * NC + c00) * 4, GL), a01 = ld_table(Tp + (q * NC + c01) * 4, GL);
+                const float4 a10 = ld_table(Tp + (q * NC + c10) * 4, GL), a11 = ld_table(Tp + (q * NC + c11) * 4, GL);
                 u[4 * q + 0] = fmaf(pz, fmaf(px, a11.x, a10.x), fmaf(px, a01.x, a00.x));
                 u[4 * q + 1] = fmaf(pz, fmaf(px, a11.y, a10.y), fmaf(px, a01.y, a00.y));
                 u[4 * q + 2] = fmaf(pz, fmaf(px, a11.z, a10.z), fmaf(px, a01.z, a00.z));
                 u[4 * q + 3] = fmaf(pz, fmaf(px, a11.w, a10.w), fmaf(px, a01.w, a00.w));
             }
             const float* bline = bp + (zj * HX + xj) * C * (2 * kRows);
-            if (C == 1) chunk_row_fma<C, 0>(u, bline, acc);
-            else if (C == 2) {
-                if (a == 0) chunk_row_fma<C, 0>(u, bline, acc); else chunk_row_fma<C, (C > 1 ? 1 : 0)>(u, bline, acc);
+            if constexpr (C == 1) chunk_row_fma<C, 0, GL>(u, bline, acc);
+            else if constexpr (C == 2) {
+                if (a == 0) chunk_row_fma<C, 0, GL>(u, bline, acc); else chunk_row_fma<C, 1, GL>(u, bline, acc);
+            } else {
+                static_assert(C == 4, "lines of 8, 16 or 32");
+                switch (a) {
+                    case 0: chunk_row_fma<C, 0, GL>(u, bline, acc); break;
+                    case 1: chunk_row_fma<C, 1, GL>(u, bline, acc); break;
+                    case 2: chunk_row_fma<C, 2, GL>(u, bline, acc); break;
+                    default: chunk_row_fma<C, 3, GL>(u, bline, acc); break;
+                }
             }
         }
     }
@@ -837,12 +852,13 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     constexpr bool DENSE = CPL == CPL_DENSE;
     constexpr bool SYM = CPL == CPL_GRID_SYM;
     constexpr bool MW = EPC > 1;       // multi-worker mode: EPC environments per CTA, one 64-thread worker each
-    static_assert(CL == 0 || (CPL == CPL_GRID_SYM && GEO == 2 && sizeof(real) == 4), "cluster mode: fp32 GRID_SYM, gx = 8");
+    static_assert(CL == 0 || (CPL == CPL_GRID_SYM && (GEO == 2 || GEO == 3 || GEO == 4) && sizeof(real) == 4),
+                  "cluster mode: fp32 GRID_SYM with gx = 8 or with lines of 16 / 32");
     static_assert(!MW || (CPL == CPL_GRID_SYM && GEO == 1 && sizeof(real) == 4 && CL == 0 && kYParity && MAXT == EPC * kMwThreads),
                   "multi-worker mode: fp32 GRID_SYM on the 8 x 8 x 8 grid with y parity");
     const int GZ = GEO == 1 ? 8 : p.GZ, GX = (GEO == 1 || GEO == 2) ? 8 : p.GX;      // GEO == 2: gx = 8 fixed, gz at run time
-    constexpr int CH = GEO == 3 ? 2 : 1;                                 // GEO == 3: lines of 16, two threads (chunks) per line
-    static_assert(GEO != 3 || (CPL == CPL_GRID_SYM && sizeof(real) == 4 && CL == 0 && EPC == 1), "GEO 3: fp32 GRID_SYM, one CTA");
+    constexpr int CH = GEO == 3 ? 2 : GEO == 4 ? 4 : 1;                  // GEO == 3 / 4: lines of 16 / 32, 2 / 4 threads (chunks) per line
+    static_assert((GEO != 3 && GEO != 4) || (CPL == CPL_GRID_SYM && sizeof(real) == 4 && EPC == 1), "GEO 3 / 4: fp32 GRID_SYM");
     const int GY = CH * kRows;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wid = MW ? (int)(threadIdx.x / kMwThreads) : 0;         // worker of this thread
@@ -886,10 +902,10 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     if (SYM) {
         const int HX = GX >> 1;
         if (MW) mw_decode(tid, zq, xq, img);
-        else if (CH > 1) {                                // tid = (chunk * quads + q) * 4 + image: the chunk is warp-uniform
+        else if (CH > 1) {                                // thread (chunk * quads + q) * 4 + image of the environment: the chunk is warp-uniform
             const int nq4 = (GZ >> 1) * HX * 4;
-            chunk = tid / nq4;
-            const int r4 = tid % nq4, q = r4 >> 2;
+            chunk = tid_g / nq4;
+            const int r4 = tid_g % nq4, q = r4 >> 2;
             zq = q / HX; xq = q % HX; img = r4 & 3;
         } else { const int q = tid_g >> 2; zq = q / HX; xq = q % HX; img = tid & 3; }
         qline = zq * HX + xq;
@@ -1072,8 +1088,8 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                 real as[kRows], ac[kRows];
                 if (DENSE) couple_dense<real>(SC + pbuf * scsz, reinterpret_cast<const real*>(p.alpha), Np, i0, as, ac);
                 else if (SYM) {
-                    if (GEO == 3)
-                        couple_grid_sym_chunks<CH>(reinterpret_cast<const float*>(SC + pbuf * scsz + sc_sector),
+                    if (GEO == 3 || GEO == 4)
+                        couple_grid_sym_chunks<CH, CL != 0>(reinterpret_cast<const float*>(SC + pbuf * scsz + sc_sector),
                                                    reinterpret_cast<const float*>(T), GZ, GX, zq, xq, chunk, (float)sgn_z, (float)sgn_x,
                                                    reinterpret_cast<float(&)[kRows]>(as), reinterpret_cast<float(&)[kRows]>(ac));
                     else if (MW)

@@ -47,15 +47,15 @@ def coupling_rows(neur_coords, rows, spatial_kernel, wavelet_amp=1.0, wavelet_st
 
 def grid_structure(neur_grid, grid_size):
     """Return (gx, gy, gz_used) when ``neur_grid`` is the un-shuffled regular grid in whole
-    z-planes with gy == LINE or 2 * LINE (the layouts the GRID kernels handle), else None."""
+    z-planes with gy == LINE, 2 * LINE or 4 * LINE (the layouts the GRID kernels handle), else None."""
     g = np.asarray(neur_grid)
     gx, gy, gz = (int(v) for v in grid_size)
     n = g.shape[0]
-    if gy not in (LINE, 2 * LINE) or n % (gx * gy) != 0 or n > gx * gy * gz or (n // LINE) % 32 != 0:
-        return None            # the GRID kernels want whole warps of 8-oscillator (half-)lines (n % 256 == 0)
-    if gy == 2 * LINE:         # lines of 16 (cubic 16^3 grids): fp32 mirror-symmetric kernel, one CTA per environment
+    if gy not in (LINE, 2 * LINE, 4 * LINE) or n % (gx * gy) != 0 or n > gx * gy * gz or (n // LINE) % 32 != 0:
+        return None            # the GRID kernels want whole warps of 8-oscillator (partial) lines (n % 256 == 0)
+    if gy != LINE:             # lines of 16 / 32 (cubic 16^3 / 32^3 grids): fp32 mirror-symmetric kernel
         gzu = n // (gx * gy)
-        if gx % 2 or gzu % 2 or n > 4096 or ((gx // 2) * (gzu // 2)) % 8:
+        if gx % 2 or gzu % 2 or ((gx // 2) * (gzu // 2)) % 8 or n > 65536:
             return None
     _, ref = neuron_grid(gx, gy, gz, n, 1.0)
     if g.shape != ref.shape or not np.array_equal(g, ref):

@@ -92,7 +92,7 @@ int  dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out);
 /* which step-kernel variant a launch over n_envs environments of this handle uses (for op counts in benchmarks):
  * 0 plain Toeplitz GRID, 1 DENSE, 2 parity-sector GRID_SYM (run-time extents), 3 GRID_SYM unrolled for the
  * 8 x 8 x 8 grid (one CTA per environment), 4 multi-worker (8 environments per CTA sharing precomputed sector
- * coefficients), 5 cluster mode (N > 4096), 6 GRID_SYM with gx = 8 fixed, 7 GRID_SYM with lines of 16 (gy = 16);
+ * coefficients), 5 cluster mode (N > 4096), 6 GRID_SYM with gx = 8 fixed, 7 / 8 GRID_SYM with lines of 16 / 32 (gy = 16 / 32);
  * negative = error code */
 int  dbsgym_step_variant(const DbsGymHandle* h, int32_t n_envs);
 void dbsgym_destroy(DbsGymHandle* h);

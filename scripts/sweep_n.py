@@ -24,9 +24,10 @@ from dbsgym_b200.schedule import StepSchedule, transient_grid
 out = []
 # 8 x 8 x gz grids (lines of 8), then the cubic grids of SURVEY.md 8d config 5 that fit one CTA: the first 4 / 8 / 16
 # z-planes of the 16 x 16 x 16 grid (lines of 16, two threads per line)
-GRIDS = [(8, 8, gz) for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024)] + [(16, 16, gz) for gz in (4, 8, 16)]
+GRIDS = ([(8, 8, gz) for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024)] + [(16, 16, gz) for gz in (4, 8, 16)] +
+         [(32, 32, gz) for gz in (8, 16, 32)])           # 32^3: lines of 32, four threads per line, cluster mode
 if os.environ.get("SWEEP_ONLY_CUBIC"):
-    GRIDS = [g for g in GRIDS if g[1] == 16]
+    GRIDS = [g for g in GRIDS if g[1] != 8]
 for gx, gy, gz in GRIDS:
     N = gx * gy * gz
     B = 2097152 // N
@@ -54,7 +55,7 @@ for gx, gy, gz in GRIDS:
     rew = torch.empty(B, dtype=torch.float32, device=dev); done = torch.empty(B, dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     eng.set_timing(True); eng.counters(reset=True)
-    for i in range(5 if N <= 8192 else 2):
+    for i in range(5 if N <= 8192 else 2):     # (warm-up)
         eng.step_device(act[i].data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), st)
     torch.cuda.synchronize(); eng.counters(reset=True)
     ms = []
@@ -72,13 +73,13 @@ for gx, gy, gz in GRIDS:
     ypar = bool(eng.lib.dbsgym_build_flags() & 1)          # own op count of the sector contraction, see bench.py
     variant = eng.step_variant(B)
     SYM_FLOP, SYM_LIN = ((148 if variant == 4 else 196 if ypar else 304) / 256.0), ((160 if ypar else 128) / 8.0)
-    if variant == 7:          # lines of 16: per (zj,xj) block and thread 24 FFMA2 (sector row of 16) + 2 x 64 FFMA2, N^2/512 of those
-        SYM_FLOP, SYM_LIN = (4 * 152) / 512.0, 128 / 8.0
+    if gy != 8:               # lines of 16 / 32: per (zj,xj) block and thread 24 / 48 FFMA2 (sector row) + 2 / 4 x 64 FFMA2,
+        SYM_FLOP, SYM_LIN = (4 * 152) / 512.0, 128 / 8.0          # N^2/512 resp. N^2/1024 of those: 1.1875 N^2 flop per RHS
     out.append({"N": N, "grid": [gx, gy, gz], "n_gpus": WORLD, "envs_per_gpu": B, "envs": B * WORLD, "step_kernel_ms": float(k_step), "obs_kernel_ms": float(k_obs),
                 "env_steps_per_s": WORLD * B / ((k_step + k_obs) * 1e-3), "oscillator_updates_per_s": WORLD * B * N * (c["accepted"] + c["rejected"]) / (n_timed * B) / ((k_step + k_obs) * 1e-3),
                 "rhs_per_env_step": rhs, "executed_tflops": WORLD * rhs * (SYM_FLOP * N * N + SYM_LIN * N) * B / (k_step * 1e-3) / 1e12,
                 "dense_equivalent_tflops": WORLD * rhs * 4 * N * N * B / (k_step * 1e-3) / 1e12,
-                "transient_s": t_tr, "status": c["status"], "ctas_per_env": 1 if gy == 16 else max(1, N // 4096), "variant": variant})
+                "transient_s": t_tr, "status": c["status"], "ctas_per_env": max(1, N // 4096), "variant": variant})
     if RANK == 0:
         print(json.dumps(out[-1]), flush=True)
     eng.close()
