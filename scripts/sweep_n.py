@@ -25,7 +25,7 @@ out = []
 # 8 x 8 x gz grids (lines of 8), then the cubic grids of SURVEY.md 8d config 5 that fit one CTA: the first 4 / 8 / 16
 # z-planes of the 16 x 16 x 16 grid (lines of 16, two threads per line)
 GRIDS = ([(8, 8, gz) for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024)] + [(16, 16, gz) for gz in (4, 8, 16)] +
-         [(32, 32, gz) for gz in (8, 16, 32)])           # 32^3: lines of 32, four threads per line, cluster mode
+         [(32, 32, gz) for gz in (8, 16, 32, 64)])       # 32^3 (and 32 x 32 x 64 for N = 65536): lines of 32, cluster mode
 if os.environ.get("SWEEP_ONLY_CUBIC"):
     GRIDS = [g for g in GRIDS if g[1] != 8]
 for gx, gy, gz in GRIDS:
