@@ -93,6 +93,7 @@ struct StepParams {
 };
 
 constexpr int kTailBins = 32;      // at most one rfft bin per lane of the tail warp
+constexpr int kClTileFloats = 8192;   // cluster mode: 32 KB operand tile staged in shared memory per CTA
 constexpr int kClSlots = 2 * 16;   // doubles per CTA and parity in cl_scratch (= 2 * kSampleBatch)
 
 __device__ __forceinline__ void cluster_barrier() {
@@ -463,18 +464,16 @@ __device__ __forceinline__ float4 ld_table(const float* p, bool gl) {
     return gl ? __ldg(reinterpret_cast<const float4*>(p)) : *reinterpret_cast<const float4*>(p);
 }
 
-template <int HZ, int HX, bool GL = false>   // HZ == 0: z half-planes given at run time (hz_rt); the x loop is always unrolled.
-                                             // GL: table and operand live in global memory (cluster mode)
-__device__ __forceinline__ void couple_grid_sym_fixed(const float* __restrict__ bp, const float* __restrict__ T,
-                                                      int zq, int xq, float pz, float px, int hz_rt,
-                                                      float (&as)[kRows], float (&ac)[kRows]) {
+template <int HZ, int HX, bool GL = false, bool GLO = GL>   // HZ == 0: z half-planes given at run time (hz_rt); the x loop is
+                                             // always unrolled.  GL: the table lives in global memory (cluster mode); GLO: the operand too
+// accumulates the source planes zj in [z0, z1) (HZ > 0: all of them) into acc
+__device__ __forceinline__ void couple_grid_sym_fixed_acc(const float* __restrict__ bp, const float* __restrict__ T,
+                                                          int zq, int xq, float pz, float px, int hz_rt, int z0, int z1,
+                                                          float2 (&acc)[kRows]) {
     const int hz = HZ > 0 ? HZ : hz_rt;
     const int GZ = 2 * hz;
     constexpr int GX = 2 * HX;
     const int NC = GZ * GX;
-    float2 acc[kRows];
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) acc[r] = make_float2(0.f, 0.f);
     const float2 px2 = make_float2(px, px), pz2 = make_float2(pz, pz);
     const float* tz1 = T + ((GZ - 1 - zq) * GX + (GX - 1 - xq)) * 4;      // row (dz1, dx1) of block (0,0); moves by immediates
     auto zplane = [&](int zj) {
@@ -494,7 +493,7 @@ __device__ __forceinline__ void couple_grid_sym_fixed(const float* __restrict__ 
             r.a11l = ld_table(t11, GL); r.a11h = ld_table(t11 + NC * 4, GL);
             float u[kRows], b[2 * kRows];
             sym_combine(r, px2, pz2, u);
-            if (GL) {
+            if (GLO) {
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     const float4 v = __ldcg(reinterpret_cast<const float4*>(bp + (zj * HX + xj) * (2 * kRows)) + q4);
@@ -533,8 +532,18 @@ __device__ __forceinline__ void couple_grid_sym_fixed(const float* __restrict__ 
         for (int zj = 0; zj < HZ; ++zj) zplane(zj);
     } else {
 #pragma unroll 1
-        for (int zj = 0; zj < hz; ++zj) zplane(zj);
+        for (int zj = z0; zj < z1; ++zj) zplane(zj);
     }
+}
+
+template <int HZ, int HX, bool GL = false>
+__device__ __forceinline__ void couple_grid_sym_fixed(const float* __restrict__ bp, const float* __restrict__ T,
+                                                      int zq, int xq, float pz, float px, int hz_rt,
+                                                      float (&as)[kRows], float (&ac)[kRows]) {
+    float2 acc[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) acc[r] = make_float2(0.f, 0.f);
+    couple_grid_sym_fixed_acc<HZ, HX, GL, GL>(bp, T, zq, xq, pz, px, hz_rt, 0, HZ > 0 ? HZ : hz_rt, acc);
 #pragma unroll
     for (int r = 0; r < kRows; ++r) { as[r] = acc[r].x; ac[r] = acc[r].y; }
 }
@@ -569,17 +578,14 @@ __device__ __forceinline__ void chunk_row_fma(const float (&u)[8 * C], const flo
     }
 }
 
-template <int C, bool GL>
-__device__ __forceinline__ void couple_grid_sym_chunks(const float* __restrict__ bp, const float* __restrict__ T,
-                                                       int GZ, int GX, int zq, int xq, int a, float pz, float px,
-                                                       float (&as)[kRows], float (&ac)[kRows]) {
-    const int NC = GZ * GX, HZ = GZ >> 1, HX = GX >> 1;
-    float2 acc[kRows];
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) acc[r] = make_float2(0.f, 0.f);
+template <int C, bool GL, bool GLO>      // GL: table in global memory; GLO: operand in global memory
+__device__ __forceinline__ void couple_grid_sym_chunks_acc(const float* __restrict__ bp, const float* __restrict__ T,
+                                                           int GZ, int GX, int zq, int xq, int a, float pz, float px,
+                                                           int z0, int z1, float2 (&acc)[kRows]) {
+    const int NC = GZ * GX, HX = GX >> 1;
     const float* Tp = T;                                            // piece q of row c at float4 index q * NC + c
 #pragma unroll 1
-    for (int zj = 0; zj < HZ; ++zj) {
+    for (int zj = z0; zj < z1; ++zj) {
         const int dz0 = zq > zj ? zq - zj : zj - zq, dz1 = GZ - 1 - zq - zj;
 #pragma unroll 1
         for (int xj = 0; xj < HX; ++xj) {
@@ -596,20 +602,30 @@ __device__ __forceinline__ void couple_grid_sym_chunks(const float* __restrict__
                 u[4 * q + 3] = fmaf(pz, fmaf(px, a11.w, a10.w), fmaf(px, a01.w, a00.w));
             }
             const float* bline = bp + (zj * HX + xj) * C * (2 * kRows);
-            if constexpr (C == 1) chunk_row_fma<C, 0, GL>(u, bline, acc);
+            if constexpr (C == 1) chunk_row_fma<C, 0, GLO>(u, bline, acc);
             else if constexpr (C == 2) {
-                if (a == 0) chunk_row_fma<C, 0, GL>(u, bline, acc); else chunk_row_fma<C, 1, GL>(u, bline, acc);
+                if (a == 0) chunk_row_fma<C, 0, GLO>(u, bline, acc); else chunk_row_fma<C, 1, GLO>(u, bline, acc);
             } else {
                 static_assert(C == 4, "lines of 8, 16 or 32");
                 switch (a) {
-                    case 0: chunk_row_fma<C, 0, GL>(u, bline, acc); break;
-                    case 1: chunk_row_fma<C, 1, GL>(u, bline, acc); break;
-                    case 2: chunk_row_fma<C, 2, GL>(u, bline, acc); break;
-                    default: chunk_row_fma<C, 3, GL>(u, bline, acc); break;
+                    case 0: chunk_row_fma<C, 0, GLO>(u, bline, acc); break;
+                    case 1: chunk_row_fma<C, 1, GLO>(u, bline, acc); break;
+                    case 2: chunk_row_fma<C, 2, GLO>(u, bline, acc); break;
+                    default: chunk_row_fma<C, 3, GLO>(u, bline, acc); break;
                 }
             }
         }
     }
+}
+
+template <int C, bool GL>
+__device__ __forceinline__ void couple_grid_sym_chunks(const float* __restrict__ bp, const float* __restrict__ T,
+                                                       int GZ, int GX, int zq, int xq, int a, float pz, float px,
+                                                       float (&as)[kRows], float (&ac)[kRows]) {
+    float2 acc[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) acc[r] = make_float2(0.f, 0.f);
+    couple_grid_sym_chunks_acc<C, GL, GL>(bp, T, GZ, GX, zq, xq, a, pz, px, 0, GZ >> 1, acc);
 #pragma unroll
     for (int r = 0; r < kRows; ++r) { as[r] = acc[r].x; ac[r] = acc[r].y; }
 }
@@ -882,7 +898,9 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     double* part = reinterpret_cast<double*>(WD + Nl);    // [nwarps][kSampleBatch][2]
     double* red = part + nwarps * kSampleBatch * 2;       // [nwarps]
     double* t_delta = red + nwarps;                       // [32] observation tail scratch
-    int* t_pos = reinterpret_cast<int*>(t_delta + 32);    // [32]
+    int* t_pos = reinterpret_cast<int*>(t_delta + 32);    // [36]
+    // cluster mode: operand tile [4 sectors][TZ planes] (kClTileFloats + 16 floats), 16-byte aligned
+    float* cl_tile = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(t_pos + 36) + 15) & ~uintptr_t(15));
     const real* T = CL ? reinterpret_cast<const real*>(p.table) : Ts;
     const float4* U4 = reinterpret_cast<const float4*>(smem_raw);       // MW: [16][2][64] sector coefficients
 
@@ -1088,7 +1106,42 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                 real as[kRows], ac[kRows];
                 if (DENSE) couple_dense<real>(SC + pbuf * scsz, reinterpret_cast<const real*>(p.alpha), Np, i0, as, ac);
                 else if (SYM) {
-                    if (GEO == 3 || GEO == 4)
+                    if constexpr (CL != 0) {
+                        // Cluster mode: the operand of the whole environment sits in global memory (L2).  Every CTA
+                        // stages it through its own shared memory in tiles of whole source z-planes (one cooperative,
+                        // coalesced copy per tile and CTA instead of every warp fetching every line from L2), the
+                        // contraction then reads shared memory; only the coupling table still comes through L1.
+                        const int HZc = GZ >> 1;
+                        const int plane_f = (GX >> 1) * CH * 2 * kRows;             // floats per source z-plane and sector
+                        int TZ = kClTileFloats / (4 * plane_f);
+                        if (TZ < 1) TZ = 1;
+                        const int tsec = TZ * plane_f + 4;                          // sector stride in the tile (staggered banks)
+                        const float* opg = reinterpret_cast<const float*>(SC + pbuf * scsz);
+                        float2 acc2[kRows];
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) acc2[r] = make_float2(0.f, 0.f);
+#pragma unroll 1
+                        for (int z0 = 0; z0 < HZc; z0 += TZ) {
+                            const int tz = HZc - z0 < TZ ? HZc - z0 : TZ;
+                            const int n4 = tz * plane_f / 4;                         // float4 per sector in this tile
+                            __syncthreads();                                         // the previous tile has been consumed
+                            for (int i = tid; i < 4 * n4; i += nt) {
+                                const int sp = i / n4, r4 = i - sp * n4;
+                                reinterpret_cast<float4*>(cl_tile + sp * tsec)[r4] =
+                                    __ldcg(reinterpret_cast<const float4*>(opg + sp * sec_stride + z0 * plane_f) + r4);
+                            }
+                            __syncthreads();
+                            const float* bpt = cl_tile + img * tsec - z0 * plane_f;  // so that plane zj is found at zj * plane_f
+                            if constexpr (GEO == 3 || GEO == 4)
+                                couple_grid_sym_chunks_acc<CH, true, false>(bpt, reinterpret_cast<const float*>(T), GZ, GX, zq, xq, chunk,
+                                                                            (float)sgn_z, (float)sgn_x, z0, z0 + tz, acc2);
+                            else
+                                couple_grid_sym_fixed_acc<0, 4, true, false>(bpt, reinterpret_cast<const float*>(T), zq, xq, (float)sgn_z,
+                                                                             (float)sgn_x, HZc, z0, z0 + tz, acc2);
+                        }
+#pragma unroll
+                        for (int r = 0; r < kRows; ++r) { as[r] = real(acc2[r].x); ac[r] = real(acc2[r].y); }
+                    } else if (GEO == 3 || GEO == 4)
                         couple_grid_sym_chunks<CH, CL != 0>(reinterpret_cast<const float*>(SC + pbuf * scsz + sc_sector),
                                                    reinterpret_cast<const float*>(T), GZ, GX, zq, xq, chunk, (float)sgn_z, (float)sgn_x,
                                                    reinterpret_cast<float(&)[kRows]>(as), reinterpret_cast<float(&)[kRows]>(ac));
@@ -1357,7 +1410,8 @@ inline size_t step_smem_bytes_mw(int Np) { return kMwUFloat4 * sizeof(float4) + 
 inline size_t step_smem_bytes_cluster(int nthreads, size_t real_bytes) {
     const int nwarps = (nthreads + 31) / 32, Nl = nthreads * kRows;
     return (size_t)((kSlots + 1) * Nl) * real_bytes + (size_t)Nl * sizeof(int) +
-           (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 36 * sizeof(int);
+           (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 36 * sizeof(int) +
+           (size_t)(kClTileFloats + 16) * sizeof(float) + 16;
 }
 
 inline size_t step_smem_bytes(int Np, int tab, int nthreads, size_t real_bytes) {
