@@ -113,17 +113,21 @@ class BatchedKuramoto:
         # Per-oscillator vectors that did not change since this environment's last reset are not uploaded again:
         # without drift the natural frequencies and the electrode (stimulation / recording conductances) are the
         # very same objects from reset to reset (host_env.begin_episode_fast), only the initial phases are new.
-        same = all(self.w0_model[i] is s.w0 and self.electrodes[i] is s.electrode for i, s in zip(ids, setups))
+        same_w0 = all(self.w0_model[i] is s.w0 for i, s in zip(ids, setups))
+        same_el = all(self.electrodes[i] is s.electrode for i, s in zip(ids, setups))
         y0 = np.empty((n, N))
         for r, s in enumerate(setups):
             y0[r] = s.y0
-        if same:
-            self.engine.set_env_params(ids, y0=y0)
-        else:
-            w0, stim, rec = np.empty((n, N)), np.empty((n, N)), np.empty((n, N))
+        w0 = stim = rec = None
+        if not same_w0:
+            w0 = np.empty((n, N))
             for r, s in enumerate(setups):
-                w0[r] = s.w0; stim[r] = s.stim; rec[r] = s.rec
-            self.engine.set_env_params(ids, w0=w0, stim=stim, rec=rec, y0=y0)
+                w0[r] = s.w0
+        if not same_el:
+            stim, rec = np.empty((n, N)), np.empty((n, N))
+            for r, s in enumerate(setups):
+                stim[r] = s.stim; rec[r] = s.rec
+        self.engine.set_env_params(ids, w0=w0, stim=stim, rec=rec, y0=y0)
         self.engine.set_episode(ids, step_idx=0,
                                 episode_len=[self.hosts[i].total_episode_counts for i in ids])
         for i, s in zip(ids, setups):

@@ -74,6 +74,8 @@ struct DbsGymHandle {
     double* trace = nullptr; int32_t* trace_len = nullptr; int trace_cap = 0; bool trace_on = false;
     // FSAL carried across segments / launches (fp32): last stage derivative per environment + valid flags
     void* k_fsal = nullptr; int32_t* fsal_valid = nullptr; bool fsal_on = false;
+    // grow-only staging pair for host -> device row uploads (pinned host side: true DMA, no cudaMalloc / cudaFree per call)
+    void* stage_dev = nullptr; void* stage_host = nullptr; size_t stage_bytes = 0;
     bool mirror_on = false;              // obs kernel writes the mirror (set while a mirror step / reset runs)
     bool mirror_pending = false;         // between dbsgym_step_host_mirror_begin and _end
     uint8_t* st_done = nullptr;
@@ -184,19 +186,35 @@ int upload_ids(DbsGymHandle* h, const int32_t* env_ids, int n, const int32_t** d
     return DBSGYM_OK;
 }
 
-// scatter n rows of `row_bytes` from a host staging vector into a [B][row] device array
+int ensure_stage(DbsGymHandle* h, size_t bytes) {
+    if (bytes <= h->stage_bytes) return DBSGYM_OK;
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (h->stage_dev) cudaFree(h->stage_dev);
+    if (h->stage_host) cudaFreeHost(h->stage_host);
+    h->stage_dev = h->stage_host = nullptr; h->stage_bytes = 0;
+    const size_t cap = bytes + bytes / 4;
+    CU(h, cudaMalloc(&h->stage_dev, cap));
+    CU(h, cudaMallocHost(&h->stage_host, cap));
+    h->stage_bytes = cap;
+    return DBSGYM_OK;
+}
+
+// scatter n rows of `row_bytes` from host memory (h->stage_host itself, or any other buffer) into a [B][row] device array
 int scatter_to_device(DbsGymHandle* h, void* dst, const void* host_rows, const int32_t* ids_dev, int n,
                       size_t row_bytes) {
-    void* tmp = nullptr;
-    CU(h, cudaMalloc(&tmp, row_bytes * (size_t)n));
-    cudaError_t e = cudaMemcpyAsync(tmp, host_rows, row_bytes * (size_t)n, cudaMemcpyHostToDevice, h->stream);
+    const size_t bytes = row_bytes * (size_t)n;
+    if (host_rows != h->stage_host || bytes > h->stage_bytes) {
+        int rc = ensure_stage(h, bytes);
+        if (rc) return rc;
+        memcpy(h->stage_host, host_rows, bytes);
+    }
+    cudaError_t e = cudaMemcpyAsync(h->stage_dev, h->stage_host, bytes, cudaMemcpyHostToDevice, h->stream);
     if (e == cudaSuccess) {
         scatter_rows_kernel<<<n, 128, 0, h->stream>>>(static_cast<unsigned char*>(dst),
-                                                      static_cast<const unsigned char*>(tmp), ids_dev, n, row_bytes);
+                                                      static_cast<const unsigned char*>(h->stage_dev), ids_dev, n, row_bytes);
         e = cudaGetLastError();
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(tmp);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);      // the staging pair is reused by the next call
     if (e != cudaSuccess) return fail(h, DBSGYM_ECUDA, "scatter failed: %s", cudaGetErrorString(e));
     return DBSGYM_OK;
 }
@@ -221,6 +239,15 @@ void to_real_rows(const double* src, int n, int N, int Np, std::vector<unsigned 
     real* o = reinterpret_cast<real*>(out.data());
     for (int r = 0; r < n; ++r)
         for (int i = 0; i < N; ++i) o[(size_t)r * Np + i] = (real)src[(size_t)r * N + i];
+}
+// the same conversion straight into the pinned staging buffer
+template <typename real>
+void to_real_rows_stage(const double* src, int n, int N, int Np, void* stage) {
+    real* o = reinterpret_cast<real*>(stage);
+    for (int r = 0; r < n; ++r) {
+        for (int i = 0; i < N; ++i) o[(size_t)r * Np + i] = (real)src[(size_t)r * N + i];
+        for (int i = N; i < Np; ++i) o[(size_t)r * Np + i] = real(0);
+    }
 }
 
 void fill_params(DbsGymHandle* h, StepParams& p) {
@@ -628,6 +655,8 @@ void dbsgym_destroy(DbsGymHandle* h) {
     if (h->pin_ints) cudaFreeHost(h->pin_ints);
     if (h->mirror_host) cudaFreeHost(h->mirror_host);
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
+    if (h->stage_dev) cudaFree(h->stage_dev);
+    if (h->stage_host) cudaFreeHost(h->stage_host);
     if (h->trace) cudaFree(h->trace);
     if (h->trace_len) cudaFree(h->trace_len);
     for (int i = 0; i < 3; ++i)
@@ -698,11 +727,13 @@ int dbsgym_set_env_params(DbsGymHandle* h, const int32_t* env_ids, int32_t n, co
     std::vector<unsigned char> buf;
     const size_t row = (size_t)h->Np * h->rb;
     struct { const double* src; void* dst; } vecs[3] = {{w0, h->w0}, {stim_cond, h->stim}, {rec_cond, h->rec}};
+    rc = ensure_stage(h, row * (size_t)n);
+    if (rc) return rc;
     for (auto& v : vecs) {
         if (!v.src) continue;
-        if (h->f64) to_real_rows<double>(v.src, n, h->N, h->Np, buf);
-        else to_real_rows<float>(v.src, n, h->N, h->Np, buf);
-        rc = scatter_to_device(h, v.dst, buf.data(), ids, n, row);
+        if (h->f64) to_real_rows_stage<double>(v.src, n, h->N, h->Np, h->stage_host);
+        else to_real_rows_stage<float>(v.src, n, h->N, h->Np, h->stage_host);
+        rc = scatter_to_device(h, v.dst, h->stage_host, ids, n, row);
         if (rc) return rc;
     }
     if (y0) {
