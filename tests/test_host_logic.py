@@ -224,3 +224,41 @@ def test_batched_eval_metric_equals_row_by_row_reference_formula():
         ref.append(np.sum(ft[np.where((freq > 12.5) & (freq < 21))]))
     np.testing.assert_allclose(calc_psd_for_simple_eval(x, 0.0005), ref, rtol=1e-12)
     np.testing.assert_allclose(calc_psd_for_simple_eval([r for r in x], 0.0005), ref, rtol=1e-12)
+
+
+def test_coupling_table_for_cubic_grids_with_lines_of_16_and_32():
+    """The structured kernels also take lines of 16 / 32 oscillators (cubic 16^3 / 32^3 grids):
+    the table still expands to the dense alpha of utils.py:457-466 + env.py:219-223; shapes the kernels cannot serve
+    (odd extents, too few fundamental lines for warp-uniform chunks, lines of 24) fall back to DENSE (None)."""
+    for G, gz in ((16, 4), (32, 4)):
+        n = G * G * gz
+        coords, grid = geometry.neuron_grid(G, G, G, n, 0.1)
+        t = geometry.coupling_table(coords, grid, [G, G, G], "cos")
+        assert t is not None and t.shape == (n,)
+        rows = np.array([0, 17, n // 2 + 5, n - 1])
+        alpha = geometry.coupling_rows(coords, rows, "cos")
+        d = np.abs(grid[rows][:, None, :] - grid[None, :, :])
+        expanded = t.reshape(gz, G, G)[d[..., 2], d[..., 0], d[..., 1]]
+        assert np.max(np.abs(expanded - alpha)) < 1e-13
+    c, g = geometry.neuron_grid(16, 16, 16, 16 * 16 * 3, 0.1)          # odd number of populated z-planes
+    assert geometry.coupling_table(c, g, [16, 16, 16], "cos") is None
+    c, g = geometry.neuron_grid(4, 16, 16, 4 * 16 * 4, 0.1)            # 2 x 2 fundamental lines: chunks not warp-uniform
+    assert geometry.coupling_table(c, g, [4, 16, 16], "cos") is None
+    c, g = geometry.neuron_grid(8, 24, 8, 8 * 24 * 8, 0.1)             # lines of 24
+    assert geometry.coupling_table(c, g, [8, 24, 8], "cos") is None
+
+
+def test_device_metric_weights_fold_smoothing_and_band_sum():
+    """evaluation.bbpow_spec: sum(filtfilt([1]*12, 5, ft)[band]) == w @ ft[k_lo : k_lo + len(w)] for arbitrary spectra --
+    the identity the device evaluation kernel relies on (evaluate_HF_DBS.py:130-134)."""
+    from scipy.signal import filtfilt
+    from dbsgym_b200.evaluation import bbpow_spec
+    for n in (19039, 19998, 4001):
+        sp = bbpow_spec(n, 0.0005)
+        freq = np.fft.rfftfreq(n, 0.0005)
+        band = (freq > 12.5) & (freq < 21)
+        ft = np.random.default_rng(n).uniform(0, 1, freq.size) ** 3
+        ref = filtfilt([1] * 12, 5, ft)[band].sum()
+        w = sp["weights"]
+        assert abs(w @ ft[sp["k_lo"]:sp["k_lo"] + w.size] - ref) < 1e-12 * abs(ref)
+        assert sp["padlen"] == 15 and len(sp["b"]) == 5 and sp["a"][0] == 1.0
