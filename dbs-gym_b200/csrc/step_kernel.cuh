@@ -654,7 +654,11 @@ __device__ __forceinline__ void couple_sym_upre(const float* __restrict__ bp, co
     float2 acc[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) acc[r] = make_float2(0.f, 0.f);
-#pragma unroll
+#ifndef DBSGYM_MW_UNROLL
+#define DBSGYM_MW_UNROLL 16       // 16 = fully unrolled; 4 / 8 were tried for the instruction-cache footprint
+#endif
+    constexpr int kUnroll = DBSGYM_MW_UNROLL;
+#pragma unroll kUnroll
     for (int blk = 0; blk < 16; ++blk) {
         float u[kRows], b[2 * kRows];
         unpack(U4[(2 * blk) * kMwThreads + tid_w], u);
