@@ -42,6 +42,25 @@ def test_create_rejects_bad_config_without_touching_a_gpu(lib):
     assert lib.dbsgym_create(C.byref(cfg), C.byref(h)) == -1        # zero sizes
     assert not h.value
 
+    def grid_cfg(n_osc, grid, precision=_capi.F32):
+        c = _capi.DbsGymConfig()
+        c.struct_bytes = C.sizeof(_capi.DbsGymConfig)
+        c.device, c.n_envs, c.n_osc, c.window = 0, 4, n_osc, 2340
+        c.grid[0], c.grid[1], c.grid[2] = grid
+        c.precision, c.coupling, c.max_step_samples, c.max_steps = precision, _capi.COUPLING_GRID, 20, 4096
+        c.K, c.rtol, c.atol, c.dt0 = 0.52, 1e-5, 1e-5, 0.05
+        c.safety, c.factor_min, c.factor_max, c.action_lo, c.action_hi = 0.9, 0.2, 10.0, -5.0, 5.0
+        return c
+
+    # grid shapes the structured kernels cannot serve are refused with a message (before any device is touched)
+    for c, msg in ((grid_cfg(8 * 24 * 8, (8, 24, 8)), b"gy"),                              # lines of 24
+                   (grid_cfg(4096, (16, 16, 16), _capi.F64), b"gy = 16 supports fp32"),        # lines of 16 in fp64
+                   (grid_cfg(16 * 16 * 3, (16, 16, 16)), b"even gx and gz"),                  # odd number of z-planes
+                   (grid_cfg(500, (8, 8, 8)), b"whole z-planes")):                           # not whole planes
+        assert lib.dbsgym_create(C.byref(c), C.byref(h)) == -1
+        assert msg in lib.dbsgym_last_error(None), lib.dbsgym_last_error(None)
+        assert not h.value
+
 
 def test_no_cpu_fallback(lib):
     """Without a CUDA device the engine must fail loudly, never compute on the host."""
