@@ -1,4 +1,9 @@
-// Observation / reward kernel (sm_100a), HBM-bound.
+// Observation / reward kernels (sm_100a), HBM-bound.
+//
+// For the beta-power rewards the per-step work (window append, reward, episode bookkeeping) is fused into the step
+// kernel's tail (step_kernel.cuh: obs_tail, with incrementally updated rfft bins); this file holds its companions
+// (spec_init_kernel, obs_copy_kernel) and the stand-alone observation kernel that still serves the R2 reward, window
+// emission at reset and the A/B switch DBSGYM_NO_FUSED_OBS:
 //
 // Per environment: append the step's recorded LFP samples to the observation ring
 // (reference environment/env.py:447-448), emit the window in chronological order as the
