@@ -1,7 +1,7 @@
-"""Importable name of the package that lives in ``dbs-gym_b200/`` (a hyphen cannot be imported)."""
-import os as _os
+"""dbsgym_b200 -- B200-native batched implementation of DBS-Gym's environment step.
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "dbs-gym_b200")
-__path__.insert(0, _real)
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+Host side mirrors the reference's ``environment`` package (``SpatialKuramoto``, the env0/1/2
+configs, ``utils``); the integration, LFP, window and reward run in hand-written sm_100a CUDA
+kernels behind the C-ABI of ``include/dbsgym.h`` (``csrc/``).  No CPU fallback exists.
+"""
+__version__ = "0.1.0"

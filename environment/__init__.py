@@ -1,3 +1,3 @@
 """Drop-in for the reference's ``environment`` package: same import paths
 (``environment.env``, ``environment.utils``, ``environment.env_configs.env{0,1,2}``), backed by
-the B200 engine in ``dbs-gym_b200/``."""
+the B200 engine in ``dbsgym_b200/``."""

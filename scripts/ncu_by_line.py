@@ -7,7 +7,7 @@ from collections import Counter, defaultdict
 rep, pat = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(root, "dbs-gym_b200", "csrc", "libdbsgym.so")
+so = os.path.join(root, "dbsgym_b200", "csrc", "libdbsgym.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, check=True, capture_output=True)
 cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
@@ -49,7 +49,7 @@ for (sass, loc), (s2, e, ns, sd) in zip(seq, ncu):
     for k, v in sd.items():
         st[k] += v
 tot, ts = sum(ex.values()), sum(sm.values())
-src = open(os.path.join(root, "dbs-gym_b200", "csrc", "step_kernel.cuh")).read().split("\n")
+src = open(os.path.join(root, "dbsgym_b200", "csrc", "step_kernel.cuh")).read().split("\n")
 print(f"total warp instructions {tot}, samples {ts}")
 print("-- stall reasons"); T = sum(st.values())
 for k, v in st.most_common(8):

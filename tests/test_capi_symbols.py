@@ -74,7 +74,7 @@ def test_no_cpu_fallback(lib):
 
 
 def test_product_does_not_import_oracle():
-    pkg = os.path.join(ROOT, "dbs-gym_b200")
+    pkg = os.path.join(ROOT, "dbsgym_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):

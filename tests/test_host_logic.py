@@ -1,4 +1,4 @@
-"""Product HOST code (dbs-gym_b200/*.py) against the reference-generated fixtures.  CPU only.
+"""Product HOST code (dbsgym_b200/*.py) against the reference-generated fixtures.  CPU only.
 Integer / index results must be bit-exact; float vectors agree to rounding."""
 import re
 
