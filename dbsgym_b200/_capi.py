@@ -17,6 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("DBSGYM_LIB") or os.path.join(CSRC, "libdbsgym.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "dbsgym.h")
 
+ABI_VERSION = 2
 F32, F64 = 0, 1
 COUPLING_GRID, COUPLING_DENSE = 0, 1
 REWARD_BBPOW, REWARD_TEMP_CONST, REWARD_BBPOW_THRESH = 0, 1, 2
@@ -26,7 +27,8 @@ EXPORTS = [
     "dbsgym_set_coupling_grid", "dbsgym_set_coupling_dense", "dbsgym_set_env_params",
     "dbsgym_set_recording", "dbsgym_set_schedule", "dbsgym_set_reward", "dbsgym_set_episode",
     "dbsgym_transient", "dbsgym_step", "dbsgym_step_host", "dbsgym_step_host_samples", "dbsgym_host_mirror", "dbsgym_step_host_mirror", "dbsgym_step_host_mirror_begin", "dbsgym_step_host_mirror_end", "dbsgym_get_obs_host",
-    "dbsgym_get_lfp", "dbsgym_get_rewards", "dbsgym_get_state", "dbsgym_get_window",
+    "dbsgym_get_lfp", "dbsgym_get_rewards", "dbsgym_get_phases", "dbsgym_get_window",
+    "dbsgym_state_bytes", "dbsgym_get_state", "dbsgym_set_state", "dbsgym_launch_count", "dbsgym_measure_mufu_peak",
     "dbsgym_set_window", "dbsgym_get_episode", "dbsgym_counters", "dbsgym_last_step_ms",
     "dbsgym_set_timing", "dbsgym_measure_fp32_peak", "dbsgym_measure_fp32_peak_mode",
     "dbsgym_rhs_reused", "dbsgym_trace_begin", "dbsgym_trace_end", "dbsgym_trace_get", "dbsgym_eval_bbpow",
@@ -41,7 +43,12 @@ class DbsGymConfig(C.Structure):
         ("max_steps", C.c_int32), ("K", C.c_double), ("rtol", C.c_double), ("atol", C.c_double),
         ("dt0", C.c_double), ("safety", C.c_double), ("factor_min", C.c_double),
         ("factor_max", C.c_double), ("action_lo", C.c_double), ("action_hi", C.c_double),
+        ("mw_mode", C.c_int32), ("force_cluster", C.c_int32), ("ctas_per_sm", C.c_int32), ("debug_flags", C.c_uint32),
     ]
+
+
+# DbsGymConfig.debug_flags
+DBG_NO_GEO1, DBG_NO_SYM, DBG_NO_FSAL_REUSE, DBG_NO_FUSED_OBS, DBG_NO_FAST_OBS = 1, 2, 4, 8, 16
 
 
 class DbsGymRewardSpec(C.Structure):
@@ -123,14 +130,19 @@ def load():
         "dbsgym_step": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "dbsgym_step_host": (C.c_int, [vp, vp, vp, vp, vp]),
         "dbsgym_step_host_samples": (C.c_int, [vp, vp, vp, vp, vp, vp]),
-        "dbsgym_host_mirror": (C.c_int, [vp, C.POINTER(f32p)]),
+        "dbsgym_host_mirror": (C.c_int, [vp, C.POINTER(f32p), i32p]),
         "dbsgym_step_host_mirror": (C.c_int, [vp, vp, i32p, i32p, vp, vp]),
         "dbsgym_step_host_mirror_begin": (C.c_int, [vp, vp]),
         "dbsgym_step_host_mirror_end": (C.c_int, [vp, i32p, i32p, vp, vp]),
         "dbsgym_get_obs_host": (C.c_int, [vp, vp]),
         "dbsgym_get_lfp": (C.c_int, [vp, vp, vp, vp]),
         "dbsgym_get_rewards": (C.c_int, [vp, vp, vp]),
-        "dbsgym_get_state": (C.c_int, [vp, vp, C.c_int32, vp]),
+        "dbsgym_get_phases": (C.c_int, [vp, vp, C.c_int32, vp]),
+        "dbsgym_state_bytes": (C.c_int, [vp, u64p]),
+        "dbsgym_get_state": (C.c_int, [vp, vp, C.c_uint64]),
+        "dbsgym_set_state": (C.c_int, [vp, vp, C.c_uint64]),
+        "dbsgym_launch_count": (C.c_int, [vp, u64p, C.c_int32]),
+        "dbsgym_measure_mufu_peak": (C.c_int, [C.c_int32, C.c_double, f64p]),
         "dbsgym_get_window": (C.c_int, [vp, vp, C.c_int32, vp]),
         "dbsgym_set_window": (C.c_int, [vp, vp, C.c_int32, vp]),
         "dbsgym_get_episode": (C.c_int, [vp, vp, vp]),
@@ -149,7 +161,7 @@ def load():
     for name, (res, args) in P.items():
         fn = getattr(lib, name)        # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args
-    if lib.dbsgym_abi_version() != 1:
+    if lib.dbsgym_abi_version() != ABI_VERSION:
         raise DbsGymError("libdbsgym.so ABI version mismatch; rebuild")
     _lib = lib
     return lib

@@ -16,7 +16,9 @@ from .schedule import StepSchedule, transient_grid
 
 _SHARED_KEYS = ("num_oscillators", "grid_size", "K", "spatial_kernel", "wavelet_amp", "wavelet_steepness",
                 "electrode_width", "electrode_pause", "verbose_dt", "observe_wind_counts",
-                "transient_state_len", "dbs_action_bounds", "reward_func", "recording_kernel")
+                "transient_state_len", "dbs_action_bounds", "reward_func", "recording_kernel",
+                # the coupling operator is built once, from the first dict: the neuron geometry must be common
+                "neur_coords", "neur_grid")
 
 
 def _pinned(shape, dtype):
@@ -34,7 +36,7 @@ def _pinned(shape, dtype):
 
 class BatchedKuramoto:
     def __init__(self, params_dicts, *, precision="f32", device=0, compat_env2=False, force_dense=False,
-                 save_init=False, transfer="delta"):
+                 save_init=False, transfer="delta", engine_options=None):
         if isinstance(params_dicts, dict):
             params_dicts = [params_dicts]
         self.params_dicts = list(params_dicts)
@@ -72,7 +74,7 @@ class BatchedKuramoto:
         self.engine = KuramotoEngine(B, self.n_osc, p0["grid_size"], self.window, p0["K"],
                                      precision=precision, coupling_table=table, alpha=alpha, device=device,
                                      max_step_samples=max(self.schedule.max_samples, 20),
-                                     action_bounds=p0["dbs_action_bounds"])
+                                     action_bounds=p0["dbs_action_bounds"], options=engine_options)
         self.engine.set_recording(p0["recording_kernel"] == "gaussian")
         self.engine.set_schedule(self.schedule)
         self.engine.set_reward(p0["reward_func"], p0["verbose_dt"])
@@ -97,11 +99,12 @@ class BatchedKuramoto:
         smax = self.engine.max_step_samples
         self.samples_buf, t = _pinned((B, smax), np.float32); self._pin.append(t)
         self.nsamp_buf, t = _pinned((B,), np.int32); self._pin.append(t)
-        # [B, 2W]: every sample is stored twice (column c and c + W) so the chronological window is always
-        # the contiguous slice [:, pos:pos+W] and nothing ever has to be moved
-        self._mirror = None            # created lazily (needs the first transient to have run)
-        self._mirror_pos = 0
-        self._mirror_ok = False
+        # host mirror: a pinned sample log per environment, appended to by the step kernel itself (dbsgym.h:
+        # dbsgym_host_mirror).  The window is always one contiguous slice of it and later steps only append BEHIND
+        # a window already handed out, so step() returns views that stay intact for >= 13 further steps; a reset
+        # switches to the second buffer (fetched again lazily).
+        self._mirror = None
+        self._mirror_used = False
         self._lfp_cache = None
         self.current_step = np.zeros(B, dtype=np.int64)
         self._upload_and_run_transient(np.arange(B), setups)
@@ -136,7 +139,7 @@ class BatchedKuramoto:
             self.current_step[i] = 0
         self.engine.transient(self.t_transient, env_ids=ids)
         self._lfp_cache = None
-        self._mirror_ok = False
+        self._mirror = None            # the reset moved the mirror on to its other buffer
 
     def reset_envs(self, ids):
         """reset() of the listed environments, in the order given (reference env.py:467-614)."""
@@ -176,8 +179,20 @@ class BatchedKuramoto:
         return setups
 
     def observations(self):
-        """Current observation windows [B, W] float32 (host), read back from the device."""
+        """Current observation windows [B, W] float32 (host), read back from the device into one of two pinned
+        buffers used alternately: the returned array stays intact until the call after the next one."""
+        self._obs_flip ^= 1
+        self.obs_buf = self._obs_bufs[self._obs_flip]
         return self.engine.obs_host(self.obs_buf)
+
+    def observations_after_reset(self):
+        """Windows of all environments right after reset_envs(): with the delta transfer a view of the mirror buffer
+        the reset switched to (every log restarts at column 0 there), otherwise a read-back."""
+        if self.transfer == "delta" and self._mirror_used:
+            self._mirror = self.engine.host_mirror()
+            g = self._mirror.shape[1] // 2 - self.window
+            return self._mirror[:, g:g + self.window]
+        return self.observations()
 
     def step_begin(self, actions):
         """Launch one step of every environment and return at once (the GPU works); finish with step_end().
@@ -188,6 +203,7 @@ class BatchedKuramoto:
         if self.transfer == "delta":
             if self._mirror is None:
                 self._mirror = self.engine.host_mirror()
+                self._mirror_used = True
             self.engine.step_host_mirror_begin(self.act_buf)
 
     def step_end(self):
@@ -207,13 +223,15 @@ class BatchedKuramoto:
         return self.obs_buf, self.rew_buf, self.done_buf.view(np.bool_)
 
     def step(self, actions):
-        """Advance every environment by one step.  Returns host views: obs [B,W] f32, reward [B] f32
-        and done [B] bool, all overwritten by later calls (copy what you keep)."""
+        """Advance every environment by one step.  Returns host views: obs [B,W] f32, reward [B] f32 and done [B]
+        bool.  reward / done are overwritten by the next call; obs stays intact for at least one further step()
+        (delta transfer: >= 13 steps, see dbsgym_host_mirror; full transfer: two alternating buffers)."""
         self.act_buf[:] = np.asarray(actions, dtype=np.float32).reshape(self.num_envs)
         self._lfp_cache = None
         if self.transfer == "delta":
             if self._mirror is None:
                 self._mirror = self.engine.host_mirror()
+                self._mirror_used = True
             pos, n = self.engine.step_host_mirror(self.act_buf, self.rew_buf, self.done_buf)
             self.current_step += 1
             if n >= 0:
@@ -242,7 +260,6 @@ class BatchedKuramoto:
                                 torch.cuda.current_stream(dev).cuda_stream)
         self.current_step += 1
         self._lfp_cache = None
-        self._mirror_ok = False
         return obs, reward, done
 
     # -------------------------------------------------------------------------------------

@@ -20,6 +20,10 @@ namespace {
 
 thread_local char g_create_err[512] = "";
 
+// Host mirror log: samples that stay valid behind a returned window.  A window handed to the caller (W columns ending at the
+// write position) is overwritten only after kMirrorGuard further samples have been appended: 13 steps of <= 19 samples.
+constexpr int kMirrorGuard = 256;
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -64,8 +68,12 @@ struct DbsGymHandle {
     int32_t* status = nullptr;
     // host-API staging
     float *st_actions = nullptr, *st_obs = nullptr, *st_reward = nullptr, *st_samples = nullptr;
-    float* mirror_host = nullptr;        // pinned + mapped [B][2W] window mirror (dbsgym_host_mirror)
-    float* mirror_dev = nullptr;
+    // pinned + mapped window mirrors (dbsgym_host_mirror): two buffers [B][2 * mir_len], used alternately -- every
+    // reset (dbsgym_transient) moves on to the other one, so windows handed out before it stay untouched
+    float* mirror_host[2] = {nullptr, nullptr};
+    float* mirror_dev[2] = {nullptr, nullptr};
+    int mirror_cur = 0, mir_len = 0;
+    int32_t* mpos = nullptr;             // [B] write column of every environment's mirror log
     int32_t* pin_ints = nullptr;         // pinned landing buffer: n_samples[B], head[B]
     // zero-copy control block of the host-mirror step (pinned + mapped): actions[B] f32 | reward[B] f32 |
     // n_samples[B] i32 | head[B] i32 | done[B] u8 -- read / written by the step kernel itself through PCIe
@@ -85,6 +93,10 @@ struct DbsGymHandle {
     int ctas_per_sm = 0;                 // 0 = whatever fits
     int num_sms = 0;
     int mw_mode = -1;                    // multi-worker step kernel: -1 auto (full-occupancy batches), 0 never, 1 always
+    bool no_geo1 = false, no_fast_obs = false, no_fused_obs = false;     // DbsGymConfig.debug_flags
+    unsigned long long n_launches = 0;   // kernels launched by this handle (dbsgym_launch_count)
+    // ordering between the private stream and caller streams (dbsgym_step / dbsgym_transient on a user stream)
+    cudaEvent_t ev_own = nullptr, ev_user = nullptr; bool user_pending = false;
     bool grid_sym = false;               // GRID coupling: use the reflection-symmetry reduced contraction
     bool timing = false;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
@@ -169,6 +181,21 @@ __global__ void fma2_peak_kernel(float* out, int iters, float a, float b) {
     if (s == 123.456f) out[0] = s;
 }
 
+// dependent MUFU.SIN / MUFU.COS chains: 2 * kChains * iters special-function operations per thread
+__global__ void mufu_peak_kernel(float* out, int iters, float a) {
+    float v[kChains];
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) v[c] = 0.001f * (float)(threadIdx.x + c);
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int c = 0; c < kChains; ++c) v[c] = __cosf(__sinf(v[c]) + a);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChains; ++c) s += v[c];
+    if (s == 123.456f) out[0] = s;
+}
+
 int upload_ids(DbsGymHandle* h, const int32_t* env_ids, int n, const int32_t** dev) {
     *dev = nullptr;
     if (!env_ids) return DBSGYM_OK;
@@ -212,6 +239,7 @@ int scatter_to_device(DbsGymHandle* h, void* dst, const void* host_rows, const i
     if (e == cudaSuccess) {
         scatter_rows_kernel<<<n, 128, 0, h->stream>>>(static_cast<unsigned char*>(dst),
                                                       static_cast<const unsigned char*>(h->stage_dev), ids_dev, n, row_bytes);
+        ++h->n_launches;
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);      // the staging pair is reused by the next call
@@ -225,6 +253,7 @@ int gather_from_device(DbsGymHandle* h, void* host_rows, const void* src, const 
     CU(h, cudaMalloc(&tmp, row_bytes * (size_t)n));
     gather_rows_kernel<<<n, 128, 0, h->stream>>>(static_cast<unsigned char*>(tmp),
                                                  static_cast<const unsigned char*>(src), ids_dev, n, row_bytes);
+    ++h->n_launches;
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(host_rows, tmp, row_bytes * (size_t)n, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -277,6 +306,7 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
     p.tail_on = 0; p.tail_kind = h->rspec.kind; p.tail_nbins = h->nbins;
     p.spec = h->spec; p.tw_full = h->tw_full;
     p.samples_f = nullptr; p.mirror = nullptr; p.reward_f = nullptr; p.reward = h->reward;
+    p.mir_len = h->mir_len; p.mpos = h->mpos;
     p.done_out = nullptr; p.done_dev = h->done;
     p.step_idx_rw = h->step_idx; p.episode_len = h->episode_len;
     p.nsamp_out = nullptr; p.head_out = nullptr;
@@ -301,6 +331,7 @@ cudaError_t launch_step_t(DbsGymHandle* h, const StepParams& p, cudaStream_t s) 
         if (e != cudaSuccess) return e;
     }
     kern<<<p.n_launch, h->nthreads, smem, s>>>(p);
+    ++h->n_launches;
     return cudaGetLastError();
 }
 
@@ -313,6 +344,7 @@ cudaError_t launch_step_mw(DbsGymHandle* h, const StepParams& p, cudaStream_t s)
     int ctas = (p.n_launch + kMwEnvs - 1) / kMwEnvs;
     if (ctas > h->num_sms) ctas = h->num_sms;
     kern<<<ctas, kMwEnvs * kMwThreads, smem, s>>>(p);
+    ++h->n_launches;
     return cudaGetLastError();
 }
 
@@ -331,8 +363,7 @@ cudaError_t launch_step_m(DbsGymHandle* h, const StepParams& p, cudaStream_t s) 
         return launch_step_t<real, CPL, 512, 4>(h, p, s);
     }
     if constexpr (CPL == CPL_GRID_SYM && sizeof(real) == 4) {
-        static const bool no_geo1 = getenv("DBSGYM_NO_GEO1") != nullptr;        // A/B switch for tuning runs
-        if (t == 64 && p.GZ == 8 && p.GX == 8 && !no_geo1) {
+        if (t == 64 && p.GZ == 8 && p.GX == 8 && !h->no_geo1) {
             // enough environments to fill every SM with kMwEnvs of them: share the sector-coefficient table
             const bool mw = kYParity && (h->mw_mode == 1 || (h->mw_mode < 0 && p.n_launch >= kMwEnvs * h->num_sms));
             if (mw) return launch_step_mw(h, p, s);
@@ -370,6 +401,7 @@ cudaError_t launch_step_cluster_t(DbsGymHandle* h, const StepParams& p, cudaStre
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)h->cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
+    ++h->n_launches;
     return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
@@ -398,7 +430,8 @@ cudaError_t launch_obs(DbsGymHandle* h, float* obs, float* reward_f, uint8_t* do
                        const int32_t* ids_dev, int n, cudaStream_t s, float* samples_f = nullptr) {
     ObsParams o;
     o.samples_f = samples_f;
-    o.mirror = h->mirror_on ? h->mirror_dev : nullptr;
+    o.mirror = h->mirror_on ? h->mirror_dev[h->mirror_cur] : nullptr;
+    o.mir_len = h->mir_len; o.mpos = h->mpos;
     o.B = h->B; o.W = h->W; o.smax = h->smax;
     o.ring = h->ring; o.head = h->head;
     o.lfp_rec = h->lfp_rec; o.n_samples = h->n_samples;
@@ -410,8 +443,8 @@ cudaError_t launch_obs(DbsGymHandle* h, float* obs, float* reward_f, uint8_t* do
     o.temp_scale = h->rspec.temp_scale;
     o.lin_g = h->lin_g; o.tw_seed = h->tw_seed; o.tw_inner = h->tw_inner; o.iters = h->obs_iters;
     o.append = append; o.env_ids = ids_dev; o.n_launch = n;
-    static const bool no_fast = getenv("DBSGYM_NO_FAST_OBS") != nullptr;     // A/B switch
-    if (append && o.kind != 1 && h->obs_iters == kFastIters && h->nbins <= kFastMaxBins && h->smax <= kObsThreads && !no_fast) {
+    ++h->n_launches;
+    if (append && o.kind != 1 && h->obs_iters == kFastIters && h->nbins <= kFastMaxBins && h->smax <= kObsThreads && !h->no_fast_obs) {
         const size_t smem = obs_fast_smem_bytes(h->nbins, h->rb);
         if (h->f64) obs_kernel_fast<double><<<n, kObsThreads, smem, s>>>(o);
         else obs_kernel_fast<float><<<n, kObsThreads, smem, s>>>(o);
@@ -426,15 +459,38 @@ cudaError_t launch_obs(DbsGymHandle* h, float* obs, float* reward_f, uint8_t* do
 // running rfft bins of the given environments from their whole rings (fused-tail state)
 cudaError_t launch_spec_init(DbsGymHandle* h, const int32_t* ids_dev, int n, cudaStream_t s) {
     if (!h->fuse_tail) return cudaSuccess;
+    ++h->n_launches;
     if (h->f64) spec_init_kernel<double><<<n, kObsThreads, 0, s>>>(h->ring, h->tw_full, h->spec, h->W, h->nbins, kTailBins, ids_dev, n);
     else spec_init_kernel<float><<<n, kObsThreads, 0, s>>>(h->ring, h->tw_full, h->spec, h->W, h->nbins, kTailBins, ids_dev, n);
     return cudaGetLastError();
 }
 
 cudaError_t launch_obs_copy(DbsGymHandle* h, float* obs, cudaStream_t s) {
+    ++h->n_launches;
     if (h->f64) obs_copy_kernel<double><<<h->B, kCopyThreads, 0, s>>>(h->ring, h->head, obs, h->W, h->B);
     else obs_copy_kernel<float><<<h->B, kCopyThreads, 0, s>>>(h->ring, h->head, obs, h->W, h->B);
     return cudaGetLastError();
+}
+
+// Ordering between the handle's private stream and caller streams.  Work the caller queued on ITS stream (dbsgym_step /
+// dbsgym_transient with a stream argument) is not ordered against the private stream by CUDA; these two helpers add the
+// missing edges with events: own-stream work waits for the last user-stream call, and a user-stream call waits for
+// whatever the private stream had queued before it.
+cudaError_t enter_own(DbsGymHandle* h) {
+    if (!h->user_pending) return cudaSuccess;
+    h->user_pending = false;
+    return cudaStreamWaitEvent(h->stream, h->ev_user, 0);
+}
+cudaError_t enter_user(DbsGymHandle* h, cudaStream_t s) {
+    if (s == h->stream) return enter_own(h);
+    cudaError_t e = cudaEventRecord(h->ev_own, h->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(s, h->ev_own, 0);
+    return e;
+}
+cudaError_t leave_user(DbsGymHandle* h, cudaStream_t s) {
+    if (s == h->stream) return cudaSuccess;
+    h->user_pending = true;
+    return cudaEventRecord(h->ev_user, s);
 }
 
 int check_ready(DbsGymHandle* h, bool need_step) {
@@ -461,7 +517,7 @@ int step_impl(DbsGymHandle* h, const float* actions_dev, float* obs_dev, float* 
         // ring append, host mirror, beta-power reward and episode bookkeeping happen in the step kernel's tail;
         // a separate (pure copy) kernel runs only when the caller wants the chronological window on the device
         p.tail_on = 1;
-        p.samples_f = samples_dev; p.mirror = h->mirror_on ? h->mirror_dev : nullptr;
+        p.samples_f = samples_dev; p.mirror = h->mirror_on ? h->mirror_dev[h->mirror_cur] : nullptr;
         p.reward_f = reward_dev; p.done_out = done_dev;
         if (h->trace_on) { p.trace = h->trace; p.trace_len = h->trace_len; p.trace_cap = h->trace_cap; }
     }
@@ -471,6 +527,44 @@ int step_impl(DbsGymHandle* h, const float* actions_dev, float* obs_dev, float* 
     if (!h->fuse_tail) CU(h, launch_obs(h, obs_dev, reward_dev, done_dev, 1, nullptr, h->B, s, samples_dev));
     else if (obs_dev) CU(h, launch_obs_copy(h, obs_dev, s));
     if (h->timing) CU(h, cudaEventRecord(h->ev[2], s));
+    return DBSGYM_OK;
+}
+
+struct SnapshotHeader {
+    uint32_t magic, abi;
+    int32_t B, N, Np, W, smax, f64, fsal, nbins_pitch;
+    uint64_t bytes;
+};
+struct SnapPart { void* dev; size_t bytes; };
+
+SnapshotHeader snapshot_header(const DbsGymHandle* h, uint64_t bytes) {
+    SnapshotHeader hd;
+    memset(&hd, 0, sizeof(hd));
+    hd.magic = 0x44425347u; hd.abi = DBSGYM_ABI_VERSION;
+    hd.B = h->B; hd.N = h->N; hd.Np = h->Np; hd.W = h->W; hd.smax = h->smax; hd.f64 = h->f64 ? 1 : 0;
+    hd.fsal = h->fsal_on ? 1 : 0; hd.nbins_pitch = kTailBins; hd.bytes = bytes;
+    return hd;
+}
+
+std::vector<SnapPart> snapshot_parts(DbsGymHandle* h) {
+    const size_t B = (size_t)h->B, BN = B * h->Np;
+    std::vector<SnapPart> v = {
+        {h->phase, BN * h->rb}, {h->wind, BN * 4}, {h->w0, BN * h->rb}, {h->stim, BN * h->rb}, {h->rec, BN * h->rb},
+        {h->ring, B * h->W * h->rb}, {h->head, B * 4}, {h->spec, B * kTailBins * 2 * sizeof(double)},
+        {h->step_idx, B * 4}, {h->episode_len, B * 4}, {h->done, B},
+        {h->lfp_true, B * h->smax * 8}, {h->lfp_rec, B * h->smax * 8}, {h->n_samples, B * 4},
+        {h->u, B * 8}, {h->reward, B * 8}, {h->counters, 4 * sizeof(unsigned long long)}, {h->status, 4}};
+    if (h->fsal_on) { v.push_back({h->k_fsal, BN * h->rb}); v.push_back({h->fsal_valid, B * 4}); }
+    return v;
+}
+
+// (re)write the windows of the listed environments (NULL = all) into the current mirror buffer
+int mirror_refresh(DbsGymHandle* h, const int32_t* ids_dev, int n) {
+    const bool was = h->mirror_on;
+    h->mirror_on = true;
+    cudaError_t e = launch_obs(h, nullptr, nullptr, nullptr, 0, ids_dev, n, h->stream);
+    h->mirror_on = was;
+    if (e != cudaSuccess) return fail(h, DBSGYM_ECUDA, "mirror refresh failed: %s", cudaGetErrorString(e));
     return DBSGYM_OK;
 }
 
@@ -489,7 +583,7 @@ int dbsgym_step_variant(const DbsGymHandle* h, int32_t n_envs) {
     if (h->f64) return 2;
     if (h->cfg.grid[1] == 2 * kRows) return 7;
     if (h->cfg.grid[1] == 4 * kRows) return 8;
-    const bool geo1 = h->nthreads == 64 && h->cfg.grid[2] == 8 && h->cfg.grid[0] == 8 && !getenv("DBSGYM_NO_GEO1");
+    const bool geo1 = h->nthreads == 64 && h->cfg.grid[2] == 8 && h->cfg.grid[0] == 8 && !h->no_geo1;
     if (geo1) {
         const bool mw = kYParity && (h->mw_mode == 1 || (h->mw_mode < 0 && n_envs >= kMwEnvs * h->num_sms));
         return mw ? 4 : 3;
@@ -562,8 +656,7 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
     h->nthreads = Np / kRows;
     if (cfg->coupling == DBSGYM_COUPLING_GRID) {
         // more than 512 grid lines (N > 4096): one environment spans a thread-block cluster of 2..16 CTAs
-        int want = 1;
-        if (const char* e = getenv("DBSGYM_FORCE_CLUSTER")) want = atoi(e);      // test hook: cluster mode at small N
+        int want = cfg->force_cluster > 1 ? cfg->force_cluster : 1;             // (test hook: cluster mode at small N)
         while (h->nthreads / want > 512) want *= 2;
         if (want > 1) {
             const int lines = Np / kRows;
@@ -580,9 +673,8 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
         // only the z-planes actually populated take part
         h->cfg.grid[2] = cfg->n_osc / (cfg->grid[0] * cfg->grid[1]);
         h->tab = h->cfg.grid[2] * cfg->grid[0] * cfg->grid[1];
-        // mirror symmetry in z and x needs even extents; DBSGYM_NO_SYM=1 keeps the plain Toeplitz kernel (A/B runs)
-        const char* nosym = getenv("DBSGYM_NO_SYM");
-        h->grid_sym = h->cfg.grid[2] % 2 == 0 && cfg->grid[0] % 2 == 0 && !(nosym && nosym[0] == '1');
+        // mirror symmetry in z and x needs even extents; DBSGYM_DBG_NO_SYM keeps the plain Toeplitz kernel (A/B runs)
+        h->grid_sym = h->cfg.grid[2] % 2 == 0 && cfg->grid[0] % 2 == 0 && !(cfg->debug_flags & DBSGYM_DBG_NO_SYM);
     }
     if (h->cluster == 1) {                               // does one environment's state fit the shared memory of an SM?
         int max_smem = 0;
@@ -596,8 +688,11 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
         }
     }
     memset(&h->rspec, 0, sizeof(h->rspec));
-    if (const char* e = getenv("DBSGYM_CTAS_PER_SM")) h->ctas_per_sm = atoi(e);
-    if (const char* e = getenv("DBSGYM_MW")) h->mw_mode = atoi(e);             // A/B and test hook
+    h->ctas_per_sm = cfg->ctas_per_sm > 0 ? cfg->ctas_per_sm : 0;
+    h->mw_mode = cfg->mw_mode == 1 ? 0 : cfg->mw_mode == 2 ? 1 : -1;
+    h->no_geo1 = (cfg->debug_flags & DBSGYM_DBG_NO_GEO1) != 0;
+    h->no_fast_obs = (cfg->debug_flags & DBSGYM_DBG_NO_FAST_OBS) != 0;
+    h->no_fused_obs = (cfg->debug_flags & DBSGYM_DBG_NO_FUSED_OBS) != 0;
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
     const size_t BN = (size_t)h->B * Np;
     bool ok = true;
@@ -615,7 +710,7 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
     A((void**)&h->u, (size_t)h->B * 8); A((void**)&h->reward, (size_t)h->B * 8);
     A((void**)&h->done, (size_t)h->B);
     A((void**)&h->counters, 4 * sizeof(unsigned long long)); A((void**)&h->status, 4);
-    h->fsal_on = !h->f64 && getenv("DBSGYM_NO_FSAL_REUSE") == nullptr;       // A/B switch
+    h->fsal_on = !h->f64 && !(cfg->debug_flags & DBSGYM_DBG_NO_FSAL_REUSE);
     if (h->fsal_on) { A(&h->k_fsal, BN * h->rb); A((void**)&h->fsal_valid, (size_t)h->B * 4); }
     A((void**)&h->spec, (size_t)h->B * kTailBins * 2 * sizeof(double));
     A((void**)&h->st_actions, (size_t)h->B * 4); A((void**)&h->st_obs, (size_t)h->B * h->W * 4);
@@ -625,8 +720,12 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
         A(&h->cl_operand, (size_t)h->B * 2 * (2 * (size_t)Np + kScPad) * sizeof(float));
         A((void**)&h->cl_scratch, (size_t)h->B * 2 * h->cluster * kClSlots * sizeof(double));
     }
+    A((void**)&h->mpos, (size_t)h->B * 4);
+    h->mir_len = h->W + kMirrorGuard;
     ok = ok && cudaMallocHost(&h->pin_ints, (size_t)h->B * 8) == cudaSuccess;
     for (int i = 0; i < 3 && ok; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_own, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming) == cudaSuccess;
     if (ok) {
         // episode_len defaults to "never done"
         std::vector<int32_t> big((size_t)h->B, 0x7fffffff);
@@ -649,11 +748,14 @@ void dbsgym_destroy(DbsGymHandle* h) {
                     h->step_idx, h->episode_len, h->lfp_true, h->lfp_rec, h->u, h->reward, h->done, h->sched_nI,
                     h->sched_nII, h->sched_offI, h->sched_offII, h->ts_dev, h->ids_dev, h->lin_g, h->tw_seed,
                     h->tw_inner, h->spec, h->tw_full, h->k_fsal, h->fsal_valid, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples,
-                    h->cl_operand, h->cl_scratch};
+                    h->cl_operand, h->cl_scratch, h->mpos};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->pin_ints) cudaFreeHost(h->pin_ints);
-    if (h->mirror_host) cudaFreeHost(h->mirror_host);
+    for (float* m : h->mirror_host)
+        if (m) cudaFreeHost(m);
+    if (h->ev_own) cudaEventDestroy(h->ev_own);
+    if (h->ev_user) cudaEventDestroy(h->ev_user);
     if (h->ctl_host) cudaFreeHost(h->ctl_host);
     if (h->stage_dev) cudaFree(h->stage_dev);
     if (h->stage_host) cudaFreeHost(h->stage_host);
@@ -717,6 +819,7 @@ int dbsgym_set_env_params(DbsGymHandle* h, const int32_t* env_ids, int32_t n, co
     if (n <= 0 || n > h->B) return fail(h, DBSGYM_EINVAL, "n=%d out of range", n);
     CU(h, cudaSetDevice(h->cfg.device));
     const int32_t* ids = nullptr;
+    CU(h, enter_own(h));
     int rc = upload_ids(h, env_ids, n, &ids);
     if (rc) return rc;
     if (h->fsal_valid) {                            // the carried stage derivative belongs to the old vectors
@@ -850,8 +953,7 @@ int dbsgym_set_reward(DbsGymHandle* h, const DbsGymRewardSpec* spec, const doubl
     }
     h->rspec = *spec;
     h->have_reward = true;
-    const bool no_fuse = getenv("DBSGYM_NO_FUSED_OBS") != nullptr;     // A/B switch (read per call): separate observation kernel
-    h->fuse_tail = spec->kind != DBSGYM_REWARD_TEMP_CONST && h->nbins <= kTailBins && h->smax <= 32 && h->smax <= W && !no_fuse;
+    h->fuse_tail = spec->kind != DBSGYM_REWARD_TEMP_CONST && h->nbins <= kTailBins && h->smax <= 32 && h->smax <= W && !h->no_fused_obs;
     if (h->fuse_tail) {                              // the bins of whatever the rings hold now
         CU(h, launch_spec_init(h, nullptr, h->B, h->stream));
         CU(h, cudaStreamSynchronize(h->stream));
@@ -865,6 +967,7 @@ int dbsgym_set_episode(DbsGymHandle* h, const int32_t* env_ids, int32_t n, const
     if (n <= 0 || n > h->B) return fail(h, DBSGYM_EINVAL, "n=%d out of range", n);
     CU(h, cudaSetDevice(h->cfg.device));
     const int32_t* ids = nullptr;
+    CU(h, enter_own(h));
     int rc = upload_ids(h, env_ids, n, &ids);
     if (rc) return rc;
     if (step_idx) { rc = scatter_to_device(h, h->step_idx, step_idx, ids, n, 4); if (rc) return rc; }
@@ -873,6 +976,7 @@ int dbsgym_set_episode(DbsGymHandle* h, const int32_t* env_ids, int32_t n, const
         std::vector<uint8_t> z((size_t)n, 0);
         // done flags of re-armed environments are cleared (1-byte rows cannot use the 4-byte scatter)
         std::vector<uint8_t> all((size_t)h->B);
+        CU(h, cudaStreamSynchronize(h->stream));
         CU(h, cudaMemcpy(all.data(), h->done, (size_t)h->B, cudaMemcpyDeviceToHost));
         for (int i = 0; i < n; ++i) all[env_ids ? env_ids[i] : i] = 0;
         CU(h, cudaMemcpy(h->done, all.data(), (size_t)h->B, cudaMemcpyHostToDevice));
@@ -905,9 +1009,23 @@ int dbsgym_transient(DbsGymHandle* h, const int32_t* env_ids, int32_t n, const d
     StepParams p;
     fill_params(h, p);
     p.mode = MODE_TRANSIENT; p.env_ids = ids; p.n_launch = n; p.ts = h->ts_dev; p.n_ts = n_ts;
+    CU(h, enter_user(h, s));
     CU(h, launch_step(h, p, s));
     CU(h, launch_spec_init(h, ids, n, s));
-    CU(h, launch_obs(h, obs_dev, nullptr, nullptr, 0, ids, n, s));
+    const bool mir = h->mirror_on;
+    h->mirror_on = false;
+    cudaError_t eo = obs_dev ? launch_obs(h, obs_dev, nullptr, nullptr, 0, ids, n, s) : cudaSuccess;
+    h->mirror_on = mir;
+    CU(h, eo);
+    if (mir) {
+        // A reset replaces whole windows.  Windows handed out earlier must survive it (a caller may still hold the
+        // observation of the previous step), so the mirror moves on to its other buffer: every log restarts at column 0
+        // there and ALL environments' windows are written afresh (which also re-aligns their positions).
+        h->mirror_cur ^= 1;
+        CU(h, cudaMemsetAsync(h->mpos, 0, (size_t)h->B * 4, s));
+        CU(h, launch_obs(h, nullptr, nullptr, nullptr, 0, nullptr, h->B, s));
+    }
+    CU(h, leave_user(h, s));
     if (ids) CU(h, cudaStreamSynchronize(s));      // ids_dev is reused by the next call
     return DBSGYM_OK;
 }
@@ -919,7 +1037,11 @@ int dbsgym_step(DbsGymHandle* h, const float* actions_dev, float* obs_dev, float
     if (!actions_dev) return fail(h, DBSGYM_EINVAL, "actions_dev is null");
     CU(h, cudaSetDevice(h->cfg.device));
     cudaStream_t s = pick_stream(h, stream);
-    return step_impl(h, actions_dev, obs_dev, reward_dev, done_dev, s);
+    CU(h, enter_user(h, s));
+    rc = step_impl(h, actions_dev, obs_dev, reward_dev, done_dev, s);
+    if (rc) return rc;
+    CU(h, leave_user(h, s));
+    return DBSGYM_OK;
 }
 
 int dbsgym_step_host(DbsGymHandle* h, const float* actions, float* obs, float* reward, uint8_t* done) {
@@ -928,6 +1050,7 @@ int dbsgym_step_host(DbsGymHandle* h, const float* actions, float* obs, float* r
     if (!actions) return fail(h, DBSGYM_EINVAL, "actions is null");
     CU(h, cudaSetDevice(h->cfg.device));
     cudaStream_t s = h->stream;
+    CU(h, enter_own(h));
     CU(h, cudaMemcpyAsync(h->st_actions, actions, (size_t)h->B * 4, cudaMemcpyHostToDevice, s));
     rc = step_impl(h, h->st_actions, obs ? h->st_obs : nullptr, h->st_reward, h->st_done, s);
     if (rc) return rc;
@@ -945,6 +1068,7 @@ int dbsgym_step_host_samples(DbsGymHandle* h, const float* actions, float* sampl
     if (!actions || !samples || !n_samples) return fail(h, DBSGYM_EINVAL, "null argument");
     CU(h, cudaSetDevice(h->cfg.device));
     cudaStream_t s = h->stream;
+    CU(h, enter_own(h));
     CU(h, cudaMemcpyAsync(h->st_actions, actions, (size_t)h->B * 4, cudaMemcpyHostToDevice, s));
     rc = step_impl(h, h->st_actions, nullptr, h->st_reward, h->st_done, s, h->st_samples);
     if (rc) return rc;
@@ -956,21 +1080,28 @@ int dbsgym_step_host_samples(DbsGymHandle* h, const float* actions, float* sampl
     return DBSGYM_OK;
 }
 
-int dbsgym_host_mirror(DbsGymHandle* h, float** mirror) {
+int dbsgym_host_mirror(DbsGymHandle* h, float** mirror, int32_t* row_floats) {
     if (!h || !mirror) return fail(h, DBSGYM_EINVAL, "null argument");
     CU(h, cudaSetDevice(h->cfg.device));
-    if (!h->mirror_host) {
-        const size_t bytes = (size_t)h->B * 2 * h->W * sizeof(float);
-        CU(h, cudaHostAlloc(reinterpret_cast<void**>(&h->mirror_host), bytes, cudaHostAllocMapped | cudaHostAllocPortable));
-        CU(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->mirror_dev), h->mirror_host, 0));
-        // fill it from the current device windows
-        CU(h, cudaStreamSynchronize(h->stream));
-        h->mirror_on = true;
-        CU(h, launch_obs(h, nullptr, nullptr, nullptr, 0, nullptr, h->B, h->stream));
+    if (!h->mirror_host[0]) {
+        const size_t bytes = (size_t)h->B * 2 * h->mir_len * sizeof(float);
+        for (int i = 0; i < 2; ++i) {
+            CU(h, cudaHostAlloc(reinterpret_cast<void**>(&h->mirror_host[i]), bytes, cudaHostAllocMapped | cudaHostAllocPortable));
+            CU(h, cudaHostGetDevicePointer(reinterpret_cast<void**>(&h->mirror_dev[i]), h->mirror_host[i], 0));
+        }
+        // fill the first buffer from the current device windows, every log starting at column 0
+        CU(h, enter_own(h));
+        CU(h, cudaMemsetAsync(h->mpos, 0, (size_t)h->B * 4, h->stream));
+        h->mirror_cur = 0;
+        int rc = mirror_refresh(h, nullptr, h->B);
+        if (rc) return rc;
         CU(h, cudaStreamSynchronize(h->stream));
     }
     h->mirror_on = true;
-    *mirror = h->mirror_host;
+    CU(h, enter_own(h));
+    CU(h, cudaStreamSynchronize(h->stream));       // whatever a reset queued for the current buffer has landed
+    *mirror = h->mirror_host[h->mirror_cur];
+    if (row_floats) *row_floats = 2 * h->mir_len;
     return DBSGYM_OK;
 }
 
@@ -980,11 +1111,12 @@ int dbsgym_step_host_mirror_begin(DbsGymHandle* h, const float* actions) {
     int rc = check_ready(h, true);
     if (rc) return rc;
     if (!actions) return fail(h, DBSGYM_EINVAL, "null argument");
-    if (!h->mirror_host) return fail(h, DBSGYM_ESTATE, "no host mirror: call dbsgym_host_mirror first");
+    if (!h->mirror_host[0]) return fail(h, DBSGYM_ESTATE, "no host mirror: call dbsgym_host_mirror first");
     if (h->mirror_pending) return fail(h, DBSGYM_ESTATE, "a host-mirror step is already in flight (call dbsgym_step_host_mirror_end)");
     const int B = h->B;
     CU(h, cudaSetDevice(h->cfg.device));
     cudaStream_t s = h->stream;
+    CU(h, enter_own(h));
     h->mirror_on = true;
     if (h->fuse_tail) {
         // zero-copy control block: the kernel reads the actions from, and its tail writes reward / done / n_samples /
@@ -1004,7 +1136,7 @@ int dbsgym_step_host_mirror_begin(DbsGymHandle* h, const float* actions) {
         rc = step_impl(h, h->st_actions, nullptr, h->st_reward, h->st_done, s, nullptr);
         if (rc) return rc;
         CU(h, cudaMemcpyAsync(h->pin_ints, h->n_samples, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-        CU(h, cudaMemcpyAsync(h->pin_ints + B, h->head, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+        CU(h, cudaMemcpyAsync(h->pin_ints + B, h->mpos, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
     }
     h->mirror_pending = true;
     return DBSGYM_OK;
@@ -1034,7 +1166,7 @@ int dbsgym_step_host_mirror_end(DbsGymHandle* h, int32_t* pos, int32_t* n_new, f
     const int n = ns[0], hd0 = hd[0];
     bool uniform = true;
     for (int b = 1; b < B && uniform; ++b) uniform = ns[b] == n && hd[b] == hd0;
-    *pos = hd0;
+    *pos = (hd0 - h->W + h->mir_len) % h->mir_len;      // column of the oldest sample of the window
     *n_new = uniform ? n : -1;
     return DBSGYM_OK;
 }
@@ -1052,7 +1184,14 @@ int dbsgym_get_obs_host(DbsGymHandle* h, float* obs) {
     if (rc) return rc;
     if (!obs) return fail(h, DBSGYM_EINVAL, "obs is null");
     CU(h, cudaSetDevice(h->cfg.device));
-    CU(h, launch_obs(h, h->st_obs, nullptr, nullptr, 0, nullptr, h->B, h->stream));
+    CU(h, enter_own(h));
+    {
+        const bool mir = h->mirror_on;             // (a plain read-back: the mirror is not touched)
+        h->mirror_on = false;
+        cudaError_t eo = launch_obs(h, h->st_obs, nullptr, nullptr, 0, nullptr, h->B, h->stream);
+        h->mirror_on = mir;
+        CU(h, eo);
+    }
     CU(h, cudaMemcpyAsync(obs, h->st_obs, (size_t)h->B * h->W * 4, cudaMemcpyDeviceToHost, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     return DBSGYM_OK;
@@ -1078,7 +1217,7 @@ int dbsgym_get_rewards(DbsGymHandle* h, double* reward, double* u) {
     return DBSGYM_OK;
 }
 
-int dbsgym_get_state(DbsGymHandle* h, const int32_t* env_ids, int32_t n, double* y) {
+int dbsgym_get_phases(DbsGymHandle* h, const int32_t* env_ids, int32_t n, double* y) {
     if (!h || !y) return fail(h, DBSGYM_EINVAL, "null argument");
     if (n <= 0 || n > h->B) return fail(h, DBSGYM_EINVAL, "n=%d out of range", n);
     CU(h, cudaSetDevice(h->cfg.device));
@@ -1102,6 +1241,70 @@ int dbsgym_get_state(DbsGymHandle* h, const int32_t* env_ids, int32_t n, double*
             for (int i = 0; i < h->N; ++i)
                 y[(size_t)r * h->N + i] = (double)p[(size_t)r * h->Np + i] + kTwoPi * (double)wd[(size_t)r * h->Np + i];
     }
+    return DBSGYM_OK;
+}
+
+// ---- whole-handle snapshot ---------------------------------------------------------------------------
+// Everything a later step depends on, as one opaque blob: phases + winding counts, per-oscillator vectors, observation
+// rings + heads, running rfft bins, episode counters, the carried FSAL row, the last step's samples and the counters.
+int dbsgym_state_bytes(const DbsGymHandle* h, uint64_t* bytes) {
+    if (!h || !bytes) return DBSGYM_EINVAL;
+    uint64_t total = sizeof(SnapshotHeader);
+    for (const SnapPart& sp : snapshot_parts(const_cast<DbsGymHandle*>(h))) total += sp.bytes;
+    *bytes = total;
+    return DBSGYM_OK;
+}
+
+int dbsgym_get_state(DbsGymHandle* h, void* blob, uint64_t bytes) {
+    if (!h || !blob) return fail(h, DBSGYM_EINVAL, "null argument");
+    uint64_t need = 0;
+    dbsgym_state_bytes(h, &need);
+    if (bytes < need) return fail(h, DBSGYM_EINVAL, "snapshot buffer too small: %llu < %llu bytes",
+                                  (unsigned long long)bytes, (unsigned long long)need);
+    if (h->mirror_pending) return fail(h, DBSGYM_ESTATE, "a host-mirror step is in flight");
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaDeviceSynchronize());
+    unsigned char* out = static_cast<unsigned char*>(blob);
+    SnapshotHeader hd = snapshot_header(h, need);
+    memcpy(out, &hd, sizeof(hd));
+    out += sizeof(hd);
+    for (const SnapPart& sp : snapshot_parts(h)) {
+        CU(h, cudaMemcpy(out, sp.dev, sp.bytes, cudaMemcpyDeviceToHost));
+        out += sp.bytes;
+    }
+    return DBSGYM_OK;
+}
+
+int dbsgym_set_state(DbsGymHandle* h, const void* blob, uint64_t bytes) {
+    if (!h || !blob) return fail(h, DBSGYM_EINVAL, "null argument");
+    uint64_t need = 0;
+    dbsgym_state_bytes(h, &need);
+    if (bytes < need) return fail(h, DBSGYM_EINVAL, "snapshot is %llu bytes, this handle needs %llu",
+                                  (unsigned long long)bytes, (unsigned long long)need);
+    SnapshotHeader hd, want = snapshot_header(h, need);
+    memcpy(&hd, blob, sizeof(hd));
+    if (memcmp(&hd, &want, sizeof(hd)) != 0)
+        return fail(h, DBSGYM_EINVAL, "snapshot does not belong to a handle of this shape (n_envs, n_osc, window, precision, ...)");
+    if (h->mirror_pending) return fail(h, DBSGYM_ESTATE, "a host-mirror step is in flight");
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaDeviceSynchronize());
+    const unsigned char* in = static_cast<const unsigned char*>(blob) + sizeof(hd);
+    for (const SnapPart& sp : snapshot_parts(h)) {
+        CU(h, cudaMemcpy(sp.dev, in, sp.bytes, cudaMemcpyHostToDevice));
+        in += sp.bytes;
+    }
+    if (h->mirror_on) {                             // the host mirror follows the restored rings
+        int rc = mirror_refresh(h, nullptr, h->B);
+        if (rc) return rc;
+        CU(h, cudaStreamSynchronize(h->stream));
+    }
+    return DBSGYM_OK;
+}
+
+int dbsgym_launch_count(DbsGymHandle* h, uint64_t* launches, int32_t reset) {
+    if (!h || !launches) return DBSGYM_EINVAL;
+    *launches = h->n_launches;
+    if (reset) h->n_launches = 0;
     return DBSGYM_OK;
 }
 
@@ -1149,7 +1352,8 @@ int dbsgym_set_window(DbsGymHandle* h, const int32_t* env_ids, int32_t n, const 
     CU(h, launch_spec_init(h, ids, n, h->stream));
     CU(h, cudaStreamSynchronize(h->stream));
     if (h->mirror_on) {                             // keep the host mirror in sync with the overwritten rings
-        CU(h, launch_obs(h, nullptr, nullptr, nullptr, 0, ids, n, h->stream));
+        rc = mirror_refresh(h, ids, n);
+        if (rc) return rc;
         CU(h, cudaStreamSynchronize(h->stream));
     }
     return DBSGYM_OK;
@@ -1216,7 +1420,9 @@ int dbsgym_trace_begin(DbsGymHandle* h, int32_t capacity) {
     if (!h->fuse_tail) return fail(h, DBSGYM_ESTATE, "the evaluation trace needs a beta-power reward (fused observation tail)");
     CU(h, cudaSetDevice(h->cfg.device));
     CU(h, cudaStreamSynchronize(h->stream));
-    if (capacity > h->trace_cap) {
+    CU(h, enter_own(h));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (capacity != h->trace_cap) {                 // the row stride of the trace IS the capacity (header: [n_envs][capacity])
         if (h->trace) cudaFree(h->trace);
         h->trace = nullptr; h->trace_cap = 0;
         CU(h, cudaMalloc(&h->trace, (size_t)h->B * capacity * sizeof(double)));
@@ -1294,6 +1500,10 @@ int dbsgym_measure_fp32_peak(int32_t device, double ms_target, double* tflops) {
     return DBSGYM_OK;
 }
 
+int dbsgym_measure_mufu_peak(int32_t device, double ms_target, double* tops) {
+    return dbsgym_measure_fp32_peak_mode(device, ms_target, 2, tops);
+}
+
 int dbsgym_measure_fp32_peak_mode(int32_t device, double ms_target, int32_t packed, double* tflops) {
     if (!tflops) return DBSGYM_EINVAL;
     DbsGymHandle* h = nullptr;
@@ -1310,14 +1520,16 @@ int dbsgym_measure_fp32_peak_mode(int32_t device, double ms_target, int32_t pack
     double best = 0.0;
     for (int rep = 0; rep < 8; ++rep) {
         cudaEventRecord(a);
-        if (packed) fma2_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001f, 1e-9f);
+        if (packed == 2) mufu_peak_kernel<<<blocks, threads>>>(out, iters, 1e-3f);
+        else if (packed) fma2_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001f, 1e-9f);
         else fma_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001f, 1e-9f);
         cudaEventRecord(b);
         cudaError_t e = cudaEventSynchronize(b);
         if (e != cudaSuccess) { cudaFree(out); return fail(h, DBSGYM_ECUDA, "peak kernel: %s", cudaGetErrorString(e)); }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, a, b);
-        const double fl = (packed ? 4.0 : 2.0) * kChains * (double)iters * blocks * threads;
+        // packed == 2: special-function operations (one MUFU each; the FADD between them runs on another pipe)
+        const double fl = (packed == 2 ? 2.0 : packed ? 4.0 : 2.0) * kChains * (double)iters * blocks * threads;
         const double tf = fl / (ms * 1e-3) / 1e12;
         if (rep >= 2 && tf > best) best = tf;
         if (ms < ms_target && iters < (1 << 24)) iters *= 2;

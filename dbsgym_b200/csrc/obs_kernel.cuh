@@ -33,6 +33,7 @@ struct ObsParams {
     void* ring; int32_t* head;
     const double* lfp_rec; const int32_t* n_samples;
     float* obs; float* samples_f; float* mirror; float* reward_f; double* reward; uint8_t* done_out; uint8_t* done_dev;
+    int mir_len; int32_t* mpos;     // host mirror log: row = 2 * mir_len floats, per-environment write column (dbsgym.h)
     int32_t* step_idx; const int32_t* episode_len; const double* u;
     int kind, nbins;
     double power_scale, action_cost, threshold, threshold_penalty, temp_scale;
@@ -90,9 +91,11 @@ __global__ void __launch_bounds__(kObsThreads) obs_kernel(const ObsParams p) {
         xs[pos] = v;
         if (p.samples_f) p.samples_f[(size_t)env * p.smax + i] = (float)v;
         if (p.mirror) {                               // zero-copy store into the pinned host mirror (both copies)
-            float* mr = p.mirror + (size_t)env * 2 * W;
-            mr[pos] = (float)v;
-            mr[pos + W] = (float)v;
+            float* mr = p.mirror + (size_t)env * 2 * p.mir_len;
+            int c = p.mpos[env] + i;
+            if (c >= p.mir_len) c -= p.mir_len;
+            mr[c] = (float)v;
+            mr[c + p.mir_len] = (float)v;
         }
     }
     int new_head = head + S;
@@ -108,9 +111,17 @@ __global__ void __launch_bounds__(kObsThreads) obs_kernel(const ObsParams p) {
         }
     }
     if (!p.append) {
-        if (p.mirror) {                               // reset / refresh: the whole window, ring storage order
-            float* mr = p.mirror + (size_t)env * 2 * W;
-            for (int m = tid; m < W; m += kObsThreads) { const float v = (float)xs[m]; mr[m] = v; mr[m + W] = v; }
+        if (p.mirror) {                               // reset / refresh: the whole window, ending at the write column
+            float* mr = p.mirror + (size_t)env * 2 * p.mir_len;
+            const int mp = p.mpos[env];
+            for (int m = tid; m < W; m += kObsThreads) {
+                int n = m - new_head;                 // chronological index of ring slot m
+                if (n < 0) n += W;
+                int c = mp - W + n;
+                if (c < 0) c += p.mir_len;
+                const float v = (float)xs[m];
+                mr[c] = v; mr[c + p.mir_len] = v;
+            }
         }
         return;
     }
@@ -195,6 +206,11 @@ __global__ void __launch_bounds__(kObsThreads) obs_kernel(const ObsParams p) {
         p.done_dev[env] = dn;
         if (p.done_out) p.done_out[env] = dn;
         p.head[env] = new_head;
+        if (p.mirror) {
+            int nm = p.mpos[env] + S;
+            if (nm >= p.mir_len) nm -= p.mir_len;
+            p.mpos[env] = nm;
+        }
     }
 }
 
@@ -230,9 +246,11 @@ __global__ void __launch_bounds__(kObsThreads) obs_kernel_fast(const ObsParams p
         ring[pos] = v;
         if (p.samples_f) p.samples_f[(size_t)env * p.smax + tid] = (float)v;
         if (p.mirror) {
-            float* mr = p.mirror + (size_t)env * 2 * W;
-            mr[pos] = (float)v;
-            mr[pos + W] = (float)v;
+            float* mr = p.mirror + (size_t)env * 2 * p.mir_len;
+            int c = p.mpos[env] + tid;
+            if (c >= p.mir_len) c -= p.mir_len;
+            mr[c] = (float)v;
+            mr[c + p.mir_len] = (float)v;
         }
     }
     {
@@ -309,6 +327,11 @@ __global__ void __launch_bounds__(kObsThreads) obs_kernel_fast(const ObsParams p
         p.done_dev[env] = dn;
         if (p.done_out) p.done_out[env] = dn;
         p.head[env] = new_head;
+        if (p.mirror) {
+            int nm = p.mpos[env] + S;
+            if (nm >= p.mir_len) nm -= p.mir_len;
+            p.mpos[env] = nm;
+        }
     }
 }
 

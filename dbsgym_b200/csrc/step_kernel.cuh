@@ -77,6 +77,9 @@ struct StepParams {
     double* spec;                  // [B][2 * kTailBins] running DFT bins of the ring (storage order), float64
     const double* tw_full;         // [W][nbins][2] cos, sin of 2*pi*k*m/W
     float* samples_f; float* mirror; float* reward_f; double* reward; uint8_t* done_out; uint8_t* done_dev;
+    // host mirror (append-only log, see dbsgym.h: dbsgym_host_mirror): rows of 2 * mir_len floats, every sample stored at
+    // column c and c + mir_len, c = per-environment write position mpos advanced modulo mir_len = W + guard
+    int mir_len; int32_t* mpos;
     int32_t* step_idx_rw; const int32_t* episode_len;
     int32_t* nsamp_out; int32_t* head_out;      // optional copies of n_samples / the new ring head (mapped host memory)
     // FSAL across segments and launches (fp32 mode): the first stage of a segment is f(y0) with the NEW pulse; the
@@ -763,7 +766,7 @@ __device__ __forceinline__ void obs_tail_prefetch(const StepParams& p, int env, 
         t_pos[lane] = pos;
         t_delta[lane] = (double)(reinterpret_cast<const real*>(p.ring) + (size_t)env * W)[pos];
     }
-    if (lane == 0) t_pos[32] = head;
+    if (lane == 0) { t_pos[32] = head; t_pos[33] = p.mirror ? p.mpos[env] : 0; }
 }
 
 template <typename real>
@@ -779,9 +782,11 @@ __device__ __forceinline__ void obs_tail(const StepParams& p, int env, int lane,
         ring[pos] = v;
         if (p.samples_f) p.samples_f[(size_t)env * p.smax + lane] = (float)v;
         if (p.mirror) {                               // zero-copy store into the pinned host mirror (both copies)
-            float* mr = p.mirror + (size_t)env * 2 * W;
-            mr[pos] = (float)v;
-            mr[pos + W] = (float)v;
+            float* mr = p.mirror + (size_t)env * 2 * p.mir_len;
+            int c = t_pos[33] + lane;
+            if (c >= p.mir_len) c -= p.mir_len;
+            mr[c] = (float)v;
+            mr[c + p.mir_len] = (float)v;
         }
         t_delta[lane] = (double)v - t_delta[lane];
         if (p.trace) {                                // evaluation trace: theta_mean of the step (env.py:441)
@@ -824,8 +829,14 @@ __device__ __forceinline__ void obs_tail(const StepParams& p, int env, int lane,
         if (nh >= W) nh -= W;
         p.head[env] = nh;
         if (p.trace) p.trace_len[env] = min(p.trace_len[env] + S, p.trace_cap);
+        int nm = nh;                                  // reported position: the mirror's write column when it is on
+        if (p.mirror) {
+            nm = t_pos[33] + S;
+            if (nm >= p.mir_len) nm -= p.mir_len;
+            p.mpos[env] = nm;
+        }
         if (p.nsamp_out) p.nsamp_out[env] = S;
-        if (p.head_out) p.head_out[env] = nh;
+        if (p.head_out) p.head_out[env] = nm;
     }
 }
 

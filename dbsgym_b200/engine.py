@@ -42,7 +42,10 @@ def _f64(a, shape=None):
 class KuramotoEngine:
     def __init__(self, n_envs, n_osc, grid_size, window, K, *, precision="f32", coupling_table=None,
                  alpha=None, device=0, max_step_samples=20, rtol=1e-5, atol=1e-5, dt0=0.05,
-                 action_bounds=(-5.0, 5.0), max_steps=4096):
+                 action_bounds=(-5.0, 5.0), max_steps=4096, options=None):
+        """``options``: tuning / diagnostic switches of DbsGymConfig (include/dbsgym.h) -- ``mw`` (None auto, False
+        never, True always use the multi-worker step kernel), ``force_cluster``, ``ctas_per_sm`` and the boolean A/B
+        switches ``no_geo1``, ``no_sym``, ``no_fsal_reuse``, ``no_fused_obs``, ``no_fast_obs``."""
         if precision not in ("f32", "f64"):
             raise ValueError("precision must be 'f32' or 'f64'")
         if (coupling_table is None) == (alpha is None):
@@ -63,6 +66,21 @@ class KuramotoEngine:
         cfg.K, cfg.rtol, cfg.atol, cfg.dt0 = float(K), float(rtol), float(atol), float(dt0)
         cfg.safety, cfg.factor_min, cfg.factor_max = 0.9, 0.2, 10.0     # diffrax PIDController defaults
         cfg.action_lo, cfg.action_hi = float(action_bounds[0]), float(action_bounds[1])
+        opt = dict(options or {})
+        mw = opt.pop("mw", None)
+        cfg.mw_mode = 0 if mw is None else (2 if mw else 1)
+        cfg.force_cluster = int(opt.pop("force_cluster", 0) or 0)
+        cfg.ctas_per_sm = int(opt.pop("ctas_per_sm", 0) or 0)
+        flags = 0
+        for name, bit in (("no_geo1", _capi.DBG_NO_GEO1), ("no_sym", _capi.DBG_NO_SYM),
+                          ("no_fsal_reuse", _capi.DBG_NO_FSAL_REUSE), ("no_fused_obs", _capi.DBG_NO_FUSED_OBS),
+                          ("no_fast_obs", _capi.DBG_NO_FAST_OBS)):
+            if opt.pop(name, False):
+                flags |= bit
+        if opt:
+            raise ValueError(f"unknown engine options: {sorted(opt)}")
+        cfg.debug_flags = flags
+        self.options = dict(options or {})
         self._h = C.c_void_p()
         rc = self.lib.dbsgym_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
@@ -174,10 +192,11 @@ class KuramotoEngine:
                                                    _capi.ptr(n_samples), _capi.ptr(reward), _capi.ptr(done)))
 
     def host_mirror(self):
-        """Pinned [B, 2W] float32 host array the GPU keeps in sync with the observation rings (dbsgym.h)."""
-        ptr = C.POINTER(C.c_float)()
-        self._ck(self.lib.dbsgym_host_mirror(self._h, C.byref(ptr)))
-        return np.ctypeslib.as_array(ptr, shape=(self.n_envs, 2 * self.window))
+        """The CURRENT pinned [B, 2 (W + 256)] float32 host log the GPU appends the window samples to (dbsgym.h:
+        dbsgym_host_mirror).  Ask again after every transient(): a reset moves on to the other buffer."""
+        ptr, row = C.POINTER(C.c_float)(), C.c_int32(0)
+        self._ck(self.lib.dbsgym_host_mirror(self._h, C.byref(ptr), C.byref(row)))
+        return np.ctypeslib.as_array(ptr, shape=(self.n_envs, row.value))
 
     def step_host_mirror(self, actions, reward, done):
         """One step; the host mirror is updated by the GPU.  Returns (pos, n_new): the chronological window of
@@ -224,8 +243,26 @@ class KuramotoEngine:
         ids = _ids(env_ids)
         n = self.n_envs if ids is None else len(ids)
         y = np.empty((n, self.n_osc))
-        self._ck(self.lib.dbsgym_get_state(self._h, _capi.ptr(ids), n, _capi.ptr(y)))
+        self._ck(self.lib.dbsgym_get_phases(self._h, _capi.ptr(ids), n, _capi.ptr(y)))
         return y
+
+    def get_state(self):
+        """Opaque snapshot of the whole handle (dbsgym.h: dbsgym_get_state) as a uint8 array."""
+        nb = C.c_uint64()
+        self._ck(self.lib.dbsgym_state_bytes(self._h, C.byref(nb)))
+        blob = np.empty(nb.value, dtype=np.uint8)
+        self._ck(self.lib.dbsgym_get_state(self._h, _capi.ptr(blob), nb.value))
+        return blob
+
+    def set_state(self, blob):
+        blob = np.ascontiguousarray(blob, dtype=np.uint8)
+        self._ck(self.lib.dbsgym_set_state(self._h, _capi.ptr(blob), blob.size))
+
+    def launch_count(self, reset=False):
+        """Kernels launched through this handle since create / the last reset of the count."""
+        v = C.c_uint64()
+        self._ck(self.lib.dbsgym_launch_count(self._h, C.byref(v), 1 if reset else 0))
+        return v.value
 
     def window_values(self, env_ids=None):
         ids = _ids(env_ids)
@@ -307,6 +344,16 @@ class KuramotoEngine:
         ms = (C.c_float * 2)()
         self._ck(self.lib.dbsgym_last_step_ms(self._h, ms))
         return float(ms[0]), float(ms[1])
+
+
+def measure_mufu_peak(device=0, ms_target=20.0):
+    """MUFU (sin / cos special-function unit) peak in 1e12 operations per second."""
+    lib = _capi.load()
+    out = C.c_double()
+    rc = lib.dbsgym_measure_mufu_peak(int(device), float(ms_target), C.byref(out))
+    if rc != 0:
+        raise _capi.DbsGymError(f"MUFU peak measurement failed ({rc})")
+    return out.value
 
 
 def measure_fp32_peak(device=0, ms_target=20.0, packed=None):

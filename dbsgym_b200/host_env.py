@@ -126,7 +126,7 @@ class HostEnvState:
                                                      M=self.reset_plasticity_episode * 2,
                                                      step_scale=self.plasticity_percent * 0.01)
         elif self.verbose:
-            print("No temporal drift events!")
+            print("temporal drift is off")
         self.spatial_events = []
         self.spatial_var_freq = p["spatial_var_freq"]
         self.spatial_var_episode = self.spatial_var_freq
@@ -194,14 +194,14 @@ class HostEnvState:
                 if self.save_events:
                     self.temporal_events["electrode_drift"].append([self.reset_count, self.elec_coords])
                 if self.verbose:
-                    print(f"Electode drift! Changed electrode location to {self.elec_coords}")
+                    print(f"[reset {self.reset_count}] electrode moved to {self.elec_coords}")
             if self.elec_encaps_episode == self.reset_count:
                 self.elec_encaps_episode += self.calc_next_event(p["encapsulation_drift_freq"], [-2, -1, 0, 1, 2])
                 self.encapsulation_coeff += self.encaps_precent      # added as an absolute amount (F7)
                 if self.save_events:
                     self.temporal_events["encapsulation_drift"].append([self.reset_count, self.encaps_precent])
                 if self.verbose:
-                    print(f"Electode encapsulation! Reduced electrode conductances by {self.encapsulation_coeff}")
+                    print(f"[reset {self.reset_count}] encapsulation: conduct_modifier is now {self.encapsulation_coeff}")
             if self.plasticity_episode == self.reset_count:
                 self.plasticity_episode += self.calc_next_temp_event(p["plasticity_drift_freq"], [0, 1])
                 self.w0_without_locus = self.w0_process[self.plasticity_process_count]
@@ -209,10 +209,10 @@ class HostEnvState:
                 if self.save_events:
                     self.temporal_events["plasticity_drift"].append([self.reset_count, self.w0_without_locus])
                 if self.verbose:
-                    print(f"Drift of w0 by {self.plasticity_percent}%, to {self.plasticity_process_count}")
+                    print(f"[reset {self.reset_count}] plasticity walk advanced to entry {self.plasticity_process_count}")
             if self.reset_count % self.reset_plasticity_episode == 0:
                 if self.verbose:
-                    print("Reseting plastisity...")
+                    print(f"[reset {self.reset_count}] plasticity walk regenerated")
                 self.plasticity_process_count = 0
                 self.w0_without_locus = copy.deepcopy(self.w0_without_locus_)
                 self.w0_process = generate_perturbations(self.w0_without_locus,
@@ -227,7 +227,7 @@ class HostEnvState:
                 self.spatial_var_episode += self.spatial_var_freq
                 self.spatial_events.append([self.reset_count, table[pick]])
                 if self.verbose:
-                    print("Reinit spatial parameters! New coordinates are: ", table[pick])
+                    print(f"[reset {self.reset_count}] new stimulation / recording contacts: {table[pick]}")
         if p["save_events"] and p["log_path"] is not None and self.reset_count > 1:
             np.save(os.path.join(p["log_path"], f"temp_{self.reset_count}.npy"), self.temporal_events)
 

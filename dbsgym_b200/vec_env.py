@@ -39,16 +39,49 @@ class _LazyAttrList:
         return (self._getter(i) for i in self._indices)
 
 
+class _InfoList(list):
+    """``infos`` of a step: one dict per environment like DummyVecEnv returns, but the dicts of environments that
+    did not finish are created only when somebody indexes them (building thousands of dicts per step costs more
+    than the GPU step).  Every environment gets its OWN dict, so a wrapper that mutates ``infos[i]`` touches
+    nothing else."""
+
+    def __init__(self, n):
+        super().__init__([None] * n)
+
+    def _fill(self, i):
+        d = list.__getitem__(self, i)
+        if d is None:
+            d = {"TimeLimit.truncated": False}
+            list.__setitem__(self, i, d)
+        return d
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self._fill(i) for i in range(*k.indices(len(self)))]
+        return self._fill(k if k >= 0 else k + len(self))
+
+    def __iter__(self):
+        return (self._fill(i) for i in range(len(self)))
+
+
 class BatchedKuramotoVecEnv(VecEnvBase):
+    """``copy_obs=False`` (default): ``step_wait`` returns a zero-copy view of the pinned host log the GPU appends the
+    window samples to.  Later steps only append behind it and a reset switches to a second buffer, so the array
+    stays intact for at least one further ``step()`` -- what SB3 needs: ``collect_rollouts`` stores
+    ``self._last_obs`` right after the NEXT ``env.step()`` returns -- and in practice for 13 steps.  Keep an
+    observation longer than that only as a copy, or pass ``copy_obs=True`` for arrays you own."""
+
     def __init__(self, params_dicts, num_envs=None, precision=None, device=0, compat_env2=False,
-                 monitor=True, transfer="delta"):
+                 monitor=True, transfer="delta", copy_obs=False, engine_options=None):
         if isinstance(params_dicts, dict):
             n = int(num_envs or params_dicts.get("num_envs", 1))
             # like DummyVecEnv([make_env(d)] * n): every env gets its own copy of the dict
             params_dicts = [copy.deepcopy(params_dicts) for _ in range(n)]
         p0 = params_dicts[0]
         self.core = BatchedKuramoto(params_dicts, precision=precision or _default_precision(p0),
-                                    device=device, compat_env2=compat_env2, transfer=transfer)
+                                    device=device, compat_env2=compat_env2, transfer=transfer,
+                                    engine_options=engine_options)
+        self.copy_obs = bool(copy_obs)
         B, W = self.core.num_envs, self.core.window
         obs_space = Box(low=-1.5, high=1.5, shape=(1, W), dtype=np.float32)
         act_space = Box(low=-1., high=1., shape=(1,), dtype=np.float32)
@@ -75,16 +108,16 @@ class BatchedKuramotoVecEnv(VecEnvBase):
         results runs while the GPU works, step_wait() only waits and reads the results."""
         self.core.step_begin(np.asarray(actions, dtype=np.float32).reshape(self.num_envs, -1)[:, 0])
         self._ep_len += 1
-        # one shared info dict for the environments that did not finish (building thousands of dicts per
-        # step costs more than the GPU step); finished environments get their own
-        self._infos = [{"TimeLimit.truncated": False}] * self.num_envs
+        self._infos = _InfoList(self.num_envs)        # per-environment dicts, created when indexed
 
     def step_wait(self):
         obs, rew, done = self.core.step_end()
         obs = obs.reshape(self.num_envs, 1, -1)       # a view (host window mirror / pinned buffer): no 38 MB copy
+        if self.copy_obs:
+            obs = obs.copy()
         rew = rew.copy()
         done = done.copy()
-        self._ep_ret += rew
+        self._ep_ret += rew                           # float64 accumulation of the float32 rewards SB3 sees (Monitor does the same)
         infos = self._infos
         finished = np.flatnonzero(done)
         if finished.size:
@@ -95,8 +128,10 @@ class BatchedKuramotoVecEnv(VecEnvBase):
                                            "t": round(time.time() - self._t0, 6)}
             self.core.reset_envs(finished)            # index order == sequential DummyVecEnv order
             term = {i: infos[i]["terminal_observation"] for i in finished}
-            fresh = self.core.observations()          # writes the whole current obs buffer
+            fresh = self.core.observations_after_reset()     # owned array / view of the NEW mirror buffer
             obs = fresh.reshape(self.num_envs, 1, -1)
+            if self.copy_obs:
+                obs = obs.copy()
             for i in finished:
                 infos[i]["terminal_observation"] = term[i]
             self._ep_ret[finished] = 0

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define DBSGYM_ABI_VERSION 1
+#define DBSGYM_ABI_VERSION 2
 #define DBSGYM_OWN_STREAM ((void*)(intptr_t)-1)
 
 typedef struct DbsGymHandle DbsGymHandle;
@@ -70,7 +70,20 @@ typedef struct DbsGymConfig {
     double   rtol, atol, dt0;   /* env.py:249, :267                                               */
     double   safety, factor_min, factor_max;   /* diffrax PIDController defaults .9 / .2 / 10     */
     double   action_lo, action_hi;             /* dbs_action_bounds, env.py:389-393               */
+    /* tuning / diagnostics (all 0 = library defaults; nothing in the library reads the environment) */
+    int32_t  mw_mode;           /* multi-worker step kernel (8 x 8 x 8 grid, fp32): 0 = when the launch fills the
+                                   GPU, 1 = never, 2 = always                                                  */
+    int32_t  force_cluster;     /* > 1: integrate one environment with a cluster of that many CTAs even when
+                                   n_osc <= 4096 (tests of the cluster path at small sizes)                    */
+    int32_t  ctas_per_sm;       /* > 0: pad shared memory so that exactly this many CTAs share an SM           */
+    uint32_t debug_flags;       /* DBSGYM_DBG_* (A/B switches used by tests and tuning runs)                   */
 } DbsGymConfig;
+
+enum { DBSGYM_DBG_NO_GEO1 = 1u,          /* skip the kernels specialised for the 8 x 8 x 8 grid               */
+       DBSGYM_DBG_NO_SYM = 2u,           /* plain Toeplitz contraction instead of the parity sectors          */
+       DBSGYM_DBG_NO_FSAL_REUSE = 4u,    /* evaluate the first stage of every segment (fp32 too)              */
+       DBSGYM_DBG_NO_FUSED_OBS = 8u,     /* separate observation / reward kernel instead of the fused tail    */
+       DBSGYM_DBG_NO_FAST_OBS = 16u };   /* generic observation kernel instead of the streamlined one         */
 
 typedef struct DbsGymRewardSpec {
     uint32_t struct_bytes;
@@ -162,16 +175,23 @@ int dbsgym_step_host(DbsGymHandle* h, const float* actions, float* obs,
  * slide its own copy (obs_{t+1} = concat(obs_t[n:], samples)).  reward / done as above. */
 int dbsgym_step_host_samples(DbsGymHandle* h, const float* actions, float* samples,
                              int32_t* n_samples, float* reward, uint8_t* done);
-/* Host mirror of the observation windows, written by the GPU itself.  dbsgym_host_mirror() returns
- * (allocating on first use) a pinned, device-mapped float32 array [B][2*W] owned by the library.  The
- * observation kernel stores every window sample twice through PCIe, at its ring column c and at c + W,
- * so the chronological window of environment b is always the CONTIGUOUS slice
- * mirror[b][pos .. pos + W - 1] and no data ever has to be moved or re-copied by the CPU.
+/* Host mirror of the observation windows, written by the GPU itself: an append-only sample log per environment.
+ * dbsgym_host_mirror() returns the CURRENT one of two pinned, device-mapped float32 arrays [B][*row_floats]
+ * (row_floats = 2 * L, L = W + 256) owned by the library.  The step kernel stores every new window sample twice
+ * through PCIe, at column c and at c + L (c = the environment's write position, advanced modulo L), so the
+ * chronological window of environment b is always the CONTIGUOUS slice mirror[b][pos .. pos + W - 1] and no data
+ * ever has to be moved or re-copied by the CPU.
+ * LIFETIME of a window handed out this way (what lets a VecEnv return it without copying, like the arrays
+ * DummyVecEnv returns): the next steps only append BEHIND it -- its first sample is overwritten after 256 further
+ * samples, i.e. it stays intact for at least 13 more steps (<= 19 samples each) -- and a reset
+ * (dbsgym_transient) switches to the other buffer and rewrites all windows there, so a window of the old buffer
+ * stays intact until the reset after the next one.  Call dbsgym_host_mirror() again after every dbsgym_transient
+ * to get the buffer that is current.
  * dbsgym_step_host_mirror() = one step; only actions (H2D) and reward / done / the new samples (D2H,
  * zero-copy) cross PCIe.  *pos receives the column of the oldest sample and *n_new the number of new
- * samples; if the environments are out of lockstep (different ring positions) *n_new = -1 and the caller
- * must use per-environment positions (dbsgym_get_episode / dbsgym_get_obs_host) instead. */
-int dbsgym_host_mirror(DbsGymHandle* h, float** mirror);
+ * samples; if the environments are out of lockstep (different log positions, possible after a reset of a subset)
+ * *n_new = -1 and the caller must read the windows back instead (dbsgym_get_obs_host). */
+int dbsgym_host_mirror(DbsGymHandle* h, float** mirror, int32_t* row_floats);
 int dbsgym_step_host_mirror(DbsGymHandle* h, const float* actions, int32_t* pos, int32_t* n_new,
                             float* reward, uint8_t* done);
 /* reset observation (window as float32) of all environments to a host buffer [B][W] */
@@ -187,7 +207,19 @@ int dbsgym_get_obs_host(DbsGymHandle* h, float* obs);
 int dbsgym_get_lfp(DbsGymHandle* h, double* lfp_true, double* lfp_rec, int32_t* n_samples);
 int dbsgym_get_rewards(DbsGymHandle* h, double* reward, double* u);
 /* unwrapped phases, float64 [n][N] */
-int dbsgym_get_state(DbsGymHandle* h, const int32_t* env_ids, int32_t n, double* y);
+int dbsgym_get_phases(DbsGymHandle* h, const int32_t* env_ids, int32_t n, double* y);
+/* Snapshot / restore of the whole handle (the reference never checkpoints the environment; SB3's
+ * CheckpointCallback saves only the agent, aDBS_RL/train_aDBS_RL.py:145-150).  The blob holds everything later steps
+ * depend on -- phases + winding counts, w0 / conductances, observation rings + heads, running rfft bins, step counters,
+ * done flags, the carried FSAL row, the last step's samples, reward, u and the solver counters -- so that
+ * set_state(get_state()) followed by the same actions reproduces the same outputs bit for bit.  Coupling, schedule and
+ * reward definition are configuration, not state: the restoring handle must have been set up the same way
+ * (the header of the blob is checked against n_envs, n_osc, window, precision). */
+int dbsgym_state_bytes(const DbsGymHandle* h, uint64_t* bytes);
+int dbsgym_get_state(DbsGymHandle* h, void* blob, uint64_t bytes);
+int dbsgym_set_state(DbsGymHandle* h, const void* blob, uint64_t bytes);
+/* kernels launched through this handle since create (or the last call with reset != 0) */
+int dbsgym_launch_count(DbsGymHandle* h, uint64_t* launches, int32_t reset);
 /* observation window in chronological order, float64 [n][W] */
 int dbsgym_get_window(DbsGymHandle* h, const int32_t* env_ids, int32_t n, double* window);
 int dbsgym_set_window(DbsGymHandle* h, const int32_t* env_ids, int32_t n, const double* window);
@@ -231,7 +263,9 @@ int dbsgym_eval_bbpow(DbsGymHandle* h, const DbsGymEvalSpec* spec, const double*
 /* FP32-FMA throughput micro-benchmark used for the roofline denominator: runs a dependent-
  * chain FFMA kernel on `device` for about `ms_target` ms; returns TFLOP/s in *tflops. */
 int dbsgym_measure_fp32_peak(int32_t device, double ms_target, double* tflops);
-/* the two variants separately: packed == 0 scalar FFMA chains, packed == 1 FFMA2 (f32x2) chains */
+/* special-function unit: dependent MUFU.SIN / MUFU.COS chains, result in 1e12 operations per second */
+int dbsgym_measure_mufu_peak(int32_t device, double ms_target, double* tops);
+/* the variants separately: packed == 0 scalar FFMA chains, packed == 1 FFMA2 (f32x2) chains, 2 = MUFU (as above) */
 int dbsgym_measure_fp32_peak_mode(int32_t device, double ms_target, int32_t packed, double* tflops);
 
 #ifdef __cplusplus

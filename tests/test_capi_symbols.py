@@ -22,12 +22,12 @@ def test_header_and_exports_agree(lib):
     raw = C.CDLL(_capi.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.dbsgym_abi_version() == 1
+    assert lib.dbsgym_abi_version() == _capi.ABI_VERSION == 2
 
 
 def test_struct_layouts_match_header():
     # sizes are checked inside the library as well (struct_bytes); these guard the ctypes mirror
-    assert C.sizeof(_capi.DbsGymConfig) == 4 * 12 + 8 * 9
+    assert C.sizeof(_capi.DbsGymConfig) == 4 * 12 + 8 * 9 + 4 * 4
     assert C.sizeof(_capi.DbsGymRewardSpec) == 4 * 4 + 8 * 5
     assert C.sizeof(_capi.DbsGymEvalSpec) == 4 * 2 + 8 * 14 + 4 * 2
 
@@ -71,6 +71,13 @@ def test_no_cpu_fallback(lib):
     import numpy as np
     with pytest.raises(_capi.DbsGymError, match="no CPU path|no CUDA|CUDA"):
         KuramotoEngine(1, 512, [8, 8, 8], 2340, 0.52, coupling_table=np.ones(512))
+
+
+def test_release_library_reads_no_environment_variables():
+    """Tuning / A-B switches travel in DbsGymConfig (mw_mode, force_cluster, ctas_per_sm, debug_flags): the library
+    itself must not consult the process environment."""
+    for f in ("api.cu", "step_kernel.cuh", "obs_kernel.cuh", "eval_kernel.cuh"):
+        assert "getenv" not in open(os.path.join(ROOT, "dbsgym_b200", "csrc", f)).read(), f
 
 
 def test_product_does_not_import_oracle():

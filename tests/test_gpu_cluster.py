@@ -5,19 +5,15 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _engine(N, gz, B, monkeypatch=None, force_cluster=None, precision="f32", gx=8, gy=8):
+def _engine(N, gz, B, force_cluster=None, precision="f32", gx=8, gy=8, mw=None):
     from dbsgym_b200.engine import KuramotoEngine
     from dbsgym_b200.geometry import coupling_table, distances_from, neuron_grid
     from dbsgym_b200.schedule import StepSchedule, transient_grid
-    if monkeypatch is not None:
-        if force_cluster:
-            monkeypatch.setenv("DBSGYM_FORCE_CLUSTER", str(force_cluster))
-        else:
-            monkeypatch.delenv("DBSGYM_FORCE_CLUSTER", raising=False)
+    options = {"force_cluster": force_cluster or 0, "mw": mw}
     coords, grid = neuron_grid(gx, gy, gz, N, 0.1)
     table = coupling_table(coords, grid, [gx, gy, gz], "cos")
     assert table is not None
-    eng = KuramotoEngine(B, N, [gx, gy, gz], 2340, 0.52, precision=precision, coupling_table=table)
+    eng = KuramotoEngine(B, N, [gx, gy, gz], 2340, 0.52, precision=precision, coupling_table=table, options=options)
     tt = transient_grid(200.0, 0.05)
     sched = StepSchedule(80, tt[-1], 0.15, 0.75, 0.05)
     eng.set_schedule(sched)
@@ -37,13 +33,13 @@ def _engine(N, gz, B, monkeypatch=None, force_cluster=None, precision="f32", gx=
 
 @pytest.mark.parametrize("N,gz,C,gx,gy", [(1024, 16, 2, 8, 8), (1024, 16, 4, 8, 8), (4096, 64, 8, 8, 8), (2048, 32, 2, 8, 8),
                                          (4096, 16, 2, 16, 16), (4096, 4, 4, 32, 32)])
-def test_cluster_mode_equals_single_cta_mode(monkeypatch, N, gz, C, gx, gy):
+def test_cluster_mode_equals_single_cta_mode(N, gz, C, gx, gy):
     """Same inputs through the single-CTA kernel and through the C-CTA cluster kernel (forced at a size both can run):
     steps, a transient with rejections, LFP, rewards and counters must agree (only reduction orders differ)."""
     acts = np.random.default_rng(1).uniform(-1, 1, (3, 3)).astype(np.float32)
     res = {}
     for mode in (None, C):
-        eng, d = _engine(N, gz, 3, monkeypatch, mode, gx=gx, gy=gy)
+        eng, d = _engine(N, gz, 3, mode, gx=gx, gy=gy)
         eng.counters(reset=True)
         out = []
         for a in acts:
@@ -111,8 +107,8 @@ def test_n8192_cluster_step_matches_oracle(gx, gy, gz):
 
 
 @pytest.mark.parametrize("B", [5, 21])
-def test_multi_worker_kernel_equals_the_single_environment_kernel(monkeypatch, B):
-    """DBSGYM_MW=1 forces the multi-worker step kernel (8 environments per CTA sharing the precomputed sector
+def test_multi_worker_kernel_equals_the_single_environment_kernel(B):
+    """options mw=True forces the multi-worker step kernel (8 environments per CTA sharing the precomputed sector
     coefficients, persistent loop, named barriers) at a batch size where the default would use one CTA per
     environment.  The contraction is the same sum in the same order; only the lane order of the warp reductions
     (LFP samples, error norm) differs, so results agree to an ulp of float32 and the counters exactly -- for full
@@ -120,8 +116,8 @@ def test_multi_worker_kernel_equals_the_single_environment_kernel(monkeypatch, B
     acts = np.random.default_rng(2).uniform(-1, 1, (4, B)).astype(np.float32)
     res = {}
     for mode in ("0", "1"):
-        monkeypatch.setenv("DBSGYM_MW", mode)
-        eng, d = _engine(512, 8, B)
+        eng, d = _engine(512, 8, B, mw=(mode == "1"))
+        assert eng.step_variant() == (4 if mode == "1" else 3)
         eng.counters(reset=True)
         out = []
         for a in acts[:3]:

@@ -1,6 +1,6 @@
 """The observation tail fused into the step kernel: ring append + incrementally updated rfft bins (beta-power
 rewards R1 / R3, reference env.py:447-454, :638-650, :669-688, utils.py:21-27) against a from-scratch numpy rfft
-of the device window, and against the separate observation kernel (DBSGYM_NO_FUSED_OBS=1)."""
+of the device window, and against the separate observation kernel (engine option no_fused_obs)."""
 import numpy as np
 import pytest
 
@@ -11,14 +11,14 @@ pytestmark = pytest.mark.gpu
 W = 2340
 
 
-def _engine(B, precision, reward="bbpow_action"):
+def _engine(B, precision, reward="bbpow_action", options=None):
     from dbsgym_b200.batched import BatchedKuramoto
     from dbsgym_b200.engine import KuramotoEngine
     from dbsgym_b200.geometry import coupling_table
     d = make_params("env1", 10)
     core = BatchedKuramoto([d], precision=precision)
     table = coupling_table(d["neur_coords"], d["neur_grid"], d["grid_size"], "cos")
-    eng = KuramotoEngine(B, 512, [8, 8, 8], W, d["K"], precision=precision, coupling_table=table)
+    eng = KuramotoEngine(B, 512, [8, 8, 8], W, d["K"], precision=precision, coupling_table=table, options=options)
     eng.set_schedule(core.schedule)
     eng.set_recording(True)
     eng.set_reward(reward, 0.05)
@@ -70,17 +70,13 @@ def test_incremental_bins_track_the_window_over_many_steps(precision):
 
 
 @pytest.mark.parametrize("reward", ["bbpow_action", "bbpow_threth_action"])
-def test_fused_tail_equals_separate_observation_kernel(monkeypatch, reward):
+def test_fused_tail_equals_separate_observation_kernel(reward):
     """Same inputs through both paths: identical phases, windows, observations, done flags and step
     counters; rewards agree to the float32 DFT accuracy of the separate kernel."""
     B, n = 5, 12
     outs = {}
     for mode in ("fused", "separate"):
-        if mode == "separate":
-            monkeypatch.setenv("DBSGYM_NO_FUSED_OBS", "1")
-        else:
-            monkeypatch.delenv("DBSGYM_NO_FUSED_OBS", raising=False)
-        eng, sched, rng = _engine(B, "f32", reward)
+        eng, sched, rng = _engine(B, "f32", reward, options={"no_fused_obs": mode == "separate"})
         eng.set_episode(None, step_idx=0, episode_len=n - 2)
         rec = []
         for k in range(n):
@@ -138,20 +134,16 @@ def test_device_evaluation_metric_matches_scipy_on_the_recorded_trace(precision)
     eng.close()
 
 
-def test_fsal_reuse_across_segments_and_launches(monkeypatch):
+def test_fsal_reuse_across_segments_and_launches():
     """fp32 mode takes the first stage of every segment from the last stage of the previous accepted sub-step (same
     state, only the pulse term changes) instead of evaluating the RHS again -- also across kernel launches and after
     a reset transient.  The counters keep the reference's (logical) count of 32 evaluations per step; 2 per step
     are reused (1 in the very first step after the vectors were uploaded); phases, windows and rewards agree with the
-    kernel that evaluates every stage (DBSGYM_NO_FSAL_REUSE=1) to float32 rounding."""
+    kernel that evaluates every stage (engine option no_fsal_reuse) to float32 rounding."""
     B, n = 6, 8
     outs = {}
     for mode in ("reuse", "evaluate"):
-        if mode == "evaluate":
-            monkeypatch.setenv("DBSGYM_NO_FSAL_REUSE", "1")
-        else:
-            monkeypatch.delenv("DBSGYM_NO_FSAL_REUSE", raising=False)
-        eng, sched, rng = _engine(B, "f32")
+        eng, sched, rng = _engine(B, "f32", options={"no_fsal_reuse": mode == "evaluate"})
         eng.counters(reset=True)
         for k in range(n):
             eng.step_host(rng.uniform(-1, 1, B).astype(np.float32))

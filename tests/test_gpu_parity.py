@@ -18,12 +18,12 @@ PHASE_TOL = {"f64": 1e-9, "f32": 1e-5}
 LFP_TOL = {"f64": 1e-11, "f32": 2e-6}
 
 
-def _engine_from_params(d, B, precision, force_dense=False, transfer="full"):
+def _engine_from_params(d, B, precision, force_dense=False, transfer="full", engine_options=None):
     # transfer="full": these tests overwrite device state between steps (teacher forcing), which the
     # host-side window mirror of the delta-transfer mode cannot see
     from dbsgym_b200.batched import BatchedKuramoto
     return BatchedKuramoto([copy.deepcopy(d) for _ in range(B)], precision=precision, force_dense=force_dense,
-                           transfer=transfer)
+                           transfer=transfer, engine_options=engine_options)
 
 
 def _teacher_forced(core, g, precision, n_steps, reward_tol_rel):
@@ -181,15 +181,14 @@ def test_half_grid_256_oscillators():
     core.close()
 
 
-def test_plain_toeplitz_contraction_matches_symmetric_one(monkeypatch):
-    """CPL_GRID (DBSGYM_NO_SYM=1) and the default CPL_GRID_SYM kernel evaluate the same sum."""
+def test_plain_toeplitz_contraction_matches_symmetric_one():
+    """CPL_GRID (engine option no_sym) and the default CPL_GRID_SYM kernel evaluate the same sum."""
     g = load_golden("step_env0.npz")
     d = make_params("env0", 10)
     outs = {}
     for nosym in ("0", "1"):
-        monkeypatch.setenv("DBSGYM_NO_SYM", nosym)
         for prec in ("f64", "f32"):
-            core = _engine_from_params(d, 1, prec)
+            core = _engine_from_params(d, 1, prec, engine_options={"no_sym": nosym == "1"})
             core.engine.set_env_params(None, y0=g["y_after_transient"][None, :])
             core.step(np.array([g["actions"][0]]))
             outs[(nosym, prec)] = core.engine.state()[0]

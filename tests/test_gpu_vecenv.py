@@ -269,3 +269,213 @@ def test_env2_drift_resets_match_reference_golden():
         assert env.elec_drift_episode == g["elec_drift_episode"][r]
         assert env.elec_encaps_episode == g["encaps_episode"][r]
     env.close()
+
+
+def _short_dicts(B, seed=30, episode_len=126.0):
+    return [make_params("env1", seed + e, transient_state_len=118.0, total_episode_len=episode_len,
+                        rand_seed=70 + seed + e) for e in range(B)]
+
+
+def test_step_wait_observation_stays_intact_across_following_steps_and_resets():
+    """ADVICE r1 (high) / VERDICT weak #2: the array step_wait() returns must not be modified by later steps.  The
+    default (zero-copy) VecEnv hands out a view of the pinned host log; it is held here WITHOUT copying across the
+    next 13 steps -- among them the auto-reset of every environment -- and compared with a copy taken at once."""
+    from dbsgym_b200.vec_env import BatchedKuramotoVecEnv
+    B = 4
+    venv = BatchedKuramotoVecEnv(_short_dicts(B, episode_len=18.0))          # 20-step episodes
+    held = [(venv.reset(),)]
+    held[0] = (held[0][0], held[0][0].copy(), 0)
+    rng = np.random.default_rng(4)
+    n_done = 0
+    for k in range(1, 60):
+        obs, rew, done, infos = venv.step(rng.uniform(-1, 1, (B, 1)).astype(np.float32))
+        n_done += int(done.all())
+        held.append((obs, obs.copy(), k))
+        for view, snapshot, born in held:
+            assert np.array_equal(view, snapshot), f"observation of step {born} changed during step {k}"
+        held = held[-13:]                                   # guaranteed lifetime: 13 further steps
+    assert n_done == 2
+    venv.close()
+
+
+class _RolloutBufferStandIn:
+    """The part of stable_baselines3.common.buffers.RolloutBuffer.add that matters here: the observation is copied into
+    the buffer WHEN add() IS CALLED -- and OnPolicyAlgorithm.collect_rollouts calls add(self._last_obs, ...) only after
+    env.step() of the following step has returned (same for _store_transition of the off-policy algorithms)."""
+
+    def __init__(self, n_steps, B, W):
+        self.observations = np.zeros((n_steps, B, 1, W), dtype=np.float32)
+        self.rewards = np.zeros((n_steps, B), dtype=np.float32)
+        self.episode_starts = np.zeros((n_steps, B), dtype=np.float32)
+        self.pos = 0
+
+    def add(self, obs, reward, episode_start):
+        self.observations[self.pos] = np.array(obs)
+        self.rewards[self.pos] = np.array(reward)
+        self.episode_starts[self.pos] = np.array(episode_start)
+        self.pos += 1
+
+
+def _collect_rollouts(venv, n_steps, seed):
+    """stable_baselines3 OnPolicyAlgorithm.collect_rollouts, call for call, with a random policy."""
+    B = venv.num_envs
+    buf = _RolloutBufferStandIn(n_steps, B, venv.observation_space.shape[1])
+    rng = np.random.default_rng(seed)
+    last_obs = venv.reset()
+    last_episode_starts = np.ones(B, dtype=bool)
+    terminal = []
+    for _ in range(n_steps):
+        actions = rng.uniform(-1, 1, (B, 1)).astype(np.float32)       # policy(obs_as_tensor(self._last_obs))
+        new_obs, rewards, dones, infos = venv.step(actions)
+        for idx, done in enumerate(dones):
+            if done and infos[idx].get("terminal_observation") is not None:
+                terminal.append(np.array(infos[idx]["terminal_observation"]))
+        buf.add(last_obs, rewards, last_episode_starts)               # <- after the step, exactly like SB3
+        last_obs = new_obs
+        last_episode_starts = dones
+    return buf, terminal
+
+
+def test_sb3_collect_rollouts_call_order_gives_the_same_buffer_as_owned_copies():
+    """The zero-copy VecEnv driven in SB3's call order (rollout_buffer.add(self._last_obs) AFTER the next env.step) must
+    fill the rollout buffer with exactly what a VecEnv that returns owned copies (DummyVecEnv semantics) gives."""
+    from dbsgym_b200.vec_env import BatchedKuramotoVecEnv
+    B, n_steps = 3, 45
+    bufs = {}
+    for mode, kw in (("views", {}), ("copies", {"copy_obs": True}), ("full", {"transfer": "full", "copy_obs": True})):
+        venv = BatchedKuramotoVecEnv(_short_dicts(B, seed=80, episode_len=18.0), **kw)
+        bufs[mode] = _collect_rollouts(venv, n_steps, seed=2)
+        venv.close()
+    ref, ref_term = bufs["full"]
+    assert ref.episode_starts.sum() == B * 3 and len(ref_term) == 2 * B      # two episode ends inside the rollout
+    for mode in ("views", "copies"):
+        buf, term = bufs[mode]
+        assert np.array_equal(buf.observations, ref.observations), mode
+        assert np.array_equal(buf.rewards, ref.rewards) and np.array_equal(buf.episode_starts, ref.episode_starts)
+        assert all(np.array_equal(a, b) for a, b in zip(term, ref_term))
+    # consecutive stored observations are genuinely different windows (the check above is not vacuous)
+    assert not np.array_equal(ref.observations[3], ref.observations[4])
+
+
+def test_out_of_lockstep_batch_falls_back_to_owned_readback_and_recovers():
+    """After a reset of a SUBSET the environments sit at different step indices (their steps append 17 / 18 / 19 samples
+    at different times), so the windows are no longer one common slice of the host log: step() must notice, return a
+    read-back (two alternating buffers: intact for one further step) that equals the device windows, and go back to the
+    zero-copy path after the next reset of all environments."""
+    from dbsgym_b200.batched import BatchedKuramoto
+    B = 3
+    core = BatchedKuramoto(_short_dicts(B, seed=60, episode_len=5400.0))
+    rng = np.random.default_rng(1)
+    for _ in range(70):                                   # past step 65, where the schedule changes from 18 to 19 / 17 samples
+        core.step(rng.uniform(-1, 1, B).astype(np.float32))
+    core.reset_envs([1])
+    prev = None
+    fell_back = False
+    for k in range(70):
+        obs, rew, done = core.step(rng.uniform(-1, 1, B).astype(np.float32))
+        np.testing.assert_array_equal(obs, core.engine.window_values().astype(np.float32))
+        fell_back = fell_back or not np.shares_memory(obs, core._mirror)
+        if prev is not None:
+            assert np.array_equal(prev[0], prev[1])       # last step's array survived this step
+        prev = (obs, obs.copy())
+    assert fell_back
+    core.reset_envs(range(B))
+    obs, rew, done = core.step(rng.uniform(-1, 1, B).astype(np.float32))
+    assert np.shares_memory(obs, core._mirror)
+    np.testing.assert_array_equal(obs, core.engine.window_values().astype(np.float32))
+    core.close()
+
+
+def test_snapshot_restore_round_trip_is_bit_exact():
+    """dbsgym_get_state / dbsgym_set_state: run 5 steps, snapshot, run 6 more; restore into the same handle AND into a
+    freshly built one, repeat the 6 steps: identical observations, rewards, phases, counters."""
+    from dbsgym_b200.batched import BatchedKuramoto
+    B = 3
+    dicts = _short_dicts(B, seed=90, episode_len=5400.0)
+    a = BatchedKuramoto(copy.deepcopy(dicts), transfer="full")
+    acts = np.random.default_rng(3).uniform(-1, 1, (11, B)).astype(np.float32)
+    for k in range(5):
+        a.step(acts[k])
+    blob = a.engine.get_state()
+
+    def tail(core):
+        out = []
+        for k in range(5, 11):
+            o, r, d = core.step(acts[k])
+            out.append((o.copy(), r.copy(), d.copy(), core.engine.state().copy(), core.engine.rewards()[0].copy()))
+        return out, core.engine.counters()
+    ref, c_ref = tail(a)
+    a.engine.set_state(blob)
+    again, c_again = tail(a)
+    b = BatchedKuramoto(copy.deepcopy(dicts), transfer="full")         # another handle of the same shape
+    b.engine.set_state(blob)
+    other, c_other = tail(b)
+    assert c_ref == c_again == c_other
+    for x, y, z in zip(ref, again, other):
+        for u, v, w in zip(x, y, z):
+            assert np.array_equal(u, v) and np.array_equal(u, w)
+    with pytest.raises(Exception, match="shape|bytes"):
+        c = BatchedKuramoto(copy.deepcopy(dicts[:2]), transfer="full")
+        try:
+            c.engine.set_state(blob)
+        finally:
+            c.close()
+    a.close(); b.close()
+
+
+def test_trace_capacity_can_shrink_between_evaluations():
+    """a second, SHORTER trace on the same handle must use its own capacity as the row stride."""
+    from dbsgym_b200.batched import BatchedKuramoto
+    B = 2
+    core = BatchedKuramoto(_short_dicts(B, seed=95, episode_len=5400.0))
+    eng = core.engine
+    acts = np.full(B, 0.3, dtype=np.float32)
+    eng.trace_begin(19 * 6)
+    for _ in range(6):
+        core.step(acts)
+    t1, n1 = eng.trace()
+    assert t1.shape == (B, 19 * 6) and np.all(n1 > 17 * 5)
+    eng.trace_begin(19 * 2)
+    lf = []
+    for _ in range(2):
+        core.step(acts)
+        t, _, n = eng.lfp()
+        lf.append([t[i, :n[i]].copy() for i in range(B)])
+    t2, n2 = eng.trace()
+    assert t2.shape == (B, 19 * 2)
+    for i in range(B):
+        want = np.concatenate([lf[0][i], lf[1][i]])
+        assert n2[i] == len(want) and np.array_equal(t2[i, :n2[i]], want)
+    core.close()
+
+
+def test_step_tensor_is_ordered_against_own_stream_work_without_explicit_sync():
+    """step_tensor launches on torch's current stream, reset_envs / observations / step on the
+    handle's private stream.  No torch.cuda.synchronize() between them here: the library orders the two streams itself."""
+    import torch
+    from dbsgym_b200.batched import BatchedKuramoto
+    B = 64
+    dicts = _short_dicts(2, seed=97, episode_len=5400.0)
+    dicts = [copy.deepcopy(dicts[e % 2]) for e in range(B)]
+    res = []
+    for sync in (True, False):
+        core = BatchedKuramoto(copy.deepcopy(dicts))
+        acts = torch.full((B,), 0.4, device="cuda")
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):
+            for _ in range(4):
+                o, r, d = core.step_tensor(acts)
+                if sync:
+                    torch.cuda.synchronize()
+            y_mid = core.engine.state()                  # (device-synchronising getter)
+            o, r, d = core.step_tensor(acts)
+            if sync:
+                torch.cuda.synchronize()
+            w = core.observations().copy()               # own stream right behind a user-stream step
+            o2, r2, d2 = core.step(np.full(B, -0.2, dtype=np.float32))
+            o3, r3, d3 = core.step_tensor(acts)          # user stream right behind an own-stream step
+        torch.cuda.synchronize()
+        res.append((y_mid, w, np.array(o2), r2.copy(), o3.cpu().numpy(), r3.cpu().numpy(), core.engine.state()))
+        core.close()
+    for u, v in zip(*res):
+        assert np.array_equal(u, v)

@@ -262,3 +262,29 @@ def test_device_metric_weights_fold_smoothing_and_band_sum():
         w = sp["weights"]
         assert abs(w @ ft[sp["k_lo"]:sp["k_lo"] + w.size] - ref) < 1e-12 * abs(ref)
         assert sp["padlen"] == 15 and len(sp["b"]) == 5 and sp["a"][0] == 1.0
+
+
+def test_vecenv_infos_are_per_environment_dicts():
+    """infos[i] must be a dict of its own (wrappers mutate them), created lazily."""
+    from dbsgym_b200.vec_env import _InfoList
+    infos = _InfoList(5)
+    infos[1]["x"] = 1
+    assert "x" not in infos[0] and infos[1] == {"TimeLimit.truncated": False, "x": 1}
+    assert len(infos) == 5 and all(isinstance(d, dict) for d in infos) and infos[-1] is infos[4]
+    assert len({id(d) for d in infos}) == 5
+    infos[2] = {"terminal_observation": 3}
+    assert infos[2] == {"terminal_observation": 3} and [d for d in infos[1:3]] == [infos[1], infos[2]]
+
+
+def test_batch_rejects_environments_with_different_geometry():
+    """the coupling operator is built from the first dict only, so neur_coords / neur_grid are shared keys."""
+    import copy
+    from dbsgym_b200.batched import _SHARED_KEYS, _same
+    assert "neur_coords" in _SHARED_KEYS and "neur_grid" in _SHARED_KEYS
+    d = make_params("env0", 3)
+    e = copy.deepcopy(d)
+    e["neur_coords"] = e["neur_coords"] * 1.5
+    assert _same(d["neur_grid"], e["neur_grid"]) and not _same(d["neur_coords"], e["neur_coords"])
+    from dbsgym_b200.batched import BatchedKuramoto
+    with pytest.raises(ValueError, match="neur_coords"):
+        BatchedKuramoto([d, e])                        # refused before any device is touched
