@@ -24,7 +24,7 @@ REWARD_BBPOW, REWARD_TEMP_CONST, REWARD_BBPOW_THRESH = 0, 1, 2
 
 EXPORTS = [
     "dbsgym_abi_version", "dbsgym_build_flags", "dbsgym_step_variant", "dbsgym_create", "dbsgym_destroy", "dbsgym_last_error",
-    "dbsgym_set_coupling_grid", "dbsgym_set_coupling_dense", "dbsgym_set_env_params",
+    "dbsgym_set_coupling_grid", "dbsgym_set_coupling_dense", "dbsgym_set_coupling_spectral", "dbsgym_set_env_params",
     "dbsgym_set_recording", "dbsgym_set_schedule", "dbsgym_set_reward", "dbsgym_set_episode",
     "dbsgym_transient", "dbsgym_step", "dbsgym_step_host", "dbsgym_step_host_samples", "dbsgym_host_mirror", "dbsgym_step_host_mirror", "dbsgym_step_host_mirror_begin", "dbsgym_step_host_mirror_end", "dbsgym_get_obs_host",
     "dbsgym_get_lfp", "dbsgym_get_rewards", "dbsgym_get_phases", "dbsgym_get_window",
@@ -70,31 +70,60 @@ class DbsGymError(RuntimeError):
     pass
 
 
+UNITS = ("api", "step_f32_grid", "step_f32_sym", "step_f32_lines", "step_f32_dense", "step_f32_mw", "step_f32_spectral",
+         "step_f32_cluster", "step_f64_grid", "step_f64_sym", "step_f64_dense")
+HEADERS = ("step_kernel.cuh", "step_launch.h", "obs_kernel.cuh", "eval_kernel.cuh")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
+
+
 def sources():
-    return [os.path.join(CSRC, f) for f in ("api.cu", "step_kernel.cuh", "obs_kernel.cuh", "eval_kernel.cuh")] + [HEADER]
+    return [os.path.join(CSRC, u + ".cu") for u in UNITS] + [os.path.join(CSRC, h) for h in HEADERS] + [HEADER]
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile ``csrc/api.cu`` for sm_100a into ``csrc/libdbsgym.so`` (cross-compiles without a GPU)."""
+def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
+    """Compile the translation units of ``csrc/`` for sm_100a (in parallel; cross-compiles without a GPU) and link them into
+    ``csrc/libdbsgym.so``.  Objects go to ``csrc/build/`` and are reused while their sources are older."""
     if os.environ.get("DBSGYM_LIB"):
         return LIB_PATH
-    if not force and os.path.exists(LIB_PATH):
-        newest = max(os.path.getmtime(s) for s in sources())
-        if os.path.getmtime(LIB_PATH) >= newest:
-            return LIB_PATH
+    from concurrent.futures import ThreadPoolExecutor
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise DbsGymError("nvcc not found: cannot build libdbsgym.so")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB_PATH + ".tmp", os.path.join(CSRC, "api.cu")]
+    objdir = os.path.join(CSRC, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = NVCC_FLAGS + list(extra_flags) + (["-Xptxas=-v"] if verbose else [])
+    stamp = os.path.join(objdir, "flags.txt")
+    if not os.path.exists(stamp) or open(stamp).read() != " ".join(flags):
+        force = True
+    hdr_time = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+    hdr_time = max(hdr_time, os.path.getmtime(HEADER))
+
+    def compile_unit(u):
+        src, obj = os.path.join(CSRC, u + ".cu"), os.path.join(objdir, u + ".o")
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), hdr_time):
+            return u, False, ""
+        res = subprocess.run([nvcc] + flags + ["-c", "-o", obj + ".tmp.o", src], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise DbsGymError(f"nvcc failed on {u}.cu:\n" + res.stdout + res.stderr)
+        os.replace(obj + ".tmp.o", obj)
+        return u, True, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 4)) as pool:
+        results = list(pool.map(compile_unit, UNITS))
+    rebuilt = [u for u, did, _ in results if did]
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise DbsGymError("nvcc failed:\n" + res.stdout + res.stderr)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
-    if verbose:
-        print(res.stderr)
+        for u, did, log in results:
+            if did:
+                print(f"---- {u}\n{log}")
+    objs = [os.path.join(objdir, u + ".o") for u in UNITS]
+    if rebuilt or not os.path.exists(LIB_PATH) or os.path.getmtime(LIB_PATH) < max(os.path.getmtime(o) for o in objs):
+        res = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH + ".tmp"] + objs,
+                             capture_output=True, text=True)
+        if res.returncode != 0:
+            raise DbsGymError("link failed:\n" + res.stdout + res.stderr)
+        os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    with open(stamp, "w") as f:
+        f.write(" ".join(flags))
     return LIB_PATH
 
 
@@ -121,6 +150,7 @@ def load():
         "dbsgym_last_error": (C.c_char_p, [vp]),
         "dbsgym_set_coupling_grid": (C.c_int, [vp, vp]),
         "dbsgym_set_coupling_dense": (C.c_int, [vp, vp]),
+        "dbsgym_set_coupling_spectral": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
         "dbsgym_set_env_params": (C.c_int, [vp, vp, C.c_int32, vp, vp, vp, vp]),
         "dbsgym_set_recording": (C.c_int, [vp, C.c_int32]),
         "dbsgym_set_schedule": (C.c_int, [vp, C.c_int32, vp, vp, vp, C.c_int32, vp, C.c_int32]),

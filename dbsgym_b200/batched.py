@@ -36,7 +36,14 @@ def _pinned(shape, dtype):
 
 class BatchedKuramoto:
     def __init__(self, params_dicts, *, precision="f32", device=0, compat_env2=False, force_dense=False,
-                 save_init=False, transfer="delta", engine_options=None):
+                 save_init=False, transfer="delta", engine_options=None, coupling_eval="auto", spectral_tol=1e-10):
+        """``coupling_eval``: how the float32 kernels evaluate the coupling sum of env.py:252-256 on the 8 x 8 x 8 grid --
+        ``"exact"``: the parity-sector block contraction (the same sum as the reference, reassociated); ``"spectral"``:
+        the generalised mean-field identity over the eigenmodes of alpha above ``spectral_tol * |lambda_max|``
+        (geometry.spectral_factors; 34 modes at the default 1e-10, truncation error 2.5e-8 in the spectral norm of
+        alpha, i.e. < 1e-10 rad per time unit in d theta / dt -- three orders below float32 rounding of the exact sum);
+        ``"auto"`` = spectral where it applies (float32, regular 8 x 8 x 8 grid, ranks within the compiled range), else
+        exact.  float64 (parity mode) always evaluates the exact sum."""
         if isinstance(params_dicts, dict):
             params_dicts = [params_dicts]
         self.params_dicts = list(params_dicts)
@@ -75,6 +82,18 @@ class BatchedKuramoto:
                                      precision=precision, coupling_table=table, alpha=alpha, device=device,
                                      max_step_samples=max(self.schedule.max_samples, 20),
                                      action_bounds=p0["dbs_action_bounds"], options=engine_options)
+        if coupling_eval not in ("auto", "exact", "spectral"):
+            raise ValueError("coupling_eval must be 'auto', 'exact' or 'spectral'")
+        self.coupling_eval = "exact"
+        grid888 = table is not None and [int(g) for g in p0["grid_size"]] == [8, 8, 8] and self.n_osc == 512
+        if coupling_eval != "exact" and precision == "f32" and grid888 and not (engine_options or {}).get("no_sym"):
+            from .geometry import spectral_factors
+            vecs, vals, ranks, residual = spectral_factors(table, 8, 8, 8, tol=spectral_tol)
+            if max(ranks) <= 9:
+                self.engine.set_coupling_spectral(vecs, vals, ranks, residual)
+                self.coupling_eval = "spectral"
+        if coupling_eval == "spectral" and self.coupling_eval != "spectral":
+            raise ValueError("coupling_eval='spectral' needs float32 on the regular 8 x 8 x 8 grid with at most 9 modes per sector")
         self.engine.set_recording(p0["recording_kernel"] == "gaussian")
         self.engine.set_schedule(self.schedule)
         self.engine.set_reward(p0["reward_func"], p0["verbose_dt"])

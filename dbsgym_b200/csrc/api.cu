@@ -12,7 +12,7 @@
 #include "../../include/dbsgym.h"
 #include "eval_kernel.cuh"
 #include "obs_kernel.cuh"
-#include "step_kernel.cuh"
+#include "step_launch.h"
 
 using namespace dbsgym;
 
@@ -94,6 +94,9 @@ struct DbsGymHandle {
     int num_sms = 0;
     int mw_mode = -1;                    // multi-worker step kernel: -1 auto (full-occupancy batches), 0 never, 1 always
     bool no_geo1 = false, no_fast_obs = false, no_fused_obs = false;     // DbsGymConfig.debug_flags
+    // spectral form of the coupling operator (dbsgym_set_coupling_spectral): eigenvector entries per worker thread and
+    // eigenvalues x K / (8 N) per reduction row, and which compiled (RE, RO) pair serves them (0 = off)
+    float* spec_v = nullptr; float* spec_lam = nullptr; int spec_re = 0, spec_ro = 0;
     unsigned long long n_launches = 0;   // kernels launched by this handle (dbsgym_launch_count)
     // ordering between the private stream and caller streams (dbsgym_step / dbsgym_transient on a user stream)
     cudaEvent_t ev_own = nullptr, ev_user = nullptr; bool user_pending = false;
@@ -312,118 +315,55 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
     p.nsamp_out = nullptr; p.head_out = nullptr;
     p.trace = nullptr; p.trace_len = nullptr; p.trace_cap = 0;
     p.fsal_on = h->fsal_on ? 1 : 0; p.k_fsal = h->k_fsal; p.fsal_valid = h->fsal_valid;
+    p.spec_v = h->spec_v; p.spec_lam = h->spec_lam;
     p.power_scale = h->rspec.power_scale; p.action_cost = h->rspec.action_cost;
     p.threshold = h->rspec.threshold; p.threshold_penalty = h->rspec.threshold_penalty;
 }
 
-template <typename real, int CPL, int MAXT, int GEO = 0>
-cudaError_t launch_step_t(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
-    size_t smem = step_smem_bytes(h->Np, CPL == CPL_DENSE ? 0 : h->tab, h->nthreads, sizeof(real));
+size_t plain_smem(DbsGymHandle* h, bool dense) {
+    size_t smem = step_smem_bytes(h->Np, dense ? 0 : h->tab, h->nthreads, h->rb);
     if (h->ctas_per_sm > 0) {
         // occupancy knob: pad the dynamic shared memory so that exactly ctas_per_sm CTAs fit on an SM
         // (227 KB usable, 1 KB reserved per CTA) -- used to balance the waves of a launch
         const size_t want = (size_t)(227 * 1024) / (size_t)h->ctas_per_sm - 1024;
         if (want > smem) smem = want & ~(size_t)15;
     }
-    auto kern = step_kernel<real, CPL, MAXT, GEO>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    kern<<<p.n_launch, h->nthreads, smem, s>>>(p);
-    ++h->n_launches;
-    return cudaGetLastError();
+    return smem;
 }
 
-// multi-worker kernel: kMwEnvs environments per CTA (one per 64-thread worker), one persistent CTA per SM
-cudaError_t launch_step_mw(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
-    auto kern = step_kernel<float, CPL_GRID_SYM, kMwEnvs * kMwThreads, 1, 0, kMwEnvs>;
-    const size_t smem = step_smem_bytes_mw(h->Np);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int ctas = (p.n_launch + kMwEnvs - 1) / kMwEnvs;
-    if (ctas > h->num_sms) ctas = h->num_sms;
-    kern<<<ctas, kMwEnvs * kMwThreads, smem, s>>>(p);
-    ++h->n_launches;
-    return cudaGetLastError();
+// which float32 GRID_SYM kernel family serves this handle: 1 = 8 x 8 x 8 (unrolled), 2 = gx 8, 3 / 4 = lines of 16 / 32, 0 = generic
+int sym_geo(const DbsGymHandle* h, const StepParams& p) {
+    if (p.GY == 2 * kRows) return 3;
+    if (p.GY == 4 * kRows) return 4;
+    if (h->nthreads == 64 && p.GZ == 8 && p.GX == 8 && !h->no_geo1) return 1;
+    if (p.GX == 8 && h->nthreads <= 512) return 2;
+    return 0;
 }
 
-template <typename real, int CPL>
-cudaError_t launch_step_m(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
+// the step kernels live in their own translation units (step_*.cu, declared in step_launch.h)
+cudaError_t launch_step(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
+    ++h->n_launches;
     const int t = h->nthreads;
-    if constexpr (CPL == CPL_GRID_SYM && sizeof(real) == 4) if (p.GY == 2 * kRows) {   // lines of 16 (cubic 16^3 grids)
-        if (t <= 64) return launch_step_t<real, CPL, 64, 3>(h, p, s);
-        if (t <= 128) return launch_step_t<real, CPL, 128, 3>(h, p, s);
-        if (t <= 256) return launch_step_t<real, CPL, 256, 3>(h, p, s);
-        return launch_step_t<real, CPL, 512, 3>(h, p, s);
+    if (h->cluster > 1) return launch_f32_cluster(p.GY == 2 * kRows ? 3 : p.GY == 4 * kRows ? 4 : 2, t, h->cluster, p, s);
+    const bool dense = h->cfg.coupling == DBSGYM_COUPLING_DENSE;
+    const size_t smem = plain_smem(h, dense);
+    if (h->f64) {
+        if (dense) return launch_f64_dense(t, smem, p, s);
+        return h->grid_sym ? launch_f64_sym(t, smem, p, s) : launch_f64_grid(t, smem, p, s);
     }
-    if constexpr (CPL == CPL_GRID_SYM && sizeof(real) == 4) if (p.GY == 4 * kRows) {   // lines of 32 (cubic 32^3 grids)
-        if (t <= 128) return launch_step_t<real, CPL, 128, 4>(h, p, s);
-        if (t <= 256) return launch_step_t<real, CPL, 256, 4>(h, p, s);
-        return launch_step_t<real, CPL, 512, 4>(h, p, s);
-    }
-    if constexpr (CPL == CPL_GRID_SYM && sizeof(real) == 4) {
-        if (t == 64 && p.GZ == 8 && p.GX == 8 && !h->no_geo1) {
-            // enough environments to fill every SM with kMwEnvs of them: share the sector-coefficient table
-            const bool mw = kYParity && (h->mw_mode == 1 || (h->mw_mode < 0 && p.n_launch >= kMwEnvs * h->num_sms));
-            if (mw) return launch_step_mw(h, p, s);
-            return launch_step_t<real, CPL, 64, 1>(h, p, s);
+    if (dense) return launch_f32_dense(t, smem, p, s);
+    if (!h->grid_sym) return launch_f32_grid(t, smem, p, s);
+    if (h->spec_re > 0) return launch_f32_spectral(h->spec_ro, h->num_sms, p, s);
+    const int geo = sym_geo(h, p);
+    if (geo == 1) {
+        // enough environments to fill every SM with kMwEnvs of them: share the sector-coefficient table
+        const bool mw = kYParity && (h->mw_mode == 1 || (h->mw_mode < 0 && p.n_launch >= kMwEnvs * h->num_sms));
+        if (mw) {
+            int ctas = (p.n_launch + kMwEnvs - 1) / kMwEnvs;
+            return launch_f32_mw(ctas > h->num_sms ? h->num_sms : ctas, p, s);
         }
     }
-    if constexpr (CPL == CPL_GRID_SYM && sizeof(real) == 4) if (p.GX == 8) {   // sweep grids 8 x 8 x gz
-        if (t <= 64) return launch_step_t<real, CPL, 64, 2>(h, p, s);
-        if (t <= 128) return launch_step_t<real, CPL, 128, 2>(h, p, s);
-        if (t <= 256) return launch_step_t<real, CPL, 256, 2>(h, p, s);
-        if (t <= 512) return launch_step_t<real, CPL, 512, 2>(h, p, s);
-    }
-    if (t <= 64) return launch_step_t<real, CPL, 64>(h, p, s);
-    if (t <= 128) return launch_step_t<real, CPL, 128>(h, p, s);
-    if (t <= 256) return launch_step_t<real, CPL, 256>(h, p, s);
-    if (t <= 512) return launch_step_t<real, CPL, 512>(h, p, s);
-    return launch_step_t<real, CPL, 1024>(h, p, s);
-}
-
-// cluster mode: one environment = a cluster of h->cluster CTAs (cudaLaunchKernelEx + cluster dimension attribute)
-template <int MAXT, int GEO = 2>
-cudaError_t launch_step_cluster_t(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
-    auto kern = step_kernel<float, CPL_GRID_SYM, MAXT, GEO, 1>;
-    const size_t smem = step_smem_bytes_cluster(h->nthreads, sizeof(float));
-    cudaError_t e = cudaSuccess;
-    if (smem > 48 * 1024) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e == cudaSuccess && h->cluster > 8) e = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(p.n_launch * h->cluster));
-    cfg.blockDim = dim3((unsigned)h->nthreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)h->cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    ++h->n_launches;
-    return cudaLaunchKernelEx(&cfg, kern, p);
-}
-
-cudaError_t launch_step_cluster(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
-    const int t = h->nthreads;
-    if (p.GY == 2 * kRows) return t <= 256 ? launch_step_cluster_t<256, 3>(h, p, s) : launch_step_cluster_t<512, 3>(h, p, s);
-    if (p.GY == 4 * kRows) return t <= 256 ? launch_step_cluster_t<256, 4>(h, p, s) : launch_step_cluster_t<512, 4>(h, p, s);
-    if (t <= 64) return launch_step_cluster_t<64>(h, p, s);
-    if (t <= 128) return launch_step_cluster_t<128>(h, p, s);
-    if (t <= 256) return launch_step_cluster_t<256>(h, p, s);
-    return launch_step_cluster_t<512>(h, p, s);
-}
-
-template <typename real>
-cudaError_t launch_step_c(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
-    if (h->cfg.coupling == DBSGYM_COUPLING_DENSE) return launch_step_m<real, CPL_DENSE>(h, p, s);
-    return h->grid_sym ? launch_step_m<real, CPL_GRID_SYM>(h, p, s) : launch_step_m<real, CPL_GRID>(h, p, s);
-}
-
-cudaError_t launch_step(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
-    if (h->cluster > 1) return launch_step_cluster(h, p, s);
-    return h->f64 ? launch_step_c<double>(h, p, s) : launch_step_c<float>(h, p, s);
+    return launch_f32_sym(geo, t, smem, p, s);
 }
 
 cudaError_t launch_obs(DbsGymHandle* h, float* obs, float* reward_f, uint8_t* done_out, int append,
@@ -581,6 +521,7 @@ int dbsgym_step_variant(const DbsGymHandle* h, int32_t n_envs) {
     if (h->cfg.coupling == DBSGYM_COUPLING_DENSE) return 1;
     if (!h->grid_sym) return 0;
     if (h->f64) return 2;
+    if (h->spec_re > 0) return 9;
     if (h->cfg.grid[1] == 2 * kRows) return 7;
     if (h->cfg.grid[1] == 4 * kRows) return 8;
     const bool geo1 = h->nthreads == 64 && h->cfg.grid[2] == 8 && h->cfg.grid[0] == 8 && !h->no_geo1;
@@ -748,7 +689,7 @@ void dbsgym_destroy(DbsGymHandle* h) {
                     h->step_idx, h->episode_len, h->lfp_true, h->lfp_rec, h->u, h->reward, h->done, h->sched_nI,
                     h->sched_nII, h->sched_offI, h->sched_offII, h->ts_dev, h->ids_dev, h->lin_g, h->tw_seed,
                     h->tw_inner, h->spec, h->tw_full, h->k_fsal, h->fsal_valid, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples,
-                    h->cl_operand, h->cl_scratch, h->mpos};
+                    h->cl_operand, h->cl_scratch, h->mpos, h->spec_v, h->spec_lam};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->pin_ints) cudaFreeHost(h->pin_ints);
@@ -784,6 +725,53 @@ int dbsgym_set_coupling_grid(DbsGymHandle* h, const double* table) {
     if (!h->table) CU(h, cudaMalloc(&h->table, buf.size()));
     CU(h, cudaMemcpy(h->table, buf.data(), buf.size(), cudaMemcpyHostToDevice));
     h->have_coupling = true;
+    if (h->fsal_valid) CU(h, cudaMemset(h->fsal_valid, 0, (size_t)h->B * 4));
+    return DBSGYM_OK;
+}
+
+int dbsgym_set_coupling_spectral(DbsGymHandle* h, int32_t r_even, int32_t r_odd, int32_t r_max, const double* vecs,
+                                 const double* vals) {
+    if (!h) return DBSGYM_EINVAL;
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaDeviceSynchronize());
+    if (r_even <= 0 && r_odd <= 0) {                  // back to the exact sector-block contraction
+        h->spec_re = h->spec_ro = 0;
+        if (h->fsal_valid) CU(h, cudaMemset(h->fsal_valid, 0, (size_t)h->B * 4));
+        return DBSGYM_OK;
+    }
+    if (!vecs || !vals) return fail(h, DBSGYM_EINVAL, "null argument");
+    if (h->cfg.coupling != DBSGYM_COUPLING_GRID || h->f64 || !h->grid_sym || h->cluster > 1 || h->nthreads != 64 ||
+        h->cfg.grid[0] != 8 || h->cfg.grid[1] != 8 || h->cfg.grid[2] != 8)
+        return fail(h, DBSGYM_ESTATE, "the spectral contraction serves fp32 GRID handles on the 8 x 8 x 8 grid");
+    if (r_even < 1 || r_odd < 1 || r_even > 9 || r_odd > 9 || r_max < r_even || r_max < r_odd)
+        return fail(h, DBSGYM_EINVAL, "spectral ranks (%d even, %d odd) outside the compiled range 1..9", r_even, r_odd);
+    const int RE = 9, RO = r_odd <= 4 ? 4 : 9, R = RE + RO;
+    std::vector<float> v((size_t)kMwThreads * 4 * R, 0.f), lam((size_t)4 * R, 0.f);
+    const double scale = h->cfg.K / (8.0 * (double)h->N);
+    for (int t = 0; t < kMwThreads; ++t) {
+        int zq, xq, sec;
+        mw_decode(t, zq, xq, sec);
+        const int q = zq * 4 + xq;
+        for (int j = 0; j < 4; ++j)
+            for (int m = 0; m < R; ++m) {
+                const int s8 = m < RE ? sec : 4 + sec, mm = m < RE ? m : m - RE;
+                const int rs = m < RE ? r_even : r_odd;
+                if (mm < rs) v[((size_t)t * 4 + j) * R + m] = (float)vecs[((size_t)s8 * 64 + q * 4 + j) * r_max + mm];
+            }
+    }
+    for (int sg = 0; sg < 4; ++sg)
+        for (int m = 0; m < R; ++m) {
+            const int s8 = m < RE ? sg : 4 + sg, mm = m < RE ? m : m - RE;
+            if (mm < (m < RE ? r_even : r_odd)) lam[(size_t)sg * R + m] = (float)(vals[(size_t)s8 * r_max + mm] * scale);
+        }
+    if (h->spec_v) cudaFree(h->spec_v);
+    if (h->spec_lam) cudaFree(h->spec_lam);
+    h->spec_v = h->spec_lam = nullptr;
+    CU(h, cudaMalloc(&h->spec_v, v.size() * sizeof(float)));
+    CU(h, cudaMalloc(&h->spec_lam, lam.size() * sizeof(float)));
+    CU(h, cudaMemcpy(h->spec_v, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->spec_lam, lam.data(), lam.size() * sizeof(float), cudaMemcpyHostToDevice));
+    h->spec_re = RE; h->spec_ro = RO;
     if (h->fsal_valid) CU(h, cudaMemset(h->fsal_valid, 0, (size_t)h->B * 4));
     return DBSGYM_OK;
 }

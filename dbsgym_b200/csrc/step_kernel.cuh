@@ -87,6 +87,9 @@ struct StepParams {
     // k1 = k7 + (amp_new - amp_old) * stim replaces one RHS evaluation per segment (2 of 32 per step).  The row is
     // carried across launches in k_fsal (valid flag cleared whenever the host rewrites an environment's vectors).
     int fsal_on; void* k_fsal; int32_t* fsal_valid;
+    // spectral coupling (CPL_SPECTRAL): eigenvectors per worker thread [64][4 * (RE + RO)] and the eigenvalues, already
+    // multiplied by K / (8 N), one per reduction slot [4 * (RE + RO)] (see spectral_contract below)
+    const float* spec_v; const float* spec_lam;
     double* trace; int32_t* trace_len; int trace_cap;   // optional recording of the TRUE LFP of every step (evaluation)
     double power_scale, action_cost, threshold, threshold_penalty;
     // cluster mode (one environment = a thread-block cluster of `cluster` CTAs, N > 4096)
@@ -688,7 +691,7 @@ __device__ __forceinline__ void couple_sym_upre(const float* __restrict__ bp, co
 // coefficient table of the 8 x 8 x 8 grid, built once per CTA from the 2 KB Toeplitz table in global memory.
 // Entry (blk = zj*4+xj, half, t): u^p[dy = 4*half .. 4*half+3] of worker thread t, combined in the same order
 // (and therefore to the same bits) as sym_combine() does on the fly.
-__device__ __forceinline__ void mw_decode(int t, int& zq, int& xq, int& sec) {
+__host__ __device__ __forceinline__ void mw_decode(int t, int& zq, int& xq, int& sec) {
     const int lane = t & 31, q = (t >> 5) * 8 + (lane & 7);
     sec = lane >> 3; zq = q >> 2; xq = q & 3;
 }
@@ -711,6 +714,98 @@ __device__ __forceinline__ void mw_build_table(float4* U4, const float* __restri
         u.z = fmaf(pz, fmaf(px, a11.z, a10.z), fmaf(px, a01.z, a00.z));
         u.w = fmaf(pz, fmaf(px, a11.w, a10.w), fmaf(px, a01.w, a00.w));
         U4[e] = u;
+    }
+}
+
+// ---- coupling contraction, SPECTRAL mode: the generalised mean-field identity -------------------------------
+// alpha = sum_m lambda_m v_m v_m^T with every eigenvector in one of the 8 parity sectors (geometry.py: spectral_factors;
+// 34 modes above 1e-10 |lambda_max| for the shipped 8 x 8 x 8 cos kernel, at most RE = 9 in an even-y and RO = 4 in an
+// odd-y sector).  Per RHS evaluation and sector:
+//     c_m = sum_b v_m[b] X[b]   (projection: weighted order parameters of the sector, (sin, cos) pairs)
+//     y[a] = sum_m lambda_m v_m[a] c_m   (expansion)
+// Thread (sector sec, fundamental line q) owns X[(q, j)], j < 4, of the sectors (sec, even y) and (sec, odd y) and keeps
+// its 4 x (RE + RO) eigenvector entries in REGISTERS for the whole launch (they depend on the thread only, not on the
+// environment).  The sum over the 16 lines of a sector goes through shared memory: partials P[sec][m][q] (float2), one
+// thread per (sec, m) adds the 16 entries of a row (FADD2 tree), scales by lambda and writes C[sec][m]; two worker
+// barriers per evaluation, ~150 instructions per thread instead of ~930 for the sector-block contraction.
+template <int RE, int RO> struct SpecLayout {
+    static constexpr int R = RE + RO;
+    static constexpr int RS = 36;                                            // words per partial row: 16 float2 + 4 (readers conflict-free)
+    static constexpr int PS = R * RS + ((16 - (R * RS) % 32) + 32) % 32;     // sector stride == 16 (mod 32): STS.64 of a half warp conflict-free
+    static constexpr int CW = (2 * R + 3) & ~3;                              // words of one sector's coefficient row
+    static constexpr int CS = (CW % 16 == 0) ? CW + 4 : CW;                  // sector stride: the 4 broadcast reads hit 4 bank groups
+    static constexpr int NSUM = 4 * R;                                       // rows to reduce per evaluation
+    static constexpr int ROUNDS = (NSUM + 63) / 64;
+    static constexpr int floats = 4 * PS + 4 * CS;
+    static_assert(PS % 32 == 16 && CS % 4 == 0 && (CS % 32) != 0 && (2 * CS) % 32 != 0 && CS % 32 != (3 * CS) % 32, "bank layout");
+};
+
+template <int RE, int RO>
+__device__ __forceinline__ void spectral_contract(const float (&scw)[2 * kRows], const float (&Ve)[4][RE], const float (&Vo)[4][RO],
+                                                  const float (&lam)[SpecLayout<RE, RO>::ROUNDS], float* __restrict__ Pw,
+                                                  float* __restrict__ Cw, int tid_w, int sec, int q, int wid,
+                                                  float (&as)[kRows], float (&ac)[kRows]) {
+    using L = SpecLayout<RE, RO>;
+    // ---- projection partials over this thread's 4 + 4 sector coordinates
+    {
+        float2 be[4], bo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { be[j] = make_float2(scw[2 * j], scw[2 * j + 1]); bo[j] = make_float2(scw[8 + 2 * j], scw[8 + 2 * j + 1]); }
+        float* row = Pw + sec * L::PS + 2 * q;
+#pragma unroll
+        for (int m = 0; m < RE; ++m) {
+            float2 a = __fmul2_rn(make_float2(Ve[0][m], Ve[0][m]), be[0]);
+#pragma unroll
+            for (int j = 1; j < 4; ++j) a = __ffma2_rn(make_float2(Ve[j][m], Ve[j][m]), be[j], a);
+            *reinterpret_cast<float2*>(row + m * L::RS) = a;
+        }
+#pragma unroll
+        for (int m = 0; m < RO; ++m) {
+            float2 a = __fmul2_rn(make_float2(Vo[0][m], Vo[0][m]), bo[0]);
+#pragma unroll
+            for (int j = 1; j < 4; ++j) a = __ffma2_rn(make_float2(Vo[j][m], Vo[j][m]), bo[j], a);
+            *reinterpret_cast<float2*>(row + (RE + m) * L::RS) = a;
+        }
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(wid + 1), "n"(kMwThreads) : "memory");
+    // ---- one thread per (sector, mode): sum of the 16 line partials, times lambda * K / (8 N)
+#pragma unroll
+    for (int rd = 0; rd < L::ROUNDS; ++rd) {
+        const int g = tid_w + 64 * rd;
+        if (g < L::NSUM) {
+            const int sg = g / L::R, mg = g - sg * L::R;
+            const float4* r4 = reinterpret_cast<const float4*>(Pw + sg * L::PS + mg * L::RS);
+            float2 v[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float4 t = r4[i]; v[2 * i] = make_float2(t.x, t.y); v[2 * i + 1] = make_float2(t.z, t.w); }
+#pragma unroll
+            for (int w = 8; w > 0; w >>= 1) {
+#pragma unroll
+                for (int i = 0; i < w; ++i) v[i] = __fadd2_rn(v[i], v[i + w]);
+            }
+            *reinterpret_cast<float2*>(Cw + sg * L::CS + 2 * mg) = __fmul2_rn(make_float2(lam[rd], lam[rd]), v[0]);
+        }
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(wid + 1), "n"(kMwThreads) : "memory");
+    // ---- expansion back to this thread's sector coordinates: E_0..3 (even y), O_0..3 (odd y)
+    {
+        float c[L::CW];
+        const float4* c4 = reinterpret_cast<const float4*>(Cw + sec * L::CS);
+#pragma unroll
+        for (int i = 0; i < L::CW / 4; ++i) { const float4 t = c4[i]; c[4 * i] = t.x; c[4 * i + 1] = t.y; c[4 * i + 2] = t.z; c[4 * i + 3] = t.w; }
+        float2 acc[kRows];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            acc[i] = __fmul2_rn(make_float2(Ve[i][0], Ve[i][0]), make_float2(c[0], c[1]));
+#pragma unroll
+            for (int m = 1; m < RE; ++m) acc[i] = __ffma2_rn(make_float2(Ve[i][m], Ve[i][m]), make_float2(c[2 * m], c[2 * m + 1]), acc[i]);
+            acc[4 + i] = __fmul2_rn(make_float2(Vo[i][0], Vo[i][0]), make_float2(c[2 * RE], c[2 * RE + 1]));
+#pragma unroll
+            for (int m = 1; m < RO; ++m)
+                acc[4 + i] = __ffma2_rn(make_float2(Vo[i][m], Vo[i][m]), make_float2(c[2 * (RE + m)], c[2 * (RE + m) + 1]), acc[4 + i]);
+        }
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) { as[r] = acc[r].x; ac[r] = acc[r].y; }
     }
 }
 
@@ -849,7 +944,7 @@ template <typename real, int MAXT> struct MinBlocks {
     static constexpr int v = (sizeof(real) == 4 && MAXT <= 128) ? (DBSGYM_MINB64 * 64 / MAXT) : 1;
 };
 
-enum { CPL_GRID = 0, CPL_DENSE = 1, CPL_GRID_SYM = 2 };
+enum { CPL_GRID = 0, CPL_DENSE = 1, CPL_GRID_SYM = 2, CPL_SPECTRAL = 3 };
 #ifndef DBSGYM_SC_BUFFERS
 #define DBSGYM_SC_BUFFERS 2
 #endif
@@ -859,9 +954,11 @@ constexpr int kScPad = 16;     // reals of padding per operand buffer (GRID_SYM 
 
 // shared memory of one worker in multi-worker mode (fp32): K slots, double-buffered operand, winding counts,
 // reduction scratch, observation-tail scratch
-__host__ __device__ inline size_t step_smem_bytes_worker(int Np) {
+__host__ __device__ inline size_t step_smem_bytes_worker(int Np, int op_floats = -1) {
     const int nwarps = kMwThreads / 32;
-    return (size_t)(kSlots * Np + kMwScBuffers * (2 * Np + kScPad)) * sizeof(float) + (size_t)Np * sizeof(int) +
+    // op_floats: size of the contraction scratch (default: the double-buffered [sin, cos] operand; spectral: partials + coefficients)
+    const int opf = op_floats >= 0 ? op_floats : kMwScBuffers * (2 * Np + kScPad);
+    return (size_t)(kSlots * Np + opf) * sizeof(float) + (size_t)Np * sizeof(int) +
            (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 36 * sizeof(int);
 }
 
@@ -878,14 +975,17 @@ __host__ __device__ inline size_t step_smem_bytes_worker(int Np) {
 // contraction operand is exchanged through a double-buffered global (L2-resident) buffer, the coupling table is
 // read through the read-only path, and the barrier per RHS evaluation as well as the error-norm / LFP reductions
 // become cluster-scope (barrier.cluster release/acquire + a few doubles of global scratch).
-template <typename real, int CPL, int MAXT, int GEO = 0, int CL = 0, int EPC = 1>
+template <typename real, int CPL, int MAXT, int GEO = 0, int CL = 0, int EPC = 1, int RE = 1, int RO = 1>
 __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p) {
     constexpr bool DENSE = CPL == CPL_DENSE;
-    constexpr bool SYM = CPL == CPL_GRID_SYM;
+    constexpr bool SPEC = CPL == CPL_SPECTRAL;      // spectral contraction: multi-worker hosting, parity-sector thread layout
+    constexpr bool SYM = CPL == CPL_GRID_SYM || SPEC;
     constexpr bool MW = EPC > 1;       // multi-worker mode: EPC environments per CTA, one 64-thread worker each
+    using SL = SpecLayout<RE, RO>;
+    static_assert(!SPEC || (MW && GEO == 1 && sizeof(real) == 4 && CL == 0), "spectral mode: fp32, 8 x 8 x 8 grid, multi-worker");
     static_assert(CL == 0 || (CPL == CPL_GRID_SYM && (GEO == 2 || GEO == 3 || GEO == 4) && sizeof(real) == 4),
                   "cluster mode: fp32 GRID_SYM with gx = 8 or with lines of 16 / 32");
-    static_assert(!MW || (CPL == CPL_GRID_SYM && GEO == 1 && sizeof(real) == 4 && CL == 0 && kYParity && MAXT == EPC * kMwThreads),
+    static_assert(!MW || (SYM && GEO == 1 && sizeof(real) == 4 && CL == 0 && kYParity && MAXT == EPC * kMwThreads),
                   "multi-worker mode: fp32 GRID_SYM on the 8 x 8 x 8 grid with y parity");
     const int GZ = GEO == 1 ? 8 : p.GZ, GX = (GEO == 1 || GEO == 2) ? 8 : p.GX;      // GEO == 2: gx = 8 fixed, gz at run time
     constexpr int CH = GEO == 3 ? 2 : GEO == 4 ? 4 : 1;                  // GEO == 3 / 4: lines of 16 / 32, 2 / 4 threads (chunks) per line
@@ -903,11 +1003,12 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     const int scsz = 2 * Np + kScPad;
 
     // shared memory of this CTA (MW: the coefficient table, then one such block per worker)
-    unsigned char* wsm = smem_raw + (MW ? kMwUFloat4 * sizeof(float4) + (size_t)wid * step_smem_bytes_worker(Np) : 0);
+    unsigned char* wsm = smem_raw + (SPEC ? (size_t)wid * step_smem_bytes_worker(Np, SL::floats)
+                                          : MW ? kMwUFloat4 * sizeof(float4) + (size_t)wid * step_smem_bytes_worker(Np) : 0);
     real* K = reinterpret_cast<real*>(wsm);               // [kSlots][Nl] stage derivatives f(y_s), thread-private slots
     real* SCs = K + kSlots * Nl;                          // [kScBuffers][scsz] (sin, cos) contraction operand (not in cluster mode)
     constexpr int SCB = MW ? kMwScBuffers : kScBuffers;   // operand buffers
-    real* Ts = SCs + (CL ? 0 : SCB * scsz);               // [tab]
+    real* Ts = SCs + (CL ? 0 : SPEC ? SL::floats : SCB * scsz);   // [tab]  (SPEC: SCs holds the partials P and the coefficients C)
     real* RC = Ts + tab;                                  // [Nl] recording conductance (thread-private slots; MW: read from global)
     int* WD = reinterpret_cast<int*>(RC + (MW ? 0 : Nl)); // [Nl] fp32 mode: winding counts, y = phase + 2*pi*wind
     double* part = reinterpret_cast<double*>(WD + Nl);    // [nwarps][kSampleBatch][2]
@@ -957,7 +1058,23 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     const int sc_slot = SYM ? sc_sector + (qline * CH + chunk) * 2 * kRows : 2 * k0;
     constexpr int BMX = MW ? 8 : 1, BMZ = MW ? 16 : 2;     // lane bits of the x / z mirror image (quad_butterfly)
 
-    if (MW) {                                             // the coefficient table, once per CTA
+    // spectral mode: this thread's eigenvector entries and the eigenvalues of the reduction rows it sums -- registers,
+    // loaded once per launch (they depend on the thread only)
+    float Ve[4][RE], Vo[4][RO], lam_r[SL::ROUNDS];
+    if constexpr (SPEC) {
+        const float* v = p.spec_v + (size_t)tid * 4 * SL::R;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int m = 0; m < RE; ++m) Ve[j][m] = __ldg(v + j * SL::R + m);
+#pragma unroll
+            for (int m = 0; m < RO; ++m) Vo[j][m] = __ldg(v + j * SL::R + RE + m);
+        }
+#pragma unroll
+        for (int rd = 0; rd < SL::ROUNDS; ++rd) lam_r[rd] = (tid + 64 * rd < SL::NSUM) ? __ldg(p.spec_lam + tid + 64 * rd) : 0.f;
+    }
+    if (SPEC) {
+    } else if (MW) {                                      // the coefficient table, once per CTA
         mw_build_table(reinterpret_cast<float4*>(smem_raw), reinterpret_cast<const float*>(p.table), (int)threadIdx.x, (int)blockDim.x);
         __syncthreads();
     } else if (!DENSE && !CL) {
@@ -1086,13 +1203,13 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                 real inc[kRows];
                 stage_increment<real>(s, K, Nl, tid, nt, inc);
                 real sv[kRows], cv[kRows];
+                real scw[2 * kRows];
                 {
 #pragma unroll
                     for (int r = 0; r < kRows; ++r) {
                         inc[r] *= dt;
                         sincos_r(y0[r] + inc[r], &sv[r], &cv[r]);
                     }
-                    real scw[2 * kRows];
                     if (SYM) {                                   // to the parity-sector basis (quad butterfly)
                         real ts_[kRows], tc_[kRows];
 #pragma unroll
@@ -1115,13 +1232,17 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) { scw[2 * r] = sv[r]; scw[2 * r + 1] = cv[r]; }
                     }
-                    storev<2 * kRows>(SC + pbuf * scsz + sc_slot, scw);
+                    if (!SPEC) storev<2 * kRows>(SC + pbuf * scsz + sc_slot, scw);
                 }
-                if (CL) cluster_barrier(); else env_sync();
+                if (CL) cluster_barrier(); else if (!SPEC) env_sync();
                 real as[kRows], ac[kRows];
                 if (DENSE) couple_dense<real>(SC + pbuf * scsz, reinterpret_cast<const real*>(p.alpha), Np, i0, as, ac);
                 else if (SYM) {
-                    if constexpr (CL != 0) {
+                    if constexpr (SPEC) {
+                        spectral_contract<RE, RO>(reinterpret_cast<const float(&)[2 * kRows]>(scw), Ve, Vo, lam_r,
+                                                  reinterpret_cast<float*>(SCs), reinterpret_cast<float*>(SCs) + 4 * SL::PS, tid, img,
+                                                  qline, wid, reinterpret_cast<float(&)[kRows]>(as), reinterpret_cast<float(&)[kRows]>(ac));
+                    } else if constexpr (CL != 0) {
                         // Cluster mode: the operand of the whole environment sits in global memory (L2).  Every CTA
                         // stages it through its own shared memory in tiles of whole source z-planes (one cooperative,
                         // coalesced copy per tile and CTA instead of every warp fetching every line from L2), the
@@ -1194,10 +1315,13 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                 } else couple_grid<real>(SC + pbuf * scsz, T, GZ, GX, zi, xi, as, ac);
                 real ks[kRows];
 #pragma unroll
-                for (int r = 0; r < kRows; ++r)
-                    ks[r] = c0[r] + kn * (cv[r] * as[r] - sv[r] * ac[r]);
+                for (int r = 0; r < kRows; ++r) {
+                    if constexpr (SPEC) ks[r] = fma_r(cv[r], as[r], fma_r(-sv[r], ac[r], c0[r]));    // K / (8 N) is folded into lambda
+                    else ks[r] = c0[r] + kn * (cv[r] * as[r] - sv[r] * ac[r]);
+                }
                 store_row<real>(K + kslot(s) * Nl, tid, nt, ks);
-                if (SCB == 2 || CL) pbuf ^= 1;    // (the global operand of cluster mode is always double buffered)
+                if (SPEC) {}                      // (partials / coefficients are fenced by the two barriers of spectral_contract)
+                else if (SCB == 2 || CL) pbuf ^= 1;    // (the global operand of cluster mode is always double buffered)
                 else env_sync();                  // operand buffer is about to be overwritten by the next stage
                 ++n_rhs;
             }
@@ -1421,6 +1545,8 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
 }
 
 inline size_t step_smem_bytes_mw(int Np) { return kMwUFloat4 * sizeof(float4) + kMwEnvs * step_smem_bytes_worker(Np); }
+template <int RE, int RO>
+inline size_t step_smem_bytes_spectral(int Np, int workers) { return (size_t)workers * step_smem_bytes_worker(Np, SpecLayout<RE, RO>::floats); }
 
 inline size_t step_smem_bytes_cluster(int nthreads, size_t real_bytes) {
     const int nwarps = (nthreads + 31) / 32, Nl = nthreads * kRows;

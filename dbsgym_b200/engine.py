@@ -97,6 +97,20 @@ class KuramotoEngine:
                 raise ValueError("dense coupling must be symmetric")
             self._ck(self.lib.dbsgym_set_coupling_dense(self._h, _capi.ptr(a)))
         self.schedule = None
+        self.spectral = None
+
+    def set_coupling_spectral(self, vecs, vals, ranks, residual=None):
+        """Switch the GRID operator to its spectral form (dbsgym.h: dbsgym_set_coupling_spectral).  ``vecs`` [8][64][r_max],
+        ``vals`` [8][r_max], ``ranks`` [8] as returned by geometry.spectral_factors; ``ranks=None`` switches back."""
+        if ranks is None:
+            self._ck(self.lib.dbsgym_set_coupling_spectral(self._h, 0, 0, 0, None, None))
+            self.spectral = None
+            return
+        r_even, r_odd = max(max(ranks[:4]), 1), max(max(ranks[4:]), 1)
+        v, w = _f64(vecs), _f64(vals)
+        self._ck(self.lib.dbsgym_set_coupling_spectral(self._h, int(r_even), int(r_odd), int(v.shape[2]), _capi.ptr(v),
+                                                       _capi.ptr(w)))
+        self.spectral = {"ranks": [int(r) for r in ranks], "modes": int(sum(ranks)), "residual": residual}
 
     # ------------------------------------------------------------------ plumbing
     def _ck(self, rc):

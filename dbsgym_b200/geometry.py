@@ -154,3 +154,90 @@ class ElectrodeModel:
                 out = out + c
             self._rec_vec = out
         return self._rec_vec
+
+
+# ---- spectral form of the coupling operator (generalised mean-field identity) ----------------------------------------
+# BASELINE.json's north star asks for the coupling term "through the mean-field identity (a warp-shuffle and block
+# reduction of sum e^{i theta})".  That identity is exact only for alpha == 1; the reference's alpha = cos(distance)
+# (env.py:219-223) is not uniform, but it is a smooth kernel of a small grid and therefore numerically of very low rank:
+#     alpha = sum_m lambda_m v_m v_m^T,   sum_j alpha_ij sin(th_j - th_i) = sum_m lambda_m v_m[i] (cos th_i S_m - sin th_i C_m),
+#     S_m = sum_j v_m[j] sin th_j,  C_m = sum_j v_m[j] cos th_j          ("order parameters" weighted by the eigenvectors)
+# with 52 of the 512 eigenvalues above 1e-12 |lambda_max| on the shipped 8 x 8 x 8 grid (mode 0 IS the classical mean field).
+# alpha commutes with the three reflections of the grid, so every eigenvector lives in one of the 8 parity sectors: the
+# 64 x 64 sector blocks are diagonalised separately (at most 9 modes each).
+def sector_blocks(table, gx, gy, gz):
+    """The 8 parity-sector blocks of the block-Toeplitz operator alpha_ij = table[|dz|, |dx|, |dy|] on a gx*gy*gz grid
+    with even extents.  Sector s = 4 * [odd in y] + 2 * [odd in z] + [odd in x]; block[s][a, b] =
+    sum_g chi_s(g) alpha(a, g b) over the 8 reflections g, with a, b in the fundamental octant, index
+    a = ((zq * gx/2 + xq) * gy/2 + yq).  In the (unnormalised) sector coordinates X_s[b] = sum_g chi_s(g) x[g b] the
+    operator acts as y_s = block[s] @ X_s and (alpha x)[g a] = 1/8 sum_s chi_s(g) y_s[a]."""
+    T = np.asarray(table, dtype=np.float64).reshape(gz, gx, gy)
+    hz, hx, hy = gz // 2, gx // 2, gy // 2
+    zq, xq, yq = np.meshgrid(np.arange(hz), np.arange(hx), np.arange(hy), indexing="ij")
+    zq, xq, yq = zq.ravel(), xq.ravel(), yq.ravel()
+    blocks = []
+    for s in range(8):
+        py, pz, px = (-1.0 if s & 4 else 1.0), (-1.0 if s & 2 else 1.0), (-1.0 if s & 1 else 1.0)
+        blk = np.zeros((zq.size, zq.size))
+        for mz, sz in ((0, 1.0), (1, pz)):
+            zb = gz - 1 - zq if mz else zq
+            for mx, sx in ((0, 1.0), (1, px)):
+                xb = gx - 1 - xq if mx else xq
+                for my, sy in ((0, 1.0), (1, py)):
+                    yb = gy - 1 - yq if my else yq
+                    blk += sz * sx * sy * T[np.abs(zq[:, None] - zb[None, :]), np.abs(xq[:, None] - xb[None, :]),
+                                            np.abs(yq[:, None] - yb[None, :])]
+        blocks.append(blk)
+    return blocks
+
+
+def spectral_factors(table, gx, gy, gz, tol=1e-12):
+    """Eigen-decomposition of the 8 sector blocks, truncated at ``|lambda| > tol * |lambda|_max``.
+    Returns (vecs [8][n_fund][r_max], vals [8][r_max], ranks [8], residual): eigenvectors of unit length (zero padded),
+    eigenvalues sorted by magnitude, and ``residual`` = the largest dropped |eigenvalue| = the spectral norm of
+    (alpha - truncated alpha)."""
+    blocks = sector_blocks(table, gx, gy, gz)
+    eig = [np.linalg.eigh(0.5 * (b + b.T)) for b in blocks]
+    lam_max = max(np.abs(w).max() for w, _ in eig)
+    keep = [np.argsort(-np.abs(w)) for w, _ in eig]
+    ranks = [int(np.count_nonzero(np.abs(w) > tol * lam_max)) for w, _ in eig]
+    r_max = max(max(ranks), 1)
+    n_f = blocks[0].shape[0]
+    vecs, vals = np.zeros((8, n_f, r_max)), np.zeros((8, r_max))
+    residual = 0.0
+    for s, ((w, v), order, r) in enumerate(zip(eig, keep, ranks)):
+        vecs[s, :, :r] = v[:, order[:r]]
+        vals[s, :r] = w[order[:r]]
+        if r < w.size:
+            residual = max(residual, float(np.abs(w[order[r]])))
+    return vecs, vals, ranks, residual
+
+
+def spectral_apply(vecs, vals, x, gx, gy, gz):
+    """alpha @ x through the truncated sector eigen-decomposition (float64 host restatement of what the CUDA kernel does;
+    used by the tests to measure the truncation error against the dense operator)."""
+    x = np.asarray(x, dtype=np.float64).reshape(gz, gx, gy)
+    hz, hx, hy = gz // 2, gx // 2, gy // 2
+    out = np.zeros_like(x)
+    for s in range(8):
+        py, pz, px = (-1.0 if s & 4 else 1.0), (-1.0 if s & 2 else 1.0), (-1.0 if s & 1 else 1.0)
+        X = np.zeros((hz, hx, hy))
+        for mz, sz in ((0, 1.0), (1, pz)):
+            for mx, sx in ((0, 1.0), (1, px)):
+                for my, sy in ((0, 1.0), (1, py)):
+                    sub = x[::-1][:hz] if mz else x[:hz]
+                    sub = sub[:, ::-1][:, :hx] if mx else sub[:, :hx]
+                    sub = sub[:, :, ::-1][:, :, :hy] if my else sub[:, :, :hy]
+                    X += sz * sx * sy * sub
+        y = (vecs[s] * vals[s]) @ (vecs[s].T @ X.ravel())
+        y = y.reshape(hz, hx, hy) / 8.0
+        for mz, sz in ((0, 1.0), (1, pz)):
+            for mx, sx in ((0, 1.0), (1, px)):
+                for my, sy in ((0, 1.0), (1, py)):
+                    blk = sz * sx * sy * y
+                    blk = blk[::-1] if mz else blk
+                    blk = blk[:, ::-1] if mx else blk
+                    blk = blk[:, :, ::-1] if my else blk
+                    out[(slice(hz, None) if mz else slice(0, hz)), (slice(hx, None) if mx else slice(0, hx)),
+                        (slice(hy, None) if my else slice(0, hy))] += blk
+    return out.ravel()

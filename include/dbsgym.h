@@ -105,8 +105,8 @@ int  dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out);
 /* which step-kernel variant a launch over n_envs environments of this handle uses (for op counts in benchmarks):
  * 0 plain Toeplitz GRID, 1 DENSE, 2 parity-sector GRID_SYM (run-time extents), 3 GRID_SYM unrolled for the
  * 8 x 8 x 8 grid (one CTA per environment), 4 multi-worker (8 environments per CTA sharing precomputed sector
- * coefficients), 5 cluster mode (N > 4096), 6 GRID_SYM with gx = 8 fixed, 7 / 8 GRID_SYM with lines of 16 / 32 (gy = 16 / 32);
- * negative = error code */
+ * coefficients), 5 cluster mode (N > 4096), 6 GRID_SYM with gx = 8 fixed, 7 / 8 GRID_SYM with lines of 16 / 32 (gy = 16 / 32),
+ * 9 spectral contraction (dbsgym_set_coupling_spectral; multi-worker hosting); negative = error code */
 int  dbsgym_step_variant(const DbsGymHandle* h, int32_t n_envs);
 void dbsgym_destroy(DbsGymHandle* h);
 /* text of the last error on this handle (h == NULL: last error of a failed create) */
@@ -118,6 +118,19 @@ const char* dbsgym_last_error(const DbsGymHandle* h);
  * DENSE: alpha[i*N + j], must be symmetric.  Shared by every environment of the handle. */
 int dbsgym_set_coupling_grid(DbsGymHandle* h, const double* table);
 int dbsgym_set_coupling_dense(DbsGymHandle* h, const double* alpha);
+/* Spectral form of the GRID operator (after dbsgym_set_coupling_grid; fp32 handles on the 8 x 8 x 8 grid): the
+ * generalised mean-field identity
+ *     sum_j alpha_ij sin(th_j - th_i) = sum_m lambda_m v_m[i] (cos th_i S_m - sin th_i C_m),  S_m = sum_j v_m[j] sin th_j, C_m likewise,
+ * over the eigenpairs of alpha (env.py:219-223, :252-256) whose |lambda_m| exceeds the caller's truncation threshold.
+ * alpha commutes with the three reflections of the grid, so the eigenvectors are given per parity sector
+ * s = 4 [odd in y] + 2 [odd in z] + [odd in x]:  vecs[(s * 64 + a) * r_max + m] = unit eigenvector m of the 64 x 64
+ * sector block at fundamental-octant point a = (zq * 4 + xq) * 4 + yq, vals[s * r_max + m] its eigenvalue (in the
+ * unnormalised sector coordinates X_s[a] = sum_g chi_s(g) x[g a]); sectors even in y use their first r_even modes,
+ * sectors odd in y their first r_odd (1..9 each; pad with zeros).  The truncation error is the caller's
+ * responsibility (dbsgym_b200/geometry.py: spectral_factors returns the spectral norm of what was dropped).
+ * r_even = r_odd = 0 switches back to the exact sector-block contraction. */
+int dbsgym_set_coupling_spectral(DbsGymHandle* h, int32_t r_even, int32_t r_odd, int32_t r_max,
+                                 const double* vecs, const double* vals);
 
 /* Per-environment vectors uploaded at reset (env.py:566-598): natural frequencies after
  * remove_negative_w0, stimulation conductance of the first contact (env.py:422-423), summed

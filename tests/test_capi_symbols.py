@@ -76,8 +76,11 @@ def test_no_cpu_fallback(lib):
 def test_release_library_reads_no_environment_variables():
     """Tuning / A-B switches travel in DbsGymConfig (mw_mode, force_cluster, ctas_per_sm, debug_flags): the library
     itself must not consult the process environment."""
-    for f in ("api.cu", "step_kernel.cuh", "obs_kernel.cuh", "eval_kernel.cuh"):
-        assert "getenv" not in open(os.path.join(ROOT, "dbsgym_b200", "csrc", f)).read(), f
+    csrc = os.path.join(ROOT, "dbsgym_b200", "csrc")
+    files = [f for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".h"))]
+    assert "api.cu" in files and "step_kernel.cuh" in files
+    for f in files:
+        assert "getenv" not in open(os.path.join(csrc, f)).read(), f
 
 
 def test_product_does_not_import_oracle():

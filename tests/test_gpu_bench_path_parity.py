@@ -32,12 +32,15 @@ pytestmark = pytest.mark.gpu
 # beta power is 27 %)
 ENS_BBPOW_MEAN_TOL, ENS_BBPOW_MEDIAN_TOL, ENS_KS_TOL, ENS_KS_LATE_TOL, ENS_REWARD_MEAN_TOL = 0.02, 0.02, 0.015, 0.04, 0.02
 
-MW_KERNELS = [("single", {"mw": False}, 3), ("multi_worker", {"mw": True}, 4)]
+# the three float32 step kernels for the shipped 8 x 8 x 8 grid: (name, engine options, coupling_eval, dbsgym_step_variant)
+F32_KERNELS = [("single", {"mw": False}, "exact", 3), ("multi_worker", {"mw": True}, "exact", 4),
+               ("spectral", None, "spectral", 9)]
 
 
-def _core(dicts, precision="f32", engine_options=None, transfer="full"):
+def _core(dicts, precision="f32", engine_options=None, transfer="full", coupling_eval="exact"):
     from dbsgym_b200.batched import BatchedKuramoto
-    return BatchedKuramoto(copy.deepcopy(dicts), precision=precision, transfer=transfer, engine_options=engine_options)
+    return BatchedKuramoto(copy.deepcopy(dicts), precision=precision, transfer=transfer, engine_options=engine_options,
+                           coupling_eval=coupling_eval)
 
 
 @pytest.mark.parametrize("golden,cfg,seed,kw,n_steps", [
@@ -45,15 +48,16 @@ def _core(dicts, precision="f32", engine_options=None, transfer="full"):
     ("step_env1.npz", "env1", 11, {}, 12),
     ("step_env1_directed.npz", "env1", 12, dict(reward="temp_const_action", directed_stimulation=True,
                                                 elec_coords=[[5, 2, 3]], rec_coords=[[3, 5, 1]]), 6)])
-@pytest.mark.parametrize("name,options,variant", MW_KERNELS)
-def test_f32_kernels_teacher_forced_against_reference_goldens(golden, cfg, seed, kw, n_steps, name, options, variant):
-    """Both float32 step kernels for the 8 x 8 x 8 grid -- one CTA per environment (variant 3) and the multi-worker kernel
-    the benchmark runs (variant 4) -- against the fixtures the reference's own env.py produced."""
+@pytest.mark.parametrize("name,options,ceval,variant", F32_KERNELS)
+def test_f32_kernels_teacher_forced_against_reference_goldens(golden, cfg, seed, kw, n_steps, name, options, ceval, variant):
+    """The float32 step kernels for the 8 x 8 x 8 grid -- exact contraction with one CTA per environment (variant 3), its
+    multi-worker form (variant 4) and the spectral kernel the benchmark runs (variant 9) -- against the fixtures the
+    reference's own env.py produced."""
     from test_gpu_parity import _teacher_forced
     g = load_golden(golden)
     d = make_params(cfg, seed, **kw)
     B = 3                                    # (3 of the 8 workers of a multi-worker CTA busy, 5 idle)
-    core = _core([d] * B, engine_options=options)
+    core = _core([d] * B, engine_options=options, coupling_eval=ceval)
     assert core.engine.step_variant() == variant
     core.engine.counters(reset=True)
     c = _teacher_forced(core, g, "f32", n_steps, 5e-3 if kw else 2e-4)
@@ -81,8 +85,10 @@ def _sync_oracle(orc, core, e, y, win):
     orc.current_time = core.current_time(e)
 
 
-def test_bench_config_4096_env1_f32_against_oracle():
-    """BASELINE configs[2] as bench.py builds it (env1, 4096 environments, float32, multi-worker kernel): a sample of
+@pytest.mark.parametrize("ceval,variant", [("exact", 4), ("spectral", 9)])
+def test_bench_config_4096_env1_f32_against_oracle(ceval, variant):
+    """BASELINE configs[2] as bench.py builds it (env1, 4096 environments, float32; the spectral kernel bench.py runs by
+    default and the exact multi-worker kernel): a sample of
     environments is checked against the CPU oracle per step -- teacher-forced at 1e-5 rad, then free-running with the
     stated per-step tolerance -- plus exact counters for the whole batch."""
     import sys, os
@@ -90,9 +96,9 @@ def test_bench_config_4096_env1_f32_against_oracle():
     from bench import build_params
     B = 4096
     dicts = build_params(B, seed0=10)
-    core = _core(dicts)
+    core = _core(dicts, coupling_eval=ceval)
     eng = core.engine
-    assert eng.step_variant() == 4
+    assert eng.step_variant() == variant
     sample = [0, 7, 1183, 1184, 2500, 4095]          # first / last worker slots, both sides of a wave boundary
     orcs = {e: _oracle_for(core, e, dicts[e]) for e in sample}
     rng = np.random.default_rng(5)
@@ -208,7 +214,7 @@ def _episode(core, acts, env=0):
 def test_full_2048_step_episode_against_oracle():
     """One whole PPO rollout (2048 steps, README.md:66) of an env0 environment against the float64 CPU oracle.
     float64 GPU: the trajectory stays on the oracle's for the WHOLE episode (order parameter within 1e-8 over the first 1024 steps and 1e-5
-    over all 2048, rewards 1e-6 / 1e-3 relative).  float32 GPU (the benchmark's multi-worker kernel): rounding differences of 1e-7 per step are amplified
+    over all 2048, rewards 1e-6 / 1e-3 relative).  float32 GPU (the benchmark's spectral kernel): rounding differences of 1e-7 per step are amplified
     by the chaotic dynamics roughly like exp(k / 170) -- the order-parameter error must stay inside the stated envelope
     1e-4 / 1e-4 / 1e-3 / 1e-2 up to step 200 / 400 / 800 / 1200 (measured 5e-6 / 1e-5 / 7e-5 / 6e-4), and over the first
     1024 steps beta-band power and reward mean agree within 1e-3 relative, the reward distributions within a
@@ -226,10 +232,10 @@ def test_full_2048_step_episode_against_oracle():
     x_ref = np.concatenate(tm_ref)
     ends = np.cumsum([len(v) for v in tm_ref])
     out = {}
-    for precision, options in (("f64", None), ("f32", {"mw": True})):
-        core = _core([d] * 2, precision=precision, engine_options=options)
+    for precision, ceval in (("f64", "exact"), ("f32", "spectral")):
+        core = _core([d] * 2, precision=precision, coupling_eval=ceval)
         if precision == "f32":
-            assert core.engine.step_variant() == 4
+            assert core.engine.step_variant() == 9
         core.engine.counters(reset=True)                # (the reset transient has rejections; step() must not)
         tm, rew = _episode(core, acts)
         st = core.engine.counters()
@@ -271,9 +277,9 @@ def test_long_horizon_statistical_equivalence_f32_vs_f64():
     dicts = [make_params("env0", 200 + 3 * e, rand_seed=300 + e) for e in range(E)]
     acts = np.random.default_rng(7).uniform(-1, 1, (n, E)).astype(np.float32)
     res = {}
-    for precision, options in (("f64", None), ("f32", {"mw": True})):
+    for precision, ceval in (("f64", "exact"), ("f32", "spectral")):
         np.random.seed(0)
-        core = _core(dicts, precision=precision, engine_options=options)
+        core = _core(dicts, precision=precision, coupling_eval=ceval)
         B = core.num_envs
         tm, rew = [[] for _ in range(B)], np.zeros((n, B))
         for k in range(n):

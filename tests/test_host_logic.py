@@ -288,3 +288,30 @@ def test_batch_rejects_environments_with_different_geometry():
     from dbsgym_b200.batched import BatchedKuramoto
     with pytest.raises(ValueError, match="neur_coords"):
         BatchedKuramoto([d, e])                        # refused before any device is touched
+
+
+def test_spectral_factors_reproduce_the_coupling_operator():
+    """geometry.spectral_factors (the generalised mean-field form the float32 kernel evaluates): the truncated sector
+    eigen-decomposition must reproduce alpha = cos(distance) (env.py:219-223) to the reported residual, the leading mode
+    must be the classical mean field, and the ranks must fit the compiled kernel (9 even / 4 odd at 1e-10)."""
+    coords, grid = geometry.neuron_grid(8, 8, 8, 512, 0.1)
+    table = geometry.coupling_table(coords, grid, [8, 8, 8], "cos")
+    alpha = geometry.coupling_rows(coords, np.arange(512), "cos")
+    vecs, vals, ranks, residual = geometry.spectral_factors(table, 8, 8, 8, tol=1e-10)
+    assert ranks == [9, 4, 4, 4, 4, 4, 4, 1] and residual < 3e-8
+    lam = np.linalg.eigvalsh(alpha)
+    assert abs(vals[0, 0] - lam[-1]) < 1e-9 * lam[-1] and np.all(vecs[0, :, 0] * np.sign(vecs[0, 0, 0]) > 0)
+    rng = np.random.default_rng(0)
+    th = rng.uniform(0, 2 * np.pi, 512)
+    for x in (np.sin(th), np.cos(th), np.eye(512)[137]):
+        err = np.max(np.abs(geometry.spectral_apply(vecs, vals, x, 8, 8, 8) - alpha @ x))
+        assert err <= residual * np.linalg.norm(x) * 1.0001 + 1e-13
+    # RHS error of the identity, in rad per time unit, at the shipped K / N: far below float32 rounding (~1e-7)
+    s, c = np.sin(th), np.cos(th)
+    exact = 0.52 / 512 * (c * (alpha @ s) - s * (alpha @ c))
+    approx = 0.52 / 512 * (c * geometry.spectral_apply(vecs, vals, s, 8, 8, 8) - s * geometry.spectral_apply(vecs, vals, c, 8, 8, 8))
+    assert np.max(np.abs(exact - approx)) < 1e-10
+    # all modes kept: exact to rounding
+    v2, w2, r2, res2 = geometry.spectral_factors(table, 8, 8, 8, tol=0.0)
+    assert sum(r2) == 512 and res2 == 0.0
+    assert np.max(np.abs(geometry.spectral_apply(v2, w2, s, 8, 8, 8) - alpha @ s)) < 1e-11
