@@ -174,6 +174,60 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------
+def verbatim_reference_steps_per_sec(n_steps=16):
+    """the reference's OWN environment/env.py imported verbatim (numpy for jax.numpy, the
+    restated diffrax) -- env0 params_dict_train, np.random.seed(10), actions default_rng(0).uniform(-1, 1); a bounded
+    sample of the 2048-step rollout.  Only where /root/reference exists (not on the GPU box)."""
+    from oracle import run_reference
+    if not run_reference.reference_available():
+        return None
+    env_mod, utils_mod, cfgs = run_reference.load_reference()
+    cfg = cfgs["env0"]
+    np.random.seed(10)
+    base = copy.deepcopy(cfg.params_dict_train)
+    w0, nc, ng, w0t, wl, lm = utils_mod.generate_w0_with_locus(
+        cfg.n_neurons, cfg.grid_size, cfg.coord_modif, locus_center=base["locus_center"], locus_size=base["locus_size"],
+        wmuL=base["wmuL"], wsdL=base["wsdL"], show=False)
+    base.update(w0=w0, w0_without_locus=w0t, locus_without_w0=wl, locus_mask=lm, neur_coords=nc, neur_grid=ng,
+                reward_func="bbpow_action", verbose=0)
+    env = env_mod.SpatialKuramoto(base)
+    acts = np.random.default_rng(0).uniform(-1, 1, 2048).astype(np.float32)
+    env.step(acts[:1])
+    t0 = time.perf_counter()
+    for a in acts[1:1 + n_steps]:
+        env.step(np.array([a], dtype=np.float32))
+    return n_steps / (time.perf_counter() - t0)
+
+
+def step_kernel_model(variant, rhs_exec, ypar, n_osc=N_OSC):
+    """Executed FP32 flop of one env-step of the step kernel (FFMA = 2, FFMA2 = 4, FADD / FMUL = 1, FADD2 / FMUL2 = 2 per
+    lane), from the instruction counts of the contraction per thread; DESIGN.md section 3 derives them and
+    profiles/*_flop_count.json holds the ncu-measured count of the same kernel for comparison."""
+    N = n_osc
+    other = 700 * N                                      # tableau combinations, error norm, dense output, LFP, reward
+    if variant == 9:
+        # spectral kernel, compiled ranks (9 even, 4 odd), per thread (8 oscillators) and RHS evaluation:
+        # projection 13 x (FMUL2 + 3 FFMA2) = 182, row sums 52 x (15 FADD2 + FMUL2) / 64 = 26, expansion 4 x (FMUL2 + 8 FFMA2)
+        # + 4 x (FMUL2 + 3 FFMA2) = 192, two sector butterflies 2 x 16 FFMA2 = 128, y folds 32, k = c0 + c A s - s A c 32,
+        # range reduction of the sincos 40, stage combination (mean 27 FFMA + 16) 70
+        per_thread = 182 + 26 + 192 + 128 + 32 + 32 + 40 + 70
+        return rhs_exec * per_thread * (N // 8) + other, "spectral (34 modes in 9 + 4 padded slots per sector pair)"
+    blk = 148 if variant == 4 else (196 if (ypar and variant in (3, 6)) else 304)
+    per_rhs = (blk / 256.0) * N * N + ((160 if ypar else 128) / 8.0) * N
+    return rhs_exec * per_rhs + other, "exact parity-sector blocks"
+
+
+def measured_kernel_counts(variant):
+    """ncu-measured per-launch numbers of the step kernel committed with the round (scripts/ncu_counts.py):
+    dram bytes and executed FP32 flop at 4096 environments; None when no capture of this variant is committed."""
+    path = os.path.join(ROOT, "profiles", f"r02_step_kernel_variant{variant}_counts.json")
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def run_gpu_arm(args):
     # keep stdout clean for the ONE JSON line: libraries (NCCL's version banner, ...) write to fd 1
     json_out = os.fdopen(os.dup(1), "w")
@@ -190,16 +244,23 @@ def run_gpu_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from dbsgym_b200.engine import measure_fp32_peak
-    from dbsgym_b200.sharding import gather_episode_stats
+    from dbsgym_b200 import _capi
+    from dbsgym_b200.engine import measure_fp32_peak, measure_mufu_peak
+    from dbsgym_b200.sharding import gather_episode_stats, shard_bounds
     from dbsgym_b200.vec_env import BatchedKuramotoVecEnv
 
-    B = args.envs
+    if args.strong:                                      # fixed total work: args.envs environments over all ranks
+        lo, hi = shard_bounds(args.envs, rank, world)
+        B, seed_off = hi - lo, lo
+        total_envs = args.envs
+    else:
+        B, seed_off = args.envs, rank * args.envs
+        total_envs = B * world
     t_setup = time.perf_counter()
-    dicts = build_params(B, seed0=10 + rank * B)
+    dicts = build_params(B, seed0=10 + seed_off)
     for d in dicts:
         d["precision"] = args.precision
-    venv = BatchedKuramotoVecEnv(dicts, device=local_rank)
+    venv = BatchedKuramotoVecEnv(dicts, device=local_rank, coupling_eval=args.coupling_eval)
     venv.reset()
     eng = venv.core.engine
     setup_s = time.perf_counter() - t_setup
@@ -241,7 +302,8 @@ def run_gpu_arm(args):
         eng.step_device(act_dev[i].data_ptr(), obs_dev.data_ptr(), rew_dev.data_ptr(), done_dev.data_ptr(),
                         stream.cuda_stream)
     sync_all()
-    c0 = eng.counters(reset=True)
+    eng.counters(reset=True)
+    eng.launch_count(reset=True)
     n_clk0 = len(clocks.rows)
     t_wall = time.perf_counter()
     for i in range(K):
@@ -256,22 +318,50 @@ def run_gpu_arm(args):
     sync_all()
     wall_dev = time.perf_counter() - t_wall
     n_clk1 = len(clocks.rows)
+    launches_dev = eng.launch_count(reset=True)                     # kernels launched by the library in the timed region
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     dev_time_s = float(step_ms.sum()) * 1e-3
     counters = eng.counters()
     rhs_reused = eng.rhs_reused()
+
+    # ---------- (1b) sustained: back-to-back steps for >= args.sustain seconds (no flush, two events), clocks sampled ----------
+    sustained = None
+    if args.sustain > 0:
+        n_sus = max(K, int(args.sustain / max(dev_time_s / K, 1e-6) * 1.15))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        c0 = len(clocks.rows)
+        e0.record(stream)
+        for i in range(n_sus):
+            eng.step_device(act_dev[Wm + i % K].data_ptr(), obs_dev.data_ptr(), rew_dev.data_ptr(), done_dev.data_ptr(),
+                            stream.cuda_stream)
+        e1.record(stream)
+        sync_all()
+        sus_s = e0.elapsed_time(e1) * 1e-3
+        sm = [float(r[1]) for r in clocks.rows[c0:] if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        sustained = {"steps": n_sus, "seconds": sus_s, "value_this_rank": B * n_sus / sus_s,
+                     "sm_mhz_median": float(np.median(sm)) if sm else None, "clock_samples": len(sm),
+                     "note": "back-to-back launches, no L2 flush, one CUDA-event pair around the whole run"}
 
     # ---------- (2) end to end through the public VecEnv API with host buffers ----------
     eng.set_timing(False)
     for i in range(Wm):
         venv.step_async(actions[i].reshape(B, 1)); venv.step_wait()
     sync_all()
+    eng.launch_count(reset=True)
+    n_new_total = 0
     t0 = time.perf_counter()
     for i in range(K):
         venv.step_async(actions[Wm + i].reshape(B, 1))
         obs, rew, done, infos = venv.step_wait()
     sync_all()
     e2e_s = time.perf_counter() - t0
+    launches_e2e = eng.launch_count(reset=True)
+    # bytes that crossed PCIe per step: every new window sample is stored twice in the pinned host log (zero-copy stores),
+    # plus the control block (reward f32, sample count i32, log position i32, done u8); counted from the step counters
+    n_new_total = int(eng.lfp()[2].astype(np.int64).sum())          # samples of the LAST step, every environment
+    d2h_e2e = n_new_total * 2 * 4 + B * (4 + 4 + 4 + 1)
+    assert isinstance(obs, np.ndarray) and obs.shape == (B, 1, venv.core.window)
     # the C-ABI host call that returns the FULL [B, W] observation every step (no host-side window mirror)
     core = venv.core
     for i in range(Wm):
@@ -286,94 +376,107 @@ def run_gpu_arm(args):
     clk["samples_in_device_loop"] = n_clk1 - n_clk0
 
     # ---------- max over ranks ----------
-    times = torch.tensor([dev_time_s, e2e_s, capi_s], dtype=torch.float64, device=dev)
+    sus_s = sustained["seconds"] if sustained else 0.0
+    times = torch.tensor([dev_time_s, e2e_s, capi_s, sus_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         # NCCL is used only off the step path: gather per-env episode statistics
-        stats = gather_episode_stats(np.stack([rew.astype(np.float64), done.astype(np.float64)], axis=1),
-                                     B * world, rank, world, device=dev)
-        assert stats.shape == (B * world, 2)
-    dev_time_s, e2e_s, capi_s = (float(v) for v in times.cpu())
+        if not args.strong:
+            stats = gather_episode_stats(np.stack([rew.astype(np.float64), done.astype(np.float64)], axis=1),
+                                         B * world, rank, world, device=dev)
+            assert stats.shape == (B * world, 2)
+    dev_time_s, e2e_s, capi_s, sus_s = (float(v) for v in times.cpu())
 
     if rank == 0:
-        total_env_steps = B * world * K
+        total_env_steps = total_envs * K
         value = total_env_steps / dev_time_s
         rhs_per_env_step = counters["rhs_evals"] / (B * K)               # the reference's count (32)
         rhs_exec = (counters["rhs_evals"] - rhs_reused) / (B * K)        # executed: the first stage of a segment is carried over
         substeps_per_env_step = (counters["accepted"] + counters["rejected"]) / (B * K)
-        # Algorithmic work of the step kernel.  Dense formulation: R * 4 N^2 + ~700 N.
-        # The GRID_SYM kernel evaluates the same contraction in the parity-sector basis; its OWN executed
-        # flop count (what the roofline fraction is quoted against, SURVEY.md 8d rule for reduced
-        # formulations) per thread and (zj,xj) block -- there are N^2/256 of those per RHS -- is
-        #   z/x sectors only            : 12 FFMA2 (table rows -> sector coefficients) + 64 FFMA2      = 304 flop
-        #   + y parity                  : 12 FFMA2 + 20 FADD (even/odd coefficients) + 32 FFMA2        = 196 flop
-        #   + y parity, multi-worker    : 20 FADD + 32 FFMA2 (coefficients precomputed once per CTA)   = 148 flop
-        # (instruction counts checked in the SASS: 704 = 16 x 44 resp. 512 = 16 x 32 FFMA2 in the unrolled contraction),
-        # plus the quad butterflies (128 flop) and, with y parity, the even/odd folds (32 flop) per thread = N/8 threads.
-        from dbsgym_b200 import _capi
         ypar = bool(_capi.load().dbsgym_build_flags() & 1)
         variant = eng.step_variant(B)
         dense_flop_per_env_step = rhs_per_env_step * 4 * N_OSC * N_OSC + 700 * N_OSC
-        sym = variant in (2, 3, 4, 6)
-        blk_flop = 148 if variant == 4 else (196 if (ypar and variant in (3, 6)) else 304)
-        sym_flop_per_rhs = (blk_flop / 256.0) * N_OSC * N_OSC + ((160 if ypar else 128) / 8.0) * N_OSC
-        flop_per_env_step = (rhs_exec * sym_flop_per_rhs + 700 * N_OSC) if sym else dense_flop_per_env_step
+        flop_per_env_step, flop_model = step_kernel_model(variant, rhs_exec, ypar)
         kernel_name = {0: "step_kernel<float,GRID>", 1: "step_kernel<DENSE>", 2: "step_kernel<GRID_SYM>",
                        3: "step_kernel<float,GRID_SYM,8x8x8" + (",y-parity>" if ypar else ">"),
                        4: "step_kernel<float,GRID_SYM,8x8x8,y-parity,multi-worker (8 envs per CTA, precomputed sector coefficients)>",
-                       5: "step_kernel<cluster>", 6: "step_kernel<float,GRID_SYM,gx=8>"}.get(variant, "step_kernel")
+                       5: "step_kernel<cluster>", 6: "step_kernel<float,GRID_SYM,gx=8>",
+                       9: "step_kernel<float,SPECTRAL,8x8x8 (generalised mean-field identity, 8 envs per CTA)>"}.get(variant, "step_kernel")
         k_step = float(np.mean([m[0] for m in kern_ms])) * 1e-3
         k_obs = float(np.mean([m[1] for m in kern_ms])) * 1e-3
         peaks, peak_src = measured_peaks()
         peak_ffma = measure_fp32_peak(local_rank, packed=False)
         peak_ffma2 = measure_fp32_peak(local_rank, packed=True)
+        peak_mufu = measure_mufu_peak(local_rank)
         fp32_peak = max(peak_ffma, peak_ffma2)
         achieved_tf = flop_per_env_step * B / k_step / 1e12
-        fused_obs = os.environ.get("DBSGYM_NO_FUSED_OBS") is None     # ring append + reward live in the step kernel's tail
-        obs_bytes = B * (2 * 2340 * 4) if fused_obs else B * (2 * 2340 * 4 + 19 * 8 + 32)   # ring read + obs write (+ samples)
+        counts = measured_kernel_counts(variant)
+        traffic = None
+        if counts and counts.get("n_envs"):
+            traffic = (counts["dram_bytes_read"] + counts["dram_bytes_write"]) * B / counts["n_envs"]
+        fused_obs = not venv.core.engine.options.get("no_fused_obs", False)
+        obs_bytes = B * (2 * 2340 * 4)                              # ring read + chronological observation write
         cpu_n = 12
         cpu_as_written = cpu_port_steps_per_sec(cpu_n, "as_written", np.float32)
         cpu_matvec = cpu_port_steps_per_sec(200, "matvec", np.float64)
+        verbatim = verbatim_reference_steps_per_sec(16) if args.cpu_reference else None
+        mufu_per_env_step = (rhs_exec * 2 * N_OSC + 19 * N_OSC)       # sin + cos per oscillator and RHS, cos per LFP sample
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-            "ms_per_step": 1e3 * dev_time_s / K, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * dev_time_s / K, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
             "vs_baseline": None, "dtype": "f32" if args.precision == "f32" else "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[2]: env1, N=512 oscillators, 4096 envs per GPU, uniform(-1,1) actions",
-                       "envs_per_gpu": B, "global_envs": B * world, "precision": args.precision,
-                       "coupling": eng.coupling, "l2": "flush between timed iterations: a 256 MB buffer written, then another 256 MB buffer read (cold, clean L2)",
+            "config": {"workload": "BASELINE configs[2]: env1, N=512 oscillators, 4096 envs per GPU, uniform(-1,1) actions"
+                                   if not args.strong else
+                                   f"BASELINE configs[2] (env1, N=512), STRONG scaling: {total_envs} environments in total over all GPUs",
+                       "envs_per_gpu": B, "global_envs": total_envs, "precision": args.precision,
+                       "coupling": eng.coupling, "coupling_eval": venv.core.coupling_eval,
+                       "spectral": eng.spectral,
+                       "l2": "flush between timed iterations: a 256 MB buffer written, then another 256 MB buffer read (cold, clean L2)",
                        "timing": "sum of per-step CUDA-event intervals on the launch stream, max over ranks"},
             "oscillator_updates_per_sec": value * N_OSC * substeps_per_env_step,
             "oscillator_rhs_evals_per_sec": value * N_OSC * rhs_exec,          # executed evaluations
             "rk_substeps_per_env_step": substeps_per_env_step, "rhs_evals_per_env_step": rhs_per_env_step,
             "rhs_evals_executed_per_env_step": rhs_exec,
             "solver_status": counters["status"],
-            "e2e": {"value": B * world * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 4,
-                    "d2h_bytes_per_step": B * (int(round(counters["accepted"] / (B * K) * 0 + 18)) * 2 * 4 + 4 + 4 + 4 + 1),
-                    "api": "BatchedKuramotoVecEnv.step_async/step_wait, numpy actions in, numpy obs/reward/done out. "
-                           "Observations are views of a pinned [B,2W] host mirror of the device rings that the observation "
-                           "kernel updates through mapped memory (each new sample stored twice, ~18 samples/step), so only "
-                           "the new samples + reward + done + ring position cross PCIe (dbsgym_step_host_mirror)",
-                    "full_obs_d2h": {"value": B * world * K / capi_s, "d2h_bytes_per_step": B * (2340 * 4 + 4 + 1),
+            "e2e": {"value": total_envs * K / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * 4,
+                    "d2h_bytes_per_step": d2h_e2e, "gpu_launches": launches_e2e,
+                    "api": "BatchedKuramotoVecEnv.step_async/step_wait (copy_obs=False), numpy actions in, numpy obs/reward/done out. "
+                           "Observations are views of a pinned host sample log the step kernel appends to through mapped memory "
+                           "(each new sample stored twice, ~18 samples/step); later steps never overwrite a window already handed out "
+                           "(>= 13 steps, resets switch buffers), which is what SB3's rollout buffers need (dbsgym_step_host_mirror)",
+                    "full_obs_d2h": {"value": total_envs * K / capi_s, "d2h_bytes_per_step": B * (2340 * 4 + 4 + 1),
                                      "api": "dbsgym_step_host (whole [B,2340] f32 observation copied to pinned host memory every step)"}},
-            "gpu_launches": 2 * K,      # device-timed region: step_kernel + observation kernel per step (the e2e region: 1 per step when fused)
+            "gpu_launches": launches_dev,      # counted by the library: step kernel + observation copy kernel per device-timed step
             "roofline": {"bound": "fp32", "achieved": achieved_tf, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved_tf / fp32_peak if fp32_peak else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at 4096 envs, from the ncu
-                         # --set full capture profiles/r01_final3_step_obs_raw.csv (52.45 MB read + 0.73 MB write)
-                         "traffic": 53.19e6 * B / 4096,
+                         "traffic": traffic,
+                         "traffic_source": (counts or {}).get("source"),
                          "kernel": kernel_name,
-                         "kernel_ms": k_step * 1e3, "flop_per_env_step": flop_per_env_step,
+                         "kernel_ms": k_step * 1e3, "flop_per_env_step": flop_per_env_step, "flop_model": flop_model,
+                         "flop_per_env_step_ncu": (counts or {}).get("fp32_flop_per_env_step"),
                          "dense_formulation_flop_per_env_step": dense_flop_per_env_step,
                          "dense_equivalent_tflops": dense_flop_per_env_step * B / k_step / 1e12,
                          "peak_source": "best of the FFMA and FFMA2 micro-benchmarks run in this process (dbsgym_measure_fp32_peak_mode); nominal 74.4",
-                         "peak_ffma": peak_ffma, "peak_ffma2": peak_ffma2},
+                         "peak_ffma": peak_ffma, "peak_ffma2": peak_ffma2,
+                         "issue": {"warp_instructions_per_env_step_ncu": (counts or {}).get("warp_inst_per_env_step"),
+                                   "frac_of_issue_slots": ((counts or {}).get("warp_inst_per_env_step") or 0) * B / k_step /
+                                                          (4 * 148 * (clk.get("sm_mhz") or 1965.0) * 1e6) or None,
+                                   "note": "share of the 4 x 148 warp-issue slots per cycle the kernel fills: what actually bounds the spectral kernel"},
+                         "mufu": {"achieved_tops": mufu_per_env_step * B / k_step / 1e12, "peak_tops": peak_mufu,
+                                  "frac": mufu_per_env_step * B / k_step / 1e12 / peak_mufu if peak_mufu else None,
+                                  "peak_source": "dbsgym_measure_mufu_peak in this process (nominal 148 x 16 x 1.965 GHz = 4.65)"}},
             "roofline_obs": {"bound": "hbm", "achieved": obs_bytes / k_obs / 1e9, "peak": peaks.get("hbm_gbs"),
                              "unit": "GB/s", "frac": obs_bytes / k_obs / 1e9 / peaks.get("hbm_gbs", 1.0),
                              "kernel": "obs_copy_kernel (ring -> chronological [B,W] f32; append/reward fused into the step kernel)" if fused_obs else "obs_kernel",
                              "kernel_ms": k_obs * 1e3, "peak_source": peak_src},
             "cpu_baseline": {"value": cpu_as_written, "unit": UNIT, "cores": 1, "kind": "port",
                              "sample": f"{cpu_n} env1 steps, one env, oracle port with the reference's N x N sine RHS in float32",
-                             "matvec_f64_value": cpu_matvec, "published_reference": "17-20 it/s (notebook tqdm, unknown CPU)"},
+                             "matvec_f64_value": cpu_matvec, "published_reference": "17-20 it/s (notebook tqdm, unknown CPU)",
+                             "reference_verbatim": None if verbatim is None else {
+                                 "value": verbatim, "kind": "reference", "cores": 1,
+                                 "sample": "16 of the 2048 steps of BASELINE configs[0] (env0, seed 10): the reference's own "
+                                           "environment/env.py imported verbatim over numpy + the restated diffrax, float64"}},
+            "sustained": None if sustained is None else dict(sustained, value=total_envs * sustained["steps"] / sus_s),
             "clocks": clk, "setup_s": setup_s, "wall_s_device_loop": wall_dev,
         }
         json_out.write(json.dumps(line) + "\n")
@@ -391,6 +494,12 @@ def main():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--coupling-eval", default="auto", choices=["auto", "exact", "spectral"],
+                    help="float32 coupling evaluation: spectral (default where it applies) or the exact sector blocks")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: --envs is the TOTAL over all GPUs")
+    ap.add_argument("--sustain", type=float, default=5.0, help="seconds of back-to-back steps for the sustained figure (0 = skip)")
+    ap.add_argument("--no-cpu-reference", dest="cpu_reference", action="store_false",
+                    help="skip timing the verbatim reference env.py (only possible where /root/reference exists)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -28,6 +28,7 @@ EXPORTS = [
     "dbsgym_set_recording", "dbsgym_set_schedule", "dbsgym_set_reward", "dbsgym_set_episode",
     "dbsgym_transient", "dbsgym_step", "dbsgym_step_host", "dbsgym_step_host_samples", "dbsgym_host_mirror", "dbsgym_step_host_mirror", "dbsgym_step_host_mirror_begin", "dbsgym_step_host_mirror_end", "dbsgym_get_obs_host",
     "dbsgym_get_lfp", "dbsgym_get_rewards", "dbsgym_get_phases", "dbsgym_get_window",
+    "dbsgym_np_gauss", "dbsgym_np_choice", "dbsgym_np_reset_draws",
     "dbsgym_state_bytes", "dbsgym_get_state", "dbsgym_set_state", "dbsgym_launch_count", "dbsgym_measure_mufu_peak",
     "dbsgym_set_window", "dbsgym_get_episode", "dbsgym_counters", "dbsgym_last_step_ms",
     "dbsgym_set_timing", "dbsgym_measure_fp32_peak", "dbsgym_measure_fp32_peak_mode",
@@ -66,11 +67,25 @@ class DbsGymEvalSpec(C.Structure):
     ]
 
 
+class DbsGymNpState(C.Structure):
+    _fields_ = [("key", C.c_uint32 * 624), ("pos", C.c_int32), ("has_gauss", C.c_int32), ("gauss", C.c_double)]
+
+
+class DbsGymResetPlan(C.Structure):
+    _fields_ = [("struct_bytes", C.c_uint32), ("n_envs", C.c_int32), ("n_osc", C.c_int32), ("walk_len", C.c_int32),
+                ("coord_lo", C.c_int32), ("coord_hi", C.c_int32), ("table_len", C.c_int32),
+                ("random_freq_update", C.c_int32), ("refix_cap_rows", C.c_int32), ("refix_cap_noise", C.c_int32),
+                ("init_mean", C.c_double), ("init_sd", C.c_double)]
+
+
+RESET_ELECTRODE_MOVE, RESET_ENCAPSULATION, RESET_PLASTICITY, RESET_WALK_REGEN, RESET_SPATIAL = 1, 2, 4, 8, 16
+
+
 class DbsGymError(RuntimeError):
     pass
 
 
-UNITS = ("api", "step_f32_grid", "step_f32_sym", "step_f32_lines", "step_f32_dense", "step_f32_mw", "step_f32_spectral",
+UNITS = ("api", "host_rng", "step_f32_grid", "step_f32_sym", "step_f32_lines", "step_f32_dense", "step_f32_mw", "step_f32_spectral",
          "step_f32_cluster", "step_f64_grid", "step_f64_sym", "step_f64_dense")
 HEADERS = ("step_kernel.cuh", "step_launch.h", "obs_kernel.cuh", "eval_kernel.cuh")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
@@ -173,6 +188,9 @@ def load():
         "dbsgym_set_state": (C.c_int, [vp, vp, C.c_uint64]),
         "dbsgym_launch_count": (C.c_int, [vp, u64p, C.c_int32]),
         "dbsgym_measure_mufu_peak": (C.c_int, [C.c_int32, C.c_double, f64p]),
+        "dbsgym_np_gauss": (C.c_int, [C.POINTER(DbsGymNpState), C.c_int64, C.c_double, C.c_double, vp]),
+        "dbsgym_np_choice": (C.c_int, [C.POINTER(DbsGymNpState), C.c_int64, C.c_uint32, vp]),
+        "dbsgym_np_reset_draws": (C.c_int, [C.POINTER(DbsGymNpState), C.POINTER(DbsGymResetPlan)] + [vp] * 12),
         "dbsgym_get_window": (C.c_int, [vp, vp, C.c_int32, vp]),
         "dbsgym_set_window": (C.c_int, [vp, vp, C.c_int32, vp]),
         "dbsgym_get_episode": (C.c_int, [vp, vp, vp]),

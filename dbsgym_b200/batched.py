@@ -36,7 +36,8 @@ def _pinned(shape, dtype):
 
 class BatchedKuramoto:
     def __init__(self, params_dicts, *, precision="f32", device=0, compat_env2=False, force_dense=False,
-                 save_init=False, transfer="delta", engine_options=None, coupling_eval="auto", spectral_tol=1e-10):
+                 save_init=False, transfer="delta", engine_options=None, coupling_eval="auto", spectral_tol=1e-10,
+                 batch_resets=True):
         """``coupling_eval``: how the float32 kernels evaluate the coupling sum of env.py:252-256 on the 8 x 8 x 8 grid --
         ``"exact"``: the parity-sector block contraction (the same sum as the reference, reassociated); ``"spectral"``:
         the generalised mean-field identity over the eigenmodes of alpha above ``spectral_tol * |lambda_max|``
@@ -126,7 +127,16 @@ class BatchedKuramoto:
         self._mirror_used = False
         self._lfp_cache = None
         self.current_step = np.zeros(B, dtype=np.int64)
+        self._episode_counts = np.array([h.total_episode_counts for h in self.hosts], dtype=np.int32)
         self._upload_and_run_transient(np.arange(B), setups)
+        # configurations whose resets draw more than Gaussians (temporal drift events, spatial re-draws): the host side of
+        # every later reset runs batched (host_batch.py: one native call replays numpy's global stream for all of them)
+        self.host_batch = None
+        if (p0["temporal_drift"] or p0["spatial_feature"]) and batch_resets:
+            from .host_batch import HostBatch, HostList
+            if HostBatch.supported(self.hosts):
+                self.host_batch = HostBatch(self.hosts)
+                self.hosts = HostList(self.hosts, self.host_batch)
 
     # -------------------------------------------------------------------------------------
     def _upload_and_run_transient(self, ids, setups):
@@ -150,8 +160,7 @@ class BatchedKuramoto:
             for r, s in enumerate(setups):
                 stim[r] = s.stim; rec[r] = s.rec
         self.engine.set_env_params(ids, w0=w0, stim=stim, rec=rec, y0=y0)
-        self.engine.set_episode(ids, step_idx=0,
-                                episode_len=[self.hosts[i].total_episode_counts for i in ids])
+        self.engine.set_episode(ids, step_idx=0, episode_len=self._episode_counts[ids])
         for i, s in zip(ids, setups):
             self.electrodes[i] = s.electrode
             self.w0_model[i] = s.w0
@@ -163,6 +172,19 @@ class BatchedKuramoto:
     def reset_envs(self, ids):
         """reset() of the listed environments, in the order given (reference env.py:467-614)."""
         ids = list(ids)
+        if self.host_batch is not None:
+            w0, stim, rec, y0, electrodes = self.host_batch.begin_episodes(ids)
+            ids_a = np.asarray(ids, dtype=np.int32)
+            self.engine.set_env_params(ids_a, w0=w0, stim=stim, rec=rec, y0=y0)
+            self.engine.set_episode(ids_a, step_idx=0, episode_len=self._episode_counts[ids_a])
+            for r, i in enumerate(ids):
+                self.electrodes[i] = electrodes[r]
+                self.w0_model[i] = w0[r]
+            self.current_step[ids_a] = 0
+            self.engine.transient(self.t_transient, env_ids=ids_a)
+            self._lfp_cache = None
+            self._mirror = None
+            return
         setups = self._begin_episodes_fast(ids)
         if setups is None:
             setups = [self.hosts[i].begin_episode() for i in ids]

@@ -1,0 +1,247 @@
+"""Batched HOST logic of reset(): what ``host_env.HostEnvState.begin_episode`` does for one environment
+(reference environment/env.py:483-598, :21-57; utils.py:819-823, :902-906), for thousands at once.
+
+* the state of all environments lives in arrays (event counters, electrode / recording contacts, encapsulation
+  coefficient, plasticity walks, natural frequencies);
+* every random number of one batched reset is drawn by ONE native call that consumes numpy's legacy global stream in the
+  reference's order, environment after environment (csrc/host_rng.cu, np_stream.py), so the batch gets exactly the numbers
+  a sequential ``DummyVecEnv`` of reference environments would get and ``np.random`` is left in the same state;
+* the arithmetic on those numbers uses the reference's own expressions on whole arrays (element-wise operations and
+  row-wise ``np.mean`` / ``np.std`` are bit-identical to their per-environment forms; tests/test_host_batch.py).
+
+The per-environment ``HostEnvState`` objects stay the single source of constants and are refreshed from the arrays
+whenever somebody looks at one (``HostList``), so ``hosts[i].elec_coords`` etc. keep working.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from .host_env import cached_electrode, stim_rec_table
+from .np_stream import NumpyGlobalStream
+
+_COMMON = ("num_oscillators", "grid_size", "random_freq_update", "reset_plasticity_episode", "init_state_mean",
+           "init_state_sd", "electrode_amps", "directed_stimulation", "electrode_prc_type", "naive_dbs")
+
+
+class HostList(list):
+    """``hosts[i]`` refreshes HostEnvState i from the batch arrays before handing it out."""
+
+    def __init__(self, hosts, batch):
+        super().__init__(hosts)
+        self._batch = batch
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self[i] for i in range(*k.indices(len(self)))]
+        h = list.__getitem__(self, k)
+        self._batch.sync_to_host(k if k >= 0 else k + len(self), h)
+        return h
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class HostBatch:
+    @staticmethod
+    def supported(hosts):
+        """The batched path covers the shipped configurations: one stimulation and one recording contact, no event
+        logging to disk, quiet, freshly drawn initial phases, and common values for the keys the native draw routine
+        takes as scalars.  Anything else keeps the per-environment path."""
+        if not hosts:
+            return False
+        p0 = hosts[0].params_dict
+        for h in hosts:
+            p = h.params_dict
+            if h.save_init or h.verbose or (p["save_events"] and p["log_path"] is not None):
+                return False
+            if len(h.elec_coords) != 1 or len(h.rec_coords) != 1:
+                return False
+            if p["temporal_drift"] != p0["temporal_drift"]:
+                return False
+            if p["neur_grid"] is not p0["neur_grid"] and not np.array_equal(p["neur_grid"], p0["neur_grid"]):
+                return False
+            for k in _COMMON:
+                if k in ("reset_plasticity_episode", "random_freq_update") and not p0["temporal_drift"]:
+                    continue
+                a, b = p[k], p0[k]
+                if not (a == b if not isinstance(a, (list, np.ndarray)) else np.array_equal(a, b)):
+                    return False
+        return True
+
+    def __init__(self, hosts):
+        self.hosts = hosts
+        p0 = self.p0 = hosts[0].params_dict
+        B, N = len(hosts), int(p0["num_oscillators"])
+        self.B, self.N = B, N
+        self.drift = bool(p0["temporal_drift"])
+        self.stream = NumpyGlobalStream()
+        i32 = lambda f: np.array([f(h) for h in hosts], dtype=np.int32)      # noqa: E731
+        self.reset_count = i32(lambda h: h.reset_count)
+        self.elec = np.array([h.elec_coords[0] for h in hosts], dtype=np.int32)
+        self.rec = np.array([h.rec_coords[0] for h in hosts], dtype=np.int32)
+        self.encaps = np.array([h.encapsulation_coeff for h in hosts], dtype=np.float64)
+        self.spatial_feature = np.array([bool(h.params_dict["spatial_feature"]) for h in hosts])
+        self.spatial_var_freq = i32(lambda h: h.spatial_var_freq)
+        self.spatial_var_episode = i32(lambda h: h.spatial_var_episode)
+        self.w_locus = np.array([h.params_dict["locus_without_w0"] for h in hosts], dtype=np.float64)
+        self.lmask = np.array([h.params_dict["locus_mask"] for h in hosts], dtype=np.float64)
+        self.wl = np.array([h.w0_without_locus for h in hosts], dtype=np.float64)         # current w0_without_locus
+        self.w0 = np.array([h.w0 for h in hosts], dtype=np.float64)
+        self.init_state = np.array([h.init_state for h in hosts], dtype=np.float64)
+        self.freq = np.zeros((B, 3), dtype=np.int32)
+        self.M = 0
+        if self.drift:
+            self.elec_drift_episode = i32(lambda h: h.elec_drift_episode)
+            self.elec_encaps_episode = i32(lambda h: h.elec_encaps_episode)
+            self.plasticity_episode = i32(lambda h: h.plasticity_episode)
+            self.count = i32(lambda h: h.plasticity_process_count)
+            self.freq[:, 0] = [h.params_dict["electrode_drift_freq"] for h in hosts]
+            self.freq[:, 1] = [h.params_dict["encapsulation_drift_freq"] for h in hosts]
+            self.freq[:, 2] = [h.params_dict["plasticity_drift_freq"] for h in hosts]
+            self.encaps_percent = np.array([h.encaps_precent for h in hosts], dtype=np.float64)
+            self.step_scale = np.array([h.plasticity_percent * 0.01 for h in hosts], dtype=np.float64)
+            self.regen_every = int(p0["reset_plasticity_episode"])
+            self.M = 2 * self.regen_every
+            self.wl_orig = np.array([h.w0_without_locus_ for h in hosts], dtype=np.float64)
+            self.walk = np.array([h.w0_process for h in hosts], dtype=np.float64)         # [B, M + 1, N]
+        self.table = stim_rec_table()
+        self._electrodes = [None] * B
+        self.lo, self.hi = 1, min(p0["grid_size"]) - 2
+
+    # ------------------------------------------------------------------------------------------------------
+    def sync_to_host(self, i, h):
+        """Write environment i's mutable fields back into its HostEnvState (attribute surface of env.py:339-386, :483-557)."""
+        h.reset_count = int(self.reset_count[i])
+        h.elec_coords = [self.elec[i].tolist()]
+        h.rec_coords = [self.rec[i].tolist()]
+        h.encapsulation_coeff = float(self.encaps[i])
+        h.spatial_var_episode = int(self.spatial_var_episode[i])
+        h.w0_without_locus = self.wl[i]
+        h.w0 = self.w0[i]
+        h.init_state = self.init_state[i]
+        if self.drift:
+            h.elec_drift_episode = int(self.elec_drift_episode[i])
+            h.elec_encaps_episode = int(self.elec_encaps_episode[i])
+            h.plasticity_episode = int(self.plasticity_episode[i])
+            h.plasticity_process_count = int(self.count[i])
+            h.w0_process = self.walk[i]
+
+    # ------------------------------------------------------------------------------------------------------
+    def begin_episodes(self, ids):
+        """env.py:467-598 for the listed environments, in that order.  Returns (w0, stim, rec, y0, electrodes): arrays
+        [n, N] float64 and the ElectrodeModel of every environment."""
+        ids = np.asarray(ids, dtype=np.int64)
+        n, N = ids.size, self.N
+        rc = self.reset_count[ids] + 1
+        self.reset_count[ids] = rc
+        flags = np.zeros(n, dtype=np.uint8)
+        if self.drift:
+            f_el = self.elec_drift_episode[ids] == rc
+            f_en = self.elec_encaps_episode[ids] == rc
+            f_pl = self.plasticity_episode[ids] == rc
+            f_rg = (rc % self.regen_every) == 0
+            flags |= (f_el * _capi.RESET_ELECTRODE_MOVE + f_en * _capi.RESET_ENCAPSULATION + f_pl * _capi.RESET_PLASTICITY +
+                      f_rg * _capi.RESET_WALK_REGEN).astype(np.uint8)
+        f_sp = self.spatial_feature[ids] & (self.spatial_var_episode[ids] == rc) & (rc > 2)
+        flags |= (f_sp * _capi.RESET_SPATIAL).astype(np.uint8)
+
+        # natural frequencies of this episode (known before any draw: the plasticity event takes an entry of the walk
+        # generated EARLIER, a walk regeneration goes back to the original vector; env.py:519-541, :566)
+        wl = self.wl[ids]
+        if self.drift:
+            if f_pl.any():
+                who = ids[f_pl]
+                wl[f_pl] = self.walk[who, self.count[who]]
+                self.count[who] += 1
+            if f_rg.any():
+                self.count[ids[f_rg]] = 0
+                wl[f_rg] = self.wl_orig[ids[f_rg]]
+            self.wl[ids] = wl
+        w_locus, lmask = self.w_locus[ids], self.lmask[ids]
+        w0 = wl * (lmask * -1 + 1) + w_locus * lmask                      # utils.py:902-906 apply_locus_mask
+        bad = w0 <= 0.0
+        n_fix = bad.sum(axis=1).astype(np.int32)
+
+        # ---- every draw of this reset, in the reference's order, from numpy's global stream ----
+        n_regen = int(f_rg.sum()) if self.drift else 0
+        elec = np.ascontiguousarray(self.elec[ids])
+        inc = np.zeros((n, 3), dtype=np.int32)
+        pick = np.empty(n, dtype=np.int32)
+        fix_noise = np.empty(max(int(n_fix.sum()), 1))
+        walk_noise = np.empty((max(n_regen, 1), max(self.M, 1), N)) if n_regen else None
+        y0 = np.empty((n, N))
+        cap_rows, cap_noise = 64, 512
+        refix_env = np.zeros((cap_rows, 2), dtype=np.int32)
+        refix_noise = np.empty(cap_noise)
+        n_refix = C.c_int32(0)
+        plan = _capi.DbsGymResetPlan()
+        plan.struct_bytes = C.sizeof(_capi.DbsGymResetPlan)
+        plan.n_envs, plan.n_osc, plan.walk_len = n, N, self.M
+        plan.coord_lo, plan.coord_hi, plan.table_len = self.lo, self.hi, len(self.table)
+        plan.random_freq_update = 1 if (self.drift and self.p0["random_freq_update"]) else 0
+        plan.refix_cap_rows, plan.refix_cap_noise = cap_rows, cap_noise
+        plan.init_mean, plan.init_sd = float(self.p0["init_state_mean"]), float(self.p0["init_state_sd"])
+        st = self.stream.pull()
+        freq = np.ascontiguousarray(self.freq[ids])
+        rcode = st.lib.dbsgym_np_reset_draws(
+            C.byref(st.st), C.byref(plan), _capi.ptr(flags), _capi.ptr(freq), _capi.ptr(elec), _capi.ptr(inc),
+            _capi.ptr(pick), _capi.ptr(n_fix), _capi.ptr(fix_noise), _capi.ptr(walk_noise) if n_regen else None,
+            _capi.ptr(y0), _capi.ptr(refix_env), _capi.ptr(refix_noise), C.byref(n_refix))
+        if rcode:
+            raise _capi.DbsGymError(f"dbsgym_np_reset_draws failed ({rcode})")
+        st.push()
+
+        # ---- apply them ----
+        if self.drift:
+            self.elec_drift_episode[ids] += inc[:, 0]
+            self.elec_encaps_episode[ids] += inc[:, 1]
+            self.plasticity_episode[ids] += inc[:, 2]
+            self.elec[ids] = elec
+            if f_en.any():
+                self.encaps[ids[f_en]] += self.encaps_percent[ids[f_en]]          # added as an absolute amount
+            if n_regen:
+                who = ids[f_rg]
+                base = self.wl_orig[who]
+                sigma = self.step_scale[who] * np.std(base, axis=1, ddof=1)     # env.py:21-57 generate_perturbations
+                walk = np.empty((who.size, self.M + 1, N))
+                walk[:, 0] = base
+                for m in range(self.M):
+                    walk[:, m + 1] = walk[:, m] + sigma[:, None] * walk_noise[:, m]
+                self.walk[who] = walk
+        if f_sp.any():                                                    # env.py:544-552
+            for r in np.flatnonzero(f_sp):
+                i, row = int(ids[r]), self.table[int(pick[r])]
+                self.elec[i], self.rec[i] = row[0], row[1]
+                self.spatial_var_episode[i] += self.spatial_var_freq[i]
+                self.hosts[i].spatial_events.append([int(rc[r]), row])
+        if n_fix.any():                                                   # utils.py:819-823 on w0
+            at = 0
+            for r in np.flatnonzero(n_fix):
+                k = int(n_fix[r])
+                row = w0[r]
+                row[bad[r]] = np.abs(fix_noise[at:at + k] * 0.05) + np.mean(row)
+                at += k
+        at = 0
+        for r, k in refix_env[:n_refix.value]:                            # the same on the initial phases (env.py:598)
+            row = y0[r]
+            row[row <= 0.0] = np.abs(refix_noise[at:at + k] * 0.05) + np.mean(row)
+            at += k
+        self.w0[ids] = w0
+        self.init_state[ids] = y0
+
+        # ---- electrodes: one model per distinct (contacts, conduct_modifier), shared by the environments that have it ----
+        keys = np.column_stack([self.elec[ids], self.rec[ids], self.encaps[ids]])
+        uniq, inv = np.unique(keys, axis=0, return_inverse=True)
+        inv = np.asarray(inv).reshape(-1)
+        models = [cached_electrode(self.p0, self._cm(k[6]), [[int(v) for v in k[0:3]]], [[int(v) for v in k[3:6]]], 0) for k in uniq]
+        stim = np.stack([m.stim_vector() for m in models])[inv]
+        rec = np.stack([m.rec_vector() for m in models])[inv]
+        electrodes = [models[j] for j in inv]
+        return w0, stim, rec, y0, electrodes
+
+    def _cm(self, v):
+        """conduct_modifier as the per-environment path passes it (a Python float)."""
+        return float(v)

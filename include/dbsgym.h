@@ -273,6 +273,52 @@ typedef struct DbsGymEvalSpec {
  * smoothing and the band sum of calc_psd_for_simple_eval (evaluate_HF_DBS.py:130-134). */
 int dbsgym_eval_bbpow(DbsGymHandle* h, const DbsGymEvalSpec* spec, const double* weights, double* bbpow);
 
+/* ---- host side of a batched reset: numpy's legacy global random stream, replayed natively ---------------------------
+ * The reference draws everything reset() needs from the process-global np.random (env.py:291, :483-598; SURVEY.md
+ * Appendix C).  To hand a batch of environments the numbers a sequential DummyVecEnv of reference environments would get,
+ * the caller passes np.random.get_state() in, lets dbsgym_np_reset_draws consume the stream for all environments in
+ * index order, and writes the state back with np.random.set_state().  No GPU involved. */
+typedef struct DbsGymNpState {
+    uint32_t key[624];          /* MT19937 state words                                                         */
+    int32_t  pos;               /* 0..624                                                                      */
+    int32_t  has_gauss;         /* the polar method's cached second deviate                                    */
+    double   gauss;
+} DbsGymNpState;
+/* n draws of np.random.normal(loc, scale) (randn: loc 0, scale 1) */
+int dbsgym_np_gauss(DbsGymNpState* st, int64_t n, double loc, double scale, double* out);
+/* n draws of np.random.choice(pop_size) (== RandomState.randint(0, pop_size)) */
+int dbsgym_np_choice(DbsGymNpState* st, int64_t n, uint32_t pop_size, int32_t* out);
+
+enum { DBSGYM_RESET_ELECTRODE_MOVE = 1, DBSGYM_RESET_ENCAPSULATION = 2, DBSGYM_RESET_PLASTICITY = 4,
+       DBSGYM_RESET_WALK_REGEN = 8, DBSGYM_RESET_SPATIAL = 16 };
+typedef struct DbsGymResetPlan {
+    uint32_t struct_bytes;
+    int32_t  n_envs, n_osc;
+    int32_t  walk_len;              /* M = 2 * reset_plasticity_episode vectors per regenerated plasticity walk (env.py:539) */
+    int32_t  coord_lo, coord_hi;    /* an electrode move is redrawn until 1 <= coordinate <= min(grid_size) - 2 (env.py:487-496) */
+    int32_t  table_len;             /* rows of the stim / rec / locus table a spatial re-draw picks from (env.py:546) */
+    int32_t  random_freq_update;    /* params_dict['random_freq_update'] (env.py:457-464)                      */
+    int32_t  refix_cap_rows, refix_cap_noise;   /* capacity of refix_env (pairs) / refix_noise                 */
+    double   init_mean, init_sd;    /* env.py:594-595                                                          */
+} DbsGymResetPlan;
+/* The draws of ONE reset of n_envs environments, in index order, exactly as env.py:483-598 makes them:
+ *   flags[e]        DBSGYM_RESET_* events due at this reset
+ *   freq[e][3]      electrode_drift_freq, encapsulation_drift_freq, plasticity_drift_freq
+ *   elec_coords[e][3]  first stimulation contact, moved in place when DBSGYM_RESET_ELECTRODE_MOVE is set
+ *   next_inc[e][3]  out: what to add to elec_drift_episode / elec_encaps_episode / plasticity_episode
+ *   spatial_pick[e] out: row of the table (-1 = no re-draw)
+ *   n_fix[e]        number of non-positive natural frequencies remove_negative_w0 replaces (utils.py:819-823);
+ *                   fix_noise receives that many standard normals per environment, concatenated
+ *   walk_noise      [number of environments with DBSGYM_RESET_WALK_REGEN][walk_len][n_osc] standard normals
+ *   init_state      [n_envs][n_osc] = init_mean + init_sd * gauss
+ *   refix_env / refix_noise / n_refix   environments whose init_state came out non-positive somewhere (pairs env, count)
+ *                   and the standard normals remove_negative_w0(init_state) draws for them (env.py:598)
+ * Returns DBSGYM_ESTATE when the refix buffers are too small (state untouched: copy it before the call to retry). */
+int dbsgym_np_reset_draws(DbsGymNpState* st, const DbsGymResetPlan* plan, const uint8_t* flags, const int32_t* freq,
+                          int32_t* elec_coords, int32_t* next_inc, int32_t* spatial_pick, const int32_t* n_fix,
+                          double* fix_noise, double* walk_noise, double* init_state, int32_t* refix_env,
+                          double* refix_noise, int32_t* n_refix);
+
 /* FP32-FMA throughput micro-benchmark used for the roofline denominator: runs a dependent-
  * chain FFMA kernel on `device` for about `ms_target` ms; returns TFLOP/s in *tflops. */
 int dbsgym_measure_fp32_peak(int32_t device, double ms_target, double* tflops);

@@ -1,0 +1,119 @@
+"""host_batch.HostBatch (all environments' reset bookkeeping in arrays, every draw of a reset made by one native call on
+numpy's global stream) against host_env.HostEnvState.begin_episode run environment after environment -- which
+tests/test_host_logic.py pins to the reference's own env.py.  Everything must be bit-identical, the state np.random is
+left in included.  CPU only."""
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import make_params
+from dbsgym_b200 import _capi
+from dbsgym_b200.host_batch import HostBatch, HostList
+from dbsgym_b200.host_env import HostEnvState
+
+
+def _dicts(cfg, B, **over):
+    out = []
+    for e in range(B):
+        d = make_params(cfg, 40 + e, rand_seed=90 + e, **over)
+        out.append(d)
+    return out
+
+
+def _build(dicts, compat):
+    hosts, first = [], []
+    for d in dicts:
+        h = HostEnvState(d, compat_env2=compat)
+        hosts.append(h)
+        first.append(h.begin_episode())
+    return hosts, first
+
+
+def _state():
+    s = np.random.get_state()
+    return s[1].copy(), s[2], s[3], s[4]
+
+
+@pytest.mark.parametrize("cfg,over,compat,rounds", [
+    ("env2", dict(total_episode_len=9.0), True, 32),
+    ("env2", dict(total_episode_len=9.0, random_freq_update=False, electrode_drift_freq=2, encapsulation_drift_freq=3,
+                  reset_plasticity_episode=4, spatial_var_freq=3), True, 20),
+    ("env1", dict(spatial_var_freq=3), False, 14),
+])
+def test_batched_reset_equals_sequential_resets(cfg, over, compat, rounds):
+    _capi.build()
+    B = 7
+    dicts = _dicts(cfg, B, **over)
+    # a natural-frequency vector with non-positive entries in one environment: remove_negative_w0 must draw for it
+    dicts[3]["w0_without_locus"] = dicts[3]["w0_without_locus"].copy()
+    dicts[3]["w0_without_locus"][[5, 77, 300]] = [-0.01, 0.0, -0.2]
+    a, _ = _build(copy.deepcopy(dicts), compat)
+    end_a = _state()
+    b, _ = _build(copy.deepcopy(dicts), compat)
+    assert np.array_equal(_state()[0], end_a[0])
+    assert HostBatch.supported(b)
+    hb = HostBatch(b)
+    bl = HostList(b, hb)
+    events = 0
+    for r in range(rounds):
+        ids = list(range(B)) if r % 5 != 3 else [4, 1, 6]              # sometimes a subset, in a non-sorted order
+        st = np.random.get_state()
+        setups = [a[i].begin_episode() for i in ids]
+        after_a = _state()
+        np.random.set_state(st)
+        w0, stim, rec, y0, electrodes = hb.begin_episodes(ids)
+        after_b = _state()
+        assert np.array_equal(after_a[0], after_b[0]) and after_a[1:] == after_b[1:], f"stream position differs after round {r}"
+        for k, (i, s) in enumerate(zip(ids, setups)):
+            assert np.array_equal(s.w0, w0[k]) and np.array_equal(s.y0, y0[k]), (r, i)
+            assert np.array_equal(s.stim, stim[k]) and np.array_equal(s.rec, rec[k]), (r, i)
+            assert electrodes[k].elec_idxs == s.electrode.elec_idxs and electrodes[k].rec_idxs == s.electrode.rec_idxs
+            ha, hbv = a[i], bl[i]
+            assert ha.reset_count == hbv.reset_count
+            assert ha.elec_coords == hbv.elec_coords and ha.rec_coords == hbv.rec_coords, (r, i, ha.elec_coords, hbv.elec_coords)
+            assert ha.encapsulation_coeff == hbv.encapsulation_coeff
+            assert ha.spatial_var_episode == hbv.spatial_var_episode and ha.spatial_events == hbv.spatial_events
+            assert np.array_equal(ha.w0, hbv.w0) and np.array_equal(ha.init_state, hbv.init_state)
+            assert np.array_equal(ha.w0_without_locus, hbv.w0_without_locus)
+            if ha.params_dict["temporal_drift"]:
+                assert (ha.elec_drift_episode, ha.elec_encaps_episode, ha.plasticity_episode, ha.plasticity_process_count) == \
+                       (hbv.elec_drift_episode, hbv.elec_encaps_episode, hbv.plasticity_episode, hbv.plasticity_process_count)
+                assert np.array_equal(ha.w0_process, hbv.w0_process)
+        events += sum(len(h.spatial_events) for h in a)
+    if cfg == "env2":
+        assert len({tuple(h.elec_coords[0]) for h in a}) > 1 and max(h.encapsulation_coeff for h in a) > 2.0
+    assert events > 0
+
+
+def test_non_positive_initial_phase_is_fixed_like_remove_negative_w0():
+    """env.py:598: remove_negative_w0(init_state) -- a non-positive initial phase is a 5-sigma event at the shipped
+    N(pi, 0.6), so it is provoked here with a wide distribution; the batch must draw the replacement noise right after that
+    environment's phases, like the sequential path."""
+    _capi.build()
+    B = 5
+    dicts = _dicts("env2", B, total_episode_len=9.0, init_state_sd=2.5)
+    a, _ = _build(copy.deepcopy(dicts), True)
+    b, _ = _build(copy.deepcopy(dicts), True)
+    hb = HostBatch(b)
+    for r in range(3):
+        st = np.random.get_state()
+        setups = [h.begin_episode() for h in a]
+        after_a = _state()
+        np.random.set_state(st)
+        w0, stim, rec, y0, _ = hb.begin_episodes(range(B))
+        after_b = _state()
+        assert np.array_equal(after_a[0], after_b[0]) and after_a[1:] == after_b[1:]
+        assert all(np.array_equal(s.y0, y0[k]) for k, s in enumerate(setups))
+        assert min(s.y0.min() for s in setups) > 0
+
+
+def test_unsupported_configurations_keep_the_per_environment_path():
+    d = _dicts("env2", 2, total_episode_len=9.0)
+    hosts, _ = _build(d, True)
+    assert HostBatch.supported(hosts)
+    hosts[1].save_init = True
+    assert not HostBatch.supported(hosts)
+    hosts[1].save_init = False
+    hosts[0].elec_coords = [[4, 3, 4], [2, 2, 2]]
+    assert not HostBatch.supported(hosts)
