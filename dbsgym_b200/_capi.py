@@ -75,7 +75,7 @@ class DbsGymResetPlan(C.Structure):
     _fields_ = [("struct_bytes", C.c_uint32), ("n_envs", C.c_int32), ("n_osc", C.c_int32), ("walk_len", C.c_int32),
                 ("coord_lo", C.c_int32), ("coord_hi", C.c_int32), ("table_len", C.c_int32),
                 ("random_freq_update", C.c_int32), ("refix_cap_rows", C.c_int32), ("refix_cap_noise", C.c_int32),
-                ("init_mean", C.c_double), ("init_sd", C.c_double)]
+                ("reserved", C.c_int32 * 2), ("init_mean", C.c_double), ("init_sd", C.c_double)]
 
 
 RESET_ELECTRODE_MOVE, RESET_ENCAPSULATION, RESET_PLASTICITY, RESET_WALK_REGEN, RESET_SPATIAL = 1, 2, 4, 8, 16

@@ -46,7 +46,7 @@ class SpatialKuramoto(GymEnv):
             compat_env2 = bool(params_dict.get("compat_env2", os.environ.get("DBSGYM_COMPAT_ENV2", "") == "1"))
         self._core = BatchedKuramoto([params_dict], precision=precision or _default_precision(params_dict),
                                      device=device, compat_env2=compat_env2, save_init=save_init)
-        host = self._host = self._core.hosts[0]
+        host = self._core.hosts[0]
         self.verbose = host.verbose
         self.step_len = host.step_len
         self.observe_wind_len = host.observe_wind_len
@@ -75,6 +75,10 @@ class SpatialKuramoto(GymEnv):
         self.theta_records = None
 
     @property
+    def _host(self):
+        return self._core.hosts[0]       # (a HostList refreshes the object from the batched reset state on access)
+
+    @property
     def reset_count(self):
         return self._host.reset_count
 
@@ -88,7 +92,8 @@ class SpatialKuramoto(GymEnv):
         # HostEnvState; only reached when normal lookup fails
         if name.startswith("__") or name in ("_host", "_core"):
             raise AttributeError(name)
-        host = self.__dict__.get("_host")
+        core = self.__dict__.get("_core")
+        host = core.hosts[0] if core is not None else None
         if host is not None and hasattr(host, name):
             return getattr(host, name)
         raise AttributeError(f"'SpatialKuramoto' object has no attribute '{name}'")

@@ -86,8 +86,11 @@ class HostBatch:
         self.spatial_feature = np.array([bool(h.params_dict["spatial_feature"]) for h in hosts])
         self.spatial_var_freq = i32(lambda h: h.spatial_var_freq)
         self.spatial_var_episode = i32(lambda h: h.spatial_var_episode)
-        self.w_locus = np.array([h.params_dict["locus_without_w0"] for h in hosts], dtype=np.float64)
-        self.lmask = np.array([h.params_dict["locus_mask"] for h in hosts], dtype=np.float64)
+        w_locus = np.array([h.params_dict["locus_without_w0"] for h in hosts], dtype=np.float64)
+        lmask = np.array([h.params_dict["locus_mask"] for h in hosts], dtype=np.float64)
+        # the two constant factors of apply_locus_mask (utils.py:902-906): w0 * (lmask * -1 + 1) + w_locus * lmask
+        self.keep = lmask * -1 + 1
+        self.locus_term = w_locus * lmask
         self.wl = np.array([h.w0_without_locus for h in hosts], dtype=np.float64)         # current w0_without_locus
         self.w0 = np.array([h.w0 for h in hosts], dtype=np.float64)
         self.init_state = np.array([h.init_state for h in hosts], dtype=np.float64)
@@ -135,6 +138,8 @@ class HostBatch:
         [n, N] float64 and the ElectrodeModel of every environment."""
         ids = np.asarray(ids, dtype=np.int64)
         n, N = ids.size, self.N
+        everyone = n == self.B and np.array_equal(ids, np.arange(self.B))
+        sel = slice(None) if everyone else ids                     # (views instead of gathered copies for a full reset)
         rc = self.reset_count[ids] + 1
         self.reset_count[ids] = rc
         flags = np.zeros(n, dtype=np.uint8)
@@ -150,7 +155,7 @@ class HostBatch:
 
         # natural frequencies of this episode (known before any draw: the plasticity event takes an entry of the walk
         # generated EARLIER, a walk regeneration goes back to the original vector; env.py:519-541, :566)
-        wl = self.wl[ids]
+        wl = self.wl[sel]
         if self.drift:
             if f_pl.any():
                 who = ids[f_pl]
@@ -159,11 +164,12 @@ class HostBatch:
             if f_rg.any():
                 self.count[ids[f_rg]] = 0
                 wl[f_rg] = self.wl_orig[ids[f_rg]]
-            self.wl[ids] = wl
-        w_locus, lmask = self.w_locus[ids], self.lmask[ids]
-        w0 = wl * (lmask * -1 + 1) + w_locus * lmask                      # utils.py:902-906 apply_locus_mask
+            if not everyone:
+                self.wl[ids] = wl
+        w0 = wl * self.keep[sel]                                          # utils.py:902-906 apply_locus_mask
+        w0 += self.locus_term[sel]
         bad = w0 <= 0.0
-        n_fix = bad.sum(axis=1).astype(np.int32)
+        n_fix = np.count_nonzero(bad, axis=1).astype(np.int32)
 
         # ---- every draw of this reset, in the reference's order, from numpy's global stream ----
         n_regen = int(f_rg.sum()) if self.drift else 0
@@ -218,19 +224,21 @@ class HostBatch:
                 self.spatial_var_episode[i] += self.spatial_var_freq[i]
                 self.hosts[i].spatial_events.append([int(rc[r]), row])
         if n_fix.any():                                                   # utils.py:819-823 on w0
-            at = 0
-            for r in np.flatnonzero(n_fix):
-                k = int(n_fix[r])
-                row = w0[r]
-                row[bad[r]] = np.abs(fix_noise[at:at + k] * 0.05) + np.mean(row)
-                at += k
+            rows = np.flatnonzero(n_fix)
+            means = np.zeros(n)
+            means[rows] = np.mean(w0[rows], axis=1)                       # (row-wise mean == np.mean of the 1-d vector, bit for bit)
+            r_idx, c_idx = np.nonzero(bad)                                # row-major: the order the noise was drawn in
+            w0[r_idx, c_idx] = np.abs(fix_noise[:r_idx.size] * 0.05) + means[r_idx]
         at = 0
         for r, k in refix_env[:n_refix.value]:                            # the same on the initial phases (env.py:598)
             row = y0[r]
             row[row <= 0.0] = np.abs(refix_noise[at:at + k] * 0.05) + np.mean(row)
             at += k
-        self.w0[ids] = w0
-        self.init_state[ids] = y0
+        if everyone:
+            self.w0, self.init_state = w0, y0
+        else:
+            self.w0[ids] = w0
+            self.init_state[ids] = y0
 
         # ---- electrodes: one model per distinct (contacts, conduct_modifier), shared by the environments that have it ----
         keys = np.column_stack([self.elec[ids], self.rec[ids], self.encaps[ids]])
@@ -240,6 +248,9 @@ class HostBatch:
         stim = np.stack([m.stim_vector() for m in models])[inv]
         rec = np.stack([m.rec_vector() for m in models])[inv]
         electrodes = [models[j] for j in inv]
+        if self.B <= 256:            # small batches: keep the HostEnvState objects current for callers that hold on to one
+            for i in ids:
+                self.sync_to_host(int(i), self.hosts[int(i)])
         return w0, stim, rec, y0, electrodes
 
     def _cm(self, v):

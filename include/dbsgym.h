@@ -299,6 +299,7 @@ typedef struct DbsGymResetPlan {
     int32_t  table_len;             /* rows of the stim / rec / locus table a spatial re-draw picks from (env.py:546) */
     int32_t  random_freq_update;    /* params_dict['random_freq_update'] (env.py:457-464)                      */
     int32_t  refix_cap_rows, refix_cap_noise;   /* capacity of refix_env (pairs) / refix_noise                 */
+    int32_t  reserved[2];
     double   init_mean, init_sd;    /* env.py:594-595                                                          */
 } DbsGymResetPlan;
 /* The draws of ONE reset of n_envs environments, in index order, exactly as env.py:483-598 makes them:
