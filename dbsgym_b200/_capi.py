@@ -17,7 +17,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("DBSGYM_LIB") or os.path.join(CSRC, "libdbsgym.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "dbsgym.h")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 F32, F64 = 0, 1
 COUPLING_GRID, COUPLING_DENSE = 0, 1
 REWARD_BBPOW, REWARD_TEMP_CONST, REWARD_BBPOW_THRESH = 0, 1, 2
@@ -49,7 +49,7 @@ class DbsGymConfig(C.Structure):
 
 
 # DbsGymConfig.debug_flags
-DBG_NO_GEO1, DBG_NO_SYM, DBG_NO_FSAL_REUSE, DBG_NO_FUSED_OBS, DBG_NO_FAST_OBS = 1, 2, 4, 8, 16
+DBG_NO_GEO1, DBG_NO_SYM, DBG_NO_FSAL_REUSE, DBG_NO_FUSED_OBS, DBG_NO_FAST_OBS, DBG_NO_WARP_KERNEL = 1, 2, 4, 8, 16, 32
 
 
 class DbsGymRewardSpec(C.Structure):
@@ -85,9 +85,9 @@ class DbsGymError(RuntimeError):
     pass
 
 
-UNITS = ("api", "host_rng", "step_f32_grid", "step_f32_sym", "step_f32_lines", "step_f32_dense", "step_f32_mw", "step_f32_spectral",
+UNITS = ("api", "host_rng", "step_f32_grid", "step_f32_sym", "step_f32_lines", "step_f32_dense", "step_f32_mw", "step_f32_spectral", "step_f32_warp",
          "step_f32_cluster", "step_f64_grid", "step_f64_sym", "step_f64_dense")
-HEADERS = ("step_kernel.cuh", "step_launch.h", "obs_kernel.cuh", "eval_kernel.cuh")
+HEADERS = ("step_kernel.cuh", "warp_kernel.cuh", "step_launch.h", "obs_kernel.cuh", "eval_kernel.cuh")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
@@ -165,7 +165,7 @@ def load():
         "dbsgym_last_error": (C.c_char_p, [vp]),
         "dbsgym_set_coupling_grid": (C.c_int, [vp, vp]),
         "dbsgym_set_coupling_dense": (C.c_int, [vp, vp]),
-        "dbsgym_set_coupling_spectral": (C.c_int, [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
+        "dbsgym_set_coupling_spectral": (C.c_int, [vp, vp, C.c_int32, vp, vp]),
         "dbsgym_set_env_params": (C.c_int, [vp, vp, C.c_int32, vp, vp, vp, vp]),
         "dbsgym_set_recording": (C.c_int, [vp, C.c_int32]),
         "dbsgym_set_schedule": (C.c_int, [vp, C.c_int32, vp, vp, vp, C.c_int32, vp, C.c_int32]),

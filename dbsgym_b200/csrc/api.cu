@@ -1,6 +1,7 @@
 // C-ABI of the DBS-Gym step engine (see include/dbsgym.h for the contract).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -97,6 +98,9 @@ struct DbsGymHandle {
     // spectral form of the coupling operator (dbsgym_set_coupling_spectral): eigenvector entries per worker thread and
     // eigenvalues x K / (8 N) per reduction row, and which compiled (RE, RO) pair serves them (0 = off)
     float* spec_v = nullptr; float* spec_lam = nullptr; int spec_re = 0, spec_ro = 0;
+    // the same operator laid out for the one-warp-per-environment kernel (warp_kernel.cuh): [32 lanes][modes] float2 and
+    // [modes] eigenvalues, for the compiled rank list warp_set (-1: the ranks fit none, or DBSGYM_DBG_NO_WARP_KERNEL)
+    float* wspec_v = nullptr; float* wspec_lam = nullptr; int warp_set = -1; bool no_warp = false;
     unsigned long long n_launches = 0;   // kernels launched by this handle (dbsgym_launch_count)
     // ordering between the private stream and caller streams (dbsgym_step / dbsgym_transient on a user stream)
     cudaEvent_t ev_own = nullptr, ev_user = nullptr; bool user_pending = false;
@@ -315,7 +319,8 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
     p.nsamp_out = nullptr; p.head_out = nullptr;
     p.trace = nullptr; p.trace_len = nullptr; p.trace_cap = 0;
     p.fsal_on = h->fsal_on ? 1 : 0; p.k_fsal = h->k_fsal; p.fsal_valid = h->fsal_valid;
-    p.spec_v = h->spec_v; p.spec_lam = h->spec_lam;
+    const bool warp = h->spec_re > 0 && h->warp_set >= 0;
+    p.spec_v = warp ? h->wspec_v : h->spec_v; p.spec_lam = warp ? h->wspec_lam : h->spec_lam;
     p.power_scale = h->rspec.power_scale; p.action_cost = h->rspec.action_cost;
     p.threshold = h->rspec.threshold; p.threshold_penalty = h->rspec.threshold_penalty;
 }
@@ -353,6 +358,7 @@ cudaError_t launch_step(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
     }
     if (dense) return launch_f32_dense(t, smem, p, s);
     if (!h->grid_sym) return launch_f32_grid(t, smem, p, s);
+    if (h->spec_re > 0 && h->warp_set >= 0) return launch_f32_warp(h->warp_set, h->num_sms, p, s);
     if (h->spec_re > 0) return launch_f32_spectral(h->spec_ro, h->num_sms, p, s);
     const int geo = sym_geo(h, p);
     if (geo == 1) {
@@ -521,7 +527,7 @@ int dbsgym_step_variant(const DbsGymHandle* h, int32_t n_envs) {
     if (h->cfg.coupling == DBSGYM_COUPLING_DENSE) return 1;
     if (!h->grid_sym) return 0;
     if (h->f64) return 2;
-    if (h->spec_re > 0) return 9;
+    if (h->spec_re > 0) return h->warp_set >= 0 ? 10 : 9;
     if (h->cfg.grid[1] == 2 * kRows) return 7;
     if (h->cfg.grid[1] == 4 * kRows) return 8;
     const bool geo1 = h->nthreads == 64 && h->cfg.grid[2] == 8 && h->cfg.grid[0] == 8 && !h->no_geo1;
@@ -634,6 +640,7 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
     h->no_geo1 = (cfg->debug_flags & DBSGYM_DBG_NO_GEO1) != 0;
     h->no_fast_obs = (cfg->debug_flags & DBSGYM_DBG_NO_FAST_OBS) != 0;
     h->no_fused_obs = (cfg->debug_flags & DBSGYM_DBG_NO_FUSED_OBS) != 0;
+    h->no_warp = (cfg->debug_flags & DBSGYM_DBG_NO_WARP_KERNEL) != 0;
     cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, cfg->device);
     const size_t BN = (size_t)h->B * Np;
     bool ok = true;
@@ -689,7 +696,7 @@ void dbsgym_destroy(DbsGymHandle* h) {
                     h->step_idx, h->episode_len, h->lfp_true, h->lfp_rec, h->u, h->reward, h->done, h->sched_nI,
                     h->sched_nII, h->sched_offI, h->sched_offII, h->ts_dev, h->ids_dev, h->lin_g, h->tw_seed,
                     h->tw_inner, h->spec, h->tw_full, h->k_fsal, h->fsal_valid, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples,
-                    h->cl_operand, h->cl_scratch, h->mpos, h->spec_v, h->spec_lam};
+                    h->cl_operand, h->cl_scratch, h->mpos, h->spec_v, h->spec_lam, h->wspec_v, h->wspec_lam};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->pin_ints) cudaFreeHost(h->pin_ints);
@@ -729,13 +736,13 @@ int dbsgym_set_coupling_grid(DbsGymHandle* h, const double* table) {
     return DBSGYM_OK;
 }
 
-int dbsgym_set_coupling_spectral(DbsGymHandle* h, int32_t r_even, int32_t r_odd, int32_t r_max, const double* vecs,
-                                 const double* vals) {
+int dbsgym_set_coupling_spectral(DbsGymHandle* h, const int32_t* ranks8, int32_t r_max, const double* vecs, const double* vals) {
     if (!h) return DBSGYM_EINVAL;
     CU(h, cudaSetDevice(h->cfg.device));
     CU(h, cudaDeviceSynchronize());
-    if (r_even <= 0 && r_odd <= 0) {                  // back to the exact sector-block contraction
+    if (!ranks8) {                                    // back to the exact sector-block contraction
         h->spec_re = h->spec_ro = 0;
+        h->warp_set = -1;
         if (h->fsal_valid) CU(h, cudaMemset(h->fsal_valid, 0, (size_t)h->B * 4));
         return DBSGYM_OK;
     }
@@ -743,11 +750,16 @@ int dbsgym_set_coupling_spectral(DbsGymHandle* h, int32_t r_even, int32_t r_odd,
     if (h->cfg.coupling != DBSGYM_COUPLING_GRID || h->f64 || !h->grid_sym || h->cluster > 1 || h->nthreads != 64 ||
         h->cfg.grid[0] != 8 || h->cfg.grid[1] != 8 || h->cfg.grid[2] != 8)
         return fail(h, DBSGYM_ESTATE, "the spectral contraction serves fp32 GRID handles on the 8 x 8 x 8 grid");
-    if (r_even < 1 || r_odd < 1 || r_even > 9 || r_odd > 9 || r_max < r_even || r_max < r_odd)
-        return fail(h, DBSGYM_EINVAL, "spectral ranks (%d even, %d odd) outside the compiled range 1..9", r_even, r_odd);
+    int r_even = 1, r_odd = 1;
+    for (int s8 = 0; s8 < 8; ++s8) {
+        if (ranks8[s8] < 0 || ranks8[s8] > 9 || ranks8[s8] > r_max)
+            return fail(h, DBSGYM_EINVAL, "spectral rank %d of sector %d outside 0..min(9, r_max)", ranks8[s8], s8);
+        if (s8 < 4) r_even = std::max(r_even, (int)ranks8[s8]); else r_odd = std::max(r_odd, (int)ranks8[s8]);
+    }
+    const double scale = h->cfg.K / (8.0 * (double)h->N);
+    // ---- tables of the 64-thread worker kernel (step_kernel<CPL_SPECTRAL>): ranks padded to (9, 4) or (9, 9) ----
     const int RE = 9, RO = r_odd <= 4 ? 4 : 9, R = RE + RO;
     std::vector<float> v((size_t)kMwThreads * 4 * R, 0.f), lam((size_t)4 * R, 0.f);
-    const double scale = h->cfg.K / (8.0 * (double)h->N);
     for (int t = 0; t < kMwThreads; ++t) {
         int zq, xq, sec;
         mw_decode(t, zq, xq, sec);
@@ -755,23 +767,47 @@ int dbsgym_set_coupling_spectral(DbsGymHandle* h, int32_t r_even, int32_t r_odd,
         for (int j = 0; j < 4; ++j)
             for (int m = 0; m < R; ++m) {
                 const int s8 = m < RE ? sec : 4 + sec, mm = m < RE ? m : m - RE;
-                const int rs = m < RE ? r_even : r_odd;
-                if (mm < rs) v[((size_t)t * 4 + j) * R + m] = (float)vecs[((size_t)s8 * 64 + q * 4 + j) * r_max + mm];
+                if (mm < ranks8[s8]) v[((size_t)t * 4 + j) * R + m] = (float)vecs[((size_t)s8 * 64 + q * 4 + j) * r_max + mm];
             }
     }
     for (int sg = 0; sg < 4; ++sg)
         for (int m = 0; m < R; ++m) {
             const int s8 = m < RE ? sg : 4 + sg, mm = m < RE ? m : m - RE;
-            if (mm < (m < RE ? r_even : r_odd)) lam[(size_t)sg * R + m] = (float)(vals[(size_t)s8 * r_max + mm] * scale);
+            if (mm < ranks8[s8]) lam[(size_t)sg * R + m] = (float)(vals[(size_t)s8 * r_max + mm] * scale);
         }
-    if (h->spec_v) cudaFree(h->spec_v);
-    if (h->spec_lam) cudaFree(h->spec_lam);
-    h->spec_v = h->spec_lam = nullptr;
-    CU(h, cudaMalloc(&h->spec_v, v.size() * sizeof(float)));
-    CU(h, cudaMalloc(&h->spec_lam, lam.size() * sizeof(float)));
-    CU(h, cudaMemcpy(h->spec_v, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
-    CU(h, cudaMemcpy(h->spec_lam, lam.data(), lam.size() * sizeof(float), cudaMemcpyHostToDevice));
-    h->spec_re = RE; h->spec_ro = RO;
+    // ---- tables of the one-warp-per-environment kernel (warp_kernel.cuh): lane l owns the octant points
+    //      a_p = (zq * 4 + xq) * 4 + 2 * yp + p, zq = l >> 3, xq = (l >> 1) & 3, yp = l & 1; modes sector after sector ----
+    int compiled[8];
+    const int wset = h->no_warp ? -1 : warp_kernel_rank_set(ranks8, compiled);
+    std::vector<float> wv, wlam;
+    if (wset >= 0) {
+        int nm = 0;
+        for (int s8 = 0; s8 < 8; ++s8) nm += compiled[s8];
+        wv.assign((size_t)32 * nm * 2, 0.f);
+        wlam.assign((size_t)nm, 0.f);
+        int off = 0;
+        for (int s8 = 0; s8 < 8; ++s8) {
+            for (int m = 0; m < compiled[s8] && m < ranks8[s8]; ++m) {
+                wlam[off + m] = (float)(vals[(size_t)s8 * r_max + m] * scale);
+                for (int l = 0; l < 32; ++l)
+                    for (int pt = 0; pt < 2; ++pt) {
+                        const int a = ((l >> 3) * 4 + ((l >> 1) & 3)) * 4 + 2 * (l & 1) + pt;
+                        wv[((size_t)l * nm + off + m) * 2 + pt] = (float)vecs[((size_t)s8 * 64 + a) * r_max + m];
+                    }
+            }
+            off += compiled[s8];
+        }
+    }
+    for (float** q : {&h->spec_v, &h->spec_lam, &h->wspec_v, &h->wspec_lam}) { if (*q) cudaFree(*q); *q = nullptr; }
+    auto upload = [&](float** dst, const std::vector<float>& src) -> cudaError_t {
+        cudaError_t e = cudaMalloc(dst, src.size() * sizeof(float));
+        if (e != cudaSuccess) return e;
+        return cudaMemcpy(*dst, src.data(), src.size() * sizeof(float), cudaMemcpyHostToDevice);
+    };
+    CU(h, upload(&h->spec_v, v));
+    CU(h, upload(&h->spec_lam, lam));
+    if (wset >= 0) { CU(h, upload(&h->wspec_v, wv)); CU(h, upload(&h->wspec_lam, wlam)); }
+    h->spec_re = RE; h->spec_ro = RO; h->warp_set = wset;
     if (h->fsal_valid) CU(h, cudaMemset(h->fsal_valid, 0, (size_t)h->B * 4));
     return DBSGYM_OK;
 }

@@ -18,6 +18,11 @@ cudaError_t launch_f32_mw(int ctas, const StepParams& p, cudaStream_t s);
 // spectral kernel (8 x 8 x 8): r_odd <= 4 selects the (9, 4) instantiation, otherwise (9, 9); *workers = environments per CTA
 cudaError_t launch_f32_spectral(int r_odd, int num_sms, const StepParams& p, cudaStream_t s);
 int spectral_envs_per_cta();
+// spectral kernel, one warp per environment (warp_kernel.cuh): rank_set = index returned by warp_kernel_rank_set for the
+// eight sector ranks (-1: no compiled rank list covers them); compiled8 receives the ranks the tables must be padded to
+int warp_kernel_rank_set(const int* ranks8, int* compiled8);
+cudaError_t launch_f32_warp(int rank_set, int num_sms, const StepParams& p, cudaStream_t s);
+int warp_envs_per_cta();
 // cluster mode: one environment = `cluster` CTAs
 cudaError_t launch_f32_cluster(int geo, int threads, int cluster, const StepParams& p, cudaStream_t s);
 

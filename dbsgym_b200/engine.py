@@ -45,7 +45,7 @@ class KuramotoEngine:
                  action_bounds=(-5.0, 5.0), max_steps=4096, options=None):
         """``options``: tuning / diagnostic switches of DbsGymConfig (include/dbsgym.h) -- ``mw`` (None auto, False
         never, True always use the multi-worker step kernel), ``force_cluster``, ``ctas_per_sm`` and the boolean A/B
-        switches ``no_geo1``, ``no_sym``, ``no_fsal_reuse``, ``no_fused_obs``, ``no_fast_obs``."""
+        switches ``no_geo1``, ``no_sym``, ``no_fsal_reuse``, ``no_fused_obs``, ``no_fast_obs``, ``no_warp_kernel``."""
         if precision not in ("f32", "f64"):
             raise ValueError("precision must be 'f32' or 'f64'")
         if (coupling_table is None) == (alpha is None):
@@ -74,7 +74,7 @@ class KuramotoEngine:
         flags = 0
         for name, bit in (("no_geo1", _capi.DBG_NO_GEO1), ("no_sym", _capi.DBG_NO_SYM),
                           ("no_fsal_reuse", _capi.DBG_NO_FSAL_REUSE), ("no_fused_obs", _capi.DBG_NO_FUSED_OBS),
-                          ("no_fast_obs", _capi.DBG_NO_FAST_OBS)):
+                          ("no_fast_obs", _capi.DBG_NO_FAST_OBS), ("no_warp_kernel", _capi.DBG_NO_WARP_KERNEL)):
             if opt.pop(name, False):
                 flags |= bit
         if opt:
@@ -103,13 +103,13 @@ class KuramotoEngine:
         """Switch the GRID operator to its spectral form (dbsgym.h: dbsgym_set_coupling_spectral).  ``vecs`` [8][64][r_max],
         ``vals`` [8][r_max], ``ranks`` [8] as returned by geometry.spectral_factors; ``ranks=None`` switches back."""
         if ranks is None:
-            self._ck(self.lib.dbsgym_set_coupling_spectral(self._h, 0, 0, 0, None, None))
+            self._ck(self.lib.dbsgym_set_coupling_spectral(self._h, None, 0, None, None))
             self.spectral = None
             return
-        r_even, r_odd = max(max(ranks[:4]), 1), max(max(ranks[4:]), 1)
         v, w = _f64(vecs), _f64(vals)
-        self._ck(self.lib.dbsgym_set_coupling_spectral(self._h, int(r_even), int(r_odd), int(v.shape[2]), _capi.ptr(v),
-                                                       _capi.ptr(w)))
+        r8 = np.ascontiguousarray(ranks, dtype=np.int32)
+        assert r8.shape == (8,)
+        self._ck(self.lib.dbsgym_set_coupling_spectral(self._h, _capi.ptr(r8), int(v.shape[2]), _capi.ptr(v), _capi.ptr(w)))
         self.spectral = {"ranks": [int(r) for r in ranks], "modes": int(sum(ranks)), "residual": residual}
 
     # ------------------------------------------------------------------ plumbing

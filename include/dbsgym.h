@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define DBSGYM_ABI_VERSION 2
+#define DBSGYM_ABI_VERSION 3
 #define DBSGYM_OWN_STREAM ((void*)(intptr_t)-1)
 
 typedef struct DbsGymHandle DbsGymHandle;
@@ -83,7 +83,8 @@ enum { DBSGYM_DBG_NO_GEO1 = 1u,          /* skip the kernels specialised for the
        DBSGYM_DBG_NO_SYM = 2u,           /* plain Toeplitz contraction instead of the parity sectors          */
        DBSGYM_DBG_NO_FSAL_REUSE = 4u,    /* evaluate the first stage of every segment (fp32 too)              */
        DBSGYM_DBG_NO_FUSED_OBS = 8u,     /* separate observation / reward kernel instead of the fused tail    */
-       DBSGYM_DBG_NO_FAST_OBS = 16u };   /* generic observation kernel instead of the streamlined one         */
+       DBSGYM_DBG_NO_FAST_OBS = 16u,     /* generic observation kernel instead of the streamlined one         */
+       DBSGYM_DBG_NO_WARP_KERNEL = 32u };/* spectral coupling: the 64-thread worker kernel instead of one warp per environment */
 
 typedef struct DbsGymRewardSpec {
     uint32_t struct_bytes;
@@ -106,7 +107,9 @@ int  dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out);
  * 0 plain Toeplitz GRID, 1 DENSE, 2 parity-sector GRID_SYM (run-time extents), 3 GRID_SYM unrolled for the
  * 8 x 8 x 8 grid (one CTA per environment), 4 multi-worker (8 environments per CTA sharing precomputed sector
  * coefficients), 5 cluster mode (N > 4096), 6 GRID_SYM with gx = 8 fixed, 7 / 8 GRID_SYM with lines of 16 / 32 (gy = 16 / 32),
- * 9 spectral contraction (dbsgym_set_coupling_spectral; multi-worker hosting); negative = error code */
+ * 9 spectral contraction (dbsgym_set_coupling_spectral; multi-worker hosting, 64 threads per environment),
+ * 10 spectral contraction, one warp per environment with octant ownership (the default when the sector ranks fit a
+ * compiled rank list); negative = error code */
 int  dbsgym_step_variant(const DbsGymHandle* h, int32_t n_envs);
 void dbsgym_destroy(DbsGymHandle* h);
 /* text of the last error on this handle (h == NULL: last error of a failed create) */
@@ -125,11 +128,10 @@ int dbsgym_set_coupling_dense(DbsGymHandle* h, const double* alpha);
  * alpha commutes with the three reflections of the grid, so the eigenvectors are given per parity sector
  * s = 4 [odd in y] + 2 [odd in z] + [odd in x]:  vecs[(s * 64 + a) * r_max + m] = unit eigenvector m of the 64 x 64
  * sector block at fundamental-octant point a = (zq * 4 + xq) * 4 + yq, vals[s * r_max + m] its eigenvalue (in the
- * unnormalised sector coordinates X_s[a] = sum_g chi_s(g) x[g a]); sectors even in y use their first r_even modes,
- * sectors odd in y their first r_odd (1..9 each; pad with zeros).  The truncation error is the caller's
- * responsibility (dbsgym_b200/geometry.py: spectral_factors returns the spectral norm of what was dropped).
- * r_even = r_odd = 0 switches back to the exact sector-block contraction. */
-int dbsgym_set_coupling_spectral(DbsGymHandle* h, int32_t r_even, int32_t r_odd, int32_t r_max,
+ * unnormalised sector coordinates X_s[a] = sum_g chi_s(g) x[g a]); sector s uses its first ranks8[s] modes (0..9, at
+ * most r_max).  The truncation error is the caller's responsibility (dbsgym_b200/geometry.py: spectral_factors returns
+ * the spectral norm of what was dropped).  ranks8 == NULL switches back to the exact sector-block contraction. */
+int dbsgym_set_coupling_spectral(DbsGymHandle* h, const int32_t* ranks8, int32_t r_max,
                                  const double* vecs, const double* vals);
 
 /* Per-environment vectors uploaded at reset (env.py:566-598): natural frequencies after

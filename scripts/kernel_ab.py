@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """A/B timing of the float32 step kernels on one GPU (device-resident, CUDA events inside the library):
-exact multi-worker contraction vs the spectral kernel, same environments, same actions."""
+exact multi-worker contraction vs the spectral kernels (spectral64 = 64-thread workers, warp34 / warp32 = one warp per
+environment with 34 / 32 modes), same environments, same actions."""
 import argparse
 import os
 import sys
@@ -17,7 +18,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--envs", type=int, default=4096)
     ap.add_argument("--steps", type=int, default=60)
-    ap.add_argument("--modes", default="exact,spectral")
+    ap.add_argument("--modes", default="exact,spectral64,warp34,warp32")
     args = ap.parse_args()
     import torch
     from dbsgym_b200.batched import BatchedKuramoto
@@ -29,7 +30,11 @@ def main():
     for mode in args.modes.split(","):
         np.random.seed(0)
         t0 = time.time()
-        core = BatchedKuramoto([dict(d) for d in dicts], coupling_eval=mode)
+        kw = {"exact": dict(coupling_eval="exact"),
+              "spectral64": dict(coupling_eval="spectral", engine_options={"no_warp_kernel": True}),
+              "warp34": dict(coupling_eval="spectral", spectral_tol=1e-10),
+              "warp32": dict(coupling_eval="spectral", spectral_tol=1e-9)}[mode]
+        core = BatchedKuramoto([dict(d) for d in dicts], **kw)
         eng = core.engine
         eng.set_episode(None, step_idx=0, episode_len=2 ** 30)
         eng.set_timing(True)
@@ -41,7 +46,7 @@ def main():
                 ms.append(eng.last_step_ms()[0])
         y = eng.state()
         c = eng.counters()
-        line = f"{mode:9s} variant {eng.step_variant()} step kernel {np.mean(ms):.4f} ms (min {np.min(ms):.4f}) -> " \
+        line = f"{mode:10s} modes {(eng.spectral or {}).get('modes')} variant {eng.step_variant()} step kernel {np.mean(ms):.4f} ms (min {np.min(ms):.4f}) -> " \
                f"{B / np.mean(ms) * 1e3 / 1e6:.2f} M env-steps/s; status {c['status']}; setup {time.time() - t0:.1f}s"
         if ref is not None:
             line += f"; max |phase - {args.modes.split(',')[0]}| after {args.steps + 5} free-running steps {np.max(np.abs(y - ref)):.2e}"

@@ -22,7 +22,7 @@ def test_header_and_exports_agree(lib):
     raw = C.CDLL(_capi.LIB_PATH)
     for name in declared:
         assert hasattr(raw, name), name
-    assert lib.dbsgym_abi_version() == _capi.ABI_VERSION == 2
+    assert lib.dbsgym_abi_version() == _capi.ABI_VERSION == 3
 
 
 def test_struct_layouts_match_header():

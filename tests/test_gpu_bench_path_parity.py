@@ -32,9 +32,9 @@ pytestmark = pytest.mark.gpu
 # beta power is 27 %)
 ENS_BBPOW_MEAN_TOL, ENS_BBPOW_MEDIAN_TOL, ENS_KS_TOL, ENS_KS_LATE_TOL, ENS_REWARD_MEAN_TOL = 0.02, 0.02, 0.015, 0.04, 0.02
 
-# the three float32 step kernels for the shipped 8 x 8 x 8 grid: (name, engine options, coupling_eval, dbsgym_step_variant)
+# the four float32 step kernels for the shipped 8 x 8 x 8 grid: (name, engine options, coupling_eval, dbsgym_step_variant)
 F32_KERNELS = [("single", {"mw": False}, "exact", 3), ("multi_worker", {"mw": True}, "exact", 4),
-               ("spectral", None, "spectral", 9)]
+               ("spectral_worker", {"no_warp_kernel": True}, "spectral", 9), ("spectral_warp", None, "spectral", 10)]
 
 
 def _core(dicts, precision="f32", engine_options=None, transfer="full", coupling_eval="exact"):
@@ -51,7 +51,8 @@ def _core(dicts, precision="f32", engine_options=None, transfer="full", coupling
 @pytest.mark.parametrize("name,options,ceval,variant", F32_KERNELS)
 def test_f32_kernels_teacher_forced_against_reference_goldens(golden, cfg, seed, kw, n_steps, name, options, ceval, variant):
     """The float32 step kernels for the 8 x 8 x 8 grid -- exact contraction with one CTA per environment (variant 3), its
-    multi-worker form (variant 4) and the spectral kernel the benchmark runs (variant 9) -- against the fixtures the
+    multi-worker form (variant 4), the spectral kernel with 64-thread workers (variant 9) and the one-warp-per-environment
+    spectral kernel the benchmark runs (variant 10) -- against the fixtures the
     reference's own env.py produced."""
     from test_gpu_parity import _teacher_forced
     g = load_golden(golden)
@@ -85,8 +86,9 @@ def _sync_oracle(orc, core, e, y, win):
     orc.current_time = core.current_time(e)
 
 
-@pytest.mark.parametrize("ceval,variant", [("exact", 4), ("spectral", 9)])
-def test_bench_config_4096_env1_f32_against_oracle(ceval, variant):
+@pytest.mark.parametrize("ceval,options,variant", [("exact", None, 4), ("spectral", {"no_warp_kernel": True}, 9),
+                                                   ("spectral", None, 10)])
+def test_bench_config_4096_env1_f32_against_oracle(ceval, options, variant):
     """BASELINE configs[2] as bench.py builds it (env1, 4096 environments, float32; the spectral kernel bench.py runs by
     default and the exact multi-worker kernel): a sample of
     environments is checked against the CPU oracle per step -- teacher-forced at 1e-5 rad, then free-running with the
@@ -96,7 +98,7 @@ def test_bench_config_4096_env1_f32_against_oracle(ceval, variant):
     from bench import build_params
     B = 4096
     dicts = build_params(B, seed0=10)
-    core = _core(dicts, coupling_eval=ceval)
+    core = _core(dicts, coupling_eval=ceval, engine_options=options)
     eng = core.engine
     assert eng.step_variant() == variant
     sample = [0, 7, 1183, 1184, 2500, 4095]          # first / last worker slots, both sides of a wave boundary
@@ -235,7 +237,7 @@ def test_full_2048_step_episode_against_oracle():
     for precision, ceval in (("f64", "exact"), ("f32", "spectral")):
         core = _core([d] * 2, precision=precision, coupling_eval=ceval)
         if precision == "f32":
-            assert core.engine.step_variant() == 9
+            assert core.engine.step_variant() == 10
         core.engine.counters(reset=True)                # (the reset transient has rejections; step() must not)
         tm, rew = _episode(core, acts)
         st = core.engine.counters()
