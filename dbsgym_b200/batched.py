@@ -36,13 +36,14 @@ def _pinned(shape, dtype):
 
 class BatchedKuramoto:
     def __init__(self, params_dicts, *, precision="f32", device=0, compat_env2=False, force_dense=False,
-                 save_init=False, transfer="delta", engine_options=None, coupling_eval="auto", spectral_tol=1e-10,
+                 save_init=False, transfer="delta", engine_options=None, coupling_eval="auto", spectral_tol=1e-9,
                  batch_resets=True):
         """``coupling_eval``: how the float32 kernels evaluate the coupling sum of env.py:252-256 on the 8 x 8 x 8 grid --
         ``"exact"``: the parity-sector block contraction (the same sum as the reference, reassociated); ``"spectral"``:
         the generalised mean-field identity over the eigenmodes of alpha above ``spectral_tol * |lambda_max|``
-        (geometry.spectral_factors; 34 modes at the default 1e-10, truncation error 2.5e-8 in the spectral norm of
-        alpha, i.e. < 1e-10 rad per time unit in d theta / dt -- three orders below float32 rounding of the exact sum);
+        (geometry.spectral_factors; 32 modes at the default 1e-9 -- ranks 7 + 4 x 6 + 1 over the eight parity sectors --
+        truncation error 2.2e-7 in the spectral norm of alpha, i.e. ~1e-11 rad per time unit in d theta / dt, four orders
+        below float32 rounding of the exact sum; 1e-10 gives 34 modes);
         ``"auto"`` = spectral where it applies (float32, regular 8 x 8 x 8 grid, ranks within the compiled range), else
         exact.  float64 (parity mode) always evaluates the exact sum."""
         if isinstance(params_dicts, dict):

@@ -792,7 +792,8 @@ int dbsgym_set_coupling_spectral(DbsGymHandle* h, const int32_t* ranks8, int32_t
                 for (int l = 0; l < 32; ++l)
                     for (int pt = 0; pt < 2; ++pt) {
                         const int a = ((l >> 3) * 4 + ((l >> 1) & 3)) * 4 + 2 * (l & 1) + pt;
-                        wv[((size_t)l * nm + off + m) * 2 + pt] = (float)vecs[((size_t)s8 * 64 + a) * r_max + m];
+                        const int mode = off + m;                      // [mode pair][lane](V0[m], V1[m], V0[m + 1], V1[m + 1])
+                        wv[(((size_t)(mode >> 1) * 32 + l) * 2 + (mode & 1)) * 2 + pt] = (float)vecs[((size_t)s8 * 64 + a) * r_max + m];
                     }
             }
             off += compiled[s8];

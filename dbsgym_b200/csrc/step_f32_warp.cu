@@ -21,12 +21,14 @@ template <class RK>
 static cudaError_t launch_w(int num_sms, const StepParams& p, cudaStream_t s) {
     using L = WarpLayout<RK>;
     auto kern = warp_step_kernel<RK>;
-    const size_t smem = (size_t)kWarpEnvs * L::bytes_aligned;
+    int warps = kWarpEnvs;                                   // as many as the 227 KB of an SM hold (larger rank lists: fewer)
+    while (warps > 1 && L::cta_bytes(warps) > (size_t)227 * 1024) --warps;
+    const size_t smem = L::cta_bytes(warps);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    int ctas = (p.n_launch + kWarpEnvs - 1) / kWarpEnvs;
+    int ctas = (p.n_launch + warps - 1) / warps;
     if (ctas > num_sms) ctas = num_sms;
-    kern<<<ctas, kWarpEnvs * 32, smem, s>>>(p);
+    kern<<<ctas, warps * 32, smem, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -21,13 +21,26 @@
 // g = 4 my + 2 mz + mx (bit set = mirrored coordinate); after the butterfly index g is the sector
 // s = 4 [odd in y] + 2 [odd in z] + [odd in x] of geometry.sector_blocks.
 #pragma once
+#include <utility>
 #include "step_kernel.cuh"
+
+// mode sums in one pass (all partials in shared memory at once) or in two (half the buffer, two more __syncwarp)
+#ifndef DBSGYM_WARP_PASSES
+#define DBSGYM_WARP_PASSES 1
+#endif
+// eigenvector entries: 0 = registers of the lane (2 x modes of them), 1 = one table per CTA in shared memory (LDS.128 per
+// mode pair in projection and expansion; frees 64 registers per thread).  Measured on B200 at 8 warps per SM: the table
+// costs 11 % (0.281 -> 0.311 ms per 4096-env step), and the register file allocates warps in fours, so the next
+// occupancy step after 8 warps x 255 registers is 12 x 168, which the 12 KB of stage derivatives per warp do not allow.
+#ifndef DBSGYM_WARP_VSMEM
+#define DBSGYM_WARP_VSMEM 0
+#endif
 
 namespace dbsgym {
 
 constexpr int kWR = 16;            // oscillators per lane
 template <int V> struct IC { static constexpr int value = V; };
-
+constexpr int kWarpTs = 32;        // save times of a step() segment staged in shared memory (longer lists are read from global)
 template <int... Rs> struct RankSet {
     static_assert(sizeof...(Rs) == 8, "one rank per parity sector");
     __host__ __device__ static constexpr int get(int s) { const int r[8] = {Rs...}; return r[s]; }
@@ -37,34 +50,36 @@ template <int... Rs> struct RankSet {
         for (int i = 0; i < s; ++i) o += r[i];
         return o;
     }
-    __host__ __device__ static constexpr int coff(int s) {            // the same in the coefficient row, where sectors are padded to even counts
-        const int r[8] = {Rs...};
-        int o = 0;
-        for (int i = 0; i < s; ++i) o += (r[i] + 1) & ~1;
-        return o;
+    __host__ __device__ static constexpr int sector_of(int m) {       // the sector mode m belongs to
+        for (int s = 0; s < 8; ++s)
+            if (m < off(s + 1)) return s;
+        return 7;
     }
+    __host__ __device__ static constexpr bool first_of_sector(int m) { return off(sector_of(m)) == m; }
 };
+
+template <class F, int... I> __device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) { (f(IC<I>{}), ...); }
+template <int N, class F> __device__ __forceinline__ void static_for(F&& f) { static_for_impl(f, std::make_integer_sequence<int, N>{}); }
 
 template <class RK> struct WarpLayout {
-    static constexpr int NM = RK::off(8);
-    static constexpr int NC = RK::coff(8);
+    static constexpr int NM = RK::off(8);                       // modes (even: they are handled in pairs)
+    static constexpr int NP = NM / 2;                           // mode pairs
+    static constexpr int PASSES = DBSGYM_WARP_PASSES;
+    static constexpr int PP = (NP + PASSES - 1) / PASSES;       // mode pairs per pass
     static constexpr int RS = 36;                               // words per half row: 16 float2 partials + 4 (conflict-free both ways)
-    static constexpr int HROWS = 2 * NM;                        // half rows: (mode, lanes 0-15 / 16-31)
-    static constexpr int ROUNDS = (HROWS + 31) / 32;
-    static constexpr int p_floats = HROWS * RS;
-    static constexpr int c_floats = (2 * NC + 3) & ~3;
+    static constexpr int HR = 4 * PP;                           // half rows of a pass: (mode, lanes 0-15 / 16-31)
+    static constexpr int ROUNDS = (HR + 31) / 32;
+    static constexpr int p_floats = HR * RS;
+    static constexpr int c_floats = 2 * NM;
+    static constexpr bool VSMEM = DBSGYM_WARP_VSMEM != 0;
+    static constexpr size_t v_bytes = VSMEM ? (size_t)NP * 32 * 16 : 0;      // eigenvector table of the CTA
+    static_assert(NM % 2 == 0 && c_floats % 4 == 0, "modes come in pairs");
+    static_assert(p_floats >= 8 * 68, "the partials buffer also holds the lane sums of 8 LFP samples");
     // bytes of one warp's shared memory: K slots, partials + coefficients, winding counts, w0 + pulse, tail scratch
-    static constexpr size_t bytes = (size_t)(kSlots * 512 + p_floats + c_floats + 512 + 512) * 4 + 32 * 8 + 36 * 4 + 8;
+    static constexpr size_t bytes = (size_t)(kSlots * 512 + p_floats + c_floats + 512 + 512) * 4 + (32 + 2 * kWarpTs) * 8 + 36 * 4 + 8;
     static constexpr size_t bytes_aligned = (bytes + 15) & ~(size_t)15;
+    static constexpr size_t cta_bytes(int warps) { return v_bytes + (size_t)warps * bytes_aligned; }
 };
-
-template <int S, class RK, class F> __device__ __forceinline__ void with_sector(F&& f) {
-    f(IC<S>{}, IC<RK::get(S)>{}, IC<RK::off(S)>{}, IC<RK::coff(S)>{});
-}
-template <class RK, class F> __device__ __forceinline__ void for_each_sector(F&& f) {
-    with_sector<0, RK>(f); with_sector<1, RK>(f); with_sector<2, RK>(f); with_sector<3, RK>(f);
-    with_sector<4, RK>(f); with_sector<5, RK>(f); with_sector<6, RK>(f); with_sector<7, RK>(f);
-}
 
 // thread-private rows of 16 floats in shared memory: piece q (4 floats) of lane l at float4 index q * 32 + l
 __device__ __forceinline__ void wload16(const float* __restrict__ row, int lane, float (&o)[kWR]) {
@@ -170,6 +185,26 @@ __device__ __forceinline__ void wht8(float2 (&x)[kWR], int o) {
 
 __device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
 
+// sin / cos of a wrapped phase plus a stage increment (|x| well below 2^22): nearest multiple of 2 pi by the magic-number
+// trick -- two FMA-pipe instructions instead of FMUL + FRND (FRND runs on the 16-lane XU pipe next to the MUFUs) -- one
+// Cody-Waite constant (|k| <= 1 here: the dropped low part is k * 1.7e-7 rad, below MUFU.SIN's own 5e-7), then MUFU
+#ifndef DBSGYM_PRECISE_SINCOS
+__device__ __forceinline__ float wreduce(float x) {
+    const float t = fmaf(x, 0.15915494309189535f, 12582912.0f);          // 1.5 * 2^23: the sum is rounded to an integer
+    const float k = t - 12582912.0f;
+#ifdef DBSGYM_WARP_CW2
+    return fmaf(-k, -1.7484555314695172e-07f, fmaf(-k, 6.2831854820251465f, x));
+#else
+    return fmaf(-k, 6.2831854820251465f, x);
+#endif
+}
+__device__ __forceinline__ void wsincos(float x, float* s, float* c) { const float r = wreduce(x); *s = __sinf(r); *c = __cosf(r); }
+__device__ __forceinline__ float wcos(float x) { return __cosf(wreduce(x)); }
+#else
+__device__ __forceinline__ void wsincos(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ float wcos(float x) { return cosf(x); }
+#endif
+
 template <class RK>
 __global__ void __maxnreg__(DBSGYM_WARP_MAXNREG) warp_step_kernel(const StepParams p) {
     using L = WarpLayout<RK>;
@@ -177,36 +212,43 @@ __global__ void __maxnreg__(DBSGYM_WARP_MAXNREG) warp_step_kernel(const StepPara
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = (int)(threadIdx.x & 31), wid = (int)(threadIdx.x >> 5), nwarp = (int)(blockDim.x >> 5);
-    unsigned char* wsm = smem_raw + (size_t)wid * L::bytes_aligned;
+    unsigned char* wsm = smem_raw + L::v_bytes + (size_t)wid * L::bytes_aligned;
     float* K = reinterpret_cast<float*>(wsm);                 // [kSlots][512], thread-private interleaved rows
-    float* Pw = K + kSlots * 512;                             // [HROWS][RS] projection partials
-    float* Cw = Pw + L::p_floats;                             // [NC] float2 mode coefficients x lambda
+    float* Pw = K + kSlots * 512;                             // [HR][RS] projection partials of one pass
+    float* Cw = Pw + L::p_floats;                             // [NM] float2 mode coefficients x lambda
     int* WD = reinterpret_cast<int*>(Cw + L::c_floats);       // [16][32] winding counts
     float* C0 = reinterpret_cast<float*>(WD + 512);           // [16][32] w0 + pulse of the segment (interleaved like K)
     double* t_delta = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(C0 + 512) + 7) & ~uintptr_t(7));
-    int* t_pos = reinterpret_cast<int*>(t_delta + 32);
+    double* TS = t_delta + 32;                                // [2][kWarpTs] save times of the two segments of a step
+    int* t_pos = reinterpret_cast<int*>(TS + 2 * kWarpTs);
 
     const OctLane OL(lane);
 
-    // eigenvector entries of this lane's two points (registers for the whole launch) and the eigenvalues of the half
-    // rows it sums (already multiplied by K / (8 N))
-    float V0[NM], V1[NM], lam_r[L::ROUNDS];
-    int cslot_r[L::ROUNDS];                                   // where the mode of that half row goes in the coefficient row
-    {
-        const float2* v = reinterpret_cast<const float2*>(p.spec_v) + (size_t)lane * NM;
+    // eigenvector entries of this lane's two points, per mode pair (V0[m], V1[m], V0[m + 1], V1[m + 1]): registers for
+    // the whole launch, or one table per CTA in shared memory; and the eigenvalues of the half rows this lane sums
+    // (already multiplied by K / (8 N))
+    constexpr int NP = L::NP, PP = L::PP;
+    float4 Vr[L::VSMEM ? 1 : NP];
+    const float4* Vs4 = reinterpret_cast<const float4*>(smem_raw) + lane;
+    if constexpr (L::VSMEM) {
+        for (int i = (int)threadIdx.x; i < NP * 32; i += (int)blockDim.x)
+            reinterpret_cast<float4*>(smem_raw)[i] = __ldg(reinterpret_cast<const float4*>(p.spec_v) + i);
+        __syncthreads();
+    } else {
 #pragma unroll
-        for (int m = 0; m < NM; ++m) { const float2 t = __ldg(v + m); V0[m] = t.x; V1[m] = t.y; }
+        for (int m2 = 0; m2 < NP; ++m2) Vr[m2] = __ldg(reinterpret_cast<const float4*>(p.spec_v) + m2 * 32 + lane);
+    }
+    auto vpair = [&](auto m2) -> float4 {
+        if constexpr (L::VSMEM) return Vs4[decltype(m2)::value * 32];
+        else return Vr[decltype(m2)::value];
+    };
+    float lam_r[L::PASSES][L::ROUNDS];
+#pragma unroll
+    for (int q = 0; q < L::PASSES; ++q) {
 #pragma unroll
         for (int rd = 0; rd < L::ROUNDS; ++rd) {
-            const int hg = lane + 32 * rd;
-            lam_r[rd] = hg < L::HROWS ? __ldg(p.spec_lam + (hg >> 1)) : 0.f;
-            const int m = hg >> 1;
-            int cm = m;
-            for_each_sector<RK>([&](auto, auto, auto oo, auto co) {
-                constexpr int off = decltype(oo)::value, coff = decltype(co)::value;
-                if (m >= off) cm = m - off + coff;
-            });
-            cslot_r[rd] = cm;
+            const int m = 2 * q * PP + ((lane + 32 * rd) >> 1);
+            lam_r[q][rd] = (lane + 32 * rd < L::HR && m < NM) ? __ldg(p.spec_lam + m) : 0.f;
         }
     }
 
@@ -257,6 +299,11 @@ __global__ void __maxnreg__(DBSGYM_WARP_MAXNREG) warp_step_kernel(const StepPara
         seg_from[0] = seg_from[1] = 0;
         seg_out[0] = 0; seg_out[1] = nI;
         seg_amp[0] = (float)u; seg_amp[1] = 0.f;
+        if (nI <= kWarpTs && nII <= kWarpTs) {               // the save times are consulted all the time: keep them on chip
+            if (lane < nI) TS[lane] = seg_ts[0][lane];
+            if (lane < nII) TS[kWarpTs + lane] = seg_ts[1][lane];
+            seg_ts[0] = TS; seg_ts[1] = TS + kWarpTs;
+        }
     } else {
         nseg = 1;
         seg_ts[0] = p.ts; seg_nts[0] = p.n_ts; seg_nrec[0] = p.n_ts - 1;
@@ -317,69 +364,77 @@ __global__ void __maxnreg__(DBSGYM_WARP_MAXNREG) warp_step_kernel(const StepPara
                         for (int r = 0; r < kWR; ++r) ys[r] += y0[r];
                     } else wstage_argument(s, K, lane, dt, y0, ys);
 #pragma unroll
-                    for (int r = 0; r < kWR; ++r) sincos_r(ys[r], &sv[r], &cv[r]);
+                    for (int r = 0; r < kWR; ++r) wsincos(ys[r], &sv[r], &cv[r]);
                 }
                 float2 X[kWR];
 #pragma unroll
                 for (int r = 0; r < kWR; ++r) X[r] = make_float2(sv[r], cv[r]);
                 wht8(X, 0);
                 wht8(X, 8);
-                // ---- projection: this lane's contribution to every mode sum, P[mode][lane] ----
-                {
+                // ---- mode sums, PASSES passes of PP mode pairs: projection partials P[mode][lane] of this lane, then one
+                //      lane per half row adds 16 of them and the two halves of a mode meet by one shuffle ----
+                static_for<L::PASSES>([&](auto qq) {
+                    constexpr int q = decltype(qq)::value;
                     float* prow = Pw + (lane >> 4) * L::RS + 2 * (lane & 15);
-                    for_each_sector<RK>([&](auto ss, auto rr, auto oo, auto) {
-                        constexpr int sec = decltype(ss)::value, Rc = decltype(rr)::value, off = decltype(oo)::value;
-#pragma unroll
-                        for (int m = 0; m < Rc; ++m) {
-                            float2 a = __fmul2_rn(bcast2(V0[off + m]), X[sec]);
-                            a = __ffma2_rn(bcast2(V1[off + m]), X[8 + sec], a);
-                            *reinterpret_cast<float2*>(prow + (off + m) * 2 * L::RS) = a;
+                    static_for<PP>([&](auto jj) {
+                        constexpr int j = decltype(jj)::value, m2 = q * PP + j;
+                        if constexpr (m2 < NP) {
+                            constexpr int sa = RK::sector_of(2 * m2), sb = RK::sector_of(2 * m2 + 1);
+                            const float4 v = vpair(IC<m2>{});
+                            float2 a = __fmul2_rn(bcast2(v.x), X[sa]), b = __fmul2_rn(bcast2(v.z), X[sb]);
+                            a = __ffma2_rn(bcast2(v.y), X[8 + sa], a);
+                            b = __ffma2_rn(bcast2(v.w), X[8 + sb], b);
+                            *reinterpret_cast<float2*>(prow + (2 * j) * 2 * L::RS) = a;
+                            *reinterpret_cast<float2*>(prow + (2 * j + 1) * 2 * L::RS) = b;
                         }
                     });
-                }
-                __syncwarp();
-                // ---- one lane per half row: sum of 16 lane partials; the two halves of a mode meet by one shuffle ----
+                    __syncwarp();
+                    constexpr int live_rows = 4 * ((NP - q * PP) < PP ? (NP - q * PP) : PP);      // half rows written in this pass
+                    // all rounds side by side (loads, then the add trees, then the shuffles): independent chains
+                    float2 v[L::ROUNDS][16];
+                    bool live[L::ROUNDS];
 #pragma unroll
-                for (int rd = 0; rd < L::ROUNDS; ++rd) {
-                    const int hg = lane + 32 * rd;
-                    const bool live = (L::HROWS % 32 == 0) || hg < L::HROWS;
-                    float2 tot = make_float2(0.f, 0.f);
-                    if (live) {
-                        const float4* r4 = reinterpret_cast<const float4*>(Pw + hg * L::RS);
-                        float2 v[16];
+                    for (int rd = 0; rd < L::ROUNDS; ++rd) {
+                        const int hg = lane + 32 * rd;
+                        live[rd] = (live_rows >= 32 * (rd + 1)) || hg < live_rows;
+                        const float4* r4 = reinterpret_cast<const float4*>(Pw + (live[rd] ? hg : 0) * L::RS);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { const float4 x = r4[i]; v[2 * i] = make_float2(x.x, x.y); v[2 * i + 1] = make_float2(x.z, x.w); }
-#pragma unroll
-                        for (int w = 8; w > 0; w >>= 1) {
-#pragma unroll
-                            for (int i = 0; i < w; ++i) v[i] = __fadd2_rn(v[i], v[i + w]);
-                        }
-                        tot = v[0];
+                        for (int i = 0; i < 8; ++i) { const float4 x = r4[i]; v[rd][2 * i] = make_float2(x.x, x.y); v[rd][2 * i + 1] = make_float2(x.z, x.w); }
                     }
-                    const float2 oth = make_float2(__shfl_xor_sync(FULL, tot.x, 1), __shfl_xor_sync(FULL, tot.y, 1));
-                    tot = __fmul2_rn(bcast2(lam_r[rd]), __fadd2_rn(tot, oth));
-                    if (live && !(lane & 1)) reinterpret_cast<float2*>(Cw)[cslot_r[rd]] = tot;
-                }
-                __syncwarp();
+#pragma unroll
+                    for (int w = 8; w > 0; w >>= 1) {
+#pragma unroll
+                        for (int rd = 0; rd < L::ROUNDS; ++rd) {
+#pragma unroll
+                            for (int i = 0; i < w; ++i) v[rd][i] = __fadd2_rn(v[rd][i], v[rd][i + w]);
+                        }
+                    }
+                    float2 oth[L::ROUNDS];
+#pragma unroll
+                    for (int rd = 0; rd < L::ROUNDS; ++rd)
+                        oth[rd] = make_float2(__shfl_xor_sync(FULL, v[rd][0].x, 1), __shfl_xor_sync(FULL, v[rd][0].y, 1));
+#pragma unroll
+                    for (int rd = 0; rd < L::ROUNDS; ++rd) {
+                        const float2 tot = __fmul2_rn(bcast2(lam_r[q][rd]), __fadd2_rn(v[rd][0], oth[rd]));
+                        if (live[rd] && !(lane & 1)) reinterpret_cast<float2*>(Cw)[2 * q * PP + ((lane + 32 * rd) >> 1)] = tot;
+                    }
+                    __syncwarp();
+                });
                 // ---- expansion back to the lane's sector coordinates, then sectors -> images ----
-                for_each_sector<RK>([&](auto ss, auto rr, auto oo, auto co) {
-                    constexpr int sec = decltype(ss)::value, Rc = decltype(rr)::value, off = decltype(oo)::value, coff = decltype(co)::value;
-                    if constexpr (Rc == 0) {
-                        X[sec] = make_float2(0.f, 0.f); X[8 + sec] = make_float2(0.f, 0.f);
-                    } else {
-                        constexpr int R2 = (Rc + 1) & ~1;
-                        float2 cm[R2];
-                        const float4* c4 = reinterpret_cast<const float4*>(Cw + 2 * coff);
-#pragma unroll
-                        for (int i = 0; i < R2 / 2; ++i) { const float4 x = c4[i]; cm[2 * i] = make_float2(x.x, x.y); cm[2 * i + 1] = make_float2(x.z, x.w); }
-                        float2 a0 = __fmul2_rn(bcast2(V0[off]), cm[0]), a1 = __fmul2_rn(bcast2(V1[off]), cm[0]);
-#pragma unroll
-                        for (int m = 1; m < Rc; ++m) {
-                            a0 = __ffma2_rn(bcast2(V0[off + m]), cm[m], a0);
-                            a1 = __ffma2_rn(bcast2(V1[off + m]), cm[m], a1);
-                        }
-                        X[sec] = a0; X[8 + sec] = a1;
-                    }
+                static_for<8>([&](auto ss) {
+                    constexpr int sec = decltype(ss)::value;
+                    if constexpr (RK::get(sec) == 0) { X[sec] = make_float2(0.f, 0.f); X[8 + sec] = make_float2(0.f, 0.f); }
+                });
+                static_for<NP>([&](auto mm) {
+                    constexpr int m2 = decltype(mm)::value, ma = 2 * m2, mb = ma + 1;
+                    constexpr int sa = RK::sector_of(ma), sb = RK::sector_of(mb);
+                    const float4 v = vpair(IC<m2>{});
+                    const float4 c4 = reinterpret_cast<const float4*>(Cw)[m2];
+                    const float2 ca = make_float2(c4.x, c4.y), cb = make_float2(c4.z, c4.w);
+                    if constexpr (RK::first_of_sector(ma)) { X[sa] = __fmul2_rn(bcast2(v.x), ca); X[8 + sa] = __fmul2_rn(bcast2(v.y), ca); }
+                    else { X[sa] = __ffma2_rn(bcast2(v.x), ca, X[sa]); X[8 + sa] = __ffma2_rn(bcast2(v.y), ca, X[8 + sa]); }
+                    if constexpr (RK::first_of_sector(mb)) { X[sb] = __fmul2_rn(bcast2(v.z), cb); X[8 + sb] = __fmul2_rn(bcast2(v.w), cb); }
+                    else { X[sb] = __ffma2_rn(bcast2(v.z), cb, X[sb]); X[8 + sb] = __ffma2_rn(bcast2(v.w), cb, X[8 + sb]); }
                 });
                 wht8(X, 0);
                 wht8(X, 8);
@@ -467,53 +522,64 @@ __global__ void __maxnreg__(DBSGYM_WARP_MAXNREG) warp_step_kernel(const StepPara
 #pragma unroll
                         for (int r = 0; r < kWR; ++r) rc[r] = 0.f;
                     }
-                    // up to 4 samples per pass: their lane sums are reduced together (independent shuffle chains)
+                    // Samples in batches of up to 8.  Every lane leaves its two partial sums (plain, conductance weighted) of a
+                    // sample in the partials buffer (free between RHS evaluations), S[slot][lane]; then lane l adds one quarter
+                    // row of slot l & 7, two shuffles join the quarters, and lanes 0-7 store the 8 results: one short chain per
+                    // batch instead of a shuffle tree per sample.
+                    const float inv_h = (tnext == t) ? 0.f : 1.0f / (float)(tnext - t);
+                    constexpr int SS = 68;                                   // words per slot row: 32 float2 + 4 (conflict-free both ways)
                     while (save_idx < n_ts && ts[save_idx] <= tnext) {
-                        float acc[4];
-                        int sidx[4];
+                        int first_idx = save_idx, nb = 0;
+#pragma unroll 1
+                        for (; nb < 8 && save_idx < n_ts && ts[save_idx] <= tnext; ++nb, ++save_idx) {
+                            const double tsv = ts[save_idx];
+                            float ysmp[kWR];
+                            if (tsv == tnext) {                              // the end point of the sub-step is y1 itself
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            acc[b] = 0.f; sidx[b] = -1;
-                            if (save_idx < n_ts && ts[save_idx] <= tnext) {
-                                const int idx = save_idx++;
-                                if (idx >= rec_from && idx < n_rec) {
-                                    sidx[b] = idx;
-                                    const double tsv = ts[idx];
-                                    const bool at_end = (tsv == tnext);
-                                    const float tau = (tnext == t) ? 0.f : (float)(tsv - t) / (float)(tnext - t);
-                                    float st = 0.f, sr = 0.f;
+                                for (int r = 0; r < kWR; ++r) ysmp[r] = y0[r] + d1[r];
+                            } else {
+                                const float tau = (float)(tsv - t) * inv_h;
 #pragma unroll
-                                    for (int r = 0; r < kWR; ++r) {
-                                        float inc = (((pa[r] * tau + pb[r]) * tau + pc[r]) * tau + f0[r]) * tau;
-                                        if (at_end) inc = d1[r];
-                                        const float c = cos_r(y0[r] + inc);
-                                        st += c; sr = fmaf(c, rc[r], sr);
-                                    }
-                                    // lanes 0-15 go on with the plain sum, lanes 16-31 with the weighted one
-                                    const float send = (lane & 16) ? st : sr, mine = (lane & 16) ? sr : st;
-                                    acc[b] = mine + __shfl_xor_sync(FULL, send, 16);
-                                }
+                                for (int r = 0; r < kWR; ++r)
+                                    ysmp[r] = fmaf(fmaf(fmaf(fmaf(pa[r], tau, pb[r]), tau, pc[r]), tau, f0[r]), tau, y0[r]);
                             }
+                            float st0 = 0.f, st1 = 0.f, sr0 = 0.f, sr1 = 0.f;
+#pragma unroll
+                            for (int r = 0; r < kWR; r += 2) {
+                                const float ca = wcos(ysmp[r]), cb = wcos(ysmp[r + 1]);
+                                st0 += ca; st1 += cb;
+                                sr0 = fmaf(ca, rc[r], sr0); sr1 = fmaf(cb, rc[r + 1], sr1);
+                            }
+                            *reinterpret_cast<float2*>(Pw + nb * SS + 2 * lane) = make_float2(st0 + st1, sr0 + sr1);
                         }
+                        __syncwarp();
+                        {
+                            const int slot = lane & 7, quarter = lane >> 3;
+                            const float4* r4 = reinterpret_cast<const float4*>(Pw + slot * SS + quarter * 16);
+                            float2 v[8];
 #pragma unroll
-                        for (int o = 8; o > 0; o >>= 1) {
+                            for (int i = 0; i < 4; ++i) { const float4 x = r4[i]; v[2 * i] = make_float2(x.x, x.y); v[2 * i + 1] = make_float2(x.z, x.w); }
 #pragma unroll
-                            for (int b = 0; b < 4; ++b) acc[b] += __shfl_xor_sync(FULL, acc[b], o);
-                        }
+                            for (int w = 4; w > 0; w >>= 1) {
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            const float wr = __shfl_sync(FULL, acc[b], 16);
-                            if (lane == 0 && sidx[b] >= 0) {
-                                const double a_t = (double)acc[b] / (double)p.N;
-                                const double a_r = p.weighted_rec ? (double)wr / (double)p.N : a_t;
+                                for (int i = 0; i < w; ++i) v[i] = __fadd2_rn(v[i], v[i + w]);
+                            }
+                            float a = v[0].x, b = v[0].y;
+                            a += __shfl_xor_sync(FULL, a, 8);  b += __shfl_xor_sync(FULL, b, 8);
+                            a += __shfl_xor_sync(FULL, a, 16); b += __shfl_xor_sync(FULL, b, 16);
+                            const int idx = first_idx + lane;
+                            if (lane < nb && idx >= rec_from && idx < n_rec) {
+                                const double a_t = (double)(a * inv_n);
+                                const double a_r = p.weighted_rec ? (double)(b * inv_n) : a_t;
                                 if (p.mode == MODE_STEP) {
-                                    p.lfp_true[(size_t)env * p.smax + out_base + sidx[b]] = a_t;
-                                    p.lfp_rec[(size_t)env * p.smax + out_base + sidx[b]] = a_r;
+                                    p.lfp_true[(size_t)env * p.smax + out_base + idx] = a_t;
+                                    p.lfp_rec[(size_t)env * p.smax + out_base + idx] = a_r;
                                 } else {
-                                    reinterpret_cast<float*>(p.ring)[(size_t)env * p.W + (sidx[b] - rec_from)] = (float)a_r;
+                                    reinterpret_cast<float*>(p.ring)[(size_t)env * p.W + (idx - rec_from)] = (float)a_r;
                                 }
                             }
                         }
+                        __syncwarp();                                        // the buffer is rewritten by the next batch / RHS evaluation
                     }
                 }
                 // ---- accept: y0 <- y1, FSAL k1 <- k7 ----

@@ -1,18 +1,25 @@
 #!/usr/bin/env python
 """Attribute an ncu capture of step_kernel to CUDA source lines (run where the .ncu-rep and the .so are).
-usage: python scripts/ncu_by_line.py gpurun_out/prof.ncu-rep 'step_kernelIfLi2ELi64' [top_n]"""
+usage: python scripts/ncu_by_line.py gpurun_out/prof.ncu-rep 'step_kernelIfLi2ELi64' [top_n] [regions] [kernel-regex] [source-file]
+       (regions = name:lo-hi,... line ranges of the source file; kernel-regex default step_kernel, source file default
+       step_kernel.cuh -- e.g. warp_step_kernel warp_kernel.cuh for the one-warp-per-environment kernel)"""
 import csv, io, os, re, subprocess, sys, tempfile
 from collections import Counter, defaultdict
 
 rep, pat = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 30
+kre = sys.argv[5] if len(sys.argv) > 5 else "step_kernel"
+srcname = sys.argv[6] if len(sys.argv) > 6 else "step_kernel.cuh"
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(root, "dbsgym_b200", "csrc", "libdbsgym.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, check=True, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], cwd=tmp, capture_output=True, text=True).stdout.split("\n")
-start = [i for i, l in enumerate(dis) if l.startswith(".text.") and pat in l][0]
+for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):      # one cubin per translation unit
+    dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], cwd=tmp, capture_output=True, text=True).stdout.split("\n")
+    hits = [i for i, l in enumerate(dis) if l.startswith(".text.") and pat in l]
+    if hits:
+        break
+start = hits[0]
 cur, seq = None, []
 for l in dis[start + 1:]:
     if l.startswith(".text.") or l.startswith(".section"):
@@ -24,7 +31,7 @@ for l in dis[start + 1:]:
     m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m:
         seq.append((m.group(2).strip(), cur))
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:step_kernel"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", f"regex:{kre}"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hi = [i for i, r in enumerate(rows) if "Source" in r and "# Samples" in r][0]
 h = rows[hi]; idx = {n: i for i, n in enumerate(h)}
@@ -49,7 +56,7 @@ for (sass, loc), (s2, e, ns, sd) in zip(seq, ncu):
     for k, v in sd.items():
         st[k] += v
 tot, ts = sum(ex.values()), sum(sm.values())
-src = open(os.path.join(root, "dbsgym_b200", "csrc", "step_kernel.cuh")).read().split("\n")
+src = open(os.path.join(root, "dbsgym_b200", "csrc", srcname)).read().split("\n")
 print(f"total warp instructions {tot}, samples {ts}")
 print("-- stall reasons"); T = sum(st.values())
 for k, v in st.most_common(8):
@@ -60,11 +67,11 @@ for op, v in ops.most_common(14):
 print("-- source lines")
 for loc, v in sorted(sm.items(), key=lambda kv: -kv[1])[:top]:
     f, l = loc if loc else ("?", 0)
-    text = src[l - 1].strip()[:90] if f == "step_kernel.cuh" and l > 0 else ""
+    text = src[l - 1].strip()[:90] if f == srcname and l > 0 else ""
     print(f"   {f}:{l:4d} instr {100 * ex[loc] / tot:5.2f}% samples {100 * v / ts:5.2f}% | {text}")
 
 # ---- optional: samples grouped by code region of step_kernel.cuh (line ranges given as name:lo-hi,...)
-if len(sys.argv) > 4:
+if len(sys.argv) > 4 and sys.argv[4]:
     regions = []
     for item in sys.argv[4].split(","):
         name, rng = item.split(":"); lo, hi = rng.split("-"); regions.append((name, int(lo), int(hi)))
@@ -72,7 +79,7 @@ if len(sys.argv) > 4:
     for loc, v in sm.items():
         f, l = loc if loc else ("?", 0)
         key = "other-file:" + f
-        if f == "step_kernel.cuh":
+        if f == srcname:
             key = "unassigned"
             for name, lo, hi in regions:
                 if lo <= l <= hi:
