@@ -76,17 +76,21 @@ class BatchedKuramoto:
         table = None if force_dense else coupling_table(p0["neur_coords"], p0["neur_grid"], p0["grid_size"],
                                                         p0["spatial_kernel"], p0["wavelet_amp"],
                                                         p0["wavelet_steepness"])
-        alpha = None
+        alpha = lowrank = None
+        if coupling_eval not in ("auto", "exact", "spectral"):
+            raise ValueError("coupling_eval must be 'auto', 'exact' or 'spectral'")
         if table is None:
             alpha = coupling_rows(p0["neur_coords"], np.arange(self.n_osc), p0["spatial_kernel"],
                                   p0["wavelet_amp"], p0["wavelet_steepness"])
+            if coupling_eval != "exact" and precision == "f32":
+                # any neuron ordering (utils.py:490 shuffle=True, partial grids): alpha in its truncated eigenbasis
+                from .geometry import lowrank_factors
+                lowrank = lowrank_factors(alpha, tol=spectral_tol)
         self.engine = KuramotoEngine(B, self.n_osc, p0["grid_size"], self.window, p0["K"],
-                                     precision=precision, coupling_table=table, alpha=alpha, device=device,
+                                     precision=precision, coupling_table=table, alpha=alpha, lowrank=lowrank, device=device,
                                      max_step_samples=max(self.schedule.max_samples, 20),
                                      action_bounds=p0["dbs_action_bounds"], options=engine_options)
-        if coupling_eval not in ("auto", "exact", "spectral"):
-            raise ValueError("coupling_eval must be 'auto', 'exact' or 'spectral'")
-        self.coupling_eval = "exact"
+        self.coupling_eval = "lowrank" if lowrank is not None else "exact"
         grid888 = table is not None and [int(g) for g in p0["grid_size"]] == [8, 8, 8] and self.n_osc == 512
         if coupling_eval != "exact" and precision == "f32" and grid888 and not (engine_options or {}).get("no_sym"):
             from .geometry import spectral_factors
@@ -94,8 +98,9 @@ class BatchedKuramoto:
             if max(ranks) <= 9:
                 self.engine.set_coupling_spectral(vecs, vals, ranks, residual)
                 self.coupling_eval = "spectral"
-        if coupling_eval == "spectral" and self.coupling_eval != "spectral":
-            raise ValueError("coupling_eval='spectral' needs float32 on the regular 8 x 8 x 8 grid with at most 9 modes per sector")
+        if coupling_eval == "spectral" and self.coupling_eval == "exact":
+            raise ValueError("coupling_eval='spectral' needs float32 and either the regular 8 x 8 x 8 grid with at most 9 modes "
+                             "per sector or a dense operator with at most 256 modes above spectral_tol")
         self.engine.set_recording(p0["recording_kernel"] == "gaussian")
         self.engine.set_schedule(self.schedule)
         self.engine.set_reward(p0["reward_func"], p0["verbose_dt"])

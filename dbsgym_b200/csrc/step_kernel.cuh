@@ -90,6 +90,9 @@ struct StepParams {
     // spectral coupling (CPL_SPECTRAL): eigenvectors per worker thread [64][4 * (RE + RO)] and the eigenvalues, already
     // multiplied by K / (8 N), one per reduction slot [4 * (RE + RO)] (see spectral_contract below)
     const float* spec_v; const float* spec_lam;
+    // low-rank coupling (CPL_LOWRANK): eigenvectors [lr_rank][Np] (mode-major, rows padded to a multiple of 4 with zeros)
+    // and eigenvalues [lr_rank] of a DENSE alpha (see couple_lowrank_* below)
+    const float* lr_v; const float* lr_lam; int lr_rank;
     double* trace; int32_t* trace_len; int trace_cap;   // optional recording of the TRUE LFP of every step (evaluation)
     double power_scale, action_cost, threshold, threshold_penalty;
     // cluster mode (one environment = a thread-block cluster of `cluster` CTAs, N > 4096)
@@ -829,6 +832,68 @@ __device__ __forceinline__ void couple_dense(const real* __restrict__ sc, const 
     }
 }
 
+// ---- coupling contraction, LOWRANK mode: the generalised mean-field identity for ANY symmetric alpha ---------------
+// alpha ~ sum_m lam_m v_m v_m^T over the eigenpairs above a truncation threshold (geometry.lowrank_factors: a smooth
+// kernel of a compact neuron cloud has a few dozen of them whatever the ordering of the neurons -- env.py:219-229,
+// utils.py:483-497 with shuffle=True).  (alpha s)_i = sum_m v_m[i] C_m,  C_m = lam_m sum_j v_m[j] (s_j, c_j):
+// O(N R) instead of O(N^2) per evaluation and R N floats of operator instead of N^2.
+// Phase 1, warps over modes (four at a time): V rows stream from global / L2 (coalesced), the (sin, cos) operand comes
+// from shared memory, one shuffle reduction per mode and warp.  Phase 2, threads over their 8 oscillators.
+__device__ __forceinline__ void couple_lowrank_project(const float* __restrict__ sc, const float* __restrict__ V,
+                                                       const float* __restrict__ lam, int R4, int Np, float2* __restrict__ Cs,
+                                                       int lane, int warp, int nwarps) {
+    const float4* x4 = reinterpret_cast<const float4*>(sc);
+    const int n4 = Np >> 2;
+    for (int m0 = warp * 4; m0 < R4; m0 += nwarps * 4) {
+        float2 acc[4];
+        const float4* v4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { acc[q] = make_float2(0.f, 0.f); v4[q] = reinterpret_cast<const float4*>(V + (size_t)(m0 + q) * Np); }
+#pragma unroll 2
+        for (int j4 = lane; j4 < n4; j4 += 32) {
+            const float4 xa = x4[2 * j4], xb = x4[2 * j4 + 1];          // (s, c) of oscillators 4 j4 .. 4 j4 + 3
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 v = __ldg(v4[q] + j4);
+                acc[q] = __ffma2_rn(make_float2(v.x, v.x), make_float2(xa.x, xa.y), acc[q]);
+                acc[q] = __ffma2_rn(make_float2(v.y, v.y), make_float2(xa.z, xa.w), acc[q]);
+                acc[q] = __ffma2_rn(make_float2(v.z, v.z), make_float2(xb.x, xb.y), acc[q]);
+                acc[q] = __ffma2_rn(make_float2(v.w, v.w), make_float2(xb.z, xb.w), acc[q]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o);
+                acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
+            }
+        }
+        if (lane < 4) {
+            const float2 a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+            const float l = __ldg(lam + m0 + lane);
+            Cs[m0 + lane] = make_float2(l * a.x, l * a.y);
+        }
+    }
+}
+__device__ __forceinline__ void couple_lowrank_expand(const float2* __restrict__ Cs, const float* __restrict__ V, int R4, int Np,
+                                                      int i0, float (&as)[kRows], float (&ac)[kRows]) {
+    float2 acc[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) acc[r] = make_float2(0.f, 0.f);
+    const float* col = V + i0;
+#pragma unroll 4
+    for (int m = 0; m < R4; ++m) {
+        float v[kRows];
+        loadv<kRows>(col + (size_t)m * Np, v);
+        const float2 c = Cs[m];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) acc[r] = __ffma2_rn(make_float2(v[r], v[r]), c, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) { as[r] = acc[r].x; ac[r] = acc[r].y; }
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -944,7 +1009,7 @@ template <typename real, int MAXT> struct MinBlocks {
     static constexpr int v = (sizeof(real) == 4 && MAXT <= 128) ? (DBSGYM_MINB64 * 64 / MAXT) : 1;
 };
 
-enum { CPL_GRID = 0, CPL_DENSE = 1, CPL_GRID_SYM = 2, CPL_SPECTRAL = 3 };
+enum { CPL_GRID = 0, CPL_DENSE = 1, CPL_GRID_SYM = 2, CPL_SPECTRAL = 3, CPL_LOWRANK = 4 };
 #ifndef DBSGYM_SC_BUFFERS
 #define DBSGYM_SC_BUFFERS 2
 #endif
@@ -977,7 +1042,9 @@ __host__ __device__ inline size_t step_smem_bytes_worker(int Np, int op_floats =
 // become cluster-scope (barrier.cluster release/acquire + a few doubles of global scratch).
 template <typename real, int CPL, int MAXT, int GEO = 0, int CL = 0, int EPC = 1, int RE = 1, int RO = 1>
 __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p) {
-    constexpr bool DENSE = CPL == CPL_DENSE;
+    constexpr bool LR = CPL == CPL_LOWRANK;           // low-rank form of a DENSE operator: same thread layout and operand
+    constexpr bool DENSE = CPL == CPL_DENSE || LR;
+    static_assert(!LR || (sizeof(real) == 4 && CL == 0 && EPC == 1), "low-rank coupling: fp32, one CTA per environment");
     constexpr bool SPEC = CPL == CPL_SPECTRAL;      // spectral contraction: multi-worker hosting, parity-sector thread layout
     constexpr bool SYM = CPL == CPL_GRID_SYM || SPEC;
     constexpr bool MW = EPC > 1;       // multi-worker mode: EPC environments per CTA, one 64-thread worker each
@@ -999,7 +1066,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     const int NC_ = CL ? p.cluster : 1;                   // CTAs per environment
     const int crank = CL ? (int)(blockIdx.x % NC_) : 0;   // rank of this CTA in its cluster (1-D grid, cluster dims (C,1,1))
     const int Nl = CL ? nt * kRows : Np;                  // oscillators whose state lives in THIS CTA's (worker's) shared memory
-    const int tab = (DENSE || CL || MW) ? 0 : GZ * GX * GY;
+    const int tab = LR ? 2 * p.lr_rank : (DENSE || CL || MW) ? 0 : GZ * GX * GY;     // (LR: the mode coefficients C live there)
     const int scsz = 2 * Np + kScPad;
 
     // shared memory of this CTA (MW: the coefficient table, then one such block per worker)
@@ -1236,7 +1303,14 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                 }
                 if (CL) cluster_barrier(); else if (!SPEC) env_sync();
                 real as[kRows], ac[kRows];
-                if (DENSE) couple_dense<real>(SC + pbuf * scsz, reinterpret_cast<const real*>(p.alpha), Np, i0, as, ac);
+                if constexpr (LR) {
+                    float2* Cs = reinterpret_cast<float2*>(Ts);
+                    couple_lowrank_project(reinterpret_cast<const float*>(SC + pbuf * scsz), p.lr_v, p.lr_lam, p.lr_rank, Np, Cs,
+                                           lane, warp, nwarps);
+                    env_sync();
+                    couple_lowrank_expand(Cs, p.lr_v, p.lr_rank, Np, i0, reinterpret_cast<float(&)[kRows]>(as),
+                                          reinterpret_cast<float(&)[kRows]>(ac));
+                } else if (DENSE) couple_dense<real>(SC + pbuf * scsz, reinterpret_cast<const real*>(p.alpha), Np, i0, as, ac);
                 else if (SYM) {
                     if constexpr (SPEC) {
                         spectral_contract<RE, RO>(reinterpret_cast<const float(&)[2 * kRows]>(scw), Ve, Vo, lam_r,

@@ -41,15 +41,15 @@ def _f64(a, shape=None):
 
 class KuramotoEngine:
     def __init__(self, n_envs, n_osc, grid_size, window, K, *, precision="f32", coupling_table=None,
-                 alpha=None, device=0, max_step_samples=20, rtol=1e-5, atol=1e-5, dt0=0.05,
+                 alpha=None, lowrank=None, device=0, max_step_samples=20, rtol=1e-5, atol=1e-5, dt0=0.05,
                  action_bounds=(-5.0, 5.0), max_steps=4096, options=None):
         """``options``: tuning / diagnostic switches of DbsGymConfig (include/dbsgym.h) -- ``mw`` (None auto, False
         never, True always use the multi-worker step kernel), ``force_cluster``, ``ctas_per_sm`` and the boolean A/B
         switches ``no_geo1``, ``no_sym``, ``no_fsal_reuse``, ``no_fused_obs``, ``no_fast_obs``, ``no_warp_kernel``."""
         if precision not in ("f32", "f64"):
             raise ValueError("precision must be 'f32' or 'f64'")
-        if (coupling_table is None) == (alpha is None):
-            raise ValueError("give exactly one of coupling_table (GRID) or alpha (DENSE)")
+        if (coupling_table is None) == (alpha is None and lowrank is None):
+            raise ValueError("give exactly one of coupling_table (GRID) or alpha / lowrank (DENSE)")
         self.lib = _capi.load()
         self.n_envs, self.n_osc, self.window = int(n_envs), int(n_osc), int(window)
         self.precision = precision
@@ -91,13 +91,16 @@ class KuramotoEngine:
         if coupling_table is not None:
             t = _f64(coupling_table)
             self._ck(self.lib.dbsgym_set_coupling_grid(self._h, _capi.ptr(t)))
-        else:
+        elif alpha is not None:
             a = _f64(alpha, (self.n_osc, self.n_osc))
             if not np.array_equal(a, a.T):
                 raise ValueError("dense coupling must be symmetric")
             self._ck(self.lib.dbsgym_set_coupling_dense(self._h, _capi.ptr(a)))
         self.schedule = None
         self.spectral = None
+        self.lowrank = None
+        if lowrank is not None:                      # (vecs [r][N], vals [r], residual): the operator in low-rank form
+            self.set_coupling_lowrank(lowrank[0], lowrank[1], lowrank[2] if len(lowrank) > 2 else None)
 
     def set_coupling_spectral(self, vecs, vals, ranks, residual=None):
         """Switch the GRID operator to its spectral form (dbsgym.h: dbsgym_set_coupling_spectral).  ``vecs`` [8][64][r_max],
@@ -111,6 +114,18 @@ class KuramotoEngine:
         assert r8.shape == (8,)
         self._ck(self.lib.dbsgym_set_coupling_spectral(self._h, _capi.ptr(r8), int(v.shape[2]), _capi.ptr(v), _capi.ptr(w)))
         self.spectral = {"ranks": [int(r) for r in ranks], "modes": int(sum(ranks)), "residual": residual}
+
+    def set_coupling_lowrank(self, vecs, vals, residual=None):
+        """Switch a DENSE fp32 handle to the low-rank form of its operator (dbsgym.h: dbsgym_set_coupling_lowrank).
+        ``vecs`` [rank][n_osc], ``vals`` [rank] as returned by geometry.lowrank_factors; ``vecs=None`` switches back."""
+        if vecs is None:
+            self._ck(self.lib.dbsgym_set_coupling_lowrank(self._h, 0, None, None))
+            self.lowrank = None
+            return
+        v, w = _f64(vecs), _f64(vals)
+        assert v.ndim == 2 and v.shape[1] == self.n_osc and w.shape == (v.shape[0],)
+        self._ck(self.lib.dbsgym_set_coupling_lowrank(self._h, int(v.shape[0]), _capi.ptr(v), _capi.ptr(w)))
+        self.lowrank = {"rank": int(v.shape[0]), "residual": residual}
 
     # ------------------------------------------------------------------ plumbing
     def _ck(self, rc):

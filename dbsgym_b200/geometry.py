@@ -241,3 +241,54 @@ def spectral_apply(vecs, vals, x, gx, gy, gz):
                     out[(slice(hz, None) if mz else slice(0, hz)), (slice(hx, None) if mx else slice(0, hx)),
                         (slice(hy, None) if my else slice(0, hy))] += blk
     return out.ravel()
+
+
+def lowrank_factors(alpha, tol=1e-9, max_rank=256):
+    """Truncated eigen-decomposition of a symmetric coupling matrix (any neuron ordering): the eigenpairs with
+    ``|lambda| > tol * |lambda|_max``.  Returns (vecs [r][N], vals [r], residual) -- orthonormal eigenvectors as rows,
+    sorted by |eigenvalue|, and ``residual`` = the spectral norm of (alpha - truncated alpha), measured -- or None when more
+    than ``max_rank`` modes would be needed (the operator is not compressible: keep the full matrix).
+    A smooth kernel of a compact neuron cloud (cos(distance) with coord_modif = 0.1: env.py:219-223, utils.py:469-475)
+    has a few dozen such modes whatever the ordering of the neurons (utils.py:490 shuffle=True only permutes the rows).
+    Small matrices are diagonalised in full; larger ones by randomised subspace iteration (the spectrum decays
+    geometrically, so three power iterations resolve every kept mode), O(N^2 r) instead of O(N^3)."""
+    a = np.asarray(alpha, dtype=np.float64)
+    if a.ndim != 2 or a.shape[0] != a.shape[1]:
+        raise ValueError("alpha must be a square matrix")
+    a = 0.5 * (a + a.T)
+    n = a.shape[0]
+    if n <= 1024:
+        w, v = np.linalg.eigh(a)
+    else:
+        rng = np.random.default_rng(0)
+        k = 96
+        while True:
+            k = min(k, n)
+            q = np.linalg.qr(a @ rng.standard_normal((n, k)))[0]
+            for _ in range(3):
+                q = np.linalg.qr(a @ q)[0]
+            w, u = np.linalg.eigh(q.T @ a @ q)
+            v = q @ u
+            # the subspace holds every mode above the threshold once a margin of captured modes lies below it
+            if k == n or np.count_nonzero(np.abs(w) <= tol * np.abs(w).max()) >= 16:
+                break
+            if k > 2 * max_rank + 32:
+                return None
+            k *= 2
+    order = np.argsort(-np.abs(w))
+    w, v = w[order], v[:, order]
+    r = int(np.count_nonzero(np.abs(w) > tol * np.abs(w[0])))
+    if r > max_rank:
+        return None
+    vecs, vals = np.ascontiguousarray(v[:, :r].T), np.ascontiguousarray(w[:r])
+    # spectral norm of what was dropped: power iteration on the residual operator
+    x = np.random.default_rng(1).standard_normal(n)
+    residual = 0.0
+    for _ in range(30):
+        x /= np.linalg.norm(x)
+        y = a @ x - vecs.T @ (vals * (vecs @ x))
+        residual = float(np.linalg.norm(y))
+        if residual == 0.0:
+            break
+        x = y
+    return vecs, vals, residual

@@ -109,7 +109,7 @@ int  dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out);
  * coefficients), 5 cluster mode (N > 4096), 6 GRID_SYM with gx = 8 fixed, 7 / 8 GRID_SYM with lines of 16 / 32 (gy = 16 / 32),
  * 9 spectral contraction (dbsgym_set_coupling_spectral; multi-worker hosting, 64 threads per environment),
  * 10 spectral contraction, one warp per environment with octant ownership (the default when the sector ranks fit a
- * compiled rank list); negative = error code */
+ * compiled rank list), 11 DENSE operator in low-rank form (dbsgym_set_coupling_lowrank); negative = error code */
 int  dbsgym_step_variant(const DbsGymHandle* h, int32_t n_envs);
 void dbsgym_destroy(DbsGymHandle* h);
 /* text of the last error on this handle (h == NULL: last error of a failed create) */
@@ -133,6 +133,14 @@ int dbsgym_set_coupling_dense(DbsGymHandle* h, const double* alpha);
  * the spectral norm of what was dropped).  ranks8 == NULL switches back to the exact sector-block contraction. */
 int dbsgym_set_coupling_spectral(DbsGymHandle* h, const int32_t* ranks8, int32_t r_max,
                                  const double* vecs, const double* vals);
+
+/* Low-rank form of a DENSE operator (fp32 handles): alpha ~ sum_m vals[m] v_m v_m^T with vecs[m * N + i] = v_m[i], the
+ * eigenpairs of alpha (env.py:219-229; any neuron ordering, utils.py:483-497 shuffle=True) the caller keeps
+ * (dbsgym_b200/geometry.py: lowrank_factors returns the spectral norm of what it dropped).  The step kernel then evaluates
+ * the coupling sum of env.py:252-256 as sum_m v_m[i] (cos th_i S_m - sin th_i C_m) -- O(N rank) per evaluation instead of
+ * O(N^2), rank * N floats of operator instead of N^2; dbsgym_set_coupling_dense need not be called at all.
+ * rank <= 0 switches back to the full matrix. */
+int dbsgym_set_coupling_lowrank(DbsGymHandle* h, int32_t rank, const double* vecs, const double* vals);
 
 /* Per-environment vectors uploaded at reset (env.py:566-598): natural frequencies after
  * remove_negative_w0, stimulation conductance of the first contact (env.py:422-423), summed

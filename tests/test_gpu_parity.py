@@ -162,6 +162,40 @@ def test_shuffled_grid_uses_dense_path_and_matches_oracle():
     core.close()
 
 
+def test_shuffled_grid_f32_low_rank_kernel_matches_oracle():
+    """Shuffled coordinates in float32: the DENSE operator runs in its truncated eigenbasis (step-kernel variant 11, 32 modes:
+    a permutation does not change the spectrum) -- teacher-forced steps against the float64 oracle at the float32
+    tolerance, exact counters; coupling_eval='exact' keeps the full matrix (variant 1) and must agree."""
+    from oracle import kuramoto_oracle as ko
+    d = make_params("env1", 4, transient_state_len=118.0)
+    perm = np.random.default_rng(1).permutation(512)
+    d["neur_coords"] = d["neur_coords"][perm]
+    d["neur_grid"] = d["neur_grid"][perm]
+    orc = ko.OracleEnv(copy.deepcopy(d))
+    from dbsgym_b200.batched import BatchedKuramoto
+    cores = {"lowrank": BatchedKuramoto([copy.deepcopy(d)] * 2, precision="f32", transfer="full"),
+             "dense": BatchedKuramoto([copy.deepcopy(d)] * 2, precision="f32", transfer="full", coupling_eval="exact")}
+    assert cores["lowrank"].engine.step_variant() == 11 and cores["lowrank"].coupling_eval == "lowrank"
+    assert cores["lowrank"].engine.lowrank["rank"] == 32
+    assert cores["dense"].engine.step_variant() == 1
+    for core in cores.values():
+        assert np.max(np.abs(core.engine.state()[0] - orc.sol_state[-1])) < 5e-3       # 118-unit transient with rejections
+        core.engine.counters(reset=True)
+    for k, a in enumerate((0.4, -0.7, 0.1, 0.9)):
+        y_before = orc.sol_state[-1].copy()
+        o_ref, r_ref, *_ = orc.step(np.array([a], dtype=np.float32))
+        for name, core in cores.items():
+            core.engine.set_env_params(None, y0=np.tile(y_before, (2, 1)))        # teacher-forced
+            obs, rew, done = core.step(np.array([a, a], dtype=np.float32))
+            err = np.max(np.abs(core.engine.state()[0] - orc.sol_state[-1]))
+            assert err < 1e-5, (name, k, err)
+            assert np.max(np.abs(core.theta_records(0) - orc.theta_records)) < 2e-6
+    for core in cores.values():
+        c = core.engine.counters()
+        assert (c["accepted"], c["rejected"], c["rhs_evals"], c["status"]) == (2 * 4 * 5, 0, 2 * 4 * 32, 0)
+        core.close()
+
+
 def test_half_grid_256_oscillators():
     """N = 256 (first four z-planes, BASELINE config 5's smallest point) on the GRID kernel."""
     from oracle import kuramoto_oracle as ko

@@ -315,3 +315,31 @@ def test_spectral_factors_reproduce_the_coupling_operator():
     v2, w2, r2, res2 = geometry.spectral_factors(table, 8, 8, 8, tol=0.0)
     assert sum(r2) == 512 and res2 == 0.0
     assert np.max(np.abs(geometry.spectral_apply(v2, w2, s, 8, 8, 8) - alpha @ s)) < 1e-11
+
+
+def test_lowrank_factors_reproduce_a_shuffled_operator():
+    """geometry.lowrank_factors (the form the float32 DENSE kernel evaluates, step-kernel variant 11): a shuffled 8 x 8 x 8
+    grid has the 32 modes of the regular one; the measured residual is the true spectral norm of what was dropped; a
+    rough kernel is reported as incompressible; the randomised path (N > 1024) agrees with the full diagonalisation."""
+    from dbsgym_b200 import geometry
+    coords, grid = geometry.neuron_grid(8, 8, 8, 512, 0.1)
+    perm = np.random.default_rng(3).permutation(512)
+    alpha = geometry.coupling_rows(coords[perm], np.arange(512), "cos")
+    vecs, vals, residual = geometry.lowrank_factors(alpha, tol=1e-9)
+    assert vecs.shape == (32, 512) and np.all(np.abs(vals[:-1]) >= np.abs(vals[1:]))
+    rec = vecs.T @ (vals[:, None] * vecs)
+    assert abs(np.linalg.norm(alpha - rec, 2) - residual) < 1e-3 * residual and residual < 1e-9 * np.abs(vals[0])
+    rng = np.random.default_rng(0)
+    th = rng.uniform(0, 2 * np.pi, 512)
+    s, c = np.sin(th), np.cos(th)
+    exact = 0.52 / 512 * (c * (alpha @ s) - s * (alpha @ c))
+    approx = 0.52 / 512 * (c * (rec @ s) - s * (rec @ c))
+    assert np.max(np.abs(exact - approx)) < 1e-10                       # rad per time unit
+    assert geometry.lowrank_factors(np.exp(-40.0 * geometry.distances_from(coords, np.arange(512)) ** 2), tol=1e-9, max_rank=64) is None
+    coords2, _ = geometry.neuron_grid(16, 16, 16, 2048, 0.1)
+    alpha2 = geometry.coupling_rows(coords2, np.arange(2048), "cos")
+    v2, w2, res2 = geometry.lowrank_factors(alpha2, tol=1e-9)
+    wf = np.linalg.eigvalsh(alpha2)
+    wf = wf[np.argsort(-np.abs(wf))]
+    assert len(w2) == np.count_nonzero(np.abs(wf) > 1e-9 * np.abs(wf[0])) and np.allclose(w2, wf[:len(w2)], rtol=1e-6, atol=1e-9 * abs(wf[0]))
+    assert abs(res2 - np.abs(wf[len(w2)])) < 1e-2 * res2
