@@ -205,6 +205,16 @@ def step_kernel_model(variant, rhs_exec, ypar, n_osc=N_OSC):
     profiles/*_flop_count.json holds the ncu-measured count of the same kernel for comparison."""
     N = n_osc
     other = 700 * N                                      # tableau combinations, error norm, dense output, LFP, reward
+    if variant == 10:
+        # spectral kernel, one warp per environment, 32 modes; per LANE (16 oscillators) and RHS evaluation: stage argument
+        # (20 tableau rows per 6 evaluations x 16 FFMA + the y1 add) 109, range reduction of the sincos 16 x 6 = 96, the two
+        # sector transforms 2 x (24 FADD2 + 24 FFMA2) = 288, projection 32 x (FMUL2 + FFMA2) = 192, mode sums
+        # 2 x 17 packed adds / multiplies = 68, expansion 16 FMUL2 + 48 FFMA2 = 224, k = c0 + c A s - s A c 64;
+        # per lane and RK sub-step: error estimate 288, y1 - y0 160, dense-output coefficients 384, 3.6 LFP samples x 16 x 16,
+        # accept 64 (profiles/r02_step_kernel_variant10_counts.json: the SASS execution counts give 1.37 Mflop per env-step)
+        per_lane_rhs = 109 + 96 + 288 + 192 + 68 + 224 + 64
+        per_lane_substep = 288 + 160 + 384 + 920 + 64
+        return (rhs_exec * per_lane_rhs + 5 * per_lane_substep) * 32, "spectral, one warp per environment (32 modes, 7 + 4 x 6 + 1 over the parity sectors)"
     if variant == 9:
         # spectral kernel, compiled ranks (9 even, 4 odd), per thread (8 oscillators) and RHS evaluation:
         # projection 13 x (FMUL2 + 3 FFMA2) = 182, row sums 52 x (15 FADD2 + FMUL2) / 64 = 26, expansion 4 x (FMUL2 + 8 FFMA2)
@@ -401,7 +411,10 @@ def run_gpu_arm(args):
                        3: "step_kernel<float,GRID_SYM,8x8x8" + (",y-parity>" if ypar else ">"),
                        4: "step_kernel<float,GRID_SYM,8x8x8,y-parity,multi-worker (8 envs per CTA, precomputed sector coefficients)>",
                        5: "step_kernel<cluster>", 6: "step_kernel<float,GRID_SYM,gx=8>",
-                       9: "step_kernel<float,SPECTRAL,8x8x8 (generalised mean-field identity, 8 envs per CTA)>"}.get(variant, "step_kernel")
+                       9: "step_kernel<float,SPECTRAL,8x8x8 (generalised mean-field identity, 8 envs per CTA)>",
+                       10: "warp_step_kernel<RankSet<7,4,4,4,4,4,4,1>> (generalised mean-field identity, one warp per environment, "
+                           "octant ownership, 8 environments per SM)",
+                       11: "step_kernel<float,LOWRANK> (any operator in its truncated eigenbasis)"}.get(variant, "step_kernel")
         k_step = float(np.mean([m[0] for m in kern_ms])) * 1e-3
         k_obs = float(np.mean([m[1] for m in kern_ms])) * 1e-3
         peaks, peak_src = measured_peaks()
@@ -458,6 +471,8 @@ def run_gpu_arm(args):
                          "dense_equivalent_tflops": dense_flop_per_env_step * B / k_step / 1e12,
                          "peak_source": "best of the FFMA and FFMA2 micro-benchmarks run in this process (dbsgym_measure_fp32_peak_mode); nominal 74.4",
                          "peak_ffma": peak_ffma, "peak_ffma2": peak_ffma2,
+                         "ncu_pipes": {k: (counts or {}).get(k) for k in ("issue_slots_busy_pct", "fma_pipe_cycles_active_pct", "xu_pipe_inst_pct",
+                                                                          "lsu_pipe_inst_pct", "warps_active_pct", "registers_per_thread")},
                          "issue": {"warp_instructions_per_env_step_ncu": (counts or {}).get("warp_inst_per_env_step"),
                                    "frac_of_issue_slots": ((counts or {}).get("warp_inst_per_env_step") or 0) * B / k_step /
                                                           (4 * 148 * (clk.get("sm_mhz") or 1965.0) * 1e6) or None,

@@ -103,6 +103,7 @@ struct DbsGymHandle {
     float* wspec_v = nullptr; float* wspec_lam = nullptr; int warp_set = -1; bool no_warp = false;
     // low-rank form of a DENSE operator (dbsgym_set_coupling_lowrank): eigenvectors [lr_rank][Np], eigenvalues [lr_rank]
     float* lr_v = nullptr; float* lr_lam = nullptr; int lr_rank = 0;
+    float2* lr_part = nullptr;           // cluster mode: per-CTA mode sums [B][2][cluster][lr_rank]
     unsigned long long n_launches = 0;   // kernels launched by this handle (dbsgym_launch_count)
     // ordering between the private stream and caller streams (dbsgym_step / dbsgym_transient on a user stream)
     cudaEvent_t ev_own = nullptr, ev_user = nullptr; bool user_pending = false;
@@ -323,13 +324,13 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
     p.fsal_on = h->fsal_on ? 1 : 0; p.k_fsal = h->k_fsal; p.fsal_valid = h->fsal_valid;
     const bool warp = h->spec_re > 0 && h->warp_set >= 0;
     p.spec_v = warp ? h->wspec_v : h->spec_v; p.spec_lam = warp ? h->wspec_lam : h->spec_lam;
-    p.lr_v = h->lr_v; p.lr_lam = h->lr_lam; p.lr_rank = h->lr_rank;
+    p.lr_v = h->lr_v; p.lr_lam = h->lr_lam; p.lr_rank = h->lr_rank; p.lr_part = h->lr_part;
     p.power_scale = h->rspec.power_scale; p.action_cost = h->rspec.action_cost;
     p.threshold = h->rspec.threshold; p.threshold_penalty = h->rspec.threshold_penalty;
 }
 
 size_t plain_smem(DbsGymHandle* h, bool dense) {
-    size_t smem = step_smem_bytes(h->Np, dense ? 2 * h->lr_rank : h->tab, h->nthreads, h->rb);
+    size_t smem = step_smem_bytes(h->Np, dense ? 0 : h->tab, h->nthreads, h->rb);
     if (h->ctas_per_sm > 0) {
         // occupancy knob: pad the dynamic shared memory so that exactly ctas_per_sm CTAs fit on an SM
         // (227 KB usable, 1 KB reserved per CTA) -- used to balance the waves of a launch
@@ -352,6 +353,10 @@ int sym_geo(const DbsGymHandle* h, const StepParams& p) {
 cudaError_t launch_step(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
     ++h->n_launches;
     const int t = h->nthreads;
+    if (h->lr_rank > 0 && !h->f64) {                      // the operator in low-rank form (GRID and DENSE handles alike)
+        if (h->cluster > 1) return launch_f32_lowrank_cluster(t, h->cluster, h->lr_rank, p, s);
+        return launch_f32_lowrank(t, step_smem_bytes(h->Np, 2 * h->lr_rank, t, 4), p, s);
+    }
     if (h->cluster > 1) return launch_f32_cluster(p.GY == 2 * kRows ? 3 : p.GY == 4 * kRows ? 4 : 2, t, h->cluster, p, s);
     const bool dense = h->cfg.coupling == DBSGYM_COUPLING_DENSE;
     const size_t smem = plain_smem(h, dense);
@@ -359,7 +364,7 @@ cudaError_t launch_step(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
         if (dense) return launch_f64_dense(t, smem, p, s);
         return h->grid_sym ? launch_f64_sym(t, smem, p, s) : launch_f64_grid(t, smem, p, s);
     }
-    if (dense) return h->lr_rank > 0 ? launch_f32_lowrank(t, smem, p, s) : launch_f32_dense(t, smem, p, s);
+    if (dense) return launch_f32_dense(t, smem, p, s);
     if (!h->grid_sym) return launch_f32_grid(t, smem, p, s);
     if (h->spec_re > 0 && h->warp_set >= 0) return launch_f32_warp(h->warp_set, h->num_sms, p, s);
     if (h->spec_re > 0) return launch_f32_spectral(h->spec_ro, h->num_sms, p, s);
@@ -526,8 +531,9 @@ int dbsgym_abi_version(void) { return DBSGYM_ABI_VERSION; }
 
 int dbsgym_step_variant(const DbsGymHandle* h, int32_t n_envs) {
     if (!h) return DBSGYM_EINVAL;
+    if (h->lr_rank > 0 && !h->f64) return 11;
     if (h->cluster > 1) return 5;
-    if (h->cfg.coupling == DBSGYM_COUPLING_DENSE) return (h->lr_rank > 0 && !h->f64) ? 11 : 1;
+    if (h->cfg.coupling == DBSGYM_COUPLING_DENSE) return 1;
     if (!h->grid_sym) return 0;
     if (h->f64) return 2;
     if (h->spec_re > 0) return h->warp_set >= 0 ? 10 : 9;
@@ -699,7 +705,7 @@ void dbsgym_destroy(DbsGymHandle* h) {
                     h->step_idx, h->episode_len, h->lfp_true, h->lfp_rec, h->u, h->reward, h->done, h->sched_nI,
                     h->sched_nII, h->sched_offI, h->sched_offII, h->ts_dev, h->ids_dev, h->lin_g, h->tw_seed,
                     h->tw_inner, h->spec, h->tw_full, h->k_fsal, h->fsal_valid, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples,
-                    h->cl_operand, h->cl_scratch, h->mpos, h->spec_v, h->spec_lam, h->wspec_v, h->wspec_lam, h->lr_v, h->lr_lam};
+                    h->cl_operand, h->cl_scratch, h->mpos, h->spec_v, h->spec_lam, h->wspec_v, h->wspec_lam, h->lr_v, h->lr_lam, h->lr_part};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->pin_ints) cudaFreeHost(h->pin_ints);
@@ -837,21 +843,23 @@ int dbsgym_set_coupling_dense(DbsGymHandle* h, const double* alpha) {
 
 int dbsgym_set_coupling_lowrank(DbsGymHandle* h, int32_t rank, const double* vecs, const double* vals) {
     if (!h) return DBSGYM_EINVAL;
-    if (h->cfg.coupling != DBSGYM_COUPLING_DENSE) return fail(h, DBSGYM_ESTATE, "handle was created with GRID coupling");
     CU(h, cudaSetDevice(h->cfg.device));
     CU(h, cudaDeviceSynchronize());
     for (float** q : {&h->lr_v, &h->lr_lam}) { if (*q) cudaFree(*q); *q = nullptr; }
+    if (h->lr_part) { cudaFree(h->lr_part); h->lr_part = nullptr; }
     h->lr_rank = 0;
     if (h->fsal_valid) CU(h, cudaMemset(h->fsal_valid, 0, (size_t)h->B * 4));
-    if (rank <= 0) {                                  // back to the full matrix (needs dbsgym_set_coupling_dense)
-        h->have_coupling = h->alpha != nullptr;
+    const bool dense = h->cfg.coupling == DBSGYM_COUPLING_DENSE;
+    if (rank <= 0) {                                  // back to the full operator (DENSE: needs dbsgym_set_coupling_dense)
+        h->have_coupling = dense ? h->alpha != nullptr : h->table != nullptr;
         return DBSGYM_OK;
     }
     if (!vecs || !vals) return fail(h, DBSGYM_EINVAL, "null argument");
     if (h->f64) return fail(h, DBSGYM_ESTATE, "the low-rank contraction serves fp32 handles (fp64 parity mode evaluates the full sum)");
     const int R4 = (rank + 3) / 4 * 4, N = h->N, Np = h->Np;
     if (R4 > 1024) return fail(h, DBSGYM_EINVAL, "rank %d too large (max 1024)", rank);
-    const size_t need = step_smem_bytes(Np, 2 * R4, h->nthreads, h->rb);
+    if (Np % 256 != 0) return fail(h, DBSGYM_ESTATE, "the low-rank kernel needs whole warps of 8-oscillator threads (padded n_osc %d)", Np);
+    const size_t need = h->cluster > 1 ? step_smem_bytes_cluster_lr(h->nthreads, R4) : step_smem_bytes(Np, 2 * R4, h->nthreads, h->rb);
     int max_smem = 0;
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->cfg.device);
     if (need > (size_t)max_smem) return fail(h, DBSGYM_EINVAL, "rank %d needs %zu bytes of shared memory, the device allows %d", rank, need, max_smem);
@@ -864,6 +872,7 @@ int dbsgym_set_coupling_lowrank(DbsGymHandle* h, int32_t rank, const double* vec
     CU(h, cudaMalloc(&h->lr_lam, lam.size() * sizeof(float)));
     CU(h, cudaMemcpy(h->lr_v, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
     CU(h, cudaMemcpy(h->lr_lam, lam.data(), lam.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (h->cluster > 1) CU(h, cudaMalloc(&h->lr_part, (size_t)h->B * 2 * h->cluster * R4 * sizeof(float2)));
     h->lr_rank = R4;
     h->have_coupling = true;
     return DBSGYM_OK;

@@ -93,6 +93,7 @@ struct StepParams {
     // low-rank coupling (CPL_LOWRANK): eigenvectors [lr_rank][Np] (mode-major, rows padded to a multiple of 4 with zeros)
     // and eigenvalues [lr_rank] of a DENSE alpha (see couple_lowrank_* below)
     const float* lr_v; const float* lr_lam; int lr_rank;
+    float2* lr_part;               // cluster mode: [B][2][cluster][lr_rank] per-CTA mode sums (global, L2)
     double* trace; int32_t* trace_len; int trace_cap;   // optional recording of the TRUE LFP of every step (evaluation)
     double power_scale, action_cost, threshold, threshold_penalty;
     // cluster mode (one environment = a thread-block cluster of `cluster` CTAs, N > 4096)
@@ -839,19 +840,20 @@ __device__ __forceinline__ void couple_dense(const real* __restrict__ sc, const 
 // O(N R) instead of O(N^2) per evaluation and R N floats of operator instead of N^2.
 // Phase 1, warps over modes (four at a time): V rows stream from global / L2 (coalesced), the (sin, cos) operand comes
 // from shared memory, one shuffle reduction per mode and warp.  Phase 2, threads over their 8 oscillators.
+// (cluster mode: every CTA sums over its own slice of oscillators [off, off + n) and leaves unscaled partial sums in `out`)
 __device__ __forceinline__ void couple_lowrank_project(const float* __restrict__ sc, const float* __restrict__ V,
-                                                       const float* __restrict__ lam, int R4, int Np, float2* __restrict__ Cs,
-                                                       int lane, int warp, int nwarps) {
+                                                       const float* __restrict__ lam, int R4, int Np, int off, int n,
+                                                       float2* __restrict__ out, int lane, int warp, int nwarps) {
     const float4* x4 = reinterpret_cast<const float4*>(sc);
-    const int n4 = Np >> 2;
+    const int n4 = n >> 2;
     for (int m0 = warp * 4; m0 < R4; m0 += nwarps * 4) {
         float2 acc[4];
         const float4* v4[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { acc[q] = make_float2(0.f, 0.f); v4[q] = reinterpret_cast<const float4*>(V + (size_t)(m0 + q) * Np); }
+        for (int q = 0; q < 4; ++q) { acc[q] = make_float2(0.f, 0.f); v4[q] = reinterpret_cast<const float4*>(V + (size_t)(m0 + q) * Np + off); }
 #pragma unroll 2
         for (int j4 = lane; j4 < n4; j4 += 32) {
-            const float4 xa = x4[2 * j4], xb = x4[2 * j4 + 1];          // (s, c) of oscillators 4 j4 .. 4 j4 + 3
+            const float4 xa = x4[2 * j4], xb = x4[2 * j4 + 1];          // (s, c) of oscillators off + 4 j4 .. + 3
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float4 v = __ldg(v4[q] + j4);
@@ -871,8 +873,8 @@ __device__ __forceinline__ void couple_lowrank_project(const float* __restrict__
         }
         if (lane < 4) {
             const float2 a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
-            const float l = __ldg(lam + m0 + lane);
-            Cs[m0 + lane] = make_float2(l * a.x, l * a.y);
+            const float l = lam ? __ldg(lam + m0 + lane) : 1.f;
+            out[m0 + lane] = make_float2(l * a.x, l * a.y);
         }
     }
 }
@@ -1044,13 +1046,13 @@ template <typename real, int CPL, int MAXT, int GEO = 0, int CL = 0, int EPC = 1
 __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p) {
     constexpr bool LR = CPL == CPL_LOWRANK;           // low-rank form of a DENSE operator: same thread layout and operand
     constexpr bool DENSE = CPL == CPL_DENSE || LR;
-    static_assert(!LR || (sizeof(real) == 4 && CL == 0 && EPC == 1), "low-rank coupling: fp32, one CTA per environment");
+    static_assert(!LR || (sizeof(real) == 4 && EPC == 1 && GEO == 0), "low-rank coupling: fp32, one CTA or one cluster per environment");
     constexpr bool SPEC = CPL == CPL_SPECTRAL;      // spectral contraction: multi-worker hosting, parity-sector thread layout
     constexpr bool SYM = CPL == CPL_GRID_SYM || SPEC;
     constexpr bool MW = EPC > 1;       // multi-worker mode: EPC environments per CTA, one 64-thread worker each
     using SL = SpecLayout<RE, RO>;
     static_assert(!SPEC || (MW && GEO == 1 && sizeof(real) == 4 && CL == 0), "spectral mode: fp32, 8 x 8 x 8 grid, multi-worker");
-    static_assert(CL == 0 || (CPL == CPL_GRID_SYM && (GEO == 2 || GEO == 3 || GEO == 4) && sizeof(real) == 4),
+    static_assert(CL == 0 || LR || (CPL == CPL_GRID_SYM && (GEO == 2 || GEO == 3 || GEO == 4) && sizeof(real) == 4),
                   "cluster mode: fp32 GRID_SYM with gx = 8 or with lines of 16 / 32");
     static_assert(!MW || (SYM && GEO == 1 && sizeof(real) == 4 && CL == 0 && kYParity && MAXT == EPC * kMwThreads),
                   "multi-worker mode: fp32 GRID_SYM on the 8 x 8 x 8 grid with y parity");
@@ -1067,7 +1069,8 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     const int crank = CL ? (int)(blockIdx.x % NC_) : 0;   // rank of this CTA in its cluster (1-D grid, cluster dims (C,1,1))
     const int Nl = CL ? nt * kRows : Np;                  // oscillators whose state lives in THIS CTA's (worker's) shared memory
     const int tab = LR ? 2 * p.lr_rank : (DENSE || CL || MW) ? 0 : GZ * GX * GY;     // (LR: the mode coefficients C live there)
-    const int scsz = 2 * Np + kScPad;
+    constexpr bool CLG = CL != 0 && !LR;                  // cluster mode with the operand of the whole environment in global memory
+    const int scsz = 2 * ((CL && LR) ? Nl : Np) + kScPad;  // (low-rank cluster mode: every CTA keeps the operand of its own oscillators)
 
     // shared memory of this CTA (MW: the coefficient table, then one such block per worker)
     unsigned char* wsm = smem_raw + (SPEC ? (size_t)wid * step_smem_bytes_worker(Np, SL::floats)
@@ -1075,7 +1078,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     real* K = reinterpret_cast<real*>(wsm);               // [kSlots][Nl] stage derivatives f(y_s), thread-private slots
     real* SCs = K + kSlots * Nl;                          // [kScBuffers][scsz] (sin, cos) contraction operand (not in cluster mode)
     constexpr int SCB = MW ? kMwScBuffers : kScBuffers;   // operand buffers
-    real* Ts = SCs + (CL ? 0 : SPEC ? SL::floats : SCB * scsz);   // [tab]  (SPEC: SCs holds the partials P and the coefficients C)
+    real* Ts = SCs + (CLG ? 0 : SPEC ? SL::floats : SCB * scsz);   // [tab]  (SPEC: SCs holds the partials P and the coefficients C)
     real* RC = Ts + tab;                                  // [Nl] recording conductance (thread-private slots; MW: read from global)
     int* WD = reinterpret_cast<int*>(RC + (MW ? 0 : Nl)); // [Nl] fp32 mode: winding counts, y = phase + 2*pi*wind
     double* part = reinterpret_cast<double*>(WD + Nl);    // [nwarps][kSampleBatch][2]
@@ -1084,7 +1087,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     int* t_pos = reinterpret_cast<int*>(t_delta + 32);    // [36]
     // cluster mode: operand tile [4 sectors][TZ planes] (kClTileFloats + 16 floats), 16-byte aligned
     float* cl_tile = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(t_pos + 36) + 15) & ~uintptr_t(15));
-    const real* T = CL ? reinterpret_cast<const real*>(p.table) : Ts;
+    const real* T = CLG ? reinterpret_cast<const real*>(p.table) : Ts;
     const float4* U4 = reinterpret_cast<const float4*>(smem_raw);       // MW: [16][2][64] sector coefficients
 
     // barrier over the threads that integrate one environment
@@ -1117,7 +1120,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     } else if (!DENSE) {
         zi = tid / GX; xi = tid % GX;
     }
-    const int i0 = DENSE ? k0 : (zi * GX + xi) * GY + chunk * kRows; // first oscillator index in the global arrays
+    const int i0 = DENSE ? tid_g * kRows : (zi * GX + xi) * GY + chunk * kRows; // first oscillator index in the global arrays
     const unsigned wmask = __activemask();
     // operand slot written by this thread: plain = own line; GRID_SYM = sector img, line q
     const int sec_stride = (GZ >> 1) * (GX >> 1) * CH * 2 * kRows + (int)(16 / sizeof(real));
@@ -1158,9 +1161,9 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
     for (; slot < p.n_launch; slot += slot_stride) {      // (in cluster mode whole clusters leave together)
     const int env = p.env_ids ? p.env_ids[slot] : slot;
     const size_t base = (size_t)env * Np;
-    real* SC = CL ? reinterpret_cast<real*>(p.cl_operand) + (size_t)env * 2 * scsz : SCs;
+    real* SC = CLG ? reinterpret_cast<real*>(p.cl_operand) + (size_t)env * 2 * scsz : SCs;
     double* cls = CL ? p.cl_scratch + (size_t)env * 2 * NC_ * kClSlots : nullptr;
-    int cl_par = 0;
+    int cl_par = 0, lr_par = 0;
 
     // Register diet: only y0 and (per segment) c0 = w0 + amp * stim stay in registers across the
     // contraction; the recording conductance and the winding counts live in thread-private shared slots.
@@ -1301,12 +1304,30 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                     }
                     if (!SPEC) storev<2 * kRows>(SC + pbuf * scsz + sc_slot, scw);
                 }
-                if (CL) cluster_barrier(); else if (!SPEC) env_sync();
+                if (CLG) cluster_barrier(); else if (!SPEC) env_sync();
                 real as[kRows], ac[kRows];
                 if constexpr (LR) {
                     float2* Cs = reinterpret_cast<float2*>(Ts);
-                    couple_lowrank_project(reinterpret_cast<const float*>(SC + pbuf * scsz), p.lr_v, p.lr_lam, p.lr_rank, Np, Cs,
-                                           lane, warp, nwarps);
+                    if constexpr (CL != 0) {
+                        // every CTA of the cluster sums over its own oscillators; the partial sums meet in global memory (L2)
+                        // and every CTA adds them in the same order, so all CTAs expand with identical coefficients
+                        float2* part_g = p.lr_part + ((size_t)env * 2 + lr_par) * NC_ * p.lr_rank;
+                        couple_lowrank_project(reinterpret_cast<const float*>(SC + pbuf * scsz), p.lr_v, nullptr, p.lr_rank, Np,
+                                               crank * Nl, Nl, part_g + (size_t)crank * p.lr_rank, lane, warp, nwarps);
+                        cluster_barrier();
+                        for (int m = tid; m < p.lr_rank; m += nt) {
+                            float2 a = make_float2(0.f, 0.f);
+                            for (int r = 0; r < NC_; ++r) {
+                                const float2 b = __ldcg(part_g + (size_t)r * p.lr_rank + m);
+                                a.x += b.x; a.y += b.y;
+                            }
+                            const float l = __ldg(p.lr_lam + m);
+                            Cs[m] = make_float2(l * a.x, l * a.y);
+                        }
+                        lr_par ^= 1;
+                    } else
+                        couple_lowrank_project(reinterpret_cast<const float*>(SC + pbuf * scsz), p.lr_v, p.lr_lam, p.lr_rank, Np,
+                                               0, Np, Cs, lane, warp, nwarps);
                     env_sync();
                     couple_lowrank_expand(Cs, p.lr_v, p.lr_rank, Np, i0, reinterpret_cast<float(&)[kRows]>(as),
                                           reinterpret_cast<float(&)[kRows]>(ac));
@@ -1316,7 +1337,7 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                         spectral_contract<RE, RO>(reinterpret_cast<const float(&)[2 * kRows]>(scw), Ve, Vo, lam_r,
                                                   reinterpret_cast<float*>(SCs), reinterpret_cast<float*>(SCs) + 4 * SL::PS, tid, img,
                                                   qline, wid, reinterpret_cast<float(&)[kRows]>(as), reinterpret_cast<float(&)[kRows]>(ac));
-                    } else if constexpr (CL != 0) {
+                    } else if constexpr (CLG) {
                         // Cluster mode: the operand of the whole environment sits in global memory (L2).  Every CTA
                         // stages it through its own shared memory in tiles of whole source z-planes (one cooperative,
                         // coalesced copy per tile and CTA instead of every warp fetching every line from L2), the
@@ -1627,6 +1648,14 @@ inline size_t step_smem_bytes_cluster(int nthreads, size_t real_bytes) {
     return (size_t)((kSlots + 1) * Nl) * real_bytes + (size_t)Nl * sizeof(int) +
            (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 36 * sizeof(int) +
            (size_t)(kClTileFloats + 16) * sizeof(float) + 16;
+}
+
+// low-rank cluster mode: K slots, the double-buffered operand of the CTA's own oscillators, mode coefficients, recording
+// conductance, winding counts, reduction scratch
+inline size_t step_smem_bytes_cluster_lr(int nthreads, int rank4) {
+    const int nwarps = (nthreads + 31) / 32, Nl = nthreads * kRows;
+    return (size_t)((kSlots + 1) * Nl + kScBuffers * (2 * Nl + kScPad) + 2 * rank4) * sizeof(float) + (size_t)Nl * sizeof(int) +
+           (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 36 * sizeof(int) + 64;
 }
 
 inline size_t step_smem_bytes(int Np, int tab, int nthreads, size_t real_bytes) {

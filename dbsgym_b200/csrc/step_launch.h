@@ -12,6 +12,7 @@ cudaError_t launch_f32_sym(int geo, int threads, size_t smem, const StepParams& 
 cudaError_t launch_f32_dense(int threads, size_t smem, const StepParams& p, cudaStream_t s);
 // DENSE operator in low-rank form (dbsgym_set_coupling_lowrank): smem includes 2 * p.lr_rank floats of mode coefficients
 cudaError_t launch_f32_lowrank(int threads, size_t smem, const StepParams& p, cudaStream_t s);
+cudaError_t launch_f32_lowrank_cluster(int threads, int cluster, int rank4, const StepParams& p, cudaStream_t s);
 cudaError_t launch_f64_grid(int threads, size_t smem, const StepParams& p, cudaStream_t s);
 cudaError_t launch_f64_sym(int threads, size_t smem, const StepParams& p, cudaStream_t s);
 cudaError_t launch_f64_dense(int threads, size_t smem, const StepParams& p, cudaStream_t s);

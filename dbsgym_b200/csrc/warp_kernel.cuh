@@ -35,6 +35,16 @@
 #ifndef DBSGYM_WARP_VSMEM
 #define DBSGYM_WARP_VSMEM 0
 #endif
+// A/B switches of the per-environment prologue / epilogue
+#ifndef DBSGYM_WARP_PREFETCH
+#define DBSGYM_WARP_PREFETCH 1       // pull the next environment's rows into L2 while this one is integrated
+#endif
+#ifndef DBSGYM_WARP_HOIST
+#define DBSGYM_WARP_HOIST 0          // fetch w0 / stim together with the state instead of at the first segment (measured: 0.245 -> 0.271 ms, register pressure)
+#endif
+#ifndef DBSGYM_WARP_TAIL2
+#define DBSGYM_WARP_TAIL2 1          // warp-kernel observation tail (samples from shared memory, spread twiddle loop)
+#endif
 
 namespace dbsgym {
 
@@ -76,7 +86,7 @@ template <class RK> struct WarpLayout {
     static_assert(NM % 2 == 0 && c_floats % 4 == 0, "modes come in pairs");
     static_assert(p_floats >= 8 * 68, "the partials buffer also holds the lane sums of 8 LFP samples");
     // bytes of one warp's shared memory: K slots, partials + coefficients, winding counts, w0 + pulse, tail scratch
-    static constexpr size_t bytes = (size_t)(kSlots * 512 + p_floats + c_floats + 512 + 512) * 4 + (32 + 2 * kWarpTs) * 8 + 36 * 4 + 8;
+    static constexpr size_t bytes = (size_t)(kSlots * 512 + p_floats + c_floats + 512 + 512 + 32) * 4 + (32 + 2 * kWarpTs) * 8 + 36 * 4 + 8;
     static constexpr size_t bytes_aligned = (bytes + 15) & ~(size_t)15;
     static constexpr size_t cta_bytes(int warps) { return v_bytes + (size_t)warps * bytes_aligned; }
 };
@@ -205,6 +215,87 @@ __device__ __forceinline__ void wsincos(float x, float* s, float* c) { sincosf(x
 __device__ __forceinline__ float wcos(float x) { return cosf(x); }
 #endif
 
+// Observation tail of the warp kernel: obs_tail (step_kernel.cuh; env.py:447-454, :638-650, :669-688) with the step's samples
+// taken from shared memory instead of read back from global memory, and the twiddle products of the running rfft bins
+// spread over all 32 lanes (lane = (sample group, bin): with 10 bins three groups share the samples) instead of one lane
+// per bin walking all samples -- the tail is a pure latency chain, so its length is what it costs.
+__device__ __forceinline__ void wobs_tail(const StepParams& p, int env, int lane, int S, double* t_delta, int* t_pos,
+                                          const float* LF, double u) {
+    const int W = p.W, nb = p.tail_nbins;
+    float* ring = reinterpret_cast<float*>(p.ring) + (size_t)env * W;
+    const int head = t_pos[32];
+    const double2* tw = reinterpret_cast<const double2*>(p.tw_full);
+    if (lane < S) {
+        const int pos = t_pos[lane];
+        const float v = LF[lane];
+        ring[pos] = v;
+        if (p.samples_f) p.samples_f[(size_t)env * p.smax + lane] = v;
+        if (p.mirror) {                               // zero-copy store into the pinned host mirror (both copies)
+            float* mr = p.mirror + (size_t)env * 2 * p.mir_len;
+            int c = t_pos[33] + lane;
+            if (c >= p.mir_len) c -= p.mir_len;
+            mr[c] = v;
+            mr[c + p.mir_len] = v;
+        }
+        t_delta[lane] = (double)v - t_delta[lane];
+        if (p.trace) {                                // evaluation trace: theta_mean of the step (env.py:441)
+            const int at = p.trace_len[env] + lane;
+            if (at < p.trace_cap) p.trace[(size_t)env * p.trace_cap + at] = p.lfp_true[(size_t)env * p.smax + lane];
+        }
+    }
+    __syncwarp();
+    const int G = nb > 0 ? 32 / nb : 1;               // sample groups
+    const int g = nb > 0 ? lane / nb : 0, b = nb > 0 ? lane - g * nb : 0;
+    double re = 0.0, im = 0.0;
+    if (g < G) {
+#pragma unroll 4
+        for (int j = g; j < S; j += G) {
+            const double2 w = tw[(size_t)t_pos[j] * nb + b];
+            re = fma(t_delta[j], w.x, re);
+            im = fma(t_delta[j], w.y, im);
+        }
+    }
+    for (int k = 1; k < G; ++k) {                     // (uniform trip count; lanes >= nb do not use the result)
+        const double r2 = __shfl_sync(0xffffffffu, re, (lane + k * nb) & 31), i2 = __shfl_sync(0xffffffffu, im, (lane + k * nb) & 31);
+        if (lane < nb) { re += r2; im += i2; }
+    }
+    double pw = 0.0;
+    if (lane < nb) {
+        double2* sp = reinterpret_cast<double2*>(p.spec) + (size_t)env * kTailBins + lane;
+        double2 X = *sp;
+        X.x += re; X.y += im;
+        *sp = X;
+        const double a = X.x / (double)W, c = X.y / (double)W;
+        pw = (a * a + c * c) * 2.0;                   // utils.py:21-27: one-sided power of bin k
+    }
+    pw = warp_sum(pw);
+    if (lane == 0) {
+        const double au = fabs(u);
+        double r;
+        if (p.tail_kind == 0) r = -p.power_scale * pw - p.action_cost * au;                                   // env.py:638-650
+        else r = -((p.power_scale * pw > p.threshold) ? p.threshold_penalty : 0.0) - p.action_cost * au;      // env.py:669-688
+        p.reward[env] = r;
+        if (p.reward_f) p.reward_f[env] = (float)r;
+        const int k = p.step_idx_rw[env] + 1;
+        p.step_idx_rw[env] = k;
+        const uint8_t dn = k >= p.episode_len[env] ? 1 : 0;
+        p.done_dev[env] = dn;
+        if (p.done_out) p.done_out[env] = dn;
+        int nh = head + S;
+        if (nh >= W) nh -= W;
+        p.head[env] = nh;
+        if (p.trace) p.trace_len[env] = min(p.trace_len[env] + S, p.trace_cap);
+        int nm = nh;                                  // reported position: the mirror's write column when it is on
+        if (p.mirror) {
+            nm = t_pos[33] + S;
+            if (nm >= p.mir_len) nm -= p.mir_len;
+            p.mpos[env] = nm;
+        }
+        if (p.nsamp_out) p.nsamp_out[env] = S;
+        if (p.head_out) p.head_out[env] = nm;
+    }
+}
+
 template <class RK>
 __global__ void __maxnreg__(DBSGYM_WARP_MAXNREG) warp_step_kernel(const StepParams p) {
     using L = WarpLayout<RK>;
@@ -221,6 +312,7 @@ __global__ void __maxnreg__(DBSGYM_WARP_MAXNREG) warp_step_kernel(const StepPara
     double* t_delta = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(C0 + 512) + 7) & ~uintptr_t(7));
     double* TS = t_delta + 32;                                // [2][kWarpTs] save times of the two segments of a step
     int* t_pos = reinterpret_cast<int*>(TS + 2 * kWarpTs);
+    float* LF = reinterpret_cast<float*>(t_pos + 36);         // [32] recorded LFP samples of the step (what the window receives)
 
     const OctLane OL(lane);
 
@@ -262,18 +354,41 @@ __global__ void __maxnreg__(DBSGYM_WARP_MAXNREG) warp_step_kernel(const StepPara
     const int env = p.env_ids ? p.env_ids[slot] : slot;
     const size_t base = (size_t)env * p.Np;
 
-    float y0[kWR];
+    // every load that does not depend on another one is issued here, before anything waits: the per-environment scalars, then
+    // the four state vectors of the lane; the rows of the NEXT environment of this warp are pulled into L2 meanwhile
+    const bool step_mode = p.mode == MODE_STEP;
+    const int k_idx = step_mode ? p.step_idx[env] : 0;
+    const float act = step_mode ? p.actions[env] : 0.f;
+    const bool fsal_in = p.fsal_on && step_mode && p.fsal_valid[env] != 0;
+    float y0[kWR], c0v[kWR], stimv[kWR];
     oct_load<float, float2>(reinterpret_cast<const float*>(p.phase) + base, OL, y0);
     {
         int wd[kWR];
         oct_load<int, int2>(p.wind + base, OL, wd);
+        if (DBSGYM_WARP_HOIST) {
+            oct_load<float, float2>(reinterpret_cast<const float*>(p.w0) + base, OL, c0v);
+            oct_load<float, float2>(reinterpret_cast<const float*>(p.stim) + base, OL, stimv);
+        }
 #pragma unroll
         for (int r = 0; r < kWR; ++r) WD[r * 32 + lane] = wd[r];
+    }
+    {
+        const int nslot = slot + (int)gridDim.x * nwarp;
+        if (DBSGYM_WARP_PREFETCH && nslot < p.n_launch && lane < 16) {
+            const int nenv = p.env_ids ? p.env_ids[nslot] : nslot;
+            const size_t nb_ = (size_t)nenv * p.Np * 4 + (size_t)lane * 128;          // 512 floats = 16 lines of 128 bytes per row
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.phase) + nb_));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.wind) + nb_));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.w0) + nb_));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.stim) + nb_));
+            if (p.fsal_on) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.k_fsal) + nb_));
+            if (p.weighted_rec) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.rec) + nb_));
+        }
     }
     unsigned int n_acc = 0, n_rej = 0, n_rhs = 0, n_reuse = 0;
     bool k0_valid = false;                                // K slot 0 holds f(y0) for pulse amplitude amp_k0
     float amp_k0 = 0.f;
-    if (p.fsal_on && p.mode == MODE_STEP && p.fsal_valid[env]) {
+    if (fsal_in) {
         float k[kWR];
         wload16(reinterpret_cast<const float*>(p.k_fsal) + base, lane, k);      // (kept in this kernel's private layout)
         wstore16(K, lane, k);
@@ -283,15 +398,17 @@ __global__ void __maxnreg__(DBSGYM_WARP_MAXNREG) warp_step_kernel(const StepPara
 
     // ---- segment programme (env.py:415-441 / :605-612) ----
     int nseg;
+    double u_step = 0.0;
     const double* seg_ts[2];
     int seg_nts[2], seg_nrec[2], seg_from[2], seg_out[2];
     float seg_amp[2];
-    if (p.mode == MODE_STEP) {
-        int k = p.step_idx[env];
+    if (step_mode) {
+        int k = k_idx;
         if (k < 0 || k >= p.n_sched) { status |= STATUS_SCHEDULE; k = k < 0 ? 0 : p.n_sched - 1; }
         const int nI = p.sched_nI[k], nII = p.sched_nII[k];
-        const double a = (double)p.actions[env];                            // env.py:389-393 rescale_action, env.py:419
+        const double a = (double)act;                                       // env.py:389-393 rescale_action, env.py:419
         const double u = p.act_lo + ((p.act_hi - p.act_lo) * (a - (-1.0))) / (1.0 - (-1.0));
+        u_step = u;
         if (lane == 0) { p.u_out[env] = u; p.n_samples[env] = nI + nII - 1; }
         nseg = 2;
         seg_ts[0] = p.sched_offI + (size_t)k * p.maxI;   seg_nts[0] = nI;  seg_nrec[0] = nI;
@@ -321,18 +438,19 @@ __global__ void __maxnreg__(DBSGYM_WARP_MAXNREG) warp_step_kernel(const StepPara
         const int n_ts = seg_nts[sg], n_rec = seg_nrec[sg], rec_from = seg_from[sg], out_base = seg_out[sg];
         const float amp = seg_amp[sg];
         {                                     // w0 + pulse, constant over the segment (env.py:254-255, :421-424)
-            float c0[kWR], stim[kWR];
-            oct_load<float, float2>(reinterpret_cast<const float*>(p.w0) + base, OL, c0);
-            oct_load<float, float2>(reinterpret_cast<const float*>(p.stim) + base, OL, stim);
+            if (sg > 0 || !DBSGYM_WARP_HOIST) {  // (the first segment's vectors were fetched with the state; these hit L1 / L2)
+                oct_load<float, float2>(reinterpret_cast<const float*>(p.w0) + base, OL, c0v);
+                oct_load<float, float2>(reinterpret_cast<const float*>(p.stim) + base, OL, stimv);
+            }
 #pragma unroll
-            for (int r = 0; r < kWR; ++r) c0[r] = c0[r] + amp * stim[r];
-            wstore16(C0, lane, c0);
+            for (int r = 0; r < kWR; ++r) c0v[r] = c0v[r] + amp * stimv[r];
+            wstore16(C0, lane, c0v);
             if (k0_valid) {                      // k1 of this segment from the carried k7: only the pulse term changes
                 float k[kWR];
                 wload16(K, lane, k);
                 const float da = amp - amp_k0;
 #pragma unroll
-                for (int r = 0; r < kWR; ++r) k[r] = fmaf(da, stim[r], k[r]);
+                for (int r = 0; r < kWR; ++r) k[r] = fmaf(da, stimv[r], k[r]);
                 wstore16(K, lane, k);
             }
         }
@@ -574,6 +692,7 @@ __global__ void __maxnreg__(DBSGYM_WARP_MAXNREG) warp_step_kernel(const StepPara
                                 if (p.mode == MODE_STEP) {
                                     p.lfp_true[(size_t)env * p.smax + out_base + idx] = a_t;
                                     p.lfp_rec[(size_t)env * p.smax + out_base + idx] = a_r;
+                                    LF[(out_base + idx) & 31] = (float)a_r;
                                 } else {
                                     reinterpret_cast<float*>(p.ring)[(size_t)env * p.W + (idx - rec_from)] = (float)a_r;
                                 }
@@ -623,8 +742,8 @@ __global__ void __maxnreg__(DBSGYM_WARP_MAXNREG) warp_step_kernel(const StepPara
     }
     __syncwarp();                                                    // lane 0's LFP sample stores are visible to the tail's lanes
     if (tail) {
-        __threadfence_block();
-        obs_tail<float>(p, env, lane, seg_nrec[0] + seg_nrec[1], t_delta, t_pos);
+        if (DBSGYM_WARP_TAIL2) wobs_tail(p, env, lane, seg_nrec[0] + seg_nrec[1], t_delta, t_pos, LF, u_step);
+        else { __threadfence_block(); obs_tail<float>(p, env, lane, seg_nrec[0] + seg_nrec[1], t_delta, t_pos); }
     }
     if (p.fsal_on) {
         const bool keep_row = k0_valid && amp_k0 == 0.f;

@@ -165,30 +165,32 @@ class ElectrodeModel:
 # with 52 of the 512 eigenvalues above 1e-12 |lambda_max| on the shipped 8 x 8 x 8 grid (mode 0 IS the classical mean field).
 # alpha commutes with the three reflections of the grid, so every eigenvector lives in one of the 8 parity sectors: the
 # 64 x 64 sector blocks are diagonalised separately (at most 9 modes each).
-def sector_blocks(table, gx, gy, gz):
-    """The 8 parity-sector blocks of the block-Toeplitz operator alpha_ij = table[|dz|, |dx|, |dy|] on a gx*gy*gz grid
-    with even extents.  Sector s = 4 * [odd in y] + 2 * [odd in z] + [odd in x]; block[s][a, b] =
-    sum_g chi_s(g) alpha(a, g b) over the 8 reflections g, with a, b in the fundamental octant, index
-    a = ((zq * gx/2 + xq) * gy/2 + yq).  In the (unnormalised) sector coordinates X_s[b] = sum_g chi_s(g) x[g b] the
-    operator acts as y_s = block[s] @ X_s and (alpha x)[g a] = 1/8 sum_s chi_s(g) y_s[a]."""
+def sector_block(table, gx, gy, gz, s):
+    """Parity-sector block s = 4 * [odd in y] + 2 * [odd in z] + [odd in x] of the block-Toeplitz operator
+    alpha_ij = table[|dz|, |dx|, |dy|] on a gx*gy*gz grid with even extents: block[a, b] = sum_g chi_s(g) alpha(a, g b) over
+    the 8 reflections g, with a, b in the fundamental octant, index a = ((zq * gx/2 + xq) * gy/2 + yq).  In the
+    (unnormalised) sector coordinates X_s[b] = sum_g chi_s(g) x[g b] the operator acts as y_s = block[s] @ X_s and
+    (alpha x)[g a] = 1/8 sum_s chi_s(g) y_s[a]."""
     T = np.asarray(table, dtype=np.float64).reshape(gz, gx, gy)
     hz, hx, hy = gz // 2, gx // 2, gy // 2
     zq, xq, yq = np.meshgrid(np.arange(hz), np.arange(hx), np.arange(hy), indexing="ij")
     zq, xq, yq = zq.ravel(), xq.ravel(), yq.ravel()
-    blocks = []
-    for s in range(8):
-        py, pz, px = (-1.0 if s & 4 else 1.0), (-1.0 if s & 2 else 1.0), (-1.0 if s & 1 else 1.0)
-        blk = np.zeros((zq.size, zq.size))
-        for mz, sz in ((0, 1.0), (1, pz)):
-            zb = gz - 1 - zq if mz else zq
-            for mx, sx in ((0, 1.0), (1, px)):
-                xb = gx - 1 - xq if mx else xq
-                for my, sy in ((0, 1.0), (1, py)):
-                    yb = gy - 1 - yq if my else yq
-                    blk += sz * sx * sy * T[np.abs(zq[:, None] - zb[None, :]), np.abs(xq[:, None] - xb[None, :]),
-                                            np.abs(yq[:, None] - yb[None, :])]
-        blocks.append(blk)
-    return blocks
+    py, pz, px = (-1.0 if s & 4 else 1.0), (-1.0 if s & 2 else 1.0), (-1.0 if s & 1 else 1.0)
+    blk = np.zeros((zq.size, zq.size))
+    for mz, sz in ((0, 1.0), (1, pz)):
+        zb = gz - 1 - zq if mz else zq
+        for mx, sx in ((0, 1.0), (1, px)):
+            xb = gx - 1 - xq if mx else xq
+            for my, sy in ((0, 1.0), (1, py)):
+                yb = gy - 1 - yq if my else yq
+                blk += sz * sx * sy * T[np.abs(zq[:, None] - zb[None, :]), np.abs(xq[:, None] - xb[None, :]),
+                                        np.abs(yq[:, None] - yb[None, :])]
+    return blk
+
+
+def sector_blocks(table, gx, gy, gz):
+    """The 8 parity-sector blocks (see sector_block)."""
+    return [sector_block(table, gx, gy, gz, s) for s in range(8)]
 
 
 def spectral_factors(table, gx, gy, gz, tol=1e-12):
@@ -292,3 +294,44 @@ def lowrank_factors(alpha, tol=1e-9, max_rank=256):
             break
         x = y
     return vecs, vals, residual
+
+
+def grid_lowrank_factors(table, gx, gy, gz, tol=1e-9, max_rank=1024):
+    """lowrank_factors for the block-Toeplitz operator of a regular grid with even extents WITHOUT forming the N x N matrix:
+    every eigenvector of alpha lives in one parity sector (sector_block), so the 8 blocks of size N/8 are factorised one
+    after the other and their eigenvectors z are carried back to the grid, v[g a] = chi_s(g) z[a] / sqrt(8) (same
+    eigenvalue).  Returns (vecs [r][N] in the natural neuron order i = (z * gx + x) * gy + y, vals [r], residual) or None.
+    N = 65536 (32 x 32 x 64) takes 8 blocks of 8192 x 8192 instead of a 34 GB matrix."""
+    hz, hx, hy = gz // 2, gx // 2, gy // 2
+    zq, xq, yq = np.meshgrid(np.arange(hz), np.arange(hx), np.arange(hy), indexing="ij")
+    zq, xq, yq = zq.ravel(), xq.ravel(), yq.ravel()
+    per = []
+    for s in range(8):
+        f = lowrank_factors(sector_block(table, gx, gy, gz, s), tol=tol * 1e-3, max_rank=max_rank)
+        if f is None:
+            return None
+        per.append(f)
+    lam_max = max(np.abs(f[1][0]) for f in per if len(f[1]))
+    vecs, vals, residual = [], [], 0.0
+    for s, (zv, w, res) in enumerate(per):
+        py, pz, px = (-1.0 if s & 4 else 1.0), (-1.0 if s & 2 else 1.0), (-1.0 if s & 1 else 1.0)
+        keep = np.abs(w) > tol * lam_max
+        residual = max(residual, res, float(np.abs(w[~keep]).max()) if np.any(~keep) else 0.0)
+        for zvec, lam in zip(zv[keep], w[keep]):
+            full = np.zeros((gz, gx, gy))
+            z3 = zvec.reshape(hz, hx, hy) / np.sqrt(8.0)
+            for mz, sz in ((0, 1.0), (1, pz)):
+                for mx, sx in ((0, 1.0), (1, px)):
+                    for my, sy in ((0, 1.0), (1, py)):
+                        blk = sz * sx * sy * z3
+                        blk = blk[::-1] if mz else blk
+                        blk = blk[:, ::-1] if mx else blk
+                        blk = blk[:, :, ::-1] if my else blk
+                        full[(slice(hz, None) if mz else slice(0, hz)), (slice(hx, None) if mx else slice(0, hx)),
+                             (slice(hy, None) if my else slice(0, hy))] = blk
+            vecs.append(full.ravel())
+            vals.append(lam)
+    order = np.argsort(-np.abs(np.array(vals)))
+    if len(order) > max_rank:
+        return None
+    return np.ascontiguousarray(np.array(vecs)[order]), np.ascontiguousarray(np.array(vals)[order]), residual

@@ -134,12 +134,13 @@ int dbsgym_set_coupling_dense(DbsGymHandle* h, const double* alpha);
 int dbsgym_set_coupling_spectral(DbsGymHandle* h, const int32_t* ranks8, int32_t r_max,
                                  const double* vecs, const double* vals);
 
-/* Low-rank form of a DENSE operator (fp32 handles): alpha ~ sum_m vals[m] v_m v_m^T with vecs[m * N + i] = v_m[i], the
+/* Low-rank form of the coupling operator (fp32 handles, DENSE or GRID: the neuron ordering does not matter, and GRID
+ * handles bring the cluster mode for n_osc > 4096 with them): alpha ~ sum_m vals[m] v_m v_m^T with vecs[m * N + i] = v_m[i], the
  * eigenpairs of alpha (env.py:219-229; any neuron ordering, utils.py:483-497 shuffle=True) the caller keeps
  * (dbsgym_b200/geometry.py: lowrank_factors returns the spectral norm of what it dropped).  The step kernel then evaluates
  * the coupling sum of env.py:252-256 as sum_m v_m[i] (cos th_i S_m - sin th_i C_m) -- O(N rank) per evaluation instead of
  * O(N^2), rank * N floats of operator instead of N^2; dbsgym_set_coupling_dense need not be called at all.
- * rank <= 0 switches back to the full matrix. */
+ * rank <= 0 switches back to the full operator (matrix / grid table). */
 int dbsgym_set_coupling_lowrank(DbsGymHandle* h, int32_t rank, const double* vecs, const double* vals);
 
 /* Per-environment vectors uploaded at reset (env.py:566-598): natural frequencies after

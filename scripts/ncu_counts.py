@@ -72,6 +72,15 @@ out = {
     "registers_per_thread": metric("launch__registers_per_thread"),
     "issue_slots_busy_pct": metric("smsp__issue_active.avg.pct_of_peak_sustained_active") if "smsp__issue_active.avg.pct_of_peak_sustained_active" in hdr else None,
 }
+for key, name in (("fma_pipe_cycles_active_pct", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                  ("xu_pipe_inst_pct", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                  ("lsu_pipe_inst_pct", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+                  ("warps_active_pct", "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                  ("shared_bank_conflicts", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+                  ("shared_wavefronts", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"),
+                  ("local_load_requests", "l1tex__t_requests_pipe_lsu_mem_local_op_ld.sum")):
+    if name in hdr:
+        out[key] = metric(name)
 path = os.path.join(root, "profiles", f"r02_step_kernel_variant{variant}_counts.json")
 with open(path, "w") as f:
     json.dump(out, f, indent=1)

@@ -28,6 +28,8 @@ GRIDS = ([(8, 8, gz) for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024)] + [(16, 
          [(32, 32, gz) for gz in (8, 16, 32, 64)])       # 32^3 (and 32 x 32 x 64 for N = 65536): lines of 32, cluster mode
 if os.environ.get("SWEEP_ONLY_CUBIC"):
     GRIDS = [g for g in GRIDS if g[1] != 8]
+if os.environ.get("SWEEP_MIN_N"):
+    GRIDS = [g for g in GRIDS if g[0] * g[1] * g[2] >= int(os.environ["SWEEP_MIN_N"])]
 for gx, gy, gz in GRIDS:
     N = gx * gy * gz
     B = 2097152 // N
@@ -35,6 +37,15 @@ for gx, gy, gz in GRIDS:
     table = coupling_table(coords, grid, [gx, gy, gz], "cos")
     assert table is not None
     eng = KuramotoEngine(B, N, [gx, gy, gz], 2340, 0.52, precision="f32", coupling_table=table, device=LOCAL)
+    lowrank = None
+    if os.environ.get("SWEEP_LOWRANK"):                   # the operator in its truncated eigenbasis (step-kernel variant 11)
+        from dbsgym_b200.geometry import grid_lowrank_factors
+        t_f = time.perf_counter()
+        f = grid_lowrank_factors(table, gx, gy, gz, tol=float(os.environ.get("SWEEP_LOWRANK_TOL", "1e-9")))
+        if f is None:
+            continue
+        eng.set_coupling_lowrank(*f)
+        lowrank = {"rank": int(f[0].shape[0]), "residual_over_lambda_max": float(f[2] / abs(f[1][0])), "factorisation_s": time.perf_counter() - t_f}
     tt = transient_grid(200.0, 0.05)
     sched = StepSchedule(400, tt[-1], 0.15, 0.75, 0.05)
     eng.set_schedule(sched); eng.set_reward("bbpow_action", 0.05)
@@ -80,6 +91,8 @@ for gx, gy, gz in GRIDS:
                 "rhs_per_env_step": rhs, "executed_tflops": WORLD * rhs * (SYM_FLOP * N * N + SYM_LIN * N) * B / (k_step * 1e-3) / 1e12,
                 "dense_equivalent_tflops": WORLD * rhs * 4 * N * N * B / (k_step * 1e-3) / 1e12,
                 "transient_s": t_tr, "status": c["status"], "ctas_per_env": max(1, N // 4096), "variant": variant})
+    if lowrank is not None:                               # own op count of the low-rank contraction: 2 x 4 flop per mode and oscillator
+        out[-1].update(lowrank=lowrank, executed_tflops=WORLD * rhs * (16.0 * lowrank["rank"] * N + 150.0 * N) * B / (k_step * 1e-3) / 1e12)
     if RANK == 0:
         print(json.dumps(out[-1]), flush=True)
     eng.close()

@@ -106,6 +106,40 @@ def test_n8192_cluster_step_matches_oracle(gx, gy, gz):
     eng.close()
 
 
+@pytest.mark.parametrize("N,gz,C,gx,gy", [(1024, 16, 2, 8, 8), (4096, 16, 4, 16, 16), (8192, 128, None, 8, 8)])
+def test_low_rank_kernel_on_grid_handles_single_cta_and_cluster(N, gz, C, gx, gy):
+    """The coupling operator of a regular grid in its truncated eigenbasis (geometry.grid_lowrank_factors: factorised sector
+    by sector, never forming the N x N matrix), step-kernel variant 11, against the exact parity-sector kernels on the same
+    GRID handle: one CTA per environment, forced clusters of C CTAs (the mode sums of the CTAs meet in global memory), and
+    N = 8192 where the cluster is the only way to run.  Steps at float32 rounding, counters exact."""
+    from dbsgym_b200.geometry import grid_lowrank_factors
+    acts = np.random.default_rng(1).uniform(-1, 1, (3, 3)).astype(np.float32)
+    res = {}
+    modes = [("exact", None, False), ("lowrank", None, True)] + ([("lowrank_cluster", C, True)] if C else [])
+    for name, force, lr in modes:
+        eng, d = _engine(N, gz, 3, force, gx=gx, gy=gy)
+        if lr:
+            f = grid_lowrank_factors(d["table"], gx, gy, gz, tol=1e-9)
+            assert f is not None and f[0].shape[0] <= 128 and f[2] < 2e-9 * np.abs(f[1][0])
+            eng.set_coupling_lowrank(*f)
+            assert eng.step_variant() == 11
+        eng.counters(reset=True)
+        out = []
+        for a in acts:
+            obs, rew, done = eng.step_host(a)
+            out.append((eng.state().copy(), obs.copy(), rew.copy(), eng.lfp()[0].copy(), eng.lfp()[1].copy()))
+        res[name] = (out, eng.counters())
+        eng.close()
+    ref, cref = res["exact"]
+    assert cref["status"] == 0
+    for name in [m[0] for m in modes[1:]]:
+        out, c = res[name]
+        assert c == cref, (name, c, cref)
+        for k, (x, y) in enumerate(zip(ref, out)):
+            for u, v in zip(x, y):
+                np.testing.assert_allclose(u, v, rtol=2e-5, atol=1e-5 * (k + 1) if u.ndim == 2 and u.shape[1] == N else 5e-6)
+
+
 @pytest.mark.parametrize("B", [5, 21])
 def test_multi_worker_kernel_equals_the_single_environment_kernel(B):
     """options mw=True forces the multi-worker step kernel (8 environments per CTA sharing the precomputed sector
