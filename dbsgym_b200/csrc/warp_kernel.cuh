@@ -230,13 +230,7 @@ __device__ __forceinline__ void wobs_tail(const StepParams& p, int env, int lane
         const float v = LF[lane];
         ring[pos] = v;
         if (p.samples_f) p.samples_f[(size_t)env * p.smax + lane] = v;
-        if (p.mirror) {                               // zero-copy store into the pinned host mirror (both copies)
-            float* mr = p.mirror + (size_t)env * 2 * p.mir_len;
-            int c = t_pos[33] + lane;
-            if (c >= p.mir_len) c -= p.mir_len;
-            mr[c] = v;
-            mr[c + p.mir_len] = v;
-        }
+        // (the pinned host log received the samples when they were formed, see the dense-output part of the kernel)
         t_delta[lane] = (double)v - t_delta[lane];
         if (p.trace) {                                // evaluation trace: theta_mean of the step (env.py:441)
             const int at = p.trace_len[env] + lane;
@@ -693,6 +687,13 @@ __global__ void __maxnreg__(DBSGYM_WARP_MAXNREG) warp_step_kernel(const StepPara
                                     p.lfp_true[(size_t)env * p.smax + out_base + idx] = a_t;
                                     p.lfp_rec[(size_t)env * p.smax + out_base + idx] = a_r;
                                     LF[(out_base + idx) & 31] = (float)a_r;
+                                    if (tail && p.mirror) {       // zero-copy store into the pinned host log (both copies) as soon as the
+                                        float* mr = p.mirror + (size_t)env * 2 * p.mir_len;      // sample exists: PCIe drains under the integration
+                                        int c = t_pos[33] + out_base + idx;
+                                        if (c >= p.mir_len) c -= p.mir_len;
+                                        mr[c] = (float)a_r;
+                                        mr[c + p.mir_len] = (float)a_r;
+                                    }
                                 } else {
                                     reinterpret_cast<float*>(p.ring)[(size_t)env * p.W + (idx - rec_from)] = (float)a_r;
                                 }
