@@ -40,18 +40,27 @@ class _LazyAttrList:
 
 
 class _InfoList(list):
-    """``infos`` of a step: one dict per environment like DummyVecEnv returns, but the dicts of environments that
-    did not finish are created only when somebody indexes them (building thousands of dicts per step costs more
-    than the GPU step).  Every environment gets its OWN dict, so a wrapper that mutates ``infos[i]`` touches
-    nothing else."""
+    """``infos`` of a step: one dict per environment like DummyVecEnv returns, but the dicts are created only when
+    somebody indexes them (building thousands of dicts -- and, at an episode end, thousands of ``terminal_observation``
+    copies and Monitor records -- per step costs more than the GPU step).  Every environment gets its OWN dict, so a
+    wrapper that mutates ``infos[i]`` touches nothing else."""
 
     def __init__(self, n):
         super().__init__([None] * n)
+        self._terminal = None          # (done mask, terminal observations [B, 1, W], episode returns, lengths, wall time)
+
+    def set_terminal(self, done, term_obs, ep_ret, ep_len, t, monitor):
+        self._terminal = (done, term_obs, ep_ret, ep_len, t, monitor)
 
     def _fill(self, i):
         d = list.__getitem__(self, i)
         if d is None:
             d = {"TimeLimit.truncated": False}
+            if self._terminal is not None and self._terminal[0][i]:
+                done, term_obs, ep_ret, ep_len, t, monitor = self._terminal
+                d["terminal_observation"] = term_obs[i]
+                if monitor:
+                    d["episode"] = {"r": round(float(ep_ret[i]), 6), "l": int(ep_len[i]), "t": round(t, 6)}
             list.__setitem__(self, i, d)
         return d
 
@@ -121,19 +130,19 @@ class BatchedKuramotoVecEnv(VecEnvBase):
         infos = self._infos
         finished = np.flatnonzero(done)
         if finished.size:
-            for i in finished:
-                infos[i] = {"TimeLimit.truncated": False, "terminal_observation": obs[i].copy()}
-                if self.monitor:
-                    infos[i]["episode"] = {"r": round(float(self._ep_ret[i]), 6), "l": int(self._ep_len[i]),
-                                           "t": round(time.time() - self._t0, 6)}
+            # one copy of the finished environments' last observations (they are about to be replaced by the reset windows);
+            # the per-environment info dicts (terminal_observation, Monitor's episode record) are built when indexed
+            term = np.empty_like(obs) if finished.size == self.num_envs else None
+            if term is not None:
+                np.copyto(term, obs)
+            else:
+                term = {int(i): obs[i].copy() for i in finished}
+            infos.set_terminal(done, term, self._ep_ret.copy(), self._ep_len.copy(), time.time() - self._t0, self.monitor)
             self.core.reset_envs(finished)            # index order == sequential DummyVecEnv order
-            term = {i: infos[i]["terminal_observation"] for i in finished}
             fresh = self.core.observations_after_reset()     # owned array / view of the NEW mirror buffer
             obs = fresh.reshape(self.num_envs, 1, -1)
             if self.copy_obs:
                 obs = obs.copy()
-            for i in finished:
-                infos[i]["terminal_observation"] = term[i]
             self._ep_ret[finished] = 0
             self._ep_len[finished] = 0
         return obs, rew, done, infos
