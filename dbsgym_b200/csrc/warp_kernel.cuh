@@ -35,6 +35,9 @@
 #ifndef DBSGYM_WARP_VSMEM
 #define DBSGYM_WARP_VSMEM 0
 #endif
+#ifndef DBSGYM_WARP_MAXNREG
+#define DBSGYM_WARP_MAXNREG 255      // (step_f32_warp.cu derives it from the warps per CTA)
+#endif
 // A/B switches of the per-environment prologue / epilogue
 #ifndef DBSGYM_WARP_PREFETCH
 #define DBSGYM_WARP_PREFETCH 1       // pull the next environment's rows into L2 while this one is integrated
