@@ -91,6 +91,16 @@ class BatchedKuramoto:
                                      max_step_samples=max(self.schedule.max_samples, 20),
                                      action_bounds=p0["dbs_action_bounds"], options=engine_options)
         self.coupling_eval = "lowrank" if lowrank is not None else "exact"
+        gs = [int(g) for g in p0["grid_size"]]
+        if (table is not None and coupling_eval != "exact" and precision == "f32" and self.n_osc >= 2048 and
+                self.n_osc == gs[0] * gs[1] * gs[2] and all(g % 2 == 0 for g in gs)):
+            # large regular grids: the operator as sector-wise eigenpairs over the fundamental octant (O(N r / 8) per evaluation;
+            # from N = 2048 up faster than the exact sector blocks -- profiles/r02_sweep_n_lowrank_sectors_1gpu.jsonl)
+            from .geometry import grid_sector_factors
+            f = grid_sector_factors(table, gs[0], gs[1], gs[2], tol=spectral_tol)
+            if f is not None:
+                self.engine.set_coupling_lowrank_sectors(*f)
+                self.coupling_eval = "lowrank"
         grid888 = table is not None and [int(g) for g in p0["grid_size"]] == [8, 8, 8] and self.n_osc == 512
         if coupling_eval != "exact" and precision == "f32" and grid888 and not (engine_options or {}).get("no_sym"):
             from .geometry import spectral_factors

@@ -104,6 +104,8 @@ struct DbsGymHandle {
     // low-rank form of a DENSE operator (dbsgym_set_coupling_lowrank): eigenvectors [lr_rank][Np], eigenvalues [lr_rank]
     float* lr_v = nullptr; float* lr_lam = nullptr; int lr_rank = 0;
     float2* lr_part = nullptr;           // cluster mode: per-CTA mode sums [B][2][cluster][lr_rank]
+    // sector form of the low-rank operator: oscillators stored in octant order (perm[d] = natural index of device position d)
+    int32_t* lr_soff = nullptr; bool lr_sectors = false; std::vector<int32_t> perm; bool params_set = false;
     unsigned long long n_launches = 0;   // kernels launched by this handle (dbsgym_launch_count)
     // ordering between the private stream and caller streams (dbsgym_step / dbsgym_transient on a user stream)
     cudaEvent_t ev_own = nullptr, ev_user = nullptr; bool user_pending = false;
@@ -325,6 +327,7 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
     const bool warp = h->spec_re > 0 && h->warp_set >= 0;
     p.spec_v = warp ? h->wspec_v : h->spec_v; p.spec_lam = warp ? h->wspec_lam : h->spec_lam;
     p.lr_v = h->lr_v; p.lr_lam = h->lr_lam; p.lr_rank = h->lr_rank; p.lr_part = h->lr_part;
+    p.lr_sectors = h->lr_sectors ? 1 : 0; p.lr_soff = h->lr_soff;
     p.power_scale = h->rspec.power_scale; p.action_cost = h->rspec.action_cost;
     p.threshold = h->rspec.threshold; p.threshold_penalty = h->rspec.threshold_penalty;
 }
@@ -705,7 +708,7 @@ void dbsgym_destroy(DbsGymHandle* h) {
                     h->step_idx, h->episode_len, h->lfp_true, h->lfp_rec, h->u, h->reward, h->done, h->sched_nI,
                     h->sched_nII, h->sched_offI, h->sched_offII, h->ts_dev, h->ids_dev, h->lin_g, h->tw_seed,
                     h->tw_inner, h->spec, h->tw_full, h->k_fsal, h->fsal_valid, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples,
-                    h->cl_operand, h->cl_scratch, h->mpos, h->spec_v, h->spec_lam, h->wspec_v, h->wspec_lam, h->lr_v, h->lr_lam, h->lr_part};
+                    h->cl_operand, h->cl_scratch, h->mpos, h->spec_v, h->spec_lam, h->wspec_v, h->wspec_lam, h->lr_v, h->lr_lam, h->lr_part, h->lr_soff};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->pin_ints) cudaFreeHost(h->pin_ints);
@@ -845,6 +848,7 @@ int dbsgym_set_coupling_lowrank(DbsGymHandle* h, int32_t rank, const double* vec
     if (!h) return DBSGYM_EINVAL;
     CU(h, cudaSetDevice(h->cfg.device));
     CU(h, cudaDeviceSynchronize());
+    if (h->lr_sectors) return fail(h, DBSGYM_ESTATE, "the handle stores its oscillators in octant order (sector form): create a new handle");
     for (float** q : {&h->lr_v, &h->lr_lam}) { if (*q) cudaFree(*q); *q = nullptr; }
     if (h->lr_part) { cudaFree(h->lr_part); h->lr_part = nullptr; }
     h->lr_rank = 0;
@@ -878,6 +882,58 @@ int dbsgym_set_coupling_lowrank(DbsGymHandle* h, int32_t rank, const double* vec
     return DBSGYM_OK;
 }
 
+int dbsgym_set_coupling_lowrank_sectors(DbsGymHandle* h, const int32_t* soff9, const double* zvecs, const double* vals) {
+    if (!h || !soff9 || !zvecs || !vals) return fail(h, DBSGYM_EINVAL, "null argument");
+    if (h->cfg.coupling != DBSGYM_COUPLING_GRID || h->f64)
+        return fail(h, DBSGYM_ESTATE, "the sector form of the low-rank operator serves fp32 GRID handles");
+    if (h->params_set || h->lr_rank > 0)
+        return fail(h, DBSGYM_ESTATE, "set the sector form right after dbsgym_set_coupling_grid, before any environment vectors are "
+                                      "uploaded (it changes the order the oscillators are stored in)");
+    const int gx = h->cfg.grid[0], gy = h->cfg.grid[1], gz = h->cfg.grid[2], N = h->N, Np = h->Np;
+    if (gx % 2 || gy % 2 || gz % 2 || N != gx * gy * gz || Np != N || Np % 256 != 0)
+        return fail(h, DBSGYM_ESTATE, "the sector form needs a full grid with even extents and whole warps of octant points");
+    const int R = soff9[8];
+    if (soff9[0] != 0 || R <= 0 || R > 1024) return fail(h, DBSGYM_EINVAL, "mode offsets out of range (at most 1024 modes)");
+    for (int s8 = 0; s8 < 8; ++s8)
+        if (soff9[s8 + 1] < soff9[s8] || (soff9[s8 + 1] - soff9[s8]) % 4 != 0)
+            return fail(h, DBSGYM_EINVAL, "the modes of every sector must be padded to a multiple of 4");
+    CU(h, cudaSetDevice(h->cfg.device));
+    CU(h, cudaDeviceSynchronize());
+    const size_t need = h->cluster > 1 ? step_smem_bytes_cluster_lr(h->nthreads, R) : step_smem_bytes(Np, 2 * R, h->nthreads, h->rb);
+    int max_smem = 0;
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->cfg.device);
+    if (need > (size_t)max_smem) return fail(h, DBSGYM_EINVAL, "%d modes need %zu bytes of shared memory, the device allows %d", R, need, max_smem);
+    // octant order: device position 8 a + g holds the image g = 4 my + 2 mz + mx of octant point a = (zq * gx/2 + xq) * gy/2 + yq
+    const int hx = gx / 2, hy = gy / 2, hz = gz / 2, P8 = N / 8;
+    h->perm.assign((size_t)N, 0);
+    for (int zq = 0; zq < hz; ++zq)
+        for (int xq = 0; xq < hx; ++xq)
+            for (int yq = 0; yq < hy; ++yq) {
+                const int a = (zq * hx + xq) * hy + yq;
+                for (int g = 0; g < 8; ++g) {
+                    const int z = (g & 2) ? gz - 1 - zq : zq, x = (g & 1) ? gx - 1 - xq : xq, y = (g & 4) ? gy - 1 - yq : yq;
+                    h->perm[(size_t)a * 8 + g] = (z * gx + x) * gy + y;
+                }
+            }
+    std::vector<float> z((size_t)R * P8), lam((size_t)R);
+    for (int m = 0; m < R; ++m) {
+        lam[m] = (float)(vals[m] / 8.0);               // (alpha x)[g a] = 1/8 sum_s chi_s(g) (block_s X_s)[a]
+        for (int a = 0; a < P8; ++a) z[(size_t)m * P8 + a] = (float)zvecs[(size_t)m * P8 + a];
+    }
+    CU(h, cudaMalloc(&h->lr_v, z.size() * sizeof(float)));
+    CU(h, cudaMalloc(&h->lr_lam, lam.size() * sizeof(float)));
+    CU(h, cudaMalloc(&h->lr_soff, 9 * sizeof(int32_t)));
+    CU(h, cudaMemcpy(h->lr_v, z.data(), z.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->lr_lam, lam.data(), lam.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->lr_soff, soff9, 9 * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (h->cluster > 1) CU(h, cudaMalloc(&h->lr_part, (size_t)h->B * 2 * h->cluster * R * sizeof(float2)));
+    h->lr_rank = R;
+    h->lr_sectors = true;
+    h->have_coupling = true;
+    if (h->fsal_valid) CU(h, cudaMemset(h->fsal_valid, 0, (size_t)h->B * 4));
+    return DBSGYM_OK;
+}
+
 int dbsgym_set_recording(DbsGymHandle* h, int32_t weighted) {
     if (!h) return DBSGYM_EINVAL;
     h->weighted_rec = weighted ? 1 : 0;
@@ -897,6 +953,22 @@ int dbsgym_set_env_params(DbsGymHandle* h, const int32_t* env_ids, int32_t n, co
         std::vector<int32_t> z((size_t)n, 0);
         rc = scatter_to_device(h, h->fsal_valid, z.data(), ids, n, 4);
         if (rc) return rc;
+    }
+    h->params_set = true;
+    // sector form of the low-rank operator: the device keeps the oscillators in octant order
+    std::vector<double> pv[4];
+    if (!h->perm.empty()) {
+        const double** srcs[4] = {&w0, &stim_cond, &rec_cond, &y0};
+        for (int k = 0; k < 4; ++k) {
+            if (!*srcs[k]) continue;
+            pv[k].resize((size_t)n * h->N);
+            for (int r = 0; r < n; ++r) {
+                const double* a = *srcs[k] + (size_t)r * h->N;
+                double* b = pv[k].data() + (size_t)r * h->N;
+                for (int d = 0; d < h->N; ++d) b[d] = a[h->perm[d]];
+            }
+            *srcs[k] = pv[k].data();
+        }
     }
     std::vector<unsigned char> buf;
     const size_t row = (size_t)h->Np * h->rb;
@@ -1299,6 +1371,16 @@ int dbsgym_get_phases(DbsGymHandle* h, const int32_t* env_ids, int32_t n, double
     std::vector<unsigned char> ph((size_t)n * h->Np * h->rb);
     rc = gather_from_device(h, ph.data(), h->phase, ids, n, (size_t)h->Np * h->rb);
     if (rc) return rc;
+    if (!h->perm.empty()) {                          // octant order on the device (sector form of the low-rank operator, fp32)
+        std::vector<int32_t> wd((size_t)n * h->Np);
+        rc = gather_from_device(h, wd.data(), h->wind, ids, n, (size_t)h->Np * 4);
+        if (rc) return rc;
+        const float* p = reinterpret_cast<const float*>(ph.data());
+        for (int r = 0; r < n; ++r)
+            for (int d = 0; d < h->N; ++d)
+                y[(size_t)r * h->N + h->perm[d]] = (double)p[(size_t)r * h->Np + d] + kTwoPi * (double)wd[(size_t)r * h->Np + d];
+        return DBSGYM_OK;
+    }
     if (h->f64) {
         const double* p = reinterpret_cast<const double*>(ph.data());
         for (int r = 0; r < n; ++r)

@@ -94,6 +94,10 @@ struct StepParams {
     // and eigenvalues [lr_rank] of a DENSE alpha (see couple_lowrank_* below)
     const float* lr_v; const float* lr_lam; int lr_rank;
     float2* lr_part;               // cluster mode: [B][2][cluster][lr_rank] per-CTA mode sums (global, L2)
+    // sector form (lr_sectors != 0): the oscillators are stored in OCTANT order (position 8 a + g = image g of octant point
+    // a, g = 4 my + 2 mz + mx), lr_v holds the eigenvectors of the 8 parity-sector blocks over the octant points only,
+    // [lr_rank][Np / 8], modes sorted by sector (counts padded to multiples of 4), lr_soff[9] = first mode of every sector
+    int lr_sectors; const int32_t* lr_soff;
     double* trace; int32_t* trace_len; int trace_cap;   // optional recording of the TRUE LFP of every step (evaluation)
     double power_scale, action_cost, threshold, threshold_penalty;
     // cluster mode (one environment = a thread-block cluster of `cluster` CTAs, N > 4096)
@@ -896,6 +900,44 @@ __device__ __forceinline__ void couple_lowrank_expand(const float2* __restrict__
     for (int r = 0; r < kRows; ++r) { as[r] = acc[r].x; ac[r] = acc[r].y; }
 }
 
+// Sector form of the low-rank contraction (regular grids with even extents): alpha commutes with the three reflections, so
+// every eigenvector lives in one parity sector and is fixed by its values on the fundamental octant.  A thread owns the 8
+// mirror images of one octant point (the oscillators are stored in that order), transforms its (sin, cos) values to the 8
+// sector coordinates by an in-register Walsh-Hadamard butterfly, and the mode sums / expansions run over N / 8 octant points
+// with sector-wise eigenvectors: 1/8 of the multiply-adds AND 1/8 of the eigenvector traffic of the plain form.
+__device__ __forceinline__ void wht8_pairs(float (&a)[kRows], float (&b)[kRows]) {
+#pragma unroll
+    for (int h = 1; h < 8; h <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if ((i & h) == 0) {
+                const float2 u = make_float2(a[i], b[i]), v = make_float2(a[i + h], b[i + h]);
+                const float2 p_ = __fadd2_rn(u, v), m_ = __ffma2_rn(v, make_float2(-1.f, -1.f), u);
+                a[i] = p_.x; b[i] = p_.y; a[i + h] = m_.x; b[i + h] = m_.y;
+            }
+        }
+    }
+}
+// expansion in sector form: Y_s[point] = sum over the modes of sector s of Z[m][point] C_m (C already carries lambda / 8)
+__device__ __forceinline__ void couple_lowrank_expand_sectors(const float2* __restrict__ Cs, const float* __restrict__ Z,
+                                                              const int32_t* __restrict__ soff, int Np8, int point,
+                                                              float (&as)[kRows], float (&ac)[kRows]) {
+    const float* col = Z + point;
+#pragma unroll
+    for (int sct = 0; sct < 8; ++sct) {
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+        const int m1 = soff[sct + 1];
+        for (int m = soff[sct]; m < m1; m += 2) {          // (sector counts are multiples of 4)
+            const float z0 = __ldg(col + (size_t)m * Np8), z1 = __ldg(col + (size_t)(m + 1) * Np8);
+            const float4 c = *reinterpret_cast<const float4*>(Cs + m);
+            acc0 = __ffma2_rn(make_float2(z0, z0), make_float2(c.x, c.y), acc0);
+            acc1 = __ffma2_rn(make_float2(z1, z1), make_float2(c.z, c.w), acc1);
+        }
+        as[sct] = acc0.x + acc1.x; ac[sct] = acc0.y + acc1.y;
+    }
+    wht8_pairs(as, ac);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -1302,18 +1344,42 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
 #pragma unroll
                         for (int r = 0; r < kRows; ++r) { scw[2 * r] = sv[r]; scw[2 * r + 1] = cv[r]; }
                     }
-                    if (!SPEC) storev<2 * kRows>(SC + pbuf * scsz + sc_slot, scw);
+                    if constexpr (LR) {
+                        if (p.lr_sectors) {                          // sector coordinates of this thread's octant point, XS[sector][point]
+                            real xs_[kRows], xc_[kRows];
+#pragma unroll
+                            for (int r = 0; r < kRows; ++r) { xs_[r] = sv[r]; xc_[r] = cv[r]; }
+                            wht8_pairs(reinterpret_cast<float(&)[kRows]>(xs_), reinterpret_cast<float(&)[kRows]>(xc_));
+                            float2* xsm = reinterpret_cast<float2*>(SC + pbuf * scsz);
+#pragma unroll
+                            for (int r = 0; r < kRows; ++r) xsm[r * nt + tid] = make_float2((float)xs_[r], (float)xc_[r]);
+                        } else storev<2 * kRows>(SC + pbuf * scsz + sc_slot, scw);
+                    } else if (!SPEC) storev<2 * kRows>(SC + pbuf * scsz + sc_slot, scw);
                 }
                 if (CLG) cluster_barrier(); else if (!SPEC) env_sync();
                 real as[kRows], ac[kRows];
                 if constexpr (LR) {
                     float2* Cs = reinterpret_cast<float2*>(Ts);
+                    const float* opnd = reinterpret_cast<const float*>(SC + pbuf * scsz);
+                    // one pass of phase 1 over the oscillators (plain form) or over the octant points of a sector (sector form):
+                    // all modes [m_lo, m_hi) against `n` operand entries at `x`, eigenvector rows of length `ld` starting at `off`
+                    auto project = [&](const float* lamp, float2* out) {
+                        if (p.lr_sectors) {
+#pragma unroll 1
+                            for (int sct = 0; sct < 8; ++sct) {
+                                const int m_lo = p.lr_soff[sct], m_hi = p.lr_soff[sct + 1];
+                                if (m_hi > m_lo)
+                                    couple_lowrank_project(opnd + 2 * sct * nt, p.lr_v + (size_t)m_lo * (Np >> 3),
+                                                           lamp ? lamp + m_lo : nullptr, m_hi - m_lo, Np >> 3, crank * nt, nt,
+                                                           out + m_lo, lane, warp, nwarps);
+                            }
+                        } else couple_lowrank_project(opnd, p.lr_v, lamp, p.lr_rank, Np, crank * Nl, Nl, out, lane, warp, nwarps);
+                    };
                     if constexpr (CL != 0) {
                         // every CTA of the cluster sums over its own oscillators; the partial sums meet in global memory (L2)
                         // and every CTA adds them in the same order, so all CTAs expand with identical coefficients
                         float2* part_g = p.lr_part + ((size_t)env * 2 + lr_par) * NC_ * p.lr_rank;
-                        couple_lowrank_project(reinterpret_cast<const float*>(SC + pbuf * scsz), p.lr_v, nullptr, p.lr_rank, Np,
-                                               crank * Nl, Nl, part_g + (size_t)crank * p.lr_rank, lane, warp, nwarps);
+                        project(nullptr, part_g + (size_t)crank * p.lr_rank);
                         cluster_barrier();
                         for (int m = tid; m < p.lr_rank; m += nt) {
                             float2 a = make_float2(0.f, 0.f);
@@ -1325,12 +1391,14 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                             Cs[m] = make_float2(l * a.x, l * a.y);
                         }
                         lr_par ^= 1;
-                    } else
-                        couple_lowrank_project(reinterpret_cast<const float*>(SC + pbuf * scsz), p.lr_v, p.lr_lam, p.lr_rank, Np,
-                                               0, Np, Cs, lane, warp, nwarps);
+                    } else project(p.lr_lam, Cs);
                     env_sync();
-                    couple_lowrank_expand(Cs, p.lr_v, p.lr_rank, Np, i0, reinterpret_cast<float(&)[kRows]>(as),
-                                          reinterpret_cast<float(&)[kRows]>(ac));
+                    if (p.lr_sectors)
+                        couple_lowrank_expand_sectors(Cs, p.lr_v, p.lr_soff, Np >> 3, tid_g, reinterpret_cast<float(&)[kRows]>(as),
+                                                      reinterpret_cast<float(&)[kRows]>(ac));
+                    else
+                        couple_lowrank_expand(Cs, p.lr_v, p.lr_rank, Np, i0, reinterpret_cast<float(&)[kRows]>(as),
+                                              reinterpret_cast<float(&)[kRows]>(ac));
                 } else if (DENSE) couple_dense<real>(SC + pbuf * scsz, reinterpret_cast<const real*>(p.alpha), Np, i0, as, ac);
                 else if (SYM) {
                     if constexpr (SPEC) {

@@ -38,6 +38,9 @@
 #ifndef DBSGYM_WARP_MAXNREG
 #define DBSGYM_WARP_MAXNREG 255      // (step_f32_warp.cu derives it from the warps per CTA)
 #endif
+#ifndef DBSGYM_WARP_MIRROR_STORES
+#define DBSGYM_WARP_MIRROR_STORES 1  // (0: A/B builds that measure what the zero-copy sample stores cost; the host log is then wrong)
+#endif
 // A/B switches of the per-environment prologue / epilogue
 #ifndef DBSGYM_WARP_PREFETCH
 #define DBSGYM_WARP_PREFETCH 1       // pull the next environment's rows into L2 while this one is integrated
@@ -690,7 +693,7 @@ __global__ void __maxnreg__(DBSGYM_WARP_MAXNREG) warp_step_kernel(const StepPara
                                     p.lfp_true[(size_t)env * p.smax + out_base + idx] = a_t;
                                     p.lfp_rec[(size_t)env * p.smax + out_base + idx] = a_r;
                                     LF[(out_base + idx) & 31] = (float)a_r;
-                                    if (tail && p.mirror) {       // zero-copy store into the pinned host log (both copies) as soon as the
+                                    if (DBSGYM_WARP_MIRROR_STORES && tail && p.mirror) {       // zero-copy store into the pinned host log (both copies) as soon as the
                                         float* mr = p.mirror + (size_t)env * 2 * p.mir_len;      // sample exists: PCIe drains under the integration
                                         int c = t_pos[33] + out_base + idx;
                                         if (c >= p.mir_len) c -= p.mir_len;

@@ -127,6 +127,16 @@ class KuramotoEngine:
         self._ck(self.lib.dbsgym_set_coupling_lowrank(self._h, int(v.shape[0]), _capi.ptr(v), _capi.ptr(w)))
         self.lowrank = {"rank": int(v.shape[0]), "residual": residual}
 
+    def set_coupling_lowrank_sectors(self, soff, zvecs, vals, residual=None):
+        """Sector form of the low-rank operator (dbsgym.h: dbsgym_set_coupling_lowrank_sectors; fp32 GRID handles, before any
+        set_env_params): ``soff`` [9], ``zvecs`` [modes][n_osc / 8], ``vals`` [modes] as returned by
+        geometry.grid_sector_factors."""
+        o = np.ascontiguousarray(soff, dtype=np.int32)
+        z, w = _f64(zvecs), _f64(vals)
+        assert o.shape == (9,) and z.shape == (int(o[8]), self.n_osc // 8) and w.shape == (int(o[8]),)
+        self._ck(self.lib.dbsgym_set_coupling_lowrank_sectors(self._h, _capi.ptr(o), _capi.ptr(z), _capi.ptr(w)))
+        self.lowrank = {"rank": int(np.count_nonzero(w)), "padded_modes": int(o[8]), "sectors": True, "residual": residual}
+
     # ------------------------------------------------------------------ plumbing
     def _ck(self, rc):
         _capi.check(self.lib, self._h, rc)

@@ -335,3 +335,33 @@ def grid_lowrank_factors(table, gx, gy, gz, tol=1e-9, max_rank=1024):
     if len(order) > max_rank:
         return None
     return np.ascontiguousarray(np.array(vecs)[order]), np.ascontiguousarray(np.array(vals)[order]), residual
+
+
+def grid_sector_factors(table, gx, gy, gz, tol=1e-9, max_modes=1024):
+    """The operator of a regular grid with even extents as sector-wise eigenpairs over the fundamental octant (the form
+    dbsgym_set_coupling_lowrank_sectors takes): returns (soff [9], zvecs [modes][N / 8], vals [modes], residual) with the modes
+    sorted by sector s = 4 [odd y] + 2 [odd z] + [odd x], every sector padded to a multiple of 4 modes (zero rows, zero
+    eigenvalues), eigenvalues of the sector blocks (sector_block) kept where |lambda| > tol * |lambda|_max; ``residual`` = the
+    spectral norm of what was dropped.  None when more than ``max_modes`` would be needed."""
+    per = []
+    for s in range(8):
+        f = lowrank_factors(sector_block(table, gx, gy, gz, s), tol=tol * 1e-3, max_rank=max_modes)
+        if f is None:
+            return None
+        per.append(f)
+    lam_max = max(np.abs(f[1][0]) for f in per if len(f[1]))
+    soff, rows, vals, residual = [0], [], [], 0.0
+    n_f = (gx // 2) * (gy // 2) * (gz // 2)
+    for zv, w, res in per:
+        keep = np.abs(w) > tol * lam_max
+        residual = max(residual, res, float(np.abs(w[~keep]).max()) if np.any(~keep) else 0.0)
+        r = int(keep.sum())
+        pad = (-r) % 4
+        rows.append(zv[keep]); vals.append(w[keep])
+        if pad:
+            rows.append(np.zeros((pad, n_f))); vals.append(np.zeros(pad))
+        soff.append(soff[-1] + r + pad)
+    if soff[-1] > max_modes:
+        return None
+    return (np.array(soff, dtype=np.int32), np.ascontiguousarray(np.concatenate(rows)), np.ascontiguousarray(np.concatenate(vals)),
+            residual)

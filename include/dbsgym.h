@@ -143,6 +143,16 @@ int dbsgym_set_coupling_spectral(DbsGymHandle* h, const int32_t* ranks8, int32_t
  * rank <= 0 switches back to the full operator (matrix / grid table). */
 int dbsgym_set_coupling_lowrank(DbsGymHandle* h, int32_t rank, const double* vecs, const double* vals);
 
+/* Sector form of the low-rank operator for regular grids with even extents (fp32 GRID handles, right after
+ * dbsgym_set_coupling_grid and before any dbsgym_set_env_params): the eigenpairs of the 8 parity-sector blocks of alpha
+ * (dbsgym_b200/geometry.py: sector_block) over the N / 8 points of the fundamental octant, a = (zq * gx/2 + xq) * gy/2 + yq:
+ * zvecs[m * N/8 + a], vals[m] (block eigenvalues), modes sorted by sector s = 4 [odd y] + 2 [odd z] + [odd x] with
+ * soff9[s] = first mode of sector s, soff9[8] = number of modes, every sector padded to a multiple of 4 modes (zero rows).
+ * 1/8 of the multiply-adds and of the eigenvector traffic of dbsgym_set_coupling_lowrank.  The library then stores the
+ * oscillators in octant order internally; every entry point of this header keeps taking and returning the natural order
+ * (dbsgym_get_state / dbsgym_set_state blobs are opaque and only valid for a handle in the same mode). */
+int dbsgym_set_coupling_lowrank_sectors(DbsGymHandle* h, const int32_t* soff9, const double* zvecs, const double* vals);
+
 /* Per-environment vectors uploaded at reset (env.py:566-598): natural frequencies after
  * remove_negative_w0, stimulation conductance of the first contact (env.py:422-423), summed
  * recording conductance (env.py:410-411; NULL = 'naive' recording kernel) and the unwrapped

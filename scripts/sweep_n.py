@@ -39,13 +39,23 @@ for gx, gy, gz in GRIDS:
     eng = KuramotoEngine(B, N, [gx, gy, gz], 2340, 0.52, precision="f32", coupling_table=table, device=LOCAL)
     lowrank = None
     if os.environ.get("SWEEP_LOWRANK"):                   # the operator in its truncated eigenbasis (step-kernel variant 11)
-        from dbsgym_b200.geometry import grid_lowrank_factors
+        from dbsgym_b200.geometry import grid_lowrank_factors, grid_sector_factors
         t_f = time.perf_counter()
-        f = grid_lowrank_factors(table, gx, gy, gz, tol=float(os.environ.get("SWEEP_LOWRANK_TOL", "1e-9")))
-        if f is None:
-            continue
-        eng.set_coupling_lowrank(*f)
-        lowrank = {"rank": int(f[0].shape[0]), "residual_over_lambda_max": float(f[2] / abs(f[1][0])), "factorisation_s": time.perf_counter() - t_f}
+        tol = float(os.environ.get("SWEEP_LOWRANK_TOL", "1e-9"))
+        if os.environ["SWEEP_LOWRANK"] == "sectors":      # sector form: eigenvectors over the fundamental octant only
+            f = grid_sector_factors(table, gx, gy, gz, tol=tol)
+            if f is None:
+                continue
+            eng.set_coupling_lowrank_sectors(*f)
+            lowrank = {"rank": int(np.count_nonzero(f[2])), "padded_modes": int(f[0][8]), "form": "sectors",
+                       "residual_over_lambda_max": float(f[3] / np.abs(f[2]).max()), "factorisation_s": time.perf_counter() - t_f}
+        else:
+            f = grid_lowrank_factors(table, gx, gy, gz, tol=tol)
+            if f is None:
+                continue
+            eng.set_coupling_lowrank(*f)
+            lowrank = {"rank": int(f[0].shape[0]), "form": "plain", "residual_over_lambda_max": float(f[2] / abs(f[1][0])),
+                       "factorisation_s": time.perf_counter() - t_f}
     tt = transient_grid(200.0, 0.05)
     sched = StepSchedule(400, tt[-1], 0.15, 0.75, 0.05)
     eng.set_schedule(sched); eng.set_reward("bbpow_action", 0.05)
@@ -92,7 +102,7 @@ for gx, gy, gz in GRIDS:
                 "dense_equivalent_tflops": WORLD * rhs * 4 * N * N * B / (k_step * 1e-3) / 1e12,
                 "transient_s": t_tr, "status": c["status"], "ctas_per_env": max(1, N // 4096), "variant": variant})
     if lowrank is not None:                               # own op count of the low-rank contraction: 2 x 4 flop per mode and oscillator
-        out[-1].update(lowrank=lowrank, executed_tflops=WORLD * rhs * (16.0 * lowrank["rank"] * N + 150.0 * N) * B / (k_step * 1e-3) / 1e12)
+        out[-1].update(lowrank=lowrank, executed_tflops=WORLD * rhs * (16.0 * lowrank.get("padded_modes", lowrank["rank"]) * N / (8 if lowrank["form"] == "sectors" else 1) + 150.0 * N) * B / (k_step * 1e-3) / 1e12)
     if RANK == 0:
         print(json.dumps(out[-1]), flush=True)
     eng.close()

@@ -5,7 +5,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def _engine(N, gz, B, force_cluster=None, precision="f32", gx=8, gy=8, mw=None):
+def _engine(N, gz, B, force_cluster=None, precision="f32", gx=8, gy=8, mw=None, sectors=False):
     from dbsgym_b200.engine import KuramotoEngine
     from dbsgym_b200.geometry import coupling_table, distances_from, neuron_grid
     from dbsgym_b200.schedule import StepSchedule, transient_grid
@@ -14,6 +14,11 @@ def _engine(N, gz, B, force_cluster=None, precision="f32", gx=8, gy=8, mw=None):
     table = coupling_table(coords, grid, [gx, gy, gz], "cos")
     assert table is not None
     eng = KuramotoEngine(B, N, [gx, gy, gz], 2340, 0.52, precision=precision, coupling_table=table, options=options)
+    if sectors:                                  # sector form of the low-rank operator: before any vector is uploaded
+        from dbsgym_b200.geometry import grid_sector_factors
+        f = grid_sector_factors(table, gx, gy, gz, tol=1e-9)
+        assert f is not None and f[3] < 2e-9 * np.abs(f[2]).max()
+        eng.set_coupling_lowrank_sectors(*f)
     tt = transient_grid(200.0, 0.05)
     sched = StepSchedule(80, tt[-1], 0.15, 0.75, 0.05)
     eng.set_schedule(sched)
@@ -111,14 +116,18 @@ def test_low_rank_kernel_on_grid_handles_single_cta_and_cluster(N, gz, C, gx, gy
     """The coupling operator of a regular grid in its truncated eigenbasis (geometry.grid_lowrank_factors: factorised sector
     by sector, never forming the N x N matrix), step-kernel variant 11, against the exact parity-sector kernels on the same
     GRID handle: one CTA per environment, forced clusters of C CTAs (the mode sums of the CTAs meet in global memory), and
-    N = 8192 where the cluster is the only way to run.  Steps at float32 rounding, counters exact."""
+    N = 8192 where the cluster is the only way to run -- in the plain form and in the sector form (oscillators stored in
+    octant order inside the library, eigenvectors over the octant only).  Steps at float32 rounding, counters exact."""
     from dbsgym_b200.geometry import grid_lowrank_factors
     acts = np.random.default_rng(1).uniform(-1, 1, (3, 3)).astype(np.float32)
     res = {}
-    modes = [("exact", None, False), ("lowrank", None, True)] + ([("lowrank_cluster", C, True)] if C else [])
+    modes = ([("exact", None, False), ("lowrank", None, True), ("sectors", None, "sectors")] +
+             ([("lowrank_cluster", C, True), ("sectors_cluster", C, "sectors")] if C else []))
     for name, force, lr in modes:
-        eng, d = _engine(N, gz, 3, force, gx=gx, gy=gy)
-        if lr:
+        eng, d = _engine(N, gz, 3, force, gx=gx, gy=gy, sectors=(lr == "sectors"))
+        if lr == "sectors":
+            assert eng.step_variant() == 11 and eng.lowrank["sectors"]
+        elif lr:
             f = grid_lowrank_factors(d["table"], gx, gy, gz, tol=1e-9)
             assert f is not None and f[0].shape[0] <= 128 and f[2] < 2e-9 * np.abs(f[1][0])
             eng.set_coupling_lowrank(*f)
