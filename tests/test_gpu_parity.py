@@ -196,6 +196,43 @@ def test_shuffled_grid_f32_low_rank_kernel_matches_oracle():
         core.close()
 
 
+def test_large_regular_grid_selects_the_sector_low_rank_form_and_matches_oracle():
+    """N = 2048 on a 16 x 16 x 8 grid through the public BatchedKuramoto: float32 'auto' takes the operator as sector-wise
+    eigenpairs over the fundamental octant (step-kernel variant 11, oscillators stored in octant order inside the library) --
+    reset transient and teacher-forced steps against the float64 oracle; coupling_eval='exact' keeps the structured kernel."""
+    from oracle import kuramoto_oracle as ko
+    import dbsgym_b200.utils as U
+    from dbsgym_b200.batched import BatchedKuramoto
+    np.random.seed(5)
+    w0, nc, ng, w0t, wl, lm = U.generate_w0_with_locus(2048, [16, 16, 8], 0.1, [7, 7, 4], 0.55, 17, 1, show=False)
+    d = make_params("env1", 5, transient_state_len=118.0, num_oscillators=2048, grid_size=[16, 16, 8], elec_coords=[[7, 6, 4]],
+                    rec_coords=[[5, 8, 3]])
+    d.update(w0=w0, w0_without_locus=w0t, locus_without_w0=wl, locus_mask=lm, neur_coords=nc, neur_grid=ng)
+    orc = ko.OracleEnv(copy.deepcopy(d))
+    core = BatchedKuramoto([copy.deepcopy(d)] * 2, precision="f32", transfer="full")
+    assert core.engine.coupling == "grid" and core.coupling_eval == "lowrank"
+    assert core.engine.step_variant() == 11 and core.engine.lowrank["sectors"]
+    exact = BatchedKuramoto([copy.deepcopy(d)] * 2, precision="f32", transfer="full", coupling_eval="exact")
+    assert exact.engine.step_variant() == 7
+    for c in (core, exact):
+        assert np.max(np.abs(c.engine.state()[0] - orc.sol_state[-1])) < 2e-3          # 118-unit transient with rejections
+        c.engine.counters(reset=True)
+    for k, a in enumerate((0.6, -0.3, 0.9)):
+        y_before = orc.sol_state[-1].copy()
+        o_ref, r_ref, *_ = orc.step(np.array([a], dtype=np.float32))
+        for name, c in (("lowrank", core), ("exact", exact)):
+            c.engine.set_env_params(None, y0=np.tile(y_before, (2, 1)))                # teacher-forced
+            obs, rew, done = c.step(np.array([a, a], dtype=np.float32))
+            err = np.max(np.abs(c.engine.state()[0] - orc.sol_state[-1]))
+            assert err < 1e-5, (name, k, err)
+            assert np.max(np.abs(c.theta_records(0) - orc.theta_records)) < 2e-6
+            assert np.max(np.abs(c.theta_mean(0) - orc.theta_mean)) < 2e-6
+    for c in (core, exact):
+        cc = c.engine.counters()
+        assert (cc["accepted"], cc["rejected"], cc["rhs_evals"], cc["status"]) == (2 * 3 * 5, 0, 2 * 3 * 32, 0)
+        c.close()
+
+
 def test_half_grid_256_oscillators():
     """N = 256 (first four z-planes, BASELINE config 5's smallest point) on the GRID kernel."""
     from oracle import kuramoto_oracle as ko
