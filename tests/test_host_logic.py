@@ -343,3 +343,44 @@ def test_lowrank_factors_reproduce_a_shuffled_operator():
     wf = wf[np.argsort(-np.abs(wf))]
     assert len(w2) == np.count_nonzero(np.abs(wf) > 1e-9 * np.abs(wf[0])) and np.allclose(w2, wf[:len(w2)], rtol=1e-6, atol=1e-9 * abs(wf[0]))
     assert abs(res2 - np.abs(wf[len(w2)])) < 1e-2 * res2
+
+
+def test_grid_sector_factors_and_grid_lowrank_factors_agree_with_the_full_matrix():
+    """The two factorisations of a regular grid's operator that never form the N x N matrix (sector-wise eigenpairs over the
+    fundamental octant for dbsgym_set_coupling_lowrank_sectors; the same carried back to the grid for
+    dbsgym_set_coupling_lowrank) against the dense alpha of a 16 x 16 x 8 grid: eigenvalues, reconstruction, padding."""
+    from dbsgym_b200 import geometry
+    gx, gy, gz, N = 16, 16, 8, 2048
+    coords, grid = geometry.neuron_grid(gx, gy, gz, N, 0.1)
+    table = geometry.coupling_table(coords, grid, [gx, gy, gz], "cos")
+    alpha = geometry.coupling_rows(coords, np.arange(N), "cos")
+    soff, z, w, res = geometry.grid_sector_factors(table, gx, gy, gz, tol=1e-9)
+    assert soff.shape == (9,) and soff[0] == 0 and np.all(np.diff(soff) % 4 == 0) and z.shape == (soff[8], N // 8)
+    v, lam, res2 = geometry.grid_lowrank_factors(table, gx, gy, gz, tol=1e-9)
+    kept = np.sort(np.abs(w[w != 0]))[::-1]
+    assert len(kept) == len(lam) and np.allclose(kept, np.abs(lam), rtol=1e-9)
+    rec = v.T @ (lam[:, None] * v)
+    assert abs(np.linalg.norm(alpha - rec, 2) - res2) < 2e-2 * res2 and res2 < 1e-9 * np.abs(lam[0]) and abs(res - res2) < 1e-2 * res2
+    # sector form applied by hand: x -> sector coordinates over the octant -> modes -> back, against alpha @ x
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(N).reshape(gz, gx, gy)
+    hz, hx, hy = gz // 2, gx // 2, gy // 2
+    out = np.zeros_like(x)
+    for s in range(8):
+        py, pz, px = (-1.0 if s & 4 else 1.0), (-1.0 if s & 2 else 1.0), (-1.0 if s & 1 else 1.0)
+        X = np.zeros((hz, hx, hy))
+        imgs = []
+        for mz, sz in ((0, 1.0), (1, pz)):
+            for mx, sx in ((0, 1.0), (1, px)):
+                for my, sy in ((0, 1.0), (1, py)):
+                    sl = (slice(None, None, -1) if mz else slice(None), slice(None, None, -1) if mx else slice(None),
+                          slice(None, None, -1) if my else slice(None))
+                    X += sz * sx * sy * x[sl][:hz, :hx, :hy]
+                    imgs.append((sl, sz * sx * sy))
+        zs, ws = z[soff[s]:soff[s + 1]], w[soff[s]:soff[s + 1]]
+        y = (zs.T @ (ws * (zs @ X.ravel()))).reshape(hz, hx, hy) / 8.0
+        for sl, sign in imgs:
+            full = np.zeros_like(x)
+            full[:hz, :hx, :hy] = sign * y
+            out += full[sl]
+    assert np.max(np.abs(out.ravel() - alpha @ x.ravel())) < 1e-8 * np.abs(alpha @ x.ravel()).max()
