@@ -189,9 +189,17 @@ class BatchedKuramoto:
         """reset() of the listed environments, in the order given (reference env.py:467-614)."""
         ids = list(ids)
         if self.host_batch is not None:
-            w0, stim, rec, y0, electrodes = self.host_batch.begin_episodes(ids)
+            w0, stim, rec, y0, electrodes, el_ch, w0_ch = self.host_batch.begin_episodes(ids, changed_only=True)
             ids_a = np.asarray(ids, dtype=np.int32)
-            self.engine.set_env_params(ids_a, w0=w0, stim=stim, rec=rec, y0=y0)
+            # the initial phases are new every time; natural frequencies and electrode conductances only where they changed
+            if w0_ch.all() and el_ch.all():
+                self.engine.set_env_params(ids_a, w0=w0, stim=stim, rec=rec, y0=y0)
+            else:
+                self.engine.set_env_params(ids_a, y0=y0)
+                if w0_ch.any():
+                    self.engine.set_env_params(ids_a[w0_ch], w0=np.ascontiguousarray(w0[w0_ch]))
+                if el_ch.any():
+                    self.engine.set_env_params(ids_a[el_ch], stim=stim, rec=rec)
             self.engine.set_episode(ids_a, step_idx=0, episode_len=self._episode_counts[ids_a])
             for r, i in enumerate(ids):
                 self.electrodes[i] = electrodes[r]

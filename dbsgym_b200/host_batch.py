@@ -112,6 +112,8 @@ class HostBatch:
             self.walk = np.array([h.w0_process for h in hosts], dtype=np.float64)         # [B, M + 1, N]
         self.table = stim_rec_table()
         self._electrodes = [None] * B
+        self._last_key = np.full((B, 7), np.nan)       # (contacts, conduct_modifier) the device holds stim / rec vectors for
+        self._w0_sent = np.zeros(B, dtype=bool)        # the device holds this environment's current w0
         self.lo, self.hi = 1, min(p0["grid_size"]) - 2
 
     # ------------------------------------------------------------------------------------------------------
@@ -133,9 +135,12 @@ class HostBatch:
             h.w0_process = self.walk[i]
 
     # ------------------------------------------------------------------------------------------------------
-    def begin_episodes(self, ids):
+    def begin_episodes(self, ids, changed_only=False):
         """env.py:467-598 for the listed environments, in that order.  Returns (w0, stim, rec, y0, electrodes): arrays
-        [n, N] float64 and the ElectrodeModel of every environment."""
+        [n, N] float64 and the ElectrodeModel of every environment.  With ``changed_only`` the tuple continues with two
+        boolean masks (el_changed, w0_changed) over the listed environments and ``stim`` / ``rec`` hold only the rows of the
+        environments whose electrode (contacts or conduct_modifier) differs from what the caller was given last time -- most
+        resets change neither, and the conductance vectors are 2 x 4 KB per environment to build and upload."""
         ids = np.asarray(ids, dtype=np.int64)
         n, N = ids.size, self.N
         everyone = n == self.B and np.array_equal(ids, np.arange(self.B))
@@ -242,16 +247,31 @@ class HostBatch:
 
         # ---- electrodes: one model per distinct (contacts, conduct_modifier), shared by the environments that have it ----
         keys = np.column_stack([self.elec[ids], self.rec[ids], self.encaps[ids]])
-        uniq, inv = np.unique(keys, axis=0, return_inverse=True)
-        inv = np.asarray(inv).reshape(-1)
-        models = [cached_electrode(self.p0, self._cm(k[6]), [[int(v) for v in k[0:3]]], [[int(v) for v in k[3:6]]], 0) for k in uniq]
-        stim = np.stack([m.stim_vector() for m in models])[inv]
-        rec = np.stack([m.rec_vector() for m in models])[inv]
-        electrodes = [models[j] for j in inv]
+        el_changed = np.any(keys != self._last_key[ids], axis=1) if changed_only else np.ones(n, dtype=bool)
+        rows = np.flatnonzero(el_changed)
+        if rows.size:
+            uniq, inv = np.unique(keys[rows], axis=0, return_inverse=True)
+            inv = np.asarray(inv).reshape(-1)
+            models = [cached_electrode(self.p0, self._cm(k[6]), [[int(v) for v in k[0:3]]], [[int(v) for v in k[3:6]]], 0) for k in uniq]
+            stim = np.stack([m.stim_vector() for m in models])[inv]
+            rec = np.stack([m.rec_vector() for m in models])[inv]
+            for r, j in zip(rows, inv):
+                self._electrodes[int(ids[r])] = models[j]
+        else:
+            stim = rec = np.empty((0, N))
+        electrodes = [self._electrodes[int(i)] for i in ids]
         if self.B <= 256:            # small batches: keep the HostEnvState objects current for callers that hold on to one
             for i in ids:
                 self.sync_to_host(int(i), self.hosts[int(i)])
-        return w0, stim, rec, y0, electrodes
+        self._last_key[ids] = keys                 # (either way the caller now has the current vectors of these environments)
+        if not changed_only:
+            self._w0_sent[ids] = True
+            return w0, stim, rec, y0, electrodes
+        w0_changed = ~self._w0_sent[ids] | (n_fix > 0)
+        if self.drift:
+            w0_changed |= f_pl | f_rg
+        self._w0_sent[ids] = True
+        return w0, stim, rec, y0, electrodes, el_changed, w0_changed
 
     def _cm(self, v):
         """conduct_modifier as the per-environment path passes it (a Python float)."""

@@ -44,6 +44,7 @@ def _state():
 def test_batched_reset_equals_sequential_resets(cfg, over, compat, rounds):
     _capi.build()
     B = 7
+    dev = {}                                   # what a device that only receives the CHANGED vectors would hold (changed_only path)
     dicts = _dicts(cfg, B, **over)
     # a natural-frequency vector with non-positive entries in one environment: remove_negative_w0 must draw for it
     dicts[3]["w0_without_locus"] = dicts[3]["w0_without_locus"].copy()
@@ -62,7 +63,20 @@ def test_batched_reset_equals_sequential_resets(cfg, over, compat, rounds):
         setups = [a[i].begin_episode() for i in ids]
         after_a = _state()
         np.random.set_state(st)
-        w0, stim, rec, y0, electrodes = hb.begin_episodes(ids)
+        if r % 2:                              # alternate between the full return and the changed-rows-only one
+            w0, stim_c, rec_c, y0, electrodes, el_ch, w0_ch = hb.begin_episodes(ids, changed_only=True)
+            assert stim_c.shape[0] == rec_c.shape[0] == int(el_ch.sum())
+            for k, i in enumerate(np.asarray(ids)[el_ch]):
+                dev[("stim", int(i))], dev[("rec", int(i))] = stim_c[k], rec_c[k]
+            for k, i in enumerate(ids):
+                if w0_ch[k]:
+                    dev[("w0", i)] = w0[k]
+                assert np.array_equal(dev[("w0", i)], w0[k]), "a w0 marked unchanged differs from what was sent before"
+            stim = np.stack([dev[("stim", i)] for i in ids]); rec = np.stack([dev[("rec", i)] for i in ids])
+        else:
+            w0, stim, rec, y0, electrodes = hb.begin_episodes(ids)
+            for k, i in enumerate(ids):
+                dev[("stim", i)], dev[("rec", i)], dev[("w0", i)] = stim[k], rec[k], w0[k]
         after_b = _state()
         assert np.array_equal(after_a[0], after_b[0]) and after_a[1:] == after_b[1:], f"stream position differs after round {r}"
         for k, (i, s) in enumerate(zip(ids, setups)):
