@@ -92,10 +92,10 @@ class BatchedKuramoto:
                                      action_bounds=p0["dbs_action_bounds"], options=engine_options)
         self.coupling_eval = "lowrank" if lowrank is not None else "exact"
         gs = [int(g) for g in p0["grid_size"]]
-        if (table is not None and coupling_eval != "exact" and precision == "f32" and self.n_osc >= 2048 and
+        if (table is not None and coupling_eval != "exact" and precision == "f32" and self.n_osc >= 1024 and
                 self.n_osc == gs[0] * gs[1] * gs[2] and all(g % 2 == 0 for g in gs)):
             # large regular grids: the operator as sector-wise eigenpairs over the fundamental octant (O(N r / 8) per evaluation;
-            # from N = 2048 up faster than the exact sector blocks -- profiles/r02_sweep_n_lowrank_sectors_1gpu.jsonl)
+            # from N = 1024 up faster than the exact sector blocks -- profiles/r02_sweep_n_lowrank_sectors_1gpu.jsonl)
             from .geometry import grid_sector_factors
             f = grid_sector_factors(table, gs[0], gs[1], gs[2], tol=spectral_tol)
             if f is not None:

@@ -845,41 +845,57 @@ __device__ __forceinline__ void couple_dense(const real* __restrict__ sc, const 
 // Phase 1, warps over modes (four at a time): V rows stream from global / L2 (coalesced), the (sin, cos) operand comes
 // from shared memory, one shuffle reduction per mode and warp.  Phase 2, threads over their 8 oscillators.
 // (cluster mode: every CTA sums over its own slice of oscillators [off, off + n) and leaves unscaled partial sums in `out`)
+// one group of four modes m0 .. m0 + 3 by one warp: rows of length ld, entries [off, off + n) against the operand x4
+__device__ __forceinline__ void lowrank_project_group(const float4* __restrict__ x4, const float* __restrict__ V,
+                                                      const float* __restrict__ lam, int m0, int ld, int off, int n,
+                                                      float2* __restrict__ out, int lane) {
+    const int n4 = n >> 2;
+    float2 acc[4];
+    const float4* v4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { acc[q] = make_float2(0.f, 0.f); v4[q] = reinterpret_cast<const float4*>(V + (size_t)(m0 + q) * ld + off); }
+#pragma unroll 4
+    for (int j4 = lane; j4 < n4; j4 += 32) {
+        const float4 xa = x4[2 * j4], xb = x4[2 * j4 + 1];          // (s, c) of entries 4 j4 .. 4 j4 + 3
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 v = __ldg(v4[q] + j4);
+            acc[q] = __ffma2_rn(make_float2(v.x, v.x), make_float2(xa.x, xa.y), acc[q]);
+            acc[q] = __ffma2_rn(make_float2(v.y, v.y), make_float2(xa.z, xa.w), acc[q]);
+            acc[q] = __ffma2_rn(make_float2(v.z, v.z), make_float2(xb.x, xb.y), acc[q]);
+            acc[q] = __ffma2_rn(make_float2(v.w, v.w), make_float2(xb.z, xb.w), acc[q]);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o);
+            acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
+        }
+    }
+    if (lane < 4) {
+        const float2 a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+        const float l = lam ? __ldg(lam + m0 + lane) : 1.f;
+        out[m0 + lane] = make_float2(l * a.x, l * a.y);
+    }
+}
 __device__ __forceinline__ void couple_lowrank_project(const float* __restrict__ sc, const float* __restrict__ V,
                                                        const float* __restrict__ lam, int R4, int Np, int off, int n,
                                                        float2* __restrict__ out, int lane, int warp, int nwarps) {
-    const float4* x4 = reinterpret_cast<const float4*>(sc);
-    const int n4 = n >> 2;
+    for (int m0 = warp * 4; m0 < R4; m0 += nwarps * 4)
+        lowrank_project_group(reinterpret_cast<const float4*>(sc), V, lam, m0, Np, off, n, out, lane);
+}
+// sector form: the groups of ALL sectors are dealt out to the warps together (a sector has only 4 .. 32 modes), each against
+// the operand of its own sector, XS[sector][point]
+__device__ __forceinline__ void couple_lowrank_project_sectors(const float* __restrict__ xs, const float* __restrict__ Z,
+                                                               const float* __restrict__ lam, const int32_t* __restrict__ soff,
+                                                               int R4, int Np8, int off, int n, float2* __restrict__ out,
+                                                               int lane, int warp, int nwarps) {
     for (int m0 = warp * 4; m0 < R4; m0 += nwarps * 4) {
-        float2 acc[4];
-        const float4* v4[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { acc[q] = make_float2(0.f, 0.f); v4[q] = reinterpret_cast<const float4*>(V + (size_t)(m0 + q) * Np + off); }
-#pragma unroll 2
-        for (int j4 = lane; j4 < n4; j4 += 32) {
-            const float4 xa = x4[2 * j4], xb = x4[2 * j4 + 1];          // (s, c) of oscillators off + 4 j4 .. + 3
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float4 v = __ldg(v4[q] + j4);
-                acc[q] = __ffma2_rn(make_float2(v.x, v.x), make_float2(xa.x, xa.y), acc[q]);
-                acc[q] = __ffma2_rn(make_float2(v.y, v.y), make_float2(xa.z, xa.w), acc[q]);
-                acc[q] = __ffma2_rn(make_float2(v.z, v.z), make_float2(xb.x, xb.y), acc[q]);
-                acc[q] = __ffma2_rn(make_float2(v.w, v.w), make_float2(xb.z, xb.w), acc[q]);
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                acc[q].x += __shfl_xor_sync(0xffffffffu, acc[q].x, o);
-                acc[q].y += __shfl_xor_sync(0xffffffffu, acc[q].y, o);
-            }
-        }
-        if (lane < 4) {
-            const float2 a = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
-            const float l = lam ? __ldg(lam + m0 + lane) : 1.f;
-            out[m0 + lane] = make_float2(l * a.x, l * a.y);
-        }
+        int sct = 0;
+        while (sct < 7 && m0 >= soff[sct + 1]) ++sct;
+        lowrank_project_group(reinterpret_cast<const float4*>(xs + 2 * (size_t)sct * n), Z, lam, m0, Np8, off, n, out, lane);
     }
 }
 __device__ __forceinline__ void couple_lowrank_expand(const float2* __restrict__ Cs, const float* __restrict__ V, int R4, int Np,
@@ -925,15 +941,22 @@ __device__ __forceinline__ void couple_lowrank_expand_sectors(const float2* __re
     const float* col = Z + point;
 #pragma unroll
     for (int sct = 0; sct < 8; ++sct) {
-        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f), acc2 = make_float2(0.f, 0.f), acc3 = make_float2(0.f, 0.f);
         const int m1 = soff[sct + 1];
-        for (int m = soff[sct]; m < m1; m += 2) {          // (sector counts are multiples of 4)
+        // four modes per trip (sector counts are multiples of 4), all loads of a trip issued before its arithmetic.  The
+        // mode-major table keeps a warp's loads coalesced (128 bytes per mode); a point-major copy -- one wide load per 4
+        // modes and thread -- was measured and is slower from N = 4096 up (32 different lines per request).
+#pragma unroll 2
+        for (int m = soff[sct]; m < m1; m += 4) {
             const float z0 = __ldg(col + (size_t)m * Np8), z1 = __ldg(col + (size_t)(m + 1) * Np8);
-            const float4 c = *reinterpret_cast<const float4*>(Cs + m);
-            acc0 = __ffma2_rn(make_float2(z0, z0), make_float2(c.x, c.y), acc0);
-            acc1 = __ffma2_rn(make_float2(z1, z1), make_float2(c.z, c.w), acc1);
+            const float z2 = __ldg(col + (size_t)(m + 2) * Np8), z3 = __ldg(col + (size_t)(m + 3) * Np8);
+            const float4 ca = *reinterpret_cast<const float4*>(Cs + m), cb = *reinterpret_cast<const float4*>(Cs + m + 2);
+            acc0 = __ffma2_rn(make_float2(z0, z0), make_float2(ca.x, ca.y), acc0);
+            acc1 = __ffma2_rn(make_float2(z1, z1), make_float2(ca.z, ca.w), acc1);
+            acc2 = __ffma2_rn(make_float2(z2, z2), make_float2(cb.x, cb.y), acc2);
+            acc3 = __ffma2_rn(make_float2(z3, z3), make_float2(cb.z, cb.w), acc3);
         }
-        as[sct] = acc0.x + acc1.x; ac[sct] = acc0.y + acc1.y;
+        as[sct] = (acc0.x + acc1.x) + (acc2.x + acc3.x); ac[sct] = (acc0.y + acc1.y) + (acc2.y + acc3.y);
     }
     wht8_pairs(as, ac);
 }
@@ -1364,16 +1387,10 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                     // one pass of phase 1 over the oscillators (plain form) or over the octant points of a sector (sector form):
                     // all modes [m_lo, m_hi) against `n` operand entries at `x`, eigenvector rows of length `ld` starting at `off`
                     auto project = [&](const float* lamp, float2* out) {
-                        if (p.lr_sectors) {
-#pragma unroll 1
-                            for (int sct = 0; sct < 8; ++sct) {
-                                const int m_lo = p.lr_soff[sct], m_hi = p.lr_soff[sct + 1];
-                                if (m_hi > m_lo)
-                                    couple_lowrank_project(opnd + 2 * sct * nt, p.lr_v + (size_t)m_lo * (Np >> 3),
-                                                           lamp ? lamp + m_lo : nullptr, m_hi - m_lo, Np >> 3, crank * nt, nt,
-                                                           out + m_lo, lane, warp, nwarps);
-                            }
-                        } else couple_lowrank_project(opnd, p.lr_v, lamp, p.lr_rank, Np, crank * Nl, Nl, out, lane, warp, nwarps);
+                        if (p.lr_sectors)
+                            couple_lowrank_project_sectors(opnd, p.lr_v, lamp, p.lr_soff, p.lr_rank, Np >> 3, crank * nt, nt, out,
+                                                           lane, warp, nwarps);
+                        else couple_lowrank_project(opnd, p.lr_v, lamp, p.lr_rank, Np, crank * Nl, Nl, out, lane, warp, nwarps);
                     };
                     if constexpr (CL != 0) {
                         // every CTA of the cluster sums over its own oscillators; the partial sums meet in global memory (L2)
