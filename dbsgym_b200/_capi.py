@@ -24,7 +24,7 @@ REWARD_BBPOW, REWARD_TEMP_CONST, REWARD_BBPOW_THRESH = 0, 1, 2
 
 EXPORTS = [
     "dbsgym_abi_version", "dbsgym_build_flags", "dbsgym_step_variant", "dbsgym_create", "dbsgym_destroy", "dbsgym_last_error",
-    "dbsgym_set_coupling_grid", "dbsgym_set_coupling_dense", "dbsgym_set_coupling_spectral", "dbsgym_set_coupling_lowrank", "dbsgym_set_coupling_lowrank_sectors", "dbsgym_set_env_params",
+    "dbsgym_set_coupling_grid", "dbsgym_set_coupling_dense", "dbsgym_set_coupling_spectral", "dbsgym_set_coupling_lowrank", "dbsgym_set_coupling_lowrank_sectors", "dbsgym_set_oscillator_order", "dbsgym_set_env_params",
     "dbsgym_set_recording", "dbsgym_set_schedule", "dbsgym_set_reward", "dbsgym_set_episode",
     "dbsgym_transient", "dbsgym_step", "dbsgym_step_host", "dbsgym_step_host_samples", "dbsgym_host_mirror", "dbsgym_step_host_mirror", "dbsgym_step_host_mirror_begin", "dbsgym_step_host_mirror_end", "dbsgym_get_obs_host",
     "dbsgym_get_lfp", "dbsgym_get_rewards", "dbsgym_get_phases", "dbsgym_get_window",
@@ -168,6 +168,7 @@ def load():
         "dbsgym_set_coupling_spectral": (C.c_int, [vp, vp, C.c_int32, vp, vp]),
         "dbsgym_set_coupling_lowrank": (C.c_int, [vp, C.c_int32, vp, vp]),
         "dbsgym_set_coupling_lowrank_sectors": (C.c_int, [vp, vp, vp, vp]),
+        "dbsgym_set_oscillator_order": (C.c_int, [vp, vp]),
         "dbsgym_set_env_params": (C.c_int, [vp, vp, C.c_int32, vp, vp, vp, vp]),
         "dbsgym_set_recording": (C.c_int, [vp, C.c_int32]),
         "dbsgym_set_schedule": (C.c_int, [vp, C.c_int32, vp, vp, vp, C.c_int32, vp, C.c_int32]),

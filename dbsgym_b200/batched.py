@@ -76,9 +76,19 @@ class BatchedKuramoto:
         table = None if force_dense else coupling_table(p0["neur_coords"], p0["neur_grid"], p0["grid_size"],
                                                         p0["spatial_kernel"], p0["wavelet_amp"],
                                                         p0["wavelet_steepness"])
-        alpha = lowrank = None
+        alpha = lowrank = order = None
         if coupling_eval not in ("auto", "exact", "spectral"):
             raise ValueError("coupling_eval must be 'auto', 'exact' or 'spectral'")
+        if table is None and not force_dense and precision == "f32" and coupling_eval != "exact":
+            # a shuffled regular grid (utils.py:490 shuffle=True) is a permutation of the regular one: the library stores it in
+            # grid order (the permutation is applied at the ABI boundary) and runs the structured / spectral GRID kernels
+            from .geometry import grid_permutation
+            order = grid_permutation(p0["neur_grid"], p0["grid_size"])
+            if order is not None:
+                table = coupling_table(np.asarray(p0["neur_coords"])[order], np.asarray(p0["neur_grid"])[order], p0["grid_size"],
+                                       p0["spatial_kernel"], p0["wavelet_amp"], p0["wavelet_steepness"])
+                if table is None:
+                    order = None
         if table is None:
             alpha = coupling_rows(p0["neur_coords"], np.arange(self.n_osc), p0["spatial_kernel"],
                                   p0["wavelet_amp"], p0["wavelet_steepness"])
@@ -87,7 +97,7 @@ class BatchedKuramoto:
                 from .geometry import lowrank_factors
                 lowrank = lowrank_factors(alpha, tol=spectral_tol)
         self.engine = KuramotoEngine(B, self.n_osc, p0["grid_size"], self.window, p0["K"],
-                                     precision=precision, coupling_table=table, alpha=alpha, lowrank=lowrank, device=device,
+                                     precision=precision, coupling_table=table, alpha=alpha, lowrank=lowrank, order=order, device=device,
                                      max_step_samples=max(self.schedule.max_samples, 20),
                                      action_bounds=p0["dbs_action_bounds"], options=engine_options)
         self.coupling_eval = "lowrank" if lowrank is not None else "exact"

@@ -105,7 +105,20 @@ struct DbsGymHandle {
     float* lr_v = nullptr; float* lr_lam = nullptr; int lr_rank = 0;
     float2* lr_part = nullptr;           // cluster mode: per-CTA mode sums [B][2][cluster][lr_rank]
     // sector form of the low-rank operator: oscillators stored in octant order (perm[d] = natural index of device position d)
-    int32_t* lr_soff = nullptr; bool lr_sectors = false; std::vector<int32_t> perm; bool params_set = false;
+    int32_t* lr_soff = nullptr; bool lr_sectors = false; bool params_set = false;
+    // order of the oscillators on the device: perm[d] = the CALLER's index of the oscillator at device position d (empty =
+    // identity).  Composed of the caller's own order (dbsgym_set_oscillator_order: a shuffled regular grid is stored in grid
+    // order) and the octant order of the sector form; applied wherever per-oscillator data cross the ABI.
+    std::vector<int32_t> perm, user_order, internal_order;
+    void recompute_order() {
+        perm.clear();
+        if (user_order.empty() && internal_order.empty()) return;
+        perm.resize((size_t)N);
+        for (int d = 0; d < N; ++d) {
+            const int nat = internal_order.empty() ? d : internal_order[d];
+            perm[d] = user_order.empty() ? nat : user_order[nat];
+        }
+    }
     unsigned long long n_launches = 0;   // kernels launched by this handle (dbsgym_launch_count)
     // ordering between the private stream and caller streams (dbsgym_step / dbsgym_transient on a user stream)
     cudaEvent_t ev_own = nullptr, ev_user = nullptr; bool user_pending = false;
@@ -870,7 +883,7 @@ int dbsgym_set_coupling_lowrank(DbsGymHandle* h, int32_t rank, const double* vec
     std::vector<float> v((size_t)R4 * Np, 0.f), lam((size_t)R4, 0.f);
     for (int m = 0; m < rank; ++m) {
         lam[m] = (float)vals[m];
-        for (int i = 0; i < N; ++i) v[(size_t)m * Np + i] = (float)vecs[(size_t)m * N + i];
+        for (int i = 0; i < N; ++i) v[(size_t)m * Np + i] = (float)vecs[(size_t)m * N + (h->perm.empty() ? i : h->perm[i])];
     }
     CU(h, cudaMalloc(&h->lr_v, v.size() * sizeof(float)));
     CU(h, cudaMalloc(&h->lr_lam, lam.size() * sizeof(float)));
@@ -879,6 +892,25 @@ int dbsgym_set_coupling_lowrank(DbsGymHandle* h, int32_t rank, const double* vec
     if (h->cluster > 1) CU(h, cudaMalloc(&h->lr_part, (size_t)h->B * 2 * h->cluster * R4 * sizeof(float2)));
     h->lr_rank = R4;
     h->have_coupling = true;
+    return DBSGYM_OK;
+}
+
+int dbsgym_set_oscillator_order(DbsGymHandle* h, const int32_t* order) {
+    if (!h) return DBSGYM_EINVAL;
+    if (h->params_set || h->lr_rank > 0)
+        return fail(h, DBSGYM_ESTATE, "set the oscillator order right after dbsgym_create, before any per-oscillator data are uploaded");
+    if (h->f64) return fail(h, DBSGYM_ESTATE, "oscillator orders are applied on fp32 handles (fp64 parity mode keeps the caller's order)");
+    if (h->N != h->Np) return fail(h, DBSGYM_ESTATE, "a padded handle keeps the caller's order");
+    h->user_order.clear();
+    if (order) {
+        std::vector<uint8_t> seen((size_t)h->N, 0);
+        for (int d = 0; d < h->N; ++d) {
+            if (order[d] < 0 || order[d] >= h->N || seen[order[d]]) return fail(h, DBSGYM_EINVAL, "order is not a permutation of 0 .. n_osc - 1");
+            seen[order[d]] = 1;
+        }
+        h->user_order.assign(order, order + h->N);
+    }
+    h->recompute_order();
     return DBSGYM_OK;
 }
 
@@ -905,16 +937,17 @@ int dbsgym_set_coupling_lowrank_sectors(DbsGymHandle* h, const int32_t* soff9, c
     if (need > (size_t)max_smem) return fail(h, DBSGYM_EINVAL, "%d modes need %zu bytes of shared memory, the device allows %d", R, need, max_smem);
     // octant order: device position 8 a + g holds the image g = 4 my + 2 mz + mx of octant point a = (zq * gx/2 + xq) * gy/2 + yq
     const int hx = gx / 2, hy = gy / 2, hz = gz / 2, P8 = N / 8;
-    h->perm.assign((size_t)N, 0);
+    h->internal_order.assign((size_t)N, 0);
     for (int zq = 0; zq < hz; ++zq)
         for (int xq = 0; xq < hx; ++xq)
             for (int yq = 0; yq < hy; ++yq) {
                 const int a = (zq * hx + xq) * hy + yq;
                 for (int g = 0; g < 8; ++g) {
                     const int z = (g & 2) ? gz - 1 - zq : zq, x = (g & 1) ? gx - 1 - xq : xq, y = (g & 4) ? gy - 1 - yq : yq;
-                    h->perm[(size_t)a * 8 + g] = (z * gx + x) * gy + y;
+                    h->internal_order[(size_t)a * 8 + g] = (z * gx + x) * gy + y;
                 }
             }
+    h->recompute_order();
     std::vector<float> z((size_t)R * P8), lam((size_t)R);
     for (int m = 0; m < R; ++m) {
         lam[m] = (float)(vals[m] / 8.0);               // (alpha x)[g a] = 1/8 sum_s chi_s(g) (block_s X_s)[a]

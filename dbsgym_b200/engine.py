@@ -41,9 +41,10 @@ def _f64(a, shape=None):
 
 class KuramotoEngine:
     def __init__(self, n_envs, n_osc, grid_size, window, K, *, precision="f32", coupling_table=None,
-                 alpha=None, lowrank=None, device=0, max_step_samples=20, rtol=1e-5, atol=1e-5, dt0=0.05,
+                 alpha=None, lowrank=None, order=None, device=0, max_step_samples=20, rtol=1e-5, atol=1e-5, dt0=0.05,
                  action_bounds=(-5.0, 5.0), max_steps=4096, options=None):
-        """``options``: tuning / diagnostic switches of DbsGymConfig (include/dbsgym.h) -- ``mw`` (None auto, False
+        """``order``: order[d] = the caller's index of the oscillator at grid position d (dbsgym.h: dbsgym_set_oscillator_order).
+        ``options``: tuning / diagnostic switches of DbsGymConfig (include/dbsgym.h) -- ``mw`` (None auto, False
         never, True always use the multi-worker step kernel), ``force_cluster``, ``ctas_per_sm`` and the boolean A/B
         switches ``no_geo1``, ``no_sym``, ``no_fsal_reuse``, ``no_fused_obs``, ``no_fast_obs``, ``no_warp_kernel``."""
         if precision not in ("f32", "f64"):
@@ -88,6 +89,12 @@ class KuramotoEngine:
             self._h = None
             raise _capi.DbsGymError(f"dbsgym_create failed ({rc}): {msg.decode() if msg else '?'}")
         self.device = int(device)
+        self.order = None
+        if order is not None:                        # the caller's oscillators are a permutation of the regular grid
+            o = np.ascontiguousarray(order, dtype=np.int32)
+            assert o.shape == (self.n_osc,)
+            self._ck(self.lib.dbsgym_set_oscillator_order(self._h, _capi.ptr(o)))
+            self.order = o
         if coupling_table is not None:
             t = _f64(coupling_table)
             self._ck(self.lib.dbsgym_set_coupling_grid(self._h, _capi.ptr(t)))

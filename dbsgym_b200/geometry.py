@@ -63,6 +63,24 @@ def grid_structure(neur_grid, grid_size):
     return gx, gy, n // (gx * gy)
 
 
+def grid_permutation(neur_grid, grid_size):
+    """``order`` with ``neur_grid[order]`` = the un-shuffled regular grid (row d = z*gx*gy + x*gy + y), when ``neur_grid`` is a
+    permutation of the first N rows of that grid (utils.py:483-497 with shuffle=True and n_neurons = whole z-planes); None when it
+    is not a permutation of them -- or already in grid order."""
+    g = np.asarray(neur_grid)
+    gx, gy, gz = (int(v) for v in grid_size)
+    n = g.shape[0]
+    if g.ndim != 2 or g.shape[1] != 3 or n % (gx * gy) != 0 or n > gx * gy * gz or not np.issubdtype(g.dtype, np.integer):
+        return None
+    if g.min() < 0 or g[:, 0].max() >= gx or g[:, 1].max() >= gy or g[:, 2].max() >= gz:
+        return None
+    nat = (g[:, 2] * gx + g[:, 0]) * gy + g[:, 1]            # grid row of every caller row
+    order = np.argsort(nat, kind="stable")
+    if not np.array_equal(nat[order], np.arange(n)) or np.array_equal(order, np.arange(n)):
+        return None
+    return order.astype(np.int32)
+
+
 def coupling_table(neur_coords, neur_grid, grid_size, spatial_kernel, wavelet_amp=1.0,
                    wavelet_steepness=1.0, check_rows=6, tol=1e-12):
     """Block-Toeplitz table ``T[(dz*gx+dx)*gy + dy]`` of the coupling operator, or None when the

@@ -153,6 +153,13 @@ int dbsgym_set_coupling_lowrank(DbsGymHandle* h, int32_t rank, const double* vec
  * (dbsgym_get_state / dbsgym_set_state blobs are opaque and only valid for a handle in the same mode). */
 int dbsgym_set_coupling_lowrank_sectors(DbsGymHandle* h, const int32_t* soff9, const double* zvecs, const double* vals);
 
+/* Order of the oscillators (fp32 handles, right after dbsgym_create): order[d] = the caller's index of the oscillator that
+ * sits at position d of the regular grid (row d = z * gx * gy + x * gy + y).  A grid whose neurons were shuffled
+ * (utils.py:483-497 shuffle=True with n_neurons = the whole grid) is thereby stored in grid order inside the library and
+ * runs the structured / spectral GRID kernels instead of the DENSE fallback; every entry point of this header keeps taking
+ * and returning per-oscillator data in the caller's order.  order == NULL: identity. */
+int dbsgym_set_oscillator_order(DbsGymHandle* h, const int32_t* order);
+
 /* Per-environment vectors uploaded at reset (env.py:566-598): natural frequencies after
  * remove_negative_w0, stimulation conductance of the first contact (env.py:422-423), summed
  * recording conductance (env.py:410-411; NULL = 'naive' recording kernel) and the unwrapped

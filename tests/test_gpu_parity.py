@@ -162,10 +162,12 @@ def test_shuffled_grid_uses_dense_path_and_matches_oracle():
     core.close()
 
 
-def test_shuffled_grid_f32_low_rank_kernel_matches_oracle():
-    """Shuffled coordinates in float32: the DENSE operator runs in its truncated eigenbasis (step-kernel variant 11, 32 modes:
-    a permutation does not change the spectrum) -- teacher-forced steps against the float64 oracle at the float32
-    tolerance, exact counters; coupling_eval='exact' keeps the full matrix (variant 1) and must agree."""
+def test_shuffled_grid_f32_runs_the_grid_kernels_through_the_order_map_and_the_low_rank_kernel():
+    """Shuffled coordinates in float32 (utils.py:490 shuffle=True on the whole grid).  'auto': the library stores the
+    oscillators in grid order (dbsgym_set_oscillator_order; the permutation is applied at the ABI boundary) and runs the
+    spectral warp kernel of the regular grid (variant 10).  force_dense=True: the operator as a matrix, in its truncated
+    eigenbasis (variant 11, 32 modes: a permutation does not change the spectrum).  coupling_eval='exact': the full matrix
+    (variant 1).  All three: teacher-forced steps against the float64 oracle at the float32 tolerance, exact counters."""
     from oracle import kuramoto_oracle as ko
     d = make_params("env1", 4, transient_state_len=118.0)
     perm = np.random.default_rng(1).permutation(512)
@@ -173,8 +175,11 @@ def test_shuffled_grid_f32_low_rank_kernel_matches_oracle():
     d["neur_grid"] = d["neur_grid"][perm]
     orc = ko.OracleEnv(copy.deepcopy(d))
     from dbsgym_b200.batched import BatchedKuramoto
-    cores = {"lowrank": BatchedKuramoto([copy.deepcopy(d)] * 2, precision="f32", transfer="full"),
+    cores = {"grid_order": BatchedKuramoto([copy.deepcopy(d)] * 2, precision="f32", transfer="full"),
+             "lowrank": BatchedKuramoto([copy.deepcopy(d)] * 2, precision="f32", transfer="full", force_dense=True),
              "dense": BatchedKuramoto([copy.deepcopy(d)] * 2, precision="f32", transfer="full", coupling_eval="exact")}
+    assert cores["grid_order"].engine.step_variant() == 10 and cores["grid_order"].engine.coupling == "grid"
+    assert np.array_equal(np.asarray(d["neur_grid"])[cores["grid_order"].engine.order], np.asarray(make_params("env1", 4)["neur_grid"]))
     assert cores["lowrank"].engine.step_variant() == 11 and cores["lowrank"].coupling_eval == "lowrank"
     assert cores["lowrank"].engine.lowrank["rank"] == 32
     assert cores["dense"].engine.step_variant() == 1

@@ -384,3 +384,19 @@ def test_grid_sector_factors_and_grid_lowrank_factors_agree_with_the_full_matrix
             full[:hz, :hx, :hy] = sign * y
             out += full[sl]
     assert np.max(np.abs(out.ravel() - alpha @ x.ravel())) < 1e-8 * np.abs(alpha @ x.ravel()).max()
+
+
+def test_grid_permutation_recognises_a_shuffled_regular_grid():
+    """geometry.grid_permutation: the order map a shuffled grid is handed to the library with (dbsgym_set_oscillator_order)."""
+    from dbsgym_b200 import geometry
+    coords, grid = geometry.neuron_grid(8, 8, 8, 512, 0.1)
+    assert geometry.grid_permutation(grid, [8, 8, 8]) is None                    # already in grid order
+    perm = np.random.default_rng(2).permutation(512)
+    order = geometry.grid_permutation(grid[perm], [8, 8, 8])
+    assert order is not None and np.array_equal(grid[perm][order], grid) and np.array_equal(perm[order], np.arange(512))
+    table = geometry.coupling_table(coords[perm][order], grid[perm][order], [8, 8, 8], "cos")
+    assert table is not None and geometry.coupling_table(coords[perm], grid[perm], [8, 8, 8], "cos") is None
+    assert geometry.grid_permutation(grid[perm][:300], [8, 8, 8]) is None       # a random subset of the grid is not a grid
+    holes = grid[perm].copy(); holes[0] = holes[1]
+    assert geometry.grid_permutation(holes, [8, 8, 8]) is None                   # not a permutation
+    assert geometry.grid_permutation(grid[perm] * 0.1, [8, 8, 8]) is None        # coordinates, not grid indices
