@@ -589,9 +589,17 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
         return fail(nullptr, DBSGYM_EINVAL, "rtol, atol, dt0 and max_steps must be positive");
     // DENSE: pad to whole warps (padded oscillators are inert); GRID: whole z-planes of 8-lines
     const int gran = cfg->coupling == DBSGYM_COUPLING_DENSE ? 32 * kRows : kRows;
-    const int Np = (cfg->n_osc + gran - 1) / gran * gran;
-    if (cfg->coupling == DBSGYM_COUPLING_DENSE && Np / kRows > 1024)
-        return fail(nullptr, DBSGYM_EINVAL, "n_osc %d too large for DENSE coupling (max 8192)", cfg->n_osc);
+    int Np = (cfg->n_osc + gran - 1) / gran * gran;
+    int dense_cluster = 1;
+    if (cfg->coupling == DBSGYM_COUPLING_DENSE && Np / kRows > 1024) {
+        // more than 8192 oscillators without a grid: no N x N matrix, the operator must come in low-rank form
+        // (dbsgym_set_coupling_lowrank), integrated by a cluster of CTAs with 4096 oscillators each (padded ones are inert)
+        while (dense_cluster * 4096 < cfg->n_osc) dense_cluster *= 2;
+        if (dense_cluster > 16 || cfg->precision != DBSGYM_F32)
+            return fail(nullptr, DBSGYM_EINVAL, "n_osc %d too large for DENSE coupling (fp32: at most 65536 in low-rank form; "
+                        "fp64 and the full matrix: at most 8192)", cfg->n_osc);
+        Np = dense_cluster * 4096;
+    }
     if (cfg->coupling == DBSGYM_COUPLING_GRID) {
         const int gy = cfg->grid[1];
         if (gy != kRows && gy != 2 * kRows && gy != 4 * kRows)
@@ -626,6 +634,7 @@ int dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out) {
     h->f64 = cfg->precision == DBSGYM_F64;
     h->rb = h->f64 ? 8 : 4;
     h->nthreads = Np / kRows;
+    if (dense_cluster > 1) { h->cluster = dense_cluster; h->nthreads = 512; }
     if (cfg->coupling == DBSGYM_COUPLING_GRID) {
         // more than 512 grid lines (N > 4096): one environment spans a thread-block cluster of 2..16 CTAs
         int want = cfg->force_cluster > 1 ? cfg->force_cluster : 1;             // (test hook: cluster mode at small N)
@@ -841,6 +850,7 @@ int dbsgym_set_coupling_spectral(DbsGymHandle* h, const int32_t* ranks8, int32_t
 int dbsgym_set_coupling_dense(DbsGymHandle* h, const double* alpha) {
     if (!h || !alpha) return fail(h, DBSGYM_EINVAL, "null argument");
     if (h->cfg.coupling != DBSGYM_COUPLING_DENSE) return fail(h, DBSGYM_ESTATE, "handle was created with GRID coupling");
+    if (h->cluster > 1) return fail(h, DBSGYM_ESTATE, "n_osc %d: the full matrix is not kept above 8192 oscillators, use dbsgym_set_coupling_lowrank", h->N);
     CU(h, cudaSetDevice(h->cfg.device));
     const int N = h->N, Np = h->Np;
     std::vector<unsigned char> buf((size_t)Np * Np * h->rb, 0);

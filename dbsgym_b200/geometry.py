@@ -383,3 +383,77 @@ def grid_sector_factors(table, gx, gy, gz, tol=1e-9, max_modes=1024):
         return None
     return (np.array(soff, dtype=np.int32), np.ascontiguousarray(np.concatenate(rows)), np.ascontiguousarray(np.concatenate(vals)),
             residual)
+
+
+def lowrank_factors_points(neur_coords, spatial_kernel, wavelet_amp=1.0, wavelet_steepness=1.0, tol=1e-9, max_rank=1024,
+                           block=4096, use_cuda=None):
+    """lowrank_factors for alpha_ij = kernel(|r_i - r_j|) given by the neuron coordinates alone -- for clouds too large to form
+    the N x N matrix on the host (the ragged "first 65536 rows of a 41^3 grid" of BASELINE configs[4]: 34 GB) and without the
+    reflection symmetry grid_sector_factors needs.  Randomised subspace iteration in float64 with the matrix regenerated block
+    by block for every product, on the GPU through torch when one is there (set-up work, seconds), else with numpy.
+    Returns (vecs [r][N], vals [r], residual) like lowrank_factors; ``residual`` is the largest captured eigenvalue below the
+    threshold (the subspace keeps a margin of them), or None when more than ``max_rank`` modes would be needed."""
+    pts = np.ascontiguousarray(np.asarray(neur_coords, dtype=np.float64))
+    n = pts.shape[0]
+    if n <= 8192:
+        return lowrank_factors(coupling_rows(pts, np.arange(n), spatial_kernel, wavelet_amp, wavelet_steepness), tol=tol,
+                               max_rank=min(max_rank, 1024))
+    torch = None
+    if use_cuda is not False:
+        try:
+            import torch as _t
+            if _t.cuda.is_available():
+                torch = _t
+        except Exception:  # noqa: BLE001
+            torch = None
+    if torch is not None:
+        x = torch.from_numpy(pts).cuda()
+
+        def kern(d):
+            if spatial_kernel == "cos":
+                return torch.cos(d)
+            if spatial_kernel == "wavelet":
+                s_ = wavelet_steepness
+                return wavelet_amp * (-s_) * (12 * s_ ** 4 * d ** 2 - 8 * s_ ** 2) * torch.exp(-s_ * d ** 2) / (2 * np.pi)
+            raise ValueError(f"Wrong distance matrix type: {spatial_kernel}")
+
+        def apply(q):                                 # alpha @ q without ever holding alpha
+            out = torch.empty_like(q)
+            for lo in range(0, n, block):
+                d = torch.cdist(x[lo:lo + block], x, compute_mode="donot_use_mm_for_euclid_dist")
+                out[lo:lo + block] = kern(d) @ q
+            return out
+        randn = lambda k: torch.from_numpy(np.random.default_rng(0).standard_normal((n, k))).cuda()     # noqa: E731
+        qr = lambda a: torch.linalg.qr(a)[0]                                                             # noqa: E731
+        eigh = lambda b: tuple(t.cpu().numpy() for t in torch.linalg.eigh(0.5 * (b + b.T)))              # noqa: E731
+        to_np = lambda a: a.cpu().numpy()                                                                # noqa: E731
+        from_np = lambda a: torch.from_numpy(a).cuda()                                                   # noqa: E731
+    else:
+        def apply(q):
+            out = np.empty_like(q)
+            for lo in range(0, n, block):
+                out[lo:lo + block] = coupling_rows(pts, np.arange(lo, min(lo + block, n)), spatial_kernel, wavelet_amp,
+                                                   wavelet_steepness) @ q
+            return out
+        randn = lambda k: np.random.default_rng(0).standard_normal((n, k))       # noqa: E731
+        qr = lambda a: np.linalg.qr(a)[0]                                         # noqa: E731
+        eigh = lambda b: np.linalg.eigh(0.5 * (b + b.T))                          # noqa: E731
+        to_np = from_np = lambda a: a                                             # noqa: E731
+    k = 128
+    while True:
+        q = qr(apply(randn(k)))
+        for _ in range(3):
+            q = qr(apply(q))
+        w, u = eigh(q.T @ apply(q))
+        if np.count_nonzero(np.abs(w) <= tol * np.abs(w).max()) >= 16:
+            break
+        if k > 2 * max_rank:
+            return None
+        k *= 2
+    order = np.argsort(-np.abs(w))
+    w, u = w[order], u[:, order]
+    r = int(np.count_nonzero(np.abs(w) > tol * np.abs(w[0])))
+    if r > max_rank:
+        return None
+    vecs = to_np((q @ from_np(np.ascontiguousarray(u[:, :r]))).T)
+    return np.ascontiguousarray(vecs), np.ascontiguousarray(w[:r]), float(np.abs(w[r]))

@@ -149,6 +149,72 @@ def test_low_rank_kernel_on_grid_handles_single_cta_and_cluster(N, gz, C, gx, gy
                 np.testing.assert_allclose(u, v, rtol=2e-5, atol=1e-5 * (k + 1) if u.ndim == 2 and u.shape[1] == N else 5e-6)
 
 
+def test_ragged_cloud_above_8192_oscillators_runs_in_low_rank_cluster_mode_and_matches_oracle():
+    """The first 9000 rows of a 21 x 21 x 21 grid (odd extents, a partial last plane: the shape of BASELINE configs[4]'s
+    "first 65536 rows of 41^3" point, at a size the CPU oracle can integrate): a DENSE handle above 8192 oscillators keeps no
+    matrix -- the operator comes from the coordinates as eigenpairs (geometry.lowrank_factors_points) and a cluster of 4 CTAs
+    (16384 slots, 7384 of them inert padding) integrates it.  One step() against the fp64 oracle integrator with a chunked
+    evaluation of alpha = cos(distance)."""
+    from dbsgym_b200.engine import KuramotoEngine
+    from dbsgym_b200.geometry import coupling_rows, distances_from, lowrank_factors_points, neuron_grid
+    from dbsgym_b200.schedule import StepSchedule, transient_grid
+    from oracle.diffrax_restated import Dopri5, ODETerm, PIDController, SaveAt, diffeqsolve
+    N, B = 9000, 2
+    coords, grid = neuron_grid(21, 21, 21, N, 0.1)
+    f = lowrank_factors_points(coords, "cos", tol=1e-9)
+    assert f is not None and f[0].shape[0] < 100 and f[2] < 2e-9 * abs(f[1][0])
+    eng = KuramotoEngine(B, N, [21, 21, 21], 2340, 0.52, precision="f32", lowrank=f)
+    assert eng.coupling == "dense" and eng.step_variant() == 11
+    with pytest.raises(Exception):
+        eng._ck(eng.lib.dbsgym_set_coupling_dense(eng._h, None))          # (no full matrix above 8192 oscillators)
+    tt = transient_grid(200.0, 0.05)
+    sched = StepSchedule(80, tt[-1], 0.15, 0.75, 0.05)
+    eng.set_schedule(sched); eng.set_reward("bbpow_action", 0.05); eng.set_recording(True)
+    rng = np.random.default_rng(3)
+    stim = np.tile(np.maximum(0.0, 1.0 - distances_from(coords, [N // 2])[0]), (B, 1))
+    rec = np.tile(np.maximum(0.0, 1.0 - distances_from(coords, [N // 3])[0]), (B, 1))
+    w0 = np.abs(rng.normal(0.6, 0.4, (B, N))) + 0.02
+    y0 = rng.normal(np.pi, 0.6, (B, N)) + 25.0
+    eng.set_env_params(None, w0=w0, stim=stim, rec=rec, y0=y0)
+    eng.set_window(rng.uniform(-0.2, 0.2, (B, 2340)))
+    eng.set_episode(None, step_idx=0, episode_len=1000)
+    assert np.max(np.abs(eng.state() - y0)) < 4e-6                        # (wrapped float32 phase + winding count)
+    a = np.array([0.7, -0.4], dtype=np.float32)
+    obs, rew, done = eng.step_host(a)
+    y_gpu = eng.state()
+    lfp_t, lfp_r, ns = eng.lfp()
+    c = eng.counters()
+    assert c["status"] == 0 and c["rhs_evals"] == B * 32 and c["rejected"] == 0
+
+    def coupled(v):                                    # alpha @ v in row chunks
+        out = np.empty((N, v.shape[1]))
+        for lo in range(0, N, 1000):
+            out[lo:lo + 1000] = coupling_rows(coords, np.arange(lo, min(lo + 1000, N)), "cos") @ v
+        return out
+
+    e = 0
+    u = -5 + (10 * (float(a[e]) + 1)) / 2
+    y = y0[e].copy()
+    rows = []
+    for ts, amp in [(sched.offs_I[0, :sched.n_I[0]], u), (sched.offs_II[0, :sched.n_II[0]], 0.0)]:
+        pulse = amp * stim[e]
+
+        def rhs(t, yy, args, pulse=pulse):
+            th = np.fmod(yy, 2 * np.pi)
+            sc = coupled(np.stack([np.sin(th), np.cos(th)], axis=1))
+            return w0[e] + (0.52 / N) * (np.cos(th) * sc[:, 0] - np.sin(th) * sc[:, 1]) + pulse
+        sol = diffeqsolve(ODETerm(rhs), Dopri5(), t0=ts[0], t1=ts[-1], dt0=0.05, y0=y, saveat=SaveAt(ts=ts),
+                          stepsize_controller=PIDController(rtol=1e-5, atol=1e-5))
+        y = sol.ys[-1]
+        rows.append(sol.ys)
+    allrows = np.concatenate(rows)[:-1]
+    assert np.max(np.abs(y_gpu[e] - y)) < 1e-5
+    n = ns[e]
+    np.testing.assert_allclose(lfp_t[e, :n], np.mean(np.cos(allrows), axis=1), rtol=0, atol=2e-6)
+    np.testing.assert_allclose(lfp_r[e, :n], np.mean(np.cos(allrows) * rec[e], axis=1), rtol=0, atol=2e-6)
+    eng.close()
+
+
 @pytest.mark.parametrize("B", [5, 21])
 def test_multi_worker_kernel_equals_the_single_environment_kernel(B):
     """options mw=True forces the multi-worker step kernel (8 environments per CTA sharing the precomputed sector
