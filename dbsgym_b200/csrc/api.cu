@@ -103,7 +103,6 @@ struct DbsGymHandle {
     float* wspec_v = nullptr; float* wspec_lam = nullptr; int warp_set = -1; bool no_warp = false;
     // low-rank form of a DENSE operator (dbsgym_set_coupling_lowrank): eigenvectors [lr_rank][Np], eigenvalues [lr_rank]
     float* lr_v = nullptr; float* lr_lam = nullptr; int lr_rank = 0;
-    float2* lr_part = nullptr;           // cluster mode: per-CTA mode sums [B][2][cluster][lr_rank]
     // sector form of the low-rank operator: oscillators stored in octant order (perm[d] = natural index of device position d)
     int32_t* lr_soff = nullptr; bool lr_sectors = false; bool params_set = false;
     // order of the oscillators on the device: perm[d] = the CALLER's index of the oscillator at device position d (empty =
@@ -339,7 +338,7 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
     p.fsal_on = h->fsal_on ? 1 : 0; p.k_fsal = h->k_fsal; p.fsal_valid = h->fsal_valid;
     const bool warp = h->spec_re > 0 && h->warp_set >= 0;
     p.spec_v = warp ? h->wspec_v : h->spec_v; p.spec_lam = warp ? h->wspec_lam : h->spec_lam;
-    p.lr_v = h->lr_v; p.lr_lam = h->lr_lam; p.lr_rank = h->lr_rank; p.lr_part = h->lr_part;
+    p.lr_v = h->lr_v; p.lr_lam = h->lr_lam; p.lr_rank = h->lr_rank;
     p.lr_sectors = h->lr_sectors ? 1 : 0; p.lr_soff = h->lr_soff;
     p.power_scale = h->rspec.power_scale; p.action_cost = h->rspec.action_cost;
     p.threshold = h->rspec.threshold; p.threshold_penalty = h->rspec.threshold_penalty;
@@ -730,7 +729,7 @@ void dbsgym_destroy(DbsGymHandle* h) {
                     h->step_idx, h->episode_len, h->lfp_true, h->lfp_rec, h->u, h->reward, h->done, h->sched_nI,
                     h->sched_nII, h->sched_offI, h->sched_offII, h->ts_dev, h->ids_dev, h->lin_g, h->tw_seed,
                     h->tw_inner, h->spec, h->tw_full, h->k_fsal, h->fsal_valid, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples,
-                    h->cl_operand, h->cl_scratch, h->mpos, h->spec_v, h->spec_lam, h->wspec_v, h->wspec_lam, h->lr_v, h->lr_lam, h->lr_part, h->lr_soff};
+                    h->cl_operand, h->cl_scratch, h->mpos, h->spec_v, h->spec_lam, h->wspec_v, h->wspec_lam, h->lr_v, h->lr_lam, h->lr_soff};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->pin_ints) cudaFreeHost(h->pin_ints);
@@ -873,7 +872,6 @@ int dbsgym_set_coupling_lowrank(DbsGymHandle* h, int32_t rank, const double* vec
     CU(h, cudaDeviceSynchronize());
     if (h->lr_sectors) return fail(h, DBSGYM_ESTATE, "the handle stores its oscillators in octant order (sector form): create a new handle");
     for (float** q : {&h->lr_v, &h->lr_lam}) { if (*q) cudaFree(*q); *q = nullptr; }
-    if (h->lr_part) { cudaFree(h->lr_part); h->lr_part = nullptr; }
     h->lr_rank = 0;
     if (h->fsal_valid) CU(h, cudaMemset(h->fsal_valid, 0, (size_t)h->B * 4));
     const bool dense = h->cfg.coupling == DBSGYM_COUPLING_DENSE;
@@ -899,7 +897,6 @@ int dbsgym_set_coupling_lowrank(DbsGymHandle* h, int32_t rank, const double* vec
     CU(h, cudaMalloc(&h->lr_lam, lam.size() * sizeof(float)));
     CU(h, cudaMemcpy(h->lr_v, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
     CU(h, cudaMemcpy(h->lr_lam, lam.data(), lam.size() * sizeof(float), cudaMemcpyHostToDevice));
-    if (h->cluster > 1) CU(h, cudaMalloc(&h->lr_part, (size_t)h->B * 2 * h->cluster * R4 * sizeof(float2)));
     h->lr_rank = R4;
     h->have_coupling = true;
     return DBSGYM_OK;
@@ -969,7 +966,6 @@ int dbsgym_set_coupling_lowrank_sectors(DbsGymHandle* h, const int32_t* soff9, c
     CU(h, cudaMemcpy(h->lr_v, z.data(), z.size() * sizeof(float), cudaMemcpyHostToDevice));
     CU(h, cudaMemcpy(h->lr_lam, lam.data(), lam.size() * sizeof(float), cudaMemcpyHostToDevice));
     CU(h, cudaMemcpy(h->lr_soff, soff9, 9 * sizeof(int32_t), cudaMemcpyHostToDevice));
-    if (h->cluster > 1) CU(h, cudaMalloc(&h->lr_part, (size_t)h->B * 2 * h->cluster * R * sizeof(float2)));
     h->lr_rank = R;
     h->lr_sectors = true;
     h->have_coupling = true;

@@ -93,7 +93,6 @@ struct StepParams {
     // low-rank coupling (CPL_LOWRANK): eigenvectors [lr_rank][Np] (mode-major, rows padded to a multiple of 4 with zeros)
     // and eigenvalues [lr_rank] of a DENSE alpha (see couple_lowrank_* below)
     const float* lr_v; const float* lr_lam; int lr_rank;
-    float2* lr_part;               // cluster mode: [B][2][cluster][lr_rank] per-CTA mode sums (global, L2)
     // sector form (lr_sectors != 0): the oscillators are stored in OCTANT order (position 8 a + g = image g of octant point
     // a, g = 4 my + 2 mz + mx), lr_v holds the eigenvectors of the 8 parity-sector blocks over the octant points only,
     // [lr_rank][Np / 8], modes sorted by sector (counts padded to multiples of 4), lr_soff[9] = first mode of every sector
@@ -1393,15 +1392,22 @@ __global__ void DBSGYM_KERNEL_BOUNDS(real, MAXT) step_kernel(const StepParams p)
                         else couple_lowrank_project(opnd, p.lr_v, lamp, p.lr_rank, Np, crank * Nl, Nl, out, lane, warp, nwarps);
                     };
                     if constexpr (CL != 0) {
-                        // every CTA of the cluster sums over its own oscillators; the partial sums meet in global memory (L2)
-                        // and every CTA adds them in the same order, so all CTAs expand with identical coefficients
-                        float2* part_g = p.lr_part + ((size_t)env * 2 + lr_par) * NC_ * p.lr_rank;
-                        project(nullptr, part_g + (size_t)crank * p.lr_rank);
+                        // every CTA of the cluster sums over its own oscillators into its OWN shared memory; after one cluster
+                        // barrier every CTA reads the partial sums of all ranks through distributed shared memory (mapa +
+                        // ld.shared::cluster) and adds them in the same order, so all CTAs expand with identical coefficients.
+                        // Two buffers by parity: a rank rewrites a buffer two barriers after the others finished reading it.
+                        float2* part_s = reinterpret_cast<float2*>(cl_tile) + lr_par * p.lr_rank;
+                        project(nullptr, part_s);
                         cluster_barrier();
                         for (int m = tid; m < p.lr_rank; m += nt) {
+                            const uint32_t laddr = (uint32_t)__cvta_generic_to_shared(part_s + m);
                             float2 a = make_float2(0.f, 0.f);
+#pragma unroll 4
                             for (int r = 0; r < NC_; ++r) {
-                                const float2 b = __ldcg(part_g + (size_t)r * p.lr_rank + m);
+                                uint32_t raddr;
+                                float2 b;
+                                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(r));
+                                asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(b.x), "=f"(b.y) : "r"(raddr) : "memory");
                                 a.x += b.x; a.y += b.y;
                             }
                             const float l = __ldg(p.lr_lam + m);
@@ -1736,11 +1742,12 @@ inline size_t step_smem_bytes_cluster(int nthreads, size_t real_bytes) {
 }
 
 // low-rank cluster mode: K slots, the double-buffered operand of the CTA's own oscillators, mode coefficients, recording
-// conductance, winding counts, reduction scratch
+// conductance, winding counts, reduction scratch, the two parity buffers of partial mode sums
 inline size_t step_smem_bytes_cluster_lr(int nthreads, int rank4) {
     const int nwarps = (nthreads + 31) / 32, Nl = nthreads * kRows;
     return (size_t)((kSlots + 1) * Nl + kScBuffers * (2 * Nl + kScPad) + 2 * rank4) * sizeof(float) + (size_t)Nl * sizeof(int) +
-           (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 36 * sizeof(int) + 64;
+           (size_t)(nwarps * kSampleBatch * 2 + nwarps + 32) * sizeof(double) + 36 * sizeof(int) + 64 +
+           (size_t)2 * rank4 * sizeof(float2);          // the CTA's partial mode sums, read by the other ranks through DSMEM
 }
 
 inline size_t step_smem_bytes(int Np, int tab, int nthreads, size_t real_bytes) {
