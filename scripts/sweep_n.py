@@ -36,7 +36,12 @@ for gx, gy, gz in GRIDS:
     coords, grid = neuron_grid(gx, gy, gz, N, 0.1)
     table = coupling_table(coords, grid, [gx, gy, gz], "cos")
     assert table is not None
-    eng = KuramotoEngine(B, N, [gx, gy, gz], 2340, 0.52, precision="f32", coupling_table=table, device=LOCAL)
+    opts = None
+    if os.environ.get("SWEEP_CTA_OSC"):                  # (tuning) oscillators per CTA: clusters of N / that many CTAs
+        per = int(os.environ["SWEEP_CTA_OSC"])
+        if N > per and N // per <= 16:
+            opts = {"force_cluster": N // per}
+    eng = KuramotoEngine(B, N, [gx, gy, gz], 2340, 0.52, precision="f32", coupling_table=table, device=LOCAL, options=opts)
     lowrank = None
     if os.environ.get("SWEEP_LOWRANK"):                   # the operator in its truncated eigenbasis (step-kernel variant 11)
         from dbsgym_b200.geometry import grid_lowrank_factors, grid_sector_factors
