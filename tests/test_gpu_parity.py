@@ -236,6 +236,24 @@ def test_large_regular_grid_selects_the_sector_low_rank_form_and_matches_oracle(
         cc = c.engine.counters()
         assert (cc["accepted"], cc["rejected"], cc["rhs_evals"], cc["status"]) == (2 * 3 * 5, 0, 2 * 3 * 32, 0)
         c.close()
+    # the same grid with its neurons shuffled (utils.py:490): order map (caller -> grid) composed with the octant order of the
+    # sector form inside the library; everything the caller sees stays in the caller's order
+    perm = np.random.default_rng(9).permutation(2048)
+    ds = copy.deepcopy(d)
+    for k in ("w0", "w0_without_locus", "locus_without_w0", "locus_mask", "neur_coords", "neur_grid"):
+        ds[k] = np.asarray(ds[k])[perm]
+    orc_s = ko.OracleEnv(copy.deepcopy(ds))
+    shuf = BatchedKuramoto([copy.deepcopy(ds)] * 2, precision="f32", transfer="full")
+    assert shuf.engine.coupling == "grid" and shuf.engine.order is not None and shuf.engine.step_variant() == 11
+    assert shuf.engine.lowrank["sectors"]
+    y_before = orc_s.sol_state[-1].copy()
+    orc_s.step(np.array([0.5], dtype=np.float32))
+    shuf.engine.set_env_params(None, y0=np.tile(y_before, (2, 1)))
+    assert np.max(np.abs(shuf.engine.state()[0] - y_before)) < 4e-6                     # round trip through both permutations
+    shuf.step(np.array([0.5, 0.5], dtype=np.float32))
+    assert np.max(np.abs(shuf.engine.state()[0] - orc_s.sol_state[-1])) < 1e-5
+    assert np.max(np.abs(shuf.theta_records(0) - orc_s.theta_records)) < 2e-6
+    shuf.close()
 
 
 def test_half_grid_256_oscillators():
