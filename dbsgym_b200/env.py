@@ -45,7 +45,8 @@ class SpatialKuramoto(GymEnv):
         if compat_env2 is None:
             compat_env2 = bool(params_dict.get("compat_env2", os.environ.get("DBSGYM_COMPAT_ENV2", "") == "1"))
         self._core = BatchedKuramoto([params_dict], precision=precision or _default_precision(params_dict),
-                                     device=device, compat_env2=compat_env2, save_init=save_init)
+                                     device=device, compat_env2=compat_env2, save_init=save_init,
+                                     coupling_eval=params_dict.get("coupling_eval", "auto"))
         host = self._core.hosts[0]
         self.verbose = host.verbose
         self.step_len = host.step_len

@@ -81,7 +81,7 @@ class BatchedKuramotoVecEnv(VecEnvBase):
     observation longer than that only as a copy, or pass ``copy_obs=True`` for arrays you own."""
 
     def __init__(self, params_dicts, num_envs=None, precision=None, device=0, compat_env2=False,
-                 monitor=True, transfer="delta", copy_obs=False, engine_options=None, coupling_eval="auto"):
+                 monitor=True, transfer="delta", copy_obs=False, engine_options=None, coupling_eval=None):
         if isinstance(params_dicts, dict):
             n = int(num_envs or params_dicts.get("num_envs", 1))
             # like DummyVecEnv([make_env(d)] * n): every env gets its own copy of the dict
@@ -89,7 +89,8 @@ class BatchedKuramotoVecEnv(VecEnvBase):
         p0 = params_dicts[0]
         self.core = BatchedKuramoto(params_dicts, precision=precision or _default_precision(p0),
                                     device=device, compat_env2=compat_env2, transfer=transfer,
-                                    engine_options=engine_options, coupling_eval=coupling_eval)
+                                    engine_options=engine_options,
+                                    coupling_eval=coupling_eval or p0.get("coupling_eval", "auto"))
         self.copy_obs = bool(copy_obs)
         B, W = self.core.num_envs, self.core.window
         obs_space = Box(low=-1.5, high=1.5, shape=(1, W), dtype=np.float32)
