@@ -14,6 +14,8 @@ from .geometry import coupling_rows, coupling_table
 from .host_env import HostEnvState
 from .schedule import StepSchedule, transient_grid
 
+# sector rank lists compiled into the half-grid kernel (csrc/step_f32_warp1.cu)
+HALF_GRID_RANK_SETS = ((5, 4, 4, 2, 4, 4, 2, 1), (9, 4, 4, 3, 4, 4, 3, 1))
 _SHARED_KEYS = ("num_oscillators", "grid_size", "K", "spatial_kernel", "wavelet_amp", "wavelet_steepness",
                 "electrode_width", "electrode_pause", "verbose_dt", "observe_wind_counts",
                 "transient_state_len", "dbs_action_bounds", "reward_func", "recording_kernel",
@@ -118,9 +120,18 @@ class BatchedKuramoto:
             if max(ranks) <= 9:
                 self.engine.set_coupling_spectral(vecs, vals, ranks, residual)
                 self.coupling_eval = "spectral"
+        grid884 = table is not None and gs == [8, 8, 8] and self.n_osc == 256
+        if coupling_eval != "exact" and precision == "f32" and grid884 and not (engine_options or {}).get("no_sym") \
+                and not (engine_options or {}).get("no_warp_kernel"):
+            # the half grid of BASELINE configs[4]'s smallest point: 32-point sector blocks, one octant point per lane
+            from .geometry import spectral_factors
+            vecs, vals, ranks, residual = spectral_factors(table, 8, 8, 4, tol=spectral_tol)
+            if any(all(r <= c for r, c in zip(ranks, cs)) for cs in HALF_GRID_RANK_SETS):
+                self.engine.set_coupling_spectral(vecs, vals, ranks, residual)
+                self.coupling_eval = "spectral"
         if coupling_eval == "spectral" and self.coupling_eval == "exact":
             raise ValueError("coupling_eval='spectral' needs float32 and either the regular 8 x 8 x 8 grid with at most 9 modes "
-                             "per sector or a dense operator with at most 256 modes above spectral_tol")
+                             "per sector, its 8 x 8 x 4 half with ranks inside a compiled list, or a dense operator with at most 256 modes above spectral_tol")
         self.engine.set_recording(p0["recording_kernel"] == "gaussian")
         self.engine.set_schedule(self.schedule)
         self.engine.set_reward(p0["reward_func"], p0["verbose_dt"])

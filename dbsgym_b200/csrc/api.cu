@@ -101,6 +101,7 @@ struct DbsGymHandle {
     // the same operator laid out for the one-warp-per-environment kernel (warp_kernel.cuh): [32 lanes][modes] float2 and
     // [modes] eigenvalues, for the compiled rank list warp_set (-1: the ranks fit none, or DBSGYM_DBG_NO_WARP_KERNEL)
     float* wspec_v = nullptr; float* wspec_lam = nullptr; int warp_set = -1; bool no_warp = false;
+    int half_set = -1;                   // 8 x 8 x 4 half grid: compiled rank list of warp1_kernel.cuh in use (-1: exact contraction)
     // low-rank form of a DENSE operator (dbsgym_set_coupling_lowrank): eigenvectors [lr_rank][Np], eigenvalues [lr_rank]
     float* lr_v = nullptr; float* lr_lam = nullptr; int lr_rank = 0;
     // sector form of the low-rank operator: oscillators stored in octant order (perm[d] = natural index of device position d)
@@ -336,7 +337,7 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
     p.nsamp_out = nullptr; p.head_out = nullptr;
     p.trace = nullptr; p.trace_len = nullptr; p.trace_cap = 0;
     p.fsal_on = h->fsal_on ? 1 : 0; p.k_fsal = h->k_fsal; p.fsal_valid = h->fsal_valid;
-    const bool warp = h->spec_re > 0 && h->warp_set >= 0;
+    const bool warp = (h->spec_re > 0 && h->warp_set >= 0) || h->half_set >= 0;
     p.spec_v = warp ? h->wspec_v : h->spec_v; p.spec_lam = warp ? h->wspec_lam : h->spec_lam;
     p.lr_v = h->lr_v; p.lr_lam = h->lr_lam; p.lr_rank = h->lr_rank;
     p.lr_sectors = h->lr_sectors ? 1 : 0; p.lr_soff = h->lr_soff;
@@ -381,6 +382,7 @@ cudaError_t launch_step(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
     }
     if (dense) return launch_f32_dense(t, smem, p, s);
     if (!h->grid_sym) return launch_f32_grid(t, smem, p, s);
+    if (h->half_set >= 0) return launch_f32_warp1(h->half_set, h->num_sms, p, s);
     if (h->spec_re > 0 && h->warp_set >= 0) return launch_f32_warp(h->warp_set, h->num_sms, p, s);
     if (h->spec_re > 0) return launch_f32_spectral(h->spec_ro, h->num_sms, p, s);
     const int geo = sym_geo(h, p);
@@ -551,6 +553,7 @@ int dbsgym_step_variant(const DbsGymHandle* h, int32_t n_envs) {
     if (h->cfg.coupling == DBSGYM_COUPLING_DENSE) return 1;
     if (!h->grid_sym) return 0;
     if (h->f64) return 2;
+    if (h->half_set >= 0) return 12;
     if (h->spec_re > 0) return h->warp_set >= 0 ? 10 : 9;
     if (h->cfg.grid[1] == 2 * kRows) return 7;
     if (h->cfg.grid[1] == 4 * kRows) return 8;
@@ -769,20 +772,54 @@ int dbsgym_set_coupling_grid(DbsGymHandle* h, const double* table) {
     return DBSGYM_OK;
 }
 
+// 8 x 8 x 4 half grid (N = 256): tables of warp1_kernel.cuh -- lane l owns the octant point a = l = (zq * 4 + xq) * 4 + yq;
+// [mode][lane] eigenvector entries, modes sector after sector, padded to the compiled rank list
+static int set_coupling_spectral_half(DbsGymHandle* h, const int32_t* ranks8, int32_t r_max, const double* vecs, const double* vals) {
+    int r8[8], compiled[8];
+    for (int s8 = 0; s8 < 8; ++s8) {
+        if (ranks8[s8] < 0 || ranks8[s8] > r_max) return fail(h, DBSGYM_EINVAL, "spectral rank %d of sector %d outside 0..r_max", ranks8[s8], s8);
+        r8[s8] = ranks8[s8];
+    }
+    const int wset = h->no_warp ? -1 : warp1_kernel_rank_set(r8, compiled);
+    if (wset < 0) return fail(h, DBSGYM_ESTATE, "8 x 8 x 4 grid: no compiled rank list covers these sector ranks");
+    int nm = 0;
+    for (int s8 = 0; s8 < 8; ++s8) nm += compiled[s8];
+    const double scale = h->cfg.K / (8.0 * (double)h->N);
+    std::vector<float> wv((size_t)32 * nm, 0.f), wlam((size_t)nm, 0.f);
+    int off = 0;
+    for (int s8 = 0; s8 < 8; ++s8) {
+        for (int m = 0; m < ranks8[s8]; ++m) {
+            wlam[off + m] = (float)(vals[(size_t)s8 * r_max + m] * scale);
+            for (int l = 0; l < 32; ++l) wv[(size_t)(off + m) * 32 + l] = (float)vecs[((size_t)s8 * 32 + l) * r_max + m];
+        }
+        off += compiled[s8];
+    }
+    for (float** q : {&h->wspec_v, &h->wspec_lam}) { if (*q) cudaFree(*q); *q = nullptr; }
+    CU(h, cudaMalloc(&h->wspec_v, wv.size() * sizeof(float)));
+    CU(h, cudaMemcpy(h->wspec_v, wv.data(), wv.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CU(h, cudaMalloc(&h->wspec_lam, wlam.size() * sizeof(float)));
+    CU(h, cudaMemcpy(h->wspec_lam, wlam.data(), wlam.size() * sizeof(float), cudaMemcpyHostToDevice));
+    h->half_set = wset;
+    if (h->fsal_valid) CU(h, cudaMemset(h->fsal_valid, 0, (size_t)h->B * 4));
+    return DBSGYM_OK;
+}
+
 int dbsgym_set_coupling_spectral(DbsGymHandle* h, const int32_t* ranks8, int32_t r_max, const double* vecs, const double* vals) {
     if (!h) return DBSGYM_EINVAL;
     CU(h, cudaSetDevice(h->cfg.device));
     CU(h, cudaDeviceSynchronize());
     if (!ranks8) {                                    // back to the exact sector-block contraction
         h->spec_re = h->spec_ro = 0;
-        h->warp_set = -1;
+        h->warp_set = h->half_set = -1;
         if (h->fsal_valid) CU(h, cudaMemset(h->fsal_valid, 0, (size_t)h->B * 4));
         return DBSGYM_OK;
     }
     if (!vecs || !vals) return fail(h, DBSGYM_EINVAL, "null argument");
-    if (h->cfg.coupling != DBSGYM_COUPLING_GRID || h->f64 || !h->grid_sym || h->cluster > 1 || h->nthreads != 64 ||
-        h->cfg.grid[0] != 8 || h->cfg.grid[1] != 8 || h->cfg.grid[2] != 8)
-        return fail(h, DBSGYM_ESTATE, "the spectral contraction serves fp32 GRID handles on the 8 x 8 x 8 grid");
+    const bool grid_ok = h->cfg.coupling == DBSGYM_COUPLING_GRID && !h->f64 && h->grid_sym && h->cluster <= 1 &&
+                         h->cfg.grid[0] == 8 && h->cfg.grid[1] == 8;
+    if (grid_ok && h->cfg.grid[2] == 4 && h->nthreads == 32) return set_coupling_spectral_half(h, ranks8, r_max, vecs, vals);
+    if (!grid_ok || h->nthreads != 64 || h->cfg.grid[2] != 8)
+        return fail(h, DBSGYM_ESTATE, "the spectral contraction serves fp32 GRID handles on the 8 x 8 x 8 and 8 x 8 x 4 grids");
     int r_even = 1, r_odd = 1;
     for (int s8 = 0; s8 < 8; ++s8) {
         if (ranks8[s8] < 0 || ranks8[s8] > 9 || ranks8[s8] > r_max)

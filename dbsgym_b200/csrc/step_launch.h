@@ -26,6 +26,10 @@ int spectral_envs_per_cta();
 int warp_kernel_rank_set(const int* ranks8, int* compiled8);
 cudaError_t launch_f32_warp(int rank_set, int num_sms, const StepParams& p, cudaStream_t s);
 int warp_envs_per_cta();
+// the same for the 8 x 8 x 4 half grid, one octant point per lane (warp1_kernel.cuh)
+int warp1_kernel_rank_set(const int* ranks8, int* compiled8);
+cudaError_t launch_f32_warp1(int rank_set, int num_sms, const StepParams& p, cudaStream_t s);
+int warp1_envs_per_cta();
 // cluster mode: one environment = `cluster` CTAs
 cudaError_t launch_f32_cluster(int geo, int threads, int cluster, const StepParams& p, cudaStream_t s);
 

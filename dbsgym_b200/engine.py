@@ -110,15 +110,15 @@ class KuramotoEngine:
             self.set_coupling_lowrank(lowrank[0], lowrank[1], lowrank[2] if len(lowrank) > 2 else None)
 
     def set_coupling_spectral(self, vecs, vals, ranks, residual=None):
-        """Switch the GRID operator to its spectral form (dbsgym.h: dbsgym_set_coupling_spectral).  ``vecs`` [8][64][r_max],
-        ``vals`` [8][r_max], ``ranks`` [8] as returned by geometry.spectral_factors; ``ranks=None`` switches back."""
+        """Switch the GRID operator to its spectral form (dbsgym.h: dbsgym_set_coupling_spectral).  ``vecs`` [8][n_osc / 8][r_max]
+        (8 x 8 x 8 grid: 64 octant points, 8 x 8 x 4: 32), ``vals`` [8][r_max], ``ranks`` [8] as returned by geometry.spectral_factors; ``ranks=None`` switches back."""
         if ranks is None:
             self._ck(self.lib.dbsgym_set_coupling_spectral(self._h, None, 0, None, None))
             self.spectral = None
             return
         v, w = _f64(vecs), _f64(vals)
         r8 = np.ascontiguousarray(ranks, dtype=np.int32)
-        assert r8.shape == (8,)
+        assert r8.shape == (8,) and v.shape[:2] == (8, self.n_osc // 8) and w.shape == (8, v.shape[2])
         self._ck(self.lib.dbsgym_set_coupling_spectral(self._h, _capi.ptr(r8), int(v.shape[2]), _capi.ptr(v), _capi.ptr(w)))
         self.spectral = {"ranks": [int(r) for r in ranks], "modes": int(sum(ranks)), "residual": residual}
 

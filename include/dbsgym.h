@@ -109,7 +109,8 @@ int  dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out);
  * coefficients), 5 cluster mode (N > 4096), 6 GRID_SYM with gx = 8 fixed, 7 / 8 GRID_SYM with lines of 16 / 32 (gy = 16 / 32),
  * 9 spectral contraction (dbsgym_set_coupling_spectral; multi-worker hosting, 64 threads per environment),
  * 10 spectral contraction, one warp per environment with octant ownership (the default when the sector ranks fit a
- * compiled rank list), 11 DENSE operator in low-rank form (dbsgym_set_coupling_lowrank); negative = error code */
+ * compiled rank list), 11 DENSE operator in low-rank form (dbsgym_set_coupling_lowrank), 12 spectral contraction on the
+ * 8 x 8 x 4 half grid (N = 256), one warp per environment with one octant point per lane; negative = error code */
 int  dbsgym_step_variant(const DbsGymHandle* h, int32_t n_envs);
 void dbsgym_destroy(DbsGymHandle* h);
 /* text of the last error on this handle (h == NULL: last error of a failed create) */
@@ -130,7 +131,10 @@ int dbsgym_set_coupling_dense(DbsGymHandle* h, const double* alpha);
  * sector block at fundamental-octant point a = (zq * 4 + xq) * 4 + yq, vals[s * r_max + m] its eigenvalue (in the
  * unnormalised sector coordinates X_s[a] = sum_g chi_s(g) x[g a]); sector s uses its first ranks8[s] modes (0..9, at
  * most r_max).  The truncation error is the caller's responsibility (dbsgym_b200/geometry.py: spectral_factors returns
- * the spectral norm of what was dropped).  ranks8 == NULL switches back to the exact sector-block contraction. */
+ * the spectral norm of what was dropped).  ranks8 == NULL switches back to the exact sector-block contraction.
+ * The 8 x 8 x 4 half grid (n_osc = 256) is served the same way with 32-point sector blocks (a = (zq * 4 + xq) * 4 + yq,
+ * zq < 2, vecs[(s * 32 + a) * r_max + m]); there the ranks must fit a compiled rank list ({5,4,4,2,4,4,2,1} or
+ * {9,4,4,3,4,4,3,1}), otherwise DBSGYM_ESTATE and the handle keeps the exact contraction. */
 int dbsgym_set_coupling_spectral(DbsGymHandle* h, const int32_t* ranks8, int32_t r_max,
                                  const double* vecs, const double* vals);
 

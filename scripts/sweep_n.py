@@ -28,6 +28,8 @@ GRIDS = ([(8, 8, gz) for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024)] + [(16, 
          [(32, 32, gz) for gz in (8, 16, 32, 64)])       # 32^3 (and 32 x 32 x 64 for N = 65536): lines of 32, cluster mode
 if os.environ.get("SWEEP_ONLY_CUBIC"):
     GRIDS = [g for g in GRIDS if g[1] != 8]
+if os.environ.get("SWEEP_MAX_N"):
+    GRIDS = [g for g in GRIDS if g[0] * g[1] * g[2] <= int(os.environ["SWEEP_MAX_N"])]
 if os.environ.get("SWEEP_MIN_N"):
     GRIDS = [g for g in GRIDS if g[0] * g[1] * g[2] >= int(os.environ["SWEEP_MIN_N"])]
 for gx, gy, gz in GRIDS:
@@ -61,6 +63,12 @@ for gx, gy, gz in GRIDS:
             eng.set_coupling_lowrank(*f)
             lowrank = {"rank": int(f[0].shape[0]), "form": "plain", "residual_over_lambda_max": float(f[2] / abs(f[1][0])),
                        "factorisation_s": time.perf_counter() - t_f}
+    if os.environ.get("SWEEP_SPECTRAL") and (gx, gy) == (8, 8) and gz in (4, 8):     # the warp kernels (variants 12 / 10), as BatchedKuramoto selects them
+        from dbsgym_b200.geometry import spectral_factors
+        vecs, vals, ranks, residual = spectral_factors(table, gx, gy, gz, tol=float(os.environ.get("SWEEP_LOWRANK_TOL", "1e-9")))
+        eng.set_coupling_spectral(vecs, vals, ranks, residual)
+        lowrank = {"rank": int(sum(ranks)), "padded_modes": int(sum(ranks)), "form": "sectors", "kernel": "warp",
+                   "residual_over_lambda_max": float(residual / np.abs(vals).max())}
     tt = transient_grid(200.0, 0.05)
     sched = StepSchedule(400, tt[-1], 0.15, 0.75, 0.05)
     eng.set_schedule(sched); eng.set_reward("bbpow_action", 0.05)

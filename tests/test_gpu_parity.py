@@ -273,6 +273,41 @@ def test_half_grid_256_oscillators():
     assert np.max(np.abs(core.engine.state()[0] - orc.sol_state[-1])) < 1e-7
     np.testing.assert_allclose(core.theta_mean(0), orc.theta_mean, rtol=0, atol=1e-10)
     core.close()
+    # float32: the half-grid spectral kernel (one warp per environment, one octant point per lane; step-kernel variant 12, 26
+    # modes) and the exact sector contraction, teacher-forced against the oracle; 35 environments = 3 CTAs with idle warps
+    from dbsgym_b200.batched import BatchedKuramoto
+    B = 35
+    cores = {}
+    for name, ceval, variant in (("spectral", "auto", 12), ("exact", "exact", 6)):
+        c = BatchedKuramoto([copy.deepcopy(d) for _ in range(B)], precision="f32", transfer="full", coupling_eval=ceval)
+        assert c.engine.step_variant() == variant, (name, c.engine.step_variant())
+        c.engine.counters(reset=True)
+        cores[name] = c
+    assert cores["spectral"].engine.spectral["ranks"] == [5, 4, 4, 2, 4, 4, 2, 1]
+    sample = [0, 15, 16, 34]
+    for name, c in cores.items():
+        orcs = {e: copy.deepcopy(orc) for e in sample}
+        for k, a in enumerate((0.7, -0.2, 0.95, -1.0, 0.1)):
+            y_before, w_before = c.engine.state(sample), c.engine.window_values(sample)
+            for j, e in enumerate(sample):          # every environment ran its own float32 transient: restart the oracle from its state
+                o = orcs[e]
+                o.sol_state, o.theta_state = y_before[j][None, :].copy(), w_before[j][None, :].copy()
+                o.current_step, o.current_time = int(c.current_step[e]), c.current_time(e)
+            obs, rew, done = c.step(np.full(B, a, dtype=np.float32))
+            y = c.engine.state(sample)
+            for j, e in enumerate(sample):
+                o = orcs[e]
+                o_ref, r_ref, *_ = o.step(np.array([a], dtype=np.float32))
+                err = np.max(np.abs(y[j] - o.sol_state[-1]))
+                assert err < 1e-5, (name, k, e, err)
+                assert np.max(np.abs(c.theta_records(e) - o.theta_records)) < 2e-6
+                assert np.max(np.abs(c.theta_mean(e) - o.theta_mean)) < 2e-6
+                assert rew[e] == pytest.approx(r_ref, rel=2e-4, abs=1e-7)
+                np.testing.assert_allclose(obs[e], o_ref[0], rtol=0, atol=3e-6)
+    for c in cores.values():
+        cc = c.engine.counters()
+        assert (cc["accepted"], cc["rejected"], cc["rhs_evals"], cc["status"]) == (B * 5 * 5, 0, B * 5 * 32, 0)
+        c.close()
 
 
 def test_plain_toeplitz_contraction_matches_symmetric_one():
