@@ -370,6 +370,8 @@ class BatchedKuramoto:
         return float(self.t_transient[-1]) if k == 0 else float(self.schedule.t_after[k - 1])
 
     def close(self):
+        if self.host_batch is not None:
+            self.host_batch.close()
         self.engine.close()
 
 

@@ -1064,20 +1064,39 @@ int dbsgym_set_env_params(DbsGymHandle* h, const int32_t* env_ids, int32_t n, co
             rc = scatter_to_device(h, h->phase, buf.data(), ids, n, row);
             if (rc) return rc;
         } else {
-            // fp32 state: wrapped phase + integer winding count, y = phase + 2*pi*wind
-            std::vector<float> ph((size_t)n * h->Np, 0.f);
-            std::vector<int32_t> wd((size_t)n * h->Np, 0);
-            for (int r = 0; r < n; ++r)
+            // fp32 state: wrapped phase + integer winding count, y = phase + 2*pi*wind.  Both arrays are written straight into
+            // the pinned staging buffer (phases in its first half, winding counts in the second), one copy, two scatters.
+            const size_t half = row * (size_t)n;
+            rc = ensure_stage(h, 2 * half);
+            if (rc) return rc;
+            float* ph = reinterpret_cast<float*>(h->stage_host);
+            int32_t* wd = reinterpret_cast<int32_t*>(static_cast<unsigned char*>(h->stage_host) + half);
+            for (int r = 0; r < n; ++r) {
+                const double* yr = y0 + (size_t)r * h->N;
+                float* pr = ph + (size_t)r * h->Np;
+                int32_t* wr = wd + (size_t)r * h->Np;
                 for (int i = 0; i < h->N; ++i) {
-                    const double y = y0[(size_t)r * h->N + i];
-                    const double k = std::floor(y / kTwoPi);
-                    ph[(size_t)r * h->Np + i] = (float)(y - k * kTwoPi);
-                    wd[(size_t)r * h->Np + i] = (int32_t)k;
+                    const double y = yr[i];
+                    if (y >= 0.0 && y < kTwoPi) { pr[i] = (float)y; wr[i] = 0; }          // (a freshly drawn phase: N(pi, 0.6))
+                    else {
+                        const double k = std::floor(y / kTwoPi);
+                        pr[i] = (float)(y - k * kTwoPi);
+                        wr[i] = (int32_t)k;
+                    }
                 }
-            rc = scatter_to_device(h, h->phase, ph.data(), ids, n, row);
-            if (rc) return rc;
-            rc = scatter_to_device(h, h->wind, wd.data(), ids, n, (size_t)h->Np * 4);
-            if (rc) return rc;
+                for (int i = h->N; i < h->Np; ++i) { pr[i] = 0.f; wr[i] = 0; }
+            }
+            cudaError_t e = cudaMemcpyAsync(h->stage_dev, h->stage_host, 2 * half, cudaMemcpyHostToDevice, h->stream);
+            if (e == cudaSuccess) {
+                scatter_rows_kernel<<<n, 128, 0, h->stream>>>(reinterpret_cast<unsigned char*>(h->phase),
+                                                              static_cast<const unsigned char*>(h->stage_dev), ids, n, row);
+                scatter_rows_kernel<<<n, 128, 0, h->stream>>>(reinterpret_cast<unsigned char*>(h->wind),
+                                                              static_cast<const unsigned char*>(h->stage_dev) + half, ids, n, row);
+                h->n_launches += 2;
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);      // the staging pair is reused by the next call
+            if (e != cudaSuccess) return fail(h, DBSGYM_ECUDA, "scatter failed: %s", cudaGetErrorString(e));
         }
     }
     return DBSGYM_OK;

@@ -44,6 +44,21 @@ class HostList(list):
         return (self[i] for i in range(len(self)))
 
 
+class _Prepared:
+    """One batched reset up to (and including) its random draws, not yet applied to the batch."""
+
+
+def _copy_state(st):
+    out = _capi.DbsGymNpState()
+    C.memmove(C.byref(out), C.byref(st), C.sizeof(_capi.DbsGymNpState))
+    return out
+
+
+def _same_state(a, b):
+    return (a.pos == b.pos and a.has_gauss == b.has_gauss and (not a.has_gauss or a.gauss == b.gauss) and
+            bytes(a.key) == bytes(b.key))
+
+
 class HostBatch:
     @staticmethod
     def supported(hosts):
@@ -71,8 +86,13 @@ class HostBatch:
                     return False
         return True
 
-    def __init__(self, hosts):
+    def __init__(self, hosts, speculate=None):
         self.hosts = hosts
+        # prepare the next full reset on a worker thread (see begin_episodes); on by default for batches large enough for
+        # the draws to matter
+        self.speculate = (len(hosts) >= 256) if speculate is None else bool(speculate)
+        self._job = None
+        self.prepared_used = self.prepared_dropped = 0
         p0 = self.p0 = hosts[0].params_dict
         B, N = len(hosts), int(p0["num_oscillators"])
         self.B, self.N = B, N
@@ -115,6 +135,8 @@ class HostBatch:
         self._last_key = np.full((B, 7), np.nan)       # (contacts, conduct_modifier) the device holds stim / rec vectors for
         self._w0_sent = np.zeros(B, dtype=bool)        # the device holds this environment's current w0
         self.lo, self.hi = 1, min(p0["grid_size"]) - 2
+        if self.speculate:             # the first batched reset too (a VecEnv's first auto-reset, or the reset() right after construction)
+            self._start_prepare(np.arange(B, dtype=np.int64), self.stream.pull().st)
 
     # ------------------------------------------------------------------------------------------------------
     def sync_to_host(self, i, h):
@@ -140,49 +162,100 @@ class HostBatch:
         [n, N] float64 and the ElectrodeModel of every environment.  With ``changed_only`` the tuple continues with two
         boolean masks (el_changed, w0_changed) over the listed environments and ``stim`` / ``rec`` hold only the rows of the
         environments whose electrode (contacts or conduct_modifier) differs from what the caller was given last time -- most
-        resets change neither, and the conductance vectors are 2 x 4 KB per environment to build and upload."""
+        resets change neither, and the conductance vectors are 2 x 4 KB per environment to build and upload.
+
+        The draws of a reset depend only on the host state the previous reset left and on numpy's global stream, so after a
+        reset of EVERY environment (synchronous episodes) the next one is prepared ahead of time on a worker thread
+        (``speculate``): when the next call again lists every environment and ``np.random`` still is in the state the
+        last reset left it in, its numbers are taken from there -- the same numbers, the same final stream state; in any
+        other case the prepared reset is dropped and the call draws as usual."""
         ids = np.asarray(ids, dtype=np.int64)
+        prep = self._take_prepared(ids)
+        if prep is None:
+            prep = self._prepare(ids, self.stream.pull().st)
+        out = self._commit(prep, changed_only)
+        if self.speculate and prep.everyone:
+            self._start_prepare(ids, prep.end_state)
+        return out
+
+    # ---- speculation ---------------------------------------------------------------------------------------
+    def _start_prepare(self, ids, state):
+        import threading
+        job = {"ids": ids, "state": _copy_state(state), "prep": None, "error": None}
+
+        def work():
+            try:
+                job["prep"] = self._prepare(ids, _copy_state(job["state"]))
+            except BaseException as e:          # (reported by the caller's thread when it takes the result)
+                job["error"] = e
+        job["thread"] = threading.Thread(target=work, name="dbsgym-reset-prepare", daemon=True)
+        job["thread"].start()
+        self._job = job
+
+    def _take_prepared(self, ids):
+        """The reset prepared ahead of time, if it is the one being asked for (same environments, numpy's global stream
+        untouched since); waits for the worker either way, because the caller is about to change the state it reads."""
+        job, self._job = self._job, None
+        if job is None:
+            return None
+        job["thread"].join()
+        if job["error"] is not None or job["prep"] is None or not np.array_equal(ids, job["ids"]):
+            self.prepared_dropped += 1
+            return None
+        if not _same_state(self.stream.pull().st, job["state"]):
+            self.prepared_dropped += 1
+            return None
+        self.prepared_used += 1
+        return job["prep"]
+
+    def close(self):
+        job, self._job = self._job, None
+        if job is not None:
+            job["thread"].join()
+
+    # ---- phase 1: everything up to and including the draws; does NOT modify the batch ---------------------
+    def _prepare(self, ids, state):
         n, N = ids.size, self.N
-        everyone = n == self.B and np.array_equal(ids, np.arange(self.B))
+        pr = _Prepared()
+        pr.ids, pr.n = ids, n
+        pr.everyone = everyone = n == self.B and np.array_equal(ids, np.arange(self.B))
         sel = slice(None) if everyone else ids                     # (views instead of gathered copies for a full reset)
-        rc = self.reset_count[ids] + 1
-        self.reset_count[ids] = rc
+        pr.rc = rc = self.reset_count[ids] + 1
         flags = np.zeros(n, dtype=np.uint8)
+        pr.f_en = pr.f_pl = pr.f_rg = None
         if self.drift:
             f_el = self.elec_drift_episode[ids] == rc
-            f_en = self.elec_encaps_episode[ids] == rc
-            f_pl = self.plasticity_episode[ids] == rc
-            f_rg = (rc % self.regen_every) == 0
+            pr.f_en = f_en = self.elec_encaps_episode[ids] == rc
+            pr.f_pl = f_pl = self.plasticity_episode[ids] == rc
+            pr.f_rg = f_rg = (rc % self.regen_every) == 0
             flags |= (f_el * _capi.RESET_ELECTRODE_MOVE + f_en * _capi.RESET_ENCAPSULATION + f_pl * _capi.RESET_PLASTICITY +
                       f_rg * _capi.RESET_WALK_REGEN).astype(np.uint8)
-        f_sp = self.spatial_feature[ids] & (self.spatial_var_episode[ids] == rc) & (rc > 2)
+        pr.f_sp = f_sp = self.spatial_feature[ids] & (self.spatial_var_episode[ids] == rc) & (rc > 2)
         flags |= (f_sp * _capi.RESET_SPATIAL).astype(np.uint8)
 
         # natural frequencies of this episode (known before any draw: the plasticity event takes an entry of the walk
         # generated EARLIER, a walk regeneration goes back to the original vector; env.py:519-541, :566)
-        wl = self.wl[sel]
-        if self.drift:
-            if f_pl.any():
-                who = ids[f_pl]
-                wl[f_pl] = self.walk[who, self.count[who]]
-                self.count[who] += 1
-            if f_rg.any():
-                self.count[ids[f_rg]] = 0
-                wl[f_rg] = self.wl_orig[ids[f_rg]]
-            if not everyone:
-                self.wl[ids] = wl
-        w0 = wl * self.keep[sel]                                          # utils.py:902-906 apply_locus_mask
+        w0 = self.wl[sel] * self.keep[sel]                                # utils.py:902-906 apply_locus_mask
         w0 += self.locus_term[sel]
+        pr.wl_rows, pr.wl_vals = np.empty(0, dtype=np.int64), None        # rows whose w0_without_locus changes, new vectors
+        if self.drift and (f_pl.any() or f_rg.any()):
+            rows = np.flatnonzero(f_pl | f_rg)
+            who = ids[rows]
+            vals = np.where(f_rg[rows][:, None], self.wl_orig[who], self.walk[who, np.minimum(self.count[who], self.M)])
+            pr.wl_rows, pr.wl_vals = rows, vals
+            fix = vals * self.keep[who]
+            fix += self.locus_term[who]
+            w0[rows] = fix
         bad = w0 <= 0.0
         n_fix = np.count_nonzero(bad, axis=1).astype(np.int32)
 
         # ---- every draw of this reset, in the reference's order, from numpy's global stream ----
         n_regen = int(f_rg.sum()) if self.drift else 0
-        elec = np.ascontiguousarray(self.elec[ids])
-        inc = np.zeros((n, 3), dtype=np.int32)
-        pick = np.empty(n, dtype=np.int32)
+        pr.elec = elec = np.ascontiguousarray(self.elec[ids])
+        pr.inc = inc = np.zeros((n, 3), dtype=np.int32)
+        pr.pick = pick = np.empty(n, dtype=np.int32)
         fix_noise = np.empty(max(int(n_fix.sum()), 1))
-        walk_noise = np.empty((max(n_regen, 1), max(self.M, 1), N)) if n_regen else None
+        pr.walk_noise = walk_noise = np.empty((max(n_regen, 1), max(self.M, 1), N)) if n_regen else None
         y0 = np.empty((n, N))
         cap_rows, cap_noise = 64, 512
         refix_env = np.zeros((cap_rows, 2), dtype=np.int32)
@@ -195,39 +268,16 @@ class HostBatch:
         plan.random_freq_update = 1 if (self.drift and self.p0["random_freq_update"]) else 0
         plan.refix_cap_rows, plan.refix_cap_noise = cap_rows, cap_noise
         plan.init_mean, plan.init_sd = float(self.p0["init_state_mean"]), float(self.p0["init_state_sd"])
-        st = self.stream.pull()
         freq = np.ascontiguousarray(self.freq[ids])
-        rcode = st.lib.dbsgym_np_reset_draws(
-            C.byref(st.st), C.byref(plan), _capi.ptr(flags), _capi.ptr(freq), _capi.ptr(elec), _capi.ptr(inc),
+        rcode = self.stream.lib.dbsgym_np_reset_draws(
+            C.byref(state), C.byref(plan), _capi.ptr(flags), _capi.ptr(freq), _capi.ptr(elec), _capi.ptr(inc),
             _capi.ptr(pick), _capi.ptr(n_fix), _capi.ptr(fix_noise), _capi.ptr(walk_noise) if n_regen else None,
             _capi.ptr(y0), _capi.ptr(refix_env), _capi.ptr(refix_noise), C.byref(n_refix))
         if rcode:
             raise _capi.DbsGymError(f"dbsgym_np_reset_draws failed ({rcode})")
-        st.push()
+        pr.end_state = state
 
-        # ---- apply them ----
-        if self.drift:
-            self.elec_drift_episode[ids] += inc[:, 0]
-            self.elec_encaps_episode[ids] += inc[:, 1]
-            self.plasticity_episode[ids] += inc[:, 2]
-            self.elec[ids] = elec
-            if f_en.any():
-                self.encaps[ids[f_en]] += self.encaps_percent[ids[f_en]]          # added as an absolute amount (SURVEY F7)
-            if n_regen:
-                who = ids[f_rg]
-                base = self.wl_orig[who]
-                sigma = self.step_scale[who] * np.std(base, axis=1, ddof=1)     # env.py:21-57 generate_perturbations
-                walk = np.empty((who.size, self.M + 1, N))
-                walk[:, 0] = base
-                for m in range(self.M):
-                    walk[:, m + 1] = walk[:, m] + sigma[:, None] * walk_noise[:, m]
-                self.walk[who] = walk
-        if f_sp.any():                                                    # env.py:544-552
-            for r in np.flatnonzero(f_sp):
-                i, row = int(ids[r]), self.table[int(pick[r])]
-                self.elec[i], self.rec[i] = row[0], row[1]
-                self.spatial_var_episode[i] += self.spatial_var_freq[i]
-                self.hosts[i].spatial_events.append([int(rc[r]), row])
+        # ---- the arithmetic on them that touches only this reset's own arrays ----
         if n_fix.any():                                                   # utils.py:819-823 on w0
             rows = np.flatnonzero(n_fix)
             means = np.zeros(n)
@@ -239,6 +289,45 @@ class HostBatch:
             row = y0[r]
             row[row <= 0.0] = np.abs(refix_noise[at:at + k] * 0.05) + np.mean(row)
             at += k
+        pr.w0, pr.y0, pr.n_fix = w0, y0, n_fix
+        return pr
+
+    # ---- phase 2: apply a prepared reset to the batch --------------------------------------------------------
+    def _commit(self, pr, changed_only):
+        ids, n, N, rc = pr.ids, pr.n, self.N, pr.rc
+        everyone, f_en, f_pl, f_rg, f_sp = pr.everyone, pr.f_en, pr.f_pl, pr.f_rg, pr.f_sp
+        w0, y0, n_fix, inc = pr.w0, pr.y0, pr.n_fix, pr.inc
+        self.stream.st = pr.end_state
+        self.stream.push()
+        self.reset_count[ids] = rc
+        if self.drift:
+            if f_pl.any():
+                self.count[ids[f_pl]] += 1
+            if f_rg.any():
+                self.count[ids[f_rg]] = 0
+            if pr.wl_rows.size:
+                self.wl[ids[pr.wl_rows]] = pr.wl_vals
+            self.elec_drift_episode[ids] += inc[:, 0]
+            self.elec_encaps_episode[ids] += inc[:, 1]
+            self.plasticity_episode[ids] += inc[:, 2]
+            self.elec[ids] = pr.elec
+            if f_en.any():
+                self.encaps[ids[f_en]] += self.encaps_percent[ids[f_en]]          # added as an absolute amount (SURVEY F7)
+            if pr.walk_noise is not None:
+                who = ids[f_rg]
+                base = self.wl_orig[who]
+                sigma = self.step_scale[who] * np.std(base, axis=1, ddof=1)     # env.py:21-57 generate_perturbations
+                walk = np.empty((who.size, self.M + 1, N))
+                walk[:, 0] = base
+                for m in range(self.M):
+                    walk[:, m + 1] = walk[:, m] + sigma[:, None] * pr.walk_noise[:, m]
+                self.walk[who] = walk
+        if f_sp.any():                                                    # env.py:544-552
+            for r in np.flatnonzero(f_sp):
+                i, row = int(ids[r]), self.table[int(pr.pick[r])]
+                self.elec[i], self.rec[i] = row[0], row[1]
+                self.spatial_var_episode[i] += self.spatial_var_freq[i]
+                self.hosts[i].spatial_events.append([int(rc[r]), row])
         if everyone:
             self.w0, self.init_state = w0, y0
         else:

@@ -41,7 +41,11 @@ def _state():
                   reset_plasticity_episode=4, spatial_var_freq=3), True, 20),
     ("env1", dict(spatial_var_freq=3), False, 14),
 ])
-def test_batched_reset_equals_sequential_resets(cfg, over, compat, rounds):
+@pytest.mark.parametrize("speculate", [False, True])
+def test_batched_reset_equals_sequential_resets(cfg, over, compat, rounds, speculate):
+    """``speculate``: after a reset of every environment the next one is prepared on a worker thread; it is used when the
+    next call again lists everybody and np.random is where the last reset left it (here: every full round after a full
+    round), dropped otherwise (the subset rounds, the rounds after one, a round after somebody else drew a number)."""
     _capi.build()
     B = 7
     dev = {}                                   # what a device that only receives the CHANGED vectors would hold (changed_only path)
@@ -54,11 +58,13 @@ def test_batched_reset_equals_sequential_resets(cfg, over, compat, rounds):
     b, _ = _build(copy.deepcopy(dicts), compat)
     assert np.array_equal(_state()[0], end_a[0])
     assert HostBatch.supported(b)
-    hb = HostBatch(b)
+    hb = HostBatch(b, speculate=speculate)
     bl = HostList(b, hb)
     events = 0
     for r in range(rounds):
         ids = list(range(B)) if r % 5 != 3 else [4, 1, 6]              # sometimes a subset, in a non-sorted order
+        if r == 7:
+            np.random.standard_normal(3)       # somebody else uses the global stream between two resets
         st = np.random.get_state()
         setups = [a[i].begin_episode() for i in ids]
         after_a = _state()
@@ -98,6 +104,10 @@ def test_batched_reset_equals_sequential_resets(cfg, over, compat, rounds):
     if cfg == "env2":
         assert len({tuple(h.elec_coords[0]) for h in a}) > 1 and max(h.encapsulation_coeff for h in a) > 2.0
     assert events > 0
+    full = [r for r in range(rounds) if r % 5 != 3]
+    expect_used = sum(1 for r in full if (r - 1) % 5 != 3 and r != 7) if speculate else 0   # (round 0: prepared at construction)
+    assert hb.prepared_used == expect_used and (hb.prepared_dropped > 0) == speculate
+    hb.close()
 
 
 def test_non_positive_initial_phase_is_fixed_like_remove_negative_w0():
