@@ -85,9 +85,9 @@ class DbsGymError(RuntimeError):
     pass
 
 
-UNITS = ("api", "host_rng", "step_f32_grid", "step_f32_sym", "step_f32_lines", "step_f32_dense", "step_f32_lowrank", "step_f32_mw", "step_f32_spectral", "step_f32_warp", "step_f32_warp1",
+UNITS = ("api", "host_rng", "step_f32_grid", "step_f32_sym", "step_f32_lines", "step_f32_dense", "step_f32_lowrank", "step_f32_mw", "step_f32_spectral", "step_f32_warp", "step_f32_warp1", "step_f32_oct",
          "step_f32_cluster", "step_f64_grid", "step_f64_sym", "step_f64_dense")
-HEADERS = ("step_kernel.cuh", "warp_kernel.cuh", "warp1_kernel.cuh", "step_launch.h", "obs_kernel.cuh", "eval_kernel.cuh")
+HEADERS = ("step_kernel.cuh", "warp_kernel.cuh", "warp1_kernel.cuh", "oct_kernel.cuh", "step_launch.h", "obs_kernel.cuh", "eval_kernel.cuh")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 

@@ -101,6 +101,9 @@ struct DbsGymHandle {
     // the same operator laid out for the one-warp-per-environment kernel (warp_kernel.cuh): [32 lanes][modes] float2 and
     // [modes] eigenvalues, for the compiled rank list warp_set (-1: the ranks fit none, or DBSGYM_DBG_NO_WARP_KERNEL)
     float* wspec_v = nullptr; float* wspec_lam = nullptr; int warp_set = -1; bool no_warp = false;
+    // sector form of the low-rank operator on 1024 ... 4096 oscillators: tables of oct_kernel.cuh ([mode][N / 8] eigenvector
+    // entries, eigenvalues x K / (8 N)) for the compiled rank list oct_set (-1: the block kernel of step_kernel.cuh runs)
+    float* oct_v = nullptr; float* oct_lam = nullptr; int oct_set = -1;
     int half_set = -1;                   // 8 x 8 x 4 half grid: compiled rank list of warp1_kernel.cuh in use (-1: exact contraction)
     // low-rank form of a DENSE operator (dbsgym_set_coupling_lowrank): eigenvectors [lr_rank][Np], eigenvalues [lr_rank]
     float* lr_v = nullptr; float* lr_lam = nullptr; int lr_rank = 0;
@@ -339,6 +342,7 @@ void fill_params(DbsGymHandle* h, StepParams& p) {
     p.fsal_on = h->fsal_on ? 1 : 0; p.k_fsal = h->k_fsal; p.fsal_valid = h->fsal_valid;
     const bool warp = (h->spec_re > 0 && h->warp_set >= 0) || h->half_set >= 0;
     p.spec_v = warp ? h->wspec_v : h->spec_v; p.spec_lam = warp ? h->wspec_lam : h->spec_lam;
+    if (h->oct_set >= 0) { p.spec_v = h->oct_v; p.spec_lam = h->oct_lam; }
     p.lr_v = h->lr_v; p.lr_lam = h->lr_lam; p.lr_rank = h->lr_rank;
     p.lr_sectors = h->lr_sectors ? 1 : 0; p.lr_soff = h->lr_soff;
     p.power_scale = h->rspec.power_scale; p.action_cost = h->rspec.action_cost;
@@ -369,6 +373,7 @@ int sym_geo(const DbsGymHandle* h, const StepParams& p) {
 cudaError_t launch_step(DbsGymHandle* h, const StepParams& p, cudaStream_t s) {
     ++h->n_launches;
     const int t = h->nthreads;
+    if (h->oct_set >= 0) return launch_f32_oct(h->oct_set, h->num_sms, p, s);
     if (h->lr_rank > 0 && !h->f64) {                      // the operator in low-rank form (GRID and DENSE handles alike)
         if (h->cluster > 1) return launch_f32_lowrank_cluster(t, h->cluster, h->lr_rank, p, s);
         return launch_f32_lowrank(t, step_smem_bytes(h->Np, 2 * h->lr_rank, t, 4), p, s);
@@ -548,6 +553,7 @@ int dbsgym_abi_version(void) { return DBSGYM_ABI_VERSION; }
 
 int dbsgym_step_variant(const DbsGymHandle* h, int32_t n_envs) {
     if (!h) return DBSGYM_EINVAL;
+    if (h->oct_set >= 0) return 13;
     if (h->lr_rank > 0 && !h->f64) return 11;
     if (h->cluster > 1) return 5;
     if (h->cfg.coupling == DBSGYM_COUPLING_DENSE) return 1;
@@ -732,7 +738,7 @@ void dbsgym_destroy(DbsGymHandle* h) {
                     h->step_idx, h->episode_len, h->lfp_true, h->lfp_rec, h->u, h->reward, h->done, h->sched_nI,
                     h->sched_nII, h->sched_offI, h->sched_offII, h->ts_dev, h->ids_dev, h->lin_g, h->tw_seed,
                     h->tw_inner, h->spec, h->tw_full, h->k_fsal, h->fsal_valid, h->counters, h->status, h->st_actions, h->st_obs, h->st_reward, h->st_done, h->st_samples,
-                    h->cl_operand, h->cl_scratch, h->mpos, h->spec_v, h->spec_lam, h->wspec_v, h->wspec_lam, h->lr_v, h->lr_lam, h->lr_soff};
+                    h->cl_operand, h->cl_scratch, h->mpos, h->spec_v, h->spec_lam, h->wspec_v, h->wspec_lam, h->lr_v, h->lr_lam, h->lr_soff, h->oct_v, h->oct_lam};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->pin_ints) cudaFreeHost(h->pin_ints);
@@ -1006,6 +1012,38 @@ int dbsgym_set_coupling_lowrank_sectors(DbsGymHandle* h, const int32_t* soff9, c
     h->lr_rank = R;
     h->lr_sectors = true;
     h->have_coupling = true;
+    // 1024 ... 4096 oscillators in one CTA: the register-resident kernel of oct_kernel.cuh when a compiled rank list covers
+    // the sectors' ranks (modes with a non-zero eigenvalue; the padding of every sector's block is zero)
+    h->oct_set = -1;
+    if (h->cluster <= 1 && !h->no_warp && (N == 1024 || N == 2048 || N == 4096) && h->nthreads == P8) {
+        int ranks8[8], compiled[8];
+        for (int s8 = 0; s8 < 8; ++s8) {
+            ranks8[s8] = 0;
+            for (int m = soff9[s8]; m < soff9[s8 + 1]; ++m)
+                if (vals[m] != 0.0) ranks8[s8] = m - soff9[s8] + 1;
+        }
+        const int oset = oct_kernel_rank_set(N, ranks8, compiled);
+        if (oset >= 0) {
+            int nm = 0;
+            for (int s8 = 0; s8 < 8; ++s8) nm += compiled[s8];
+            const double scale = h->cfg.K / (8.0 * (double)N);
+            std::vector<float> ov((size_t)nm * P8, 0.f), olam((size_t)nm, 0.f);
+            int off = 0;
+            for (int s8 = 0; s8 < 8; ++s8) {
+                for (int j = 0; j < ranks8[s8]; ++j) {
+                    const int m = soff9[s8] + j;
+                    olam[off + j] = (float)(vals[m] * scale);
+                    for (int a = 0; a < P8; ++a) ov[(size_t)(off + j) * P8 + a] = (float)zvecs[(size_t)m * P8 + a];
+                }
+                off += compiled[s8];
+            }
+            CU(h, cudaMalloc(&h->oct_v, ov.size() * sizeof(float)));
+            CU(h, cudaMalloc(&h->oct_lam, olam.size() * sizeof(float)));
+            CU(h, cudaMemcpy(h->oct_v, ov.data(), ov.size() * sizeof(float), cudaMemcpyHostToDevice));
+            CU(h, cudaMemcpy(h->oct_lam, olam.data(), olam.size() * sizeof(float), cudaMemcpyHostToDevice));
+            h->oct_set = oset;
+        }
+    }
     if (h->fsal_valid) CU(h, cudaMemset(h->fsal_valid, 0, (size_t)h->B * 4));
     return DBSGYM_OK;
 }

@@ -30,6 +30,9 @@ int warp_envs_per_cta();
 int warp1_kernel_rank_set(const int* ranks8, int* compiled8);
 cudaError_t launch_f32_warp1(int rank_set, int num_sms, const StepParams& p, cudaStream_t s);
 int warp1_envs_per_cta();
+// regular grids of 1024 / 2048 / 4096 oscillators in octant order, eigenvectors in registers, one CTA per environment (oct_kernel.cuh)
+int oct_kernel_rank_set(int n_osc, const int* ranks8, int* compiled8);
+cudaError_t launch_f32_oct(int rank_set, int num_sms, const StepParams& p, cudaStream_t s);
 // cluster mode: one environment = `cluster` CTAs
 cudaError_t launch_f32_cluster(int geo, int threads, int cluster, const StepParams& p, cudaStream_t s);
 

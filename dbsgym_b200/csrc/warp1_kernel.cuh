@@ -15,6 +15,11 @@
 #ifndef DBSGYM_WARP1_ENVS
 #define DBSGYM_WARP1_ENVS 16
 #endif
+// 1: the four coefficient vectors of the dense-output polynomial wait in the rows of k3 .. k6 (dead once they are formed)
+// instead of 32 registers
+#ifndef DBSGYM_WARP1_DENSE_SMEM
+#define DBSGYM_WARP1_DENSE_SMEM 0
+#endif
 #ifndef DBSGYM_WARP1_PASSES
 #define DBSGYM_WARP1_PASSES 2          // mode sums in two passes (half the partials buffer: 16 warps fit an SM)
 #endif
@@ -411,6 +416,10 @@ __global__ void __launch_bounds__(DBSGYM_WARP1_ENVS * 32, 1) warp1_step_kernel(c
                             pb[r] = 5.f * f0r - 3.f * f1r + 14.f * d - 32.f * dmr;
                             pc[r] = f1r - 4.f * f0r - 5.f * d + 16.f * dmr;
                         }
+                        if (DBSGYM_WARP1_DENSE_SMEM) {
+                            w1store8(K + 2 * kW1N, lane, pa); w1store8(K + 3 * kW1N, lane, pb);
+                            w1store8(K + 4 * kW1N, lane, pc); w1store8(K + 5 * kW1N, lane, f0);
+                        }
                     }
                     float rc[kW1R];                      // recording conductance (env.py:404-412), L1 / L2 resident
                     if (p.weighted_rec) hg_load<float>(reinterpret_cast<const float*>(p.rec) + base, OP, rc);
@@ -432,9 +441,23 @@ __global__ void __launch_bounds__(DBSGYM_WARP1_ENVS * 32, 1) warp1_step_kernel(c
                                 for (int r = 0; r < kW1R; ++r) ysmp[r] = y0[r] + d1[r];
                             } else {
                                 const float tau = (float)(tsv - tt) * inv_h;
+                                if (DBSGYM_WARP1_DENSE_SMEM) {
+                                    float c[kW1R];
+                                    w1load8(K + 2 * kW1N, lane, ysmp);
+                                    w1load8(K + 3 * kW1N, lane, c);
+#pragma unroll
+                                    for (int r = 0; r < kW1R; ++r) ysmp[r] = fmaf(ysmp[r], tau, c[r]);
+                                    w1load8(K + 4 * kW1N, lane, c);
+#pragma unroll
+                                    for (int r = 0; r < kW1R; ++r) ysmp[r] = fmaf(ysmp[r], tau, c[r]);
+                                    w1load8(K + 5 * kW1N, lane, c);
+#pragma unroll
+                                    for (int r = 0; r < kW1R; ++r) ysmp[r] = fmaf(fmaf(ysmp[r], tau, c[r]), tau, y0[r]);
+                                } else {
 #pragma unroll
                                 for (int r = 0; r < kW1R; ++r)
                                     ysmp[r] = fmaf(fmaf(fmaf(fmaf(pa[r], tau, pb[r]), tau, pc[r]), tau, f0[r]), tau, y0[r]);
+                                }
                             }
                             float st0 = 0.f, st1 = 0.f, sr0 = 0.f, sr1 = 0.f;
 #pragma unroll

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """A few steps of the sector low-rank kernel on a cubic grid (default 32 x 32 x 16, N = 16384) for ncu:
-    ncu --set full --import-source on -k regex:step_kernel -s 3 -c 1 -o gpurun_out/x python scripts/prof_lowrank.py [gz]"""
+    ncu --set full --import-source on -k regex:step_kernel -s 3 -c 1 -o gpurun_out/x python scripts/prof_lowrank.py [gz [gx = gy]]"""
 import os
 import sys
 
@@ -12,7 +12,7 @@ from dbsgym_b200.engine import KuramotoEngine  # noqa: E402
 from dbsgym_b200.geometry import coupling_table, distances_from, grid_sector_factors, neuron_grid  # noqa: E402
 from dbsgym_b200.schedule import StepSchedule, transient_grid  # noqa: E402
 
-gx = gy = 32
+gx = gy = int(sys.argv[2]) if len(sys.argv) > 2 else 32           # (16 4 / 16 8 / 16 16: the register-resident kernel, variant 13)
 gz = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 N = gx * gy * gz
 B = 2097152 // N

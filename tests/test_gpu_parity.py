@@ -203,7 +203,7 @@ def test_shuffled_grid_f32_runs_the_grid_kernels_through_the_order_map_and_the_l
 
 def test_large_regular_grid_selects_the_sector_low_rank_form_and_matches_oracle():
     """N = 2048 on a 16 x 16 x 8 grid through the public BatchedKuramoto: float32 'auto' takes the operator as sector-wise
-    eigenpairs over the fundamental octant (step-kernel variant 11, oscillators stored in octant order inside the library) --
+    eigenpairs over the fundamental octant (step-kernel variants 13 / 11, oscillators stored in octant order inside the library) --
     reset transient and teacher-forced steps against the float64 oracle; coupling_eval='exact' keeps the structured kernel."""
     from oracle import kuramoto_oracle as ko
     import dbsgym_b200.utils as U
@@ -216,23 +216,25 @@ def test_large_regular_grid_selects_the_sector_low_rank_form_and_matches_oracle(
     orc = ko.OracleEnv(copy.deepcopy(d))
     core = BatchedKuramoto([copy.deepcopy(d)] * 2, precision="f32", transfer="full")
     assert core.engine.coupling == "grid" and core.coupling_eval == "lowrank"
-    assert core.engine.step_variant() == 11 and core.engine.lowrank["sectors"]
+    assert core.engine.step_variant() == 13 and core.engine.lowrank["sectors"]       # eigenvectors in registers (oct_kernel.cuh)
+    block = BatchedKuramoto([copy.deepcopy(d)] * 2, precision="f32", transfer="full", engine_options={"no_warp_kernel": True})
+    assert block.engine.step_variant() == 11 and block.engine.lowrank["sectors"]     # the block kernel streaming them from L2
     exact = BatchedKuramoto([copy.deepcopy(d)] * 2, precision="f32", transfer="full", coupling_eval="exact")
     assert exact.engine.step_variant() == 7
-    for c in (core, exact):
+    for c in (core, block, exact):
         assert np.max(np.abs(c.engine.state()[0] - orc.sol_state[-1])) < 2e-3          # 118-unit transient with rejections
         c.engine.counters(reset=True)
     for k, a in enumerate((0.6, -0.3, 0.9)):
         y_before = orc.sol_state[-1].copy()
         o_ref, r_ref, *_ = orc.step(np.array([a], dtype=np.float32))
-        for name, c in (("lowrank", core), ("exact", exact)):
+        for name, c in (("lowrank", core), ("lowrank_block", block), ("exact", exact)):
             c.engine.set_env_params(None, y0=np.tile(y_before, (2, 1)))                # teacher-forced
             obs, rew, done = c.step(np.array([a, a], dtype=np.float32))
             err = np.max(np.abs(c.engine.state()[0] - orc.sol_state[-1]))
             assert err < 1e-5, (name, k, err)
             assert np.max(np.abs(c.theta_records(0) - orc.theta_records)) < 2e-6
             assert np.max(np.abs(c.theta_mean(0) - orc.theta_mean)) < 2e-6
-    for c in (core, exact):
+    for c in (core, block, exact):
         cc = c.engine.counters()
         assert (cc["accepted"], cc["rejected"], cc["rhs_evals"], cc["status"]) == (2 * 3 * 5, 0, 2 * 3 * 32, 0)
         c.close()
@@ -244,7 +246,7 @@ def test_large_regular_grid_selects_the_sector_low_rank_form_and_matches_oracle(
         ds[k] = np.asarray(ds[k])[perm]
     orc_s = ko.OracleEnv(copy.deepcopy(ds))
     shuf = BatchedKuramoto([copy.deepcopy(ds)] * 2, precision="f32", transfer="full")
-    assert shuf.engine.coupling == "grid" and shuf.engine.order is not None and shuf.engine.step_variant() == 11
+    assert shuf.engine.coupling == "grid" and shuf.engine.order is not None and shuf.engine.step_variant() == 13
     assert shuf.engine.lowrank["sectors"]
     y_before = orc_s.sol_state[-1].copy()
     orc_s.step(np.array([0.5], dtype=np.float32))
