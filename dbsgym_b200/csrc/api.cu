@@ -821,6 +821,7 @@ int dbsgym_set_coupling_spectral(DbsGymHandle* h, const int32_t* ranks8, int32_t
         return DBSGYM_OK;
     }
     if (!vecs || !vals) return fail(h, DBSGYM_EINVAL, "null argument");
+    if (h->lr_rank > 0) return fail(h, DBSGYM_ESTATE, "the handle already runs the low-rank form of its operator");
     const bool grid_ok = h->cfg.coupling == DBSGYM_COUPLING_GRID && !h->f64 && h->grid_sym && h->cluster <= 1 &&
                          h->cfg.grid[0] == 8 && h->cfg.grid[1] == 8;
     if (grid_ok && h->cfg.grid[2] == 4 && h->nthreads == 32) return set_coupling_spectral_half(h, ranks8, r_max, vecs, vals);

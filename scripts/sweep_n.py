@@ -26,6 +26,8 @@ out = []
 # z-planes of the 16 x 16 x 16 grid (lines of 16, two threads per line)
 GRIDS = ([(8, 8, gz) for gz in (4, 8, 16, 32, 64, 128, 256, 512, 1024)] + [(16, 16, gz) for gz in (4, 8, 16)] +
          [(32, 32, gz) for gz in (8, 16, 32, 64)])       # 32^3 (and 32 x 32 x 64 for N = 65536): lines of 32, cluster mode
+if os.environ.get("SWEEP_CONFIG5"):                      # the grids SURVEY.md 8d names for BASELINE configs[4]: first-N rows of 8^3, 16^3, 32^3
+    GRIDS = [(8, 8, 4), (8, 8, 8)] + [(16, 16, gz) for gz in (4, 8, 16)] + [(32, 32, gz) for gz in (8, 16, 32, 64)]
 if os.environ.get("SWEEP_ONLY_CUBIC"):
     GRIDS = [g for g in GRIDS if g[1] != 8]
 if os.environ.get("SWEEP_MAX_N"):
@@ -45,7 +47,8 @@ for gx, gy, gz in GRIDS:
             opts = {"force_cluster": N // per}
     eng = KuramotoEngine(B, N, [gx, gy, gz], 2340, 0.52, precision="f32", coupling_table=table, device=LOCAL, options=opts)
     lowrank = None
-    if os.environ.get("SWEEP_LOWRANK"):                   # the operator in its truncated eigenbasis (step-kernel variant 11)
+    warp_grid = bool(os.environ.get("SWEEP_SPECTRAL")) and (gx, gy) == (8, 8) and gz in (4, 8)
+    if os.environ.get("SWEEP_LOWRANK") and not warp_grid:  # the operator in its truncated eigenbasis (step-kernel variants 11 / 13)
         from dbsgym_b200.geometry import grid_lowrank_factors, grid_sector_factors
         t_f = time.perf_counter()
         tol = float(os.environ.get("SWEEP_LOWRANK_TOL", "1e-9"))
@@ -63,7 +66,7 @@ for gx, gy, gz in GRIDS:
             eng.set_coupling_lowrank(*f)
             lowrank = {"rank": int(f[0].shape[0]), "form": "plain", "residual_over_lambda_max": float(f[2] / abs(f[1][0])),
                        "factorisation_s": time.perf_counter() - t_f}
-    if os.environ.get("SWEEP_SPECTRAL") and (gx, gy) == (8, 8) and gz in (4, 8):     # the warp kernels (variants 12 / 10), as BatchedKuramoto selects them
+    if warp_grid:                                          # the warp kernels (variants 12 / 10), as BatchedKuramoto selects them
         from dbsgym_b200.geometry import spectral_factors
         vecs, vals, ranks, residual = spectral_factors(table, gx, gy, gz, tol=float(os.environ.get("SWEEP_LOWRANK_TOL", "1e-9")))
         eng.set_coupling_spectral(vecs, vals, ranks, residual)
