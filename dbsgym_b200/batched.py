@@ -39,7 +39,7 @@ def _pinned(shape, dtype):
 class BatchedKuramoto:
     def __init__(self, params_dicts, *, precision="f32", device=0, compat_env2=False, force_dense=False,
                  save_init=False, transfer="delta", engine_options=None, coupling_eval="auto", spectral_tol=1e-9,
-                 batch_resets=True):
+                 batch_resets=True, prepare_resets_ahead=None):
         """``coupling_eval``: how the float32 kernels evaluate the coupling sum of env.py:252-256 on the 8 x 8 x 8 grid --
         ``"exact"``: the parity-sector block contraction (the same sum as the reference, reassociated); ``"spectral"``:
         the generalised mean-field identity over the eigenmodes of alpha above ``spectral_tol * |lambda_max|``
@@ -47,7 +47,10 @@ class BatchedKuramoto:
         truncation error 2.2e-7 in the spectral norm of alpha, i.e. ~1e-11 rad per time unit in d theta / dt, four orders
         below float32 rounding of the exact sum; 1e-10 gives 34 modes);
         ``"auto"`` = spectral where it applies (float32, regular 8 x 8 x 8 grid, ranks within the compiled range), else
-        exact.  float64 (parity mode) always evaluates the exact sum."""
+        exact.  float64 (parity mode) always evaluates the exact sum.
+        ``prepare_resets_ahead``: let the batched host reset (host_batch.HostBatch) prepare the next reset of all environments on
+        a worker thread while the GPU steps (same numbers and same final np.random state as the synchronous path; None = for
+        batches of 256 environments and more)."""
         if isinstance(params_dicts, dict):
             params_dicts = [params_dicts]
         self.params_dicts = list(params_dicts)
@@ -172,7 +175,7 @@ class BatchedKuramoto:
         if (p0["temporal_drift"] or p0["spatial_feature"]) and batch_resets:
             from .host_batch import HostBatch, HostList
             if HostBatch.supported(self.hosts):
-                self.host_batch = HostBatch(self.hosts)
+                self.host_batch = HostBatch(self.hosts, speculate=prepare_resets_ahead)
                 self.hosts = HostList(self.hosts, self.host_batch)
 
     # -------------------------------------------------------------------------------------
