@@ -400,3 +400,39 @@ def test_grid_permutation_recognises_a_shuffled_regular_grid():
     holes = grid[perm].copy(); holes[0] = holes[1]
     assert geometry.grid_permutation(holes, [8, 8, 8]) is None                   # not a permutation
     assert geometry.grid_permutation(grid[perm] * 0.1, [8, 8, 8]) is None        # coordinates, not grid indices
+
+
+def test_compiled_rank_lists_cover_the_shipped_operator():
+    """The register-resident spectral kernels are compiled for fixed lists of modes per parity sector
+    (csrc/step_f32_warp.cu, step_f32_warp1.cu, step_f32_oct.cu).  The lists must cover what geometry.spectral_factors finds for
+    the shipped cos(distance) kernel at the default truncation (1e-9) on every grid they are meant for -- otherwise the library
+    silently keeps a slower kernel -- and batched.HALF_GRID_RANK_SETS must restate the half-grid lists."""
+    import os
+    import re
+    from dbsgym_b200 import batched, geometry
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "dbsgym_b200", "csrc")
+
+    def lists(fname, pattern):
+        text = open(os.path.join(csrc, fname)).read()
+        return [tuple(int(v) for v in m.split(",")) for m in re.findall(pattern, text)]
+
+    def ranks(gx, gy, gz):
+        coords, grid = geometry.neuron_grid(gx, gy, gz, gx * gy * gz, 0.1)
+        table = geometry.coupling_table(coords, grid, [gx, gy, gz], "cos")
+        return geometry.spectral_factors(table, gx, gy, gz, tol=1e-9)[2]
+
+    def covered(r, sets):
+        return any(all(a <= b for a, b in zip(r, s)) for s in sets)
+
+    full = lists("step_f32_warp.cu", r"RankSet<([0-9, ]+)>")
+    half = lists("step_f32_warp1.cu", r"RankSet<([0-9, ]+)>")
+    assert covered(ranks(8, 8, 8), full) and covered(ranks(8, 8, 4), half)
+    assert sorted(set(half)) == sorted(batched.HALF_GRID_RANK_SETS)
+    octs = re.findall(r"\{(\d+), \{([0-9, ]+)\}\}", open(os.path.join(csrc, "step_f32_oct.cu")).read())
+    octs = [(int(n), tuple(int(v) for v in r.split(","))) for n, r in octs]
+    assert len(octs) == 6 and all(sum(r) % 2 == 0 for _, r in octs)            # (the expansion takes the modes in pairs)
+    launched = lists("step_f32_oct.cu", r"launch_o<RankSet<([0-9, ]+)>")
+    assert launched == [r for _, r in octs]                                    # table and dispatch switch in the same order
+    for g in ((16, 16, 4), (16, 16, 8), (16, 16, 16), (8, 8, 16), (8, 8, 32), (8, 8, 64)):
+        n = g[0] * g[1] * g[2]
+        assert covered(ranks(*g), [r for m, r in octs if m == n]), g
