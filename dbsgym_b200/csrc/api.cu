@@ -1013,10 +1013,12 @@ int dbsgym_set_coupling_lowrank_sectors(DbsGymHandle* h, const int32_t* soff9, c
     h->lr_rank = R;
     h->lr_sectors = true;
     h->have_coupling = true;
-    // 1024 ... 4096 oscillators in one CTA: the register-resident kernel of oct_kernel.cuh when a compiled rank list covers
+    // 1024 ... 4096 oscillators in one CTA, 8192 in a cluster of 2: the register-resident kernel of oct_kernel.cuh when a compiled rank list covers
     // the sectors' ranks (modes with a non-zero eigenvalue; the padding of every sector's block is zero)
     h->oct_set = -1;
-    if (h->cluster <= 1 && !h->no_warp && (N == 1024 || N == 2048 || N == 4096) && h->nthreads == P8) {
+    const bool one_cta = h->cluster <= 1 && (N == 1024 || N == 2048 || N == 4096) && h->nthreads == P8;
+    const bool clustered = N == 8192 && h->cluster == 2 && h->nthreads == 512;     // a cluster of 2 CTAs of 4096 oscillators
+    if (!h->no_warp && (one_cta || clustered)) {
         int ranks8[8], compiled[8];
         for (int s8 = 0; s8 < 8; ++s8) {
             ranks8[s8] = 0;

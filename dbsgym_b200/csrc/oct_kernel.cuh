@@ -35,9 +35,9 @@ namespace dbsgym {
 
 constexpr int kOctMP = 13;         // modes per pass of the in-warp reduction: 26 half rows, one round of 32 lanes
 
-template <class RK, int NW> struct OctLayout {
+template <class RK, int NW, int NC = 1> struct OctLayout {
     static constexpr int NM = RK::off(8);                       // modes (even: the expansion takes them in pairs)
-    static constexpr int NT = 32 * NW, N = 8 * NT;
+    static constexpr int NT = 32 * NW, N = 8 * NT;          // threads and oscillators of ONE CTA (the environment has NC of them)
     static constexpr int MP = kOctMP;
     static constexpr int PASSES = (NM + MP - 1) / MP;
     static constexpr int RS = 36;                               // words per half row: 16 float2 partials + 4
@@ -47,9 +47,12 @@ template <class RK, int NW> struct OctLayout {
     static_assert(p_floats >= 8 * 68, "the partials buffer also holds the lane sums of 8 LFP samples");
     // floats: K slots, winding counts, w0 + pulse, per-warp partials, per-warp totals (2 buffers), per-warp coefficients,
     // error-norm partials (2 buffers), sample partials (2 buffers of [NW][8] float2), samples of the step
-    static constexpr size_t floats = (size_t)kSlots * N + N + N + (size_t)NW * p_floats + 2 * (size_t)NW * 2 * NMP + (size_t)NW * 2 * NMP +
-                                     2 * NW + 2 * NW * 16 + 32;
+    static constexpr int CPB = NC > 1 ? 1 : 2;                  // buffers of the warps' totals (a cluster has a second barrier per evaluation)
+    static constexpr size_t floats = (size_t)kSlots * N + N + N + (size_t)NW * p_floats + CPB * (size_t)NW * 2 * NMP + (size_t)NW * 2 * NMP +
+                                     2 * NW + 2 * NW * 16 + 32 +
+                                     (NC > 1 ? 2 * NC * 2 * NMP + 2 * NC + 2 * NC * 16 : 0);   // cluster exchange tables XC, RX, SX
     static constexpr size_t bytes = floats * 4 + (32 + 2 * kWarpTs) * 8 + 36 * 4 + 16;
+    static_assert(bytes <= (size_t)227 * 1024, "one environment (or its part) must fit the shared memory of an SM");
 };
 
 template <int NT> __device__ __forceinline__ void oload8(const float* __restrict__ row, int tid, float (&o)[8]) {
@@ -108,9 +111,26 @@ __device__ __forceinline__ void ostage_argument(int s, const float* __restrict__
     }
 }
 
-template <class RK, int NW>
-__global__ void __launch_bounds__(32 * NW, 16 / NW) oct_step_kernel(const StepParams p) {
-    using L = OctLayout<RK, NW>;
+// stores into the shared memory of CTA `rank` of the cluster, at the address `local_ptr` has in this CTA
+__device__ __forceinline__ void st_cluster(const void* local_ptr, int rank, float2 v) {
+    const uint32_t laddr = (uint32_t)__cvta_generic_to_shared(local_ptr);
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(raddr), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_cluster(const void* local_ptr, int rank, float v) {
+    const uint32_t laddr = (uint32_t)__cvta_generic_to_shared(local_ptr);
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(raddr), "f"(v) : "memory");
+}
+
+// NC > 1 (8192 oscillators: NC = 2): the environment is a thread-block cluster of NC such CTAs.  Every sum over the
+// environment then takes a second level: the CTA's total is PUSHED into the exchange tables of all CTAs of the cluster
+// (st.shared::cluster, double buffered), one cluster barrier, and every CTA adds the NC entries in the same order.
+template <class RK, int NW, int NC>
+__global__ void __launch_bounds__(32 * NW, NC > 1 ? 1 : 16 / NW) oct_step_kernel(const StepParams p) {
+    using L = OctLayout<RK, NW, NC>;
     constexpr int NM = L::NM, MP = L::MP, NT = L::NT, N = L::N, NMP = L::NMP;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -120,11 +140,19 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) oct_step_kernel(const StepPa
     float* C0 = reinterpret_cast<float*>(WD + N);             // [2][NT] float4: w0 + pulse of the segment
     float* Pw = C0 + N + wid * L::p_floats;                   // this warp's projection partials of one pass
     float* CP = C0 + N + NW * L::p_floats;                    // [2][NW][NMP] float2: the warps' mode totals, double buffered
-    float* Cw = CP + 2 * NW * 2 * NMP + wid * 2 * NMP;        // this warp's copy of the mode coefficients
-    float* RD = CP + 2 * NW * 2 * NMP + NW * 2 * NMP;         // [2][NW] error-norm partials
+    float* Cw = CP + L::CPB * NW * 2 * NMP + wid * 2 * NMP;   // this warp's copy of the mode coefficients
+    float* RD = CP + L::CPB * NW * 2 * NMP + NW * 2 * NMP;    // [2][NW] error-norm partials
     float* SL = RD + 2 * NW;                                  // [2][NW][8] float2 sample partials
     float* LF = SL + 2 * NW * 16;                             // [32] recorded LFP samples of the step
-    double* t_delta = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(LF + 32) + 7) & ~uintptr_t(7));
+    float* XC = LF + 32;                                      // cluster: [2][NC][NMP] float2 mode totals of the CTAs
+    float* RX = XC + (NC > 1 ? 2 * NC * 2 * NMP : 0);         // cluster: [2][NC] error-norm totals of the CTAs
+    float* SX = RX + (NC > 1 ? 2 * NC : 0);                   // cluster: [2][NC][8] float2 sample totals of the CTAs (read by CTA 0)
+    float* after = SX + (NC > 1 ? 2 * NC * 16 : 0);
+    double* t_delta = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(after) + 7) & ~uintptr_t(7));
+    int crank = 0;
+    if constexpr (NC > 1) asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    const int pt = crank * NT + tid;                          // octant point of this thread
+    auto sync_env = [&]() { if constexpr (NC > 1) cluster_barrier(); else __syncthreads(); };
     double* TS = t_delta + 32;                                // [2][kWarpTs] save times of the two segments of a step
     int* t_pos = reinterpret_cast<int*>(TS + 2 * kWarpTs);
 
@@ -132,7 +160,7 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) oct_step_kernel(const StepPa
     // pass (already multiplied by K / (8 N))
     float V[NM], lam_r[L::PASSES];
 #pragma unroll
-    for (int m = 0; m < NM; ++m) V[m] = __ldg(p.spec_v + (size_t)m * NT + tid);
+    for (int m = 0; m < NM; ++m) V[m] = __ldg(p.spec_v + (size_t)m * (NC * NT) + pt);
 #pragma unroll
     for (int q = 0; q < L::PASSES; ++q) {
         const int m = q * MP + (lane >> 1);
@@ -143,12 +171,13 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) oct_step_kernel(const StepPa
     const float two_pi_r = (float)kTwoPi;
     const float safety_f = (float)p.safety;
     const float inv_n = 1.0f / (float)p.N;
-    int par = 0, rpar = 0, spar = 0;                          // buffer parities (uniform over the CTA)
+    int par = 0, rpar = 0, spar = 0;                          // buffer parities (uniform over the environment)
 
 #pragma unroll 1
-    for (int slot = (int)blockIdx.x; slot < p.n_launch; slot += (int)gridDim.x) {
+    for (int slot = (int)blockIdx.x / NC; slot < p.n_launch; slot += (int)gridDim.x / NC) {
     const int env = p.env_ids ? p.env_ids[slot] : slot;
-    const size_t base = (size_t)env * p.Np + (size_t)tid * 8;
+    const size_t base = (size_t)env * p.Np + (size_t)pt * 8;
+    const size_t krow = (size_t)env * p.Np + (size_t)crank * N;       // this CTA's part of the carried-derivative row (private layout)
     const bool step_mode = p.mode == MODE_STEP;
     const int k_idx = step_mode ? p.step_idx[env] : 0;
     const float act = step_mode ? p.actions[env] : 0.f;
@@ -167,7 +196,7 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) oct_step_kernel(const StepPa
     float amp_k0 = 0.f;
     if (fsal_in) {
         float k[8];
-        oload8<NT>(reinterpret_cast<const float*>(p.k_fsal) + (size_t)env * p.Np, tid, k);      // (kept in this kernel's private layout)
+        oload8<NT>(reinterpret_cast<const float*>(p.k_fsal) + krow, tid, k);
         ostore8<NT>(K, tid, k);
         k0_valid = true;
     }
@@ -186,7 +215,7 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) oct_step_kernel(const StepPa
         const double a = (double)act;                                       // env.py:389-393 rescale_action, env.py:419
         const double u = p.act_lo + ((p.act_hi - p.act_lo) * (a - (-1.0))) / (1.0 - (-1.0));
         u_step = u;
-        if (tid == 0) { p.u_out[env] = u; p.n_samples[env] = nI + nII - 1; }
+        if (pt == 0) { p.u_out[env] = u; p.n_samples[env] = nI + nII - 1; }
         nseg = 2;
         seg_ts[0] = p.sched_offI + (size_t)k * p.maxI;   seg_nts[0] = nI;  seg_nrec[0] = nI;
         seg_ts[1] = p.sched_offII + (size_t)k * p.maxII; seg_nts[1] = nII; seg_nrec[1] = nII - 1;
@@ -206,8 +235,8 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) oct_step_kernel(const StepPa
         seg_ts[1] = nullptr; seg_nts[1] = seg_nrec[1] = seg_from[1] = seg_out[1] = 0; seg_amp[1] = 0.f;
     }
     const bool tail = p.tail_on && step_mode;
-    if (tail && wid == 0) obs_tail_prefetch<float>(p, env, lane, seg_nrec[0] + seg_nrec[1], t_delta, t_pos);
-    __syncthreads();
+    if (tail && wid == 0 && crank == 0) obs_tail_prefetch<float>(p, env, lane, seg_nrec[0] + seg_nrec[1], t_delta, t_pos);
+    sync_env();
 
 #pragma unroll 1
     for (int sg = 0; sg < nseg; ++sg) {
@@ -267,7 +296,7 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) oct_step_kernel(const StepPa
                 wht8p(X);
                 // ---- mode sums inside the warp, PASSES passes of MP modes: the lane's partial of every mode, P[mode][lane], then
                 //      one lane per half row adds 16 of them and the two halves of a mode meet by one shuffle ----
-                float2* cp_mine = reinterpret_cast<float2*>(CP) + (par * NW + wid) * NMP;
+                float2* cp_mine = reinterpret_cast<float2*>(CP) + ((NC > 1 ? 0 : par) * NW + wid) * NMP;
                 static_for<L::PASSES>([&](auto qq) {
                     constexpr int q = decltype(qq)::value;
                     float* prow = Pw + (lane >> 4) * L::RS + 2 * (lane & 15);
@@ -300,8 +329,8 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) oct_step_kernel(const StepPa
                 });
                 __syncthreads();
                 // ---- across the warps: lane = mode, the NW rows in a fixed order ----
-                {
-                    const float2* cp = reinterpret_cast<const float2*>(CP) + par * NW * NMP;
+                if (NC == 1 || wid == 0) {
+                    const float2* cp = reinterpret_cast<const float2*>(CP) + (NC > 1 ? 0 : par) * NW * NMP;
 #pragma unroll
                     for (int mb = 0; mb < NM; mb += 32) {
                         const int m = mb + lane;
@@ -309,12 +338,31 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) oct_step_kernel(const StepPa
                             float2 acc = cp[m];
 #pragma unroll
                             for (int w = 1; w < NW; ++w) acc = __fadd2_rn(acc, cp[w * NMP + m]);
+                            if constexpr (NC == 1) reinterpret_cast<float2*>(Cw)[m] = acc;
+                            else {
+                                float2* mine = reinterpret_cast<float2*>(XC) + (par * NC + crank) * NMP + m;
+#pragma unroll
+                                for (int c = 0; c < NC; ++c) st_cluster(mine, c, acc);
+                            }
+                        }
+                    }
+                }
+                if constexpr (NC > 1) {               // ---- across the CTAs of the cluster ----
+                    cluster_barrier();
+                    const float2* xc = reinterpret_cast<const float2*>(XC) + par * NC * NMP;
+#pragma unroll
+                    for (int mb = 0; mb < NM; mb += 32) {
+                        const int m = mb + lane;
+                        if (m < NM) {
+                            float2 acc = xc[m];
+#pragma unroll
+                            for (int c = 1; c < NC; ++c) acc = __fadd2_rn(acc, xc[c * NMP + m]);
                             reinterpret_cast<float2*>(Cw)[m] = acc;
                         }
                     }
-                    par ^= 1;
-                    __syncwarp();
                 }
+                par ^= 1;
+                __syncwarp();
                 // ---- expansion back to the thread's sector coordinates, then sectors -> images ----
                 static_for<8>([&](auto ss) {
                     constexpr int sec = decltype(ss)::value;
@@ -388,6 +436,13 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) oct_step_kernel(const StepPa
             sqr = RD[rpar * NW];
 #pragma unroll
             for (int w = 1; w < NW; ++w) sqr += RD[rpar * NW + w];
+            if constexpr (NC > 1) {
+                if (tid < NC) st_cluster(RX + rpar * NC + crank, tid, sqr);
+                cluster_barrier();
+                sqr = RX[rpar * NC];
+#pragma unroll
+                for (int c = 1; c < NC; ++c) sqr += RX[rpar * NC + c];
+            }
             rpar ^= 1;
             const float errf = sqrtf(sqr * inv_n);
             if (!(errf == errf)) { status |= STATUS_NAN; break; }
@@ -496,13 +551,25 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) oct_step_kernel(const StepPa
                             if (lane < 8) reinterpret_cast<float2*>(SL)[(spar * NW + wid) * 8 + lane] = make_float2(a, b);
                         }
                         __syncthreads();
-                        if (wid == 0) {
+                        if constexpr (NC > 1) {            // the CTAs' totals meet in CTA 0
+                            if (wid == 0 && lane < 8) {
+                                const float2* sl2 = reinterpret_cast<const float2*>(SL) + spar * NW * 8 + lane;
+                                float2 acc = sl2[0];
+#pragma unroll
+                                for (int w = 1; w < NW; ++w) { acc.x += sl2[w * 8].x; acc.y += sl2[w * 8].y; }
+                                st_cluster(reinterpret_cast<float2*>(SX) + (spar * NC + crank) * 8 + lane, 0, acc);
+                            }
+                            cluster_barrier();
+                        }
+                        if (wid == 0 && crank == 0) {
                             const int idx = first_idx + lane;
                             if (lane < nb && idx >= rec_from && idx < n_rec) {
-                                const float2* sl2 = reinterpret_cast<const float2*>(SL) + spar * NW * 8 + lane;
+                                const float2* sl2 = NC > 1 ? reinterpret_cast<const float2*>(SX) + spar * NC * 8 + lane
+                                                           : reinterpret_cast<const float2*>(SL) + spar * NW * 8 + lane;
+                                constexpr int NR = NC > 1 ? NC : NW;
                                 float a = sl2[0].x, b = sl2[0].y;
 #pragma unroll
-                                for (int w = 1; w < NW; ++w) { a += sl2[w * 8].x; b += sl2[w * 8].y; }
+                                for (int w = 1; w < NR; ++w) { a += sl2[w * 8].x; b += sl2[w * 8].y; }
                                 const double a_t = (double)(a * inv_n);
                                 const double a_r = p.weighted_rec ? (double)(b * inv_n) : a_t;
                                 if (step_mode) {
@@ -564,7 +631,7 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) oct_step_kernel(const StepPa
         reinterpret_cast<int4*>(p.wind + base)[0] = make_int4(wd[0], wd[1], wd[2], wd[3]);
         reinterpret_cast<int4*>(p.wind + base)[1] = make_int4(wd[4], wd[5], wd[6], wd[7]);
     }
-    if (tail && wid == 0) {
+    if (tail && wid == 0 && crank == 0) {
         __syncwarp();                                                // the step's samples (LF) were stored by lanes of this warp
         wobs_tail(p, env, lane, seg_nrec[0] + seg_nrec[1], t_delta, t_pos, LF, u_step);
     }
@@ -573,11 +640,11 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) oct_step_kernel(const StepPa
         if (keep_row) {
             float k[8];
             oload8<NT>(K, tid, k);
-            ostore8<NT>(reinterpret_cast<float*>(p.k_fsal) + (size_t)env * p.Np, tid, k);
+            ostore8<NT>(reinterpret_cast<float*>(p.k_fsal) + krow, tid, k);
         }
-        if (tid == 0) p.fsal_valid[env] = keep_row ? 1 : 0;
+        if (pt == 0) p.fsal_valid[env] = keep_row ? 1 : 0;
     }
-    if (tid == 0) {
+    if (pt == 0) {
         if (p.mode == MODE_TRANSIENT) p.head[env] = 0;
         atomicAdd(p.counters + 0, (unsigned long long)n_acc);
         atomicAdd(p.counters + 1, (unsigned long long)n_rej);
@@ -585,7 +652,7 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) oct_step_kernel(const StepPa
         atomicAdd(p.counters + 3, (unsigned long long)n_reuse);
         if (status) atomicOr(p.status, status);
     }
-    __syncthreads();                                                 // the shared tables (save times, samples) belong to the next environment now
+    sync_env();                                                      // the shared tables (save times, samples) belong to the next environment now
     }
 }
 

@@ -15,19 +15,37 @@ static const OctSet kOctSets[] = {
     {2048, {9, 7, 8, 5, 7, 5, 5, 4}},      // 8 x 8 x 32
     {4096, {9, 9, 9, 4, 9, 4, 4, 4}},      // 16 x 16 x 16
     {4096, {11, 8, 11, 7, 8, 5, 7, 5}},    // 8 x 8 x 64
+    {8192, {14, 10, 10, 8, 10, 9, 8, 5}},  // 32 x 32 x 8: a cluster of 2 CTAs per environment (1.49 -> 1.03 ms per 256-env step).
+                                           // (32 x 32 x 16 as a cluster of 4 with its 86 modes was measured SLOWER than the block kernel --
+                                           //  1.76 vs 1.61 ms, 320 bytes of spills per thread -- and is not compiled)
 };
 constexpr int kNumOctSets = sizeof(kOctSets) / sizeof(kOctSets[0]);
 
-template <class RK, int NW>
+template <class RK, int NW, int NC = 1>
 static cudaError_t launch_o(int num_sms, const StepParams& p, cudaStream_t s) {
-    using L = OctLayout<RK, NW>;
-    auto kern = oct_step_kernel<RK, NW>;
+    using L = OctLayout<RK, NW, NC>;
+    auto kern = oct_step_kernel<RK, NW, NC>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::bytes);
     if (e != cudaSuccess) return e;
-    int ctas = num_sms * (16 / NW);
-    if (ctas > p.n_launch) ctas = p.n_launch;
-    kern<<<ctas, 32 * NW, L::bytes, s>>>(p);
-    return cudaGetLastError();
+    if constexpr (NC == 1) {
+        int ctas = num_sms * (16 / NW);
+        if (ctas > p.n_launch) ctas = p.n_launch;
+        kern<<<ctas, 32 * NW, L::bytes, s>>>(p);
+        return cudaGetLastError();
+    } else {                                               // one cluster of NC CTAs (one CTA per SM) per environment in flight
+        int clusters = num_sms / NC;
+        if (clusters > p.n_launch) clusters = p.n_launch;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(clusters * NC));
+        cfg.blockDim = dim3(32 * NW);
+        cfg.dynamicSmemBytes = L::bytes;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = NC; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, kern, p);
+    }
 }
 
 // index of the compiled rank list for this oscillator count that covers the requested ranks with the fewest modes (-1: none)
@@ -52,6 +70,7 @@ cudaError_t launch_f32_oct(int rank_set, int num_sms, const StepParams& p, cudaS
         case 3: return launch_o<RankSet<9, 7, 8, 5, 7, 5, 5, 4>, 8>(num_sms, p, s);
         case 4: return launch_o<RankSet<9, 9, 9, 4, 9, 4, 4, 4>, 16>(num_sms, p, s);
         case 5: return launch_o<RankSet<11, 8, 11, 7, 8, 5, 7, 5>, 16>(num_sms, p, s);
+        case 6: return launch_o<RankSet<14, 10, 10, 8, 10, 9, 8, 5>, 16, 2>(num_sms, p, s);
     }
     return cudaErrorInvalidConfiguration;
 }

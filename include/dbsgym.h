@@ -111,7 +111,7 @@ int  dbsgym_create(const DbsGymConfig* cfg, DbsGymHandle** out);
  * 10 spectral contraction, one warp per environment with octant ownership (the default when the sector ranks fit a
  * compiled rank list), 11 DENSE operator in low-rank form (dbsgym_set_coupling_lowrank), 12 spectral contraction on the
  * 8 x 8 x 4 half grid (N = 256), one warp per environment with one octant point per lane, 13 sector form of the low-rank
- * operator with the eigenvectors in registers (1024 / 2048 / 4096 oscillators, one CTA per environment; chosen by
+ * operator with the eigenvectors in registers (1024 / 2048 / 4096 oscillators: one CTA per environment, 8192: a cluster of two; chosen by
  * dbsgym_set_coupling_lowrank_sectors when a compiled rank list covers the sectors' ranks); negative = error code */
 int  dbsgym_step_variant(const DbsGymHandle* h, int32_t n_envs);
 void dbsgym_destroy(DbsGymHandle* h);

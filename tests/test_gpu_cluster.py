@@ -111,7 +111,7 @@ def test_n8192_cluster_step_matches_oracle(gx, gy, gz):
     eng.close()
 
 
-@pytest.mark.parametrize("N,gz,C,gx,gy", [(1024, 16, 2, 8, 8), (4096, 16, 4, 16, 16), (8192, 128, None, 8, 8)])
+@pytest.mark.parametrize("N,gz,C,gx,gy", [(1024, 16, 2, 8, 8), (4096, 16, 4, 16, 16), (8192, 128, None, 8, 8), (8192, 8, None, 32, 32)])
 def test_low_rank_kernel_on_grid_handles_single_cta_and_cluster(N, gz, C, gx, gy):
     """The coupling operator of a regular grid in its truncated eigenbasis (geometry.grid_lowrank_factors: factorised sector
     by sector, never forming the N x N matrix), step-kernel variant 11, against the exact parity-sector kernels on the same
@@ -128,7 +128,8 @@ def test_low_rank_kernel_on_grid_handles_single_cta_and_cluster(N, gz, C, gx, gy
         if lr == "sectors":
             # one CTA per environment and 1024 ... 4096 oscillators: the register-resident kernel (oct_kernel.cuh, variant 13)
             # when a compiled rank list covers the operator; the block kernel (variant 11) with no_warp_kernel, in clusters, above
-            oct = name == "sectors" and N <= 4096
+            # (32 x 32 x 8: the same kernel as a cluster of 2 CTAs; 8 x 8 x 128 has 89 modes, more than any compiled list)
+            oct = name == "sectors" and (N <= 4096 or gx == 32)
             assert eng.step_variant() == (13 if oct else 11) and eng.lowrank["sectors"]
         elif lr:
             f = grid_lowrank_factors(d["table"], gx, gy, gz, tol=1e-9)
@@ -141,15 +142,16 @@ def test_low_rank_kernel_on_grid_handles_single_cta_and_cluster(N, gz, C, gx, gy
             obs, rew, done = eng.step_host(a)
             out.append((eng.state().copy(), obs.copy(), rew.copy(), eng.lfp()[0].copy(), eng.lfp()[1].copy()))
         res[name] = (out, eng.counters())
-        if N <= 4096 and name in ("exact", "sectors", "sectors_block"):       # a reset transient (with rejections) as well
+        if (N <= 4096 or gx == 32) and name in ("exact", "sectors", "sectors_block"):       # a reset transient (with rejections) as well
             eng.transient(np.arange(0.0, 125.0, 0.05))
             res[name + "_transient"] = (eng.state().copy(), eng.obs_host().copy(), eng.counters())
         eng.close()
-    if N <= 4096:
+    if N <= 4096 or gx == 32:
         y_ref, o_ref, c_ref = res["exact_transient"]
         for name in ("sectors", "sectors_block"):
             y, o, c = res[name + "_transient"]
-            assert c["status"] == 0 and abs(c["accepted"] - c_ref["accepted"]) <= 6 and c["rejected"] > 0
+            assert c["status"] == 0 and abs(c["accepted"] - c_ref["accepted"]) <= 6
+            assert c["rejected"] > 0 or gx == 32         # (the flat 32 x 32 x 8 slab integrates its transient without a rejection)
             # (free-running 125 units: float32 rounding differences are amplified by the dynamics, cf. the lines-of-16 test)
             assert np.max(np.abs(y - y_ref)) < 0.25 and np.max(np.abs(o - o_ref)) < 5e-3
     ref, cref = res["exact"]

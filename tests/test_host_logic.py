@@ -430,9 +430,9 @@ def test_compiled_rank_lists_cover_the_shipped_operator():
     assert sorted(set(half)) == sorted(batched.HALF_GRID_RANK_SETS)
     octs = re.findall(r"\{(\d+), \{([0-9, ]+)\}\}", open(os.path.join(csrc, "step_f32_oct.cu")).read())
     octs = [(int(n), tuple(int(v) for v in r.split(","))) for n, r in octs]
-    assert len(octs) == 6 and all(sum(r) % 2 == 0 for _, r in octs)            # (the expansion takes the modes in pairs)
+    assert len(octs) == 7 and all(sum(r) % 2 == 0 for _, r in octs)            # (the expansion takes the modes in pairs)
     launched = lists("step_f32_oct.cu", r"launch_o<RankSet<([0-9, ]+)>")
     assert launched == [r for _, r in octs]                                    # table and dispatch switch in the same order
-    for g in ((16, 16, 4), (16, 16, 8), (16, 16, 16), (8, 8, 16), (8, 8, 32), (8, 8, 64)):
+    for g in ((16, 16, 4), (16, 16, 8), (16, 16, 16), (8, 8, 16), (8, 8, 32), (8, 8, 64), (32, 32, 8)):
         n = g[0] * g[1] * g[2]
         assert covered(ranks(*g), [r for m, r in octs if m == n]), g
