@@ -1,5 +1,5 @@
 // Spectral step kernel for regular grids of 1024 ... 4096 oscillators: ONE CTA PER ENVIRONMENT, one octant point per thread,
-// eigenvectors in registers (sm_100a, float32).
+// eigenvectors in registers (sm_100a, float32); 8192 oscillators as a thread-block cluster of two such CTAs (NC = 2, see below).
 //
 // The algorithm of warp_kernel.cuh / warp1_kernel.cuh (adaptive Dopri5 + I-controller + dense output as the reference calls
 // diffrax, environment/env.py:247-271; coupling sum of env.py:252-256 through the generalised mean-field identity over the
